@@ -1,0 +1,58 @@
+// tests/hostcheck/hostcheck.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host (g++) build of the device-side geometry headers so that their bit-exactness against
+// oracle/_ref can be checked on the GPU-less dev box over millions of cases.  The product
+// never loads this library: the shipped path is the CUDA build of the same headers.
+#include "../../stardist_b200/csrc/clip2d.cuh"
+#include <vector>
+using namespace sdclip;
+
+extern "C" {
+
+void hc_clip_area_batch(const int32_t* a_xy, const int32_t* b_xy, int n_pairs, int n,
+                        float* out_area, int* out_status) {
+#pragma omp parallel
+  {
+    ClipSweep<128>* S = new ClipSweep<128>();
+    std::vector<int32_t> ax(n), ay(n), bx(n), by(n);
+#pragma omp for schedule(dynamic, 64)
+    for (int p = 0; p < n_pairs; p++) {
+      for (int i = 0; i < n; i++) {
+        ax[i] = a_xy[2 * ((long)p * n + i)]; ay[i] = a_xy[2 * ((long)p * n + i) + 1];
+        bx[i] = b_xy[2 * ((long)p * n + i)]; by[i] = b_xy[2 * ((long)p * n + i) + 1];
+      }
+      int st;
+      out_area[p] = clip_intersection_area<128, int32_t>(ax.data(), ay.data(), bx.data(), by.data(), n, *S, &st);
+      out_status[p] = st;
+    }
+    delete S;
+  }
+}
+
+// single pair with the result paths written out (BuildResult order) for debugging
+int hc_clip_paths(const int32_t* a_xy, int na, const int32_t* b_xy, int nb,
+                  int32_t* out_xy, int* out_counts, int max_paths, int max_pts, int* status) {
+  ClipSweep<128>* S = new ClipSweep<128>();
+  std::vector<int32_t> ax(na), ay(na), bx(nb), by(nb);
+  for (int i = 0; i < na; i++) { ax[i] = a_xy[2*i]; ay[i] = a_xy[2*i+1]; }
+  for (int i = 0; i < nb; i++) { bx[i] = b_xy[2*i]; by[i] = b_xy[2*i+1]; }
+  S->init();
+  S->add_path(ax.data(), ay.data(), na, ptClip);
+  S->add_path(bx.data(), by.data(), nb, ptSubject);
+  bool ok = S->execute();
+  *status = S->err;
+  int np = 0, tot = 0;
+  if (ok) for (int i = 0; i < S->nR; i++) {
+    if (S->R[i].pts == SDC_NIL) continue;
+    ix p0 = S->P[S->R[i].pts].prev;
+    int cnt = S->point_count(p0);
+    if (cnt < 2) continue;
+    if (np >= max_paths || tot + cnt > max_pts) { delete S; return -1; }
+    out_counts[np++] = cnt;
+    ix p = p0;
+    for (int k = 0; k < cnt; k++) { out_xy[2*tot] = S->P[p].x; out_xy[2*tot+1] = S->P[p].y; tot++; p = S->P[p].prev; }
+  }
+  delete S;
+  return np;
+}
+
+}
