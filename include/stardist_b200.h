@@ -1,0 +1,128 @@
+/* stardist_b200.h -- C ABI of libstardist_b200.so (B200 / sm_100a prediction hot path).
+ *
+ * Two families of entry points:
+ *
+ *  (1) _LIB_*  : HOST pointers, blocking.  These are the drop-in boundary: the first two have
+ *      exactly the signatures of the reference's own C ABI
+ *      (stardist/lib/stardist3d_lib.h:55-82, implemented by stardist3d_lib.c:5-41 on top of
+ *      _COMMON_* in stardist3d_impl.cpp:956,1404); the 2D ones are the analogues of the CPython
+ *      entry point c_non_max_suppression_inds (stardist/lib/stardist2d.cpp:390-615, called from
+ *      stardist/nms.py:220-225) and of polygons_to_label (stardist/geometry/geom2d.py:149-197).
+ *      Inputs are copied to the device, the CUDA kernels run, the result is copied back.
+ *
+ *  (2) sdb_*   : DEVICE pointers + cudaStream_t, stream ordered.  Used by the Python host layer
+ *      (stardist_b200/) to keep the whole predict_instances pipeline resident in HBM.
+ *
+ * All functions returning int return 0 on success, non-zero on error; sdb_last_error() gives the
+ * message.  There is no CPU fallback: without a usable CUDA device every call fails.
+ */
+#ifndef STARDIST_B200_H
+#define STARDIST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+#include <cstdbool>
+extern "C" {
+#else
+#include <stdbool.h>
+#endif
+
+typedef void* sdb_stream_t; /* a cudaStream_t (0 = default stream) */
+
+/* ----------------------------------------------------------------------------- misc */
+const char* sdb_last_error(void);
+int sdb_device_info(int* n_devices, int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernel launches issued by this library since the last reset (bench "gpu_launches") */
+long long sdb_launch_count(int reset);
+
+/* ----------------------------------------------------------------------------- (1) host ABI */
+
+/* reference: stardist3d_lib.h:55-65 (identical signature) */
+void _LIB_non_maximum_suppression_sparse(
+    const float* scores, const float* dist, const float* points,
+    const int n_polys, const int n_rays, const int n_faces,
+    const float* verts, const int* faces,
+    const float threshold, const int use_bbox, const int use_kdtree,
+    const int verbose, bool* result);
+
+/* reference: stardist3d_lib.h:67-82 (identical signature) */
+void _LIB_polyhedron_to_label(
+    const float* dist, const float* points, const float* verts, const int* faces,
+    const int n_polys, const int n_rays, const int n_faces, const int* labels,
+    const int nz, const int ny, const int nx,
+    const int render_mode, const int verbose,
+    const int use_overlap_label, const int overlap_label,
+    int* result);
+
+/* 2D analogue of c_non_max_suppression_inds (stardist2d.cpp:390): dist[n_polys*n_rays],
+ * points[n_polys*2] (y,x), sorted by descending score; result[n_polys] = kept. Returns status. */
+int _LIB_non_maximum_suppression_2d(
+    const float* dist, const float* points, const int n_polys, const int n_rays,
+    const float threshold, const int use_bbox, const int use_kdtree, const int verbose,
+    bool* result);
+
+/* 2D analogue of polygons_to_label_coord (geom2d.py:149-166): coord[n_polys*2*n_rays] as
+ * (n_polys, 2, n_rays) float32 with row 0 = y(r), row 1 = x(c); polygons are painted in the
+ * given order (later overwrite earlier) with value labels[i]+1. result is int32[ny*nx]. */
+int _LIB_polygons_to_label_2d(
+    const float* coord, const int* labels, const int n_polys, const int n_rays,
+    const int ny, const int nx, int* result);
+
+/* ----------------------------------------------------------------------------- (2) device ABI */
+
+/* 2D NMS, all pointers are device pointers; d_keep is uint8[n_polys]. */
+int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys, int n_rays,
+              float threshold, int use_bbox, int use_kdtree, int verbose,
+              unsigned char* d_keep, sdb_stream_t stream);
+
+/* paint polygons (geom2d.py:149-197): d_rank[i] = paint rank of polygon i (0 = painted first;
+ * a pixel takes the covering polygon of highest rank), d_id_by_rank[r] = value written for
+ * rank r (reference: original index + 1); d_out int32[ny*nx] is zeroed first. */
+int sdb_polygons_to_label_2d(const float* d_coord, const int* d_rank, const int* d_id_by_rank,
+                             int n_polys, int n_rays, int ny, int nx, int* d_out,
+                             sdb_stream_t stream);
+
+/* dist_to_coord (geom2d.py:130-146): coord[n,2,R] = f32(dist * sincos(phi_k) in f64) * scale + points.
+ * d_sincos = float64[2*R] = [sin(phi_k) | cos(phi_k)] evaluated by the caller with numpy (same
+ * libm/SIMD routine as the reference); d_points int32[n,2] (y,x); scaled != 0 applies the
+ * predict_instances(scale=...) rescale to points as well (model2d.py:539-546). */
+int sdb_dist_to_coord_2d(const float* d_dist, const int* d_points, int n_polys, int n_rays,
+                         const double* d_sincos, double scale_y, double scale_x, int scaled,
+                         float* d_coord, sdb_stream_t stream);
+
+/* threshold + border mask + compaction + sort (nms.py:6-17, base.py:606-610, nms.py:167):
+ * prob is [H*W] (2D) / [D*H*W] (3D) float32; candidates are pixels with prob > thresh that lie at
+ * least b_lo/b_hi pixels inside along each axis and inside valid_* (un-padded) extents.
+ * Output sorted by (prob desc, flat index desc) == np.argsort(prob, kind='stable')[::-1].
+ * d_count receives the number of candidates (also returned through *h_count after a sync). */
+int sdb_threshold_sort(const float* d_prob, int ndim, const int* shape, const int* valid_shape,
+                       const int* b_lo, const int* b_hi, float prob_thresh,
+                       int* d_sorted_index, float* d_sorted_prob, int capacity, int* h_count,
+                       sdb_stream_t stream);
+
+/* gather: out_dist[r,:] = max(1e-3, dist[idx[r],:]), out_points[r,:] = unravel(idx[r]) * grid */
+int sdb_gather_candidates(const float* d_dist, const int* d_index, int n, int n_rays, int ndim,
+                          const int* shape, const int* grid, float* d_out_dist,
+                          float* d_out_points, sdb_stream_t stream);
+
+/* ---- U-Net forward building blocks (NHWC float32; see stardist_b200/csrc/unet*.cu) ---- */
+
+/* 3x3 'same' convolution + bias + optional ReLU.  The input may be the channel concatenation
+ * [nearest-upsample2x(in_lo), in_skip] (csbdeep unet_block decoder): pass in_lo=NULL,
+ * cin_lo=0 for a plain convolution.  weights are Keras layout (3,3,Cin,Cout), Cin = cin_lo+cin_skip. */
+int sdb_conv3x3_2d(const float* d_in, const float* d_in_lo, int n, int h, int w, int cin_skip,
+                   int cin_lo, const float* d_weight, const float* d_bias, int cout, int relu,
+                   float* d_out, sdb_stream_t stream);
+
+int sdb_maxpool2x2_2d(const float* d_in, int n, int h, int w, int c, float* d_out, sdb_stream_t stream);
+
+/* 1x1 heads: prob = sigmoid(x.Wp+bp) [npix], dist = x.Wd+bd [npix*n_rays] */
+int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_wp, const float* d_bp,
+                 const float* d_wd, const float* d_bd, int n_rays, float* d_prob, float* d_dist,
+                 sdb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARDIST_B200_H */

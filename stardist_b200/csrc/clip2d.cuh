@@ -28,8 +28,16 @@
 
 #if defined(__CUDACC__)
 #define SD_HD __host__ __device__
+#define SD_HD_BIG __host__ __device__ __noinline__   // large routines: keep one copy per kernel
 #else
 #define SD_HD
+#define SD_HD_BIG
+#endif
+
+#ifdef SDC_STATS
+#define SDC_HW(k, v) do { if ((v) > hw[k]) hw[k] = (v); } while (0)
+#else
+#define SDC_HW(k, v) do {} while (0)
 #endif
 
 namespace sdclip {
@@ -167,7 +175,7 @@ struct StdSortDesc {
       adjust_heap(first, 0, last - first, v);
     }
   }
-  SD_HD void sort(int n) {
+  SD_HD_BIG void sort(int n) {
     if (n <= 1) return;
     // __introsort_loop, recursion unrolled with an explicit stack of (first,last,depth)
     int stf[40], stl[40], std_[40]; int sp = 0;
@@ -195,17 +203,20 @@ struct StdSortDesc {
 };
 
 // ---------------------------------------------------------------------------------------
-template <int NV>
+// NV = max vertices per polygon; SC scales the pools whose size is data dependent.  The GPU
+// fast path runs SC=1 (high-water marks over 1.5M fuzzed 32-gon pairs: P 84, R 22, J 6, GJ 6,
+// IL 17); a pair that overflows is re-run by the slow path with SC=4 -- still on the device.
+template <int NV, int SC = 4>
 struct ClipSweep {
   enum {
     MAXE  = 2 * NV,
-    MAXOP = 16 * NV,
-    MAXOR = 4 * NV,
-    MAXJ  = 8 * NV,
-    MAXGJ = 4 * NV,
-    MAXLM = 2 * NV,
-    MAXSB = 2 * NV + 4,
-    MAXIL = 16 * NV
+    MAXOP = 4 * NV * SC,
+    MAXOR = NV * SC,
+    MAXJ  = (NV / 2) * SC + 8,
+    MAXGJ = (NV / 2) * SC + 8,
+    MAXLM = NV + 2,            // hard bound: a closed n-gon has at most n/2 local minima
+    MAXSB = 2 * NV + 4,        // hard bound: distinct vertex Ys
+    MAXIL = 2 * NV * SC
   };
   Edge E[MAXE];
   OutPt P[MAXOP];
@@ -218,10 +229,16 @@ struct ClipSweep {
   int nE, nP, nR, nJ, nGJ, nLM, curLM, nSB, nIL;
   ix ael, sel;
   int err;
+#ifdef SDC_STATS
+  int hw[8];   // high-water marks: P,R,J,GJ,LM,SB,IL,E
+#endif
 
   SD_HD void init() {
     nE = nP = nR = nJ = nGJ = nLM = curLM = nSB = nIL = 0;
     ael = sel = SDC_NIL; err = CLIP_OK;
+#ifdef SDC_STATS
+    for (int i = 0; i < 8; ++i) hw[i] = 0;
+#endif
   }
   SD_HD void fail(int e) { if (err < e) err = e; }
 
@@ -246,7 +263,7 @@ struct ClipSweep {
     if (lo < nSB && SB[lo] == y) return;
     if (nSB >= MAXSB) { fail(CLIP_OVERFLOW); return; }
     for (int k = nSB; k > lo; --k) SB[k] = SB[k - 1];
-    SB[lo] = y; nSB++;
+    SB[lo] = y; nSB++; SDC_HW(5, nSB);
   }
   SD_HD bool sb_pop(i64& y) { if (nSB == 0) return false; y = SB[--nSB]; return true; }
 
@@ -313,26 +330,27 @@ struct ClipSweep {
     return result;
   }
 
-  // xs/ys: n vertices (already truncated to integers by the caller, stardist2d.cpp:471)
-  template <typename CoordT>
-  SD_HD bool add_path(const CoordT* xs, const CoordT* ys, int n, int poly) {
+  // v: vertex source with v.x(i), v.y(i) for i in [0,n) (already truncated to integers by the
+  // caller, stardist2d.cpp:471)
+  template <typename VSrc>
+  SD_HD_BIG bool add_path(const VSrc& v, int n, int poly) {
     int hi = n - 1;
-    while (hi > 0 && xs[hi] == xs[0] && ys[hi] == ys[0]) --hi;
-    while (hi > 0 && xs[hi] == xs[hi - 1] && ys[hi] == ys[hi - 1]) --hi;
+    while (hi > 0 && v.x(hi) == v.x(0) && v.y(hi) == v.y(0)) --hi;
+    while (hi > 0 && v.x(hi) == v.x(hi - 1) && v.y(hi) == v.y(hi - 1)) --hi;
     if (hi < 2) return false;
     if (nE + hi + 1 > MAXE) { fail(CLIP_OVERFLOW); return false; }
     const int base = nE;
     for (int i = 0; i <= hi; ++i) {
       Edge& e = E[base + i];
       e.bot.x = e.bot.y = e.top.x = e.top.y = 0; e.dx = 0.0;
-      e.cur.x = (int32_t)xs[i]; e.cur.y = (int32_t)ys[i];
+      e.cur.x = (int32_t)v.x(i); e.cur.y = (int32_t)v.y(i);
       e.poly = 0; e.side = 0; e.wdelta = 0; e.wcnt = 0; e.wcnt2 = 0;
       e.outidx = SDC_UNASSIGNED;
       e.next = (ix)(base + (i == hi ? 0 : i + 1));
       e.prev = (ix)(base + (i == 0 ? hi : i - 1));
       e.nextlml = e.nael = e.pael = e.nsel = e.psel = SDC_NIL;
     }
-    nE += hi + 1;       // slots stay reserved even if the path is rejected below (like m_edges)
+    nE += hi + 1; SDC_HW(7, nE);      // slots stay reserved even if the path is rejected below (like m_edges)
     ix estart = (ix)base, e = estart, eloopstop = estart;
     for (;;) {
       if (pt_eq(E[e].cur, E[E[e].next].cur)) {
@@ -385,14 +403,14 @@ struct ClipSweep {
       E[lm.right].wdelta = (int8_t)(-E[lm.left].wdelta);
       e = process_bound(lm.left, lfwd);
       ix e2 = process_bound(lm.right, !lfwd);
-      nLM++;
+      nLM++; SDC_HW(4, nLM);
       if (!lfwd) e = e2;
     }
     return true;
   }
 
   // ------------------------------------------------------------------ Reset (clipper.cpp:1247-1276)
-  SD_HD void reset() {
+  SD_HD_BIG void reset() {
     curLM = 0;
     if (nLM == 0) return;
     {
@@ -428,7 +446,7 @@ struct ClipSweep {
     if (n != SDC_NIL) E[n].psel = p;
     E[e].nsel = SDC_NIL; E[e].psel = SDC_NIL;
   }
-  SD_HD void swap_positions_in_ael(ix e1, ix e2) {                // clipper.cpp:1395-1439
+  SD_HD_BIG void swap_positions_in_ael(ix e1, ix e2) {                // clipper.cpp:1395-1439
     if (E[e1].nael == E[e1].pael || E[e2].nael == E[e2].pael) return;
     if (E[e1].nael == e2) {
       ix n = E[e2].nael; if (n != SDC_NIL) E[n].pael = e1;
@@ -448,7 +466,7 @@ struct ClipSweep {
     if (E[e1].pael == SDC_NIL) ael = e1;
     else if (E[e2].pael == SDC_NIL) ael = e2;
   }
-  SD_HD void swap_positions_in_sel(ix e1, ix e2) {                // clipper.cpp:2558-2601
+  SD_HD_BIG void swap_positions_in_sel(ix e1, ix e2) {                // clipper.cpp:2558-2601
     if (E[e1].nsel == SDC_NIL && E[e1].psel == SDC_NIL) return;
     if (E[e2].nsel == SDC_NIL && E[e2].psel == SDC_NIL) return;
     if (E[e1].nsel == e2) {
@@ -512,13 +530,15 @@ struct ClipSweep {
   // ------------------------------------------------------------------ output records
   SD_HD ix new_outpt() {
     if (nP >= MAXOP) { fail(CLIP_OVERFLOW); return (ix)(MAXOP - 1); }
-    return (ix)nP++;
+    nP++; SDC_HW(0, nP);
+    return (ix)(nP - 1);
   }
   SD_HD ix create_outrec() {                                      // clipper.cpp:1380-1392
     if (nR >= MAXOR) { fail(CLIP_OVERFLOW); return (ix)(MAXOR - 1); }
     OutRec& r = R[nR];
     r.ishole = 0; r.firstleft = SDC_NIL; r.pts = SDC_NIL; r.bottom = SDC_NIL; r.idx = (int16_t)nR;
-    return (ix)nR++;
+    nR++; SDC_HW(1, nR);
+    return (ix)(nR - 1);
   }
   SD_HD void set_hole_state(ix e, ix orec) {                      // clipper.cpp:2301-2324
     ix e2 = E[e].pael, tmp = SDC_NIL;
@@ -532,7 +552,7 @@ struct ClipSweep {
     if (tmp == SDC_NIL) { R[orec].firstleft = SDC_NIL; R[orec].ishole = 0; }
     else { R[orec].firstleft = (ix)E[tmp].outidx; R[orec].ishole = (int8_t)!R[R[orec].firstleft].ishole; }
   }
-  SD_HD ix add_outpt(ix e, IPt pt) {                              // clipper.cpp:2463-2499
+  SD_HD_BIG ix add_outpt(ix e, IPt pt) {                              // clipper.cpp:2463-2499
     if (E[e].outidx < 0) {
       ix orec = create_outrec();
       ix np = new_outpt();
@@ -562,11 +582,11 @@ struct ClipSweep {
   }
   SD_HD void add_join(ix op1, ix op2, IPt off) {
     if (nJ >= MAXJ) { fail(CLIP_OVERFLOW); return; }
-    J[nJ].op1 = op1; J[nJ].op2 = op2; J[nJ].off = off; nJ++;
+    J[nJ].op1 = op1; J[nJ].op2 = op2; J[nJ].off = off; nJ++; SDC_HW(2, nJ);
   }
   SD_HD void add_ghost_join(ix op, IPt off) {
     if (nGJ >= MAXGJ) { fail(CLIP_OVERFLOW); return; }
-    GJ[nGJ].op1 = op; GJ[nGJ].op2 = SDC_NIL; GJ[nGJ].off = off; nGJ++;
+    GJ[nGJ].op1 = op; GJ[nGJ].op2 = SDC_NIL; GJ[nGJ].off = off; nGJ++; SDC_HW(3, nGJ);
   }
   SD_HD void reverse_poly_pt_links(ix pp) {                       // clipper.cpp:692-703
     if (pp == SDC_NIL) return;
@@ -583,7 +603,7 @@ struct ClipSweep {
     } while (op != start);
     return a * 0.5;
   }
-  SD_HD bool first_is_bottom_pt(ix b1, ix b2) const {             // clipper.cpp:798-819
+  SD_HD_BIG bool first_is_bottom_pt(ix b1, ix b2) const {             // clipper.cpp:798-819
     ix p = P[b1].prev;
     while (pt_eq(opt(p), opt(b1)) && p != b1) p = P[p].prev;
     double dx1p = fabs(get_dx(opt(b1), opt(p)));
@@ -601,7 +621,7 @@ struct ClipSweep {
     if (mx1 == mx2 && mn1 == mn2) return area_op(b1) > 0;
     else return (dx1p >= dx2p && dx1p >= dx2n) || (dx1n >= dx2p && dx1n >= dx2n);
   }
-  SD_HD ix get_bottom_pt(ix pp) const {                           // clipper.cpp:822-857
+  SD_HD_BIG ix get_bottom_pt(ix pp) const {                           // clipper.cpp:822-857
     ix dups = SDC_NIL;
     ix p = P[pp].next;
     while (p != pp) {
@@ -643,7 +663,7 @@ struct ClipSweep {
     while (r != R[r].idx) r = (ix)R[r].idx;
     return r;
   }
-  SD_HD void append_polygon(ix e1, ix e2) {                       // clipper.cpp:2367-2460
+  SD_HD_BIG void append_polygon(ix e1, ix e2) {                       // clipper.cpp:2367-2460
     ix r1 = (ix)E[e1].outidx, r2 = (ix)E[e2].outidx;
     ix holerec;
     if (outrec1_right_of_outrec2(r1, r2)) holerec = r2;
@@ -682,7 +702,7 @@ struct ClipSweep {
     }
     R[r2].idx = R[r1].idx;
   }
-  SD_HD ix add_local_min_poly(ix e1, ix e2, IPt pt) {             // clipper.cpp:1841-1881
+  SD_HD_BIG ix add_local_min_poly(ix e1, ix e2, IPt pt) {             // clipper.cpp:1841-1881
     ix result, e, preve;
     if (is_horz(e2) || (E[e1].dx > E[e2].dx)) {
       result = add_outpt(e1, pt);
@@ -739,7 +759,7 @@ struct ClipSweep {
     if (aw != 1) return false;
     return E[e].wcnt2 != 0;
   }
-  SD_HD void intersect_edges(ix e1, ix e2, IPt pt) {              // clipper.cpp:2106-2298
+  SD_HD_BIG void intersect_edges(ix e1, ix e2, IPt pt) {              // clipper.cpp:2106-2298
     bool c1 = E[e1].outidx >= 0, c2 = E[e2].outidx >= 0;
     if (E[e1].poly == E[e2].poly) {
       if (E[e1].wcnt + E[e2].wdelta == 0) E[e1].wcnt = (int16_t)(-E[e1].wcnt);
@@ -782,7 +802,7 @@ struct ClipSweep {
   }
 
   // ------------------------------------------------------------------ InsertLocalMinimaIntoAEL (clipper.cpp:1978-2077)
-  SD_HD void insert_local_minima_into_ael(i64 boty) {
+  SD_HD_BIG void insert_local_minima_into_ael(i64 boty) {
     while (curLM < nLM && LM[curLM].y == boty) {
       ix lb = LM[curLM].left, rb = LM[curLM].right;
       curLM++;
@@ -850,7 +870,7 @@ struct ClipSweep {
       en = E[en].nsel;
     }
   }
-  SD_HD void process_horizontal(ix horz) {
+  SD_HD_BIG void process_horizontal(ix horz) {
     int dir; i64 hl, hr;
     // GetHorzDirection clipper.cpp:2610-2624
 #define SDC_HDIR() do { if (E[horz].bot.x < E[horz].top.x) { hl = E[horz].bot.x; hr = E[horz].top.x; dir = dLeftToRight; } \
@@ -936,7 +956,7 @@ struct ClipSweep {
   }
 
   // ------------------------------------------------------------------ intersections (clipper.cpp:622-690, 2827-2954)
-  SD_HD void intersect_point(ix a, ix b, IPt& ip) {
+  SD_HD_BIG void intersect_point(ix a, ix b, IPt& ip) {
     const Edge& e1 = E[a]; const Edge& e2 = E[b];
     i64 ipx, ipy;
     double b1, b2;
@@ -976,7 +996,7 @@ struct ClipSweep {
     }
     ip.x = (int32_t)ipx; ip.y = (int32_t)ipy;
   }
-  SD_HD void build_intersect_list(i64 topy) {
+  SD_HD_BIG void build_intersect_list(i64 topy) {
     if (ael == SDC_NIL) return;
     ix e = ael;
     sel = e;
@@ -996,7 +1016,7 @@ struct ClipSweep {
           intersect_point(e, en, pt);
           if (pt.y < topy) { pt.x = (int32_t)top_x(e, topy); pt.y = (int32_t)topy; }
           if (nIL >= MAXIL) { fail(CLIP_OVERFLOW); sel = SDC_NIL; return; }
-          IL[nIL].e1 = e; IL[nIL].e2 = en; IL[nIL].pt = pt; nIL++;
+          IL[nIL].e1 = e; IL[nIL].e2 = en; IL[nIL].pt = pt; nIL++; SDC_HW(6, nIL);
           swap_positions_in_sel(e, en);
           modified = true;
         } else e = en;
@@ -1009,7 +1029,7 @@ struct ClipSweep {
   SD_HD bool edges_adjacent(const INode& n) const {
     return (E[n.e1].nsel == n.e2) || (E[n.e1].psel == n.e2);
   }
-  SD_HD bool fixup_intersection_order() {
+  SD_HD_BIG bool fixup_intersection_order() {
     // CopyAELToSEL clipper.cpp:1929-1939
     ix e = ael; sel = e;
     while (e != SDC_NIL) { E[e].psel = E[e].pael; E[e].nsel = E[e].nael; e = E[e].nael; }
@@ -1057,7 +1077,7 @@ struct ClipSweep {
   }
 
   // ------------------------------------------------------------------ top of scanbeam (clipper.cpp:2957-3113)
-  SD_HD void do_maxima(ix e) {
+  SD_HD_BIG void do_maxima(ix e) {
     ix emax = get_maxima_pair_ex(e);
     if (emax == SDC_NIL) {
       if (E[e].outidx >= 0) add_outpt(e, E[e].top);
@@ -1079,7 +1099,7 @@ struct ClipSweep {
       delete_from_ael(e); delete_from_ael(emax);
     } else fail(CLIP_FAILED);       // "DoMaxima error" -> caught -> succeeded=false
   }
-  SD_HD void process_edges_at_top_of_scanbeam(i64 topy) {
+  SD_HD_BIG void process_edges_at_top_of_scanbeam(i64 topy) {
     ix e = ael;
     int guard = 0;
     while (e != SDC_NIL) {
@@ -1153,7 +1173,7 @@ struct ClipSweep {
 #undef SDC_MIN
     return l < r;
   }
-  SD_HD bool join_horz(ix op1, ix op1b, ix op2, ix op2b, IPt pt, bool discard_left) {
+  SD_HD_BIG bool join_horz(ix op1, ix op1b, ix op2, ix op2b, IPt pt, bool discard_left) {
     int dir1 = (P[op1].x > P[op1b].x) ? dRightToLeft : dLeftToRight;
     int dir2 = (P[op2].x > P[op2b].x) ? dRightToLeft : dLeftToRight;
     if (dir1 == dir2) return false;
@@ -1200,7 +1220,7 @@ struct ClipSweep {
     }
     return true;
   }
-  SD_HD bool join_points(Join& j, ix r1, ix r2) {
+  SD_HD_BIG bool join_points(Join& j, ix r1, ix r2) {
     ix op1 = j.op1, op1b, op2 = j.op2, op2b;
     bool horizontal = (P[j.op1].y == j.off.y);
     if (horizontal && pt_eq(j.off, opt(j.op1)) && pt_eq(j.off, opt(j.op2))) {
@@ -1270,7 +1290,7 @@ struct ClipSweep {
     }
   }
   // clipper.cpp:484-523; 0 outside, +1 inside, -1 on boundary
-  SD_HD int point_in_polygon(IPt pt, ix op) const {
+  SD_HD_BIG int point_in_polygon(IPt pt, ix op) const {
     int result = 0;
     ix start = op;
     for (;;) {
@@ -1310,7 +1330,7 @@ struct ClipSweep {
     } while (op != o1);
     return true;
   }
-  SD_HD void join_common_edges() {
+  SD_HD_BIG void join_common_edges() {
     for (int i = 0; i < nJ; ++i) {
       Join& j = J[i];
       ix r1 = get_outrec(P[j.op1].idx);
@@ -1347,7 +1367,7 @@ struct ClipSweep {
       }
     }
   }
-  SD_HD void fixup_out_polygon(ix orec) {                         // clipper.cpp:3143-3181
+  SD_HD_BIG void fixup_out_polygon(ix orec) {                         // clipper.cpp:3143-3181
     ix lastok = SDC_NIL;
     R[orec].bottom = SDC_NIL;
     ix pp = R[orec].pts;
@@ -1442,12 +1462,26 @@ struct ClipSweep {
 // Full pair test. ax/ay = polygon i (added first, as ptClip), bx/by = polygon j (ptSubject).
 // Returns the intersection area exactly as poly_intersection_area() would (0 when Execute fails
 // or a path is rejected); *status receives a ClipErr.
-template <int NV, typename CoordT>
-SD_HD float clip_intersection_area(const CoordT* ax, const CoordT* ay, const CoordT* bx, const CoordT* by,
-                                   int n, ClipSweep<NV>& S, int* status) {
+// vertex sources
+struct SplitXY {            // separate x[] / y[] arrays
+  const int32_t* xs; const int32_t* ys;
+  SD_HD int32_t x(int i) const { return xs[i]; }
+  SD_HD int32_t y(int i) const { return ys[i]; }
+};
+struct InterleavedXY {      // (x,y) pairs
+  const int32_t* xy;
+  SD_HD int32_t x(int i) const { return xy[2 * i]; }
+  SD_HD int32_t y(int i) const { return xy[2 * i + 1]; }
+};
+
+// Full pair test. a = polygon i (added first, as ptClip), b = polygon j (ptSubject).
+// Returns the intersection area exactly as poly_intersection_area() would (0 when Execute fails
+// or a path is rejected); *status receives a ClipErr.
+template <int NV, int SC, typename VA, typename VB>
+SD_HD float clip_intersection_area(const VA& a, const VB& b, int n, ClipSweep<NV, SC>& S, int* status) {
   S.init();
-  S.add_path(ax, ay, n, ptClip);
-  S.add_path(bx, by, n, ptSubject);
+  S.add_path(a, n, ptClip);
+  S.add_path(b, n, ptSubject);
   float area = 0.f;
   if (!S.err) {
     bool ok = S.execute();

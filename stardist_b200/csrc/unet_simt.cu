@@ -1,0 +1,256 @@
+// unet_simt.cu -- fp32 CUDA-core building blocks of the U-Net forward pass (NHWC / NDHWC).
+//
+// Reference graph: stardist/models/model2d.py:310-349 (+ csbdeep unet_block):
+//   conv3x3('same', bias, ReLU) x2 per level, 2x2 max-pool, nearest 2x up-sampling,
+//   Concatenate([UpSampling(x), skip]) (up-sampled tensor FIRST on the channel axis),
+//   features = conv3x3(->128, ReLU), prob = sigmoid(1x1), dist = 1x1 (linear).
+// Keras kernels are (kh, kw, Cin, Cout) and the op is a cross-correlation with zero padding.
+//
+// These kernels are the exact-fp32 baseline path (used for the Cin=1 stem, small layers and as
+// the in-repo cross-check of the tcgen05 path in unet_tc.cu).  The decoder's upsample+concat is
+// folded into the loader's address math: no up-sampled or concatenated tensor is materialised.
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "../../include/stardist_b200.h"
+
+namespace {
+
+using sdb::cdiv;
+
+// ------------------------------------------------------------------------------------------
+// generic 3x3 conv: CTA tile 16x16 output pixels x COUT_T output channels, K chunk of 8 channels
+template <int COUT_T>
+__global__ void __launch_bounds__(COUT_T * 4)
+k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, int H, int W,
+          int c_skip, int c_lo, const float* __restrict__ wgt, const float* __restrict__ bias,
+          int Cout, int relu, float* __restrict__ out) {
+  constexpr int CK = 8, TH = 16, TW = 16, CG = COUT_T / 4, NT = 16 * CG;
+  __shared__ __align__(16) float sA[CK][TH + 2][20];
+  __shared__ __align__(16) float sB[9][CK][COUT_T];
+  const int Cin = c_skip + c_lo;
+  const int n_ct = Cout / COUT_T;
+  const int img = blockIdx.z / n_ct, n0 = (blockIdx.z % n_ct) * COUT_T;
+  const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
+  const int t = threadIdx.x, cg = t % CG, pg = t / CG;
+  const float* skip_img = in_skip + (size_t)img * H * W * c_skip;
+  const float* lo_img = in_lo ? in_lo + (size_t)img * (H / 2) * (W / 2) * c_lo : nullptr;
+  const int Wlo = W / 2;
+
+  float acc[16][4];
+#pragma unroll
+  for (int p = 0; p < 16; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f; }
+
+  for (int c0 = 0; c0 < Cin; c0 += CK) {
+    // ---- stage the (TH+2)x(TW+2) halo tile of CK channels, transposed to channel-major
+    for (int e = t; e < (TH + 2) * (TW + 2) * (CK / 4); e += NT) {
+      const int q = e % (CK / 4), p = e / (CK / 4);
+      const int ry = p / (TW + 2), rx = p % (TW + 2);
+      const int gy = ty0 + ry - 1, gx = tx0 + rx - 1;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+        const int c = c0 + 4 * q;
+        if (c < c_lo) v = *reinterpret_cast<const float4*>(lo_img + ((size_t)(gy >> 1) * Wlo + (gx >> 1)) * c_lo + c);
+        else v = *reinterpret_cast<const float4*>(skip_img + ((size_t)gy * W + gx) * c_skip + (c - c_lo));
+      }
+      sA[4 * q + 0][ry][rx] = v.x; sA[4 * q + 1][ry][rx] = v.y;
+      sA[4 * q + 2][ry][rx] = v.z; sA[4 * q + 3][ry][rx] = v.w;
+    }
+    // ---- stage weights [9][CK][COUT_T]
+    for (int e = t; e < 9 * CK * (COUT_T / 4); e += NT) {
+      const int co4 = e % (COUT_T / 4), r = e / (COUT_T / 4);
+      const int ci = r % CK, tap = r / CK;
+      const float4 v = *reinterpret_cast<const float4*>(wgt + ((size_t)tap * Cin + c0 + ci) * Cout + n0 + 4 * co4);
+      *reinterpret_cast<float4*>(&sB[tap][ci][4 * co4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CK; ++ci) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        float a[20];
+        const float4* row = reinterpret_cast<const float4*>(&sA[ci][pg + dy][0]);
+#pragma unroll
+        for (int v4 = 0; v4 < 5; ++v4) {
+          const float4 v = row[v4];
+          a[4 * v4] = v.x; a[4 * v4 + 1] = v.y; a[4 * v4 + 2] = v.z; a[4 * v4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4 b = *reinterpret_cast<const float4*>(&sB[dy * 3 + dx][ci][4 * cg]);
+#pragma unroll
+          for (int p = 0; p < 16; ++p) {
+            const float av = a[p + dx];
+            acc[p][0] = fmaf(av, b.x, acc[p][0]); acc[p][1] = fmaf(av, b.y, acc[p][1]);
+            acc[p][2] = fmaf(av, b.z, acc[p][2]); acc[p][3] = fmaf(av, b.w, acc[p][3]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int gy = ty0 + pg;
+  if (gy >= H) return;
+  const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + 4 * cg);
+  float* orow = out + ((size_t)img * H * W + (size_t)gy * W) * Cout + n0 + 4 * cg;
+#pragma unroll
+  for (int p = 0; p < 16; ++p) {
+    const int gx = tx0 + p;
+    if (gx >= W) break;
+    float4 v = make_float4(acc[p][0] + bb.x, acc[p][1] + bb.y, acc[p][2] + bb.z, acc[p][3] + bb.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    *reinterpret_cast<float4*>(orow + (size_t)gx * Cout) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stem: Cin small (1..4), not a multiple of 8: one thread per output pixel, all Cout (<=64) in registers
+template <int COUT>
+__global__ void __launch_bounds__(128)
+k_conv3x3_stem(const float* __restrict__ in, int N, int H, int W, int Cin, const float* __restrict__ wgt,
+               const float* __restrict__ bias, int relu, float* __restrict__ out) {
+  extern __shared__ float sw[];     // [9*Cin][COUT] + bias[COUT]
+  for (int e = threadIdx.x; e < 9 * Cin * COUT; e += blockDim.x) sw[e] = wgt[e];
+  for (int e = threadIdx.x; e < COUT; e += blockDim.x) sw[9 * Cin * COUT + e] = bias[e];
+  __syncthreads();
+  const long long npix = (long long)N * H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int x = (int)(p % W), y = (int)((p / W) % H);
+  const long long img = p / ((long long)W * H);
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = sw[9 * Cin * COUT + o];
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int xx = x + dx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float* ip = in + ((img * H + yy) * W + xx) * Cin;
+      for (int c = 0; c < Cin; ++c) {
+        const float v = ip[c];
+        const float* wr = sw + ((dy * 3 + dx) * Cin + c) * COUT;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
+      }
+    }
+  }
+  float4* op = reinterpret_cast<float4*>(out + p * COUT);
+#pragma unroll
+  for (int o = 0; o < COUT; o += 4) {
+    float4 v = make_float4(acc[o], acc[o + 1], acc[o + 2], acc[o + 3]);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    op[o / 4] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_maxpool2x2(const float* __restrict__ in, int N, int H, int W, int C, float* __restrict__ out) {
+  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
+  const long long total = (long long)N * Ho * Wo * C4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(e % C4); long long r = e / C4;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho); const long long img = r / Ho;
+    const float4* b = reinterpret_cast<const float4*>(in + ((img * H + 2 * yo) * W + 2 * xo) * C) + c4;
+    const float4 v00 = b[0], v01 = b[C4], v10 = b[(size_t)W * C4], v11 = b[(size_t)W * C4 + C4];
+    float4 m;
+    m.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x)); m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
+    m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z)); m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+    reinterpret_cast<float4*>(out)[e] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// heads: per pixel NO = 1 + n_rays outputs from CF features; block = 32 pixels x 4 warps
+template <int CF>
+__global__ void __launch_bounds__(128)
+k_heads(const float* __restrict__ feat, long long npix, const float* __restrict__ wp, const float* __restrict__ bp,
+        const float* __restrict__ wd, const float* __restrict__ bd, int R, float* __restrict__ prob,
+        float* __restrict__ dist) {
+  extern __shared__ float sm[];
+  const int NO = R + 1;
+  float* sW = sm;                       // [CF][NO]  (o = 0 prob, 1.. dist)
+  float* sF = sW + CF * NO;             // [32][CF+1]
+  float* sO = sF + 32 * (CF + 1);       // [32][NO]
+  for (int e = threadIdx.x; e < CF * NO; e += blockDim.x) {
+    const int f = e / NO, o = e % NO;
+    sW[e] = (o == 0) ? wp[f] : wd[(size_t)f * R + (o - 1)];
+  }
+  const long long p0 = (long long)blockIdx.x * 32;
+  for (int e = threadIdx.x; e < 32 * (CF / 4); e += blockDim.x) {
+    const int px = e / (CF / 4), f4 = e % (CF / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p0 + px < npix) v = reinterpret_cast<const float4*>(feat + (p0 + px) * CF)[f4];
+    float* d = sF + px * (CF + 1) + 4 * f4;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  __syncthreads();
+  const int px = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = w; o < NO; o += 4) {
+    float acc = (o == 0) ? bp[0] : bd[o - 1];
+    const float* fr = sF + px * (CF + 1);
+#pragma unroll 8
+    for (int f = 0; f < CF; ++f) acc = fmaf(fr[f], sW[f * NO + o], acc);
+    if (o == 0) acc = 1.f / (1.f + expf(-acc));
+    sO[px * NO + o] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * R; e += blockDim.x) {
+    const int q = e / R, k = e % R;
+    if (p0 + q < npix) dist[(p0 + q) * R + k] = sO[q * NO + 1 + k];
+  }
+  if (threadIdx.x < 32 && p0 + threadIdx.x < npix) prob[p0 + threadIdx.x] = sO[threadIdx.x * NO];
+}
+
+}  // namespace
+
+extern "C" int sdb_conv3x3_2d(const float* d_in, const float* d_in_lo, int n, int h, int w, int cin_skip,
+                              int cin_lo, const float* d_weight, const float* d_bias, int cout, int relu,
+                              float* d_out, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cin = cin_skip + cin_lo;
+  if (d_in_lo == nullptr && cin_lo != 0) { sdb::set_error("conv3x3_2d: cin_lo without in_lo"); return 1; }
+  if (cin_lo == 0 && cin <= 4) {
+    const size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
+    const long long npix = (long long)n * h * w;
+    if (cout == 32) SDB_LAUNCH((k_conv3x3_stem<32>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_weight, d_bias, relu, d_out);
+    else if (cout == 64) SDB_LAUNCH((k_conv3x3_stem<64>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_weight, d_bias, relu, d_out);
+    else { sdb::set_error("conv3x3_2d: stem supports cout 32 or 64"); return 1; }
+    return 0;
+  }
+  if (cin_skip % 8 || cin_lo % 8 || cout % 32) { sdb::set_error("conv3x3_2d: channels must be multiples of 8 (in) / 32 (out)"); return 1; }
+  if (cin_lo && ((h & 1) || (w & 1))) { sdb::set_error("conv3x3_2d: upsampled input needs even h, w"); return 1; }
+  dim3 grid(cdiv(w, 16), cdiv(h, 16), 1);
+  if (cout % 64 == 0) {
+    grid.z = n * (cout / 64);
+    SDB_LAUNCH((k_conv3x3<64>), grid, 256, 0, st, d_in, d_in_lo, h, w, cin_skip, cin_lo, d_weight, d_bias, cout, relu, d_out);
+  } else {
+    grid.z = n * (cout / 32);
+    SDB_LAUNCH((k_conv3x3<32>), grid, 128, 0, st, d_in, d_in_lo, h, w, cin_skip, cin_lo, d_weight, d_bias, cout, relu, d_out);
+  }
+  return 0;
+}
+
+extern "C" int sdb_maxpool2x2_2d(const float* d_in, int n, int h, int w, int c, float* d_out, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((h & 1) || (w & 1) || (c & 3)) { sdb::set_error("maxpool2x2_2d: needs even h, w and c % 4 == 0"); return 1; }
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
+  SDB_LAUNCH(k_maxpool2x2, (int)std::min<long long>(cdiv(total, 256), 148 * 16), 256, 0, st, d_in, n, h, w, c, d_out);
+  return 0;
+}
+
+extern "C" int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_wp, const float* d_bp,
+                            const float* d_wd, const float* d_bd, int n_rays, float* d_prob, float* d_dist,
+                            sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfeat != 128) { sdb::set_error("heads_2d: only 128 feature channels (net_conv_after_unet) supported"); return 1; }
+  const int NO = n_rays + 1;
+  const size_t smem = (size_t)(128 * NO + 32 * 129 + 32 * NO) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) { SDB_CUDA(cudaFuncSetAttribute(k_heads<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+  if (smem > 200 * 1024) { sdb::set_error("heads_2d: n_rays too large"); return 1; }
+  SDB_LAUNCH((k_heads<128>), cdiv(npix, 32), 128, smem, st, d_feat, npix, d_wp, d_bp, d_wd, d_bd, n_rays, d_prob, d_dist);
+  return 0;
+}

@@ -2,14 +2,17 @@
 // Host (g++) build of the device-side geometry headers so that their bit-exactness against
 // oracle/_ref can be checked on the GPU-less dev box over millions of cases.  The product
 // never loads this library: the shipped path is the CUDA build of the same headers.
+#define SDC_STATS 1
 #include "../../stardist_b200/csrc/clip2d.cuh"
 #include <vector>
 using namespace sdclip;
 
 extern "C" {
 
+int hc_hw[8];
 void hc_clip_area_batch(const int32_t* a_xy, const int32_t* b_xy, int n_pairs, int n,
                         float* out_area, int* out_status) {
+  for (int k = 0; k < 8; k++) hc_hw[k] = 0;
 #pragma omp parallel
   {
     ClipSweep<128>* S = new ClipSweep<128>();
@@ -21,8 +24,11 @@ void hc_clip_area_batch(const int32_t* a_xy, const int32_t* b_xy, int n_pairs, i
         bx[i] = b_xy[2 * ((long)p * n + i)]; by[i] = b_xy[2 * ((long)p * n + i) + 1];
       }
       int st;
-      out_area[p] = clip_intersection_area<128, int32_t>(ax.data(), ay.data(), bx.data(), by.data(), n, *S, &st);
+      SplitXY va{ax.data(), ay.data()}, vb{bx.data(), by.data()};
+      out_area[p] = clip_intersection_area(va, vb, n, *S, &st);
       out_status[p] = st;
+#pragma omp critical
+      for (int k = 0; k < 8; k++) if (S->hw[k] > hc_hw[k]) hc_hw[k] = S->hw[k];
     }
     delete S;
   }
@@ -36,8 +42,9 @@ int hc_clip_paths(const int32_t* a_xy, int na, const int32_t* b_xy, int nb,
   for (int i = 0; i < na; i++) { ax[i] = a_xy[2*i]; ay[i] = a_xy[2*i+1]; }
   for (int i = 0; i < nb; i++) { bx[i] = b_xy[2*i]; by[i] = b_xy[2*i+1]; }
   S->init();
-  S->add_path(ax.data(), ay.data(), na, ptClip);
-  S->add_path(bx.data(), by.data(), nb, ptSubject);
+  SplitXY va{ax.data(), ay.data()}, vb{bx.data(), by.data()};
+  S->add_path(va, na, ptClip);
+  S->add_path(vb, nb, ptSubject);
   bool ok = S->execute();
   *status = S->err;
   int np = 0, tot = 0;
