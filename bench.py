@@ -1,0 +1,237 @@
+#!/usr/bin/env python
+"""bench.py -- predict_instances throughput of the B200 path (and of the reference CPU path).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle)
+
+A "step" is one StarDist2D.predict_instances() over one synthetic 1024x1024 image
+(BASELINE.json configs[1]: default Config2D, n_rays=32, grid (1,1), random-init U-Net).
+`value` = instances/s with the normalized, padded input already resident in HBM;
+`e2e`   = the same metric through the public API with a HOST image (pinned H2D inside, D2H of the
+          label map + polygons inside).  N>1: every rank processes its own images (weak scaling,
+          no data-path collective); value = instances of all ranks / max-over-ranks time.
+"""
+import argparse, json, os, sys, time, threading, subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SHAPE = (1024, 1024)
+N_RAYS = 32
+PROB_THRESH = 0.5          # the reference's default thresholds (base.py:241)
+NMS_THRESH = 0.4
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi SM clocks / throttle reasons while the timed region runs"""
+    def __init__(self, gpu_index=0, period=0.2):
+        super().__init__(daemon=True)
+        self.gpu, self.period, self.samples, self._halt = gpu_index, period, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                self.samples.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(self.period)
+
+    def stop(self):
+        self._halt.set(); self.join(timeout=5)
+        sm = [int(s[0]) for s in self.samples if s and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 6 for i in range(4) if s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def conv_flops(config, shape):
+    """algorithmic FLOPs of one forward pass (2*pixels*Cin*Cout*k^d per conv layer)"""
+    from stardist_b200.models.weights import unet_layers
+    sp = np.array(shape, dtype=np.float64)
+    fl = 0.0
+    for l in unet_layers(config):
+        if l['kind'] in ('conv', 'head'):
+            fl += 2.0 * np.prod(sp) * l['cin'] * l['cout'] * np.prod(l['k'])
+        elif l['kind'] == 'pool':
+            sp = sp / np.array(l['pool'])
+        elif l['kind'] == 'up':
+            sp = sp * np.array(l['pool'])
+    return fl
+
+
+def run_reference(args):
+    """the reference's CPU path on the host cores: torch-CPU fp32 U-Net (stand-in for TF-CPU, which is
+    not installable here) + the reference's own C++/OpenMP NMS (oracle/_ref) + numpy label painting."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from stardist_b200.models.config import Config2D
+    from oracle import pipeline2d
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    import bench_data
+    cfg = Config2D(n_rays=N_RAYS)
+    w = bench_data.bench_weights_2d(cfg)
+    img, _ = bench_data.synthetic_image(SHAPE, seed=0)
+    pthr = PROB_THRESH
+    def step():
+        prob, dist, pads = pipeline2d.predict(cfg, w, img)
+        pa, da, pts = pipeline2d.candidates(cfg, prob, dist, pads, img.shape, pthr)
+        labels, res = pipeline2d.instances(cfg, img.shape, pa, da, pts, NMS_THRESH)
+        return len(res['prob'])
+    for _ in range(args.warmup): step()
+    t0 = time.perf_counter(); n_inst = 0
+    for _ in range(args.steps): n_inst += step()
+    dt = time.perf_counter() - t0
+    v = n_inst / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "instances/sec (predict_instances end-to-end)", "value": v, "unit": "instances/s",
+        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "StarDist2D predict_instances, 1024x1024, n_rays=32, seeded synthetic U-Net weights (configs[1])",
+                   "prob_thresh": PROB_THRESH, "weights": "seeded Glorot body + fitted heads (bench_data.py)", "nms_thresh": NMS_THRESH},
+        "cpu_baseline": {"value": v, "unit": "instances/s", "cores": cores, "kind": "reference",
+                         "sample": "%d full 1024^2 images; NMS = reference C++/OpenMP (oracle/_ref), U-Net = torch-CPU fp32 stand-in for TF-CPU, labels = numpy restatement" % args.steps},
+        "e2e": {"value": v, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from stardist_b200 import Config2D, StarDist2D, _lib
+    import bench_data
+    cfg = Config2D(n_rays=N_RAYS)
+    model = StarDist2D(cfg, name=None, basedir=None, weights=bench_data.bench_weights_2d(cfg))
+    img, _ = bench_data.synthetic_image(SHAPE, seed=rank)
+    pthr = PROB_THRESH
+    x_dev = torch.from_numpy(img[None, ..., None]).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value)
+    for _ in range(max(3, args.warmup)):
+        model.predict_instances_device(x_dev, SHAPE, prob_thresh=pthr, nms_thresh=NMS_THRESH)
+    sampler = ClockSampler(local); sampler.start()
+    _lib.launch_count(reset=True)
+    barrier()
+    n_inst = 0; dev_ms = 0.0; stage = {}
+    for _ in range(args.steps):
+        flush.zero_()
+        model._events = []
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        labels, res = model.predict_instances_device(x_dev, SHAPE, prob_thresh=pthr, nms_thresh=NMS_THRESH)
+        e1.record(); torch.cuda.synchronize()
+        dev_ms += e0.elapsed_time(e1); n_inst += len(res['prob'])
+        ev = dict(model._events); model._events = None
+        for a, b, k in (("net_begin", "net_end", "unet"), ("net_end", "cand_end", "threshold_sort_gather"),
+                        ("cand_end", "nms_end", "nms"), ("nms_end", "label_end", "coord_label")):
+            if a in ev and b in ev: stage[k] = stage.get(k, 0.0) + ev[a].elapsed_time(ev[b])
+    launches = _lib.launch_count()
+    barrier()
+    t = torch.tensor([dev_ms, float(n_inst)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms_max, n_total = float(tmax[0]), float(tsum[1])
+    else:
+        dev_ms_max, n_total = dev_ms, float(n_inst)
+    value = n_total / (dev_ms_max / 1000.0)
+
+    # ---- end-to-end through the public API, host image in / host results out
+    model._stats = {}
+    for _ in range(2): model.predict_instances(img, prob_thresh=pthr, nms_thresh=NMS_THRESH)
+    model._stats = {}
+    barrier(); t0 = time.perf_counter(); n_e2e = 0
+    for _ in range(args.steps):
+        flush.zero_()
+        labels, res = model.predict_instances(img, prob_thresh=pthr, nms_thresh=NMS_THRESH)
+        n_e2e += len(res['prob'])
+    torch.cuda.synchronize(); e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s, float(n_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        a = te.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX); b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_s, n_e2e = float(a[0]), float(b[1])
+    clocks = sampler.stop()
+    h2d = model._stats.get('h2d_bytes', 0) // max(1, args.steps); d2h = model._stats.get('d2h_bytes', 0) // max(1, args.steps)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fl = conv_flops(cfg, SHAPE)
+        unet_ms = stage.get("unet", 0.0) / args.steps
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = fl / (unet_ms / 1000.0) / 1e12 if unet_ms > 0 else 0.0
+        out = {
+            "metric": "instances/sec (predict_instances end-to-end)", "value": value, "unit": "instances/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "StarDist2D predict_instances, 1024x1024, n_rays=32, seeded synthetic U-Net weights (configs[1])",
+                       "prob_thresh": PROB_THRESH, "weights": "seeded Glorot body + fitted heads (bench_data.py)", "nms_thresh": NMS_THRESH, "l2": "flushed (256 MiB write) between steps",
+                       "instances_per_image": n_total / (args.steps * world),
+                       "stages_ms": {k: v / args.steps for k, v in stage.items()}},
+            "clocks": clocks,
+            "e2e": {"value": n_e2e / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "U-Net conv stack (all conv3x3 launches of one forward)",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                out["cpu_baseline"] = cpu_baseline(cfg, model.weights, img, pthr)
+            except Exception as e:      # the baseline is a report, never a reason to lose the measurement
+                out["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, weights, img, pthr):
+    """bounded CPU sample of the same workload: 2 full images through the oracle path"""
+    import torch
+    from oracle import pipeline2d
+    cores = os.cpu_count(); torch.set_num_threads(cores)
+    t0 = time.perf_counter(); n = 0; reps = 2
+    for _ in range(reps):
+        prob, dist, pads = pipeline2d.predict(cfg, weights, img)
+        pa, da, pts = pipeline2d.candidates(cfg, prob, dist, pads, img.shape, pthr)
+        labels, res = pipeline2d.instances(cfg, img.shape, pa, da, pts, NMS_THRESH)
+        n += len(res['prob'])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "instances/s", "cores": cores, "kind": "reference",
+            "sample": "%d full 1024^2 images: torch-CPU fp32 U-Net (TF-CPU stand-in) + reference C++/OpenMP NMS (oracle/_ref) + numpy labels" % reps}
+
+
+if __name__ == "__main__":
+    main()

@@ -85,10 +85,10 @@ int sdb_polygons_to_label_2d(const float* d_coord, const int* d_rank, const int*
 
 /* dist_to_coord (geom2d.py:130-146): coord[n,2,R] = f32(dist * sincos(phi_k) in f64) * scale + points.
  * d_sincos = float64[2*R] = [sin(phi_k) | cos(phi_k)] evaluated by the caller with numpy (same
- * libm/SIMD routine as the reference); d_points int32[n,2] (y,x); scaled != 0 applies the
- * predict_instances(scale=...) rescale to points as well (model2d.py:539-546). */
-int sdb_dist_to_coord_2d(const float* d_dist, const int* d_points, int n_polys, int n_rays,
-                         const double* d_sincos, double scale_y, double scale_x, int scaled,
+ * libm/SIMD routine as the reference); d_points float64[n,2] (y,x) (integer pixel centres, or
+ * already multiplied by the predict_instances(scale=...) rescale, model2d.py:539-546). */
+int sdb_dist_to_coord_2d(const float* d_dist, const double* d_points, int n_polys, int n_rays,
+                         const double* d_sincos, double scale_y, double scale_x,
                          float* d_coord, sdb_stream_t stream);
 
 /* threshold + border mask + compaction + sort (nms.py:6-17, base.py:606-610, nms.py:167):

@@ -1,0 +1,92 @@
+"""ctypes binding of libstardist_b200.so (the C ABI declared in include/stardist_b200.h).
+
+The library is the product's only compute path: if it is missing, or no CUDA device is
+usable, importing the ops fails loudly -- there is no CPU fallback.
+"""
+import ctypes, os
+from ctypes import c_int, c_float, c_double, c_void_p, c_char_p, c_longlong, c_bool, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libstardist_b200.so")
+
+class StarDistB200Error(RuntimeError):
+    pass
+
+_lib = None
+
+def _declare(lib):
+    P = c_void_p
+    lib.sdb_last_error.restype = c_char_p
+    lib.sdb_last_error.argtypes = []
+    lib.sdb_launch_count.restype = c_longlong
+    lib.sdb_launch_count.argtypes = [c_int]
+    lib.sdb_device_info.argtypes = [POINTER(c_int)] * 4
+    lib._LIB_non_maximum_suppression_2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P]
+    lib._LIB_polygons_to_label_2d.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
+    lib.sdb_nms2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_polygons_to_label_2d.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P, P]
+    lib.sdb_dist_to_coord_2d.argtypes = [P, P, c_int, c_int, P, c_double, c_double, P, P]
+    lib.sdb_threshold_sort.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                       c_float, P, P, c_int, POINTER(c_int), P]
+    lib.sdb_gather_candidates.argtypes = [P, P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, P]
+    lib.sdb_conv3x3_2d.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P]
+    lib.sdb_maxpool2x2_2d.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
+    lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
+    for name in ("_LIB_non_maximum_suppression_2d", "_LIB_polygons_to_label_2d", "sdb_nms2d",
+                 "sdb_polygons_to_label_2d", "sdb_dist_to_coord_2d", "sdb_threshold_sort",
+                 "sdb_gather_candidates", "sdb_conv3x3_2d", "sdb_maxpool2x2_2d", "sdb_heads_2d",
+                 "sdb_device_info"):
+        getattr(lib, name).restype = c_int
+    # optional (added as the build widens)
+    for name, argtypes in _OPTIONAL.items():
+        if hasattr(lib, name):
+            f = getattr(lib, name); f.argtypes = argtypes[0]; f.restype = argtypes[1]
+
+_OPTIONAL = {}
+
+def register_optional(name, argtypes, restype=c_int):
+    _OPTIONAL[name] = (argtypes, restype)
+    if _lib is not None and hasattr(_lib, name):
+        f = getattr(_lib, name); f.argtypes = argtypes; f.restype = restype
+
+def load():
+    """Load the shared library (once). Raises StarDistB200Error when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise StarDistB200Error(
+                "libstardist_b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+def check(rc):
+    if rc != 0:
+        raise StarDistB200Error(load().sdb_last_error().decode("utf-8", "replace"))
+
+def launch_count(reset=False):
+    return int(load().sdb_launch_count(1 if reset else 0))
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise StarDistB200Error("stardist_b200 needs a CUDA device (sm_100a); none is visible and there is no CPU fallback")
+    return load()
+
+def ptr(t):
+    """device/host pointer of a torch tensor or numpy array as c_void_p (None -> NULL)"""
+    if t is None:
+        return c_void_p(0)
+    if hasattr(t, "data_ptr"):
+        return c_void_p(t.data_ptr())
+    return c_void_p(t.ctypes.data)
+
+def stream_ptr(stream=None):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return c_void_p(s.cuda_stream)
+
+def iarr(vals):
+    return (c_int * len(vals))(*[int(v) for v in vals])

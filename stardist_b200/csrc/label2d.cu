@@ -24,8 +24,8 @@ namespace {
 
 using sdb::cdiv;
 
-__global__ void k_dist_to_coord(const float* __restrict__ dist, const int* __restrict__ points, int n, int R,
-                                const double* __restrict__ sincos, double sy, double sx, int scaled,
+__global__ void k_dist_to_coord(const float* __restrict__ dist, const double* __restrict__ points, int n, int R,
+                                const double* __restrict__ sincos, double sy, double sx,
                                 float* __restrict__ coord) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * R) return;
@@ -36,11 +36,9 @@ __global__ void k_dist_to_coord(const float* __restrict__ dist, const int* __res
   // coord *= scale_dist  (float32 array times int64/float64 array: computed in float64, cast back)
   cy = (float)((double)cy * sy);
   cx = (float)((double)cx * sx);
-  // coord += points[..., None]  (points: int64, or float64 = int * rescale when scale is given)
-  const double py = scaled ? (double)points[2 * i] * sy : (double)points[2 * i];
-  const double px = scaled ? (double)points[2 * i + 1] * sx : (double)points[2 * i + 1];
-  cy = (float)((double)cy + py);
-  cx = (float)((double)cx + px);
+  // coord += points[..., None]  (points: int64 -> exact in float64, or float64 after rescale)
+  cy = (float)((double)cy + points[2 * i]);
+  cx = (float)((double)cx + points[2 * i + 1]);
   coord[((size_t)i * 2 + 0) * R + k] = cy;
   coord[((size_t)i * 2 + 1) * R + k] = cx;
 }
@@ -119,13 +117,13 @@ __global__ void k_rank_to_label(int* __restrict__ img, long long npix, const int
 
 }  // namespace
 
-extern "C" int sdb_dist_to_coord_2d(const float* d_dist, const int* d_points, int n_polys, int n_rays,
-                                    const double* d_sincos, double scale_y, double scale_x, int scaled,
+extern "C" int sdb_dist_to_coord_2d(const float* d_dist, const double* d_points, int n_polys, int n_rays,
+                                    const double* d_sincos, double scale_y, double scale_x,
                                     float* d_coord, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (n_polys <= 0) return 0;
   SDB_LAUNCH(k_dist_to_coord, cdiv((long long)n_polys * n_rays, 256), 256, 0, st, d_dist, d_points, n_polys, n_rays,
-             d_sincos, scale_y, scale_x, scaled, d_coord);
+             d_sincos, scale_y, scale_x, d_coord);
   return 0;
 }
 

@@ -1,0 +1,419 @@
+"""StarDistBase: prediction orchestration, device resident.
+
+Mirrors the prediction half of stardist/models/base.py:
+  _predict_setup (:371-443), _predict_generator/predict (:446-529), _predict_sparse_generator/
+  predict_sparse (:541-642), _predict_instances_generator/predict_instances (:645-790),
+  predict_instances_big (:838-983), thresholds handling (:230-252), _compute_receptive_field
+  (:1068-1098), _axes_tile_overlap (:1101-1111), StarDistPadAndCropResizer (:1162-1211).
+Training, threshold optimisation and export are out of scope.
+
+Differences by design: the network, thresholding, sort, NMS and label painting all run as CUDA
+kernels on tensors that stay in HBM; only the final labels / polygons are copied to the host.
+"""
+import json, math, numbers, warnings, functools
+from collections import namedtuple
+from pathlib import Path
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..utils import (_raise, axes_check_and_normalize, axes_dict, move_image_axes, _is_floatarray,
+                     _is_power_of_2)
+from .weights import glorot_uniform_weights
+
+Thresholds = namedtuple('Thresholds', ('prob', 'nms'))
+
+
+class NoNormalizer:
+    def before(self, x, axes):
+        return x
+
+    def after(self, mean, scale, axes):
+        return mean, scale
+
+
+class PercentileNormalizer:
+    """csbdeep.data.PercentileNormalizer (percentile based input normalization)"""
+
+    def __init__(self, pmin=2, pmax=99.8, do_after=True, dtype=np.float32, **kwargs):
+        self.pmin, self.pmax, self._do_after, self.dtype, self.kwargs = pmin, pmax, do_after, dtype, kwargs
+
+    def before(self, x, axes):
+        from ..utils import normalize_mi_ma
+        axes = axes_check_and_normalize(axes, x.ndim)
+        channel = axes_dict(axes)['C']
+        axis = None if channel is None else tuple((d for d in range(x.ndim) if d != channel))
+        self.mi = np.percentile(x, self.pmin, axis=axis, keepdims=True).astype(self.dtype, copy=False)
+        self.ma = np.percentile(x, self.pmax, axis=axis, keepdims=True).astype(self.dtype, copy=False)
+        return normalize_mi_ma(x, self.mi, self.ma, dtype=self.dtype, **self.kwargs)
+
+
+class StarDistPadAndCropResizer:
+    """stardist/models/base.py:1162-1211 (pads at the END of each axis, mode 'reflect')"""
+
+    def __init__(self, grid, mode='reflect', **kwargs):
+        assert isinstance(grid, dict)
+        self.mode = mode
+        self.grid = grid
+        self.kwargs = kwargs
+
+    def before(self, x, axes, axes_div_by):
+        assert all(a % g == 0 for g, a in zip((self.grid.get(a, 1) for a in axes), axes_div_by))
+        axes = axes_check_and_normalize(axes, x.ndim)
+
+        def _split(v):
+            return 0, v  # only pad at the end
+        self.pad = {a: _split((div_n - s % div_n) % div_n) for a, div_n, s in zip(axes, axes_div_by, x.shape)}
+        x_pad = np.pad(x, tuple(self.pad[a] for a in axes), mode=self.mode, **self.kwargs)
+        self.padded_shape = dict(zip(axes, x_pad.shape))
+        if 'C' in self.padded_shape:
+            del self.padded_shape['C']
+        return x_pad
+
+    def crop_slices(self, axes, shape):
+        axes = axes_check_and_normalize(axes, len(shape))
+        assert all(s_pad == s * g for s, s_pad, g in zip(shape,
+                                                         (self.padded_shape.get(a, _s) for a, _s in zip(axes, shape)),
+                                                         (self.grid.get(a, 1) for a in axes)))
+        return tuple(
+            slice(0, -(math.floor(p[1] / g)) if p[1] >= g else None)
+            for p, g in zip((self.pad.get(a, (0, 0)) for a in axes), (self.grid.get(a, 1) for a in axes)))
+
+    def after(self, x, axes):
+        return x[self.crop_slices(axes, x.shape)]
+
+    def point_bounds(self, axes):
+        """filter_points: a candidate is kept iff point < padded_shape - pad (per spatial axis)"""
+        return tuple(self.padded_shape[a] - self.pad[a][1] for a in axes if a.lower() in ('z', 'y', 'x'))
+
+    def filter_points(self, ndim, points, axes):
+        assert points.ndim == 2
+        axes = axes_check_and_normalize(axes, ndim)
+        bounds = np.array(self.point_bounds(axes))
+        return np.where(np.all(points < bounds, 1))
+
+
+class StarDistBase:
+    """Common prediction logic of StarDist2D / StarDist3D."""
+
+    def __init__(self, config, name=None, basedir='.', weights=None, seed=0):
+        self.name = name
+        self.basedir = None if basedir is None else Path(basedir)
+        self.logdir = None if (basedir is None or name is None) else self.basedir / name
+        if config is None:
+            if self.logdir is None or not (self.logdir / 'config.json').exists():
+                raise FileNotFoundError("config file doesn't exist: %s" % (None if self.logdir is None else str((self.logdir / 'config.json').resolve())))
+            with open(self.logdir / 'config.json') as f:
+                cfg = json.load(f)
+            config = self._config_class(**cfg)
+        isinstance(config, self._config_class) or _raise(ValueError("Invalid configuration of type '%s', was expecting type '%s'." % (type(config).__name__, self._config_class.__name__)))
+        self.config = config
+        # thresholds (base.py:230-252)
+        threshs = dict(prob=None, nms=None)
+        if self.logdir is not None and (self.logdir / 'thresholds.json').exists():
+            with open(self.logdir / 'thresholds.json') as f:
+                threshs = json.load(f)
+            if threshs.get('prob') is not None and not (0 < threshs['prob'] < 1):
+                threshs['prob'] = None
+            if threshs.get('nms') is not None and not (0 < threshs['nms'] < 1):
+                threshs['nms'] = None
+        if threshs.get('prob') is None or threshs.get('nms') is None:
+            default = dict(prob=0.5, nms=0.4)
+            for k in default:
+                if threshs.get(k) is None:
+                    threshs[k] = default[k]
+        self.thresholds = dict(prob=threshs['prob'], nms=threshs['nms'])
+        # weights: explicit dict > <logdir>/weights.npz > seeded Glorot-uniform (Keras default init)
+        if weights is None and self.logdir is not None and (self.logdir / 'weights.npz').exists():
+            weights = load_weights_npz(self.logdir / 'weights.npz')
+        if weights is None:
+            if self.logdir is not None and any((self.logdir / f).exists() for f in ('weights_best.h5', 'weights_last.h5')):
+                warnings.warn("Keras .h5 weights found but no HDF5 reader is available on this path; using random-init weights")
+            weights = glorot_uniform_weights(config, seed=seed)
+        self.weights = weights
+        self._net = None
+        self._stats = {}
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def thresholds(self):
+        return self._thresholds
+
+    @thresholds.setter
+    def thresholds(self, d):
+        self._thresholds = Thresholds(**d)
+
+    # optional per-stage CUDA-event timing (bench.py): set model._events = [] to collect
+    def _mark(self, name):
+        ev = getattr(self, '_events', None)
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
+    def _is_multiclass(self):
+        return self.config.n_classes is not None
+
+    @property
+    def net(self):
+        if self._net is None:
+            self._net = self._build()
+        return self._net
+
+    def save_weights(self, path):
+        np.savez(path, **{('%s/kernel' % k): v[0] for k, v in self.weights.items()},
+                 **{('%s/bias' % k): v[1] for k, v in self.weights.items()})
+
+    # ------------------------------------------------------------------ helpers shared with the reference
+    def _normalize_axes(self, img, axes):
+        if axes is None:
+            axes = self.config.axes
+            assert 'C' in axes
+            if img.ndim == len(axes) - 1 and self.config.n_channel_in == 1:
+                axes = axes.replace('C', '')
+        return axes_check_and_normalize(axes, img.ndim)
+
+    def _make_permute_axes(self, img_axes_in, net_axes_in, net_axes_out=None):
+        if net_axes_out is None:
+            net_axes_out = net_axes_in
+        channel_in = axes_dict(img_axes_in)['C']
+
+        def _permute_axes(data, undo=False):
+            if data is None:
+                return None
+            if undo:
+                if channel_in is not None:
+                    return move_image_axes(data, net_axes_out, img_axes_in, True)
+                else:
+                    data = move_image_axes(data, net_axes_out, img_axes_in + 'C', True)
+                    if data.shape[-1] == 1:
+                        data = data[..., 0]
+                    return data
+            else:
+                return move_image_axes(data, img_axes_in, net_axes_in, True)
+        return _permute_axes
+
+    def _check_normalizer(self, normalizer):
+        if normalizer is None:
+            return NoNormalizer()
+        hasattr(normalizer, 'before') or _raise(ValueError("normalizer must provide .before(x, axes)"))
+        return normalizer
+
+    def _predict_setup(self, img, axes, normalizer, n_tiles):
+        """ Shared setup code between `predict` and `predict_sparse` (base.py:371-443) """
+        if n_tiles is None:
+            n_tiles = [1] * img.ndim
+        try:
+            n_tiles = tuple(n_tiles)
+            img.ndim == len(n_tiles) or _raise(TypeError())
+        except TypeError:
+            raise ValueError("n_tiles must be an iterable of length %d" % img.ndim)
+        all(np.isscalar(t) and 1 <= t and int(t) == t for t in n_tiles) or _raise(
+            ValueError("all values of n_tiles must be integer values >= 1"))
+        n_tiles = tuple(map(int, n_tiles))
+        axes = self._normalize_axes(img, axes)
+        axes_net = self.config.axes
+        _permute_axes = self._make_permute_axes(axes, axes_net)
+        x = _permute_axes(img)  # x has axes_net semantics
+        channel = axes_dict(axes_net)['C']
+        self.config.n_channel_in == x.shape[channel] or _raise(ValueError())
+        axes_net_div_by = self._axes_div_by(axes_net)
+        grid = tuple(self.config.grid)
+        len(grid) == len(axes_net) - 1 or _raise(ValueError())
+        grid_dict = dict(zip(axes_net.replace('C', ''), grid))
+        normalizer = self._check_normalizer(normalizer)
+        resizer = StarDistPadAndCropResizer(grid=grid_dict)
+        x = normalizer.before(x, axes_net)
+        x = resizer.before(x, axes_net, axes_net_div_by)
+        if not _is_floatarray(x):
+            warnings.warn("Predicting on non-float input... ( forgot to normalize? )")
+        if np.prod(n_tiles) > 1:
+            raise NotImplementedError("n_tiles > 1 is not implemented yet on the B200 path "
+                                      "(use predict_instances_big for large images)")
+        return x, axes, axes_net, axes_net_div_by, _permute_axes, resizer, n_tiles, grid, grid_dict, channel
+
+    def _to_device(self, x):
+        """host float array (axes_net semantics, channels last) -> pinned -> device [1,...,C] float32"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        t = torch.from_numpy(x[np.newaxis])
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+        self._stats['h2d_bytes'] = self._stats.get('h2d_bytes', 0) + t.numel() * 4
+        return t.to(self.net.device, non_blocking=True)
+
+    def predict_direct_device(self, x_dev):
+        """x_dev [1,...,C] float32 device -> (prob [...], dist [..., R]) device tensors (padded, /grid)"""
+        prob, dist = self.net.forward(x_dev)
+        self._last = (prob[0], dist[0])
+        return prob[0], dist[0]
+
+    def _last_maps(self):
+        """(tests) padded prob / dist maps of the most recent forward pass, as numpy"""
+        return self._last[0].cpu().numpy(), self._last[1].cpu().numpy()
+
+    # ------------------------------------------------------------------ predict (dense)
+    def predict(self, img, axes=None, normalizer=None, n_tiles=None, show_tile_progress=True, **predict_kwargs):
+        """Dense prediction: returns (prob, dist) numpy arrays (base.py:446-529)."""
+        L.require_cuda()
+        x, axes, axes_net, axes_net_div_by, _permute_axes, resizer, n_tiles, grid, grid_dict, channel = \
+            self._predict_setup(img, axes, normalizer, n_tiles)
+        prob_d, dist_d = self.predict_direct_device(self._to_device(x))
+        sp_axes = axes_net.replace('C', '')
+        crop = resizer.crop_slices(sp_axes, tuple(prob_d.shape))
+        prob = prob_d[crop].contiguous().cpu().numpy()
+        dist = dist_d[crop + (slice(None),)].contiguous()
+        dist = torch.clamp_min(dist, 1e-3).cpu().numpy()   # np.maximum(1e-3, dist), base.py:517
+        return prob, dist
+
+    # ------------------------------------------------------------------ predict_sparse
+    def _predict_sparse_device(self, img, prob_thresh=None, axes=None, normalizer=None, n_tiles=None, b=2):
+        """device-resident sparse prediction (base.py:541-633): returns dict of device tensors
+        prob[n], dist[n,R], points_f32[n,nd] (for the NMS kernels), sorted by score."""
+        L.require_cuda()
+        x, axes, axes_net, axes_net_div_by, _permute_axes, resizer, n_tiles, grid, grid_dict, channel = \
+            self._predict_setup(img, axes, normalizer, n_tiles)
+        sp_axes = axes_net.replace('C', '')
+        bounds = resizer.point_bounds(sp_axes)
+        return self._candidates_from_device_input(self._to_device(x), bounds, prob_thresh=prob_thresh, b=b)
+
+    def _candidates_from_device_input(self, x_dev, bounds, prob_thresh=None, b=2):
+        """x_dev: padded, normalized input [1,...,C] float32 already in HBM; bounds = un-padded spatial
+        extent (filter_points).  Network -> threshold/border mask -> score sort -> gather."""
+        lib = L.require_cuda()
+        if prob_thresh is None:
+            prob_thresh = self.thresholds.prob
+        grid = tuple(self.config.grid)
+        self._mark('net_begin')
+        prob_d, dist_d = self.predict_direct_device(x_dev)
+        self._mark('net_end')
+        nd = self.config.n_dim
+        R = self.config.n_rays
+        shape = tuple(int(s) for s in prob_d.shape)
+        valid = tuple(int(-(-bd // g)) for bd, g in zip(bounds, grid))     # idx*g < bound  <=>  idx < ceil(bound/g)
+        if b is not None and np.isscalar(b):
+            bs = ((int(b), int(b)),) * nd
+        elif b is None:
+            bs = ((0, 0),) * nd
+        else:
+            bs = tuple((max(0, int(lo)), max(0, int(hi))) for lo, hi in b)
+        npix = int(np.prod(shape))
+        sidx = torch.empty(npix, dtype=torch.int32, device=prob_d.device)
+        sprob = torch.empty(npix, dtype=torch.float32, device=prob_d.device)
+        import ctypes
+        cnt = ctypes.c_int(0)
+        L.check(lib.sdb_threshold_sort(L.ptr(prob_d), nd, L.iarr(shape), L.iarr(valid), L.iarr([s[0] for s in bs]),
+                                      L.iarr([s[1] for s in bs]), float(np.float32(prob_thresh)), L.ptr(sidx), L.ptr(sprob),
+                                      npix, ctypes.byref(cnt), L.stream_ptr()))
+        n = int(cnt.value)
+        sidx, sprob = sidx[:n], sprob[:n]
+        dist_s = torch.empty((n, R), dtype=torch.float32, device=prob_d.device)
+        pts_f = torch.empty((n, nd), dtype=torch.float32, device=prob_d.device)
+        L.check(lib.sdb_gather_candidates(L.ptr(dist_d), L.ptr(sidx), n, R, nd, L.iarr(shape), L.iarr(grid),
+                                         L.ptr(dist_s), L.ptr(pts_f), L.stream_ptr()))
+        self._mark('cand_end')
+        return dict(prob=sprob, dist=dist_s, points_f32=pts_f, n=n)
+
+    def predict_instances_device(self, x_dev, img_shape, prob_thresh=None, nms_thresh=None, return_labels=True, **nms_kwargs):
+        """predict_instances for an input that is already resident in HBM (padded, normalized,
+        [1,...,C] float32).  Used by bench.py's device-resident timing and by predict_instances_big."""
+        cand = self._candidates_from_device_input(x_dev, tuple(img_shape), prob_thresh=prob_thresh)
+        return self._instances_from_candidates_device(tuple(img_shape), cand, nms_thresh=nms_thresh,
+                                                      return_labels=return_labels, **nms_kwargs)
+
+    def predict_sparse(self, img, prob_thresh=None, axes=None, normalizer=None, n_tiles=None, show_tile_progress=True, b=2, **predict_kwargs):
+        """Sparse version of model.predict(): (prob, dist, points) flat lists (base.py:541-642).
+        Candidate order is score-descending (stable), see csrc/candidates.cu."""
+        r = self._predict_sparse_device(img, prob_thresh=prob_thresh, axes=axes, normalizer=normalizer, n_tiles=n_tiles, b=b)
+        prob = r['prob'].cpu().numpy()
+        dist = r['dist'].cpu().numpy()
+        points = r['points_f32'].cpu().numpy().astype(np.int64)
+        return prob, dist, points
+
+    # ------------------------------------------------------------------ predict_instances
+    def predict_instances(self, img, axes=None, normalizer=None, sparse=True, prob_thresh=None, nms_thresh=None,
+                          scale=None, n_tiles=None, show_tile_progress=True, verbose=False, return_labels=True,
+                          predict_kwargs=None, nms_kwargs=None, overlap_label=None, return_predict=False):
+        """Predict instance segmentation from input image (base.py:645-790).
+
+        Returns (labels, dict(coord|dist, points, prob, ...)) [, (prob, dist) when return_predict]."""
+        L.require_cuda()
+        if predict_kwargs is None:
+            predict_kwargs = {}
+        if nms_kwargs is None:
+            nms_kwargs = {}
+        if return_predict and sparse:
+            sparse = False
+            warnings.warn("Setting sparse to False because return_predict is True")
+        nms_kwargs.setdefault("verbose", verbose)
+        _axes = self._normalize_axes(img, axes)
+        _axes_net = self.config.axes
+        _permute_axes = self._make_permute_axes(_axes, _axes_net)
+        _shape_inst = tuple(s for s, a in zip(_permute_axes(img).shape, _axes_net) if a != 'C')
+        if scale is not None:
+            from scipy import ndimage as ndi
+            if isinstance(scale, numbers.Number):
+                scale = tuple(scale if a in 'XYZ' else 1 for a in _axes)
+            scale = tuple(scale)
+            len(scale) == len(_axes) or _raise(ValueError(f"scale {scale} must be of length {len(_axes)}, i.e. one value for each of the axes {_axes}"))
+            for s, a in zip(scale, _axes):
+                s > 0 or _raise(ValueError("scale values must be greater than 0"))
+                (s in (1, None) or a in 'XYZ') or warnings.warn(f"replacing scale value {s} for non-spatial axis {a} with 1")
+            scale = tuple(s if a in 'XYZ' else 1 for s, a in zip(scale, _axes))
+            verbose and print(f"scaling image by factors {scale} for axes {_axes}")
+            img = ndi.zoom(img, scale, order=1)
+        scale_dict = None if scale is None else dict(zip(_axes, scale))
+        if sparse:
+            cand = self._predict_sparse_device(img, prob_thresh=prob_thresh, axes=axes, normalizer=normalizer, n_tiles=n_tiles)
+            res = self._instances_from_candidates_device(_shape_inst, cand, nms_thresh=nms_thresh, scale=scale_dict,
+                                                         return_labels=return_labels, overlap_label=overlap_label, **nms_kwargs)
+            return res
+        else:
+            prob, dist = self.predict(img, axes=axes, normalizer=normalizer, n_tiles=n_tiles)
+            res = self._instances_from_prediction(_shape_inst, prob, dist, points=None, prob_thresh=prob_thresh,
+                                                  nms_thresh=nms_thresh, scale=scale_dict, return_labels=return_labels,
+                                                  overlap_label=overlap_label, **nms_kwargs)
+            if return_predict:
+                return res, (prob, dist)
+            return res
+
+    # ------------------------------------------------------------------ misc
+    def _compute_receptive_field(self, img_size=None):
+        """base.py:1068-1098: empirical receptive field from the response to a unit impulse"""
+        from scipy.ndimage import zoom
+        if img_size is None:
+            img_size = tuple(g * (128 if self.config.n_dim == 2 else 64) for g in self.config.grid)
+        if np.isscalar(img_size):
+            img_size = (img_size,) * self.config.n_dim
+        img_size = tuple(img_size)
+        assert all(_is_power_of_2(s) for s in img_size)
+        mid = tuple(s // 2 for s in img_size)
+        x = np.zeros((1,) + img_size + (self.config.n_channel_in,), dtype=np.float32)
+        z = np.zeros_like(x)
+        x[(0,) + mid + (slice(None),)] = 1
+        dev = self.net.device
+        y = self.net.forward(torch.from_numpy(x).to(dev))[0][0].cpu().numpy()
+        y0 = self.net.forward(torch.from_numpy(z).to(dev))[0][0].cpu().numpy()
+        grid = tuple((np.array(x.shape[1:-1]) / np.array(y.shape)).astype(int))
+        assert grid == tuple(self.config.grid)
+        y = zoom(y, grid, order=0)
+        y0 = zoom(y0, grid, order=0)
+        ind = np.where(np.abs(y - y0) > 0)
+        if any(len(i) == 0 for i in ind):
+            untrained = type(self)(self.config, name=None, basedir=None)
+            return untrained._compute_receptive_field(img_size=img_size)
+        return [(m - np.min(i), np.max(i) - m) for (m, i) in zip(mid, ind)]
+
+    def _axes_tile_overlap(self, query_axes):
+        query_axes = axes_check_and_normalize(query_axes)
+        try:
+            self._tile_overlap
+        except AttributeError:
+            self._tile_overlap = self._compute_receptive_field()
+        overlap = dict(zip(self.config.axes.replace('C', ''), tuple(max(rf) for rf in self._tile_overlap)))
+        return tuple(overlap.get(a, 0) for a in query_axes)
+
+
+def load_weights_npz(path):
+    z = np.load(path)
+    names = sorted(set(k.rsplit('/', 1)[0] for k in z.files))
+    return {n: (z[n + '/kernel'], z[n + '/bias']) for n in names}

@@ -1,0 +1,41 @@
+"""Deterministic input generators shared by make_golden.py and the tests.
+Follow the reference's own test generators (tests/test_nms2D.py:9-16, tests/test_nms3D.py:8-15)
+with the legacy seeded RandomState (np.random.seed(42), as tests/test_nms2D.py:83 does)."""
+import numpy as np
+
+NMS2D_CASES = {
+    # name: (shape, radius, noise, n_rays, grid, prob_thresh, nms_thresh, seed)
+    "r32_356x299": ((356, 299), 10, .1, 32, (1, 1), 0.9, 0.3, 42),
+    "r11_114x217": ((114, 217), 10, .1, 11, (1, 1), 0.9, 0.3, 42),
+    "r32_grid16": ((356, 299), 10, .1, 32, (16, 16), 0.3, 0.3, 42),
+    "r32_noise0_thr0": ((200, 207), 10, 0.0, 32, (1, 1), 0.9, 0.0, 7),
+    "r64_small": ((120, 130), 6, .3, 64, (1, 1), 0.9, 0.4, 3),
+    "r32_tiny_radius": ((150, 150), 2, .5, 32, (1, 1), 0.9, 0.4, 5),
+}
+
+
+def create_random_data_2d(shape, radius, noise, n_rays, seed):
+    rs = np.random.RandomState(seed)
+    dist = radius * np.ones(shape + (n_rays,))
+    noise = np.clip(noise, 0, 1)
+    if noise > 0:
+        dist *= (1 + noise * rs.uniform(-1, 1, dist.shape))
+    prob = rs.uniform(0, 1, shape)
+    return prob.astype(np.float32), dist.astype(np.float32)
+
+
+def nms2d_inputs(name):
+    """-> dist f32[n,R], points f32[n,2], scores f32[n] sorted by descending score (stable), nms_thresh"""
+    shape, radius, noise, n_rays, grid, pthr, nthr, seed = NMS2D_CASES[name]
+    prob, dist = create_random_data_2d(shape, radius, noise, n_rays, seed)
+    prob = prob[::grid[0], ::grid[1]]; dist = dist[::grid[0], ::grid[1]]
+    mask = prob > pthr
+    b = 2
+    m2 = np.zeros_like(mask); m2[b:-b, b:-b] = True
+    mask &= m2
+    points = np.stack(np.where(mask), axis=1)
+    d = dist[mask]; s = prob[mask]
+    ind = np.argsort(s, kind='stable')[::-1]
+    d, s, points = d[ind], s[ind], points[ind]
+    points = points * np.array(grid).reshape(1, 2)
+    return np.ascontiguousarray(d, np.float32), np.ascontiguousarray(points, np.float32), s, np.float32(nthr)

@@ -1,0 +1,128 @@
+"""CPU tests (run with -m "not gpu"): the oracle is pinned against the golden vectors, the
+host build of the device geometry agrees with the reference's Clipper, the C-ABI library loads
+and exports everything include/stardist_b200.h declares.  No compute call needs a GPU here."""
+import ctypes, os, re, subprocess, sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import cases
+from oracle import ref_ext, geom2d_np, nms_np
+
+needs_ref = pytest.mark.skipif(not ref_ext.available(), reason="oracle/_ref not built (make -C oracle ref)")
+
+
+@needs_ref
+@pytest.mark.parametrize("name", list(cases.NMS2D_CASES))
+def test_ref_nms2d_matches_golden(name, golden_dir):
+    """the compiled reference reproduces the committed golden keep masks (pins oracle/_ref)"""
+    g = np.load(os.path.join(golden_dir, "nms2d.npz"))
+    d, p, s, thr = cases.nms2d_inputs(name)
+    assert len(d) == int(g[name + "/n"])
+    for kd in (1, 0):
+        keep = ref_ext.stardist2d().c_non_max_suppression_inds(d, p, kd, 1, 0, thr)
+        want = np.unpackbits(g["%s/keep_kd%d" % (name, kd)])[:len(d)].astype(bool)
+        assert np.array_equal(keep, want)
+
+
+@needs_ref
+def test_kdtree_changes_result_only_at_exact_touching_distance(golden_dir):
+    """reference property (tests/test_nms3D.py:46 analogue in 2D): kd-tree on/off -> same survivors,
+    EXCEPT when centres sit exactly at the strict radius (noise 0, thresh 0: circles at distance
+    2r are skipped by the kd-tree's `d2 < r2` but overlap after integer truncation)."""
+    g = np.load(os.path.join(golden_dir, "nms2d.npz"))
+    for name in cases.NMS2D_CASES:
+        same = np.array_equal(g[name + "/keep_kd1"], g[name + "/keep_kd0"])
+        assert same == (name != "r32_noise0_thr0")
+
+
+def _hostcheck():
+    path = os.path.join(ROOT, "tests", "hostcheck", "_build", "libhostcheck.so")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostcheck")], check=True, stdout=subprocess.DEVNULL)
+    return ctypes.CDLL(path)
+
+
+@needs_ref
+@pytest.mark.parametrize("n_rays,radius,noise,seed", [(32, 10, .1, 0), (32, 3, .5, 1), (11, 8, .1, 2), (64, 20, .4, 3), (32, 30, .9, 4)])
+def test_clip_sweep_bit_exact_vs_reference_clipper(n_rays, radius, noise, seed):
+    """clip2d.cuh (host build) == vendored Clipper 6.4.2 on fuzzed polygon pairs, float-bit exact"""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "tools"))
+    import clip_fuzz as cf
+    cf.hc = _hostcheck()
+    a, b = cf.make_pairs(40000, n_rays, radius, noise, seed)
+    r, h, st = cf.run(a, b)
+    assert np.count_nonzero(st == 2) == 0
+    assert np.array_equal(r.view(np.int32), h.view(np.int32))
+    assert np.count_nonzero(r) > 1000
+
+
+def test_capi_exports_every_declared_symbol():
+    lib_path = os.path.join(ROOT, "stardist_b200", "libstardist_b200.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("libstardist_b200.so not built (python -c 'import __graft_entry__ as g; g.build()')")
+    hdr = open(os.path.join(ROOT, "include", "stardist_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = re.findall(r"\b((?:sdb_|_LIB_)\w+)\s*\(", hdr)
+    assert len(names) >= 10
+    lib = ctypes.CDLL(lib_path)
+    missing = [n for n in sorted(set(names)) if not hasattr(lib, n)]
+    assert not missing, "declared in include/stardist_b200.h but not exported: %s" % missing
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from stardist_b200 import _lib
+    from stardist_b200.lib.stardist2d import c_non_max_suppression_inds
+    with pytest.raises(_lib.StarDistB200Error):
+        c_non_max_suppression_inds(np.ones((3, 32), np.float32), np.zeros((3, 2), np.float32), 1, 1, 0, np.float32(.4))
+
+
+# ---- polygon rule restatement (skimage is not installed: property tests only) -------------
+def test_polygon_rule_convex_matches_halfplanes():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        R = 16
+        phi = np.linspace(0, 2 * np.pi, R, endpoint=False)
+        c = rng.uniform(20, 40, 2); rad = rng.uniform(5, 15)
+        r = (c[0] + rad * np.sin(phi)).astype(np.float32); cc = (c[1] + rad * np.cos(phi)).astype(np.float32)
+        rr, cx = geom2d_np.polygon(r, cc, (64, 64))
+        img = np.zeros((64, 64), bool); img[rr, cx] = True
+        # strict interior by half-plane test must be painted, strict exterior must not
+        Y, X = np.mgrid[0:64, 0:64].astype(np.float64)
+        inside = np.ones((64, 64), bool); outside = np.zeros((64, 64), bool)
+        for k in range(R):
+            y0, x0, y1, x1 = float(r[k]), float(cc[k]), float(r[(k + 1) % R]), float(cc[(k + 1) % R])
+            cr = (x1 - x0) * (Y - y0) - (y1 - y0) * (X - x0)
+            inside &= cr < -1e-9; outside |= cr > 1e-9
+        assert img[inside].all() and not img[outside].any()
+
+
+def test_polygon_integer_vertices_are_painted():
+    # n_rays=32: rays 0/16 land on integer rows, 8/24 on integer columns for integer centres
+    d = np.full((1, 32), 5.0, np.float32); p = np.array([[20, 20]])
+    lbl = geom2d_np.polygons_to_label(d, p, (40, 40))
+    assert lbl[20, 25] == 1 and lbl[20, 15] == 1 and lbl[25, 20] == 1 and lbl[15, 20] == 1
+    assert lbl[20, 26] == 0 and lbl[14, 20] == 0
+
+
+def test_paint_order_highest_prob_wins():
+    d = np.full((2, 32), 6.0, np.float32); p = np.array([[20, 20], [20, 24]])
+    lbl = geom2d_np.polygons_to_label(d, p, (40, 48), prob=np.array([0.9, 0.8]))
+    assert lbl[20, 22] == 1          # overlap region belongs to the higher prob polygon (painted last)
+    lbl = geom2d_np.polygons_to_label(d, p, (40, 48), prob=np.array([0.8, 0.8]))
+    assert lbl[20, 22] == 2          # ties: stable ascending sort paints index 1 last
+
+
+def test_stable_score_order_definition():
+    s = np.array([.5, .9, .5, .9, .1], np.float32)
+    assert nms_np.argsort_desc(s).tolist() == [3, 1, 2, 0, 4]
+
+
+def test_unet_topology_param_counts():
+    from stardist_b200.models.config import Config2D
+    from stardist_b200.models.weights import glorot_uniform_weights, count_params
+    assert count_params(glorot_uniform_weights(Config2D())) == 1406689
+    assert count_params(glorot_uniform_weights(Config2D(grid=(2, 2)))) == 1425185  # == 2D_demo weights file

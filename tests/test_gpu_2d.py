@@ -1,0 +1,155 @@
+"""GPU parity tests of the 2D path (run on the B200 box: pytest -m gpu).  Everything goes through
+the C ABI of libstardist_b200.so; the checker is the oracle (reference C++ in oracle/_ref, numpy
+restatements) and the committed golden vectors.  Integer/index results must be bit-exact."""
+import os, sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import cases
+from oracle import ref_ext, geom2d_np, nms_np, unet_torch, pipeline2d
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    import stardist_b200
+    from stardist_b200 import _lib
+    _lib.require_cuda()
+    return stardist_b200
+
+
+@pytest.mark.parametrize("name", list(cases.NMS2D_CASES))
+@pytest.mark.parametrize("use_kdtree", [1, 0])
+def test_nms2d_golden(sd, name, use_kdtree, golden_dir):
+    from stardist_b200.lib.stardist2d import c_non_max_suppression_inds
+    g = np.load(os.path.join(golden_dir, "nms2d.npz"))
+    d, p, s, thr = cases.nms2d_inputs(name)
+    keep = c_non_max_suppression_inds(d, p, use_kdtree, 1, 0, thr)
+    want = np.unpackbits(g["%s/keep_kd%d" % (name, use_kdtree)])[:len(d)].astype(bool)
+    assert keep.dtype == np.bool_ and np.array_equal(keep, want)
+
+
+@pytest.mark.parametrize("n,R,radius,noise,thr,seed", [(20000, 32, 8, .2, .4, 0), (5000, 96, 12, .3, .5, 1),
+                                                       (3000, 32, 1.5, .9, .3, 2), (1, 32, 5, 0, .4, 3), (2, 7, 5, .1, .4, 4)])
+def test_nms2d_vs_reference_ext(sd, n, R, radius, noise, thr, seed):
+    """random candidate clouds (incl. degenerate tiny polygons): product == reference C++"""
+    from stardist_b200.lib.stardist2d import c_non_max_suppression_inds
+    rng = np.random.default_rng(seed)
+    pts = rng.integers(0, 300, (n, 2)).astype(np.float32)
+    dist = (radius * (1 + noise * rng.uniform(-1, 1, (n, R)))).astype(np.float32)
+    dist = np.maximum(np.float32(1e-3), dist)
+    for use_bbox in (1, 0):
+        want = ref_ext.stardist2d().c_non_max_suppression_inds(dist, pts, 1, use_bbox, 0, np.float32(thr))
+        got = c_non_max_suppression_inds(dist, pts, 1, use_bbox, 0, np.float32(thr))
+        assert np.array_equal(got, want)
+
+
+def test_nms2d_empty_and_errors(sd):
+    from stardist_b200.lib.stardist2d import c_non_max_suppression_inds
+    out = c_non_max_suppression_inds(np.zeros((0, 32), np.float32), np.zeros((0, 2), np.float32), 1, 1, 0, np.float32(.4))
+    assert out.shape == (0,)
+    with pytest.raises(TypeError):
+        c_non_max_suppression_inds(np.zeros((2, 32)), np.zeros((2, 2), np.float32), 1, 1, 0, np.float32(.4))
+
+
+def test_dist_to_coord_bit_exact(sd):
+    rng = np.random.default_rng(0)
+    for R in (32, 11, 96):
+        dist = rng.uniform(0.001, 50, (500, R)).astype(np.float32)
+        pts = rng.integers(0, 4000, (500, 2))
+        got = sd.dist_to_coord(dist, pts)
+        want = geom2d_np.dist_to_coord(dist, pts)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.int32), want.view(np.int32))
+        got = sd.dist_to_coord(dist, pts * np.array([2.0, 0.5]), scale_dist=(2.0, 0.5))
+        want = geom2d_np.dist_to_coord(dist, pts * np.array([2.0, 0.5]), scale_dist=(2.0, 0.5))
+        assert np.array_equal(got.view(np.int32), want.view(np.int32))
+
+
+def test_polygons_to_label_bit_exact(sd):
+    rng = np.random.default_rng(1)
+    shape = (257, 301)
+    for R, n in ((32, 300), (8, 50), (64, 100)):
+        pts = rng.integers(-5, 310, (n, 2))
+        dist = (rng.uniform(2, 18, (n, 1)) * (1 + .3 * rng.uniform(-1, 1, (n, R)))).astype(np.float32)
+        prob = rng.uniform(0, 1, n).astype(np.float32)
+        prob[::7] = prob[3]           # ties
+        got = sd.polygons_to_label(dist, pts, shape, prob=prob)
+        want = geom2d_np.polygons_to_label(dist, pts, shape, prob=prob)
+        assert got.dtype == np.int32 and np.array_equal(got, want)
+    assert np.array_equal(sd.polygons_to_label(np.zeros((0, 32), np.float32), np.zeros((0, 2), int), shape),
+                          np.zeros(shape, np.int32))
+
+
+def test_threshold_sort_gather(sd):
+    import torch, ctypes
+    from stardist_b200 import _lib as L
+    lib = L.require_cuda()
+    rng = np.random.default_rng(2)
+    for shape, grid, b in (((130, 77), (1, 1), 2), ((64, 64), (2, 2), 2), ((9, 40, 33), (1, 2, 2), 2), ((50, 60), (1, 1), 0)):
+        nd = len(shape)
+        prob = rng.uniform(0, 1, shape).astype(np.float32)
+        prob.flat[::13] = prob.flat[5]       # ties
+        R = 5
+        dist = rng.uniform(-1, 10, shape + (R,)).astype(np.float32)
+        valid = tuple(s - 3 for s in shape)
+        pd = torch.from_numpy(prob).cuda(); dd = torch.from_numpy(dist).cuda()
+        npix = prob.size
+        sidx = torch.empty(npix, dtype=torch.int32, device='cuda'); sprob = torch.empty(npix, dtype=torch.float32, device='cuda')
+        cnt = ctypes.c_int(0)
+        L.check(lib.sdb_threshold_sort(L.ptr(pd), nd, L.iarr(shape), L.iarr(valid), L.iarr([b] * nd), L.iarr([b] * nd),
+                                      0.6, L.ptr(sidx), L.ptr(sprob), npix, ctypes.byref(cnt), L.stream_ptr()))
+        n = cnt.value
+        mask = nms_np._ind_prob_thresh(prob, np.float32(0.6), b=(b if b > 0 else None))
+        idx = np.stack(np.where(mask), 1)
+        ok = np.all(idx < np.array(valid), 1)
+        flat = np.ravel_multi_index(idx[ok].T, shape)
+        order = np.argsort(prob.ravel()[flat], kind='stable')[::-1]
+        want_idx = flat[order]
+        assert n == len(want_idx)
+        assert np.array_equal(sidx[:n].cpu().numpy(), want_idx)
+        assert np.array_equal(sprob[:n].cpu().numpy(), prob.ravel()[want_idx])
+        od = torch.empty((n, R), dtype=torch.float32, device='cuda'); op = torch.empty((n, nd), dtype=torch.float32, device='cuda')
+        L.check(lib.sdb_gather_candidates(L.ptr(dd), L.ptr(sidx), n, R, nd, L.iarr(shape), L.iarr(grid), L.ptr(od), L.ptr(op), L.stream_ptr()))
+        assert np.array_equal(od.cpu().numpy(), np.maximum(np.float32(1e-3), dist.reshape(-1, R)[want_idx]))
+        assert np.array_equal(op.cpu().numpy(), (np.stack(np.unravel_index(want_idx, shape), 1) * np.array(grid)).astype(np.float32))
+
+
+@pytest.mark.parametrize("shape,grid", [((64, 96), (1, 1)), ((48, 80), (2, 2))])
+def test_unet_forward_vs_torch_fp32(sd, shape, grid):
+    """float outputs: tolerance 1e-5 relative to the map's scale (north_star), vs torch-CPU fp32"""
+    import torch
+    cfg = sd.Config2D(n_rays=32, grid=grid)
+    model = sd.StarDist2D(cfg, name=None, basedir=None)
+    rng = np.random.default_rng(3)
+    img = rng.uniform(0, 1, shape).astype(np.float32)
+    x = torch.from_numpy(img[None, ..., None]).cuda()
+    prob, dist = model.net.forward(x)
+    rp, rd = unet_torch.forward(cfg, model.weights, img[None, ..., None])
+    p, d = prob.cpu().numpy(), dist.cpu().numpy()
+    assert p.shape == rp.shape and d.shape == rd.shape
+    assert np.max(np.abs(p - rp)) <= 1e-5 * max(1.0, np.max(np.abs(rp)))
+    assert np.max(np.abs(d - rd)) <= 1e-5 * max(1e-3, np.max(np.abs(rd))) + 1e-7
+
+
+@pytest.mark.parametrize("shape", [(96, 128), (101, 75)])
+def test_predict_instances_vs_oracle(sd, shape):
+    """whole pipeline: integer outputs bit-exact given the same network maps; also the reference
+    invariants dense == sparse (tests/test_model2D.py:442-449)"""
+    cfg = sd.Config2D(n_rays=32)
+    model = sd.StarDist2D(cfg, name=None, basedir=None)
+    rng = np.random.default_rng(4)
+    img = rng.uniform(0, 1, shape).astype(np.float32)
+    pthr = pipeline2d.quantile_prob_thresh(model, img, 0.95)
+    labels, res = model.predict_instances(img, prob_thresh=pthr, nms_thresh=0.3)
+    ref_labels, ref = pipeline2d.predict_instances(cfg, model.weights, img, pthr, 0.3, cand_from=model)
+    assert labels.shape == shape and len(res['prob']) > 3
+    assert np.array_equal(res['points'], ref['points'])
+    assert np.array_equal(res['prob'], ref['prob'])
+    assert np.array_equal(res['coord'].view(np.int32), ref['coord'].view(np.int32))
+    assert np.array_equal(labels, ref_labels)
+    if shape[0] % 8 == 0 and shape[1] % 8 == 0:
+        l2, r2 = model.predict_instances(img, prob_thresh=pthr, nms_thresh=0.3, sparse=False)
+        assert np.array_equal(labels, l2) and np.array_equal(res['points'], r2['points'])
