@@ -70,4 +70,48 @@ void sdref_clip_area_batch(const long long* a_xy, const long long* b_xy, int n_p
   }
 }
 
+// ---- 3D inner functions of the reference (stardist3d_impl.cpp), exposed unchanged ----------
+// polyverts* are (n_rays,3) float arrays as produced by polyhedron_polyverts (:570-585)
+void sdref_polyverts(const float* dist, const float* center, const float* verts, int n_rays, float* out) {
+  polyhedron_polyverts(dist, center, verts, n_rays, out);
+}
+float sdref_overlap_kernel(const float* pv1, const float* c1, const float* pv2, const float* c2,
+                           const int* faces, int n_rays, int n_faces) {
+  return qhull_overlap_kernel(pv1, c1, pv2, c2, faces, n_rays, n_faces);
+}
+float sdref_overlap_convex(const float* pv1, const float* c1, const float* pv2, const float* c2,
+                           const int* faces, int n_rays, int n_faces) {
+  return qhull_overlap_convex_hulls(pv1, c1, pv2, c2, faces, n_rays, n_faces);
+}
+void sdref_bbox(const float* dist, const float* center, const float* verts, int n_rays, int* bbox) {
+  polyhedron_bbox(dist, center, verts, n_rays, bbox);
+}
+float sdref_volume(const float* dist, const float* verts, const int* faces, int n_rays, int n_faces) {
+  return polyhedron_volume(dist, verts, faces, n_rays, n_faces);
+}
+// render polyhedron 1 into its bbox, then count overlap with polyhedron 2 (early exit like :608-636)
+int sdref_overlap_render(const float* dist1, const float* c1, const float* pv1,
+                         const float* dist2, const float* c2, const float* pv2,
+                         const float* verts, const int* faces, int n_rays, int n_faces, float overlap_maximal) {
+  int bbox[6];
+  polyhedron_bbox(dist1, c1, verts, n_rays, bbox);
+  int Nz = bbox[1]-bbox[0]+1, Ny = bbox[3]-bbox[2]+1, Nx = bbox[5]-bbox[4]+1;
+  bool* rendered = new bool[(size_t)Nz*Ny*Nx];
+  render_polyhedron(dist1, c1, bbox, pv1, faces, n_rays, n_faces, rendered, Nz, Ny, Nx);
+  int r = overlap_render_polyhedron(dist2, c2, bbox, pv2, faces, n_rays, n_faces, rendered, Nz, Ny, Nx, overlap_maximal);
+  delete[] rendered;
+  return r;
+}
+float sdref_sphere_iso(float r1, const float* p1, float r2, const float* p2, const float* aniso) {
+  return intersect_sphere_isotropic(r1, p1, r2, p2, aniso);
+}
+float sdref_bbox_inter(const int* b1, const int* b2) { return intersect_bbox(b1, b2); }
+float sdref_radius_outer_iso(const float* dist, const float* verts, int n_rays, const float* aniso) {
+  return bounding_radius_outer_isotropic(dist, verts, n_rays, aniso);
+}
+float sdref_radius_inner_iso(const float* dist, const float* verts, const int* faces, int n_rays, int n_faces, const float* aniso) {
+  return bounding_radius_inner_isotropic(dist, verts, faces, n_rays, n_faces, aniso);
+}
+float sdref_radius_outer(const float* dist, int n_rays) { return bounding_radius_outer(dist, n_rays); }
+
 } // extern "C"

@@ -63,3 +63,18 @@ int hc_clip_paths(const int32_t* a_xy, int na, const int32_t* b_xy, int nb,
 }
 
 }
+
+// ---------------------------------------------------------------- 3D geometry (geom3d.cuh)
+#include "../../stardist_b200/csrc/geom3d.cuh"
+#include "../../stardist_b200/csrc/nms3d_pair.cuh"
+
+extern "C" {
+float hc_overlap_kernel(const float* pv1, const float* c1, const float* pv2, const float* c2,
+                        const int* faces, int n_rays, int n_faces) {
+  return sd3::overlap_kernel_volume(pv1, c1, pv2, c2, faces, n_rays, n_faces);
+}
+float hc_overlap_convex(const float* pv1, const float* c1, const float* pv2, const float* c2,
+                        int n_rays) {
+  return sd3::overlap_convex_volume(pv1, c1, pv2, c2, n_rays);
+}
+}
