@@ -91,6 +91,19 @@ int sdb_dist_to_coord_2d(const float* d_dist, const double* d_points, int n_poly
                          const double* d_sincos, double scale_y, double scale_x,
                          float* d_coord, sdb_stream_t stream);
 
+/* 3D label painting on device arrays (see _LIB_polyhedron_to_label): polyhedra in painting order
+ * (descending probability, geom3d.py:176-180), first cover wins; d_labels[n_polys] must be non-zero. */
+int sdb_polyhedron_to_label(const float* d_dist, const float* d_points, const float* d_verts,
+                            const int* d_faces, int n_polys, int n_rays, int n_faces,
+                            const int* d_labels, int nz, int ny, int nx, int render_mode,
+                            int use_overlap_label, int overlap_label, int* d_result,
+                            sdb_stream_t stream);
+
+/* 3D NMS on device arrays (see _LIB_non_maximum_suppression_sparse); d_keep is uint8[n_polys]. */
+int sdb_nms3d(const float* d_dist, const float* d_points, const float* d_verts, const int* d_faces,
+              int n_polys, int n_rays, int n_faces, float threshold, int use_bbox, int use_kdtree,
+              int verbose, unsigned char* d_keep, sdb_stream_t stream);
+
 /* threshold + border mask + compaction + sort (nms.py:6-17, base.py:606-610, nms.py:167):
  * prob is [H*W] (2D) / [D*H*W] (3D) float32; candidates are pixels with prob > thresh that lie at
  * least b_lo/b_hi pixels inside along each axis and inside valid_* (un-padded) extents.

@@ -1,0 +1,216 @@
+// label3d.cu -- polyhedron_to_label on the GPU.
+//
+// Reference: stardist/lib/stardist3d_impl.cpp:1404-1525 (_COMMON_polyhedron_to_label), called from
+// stardist/geometry/geom3d.py:100-198 with polyhedra sorted by descending probability.  Per
+// polyhedron: integer bbox via lrint (:536-567), then every voxel of the (clipped) bbox is tested;
+// the first polyhedron that covers a voxel wins (`result==0 ? labels[i] : result`), or, with
+// use_overlap_label, every further cover writes overlap_label (:1508-1517).
+//
+// render_mode 0 "full":  inside = kernel(p) || (hull(p) && polyhedron(p))            (:1469-1476)
+//   kernel(p)     -- float-built face planes evaluated in double (build_halfspace / point_in_halfspaces)
+//   polyhedron(p) -- union of the (centre,A,B,C) tetrahedra, float determinants `det >= 0`
+//   hull(p)       -- Qhull facet planes of the vertices.  polyhedron(p) implies hull(p) geometrically
+//                    (every tetrahedron lies in the hull), so the hull test is only an accelerator in
+//                    the reference; it is dropped here.  A voxel can differ only if it lies on a hull
+//                    facet to within Qhull's last-bit rounding (lattice-aligned inputs), DESIGN.md.
+// render_mode 1 "kernel", 3 "bbox", 4 "debug" as in the reference; 2 "hull" uses gift-wrapped facets.
+//
+// "First cover wins" == per-voxel minimum over the polyhedron index -> atomicMin on a rank image,
+// then one pass maps ranks to labels (and overlaps to overlap_label).  Compile with -fmad=false.
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "geom3d.cuh"
+#include "nms3d_pair.cuh"
+#include "../../include/stardist_b200.h"
+
+namespace {
+
+using sdb::cdiv;
+constexpr int MAXR = sd3::SD3_MAX_RAYS, MAXF = sd3::SD3_MAX_FACES;
+constexpr int RANK_NONE = 0x7fffffff;
+
+struct PaintArgs {
+  const float* dist; const float* points; const float* verts; const int* faces;
+  int n_polys, n_rays, n_faces, nz, ny, nx, mode;
+};
+
+// render_mode 2 only: hull facet planes per polyhedron (one thread each; gift wrapping is serial)
+__global__ void k_hull3d(PaintArgs A, double* __restrict__ hull_planes, int* __restrict__ hull_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_polys) return;
+  double pts[3 * MAXR]; uint32_t ed[(MAXR * MAXR + 31) / 32]; int16_t st[3 * 4 * MAXR];
+  const float* d = A.dist + (size_t)i * A.n_rays;
+  for (int j = 0; j < A.n_rays; ++j)
+    for (int c = 0; c < 3; ++c) pts[3 * j + c] = (double)(A.points[3 * i + c] + d[j] * A.verts[3 * j + c]);
+  hull_count[i] = sd3::convex_hull_planes(pts, A.n_rays, reinterpret_cast<sd3::Plane*>(hull_planes + (size_t)i * 4 * A.n_faces),
+                                          A.n_faces, ed, st, 4 * MAXR);
+}
+
+// one block per polyhedron
+__global__ void __launch_bounds__(256)
+k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img, int* __restrict__ debug_img,
+          const double* __restrict__ hull_planes, const int* __restrict__ hull_count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* pv = reinterpret_cast<float*>(smem_raw);                         // [R][3]
+  int* sfaces = reinterpret_cast<int*>(pv + 3 * A.n_rays);                // [F][3]
+  double* hs = reinterpret_cast<double*>(smem_raw + ((3 * A.n_rays * 4 + 3 * A.n_faces * 4 + 15) / 16) * 16);   // [F][4] kernel planes / hull planes
+  __shared__ int bbox[6];
+  __shared__ float center[3];
+  __shared__ int n_hull;
+  const int i = blockIdx.x;
+  const float* d = A.dist + (size_t)i * A.n_rays;
+  if (threadIdx.x < 3) center[threadIdx.x] = A.points[3 * i + threadIdx.x];
+  __syncthreads();
+  for (int j = threadIdx.x; j < A.n_rays; j += blockDim.x) {
+    pv[3 * j] = center[0] + d[j] * A.verts[3 * j];
+    pv[3 * j + 1] = center[1] + d[j] * A.verts[3 * j + 1];
+    pv[3 * j + 2] = center[2] + d[j] * A.verts[3 * j + 2];
+  }
+  for (int j = threadIdx.x; j < 3 * A.n_faces; j += blockDim.x) sfaces[j] = A.faces[j];
+  if (threadIdx.x == 0) {
+    int z1 = INT32_MAX, z2 = -1, y1 = INT32_MAX, y2 = -1, x1 = INT32_MAX, x2 = -1;
+    for (int j = 0; j < A.n_rays; ++j) {
+      const int iz = sd3::round_to_int(center[0] + d[j] * A.verts[3 * j]);
+      const int iy = sd3::round_to_int(center[1] + d[j] * A.verts[3 * j + 1]);
+      const int ix = sd3::round_to_int(center[2] + d[j] * A.verts[3 * j + 2]);
+      z1 = min(z1, iz); z2 = max(z2, iz); y1 = min(y1, iy); y2 = max(y2, iy); x1 = min(x1, ix); x2 = max(x2, ix);
+    }
+    bbox[0] = max(0, z1); bbox[1] = min(A.nz - 1, z2); bbox[2] = max(0, y1); bbox[3] = min(A.ny - 1, y2);
+    bbox[4] = max(0, x1); bbox[5] = min(A.nx - 1, x2);
+    n_hull = 0;
+  }
+  __syncthreads();
+  if (A.mode == 2) {
+    // hull facets were computed by k_hull3d (rarely used render mode)
+    if (threadIdx.x == 0) n_hull = hull_count[i];
+    for (int f = threadIdx.x; f < 4 * A.n_faces; f += blockDim.x) hs[f] = hull_planes[(size_t)i * 4 * A.n_faces + f];
+  } else {
+    for (int f = threadIdx.x; f < A.n_faces; f += blockDim.x)
+      sd3::build_halfspace(&pv[3 * sfaces[3 * f]], &pv[3 * sfaces[3 * f + 1]], &pv[3 * sfaces[3 * f + 2]], &hs[4 * f]);
+  }
+  __syncthreads();
+  const int bz = bbox[1] - bbox[0] + 1, by = bbox[3] - bbox[2] + 1, bx = bbox[5] - bbox[4] + 1;
+  if (bz <= 0 || by <= 0 || bx <= 0) return;
+  const long long nvox = (long long)bz * by * bx;
+  for (long long q = threadIdx.x; q < nvox; q += blockDim.x) {
+    const int x = bbox[4] + (int)(q % bx), y = bbox[2] + (int)((q / bx) % by), z = bbox[0] + (int)(q / ((long long)bx * by));
+    const float fz = (float)z, fy = (float)y, fx = (float)x;
+    bool inside = false;
+    auto in_planes = [&](int cnt) {
+      for (int f = 0; f < cnt; ++f)
+        if (hs[4 * f] * fz + hs[4 * f + 1] * fy + hs[4 * f + 2] * fx + hs[4 * f + 3] > 0) return false;
+      return true;
+    };
+    if (A.mode == 0) inside = in_planes(A.n_faces) || sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces);
+    else if (A.mode == 1) inside = in_planes(A.n_faces);
+    else if (A.mode == 2) inside = (n_hull >= 4) && in_planes(n_hull);
+    else if (A.mode == 3) inside = true;
+    else {
+      // "debug": flag kernel && !polyhedron with -1, label nothing
+      bool ker = true;
+      for (int f = 0; f < A.n_faces && ker; ++f)
+        ker = sd3::inside_halfspace(fz, fy, fx, pv[3 * sfaces[3 * f]], pv[3 * sfaces[3 * f] + 1], pv[3 * sfaces[3 * f] + 2],
+                                    pv[3 * sfaces[3 * f + 1]], pv[3 * sfaces[3 * f + 1] + 1], pv[3 * sfaces[3 * f + 1] + 2],
+                                    pv[3 * sfaces[3 * f + 2]], pv[3 * sfaces[3 * f + 2] + 1], pv[3 * sfaces[3 * f + 2] + 2]);
+      if (ker && !sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces))
+        debug_img[((size_t)z * A.ny + y) * A.nx + x] = 1;
+      continue;
+    }
+    if (inside) {
+      const size_t off = ((size_t)z * A.ny + y) * A.nx + x;
+      const int old = atomicMin(&rank_img[off], i);
+      if (second_img) {
+        // track the second smallest covering index as well (needed for labels==0 corner cases and
+        // overlap_label): second = min over covers excluding the minimum
+        const int loser = max(old, i);
+        if (old != i && loser != RANK_NONE) atomicMin(&second_img[off], loser);
+      }
+    }
+  }
+}
+
+__global__ void k_finalize3d(int* __restrict__ out, const int* __restrict__ rank_img, const int* __restrict__ second_img,
+                             const int* __restrict__ debug_img, long long nvox, const int* __restrict__ labels,
+                             int use_overlap, int overlap_label, int mode) {
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (long long)gridDim.x * blockDim.x) {
+    if (mode == 4) { out[v] = debug_img[v] ? -1 : 0; continue; }
+    const int r = rank_img[v];
+    int val = 0;
+    if (r != RANK_NONE) {
+      val = labels[r];
+      if (use_overlap && second_img[v] != RANK_NONE) val = overlap_label;
+    }
+    out[v] = val;
+  }
+}
+
+__global__ void k_fill(int* p, long long n, int v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace
+
+extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_points, const float* d_verts,
+                                       const int* d_faces, int n_polys, int n_rays, int n_faces,
+                                       const int* d_labels, int nz, int ny, int nx, int render_mode,
+                                       int use_overlap_label, int overlap_label, int* d_result,
+                                       sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_rays > MAXR || n_faces > MAXF) { sdb::set_error("polyhedron_to_label: too many rays/faces"); return 1; }
+  if (render_mode < 0 || render_mode > 4) { sdb::set_error("polyhedron_to_label: unknown render mode"); return 1; }
+  const long long nvox = (long long)nz * ny * nx;
+  const int fb = (int)std::min<long long>(cdiv(nvox, 256), 148 * 16);
+  if (nvox == 0) return 0;
+  sdb::DevBuf b_rank, b_second, b_debug;
+  SDB_CUDA(b_rank.alloc((size_t)nvox * sizeof(int), st));
+  SDB_LAUNCH(k_fill, fb, 256, 0, st, b_rank.as<int>(), nvox, RANK_NONE);
+  if (use_overlap_label) {
+    SDB_CUDA(b_second.alloc((size_t)nvox * sizeof(int), st));
+    SDB_LAUNCH(k_fill, fb, 256, 0, st, b_second.as<int>(), nvox, RANK_NONE);
+  }
+  if (render_mode == 4) {
+    SDB_CUDA(b_debug.alloc((size_t)nvox * sizeof(int), st));
+    SDB_CUDA(cudaMemsetAsync(b_debug.p, 0, (size_t)nvox * sizeof(int), st));
+  }
+  if (n_polys > 0) {
+    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode};
+    const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double);
+    sdb::DevBuf b_hull, b_hcnt;
+    if (render_mode == 2) {
+      SDB_CUDA(b_hull.alloc((size_t)n_polys * n_faces * 4 * sizeof(double), st));
+      SDB_CUDA(b_hcnt.alloc((size_t)n_polys * sizeof(int), st));
+      SDB_LAUNCH(k_hull3d, cdiv(n_polys, 32), 32, 0, st, A, b_hull.as<double>(), b_hcnt.as<int>());
+    }
+    SDB_LAUNCH(k_paint3d, n_polys, 256, smem, st, A, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
+               render_mode == 4 ? b_debug.as<int>() : nullptr, b_hull.as<double>(), b_hcnt.as<int>());
+  }
+  SDB_LAUNCH(k_finalize3d, fb, 256, 0, st, d_result, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
+             render_mode == 4 ? b_debug.as<int>() : nullptr, nvox, d_labels, use_overlap_label, overlap_label, render_mode);
+  return 0;
+}
+
+// reference C ABI (stardist3d_lib.h:67-82): host pointers, result int32[nz*ny*nx] zero-initialised by the caller
+extern "C" void _LIB_polyhedron_to_label(const float* dist, const float* points, const float* verts, const int* faces,
+                                         const int n_polys, const int n_rays, const int n_faces, const int* labels,
+                                         const int nz, const int ny, const int nx, const int render_mode,
+                                         const int verbose, const int use_overlap_label, const int overlap_label,
+                                         int* result) {
+  auto fail = [&](const char* what) { fprintf(stderr, "stardist_b200: _LIB_polyhedron_to_label failed: %s: %s\n", what, sdb_last_error()); abort(); };
+  cudaStream_t st = 0;
+  sdb::DevBuf d_dist, d_points, d_verts, d_faces, d_labels, d_out;
+  const long long nvox = (long long)nz * ny * nx;
+  if (d_dist.alloc((size_t)n_polys * n_rays * 4, st) || d_points.alloc((size_t)n_polys * 12, st) || d_verts.alloc((size_t)n_rays * 12, st) ||
+      d_faces.alloc((size_t)n_faces * 12, st) || d_labels.alloc((size_t)n_polys * 4, st) || d_out.alloc((size_t)nvox * 4, st)) fail("alloc");
+  if (n_polys > 0) {
+    cudaMemcpyAsync(d_dist.p, dist, (size_t)n_polys * n_rays * 4, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_points.p, points, (size_t)n_polys * 12, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_labels.p, labels, (size_t)n_polys * 4, cudaMemcpyHostToDevice, st);
+  }
+  cudaMemcpyAsync(d_verts.p, verts, (size_t)n_rays * 12, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_faces.p, faces, (size_t)n_faces * 12, cudaMemcpyHostToDevice, st);
+  if (verbose >= 1) printf("+++++++++++++++ polyhedra to label (B200) +++++++++++++++ \nn_polys = %d n_rays = %d n_faces = %d nz,ny,nx = %d %d %d\n", n_polys, n_rays, n_faces, nz, ny, nx);
+  if (sdb_polyhedron_to_label(d_dist.as<float>(), d_points.as<float>(), d_verts.as<float>(), d_faces.as<int>(), n_polys, n_rays, n_faces,
+                              d_labels.as<int>(), nz, ny, nx, render_mode, use_overlap_label, overlap_label, d_out.as<int>(), (sdb_stream_t)st)) fail("kernel");
+  if (cudaMemcpyAsync(result, d_out.p, (size_t)nvox * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("copy back");
+}

@@ -1,0 +1,602 @@
+// nms3d.cu -- star-convex polyhedron non-maximum suppression on the GPU.
+//
+// Reference: stardist/lib/stardist3d_impl.cpp:956-1385 (_COMMON_non_maximum_suppression_sparse):
+//   precompute per candidate: volume (:257), integer bbox (:536), anisotropy = running float sum of
+//   bbox extents / n (:1007-1010, summed here in index order == the OMP_NUM_THREADS=1 result),
+//   outer / inner (isotropic) bounding radii (:1032-1052); kd-tree radius (max_dist + r_outer_i)^2;
+//   greedy loop in score order; for every candidate pair the cascade (:1192-1334)
+//     S1 upper bound  min(sphere_outer ∩, bbox ∩)        -> keep   if iou <= thr (use_bbox)
+//     S2 lower bound  sphere_inner ∩                      -> suppress if iou > thr
+//     S3 kernel ∩ kernel (Qhull halfspace intersection)   -> suppress if iou > thr
+//     S4 hull ∩ hull                                      -> keep   if iou <= thr
+//     S5 voxel render of i, count voxels also inside j    -> suppress if iou > thr   (early exit)
+// Every stage is a pure function of the pair, so the greedy loop is resolved by the same
+// frontier peeling as the 2D NMS (nms2d.cu): per round K_frontier, K_pretest (S1,S2 per candidate,
+// emits the surviving pairs), K_heavy (one CTA per emitted pair: S3, S4, S5).
+// S3/S4: geom3d.cuh (Q) -- Qhull-free, float-bit-equal on all fuzzed pairs (tests/tools/qhull_fuzz.py).
+// S5 early exit is emulated on the full count: res = min(full, floor(overlap_maximal)+1).
+// Compile with -fmad=false.
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "common.cuh"
+#include "geom3d.cuh"
+#include "nms3d_pair.cuh"
+#include "../../include/stardist_b200.h"
+
+namespace {
+
+using sdb::cdiv;
+using sd3::Plane;
+
+enum { ST_UNDECIDED = 0, ST_SUPPRESSED = 1, ST_KEPT_BASE = 2 };
+constexpr int MAXR = sd3::SD3_MAX_RAYS, MAXF = sd3::SD3_MAX_FACES;
+
+struct Grid3 { float mn[3]; float cell; int g[3]; int all_pairs; };
+
+struct Arr {
+  const float* dist; const float* points; const float* verts; const int* faces;
+  int n, R, F;
+  float* volume; int* bbox; float* r_outer; float* r_outer_iso; float* r_inner_iso;
+  float* aniso_terms;    // [3][n]
+  float* aniso;          // [3]
+  const unsigned int* cell_start; const int* items; int* state;
+  float max_dist, threshold; int use_bbox;
+  Grid3 G;
+};
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_pre1(Arr A, unsigned int* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const float* d = A.dist + (size_t)i * A.R;
+  const float* c = A.points + 3 * i;
+  A.volume[i] = sd3::polyhedron_volume(d, A.verts, A.faces, A.F);
+  int bb[6];
+  sd3::polyhedron_bbox(d, c, A.verts, A.R, bb);
+  for (int k = 0; k < 6; ++k) A.bbox[6 * i + k] = bb[k];
+  // anisotropy[k] += (float)(bbox extent) / n_polys   -- the terms; summed serially by k_aniso
+  A.aniso_terms[i] = (float)(bb[1] - bb[0]) / A.n;
+  A.aniso_terms[A.n + i] = (float)(bb[3] - bb[2]) / A.n;
+  A.aniso_terms[2 * A.n + i] = (float)(bb[5] - bb[4]) / A.n;
+  const float ro = sd3::bounding_radius_outer(d, A.R);
+  A.r_outer[i] = ro;
+  atomicMax(&stats[0], __float_as_uint(ro));
+  for (int k = 0; k < 3; ++k) {
+    const float v = fminf(fmaxf(c[k], -1.0e9f), 1.0e9f);
+    atomicMin((int*)&stats[1 + 2 * k], (int)floorf(v)); atomicMax((int*)&stats[2 + 2 * k], (int)floorf(v));
+  }
+}
+
+// serial float accumulation in index order (one warp per axis stages 32 terms at a time)
+__global__ void k_aniso(Arr A) {
+  const int axis = blockIdx.x;
+  const float* t = A.aniso_terms + (size_t)axis * A.n;
+  __shared__ float buf[1024];
+  float acc = 0.f;
+  for (int base = 0; base < A.n; base += 1024) {
+    const int m = min(1024, A.n - base);
+    for (int k = threadIdx.x; k < m; k += blockDim.x) buf[k] = t[base + k];
+    __syncthreads();
+    if (threadIdx.x == 0) for (int k = 0; k < m; ++k) acc = acc + buf[k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) A.aniso[axis] = acc;
+}
+__global__ void k_aniso_norm(Arr A) {
+  // _tmp = fmax(fmax(a0,a1),a2); a_k = _tmp / a_k     (:1020-1023)
+  const float a0 = A.aniso[0], a1 = A.aniso[1], a2 = A.aniso[2];
+  const float tmp = fmaxf(fmaxf(a0, a1), a2);
+  A.aniso[0] = tmp / a0; A.aniso[1] = tmp / a1; A.aniso[2] = tmp / a2;
+}
+__global__ void k_pre2(Arr A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const float* d = A.dist + (size_t)i * A.R;
+  const float an[3] = {A.aniso[0], A.aniso[1], A.aniso[2]};
+  A.r_outer_iso[i] = sd3::bounding_radius_outer_isotropic(d, A.verts, A.R, an);
+  A.r_inner_iso[i] = sd3::bounding_radius_inner_isotropic(d, A.verts, A.faces, A.F, an);
+}
+
+// ---- uniform grid (same scheme as nms2d.cu) ------------------------------------------------
+__device__ __forceinline__ int cell_of(float v, float mn, float cell, int g) {
+  int c = (int)((v - mn) / cell);
+  return c < 0 ? 0 : (c >= g ? g - 1 : c);
+}
+__device__ __forceinline__ int cell_index(const Grid3& G, const float* p) {
+  if (G.all_pairs) return 0;
+  return (cell_of(p[0], G.mn[0], G.cell, G.g[0]) * G.g[1] + cell_of(p[1], G.mn[1], G.cell, G.g[1])) * G.g[2] +
+         cell_of(p[2], G.mn[2], G.cell, G.g[2]);
+}
+__global__ void k_cell_count(const float* __restrict__ points, int n, Grid3 G, int* __restrict__ cell_of_pt, unsigned int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cell_index(G, points + 3 * i);
+  cell_of_pt[i] = c;
+  atomicAdd(&counts[c], 1u);
+}
+__global__ void k_scan_serial(const unsigned int* __restrict__ counts, unsigned int* __restrict__ start, int n_cells) {
+  // single block: chunked Hillis-Steele scan with carry
+  __shared__ unsigned int sh[1024];
+  __shared__ unsigned int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base <= n_cells; base += 1024) {
+    const int i = base + threadIdx.x;
+    const unsigned int v = (i < n_cells) ? counts[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const unsigned int t = (threadIdx.x >= off) ? sh[threadIdx.x - off] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i <= n_cells) start[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+}
+__global__ void k_cell_fill(const int* __restrict__ cell_of_pt, int n, unsigned int* __restrict__ cursor, int* __restrict__ items) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  items[atomicAdd(&cursor[cell_of_pt[i]], 1u)] = i;
+}
+
+// would h (higher score) test c ?  kd-tree radius query (:1169-1171), strict <
+__device__ __forceinline__ bool reaches(const Arr& A, int h, const float* pc) {
+  if (A.G.all_pairs) return true;
+  const float* ph = A.points + 3 * h;
+  const float d0 = ph[0] - pc[0], d1 = ph[1] - pc[1], d2 = ph[2] - pc[2];
+  const float dd = d0 * d0 + d1 * d1 + d2 * d2;
+  const float rr = A.max_dist + A.r_outer[h];
+  return dd < rr * rr;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_neighbors(const Arr& A, int c, F&& f) {
+  const float* pc = A.points + 3 * c;
+  int cz = 0, cy = 0, cx = 0;
+  if (!A.G.all_pairs) {
+    cz = cell_of(pc[0], A.G.mn[0], A.G.cell, A.G.g[0]); cy = cell_of(pc[1], A.G.mn[1], A.G.cell, A.G.g[1]);
+    cx = cell_of(pc[2], A.G.mn[2], A.G.cell, A.G.g[2]);
+  }
+  for (int zz = max(cz - 1, 0); zz <= min(cz + 1, A.G.g[0] - 1); ++zz)
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, A.G.g[1] - 1); ++yy)
+      for (int xx = max(cx - 1, 0); xx <= min(cx + 1, A.G.g[2] - 1); ++xx) {
+        const int cell = (zz * A.G.g[1] + yy) * A.G.g[2] + xx;
+        const unsigned int e = A.cell_start[cell + 1];
+        for (unsigned int t = A.cell_start[cell]; t < e; ++t) {
+          const int h = A.items[t];
+          if (h >= c) continue;
+          if (!f(h, pc)) return;
+        }
+      }
+}
+
+__global__ void k_frontier(Arr A, int round, unsigned int* __restrict__ counters) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= A.n) return;
+  if (A.state[c] != ST_UNDECIDED) return;
+  atomicAdd(&counters[0], 1u);
+  const int kept_now = ST_KEPT_BASE + round;
+  bool blocked = false;
+  for_neighbors(A, c, [&](int h, const float* pc) {
+    const int sh = A.state[h];
+    if (sh != ST_UNDECIDED && sh != kept_now) return true;
+    if (reaches(A, h, pc)) { blocked = true; return false; }
+    return true;
+  });
+  if (!blocked) A.state[c] = kept_now;
+}
+
+// S1 + S2 for every (kept-now h, undecided c); emits pairs that need the heavy stages
+__global__ void k_pretest(Arr A, int round, int2* __restrict__ pairs, unsigned int pair_cap, unsigned int* __restrict__ counters) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= A.n) return;
+  if (A.state[c] != ST_UNDECIDED) return;
+  const int kept_now = ST_KEPT_BASE + round;
+  const float an[3] = {A.aniso[0], A.aniso[1], A.aniso[2]};
+  for_neighbors(A, c, [&](int h, const float* pc) {
+    if (A.state[h] != kept_now) return true;
+    if (!reaches(A, h, pc)) return true;
+    atomicAdd(&counters[4], 1u);
+    const float A_min = fminf(A.volume[h], A.volume[c]);
+    // S1 (:1213-1228)
+    float A_inter = fminf(sd3::intersect_sphere_isotropic(A.r_outer_iso[h], A.points + 3 * h, A.r_outer_iso[c], pc, an),
+                          sd3::intersect_bbox(A.bbox + 6 * h, A.bbox + 6 * c));
+    float iou = (float)fmin(1.0, (double)A_inter / ((double)A_min + 1e-10));
+    if (A.use_bbox && (((double)A_inter < 1.e-10) || (iou <= A.threshold))) return true;
+    // S2 (:1232-1248)
+    A_inter = sd3::intersect_sphere_isotropic(A.r_inner_iso[h], A.points + 3 * h, A.r_inner_iso[c], pc, an);
+    iou = (float)fmax(0.0, (double)A_inter / ((double)A_min + 1e-10));
+    if (iou > A.threshold) { A.state[c] = ST_SUPPRESSED; return false; }
+    const unsigned int k = atomicAdd(&counters[1], 1u);
+    if (k < pair_cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
+    return true;
+  });
+}
+
+// ---- heavy stages: one CTA (128 threads) per pair ------------------------------------------
+struct PlaneAt { const Plane* p; __device__ Plane operator()(int i) const { return p[i]; } };
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  double s = 0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+  return s;
+}
+
+// warp-cooperative gift wrapping pivot: lanes scan the points, then a shuffle tournament
+__device__ int warp_pivot(const double* pts, int n, int a, int b, int skip) {
+  const int lane = threadIdx.x & 31;
+  auto orient = [&](int p, int q, int r, int s) -> double {
+    const double b0 = pts[3 * q] - pts[3 * p], b1 = pts[3 * q + 1] - pts[3 * p + 1], b2 = pts[3 * q + 2] - pts[3 * p + 2];
+    const double c0 = pts[3 * r] - pts[3 * p], c1 = pts[3 * r + 1] - pts[3 * p + 1], c2 = pts[3 * r + 2] - pts[3 * p + 2];
+    const double d0 = pts[3 * s] - pts[3 * p], d1 = pts[3 * s + 1] - pts[3 * p + 1], d2 = pts[3 * s + 2] - pts[3 * p + 2];
+    return d0 * (b1 * c2 - b2 * c1) + d1 * (b2 * c0 - b0 * c2) + d2 * (b0 * c1 - b1 * c0);
+  };
+  int q = -1;
+  for (int r = lane; r < n; r += 32) {
+    if (r == a || r == b || r == skip) continue;
+    if (q < 0) { q = r; continue; }
+    if (orient(a, b, q, r) > 0) q = r;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const int other = __shfl_xor_sync(0xffffffffu, q, o);
+    int best = q;
+    if (q < 0) best = other;
+    else if (other >= 0 && other != q) {
+      // deterministic tournament: both lanes evaluate the same comparison
+      const int lo = min(q, other), hi = max(q, other);
+      best = (orient(a, b, lo, hi) > 0) ? hi : lo;
+    }
+    q = best;
+  }
+  return q;
+}
+
+// hull facet planes by warp 0 (other warps idle); identical facet set to sd3::convex_hull_planes up to order
+__device__ int hull_planes_warp(const double* pts, int n, Plane* out, int max_planes, uint32_t* edge_done, int16_t* stack, int max_stack) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < (n * n + 31) / 32; i += 32) edge_done[i] = 0;
+  __syncwarp();
+  // start edge (serial scan by every lane redundantly: cheap, n <= 256)
+  int p0 = 0;
+  for (int i = 1; i < n; ++i)
+    if (pts[3 * i] < pts[3 * p0] || (pts[3 * i] == pts[3 * p0] && (pts[3 * i + 1] < pts[3 * p0 + 1] ||
+        (pts[3 * i + 1] == pts[3 * p0 + 1] && pts[3 * i + 2] < pts[3 * p0 + 2])))) p0 = i;
+  int p1 = -1;
+  for (int i = 0; i < n; ++i) {
+    if (i == p0) continue;
+    if (p1 < 0) { p1 = i; continue; }
+    const double ax = pts[3 * p1] - pts[3 * p0], ay = pts[3 * p1 + 1] - pts[3 * p0 + 1];
+    const double bx = pts[3 * i] - pts[3 * p0], by = pts[3 * i + 1] - pts[3 * p0 + 1];
+    const double cr = ax * by - ay * bx;
+    if (cr < 0 || (cr == 0 && (bx * bx + by * by) > (ax * ax + ay * ay))) p1 = i;
+  }
+  if (p1 < 0) return -1;
+  int p2 = warp_pivot(pts, n, p0, p1, -1);
+  if (p2 < 0) return -1;
+  int nf = 0, sp = 0;
+  auto done = [&](int a, int b) -> bool { const int e = a * n + b; return (edge_done[e >> 5] >> (e & 31)) & 1u; };
+  auto emit = [&](int a, int b, int c) -> bool {
+    if (nf >= max_planes) return false;
+    if (lane == 0) {
+      const double b0 = pts[3 * b] - pts[3 * a], b1 = pts[3 * b + 1] - pts[3 * a + 1], b2 = pts[3 * b + 2] - pts[3 * a + 2];
+      const double c0 = pts[3 * c] - pts[3 * a], c1 = pts[3 * c + 1] - pts[3 * a + 1], c2 = pts[3 * c + 2] - pts[3 * a + 2];
+      double n0 = b1 * c2 - b2 * c1, n1 = b2 * c0 - b0 * c2, n2 = b0 * c1 - b1 * c0;
+      const double l = sqrt(n0 * n0 + n1 * n1 + n2 * n2);
+      if (l > 0) { n0 /= l; n1 /= l; n2 /= l; }
+      Plane P; P.n0 = n0; P.n1 = n1; P.n2 = n2; P.d = -(n0 * pts[3 * a] + n1 * pts[3 * a + 1] + n2 * pts[3 * a + 2]);
+      out[nf] = P;
+      int e;
+      e = a * n + b; edge_done[e >> 5] |= (1u << (e & 31));
+      e = b * n + c; edge_done[e >> 5] |= (1u << (e & 31));
+      e = c * n + a; edge_done[e >> 5] |= (1u << (e & 31));
+    }
+    nf++;
+    __syncwarp();
+    return true;
+  };
+  auto push = [&](int a, int b, int c) {
+    if (sp < max_stack) { if (lane == 0) { stack[3 * sp] = (int16_t)a; stack[3 * sp + 1] = (int16_t)b; stack[3 * sp + 2] = (int16_t)c; } sp++; }
+  };
+  if (!emit(p0, p1, p2)) return -1;
+  push(p1, p0, p2); push(p2, p1, p0); push(p0, p2, p1);
+  __syncwarp();
+  int guard = 0;
+  while (sp > 0) {
+    if (++guard > 16 * n + 64) return -1;
+    --sp;
+    const int a = stack[3 * sp], b = stack[3 * sp + 1], opp = stack[3 * sp + 2];
+    __syncwarp();
+    if (done(a, b)) continue;
+    const int q = warp_pivot(pts, n, a, b, opp);
+    if (q < 0) return -1;
+    if (!emit(a, b, q)) return -1;
+    if (!done(q, b)) push(q, b, a);
+    if (!done(a, q)) push(a, q, b);
+    __syncwarp();
+  }
+  return nf;
+}
+
+__global__ void __launch_bounds__(128)
+k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counters, unsigned int pair_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned int n_pairs = min(counters[1], pair_cap);
+  float* pv1 = reinterpret_cast<float*>(smem_raw);                 // [R][3]
+  float* pv2 = pv1 + 3 * A.R;
+  int* sfaces = reinterpret_cast<int*>(pv2 + 3 * A.R);             // [F][3]
+  size_t off = ((size_t)(6 * A.R + 3 * A.F) * 4 + 15) / 16 * 16;
+  Plane* planes = reinterpret_cast<Plane*>(smem_raw + off);        // [2F]
+  off += (size_t)2 * A.F * sizeof(Plane);
+  double* pts = reinterpret_cast<double*>(smem_raw + off);         // [R][3] (hull stage)
+  off += (size_t)3 * A.R * sizeof(double);
+  uint32_t* edge_done = reinterpret_cast<uint32_t*>(smem_raw + off);
+  off += (size_t)((A.R * A.R + 31) / 32) * 4;
+  int16_t* stack = reinterpret_cast<int16_t*>(smem_raw + off);     // [3*4R]
+  __shared__ double red[4];
+  __shared__ int sh_i[4];
+  __shared__ float c1[3], c2[3];
+  for (int j = threadIdx.x; j < 3 * A.F; j += blockDim.x) sfaces[j] = A.faces[j];
+
+  for (unsigned int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+    const int h = pairs[pi].x, c = pairs[pi].y;
+    __syncthreads();
+    if (threadIdx.x == 0) sh_i[2] = A.state[c];
+    __syncthreads();
+    if (sh_i[2] == ST_SUPPRESSED) continue;             // another pair already suppressed c (uniform per block)
+    if (threadIdx.x < 3) { c1[threadIdx.x] = A.points[3 * h + threadIdx.x]; c2[threadIdx.x] = A.points[3 * c + threadIdx.x]; }
+    __syncthreads();
+    const float* d1 = A.dist + (size_t)h * A.R; const float* d2 = A.dist + (size_t)c * A.R;
+    for (int j = threadIdx.x; j < A.R; j += blockDim.x)
+      for (int k = 0; k < 3; ++k) {
+        pv1[3 * j + k] = c1[k] + d1[j] * A.verts[3 * j + k];
+        pv2[3 * j + k] = c2[k] + d2[j] * A.verts[3 * j + k];
+      }
+    __syncthreads();
+    const float A_min = fminf(A.volume[h], A.volume[c]);
+    const double den = (double)A_min + 1e-10;
+    atomicAdd(&counters[5], threadIdx.x == 0 ? 1u : 0u);
+
+    // ---- S3: kernel ∩ kernel (:1261-1277) ------------------------------------------------
+    for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
+      double hs[4];
+      sd3::build_halfspace(&pv1[3 * sfaces[3 * f]], &pv1[3 * sfaces[3 * f + 1]], &pv1[3 * sfaces[3 * f + 2]], hs);
+      Plane P; P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f] = P;
+      sd3::build_halfspace(&pv2[3 * sfaces[3 * f]], &pv2[3 * sfaces[3 * f + 1]], &pv2[3 * sfaces[3 * f + 2]], hs);
+      P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f + 1] = P;
+    }
+    __syncthreads();
+    double p[3];
+    for (int k = 0; k < 3; ++k) p[k] = .5 * (double)(c1[k] + c2[k]);
+    int np = 2 * A.F;
+    int infeasible = 0;
+    for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) infeasible = 1;
+    infeasible = __syncthreads_or(infeasible);
+    float vol_kernel = 0.f;
+    double L = 0;
+    {
+      double m = 0;
+      for (int k = threadIdx.x; k < 3 * A.R; k += blockDim.x) {
+        m = fmax(m, fabs((double)pv1[k] - p[k % 3])); m = fmax(m, fabs((double)pv2[k] - p[k % 3]));
+      }
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+      __syncthreads();
+      m = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+      L = 4.0 * m + 1.0;
+    }
+    if (!infeasible) {
+      PlaneAt PA{planes};
+      double part = 0; int ovf = 0;
+      for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+      vol_kernel = (float)block_sum(part, red);     // NOTE: summation order differs from the serial host version (ulp-level in double)
+    }
+    float iou = (float)((double)vol_kernel / den);
+    if (iou > A.threshold) { if (threadIdx.x == 0) A.state[c] = ST_SUPPRESSED; continue; }
+
+    // ---- S4: hull ∩ hull (:1282-1295) -----------------------------------------------------
+    atomicAdd(&counters[6], threadIdx.x == 0 ? 1u : 0u);
+    float vol_convex = 1.e10f;
+    {
+      int n1 = -1, n2 = -1;
+      __syncthreads();
+      for (int k = threadIdx.x; k < 3 * A.R; k += blockDim.x) pts[k] = (double)pv1[k];
+      __syncthreads();
+      if (threadIdx.x < 32) { n1 = hull_planes_warp(pts, A.R, planes, A.F, edge_done, stack, 4 * A.R); if (threadIdx.x == 0) sh_i[0] = n1; }
+      __syncthreads();
+      n1 = sh_i[0];
+      if (n1 >= 4) {
+        for (int k = threadIdx.x; k < 3 * A.R; k += blockDim.x) pts[k] = (double)pv2[k];
+        __syncthreads();
+        if (threadIdx.x < 32) { n2 = hull_planes_warp(pts, A.R, planes + n1, A.F, edge_done, stack, 4 * A.R); if (threadIdx.x == 0) sh_i[1] = n2; }
+        __syncthreads();
+        n2 = sh_i[1];
+      }
+      if (n1 >= 4 && n2 >= 4) {
+        np = n1 + n2;
+        for (int k = 0; k < 3; ++k) p[k] = .5 * ((double)c1[k] + (double)c2[k]);
+        int inf2 = 0;
+        for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) inf2 = 1;
+        inf2 = __syncthreads_or(inf2);
+        if (!inf2) {
+          PlaneAt PA{planes};
+          double part = 0; int ovf = 0;
+          for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+          vol_convex = (float)block_sum(part, red);
+        }
+      }
+    }
+    iou = (float)((double)vol_convex / den);
+    if (iou <= A.threshold) continue;
+
+    // ---- S5: rendered overlap inside bbox(h) (:1305-1330) ------------------------------------
+    atomicAdd(&counters[7], threadIdx.x == 0 ? 1u : 0u);
+    const int* bb = A.bbox + 6 * h;
+    const int Nz = bb[1] - bb[0] + 1, Ny = bb[3] - bb[2] + 1, Nx = bb[5] - bb[4] + 1;
+    const long long nv = (long long)Nz * Ny * Nx;
+    const float overlap_maximal = (float)(den * (double)A.threshold);      // (A_min+1e-10)*threshold passed as float
+    int cnt = 0;
+    int first_hit = 0;
+    for (long long q = threadIdx.x; q < nv; q += blockDim.x) {
+      const int x = (int)(q % Nx), y = (int)((q / Nx) % Ny), z = (int)(q / ((long long)Nx * Ny));
+      const float fz = (float)(z + bb[0]), fy = (float)(y + bb[2]), fx = (float)(x + bb[4]);
+      if (sd3::inside_polyhedron(fz, fy, fx, c1, pv1, sfaces, A.F) && sd3::inside_polyhedron(fz, fy, fx, c2, pv2, sfaces, A.F)) {
+        cnt++; if (q == 0) first_hit = 1;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh_i[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int full = sh_i[0] + sh_i[1] + sh_i[2] + sh_i[3];
+      // early exit emulation: the serial loop returns the first running count with (float)res > overlap_maximal
+      int res;
+      if (overlap_maximal < 0.f) res = (nv > 0) ? first_hit : 0;
+      else {
+        const long long stop = (long long)floorf(overlap_maximal) + 1;      // smallest integer > overlap_maximal
+        res = (full >= stop) ? (int)stop : full;
+      }
+      const float A_inter_render = (float)res;
+      const float iou5 = (float)((double)A_inter_render / den);
+      if (iou5 > A.threshold) A.state[c] = ST_SUPPRESSED;
+    }
+  }
+}
+
+__global__ void k_reset(unsigned int* counters) { if (threadIdx.x < 2) counters[threadIdx.x] = 0; }
+__global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = (state[i] != ST_SUPPRESSED) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float* d_verts, const int* d_faces,
+                         int n_polys, int n_rays, int n_faces, float threshold, int use_bbox, int use_kdtree,
+                         int verbose, unsigned char* d_keep, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = n_polys;
+  if (n <= 0) return 0;
+  if (n_rays < 4 || n_rays > MAXR || n_faces > MAXF || n_faces < 1) { sdb::set_error("nms3d: unsupported n_rays / n_faces"); return 1; }
+  sdb::DevBuf b_vol, b_bbox, b_ro, b_roi, b_rii, b_terms, b_aniso, b_stats, b_cellpt, b_counts, b_start, b_items, b_state, b_pairs, b_counters;
+  SDB_CUDA(b_vol.alloc((size_t)n * 4, st)); SDB_CUDA(b_bbox.alloc((size_t)n * 24, st)); SDB_CUDA(b_ro.alloc((size_t)n * 4, st));
+  SDB_CUDA(b_roi.alloc((size_t)n * 4, st)); SDB_CUDA(b_rii.alloc((size_t)n * 4, st)); SDB_CUDA(b_terms.alloc((size_t)n * 12, st));
+  SDB_CUDA(b_aniso.alloc(16, st)); SDB_CUDA(b_stats.alloc(32, st)); SDB_CUDA(b_state.alloc((size_t)n * 4, st));
+  SDB_CUDA(b_counters.alloc(32, st));
+  const int init_stats[8] = {0, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0};
+  SDB_CUDA(cudaMemcpyAsync(b_stats.p, init_stats, sizeof(init_stats), cudaMemcpyHostToDevice, st));
+  SDB_CUDA(cudaMemsetAsync(b_state.p, 0, (size_t)n * 4, st));
+  SDB_CUDA(cudaMemsetAsync(b_counters.p, 0, 32, st));
+  Arr A;
+  A.dist = d_dist; A.points = d_points; A.verts = d_verts; A.faces = d_faces; A.n = n; A.R = n_rays; A.F = n_faces;
+  A.volume = b_vol.as<float>(); A.bbox = b_bbox.as<int>(); A.r_outer = b_ro.as<float>(); A.r_outer_iso = b_roi.as<float>();
+  A.r_inner_iso = b_rii.as<float>(); A.aniso_terms = b_terms.as<float>(); A.aniso = b_aniso.as<float>();
+  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox;
+  A.cell_start = nullptr; A.items = nullptr; A.max_dist = 0; memset(&A.G, 0, sizeof(A.G));
+  SDB_LAUNCH(k_pre1, cdiv(n, 128), 128, 0, st, A, b_stats.as<unsigned int>());
+  SDB_LAUNCH(k_aniso, 3, 256, 0, st, A);
+  SDB_LAUNCH(k_aniso_norm, 1, 1, 0, st, A);
+  SDB_LAUNCH(k_pre2, cdiv(n, 128), 128, 0, st, A);
+  int h_stats[8]; float h_aniso[3];
+  SDB_CUDA(cudaMemcpyAsync(h_stats, b_stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaMemcpyAsync(h_aniso, b_aniso.p, 12, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  float max_dist; { unsigned int u = (unsigned int)h_stats[0]; memcpy(&max_dist, &u, 4); }
+  A.max_dist = max_dist;
+  Grid3 G; G.all_pairs = use_kdtree ? 0 : 1;
+  {
+    double cell = 2.0 * (double)max_dist * (1.0 + 1e-5) + 1e-3;
+    if (cell < 1.0) cell = 1.0;
+    double ext[3];
+    for (int k = 0; k < 3; ++k) { G.mn[k] = (float)h_stats[1 + 2 * k]; ext[k] = (double)h_stats[2 + 2 * k] - h_stats[1 + 2 * k] + 1.0; }
+    while ((floor(ext[0] / cell) + 1) * (floor(ext[1] / cell) + 1) * (floor(ext[2] / cell) + 1) > 4.0e6) cell *= 2;
+    G.cell = (float)cell;
+    for (int k = 0; k < 3; ++k) G.g[k] = G.all_pairs ? 1 : (int)floor(ext[k] / cell) + 1;
+  }
+  A.G = G;
+  const int n_cells = G.g[0] * G.g[1] * G.g[2];
+  SDB_CUDA(b_cellpt.alloc((size_t)n * 4, st)); SDB_CUDA(b_counts.alloc((size_t)(n_cells + 1) * 4, st));
+  SDB_CUDA(b_start.alloc((size_t)(n_cells + 1) * 4, st)); SDB_CUDA(b_items.alloc((size_t)n * 4, st));
+  SDB_CUDA(cudaMemsetAsync(b_counts.p, 0, (size_t)(n_cells + 1) * 4, st));
+  SDB_LAUNCH(k_cell_count, cdiv(n, 256), 256, 0, st, d_points, n, G, b_cellpt.as<int>(), b_counts.as<unsigned int>());
+  SDB_LAUNCH(k_scan_serial, 1, 1024, 0, st, b_counts.as<unsigned int>(), b_start.as<unsigned int>(), n_cells);
+  SDB_CUDA(cudaMemcpyAsync(b_counts.p, b_start.p, (size_t)(n_cells + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  SDB_LAUNCH(k_cell_fill, cdiv(n, 256), 256, 0, st, b_cellpt.as<int>(), n, b_counts.as<unsigned int>(), b_items.as<int>());
+  A.cell_start = b_start.as<unsigned int>(); A.items = b_items.as<int>();
+
+  // pair list: grown on overflow (the round is re-run, decisions are idempotent)
+  size_t pair_cap = std::max<size_t>(1 << 16, (size_t)n * 4);
+  SDB_CUDA(b_pairs.alloc(pair_cap * sizeof(int2), st));
+  const size_t smem = ((size_t)(6 * n_rays + 3 * n_faces) * 4 + 15) / 16 * 16 + (size_t)2 * n_faces * sizeof(Plane) +
+                      (size_t)3 * n_rays * 8 + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 64;
+  SDB_CUDA(cudaFuncSetAttribute(k_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  if (verbose) {
+    printf("Non Maximum Suppression (3D, B200) ++++ \nNMS: n_polys  = %d \nNMS: n_rays   = %d  \nNMS: n_faces  = %d \nNMS: thresh   = %.3f \nNMS: use_bbox = %d \nNMS: use_kdtree = %d \n",
+           n, n_rays, n_faces, threshold, use_bbox, use_kdtree);
+    printf("NMS: calculated anisotropy: %.2f \t %.2f \t %.2f \n", h_aniso[0], h_aniso[1], h_aniso[2]);
+  }
+  unsigned int* h_pin = nullptr;
+  SDB_CUDA(cudaMallocHost(&h_pin, 8 * sizeof(unsigned int)));
+  int rc = 0;
+  for (int round = 0;; ++round) {
+    SDB_LAUNCH(k_reset, 1, 32, 0, st, b_counters.as<unsigned int>());
+    SDB_LAUNCH(k_frontier, cdiv(n, 256), 256, 0, st, A, round, b_counters.as<unsigned int>());
+    for (;;) {
+      SDB_LAUNCH(k_pretest, cdiv(n, 128), 128, 0, st, A, round, b_pairs.as<int2>(), (unsigned int)pair_cap, b_counters.as<unsigned int>());
+      SDB_LAUNCH(k_heavy, 148 * 4, 128, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap);
+      if (cudaMemcpyAsync(h_pin, b_counters.p, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+        sdb::set_error(std::string("nms3d: round failed: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; break;
+      }
+      if (h_pin[1] <= pair_cap) break;
+      // overflow: enlarge the list and redo the pretest/heavy stages of this round (already suppressed
+      // candidates are skipped, nothing is lost)
+      pair_cap = (size_t)h_pin[1] + (size_t)h_pin[1] / 2;
+      SDB_CUDA(b_pairs.alloc(pair_cap * sizeof(int2), st));
+      unsigned int zero = 0;
+      SDB_CUDA(cudaMemcpyAsync(b_counters.as<unsigned int>() + 1, &zero, 4, cudaMemcpyHostToDevice, st));
+    }
+    if (rc) break;
+    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u, convex %u, render %u so far)\n",
+                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[6], h_pin[7]);
+    if (h_pin[0] == 0) break;
+    if (round > 4 * n + 8) { sdb::set_error("nms3d: no progress"); rc = 1; break; }
+  }
+  cudaFreeHost(h_pin);
+  if (rc) return rc;
+  SDB_LAUNCH(k_finish, cdiv(n, 256), 256, 0, st, b_state.as<int>(), n, d_keep);
+  return 0;
+}
+
+// reference C ABI (stardist3d_lib.h:55-65): host pointers
+extern "C" void _LIB_non_maximum_suppression_sparse(const float* scores, const float* dist, const float* points,
+                                                    const int n_polys, const int n_rays, const int n_faces,
+                                                    const float* verts, const int* faces, const float threshold,
+                                                    const int use_bbox, const int use_kdtree, const int verbose,
+                                                    bool* result) {
+  (void)scores;     // not used by the reference either (the arrays arrive sorted)
+  if (n_polys <= 0) return;
+  auto fail = [&](const char* what) { fprintf(stderr, "stardist_b200: _LIB_non_maximum_suppression_sparse failed: %s: %s\n", what, sdb_last_error()); abort(); };
+  cudaStream_t st = 0;
+  sdb::DevBuf d_dist, d_points, d_verts, d_faces, d_keep;
+  if (d_dist.alloc((size_t)n_polys * n_rays * 4, st) || d_points.alloc((size_t)n_polys * 12, st) || d_verts.alloc((size_t)n_rays * 12, st) ||
+      d_faces.alloc((size_t)n_faces * 12, st) || d_keep.alloc((size_t)n_polys, st)) fail("alloc");
+  cudaMemcpyAsync(d_dist.p, dist, (size_t)n_polys * n_rays * 4, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_points.p, points, (size_t)n_polys * 12, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_verts.p, verts, (size_t)n_rays * 12, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(d_faces.p, faces, (size_t)n_faces * 12, cudaMemcpyHostToDevice, st);
+  if (sdb_nms3d(d_dist.as<float>(), d_points.as<float>(), d_verts.as<float>(), d_faces.as<int>(), n_polys, n_rays, n_faces,
+                threshold, use_bbox, use_kdtree, verbose, d_keep.as<unsigned char>(), (sdb_stream_t)st)) fail("kernel");
+  if (cudaMemcpyAsync(result, d_keep.p, (size_t)n_polys, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("copy back");
+}

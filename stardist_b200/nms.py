@@ -124,3 +124,90 @@ def non_maximum_suppression_inds(dist, points, scores, thresh=0.5, use_bbox=True
                                       int(verbose),
                                       np.float32(thresh))
     return inds
+
+
+#########  3D  (stardist/nms.py:233-384)
+
+def non_maximum_suppression_3d(dist, prob, rays, grid=(1, 1, 1), b=2, nms_thresh=0.5, prob_thresh=0.5, use_bbox=True, use_kdtree=True, verbose=False):
+    """Non-Maximum-Supression of 3D polyhedra
+
+    dist.shape = (Nz,Ny,Nx, n_rays), prob.shape = (Nz,Ny,Nx)
+    returns the retained points, probabilities, and distances
+    """
+    dist = np.asarray(dist)
+    prob = np.asarray(prob)
+    assert prob.ndim == 3 and dist.ndim == 4 and dist.shape[-1] == len(rays) and prob.shape == dist.shape[:3]
+    grid = _normalize_grid(grid, 3)
+    verbose and print("predicting instances with prob_thresh = {prob_thresh} and nms_thresh = {nms_thresh}".format(prob_thresh=prob_thresh, nms_thresh=nms_thresh), flush=True)
+    ind_thresh = _ind_prob_thresh(prob, prob_thresh, b)
+    points = np.stack(np.where(ind_thresh), axis=1)
+    verbose and print("found %s candidates" % len(points))
+    probi = prob[ind_thresh]
+    disti = dist[ind_thresh]
+    _sorted = _argsort_desc(probi)
+    probi = probi[_sorted]
+    disti = disti[_sorted]
+    points = points[_sorted]
+    verbose and print("non-maximum suppression...")
+    points = (points * np.array(grid).reshape((1, 3)))
+    inds = non_maximum_suppression_3d_inds(disti, points, rays=rays, scores=probi, thresh=nms_thresh,
+                                           use_bbox=use_bbox, use_kdtree=use_kdtree, verbose=verbose)
+    verbose and print("keeping %s/%s polyhedra" % (np.count_nonzero(inds), len(inds)))
+    return points[inds], probi[inds], disti[inds]
+
+
+def non_maximum_suppression_3d_sparse(dist, prob, points, rays, b=2, nms_thresh=0.5, use_kdtree=True, verbose=False):
+    """Non-Maximum-Supression of 3D polyhedra from a list of dists, probs and points
+
+    returns the retained instances (pointsi, probi, disti, indsi) with pointsi = points[indsi] ...
+    """
+    dist = np.asarray(dist)
+    prob = np.asarray(prob)
+    points = np.asarray(points)
+    assert dist.ndim == 2 and prob.ndim == 1 and points.ndim == 2 and \
+        dist.shape[-1] == len(rays) and points.shape[-1] == 3 and len(prob) == len(dist) == len(points)
+    verbose and print("predicting instances with nms_thresh = {nms_thresh}".format(nms_thresh=nms_thresh), flush=True)
+    inds_original = np.arange(len(prob))
+    _sorted = _argsort_desc(prob)
+    probi = prob[_sorted]
+    disti = dist[_sorted]
+    pointsi = points[_sorted]
+    inds_original = inds_original[_sorted]
+    verbose and print("non-maximum suppression...")
+    inds = non_maximum_suppression_3d_inds(disti, pointsi, rays=rays, scores=probi, thresh=nms_thresh, use_kdtree=use_kdtree, verbose=verbose)
+    verbose and print("keeping %s/%s polyhedra" % (np.count_nonzero(inds), len(inds)))
+    return pointsi[inds], probi[inds], disti[inds], inds_original[inds]
+
+
+def non_maximum_suppression_3d_inds(dist, points, rays, scores, thresh=0.5, use_bbox=True, use_kdtree=True, verbose=1):
+    """
+    Applies non maximum supression to ray-convex polyhedra given by dists and rays
+    sorted by scores and IoU threshold; returns the boolean survivor mask (in input order)
+    """
+    from .lib.stardist3d import c_non_max_suppression_inds
+    assert dist.ndim == 2
+    assert points.ndim == 2
+    assert dist.shape[1] == len(rays)
+    n_poly = dist.shape[0]
+    if scores is None:
+        scores = np.ones(n_poly)
+    assert len(scores) == n_poly
+    assert points.shape[0] == n_poly
+    # sort scores descendingly (nms.py:359-363)
+    ind = _argsort_desc(scores)
+    survivors = np.ones(n_poly, bool)
+    dist = dist[ind]
+    points = points[ind]
+    scores = scores[ind]
+
+    def _prep(x, dtype):
+        return np.ascontiguousarray(x.astype(dtype, copy=False))
+    if verbose:
+        t = time()
+    survivors[ind] = c_non_max_suppression_inds(_prep(dist, np.float32), _prep(points, np.float32),
+                                                _prep(rays.vertices, np.float32), _prep(rays.faces, np.int32),
+                                                _prep(scores, np.float32), int(use_bbox), int(use_kdtree),
+                                                int(verbose), np.float32(thresh))
+    if verbose:
+        print("NMS took %.4f s" % (time() - t))
+    return survivors

@@ -39,3 +39,46 @@ def nms2d_inputs(name):
     d, s, points = d[ind], s[ind], points[ind]
     points = points * np.array(grid).reshape(1, 2)
     return np.ascontiguousarray(d, np.float32), np.ascontiguousarray(points, np.float32), s, np.float32(nthr)
+
+
+# ---------------------------------------------------------------------------------- 3D
+NMS3D_CASES = {
+    # name: (shape, noise, n_rays, prob_thresh, nms_thresh, seed, anisotropy)   (tests/test_nms3D.py:25-30,46,62)
+    "r5_thr0": ((33, 44, 55), 0.0, 5, 0.9, 0.0, 42, None),
+    "r14_thr02": ((43, 31, 34), 0.0, 14, 0.9, 0.2, 42, None),
+    "r22_thr04": ((33, 44, 55), 0.0, 22, 0.9, 0.4, 42, None),
+    "r32_thr06": ((33, 44, 55), 0.0, 32, 0.9, 0.6, 42, None),
+    "r32_noise01_thr01": ((33, 44, 55), 0.1, 32, 0.9, 0.1, 42, None),
+    "r96_noise02_thr03": ((33, 44, 55), 0.2, 96, 0.9, 0.3, 7, None),
+    "r96_aniso_thr03": ((24, 48, 50), 0.3, 96, 0.93, 0.3, 11, (2, 1, 1)),
+}
+
+
+def rays_golden_spiral(n, anisotropy=None):
+    from stardist_b200.rays3d import Rays_GoldenSpiral     # host-only metadata, verified == reference rays3d.py
+    return Rays_GoldenSpiral(n, anisotropy=anisotropy)
+
+
+def create_random_data_3d(shape, noise, n_rays, seed):
+    rs = np.random.RandomState(seed)
+    dist = 10 * np.ones(shape + (n_rays,))
+    noise = np.clip(noise, 0, 1)
+    dist *= (1 + noise * rs.uniform(-1, 1, dist.shape))
+    prob = rs.uniform(0, 1, shape)
+    return prob.astype(np.float32), dist.astype(np.float32)
+
+
+def nms3d_inputs(name):
+    """-> dist f32[n,R], points f32[n,3], scores f32[n] (sorted desc, stable), rays, nms_thresh, shape"""
+    shape, noise, n_rays, pthr, nthr, seed, aniso = NMS3D_CASES[name]
+    prob, dist = create_random_data_3d(shape, noise, n_rays, seed)
+    mask = prob > pthr
+    b = 2
+    m2 = np.zeros_like(mask); m2[b:-b, b:-b, b:-b] = True
+    mask &= m2
+    points = np.stack(np.where(mask), axis=1)
+    d = dist[mask]; s = prob[mask]
+    ind = np.argsort(s, kind='stable')[::-1]
+    d, s, points = d[ind], s[ind], points[ind]
+    return (np.ascontiguousarray(d, np.float32), np.ascontiguousarray(points, np.float32), np.ascontiguousarray(s, np.float32),
+            rays_golden_spiral(n_rays, aniso), np.float32(nthr), shape)

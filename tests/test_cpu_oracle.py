@@ -96,7 +96,9 @@ def test_polygon_rule_convex_matches_halfplanes():
         for k in range(R):
             y0, x0, y1, x1 = float(r[k]), float(cc[k]), float(r[(k + 1) % R]), float(cc[(k + 1) % R])
             cr = (x1 - x0) * (Y - y0) - (y1 - y0) * (X - x0)
-            inside &= cr < -1e-9; outside |= cr > 1e-9
+            sgn = np.sign((x1 - x0) * (c[0] - y0) - (y1 - y0) * (c[1] - x0))     # side of the centre
+            inside &= sgn * cr > 1e-9; outside |= sgn * cr < -1e-9
+        assert inside.sum() > 50
         assert img[inside].all() and not img[outside].any()
 
 
