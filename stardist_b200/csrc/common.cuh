@@ -9,6 +9,10 @@ namespace sdb {
 
 void set_error(const std::string& msg);
 extern long long g_launch_count;
+// one-time per-device runtime setup (keeps the stream-ordered memory pool's blocks cached instead of
+// returning them to the OS at every synchronisation) + a small persistent pinned scratch buffer
+void ensure_runtime_init();
+unsigned int* pinned_scratch();     // 64 uint32, per process
 
 #define SDB_CUDA(call)                                                                      \
   do {                                                                                      \
@@ -41,6 +45,7 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   cudaError_t alloc(size_t n, cudaStream_t st) {
+    ensure_runtime_init();
     release();
     s = st; bytes = n;
     if (n == 0) n = 16;

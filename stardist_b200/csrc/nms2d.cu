@@ -227,12 +227,11 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
     printf("NMS: n_polys    = %d \nNMS: n_rays     = %d  \nNMS: thresh     = %.3f \nNMS: use_bbox   = %d\nNMS: use_kdtree = %d\n", n, R, threshold, use_bbox, use_kdtree);
     printf("NMS: max_dist = %g grid = %d x %d cell = %g\n", max_dist, G.gx, G.gy, G.cell);
   }
-  unsigned int* h_pin = nullptr;
-  SDB_CUDA(cudaMallocHost(&h_pin, 16 * sizeof(unsigned int)));
+  unsigned int* h_pin = sdb::pinned_scratch();
+  if (!h_pin) { sdb::set_error("nms2d: pinned host allocation failed"); return 1; }
   int rc;
   if (R <= 32) rc = run_rounds_nv32(A, b_slow.as<int>(), b_counters.as<unsigned int>(), st, verbose, h_pin);
   else rc = run_rounds_nv128(A, b_slow.as<int>(), b_counters.as<unsigned int>(), st, verbose, h_pin);
-  cudaFreeHost(h_pin);
   if (rc) return rc;
   SDB_LAUNCH(k_finish, cdiv(n, 256), 256, 0, st, b_state.as<int>(), n, d_keep);
   return 0;

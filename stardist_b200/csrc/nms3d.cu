@@ -547,8 +547,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
            n, n_rays, n_faces, threshold, use_bbox, use_kdtree);
     printf("NMS: calculated anisotropy: %.2f \t %.2f \t %.2f \n", h_aniso[0], h_aniso[1], h_aniso[2]);
   }
-  unsigned int* h_pin = nullptr;
-  SDB_CUDA(cudaMallocHost(&h_pin, 8 * sizeof(unsigned int)));
+  unsigned int* h_pin = sdb::pinned_scratch();
+  if (!h_pin) { sdb::set_error("nms3d: pinned host allocation failed"); return 1; }
   int rc = 0;
   for (int round = 0;; ++round) {
     SDB_LAUNCH(k_reset, 1, 32, 0, st, b_counters.as<unsigned int>());
@@ -573,7 +573,6 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
     if (h_pin[0] == 0) break;
     if (round > 4 * n + 8) { sdb::set_error("nms3d: no progress"); rc = 1; break; }
   }
-  cudaFreeHost(h_pin);
   if (rc) return rc;
   SDB_LAUNCH(k_finish, cdiv(n, 256), 256, 0, st, b_state.as<int>(), n, d_keep);
   return 0;

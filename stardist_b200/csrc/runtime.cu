@@ -8,6 +8,28 @@ static std::mutex g_err_mu;
 static std::string g_err;
 long long g_launch_count = 0;
 void set_error(const std::string& msg) { std::lock_guard<std::mutex> l(g_err_mu); g_err = msg; }
+
+static std::mutex g_init_mu;
+static bool g_init_done[64] = {false};
+static unsigned int* g_pinned = nullptr;
+void ensure_runtime_init() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  if (g_init_done[dev]) return;
+  std::lock_guard<std::mutex> l(g_init_mu);
+  if (g_init_done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  g_init_done[dev] = true;
+}
+unsigned int* pinned_scratch() {
+  std::lock_guard<std::mutex> l(g_init_mu);
+  if (!g_pinned) { if (cudaMallocHost(&g_pinned, 64 * sizeof(unsigned int)) != cudaSuccess) g_pinned = nullptr; }
+  return g_pinned;
+}
 }  // namespace sdb
 
 extern "C" const char* sdb_last_error(void) {
