@@ -32,10 +32,19 @@ def _declare(lib):
     lib.sdb_conv3x3_2d.argtypes = [P, P, c_int, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P]
     lib.sdb_maxpool2x2_2d.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
     lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
+    lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int, P, P, P]
+    lib.sdb_tc_error_check.argtypes = [P]
+    lib.sdb_split_weights.argtypes = [P, c_int, c_int, P, P, P]
+    lib.sdb_stem_split.argtypes = [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P]
+    lib.sdb_maxpool_split.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, P]
+    lib.sdb_heads_split.argtypes = [P, P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
+    lib.sdb_polyhedron_to_label.argtypes = [P, P, P, P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]
+    lib.sdb_nms3d.argtypes = [P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
     for name in ("_LIB_non_maximum_suppression_2d", "_LIB_polygons_to_label_2d", "sdb_nms2d",
                  "sdb_polygons_to_label_2d", "sdb_dist_to_coord_2d", "sdb_threshold_sort",
                  "sdb_gather_candidates", "sdb_conv3x3_2d", "sdb_maxpool2x2_2d", "sdb_heads_2d",
-                 "sdb_device_info"):
+                 "sdb_device_info", "sdb_conv3x3_tc", "sdb_tc_error_check", "sdb_split_weights", "sdb_stem_split",
+                 "sdb_maxpool_split", "sdb_heads_split", "sdb_polyhedron_to_label", "sdb_nms3d"):
         getattr(lib, name).restype = c_int
     # optional (added as the build widens)
     for name, argtypes in _OPTIONAL.items():

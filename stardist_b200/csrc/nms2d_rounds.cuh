@@ -4,11 +4,35 @@
 #pragma once
 #include "nms2d_common.cuh"
 #include "clip2d.cuh"
+#include <algorithm>
 
 namespace sdnms {
 namespace {
 
-__global__ void k_frontier(NmsArrays A, int round, unsigned int* __restrict__ counters /* [0]=undecided */) {
+struct DevVerts {
+  const int2* v;
+  __device__ int32_t x(int i) const { return v[i].x; }
+  __device__ int32_t y(int i) const { return v[i].y; }
+};
+
+// overlap test of kept h against candidate c; returns 1 suppressed, 0 not, -1 pool overflow
+template <int NV, int SC>
+__device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSweep<NV, SC>& S) {
+  DevVerts va{A.verts + (size_t)h * A.R}, vb{A.verts + (size_t)c * A.R};
+  int status;
+  const float inter = sdclip::clip_intersection_area(va, vb, A.R, S, &status);
+  if (status == sdclip::CLIP_OVERFLOW) return -1;
+  // overlap = area_inter / fmin(areas[i]+1e-10, areas[j]+1e-10)  (double), stored to float (:580)
+  const double den = fmin((double)A.area[h] + 1.e-10, (double)A.area[c] + 1.e-10);
+  const float overlap = (float)((double)inter / den);
+  return overlap > A.threshold ? 1 : 0;
+}
+
+// counters: [0] undecided at round start, [1] pairs emitted this round, [2] pair tests (total),
+//           [3] slow-path pool overflows (fatal), [4] slow pairs this round, [5] sticky "pair list
+//           overflowed" flag: every later kernel of the batch becomes a no-op until the host recovers
+__global__ void k_frontier2(NmsArrays A, int round, unsigned int* __restrict__ counters) {
+  if (counters[5]) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= A.n) return;
   if (A.state[c] != ST_UNDECIDED) return;
@@ -34,28 +58,12 @@ __global__ void k_frontier(NmsArrays A, int round, unsigned int* __restrict__ co
   if (!blocked) A.state[c] = kept_now;
 }
 
-struct DevVerts {
-  const int2* v;
-  __device__ int32_t x(int i) const { return v[i].x; }
-  __device__ int32_t y(int i) const { return v[i].y; }
-};
-
-// overlap test of kept h against candidate c; returns 1 suppressed, 0 not, -1 pool overflow
-template <int NV, int SC>
-__device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSweep<NV, SC>& S) {
-  DevVerts va{A.verts + (size_t)h * A.R}, vb{A.verts + (size_t)c * A.R};
-  int status;
-  const float inter = sdclip::clip_intersection_area(va, vb, A.R, S, &status);
-  if (status == sdclip::CLIP_OVERFLOW) return -1;
-  // overlap = area_inter / fmin(areas[i]+1e-10, areas[j]+1e-10)  (double), stored to float (:580)
-  const double den = fmin((double)A.area[h] + 1.e-10, (double)A.area[c] + 1.e-10);
-  const float overlap = (float)((double)inter / den);
-  return overlap > A.threshold ? 1 : 0;
-}
-
-template <int NV, int SC>
-__device__ void suppress_candidate(const NmsArrays& A, int c, int round, sdclip::ClipSweep<NV, SC>& S,
-                                   int* __restrict__ slow_list, unsigned int* __restrict__ counters) {
+// emit (kept-now h, undecided c) pairs that the reference would test (:548-576)
+__global__ void k_pairs(NmsArrays A, int round, int2* __restrict__ pairs, unsigned int cap, unsigned int* __restrict__ counters) {
+  if (counters[5]) return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= A.n) return;
+  if (A.state[c] != ST_UNDECIDED) return;
   const float cy = A.points[2 * c], cx = A.points[2 * c + 1];
   const int4 bc = A.bbox[c];
   const int kept_now = ST_KEPT_BASE + round;
@@ -70,71 +78,105 @@ __device__ void suppress_candidate(const NmsArrays& A, int c, int round, sdclip:
         if (h >= c) continue;
         if (A.state[h] != kept_now) continue;
         if (!reaches(A, h, c, cy, cx, bc)) continue;
-        atomicAdd(&counters[2], 1u);                 // pair evaluations (stats)
-        const int r = pair_suppresses<NV, SC>(A, h, c, S);
-        if (r == 1) { A.state[c] = ST_SUPPRESSED; return; }
-        if (r < 0) {
-          if (slow_list) { unsigned int k = atomicAdd(&counters[1], 1u); slow_list[k] = c; }
-          else atomicAdd(&counters[3], 1u);          // overflow in the slow path: hard error
-          return;
-        }
+        const unsigned int k = atomicAdd(&counters[1], 1u);
+        if (k < cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
       }
     }
 }
+__global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ counters) {
+  if (counters[1] > cap) counters[5] = 1;
+}
 
+// one pair per thread: every lane of a warp carries a clipping problem
 template <int NV>
-__global__ void __launch_bounds__(128) k_suppress(NmsArrays A, int round, int* __restrict__ slow_list,
-                                                  unsigned int* __restrict__ counters) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.n) return;
-  if (A.state[c] != ST_UNDECIDED) return;
+__global__ void __launch_bounds__(128) k_clip(NmsArrays A, const int2* __restrict__ pairs, unsigned int cap,
+                                              int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
+  if (counters[5]) return;
+  const unsigned int n_pairs = counters[1];
+  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  const int2 pr = pairs[t];
+  if (A.state[pr.y] == ST_SUPPRESSED) return;          // already suppressed by another pair (benign race)
   sdclip::ClipSweep<NV, 1> S;
-  suppress_candidate<NV, 1>(A, c, round, S, slow_list, counters);
+  const int r = pair_suppresses<NV, 1>(A, pr.x, pr.y, S);
+  if (r == 1) A.state[pr.y] = ST_SUPPRESSED;
+  else if (r < 0) { const unsigned int k = atomicAdd(&counters[4], 1u); slow_pairs[k] = pr; }
 }
 
 template <int NV>
-__global__ void __launch_bounds__(64) k_suppress_slow(NmsArrays A, int round, const int* __restrict__ slow_list,
-                                                     unsigned int* __restrict__ counters) {
-  const unsigned int n_slow = counters[1];
+__global__ void __launch_bounds__(64) k_clip_slow(NmsArrays A, const int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
+  if (counters[5]) return;
+  const unsigned int n_slow = counters[4];
   if (blockIdx.x * blockDim.x >= n_slow) return;
   sdclip::ClipSweep<NV, 4> S;
-  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_slow; t += gridDim.x * blockDim.x)
-    suppress_candidate<NV, 4>(A, slow_list[t], round, S, nullptr, counters);
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_slow; t += gridDim.x * blockDim.x) {
+    const int2 pr = slow_pairs[t];
+    const int r = pair_suppresses<NV, 4>(A, pr.x, pr.y, S);
+    if (r == 1) A.state[pr.y] = ST_SUPPRESSED;
+    else if (r < 0) atomicAdd(&counters[3], 1u);
+  }
 }
 
 __global__ void k_reset_counters(unsigned int* counters) {
-  if (threadIdx.x < 2) counters[threadIdx.x] = 0;     // undecided, slow-list length
+  if (counters[5]) return;
+  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; }
 }
 
 template <int NV>
-int run_rounds(NmsArrays A, int* d_slow, unsigned int* d_counters, cudaStream_t st, int verbose,
-               unsigned int* h_pin /* pinned [4*BATCH] */) {
+int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaStream_t st, int verbose,
+               unsigned int* h_pin /* pinned [8*BATCH] */) {
+  (void)d_slow_unused;
   const int n = A.n;
   constexpr int BATCH = 4;     // rounds launched per host synchronisation
+  size_t cap = std::max<size_t>((size_t)n * 2, 1 << 15);
+  sdb::DevBuf b_pairs, b_slow;
+  SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
+  SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
+  SDB_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), st));
   int round = 0;
+  auto launch_pair_stage = [&](int r) -> int {
+    SDB_LAUNCH(k_pairs, cdiv(n, 256), 256, 0, st, A, r, b_pairs.as<int2>(), (unsigned int)cap, d_counters);
+    SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
+    // grid sized for the capacity; threads beyond counters[1] exit immediately
+    SDB_LAUNCH((k_clip<NV>), cdiv(cap, 128), 128, 0, st, A, b_pairs.as<int2>(), (unsigned int)cap, b_slow.as<int2>(), d_counters);
+    SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
+    return 0;
+  };
   for (;;) {
+    const int round0 = round;
     for (int b = 0; b < BATCH; ++b, ++round) {
       SDB_LAUNCH(k_reset_counters, 1, 32, 0, st, d_counters);
-      SDB_LAUNCH(k_frontier, cdiv(n, 256), 256, 0, st, A, round, d_counters);
-      SDB_LAUNCH((k_suppress<NV>), cdiv(n, 128), 128, 0, st, A, round, d_slow, d_counters);
-      // slow path (pool overflow in the fast path): usually zero entries; grid-stride over the list
-      SDB_LAUNCH((k_suppress_slow<NV>), 8, 64, 0, st, A, round, d_slow, d_counters);
-      SDB_CUDA(cudaMemcpyAsync(h_pin + 4 * b, d_counters, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, d_counters);
+      if (launch_pair_stage(round)) return 1;
+      SDB_CUDA(cudaMemcpyAsync(h_pin + 8 * b, d_counters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     }
     SDB_CUDA(cudaStreamSynchronize(st));
     bool done = false;
     for (int b = 0; b < BATCH; ++b) {
-      const unsigned int* c = h_pin + 4 * b;
+      const unsigned int* c = h_pin + 8 * b;
       if (c[3] != 0) { sdb::set_error("nms2d: polygon clipping pools overflowed in the slow path"); return 1; }
+      if (c[5] != 0) {
+        // pair list overflowed in round round0+b: its frontier marks are in place, the later kernels of
+        // the batch were no-ops.  Grow the list, clear the flag, redo the pair stage of that round.
+        cap = (size_t)c[1] + (size_t)c[1] / 2 + 1024;
+        SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
+        SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
+        const unsigned int zeros[8] = {c[0], 0, c[2], 0, 0, 0, 0, 0};
+        SDB_CUDA(cudaMemcpyAsync(d_counters, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st));
+        round = round0 + b;
+        if (launch_pair_stage(round)) return 1;
+        SDB_CUDA(cudaStreamSynchronize(st));
+        round += 1;
+        break;
+      }
       if (c[0] == 0) { done = true; break; }
     }
-    if (verbose) printf("NMS2D(b200): rounds=%d undecided(last batch)=%u pair tests so far=%u\n", round, h_pin[4 * (BATCH - 1)], h_pin[4 * (BATCH - 1) + 2]);
+    if (verbose) printf("NMS2D(b200): rounds=%d undecided(last)=%u pair tests so far=%u\n", round, h_pin[8 * (BATCH - 1)], h_pin[8 * (BATCH - 1) + 2] + h_pin[8 * (BATCH - 1) + 1]);
     if (done) break;
     if (round > 4 * n + 8) { sdb::set_error("nms2d: no progress"); return 1; }
   }
   return 0;
 }
-
 
 }  // namespace
 }  // namespace sdnms

@@ -1,0 +1,530 @@
+// unet_tc.cu -- tcgen05 / TMA / TMEM implicit-GEMM 3x3 convolution for the U-Net backbone (sm_100a).
+//
+// Reference op: Keras Conv2D(3x3, padding='same', bias, ReLU) as composed by csbdeep's unet_block
+// (stardist/models/model2d.py:310-349).  Parity target for the float maps is 1e-5
+// relative, i.e. fp32-faithful -- a single TF32/BF16 pass (10/8 mantissa bits) is not enough.
+//
+// Number format: every activation tensor lives in HBM as TWO fp16 planes (hi, lo) with
+//   hi = fp16(v), lo = fp16(v - hi)      (22 significant bits, same 4 bytes/element as fp32)
+// written by the producing kernel's epilogue, and weights are split the same way once per model.
+// A convolution is then 3 fp16 tensor-core passes  hi*Whi + lo*Whi + hi*Wlo  accumulated in fp32
+// in TMEM (each fp16 x fp16 product is exact in fp32; the dropped lo*Wlo term is ~2^-22).
+// Compared with 3xTF32 this doubles the MMA rate (kind::f16) and needs no in-kernel split pass.
+//
+// Mapping: CTA tile = 8x16 output pixels (M = 128, one TMEM lane per pixel) x all Cout (N <= 256).
+//   K loop over (tap, channel block): the A operand of a tap is ONE 4-D TMA box load
+//   {KC channels, 16 x, 8 y, 1 image} at coordinates shifted by the tap; out-of-bounds
+//   elements are zero-filled by TMA == the 'same' zero padding.  Rows of KC fp16 (128 B or 64 B)
+//   land in the K-major SWIZZLE_128B / SWIZZLE_64B layout that the UMMA descriptor expects.
+//   B operand = weights [tap][Cout][Cin] (K-major), 3-D TMA box {KC, N, 1}.
+//   The decoder's Concatenate([UpSampling(x), skip]) is two activation sources on the K axis; the
+//   up-sampled source is materialised by its producer's epilogue (each pixel written 2x2).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
+//   lane), warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> hi/lo split -> 16 B global stores).
+// All mbarrier waits are bounded (a hang would cost a GPU-box strike): on timeout an error flag is
+// raised and the kernel drains.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <vector>
+#include <algorithm>
+#include <map>
+#include <tuple>
+#include "common.cuh"
+#include "../../include/stardist_b200.h"
+
+namespace {
+
+using sdb::cdiv;
+
+struct ConvParams {
+  int H, W;              // output (== input) spatial size
+  int c_src0;            // channels taken from source 0 (0 for a plain convolution)
+  int c_total;           // Cin
+  int relu;
+  int up2x;              // write every output pixel to the 2x2 block of a (2H, 2W) tensor
+  const float* bias;
+  __half* out_hi; __half* out_lo;
+  unsigned int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: returns false after ~2 s without completion (a hang would cost a GPU-box strike)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    for (int it = 0; it < 256; ++it) { if (mbar_try_wait(bar, parity)) return true; }
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) return false;
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start addr>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SW128, 4 = SW64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                               // LBO (unused for swizzled K-major)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------- the kernel
+template <int N, int KC>
+struct TcCfg {
+  static constexpr int ROWB = KC * 2;                       // bytes per operand row
+  static constexpr int A_BYTES = 128 * ROWB;                // one A plane tile
+  static constexpr int B_BYTES = N * ROWB;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2);
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  static constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : 4u;
+  static constexpr uint32_t SBO = 8 * ROWB;
+  // instruction descriptor, kind::f16: D=F32 (bit 4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
+
+template <int N, int KC>
+__global__ void __launch_bounds__(192, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
+          const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
+          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P) {
+  using C = TcCfg<N, KC>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* accum_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 8, img = blockIdx.z;
+  const int n_cb = P.c_total / KC;
+  const int n_kb = 9 * n_cb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int s = kb % C::STAGES;
+        if (kb >= C::STAGES) {
+          if (!mbar_wait(&empty_bar[s], ((kb / C::STAGES) - 1) & 1)) { atomicExch(P.error_flag, 1u); break; }
+        }
+        const int tap = kb / n_cb, cb = kb % n_cb;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int ch = cb * KC;
+        unsigned char* st = smem + s * C::STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+        if (ch < P.c_src0) {
+          tma_load_4d(st, &tm_a0_hi, &full_bar[s], ch, x0 + dx, y0 + dy, img);
+          tma_load_4d(st + C::A_BYTES, &tm_a0_lo, &full_bar[s], ch, x0 + dx, y0 + dy, img);
+        } else {
+          tma_load_4d(st, &tm_a1_hi, &full_bar[s], ch - P.c_src0, x0 + dx, y0 + dy, img);
+          tma_load_4d(st + C::A_BYTES, &tm_a1_lo, &full_bar[s], ch - P.c_src0, x0 + dx, y0 + dy, img);
+        }
+        tma_load_3d(st + 2 * C::A_BYTES, &tm_w_hi, &full_bar[s], ch, 0, tap);
+        tma_load_3d(st + 2 * C::A_BYTES + C::B_BYTES, &tm_w_lo, &full_bar[s], ch, 0, tap);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      bool ok = true;
+      for (int kb = 0; kb < n_kb && ok; ++kb) {
+        const int s = kb % C::STAGES;
+        if (!mbar_wait(&full_bar[s], (kb / C::STAGES) & 1)) { atomicExch(P.error_flag, 2u); ok = false; break; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_hi = smem_u32(smem + s * C::STAGE_BYTES), a_lo = a_hi + C::A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * C::A_BYTES, b_lo = b_hi + C::B_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < KC / 16; ++ks) {
+          const uint32_t koff = ks * 32;      // 16 fp16 = 32 B along K inside the swizzled row
+          const uint64_t dah = make_desc(a_hi + koff, C::SBO, C::LAYOUT), dal = make_desc(a_lo + koff, C::SBO, C::LAYOUT);
+          const uint64_t dbh = make_desc(b_hi + koff, C::SBO, C::LAYOUT), dbl = make_desc(b_lo + koff, C::SBO, C::LAYOUT);
+          umma_f16(tmem_base, dah, dbh, C::IDESC, (kb | ks) ? 1u : 0u);
+          umma_f16(tmem_base, dal, dbh, C::IDESC, 1u);
+          umma_f16(tmem_base, dah, dbl, C::IDESC, 1u);
+        }
+        tcgen05_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
+      }
+      tcgen05_commit(accum_bar);             // accumulator complete (also arrives if we bailed out)
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;             // pixel row of the tile
+    const int ty = m >> 4, tx = m & 15;
+    const int y = y0 + ty, x = x0 + tx;
+    const bool in_img = (y < P.H) && (x < P.W);
+    const bool ok = mbar_wait(accum_bar, 0);
+    if (!ok) atomicExch(P.error_flag, 3u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ok) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                       "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                       "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (in_img) {
+          __align__(16) __half hi[32];
+          __align__(16) __half lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = __uint_as_float(r[j]) + __ldg(P.bias + c0 + j);
+            if (P.relu) v = fmaxf(v, 0.f);
+            const __half h = __float2half_rn(v);
+            hi[j] = h;
+            lo[j] = __float2half_rn(v - __half2float(h));
+          }
+          if (!P.up2x) {
+            const size_t off = (((size_t)img * P.H + y) * P.W + x) * N + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+              reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
+          } else {
+            const int H2 = 2 * P.H, W2 = 2 * P.W;
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+              const size_t off = (((size_t)img * H2 + (2 * y + (rep >> 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- small SIMT companions
+// stem: Cin (1..4) -> COUT, fp32 input, split fp16 output
+template <int COUT>
+__global__ void __launch_bounds__(128)
+k_stem_split(const float* __restrict__ in, int N_, int H, int W, int Cin, const float* __restrict__ wgt,
+             const float* __restrict__ bias, int relu, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  extern __shared__ float sw[];
+  for (int e = threadIdx.x; e < 9 * Cin * COUT; e += blockDim.x) sw[e] = wgt[e];
+  for (int e = threadIdx.x; e < COUT; e += blockDim.x) sw[9 * Cin * COUT + e] = bias[e];
+  __syncthreads();
+  const long long npix = (long long)N_ * H * W;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  const int x = (int)(p % W), y = (int)((p / W) % H);
+  const long long img = p / ((long long)W * H);
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = sw[9 * Cin * COUT + o];
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = y + dy - 1;
+    if (yy < 0 || yy >= H) continue;
+    for (int dx = 0; dx < 3; ++dx) {
+      const int xx = x + dx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float* ip = in + ((img * H + yy) * W + xx) * Cin;
+      for (int c = 0; c < Cin; ++c) {
+        const float v = ip[c];
+        const float* wr = sw + ((dy * 3 + dx) * Cin + c) * COUT;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
+      }
+    }
+  }
+  __align__(16) __half hi[COUT];
+  __align__(16) __half lo[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) {
+    float v = acc[o];
+    if (relu) v = fmaxf(v, 0.f);
+    const __half h = __float2half_rn(v);
+    hi[o] = h; lo[o] = __float2half_rn(v - __half2float(h));
+  }
+#pragma unroll
+  for (int j = 0; j < COUT / 8; ++j) {
+    reinterpret_cast<uint4*>(out_hi + p * COUT)[j] = reinterpret_cast<const uint4*>(hi)[j];
+    reinterpret_cast<uint4*>(out_lo + p * COUT)[j] = reinterpret_cast<const uint4*>(lo)[j];
+  }
+}
+
+__global__ void k_maxpool_split(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int N_, int H, int W, int C,
+                                __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int Ho = H / 2, Wo = W / 2, C2 = C / 2;
+  const long long total = (long long)N_ * Ho * Wo * C2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c2 = (int)(e % C2); long long r = e / C2;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho); const long long img = r / Ho;
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t off = (((size_t)img * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C + 2 * c2;
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(in_hi + off));
+      const float2 l = __half22float2(*reinterpret_cast<const __half2*>(in_lo + off));
+      m0 = fmaxf(m0, h.x + l.x); m1 = fmaxf(m1, h.y + l.y);
+    }
+    const __half h0 = __float2half_rn(m0), h1 = __float2half_rn(m1);
+    const size_t o = (size_t)e * 2;
+    *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(__float2half_rn(m0 - __half2float(h0)), __float2half_rn(m1 - __half2float(h1)));
+  }
+}
+
+// heads on split features: prob = sigmoid(x.Wp+bp), dist = x.Wd+bd
+template <int CF>
+__global__ void __launch_bounds__(128)
+k_heads_split(const __half* __restrict__ f_hi, const __half* __restrict__ f_lo, long long npix, const float* __restrict__ wp,
+              const float* __restrict__ bp, const float* __restrict__ wd, const float* __restrict__ bd, int R,
+              float* __restrict__ prob, float* __restrict__ dist) {
+  extern __shared__ float sm[];
+  const int NO = R + 1;
+  float* sW = sm;
+  float* sF = sW + CF * NO;
+  float* sO = sF + 32 * (CF + 1);
+  for (int e = threadIdx.x; e < CF * NO; e += blockDim.x) {
+    const int f = e / NO, o = e % NO;
+    sW[e] = (o == 0) ? wp[f] : wd[(size_t)f * R + (o - 1)];
+  }
+  const long long p0 = (long long)blockIdx.x * 32;
+  for (int e = threadIdx.x; e < 32 * (CF / 2); e += blockDim.x) {
+    const int px = e / (CF / 2), f2 = e % (CF / 2);
+    float2 v = make_float2(0.f, 0.f);
+    if (p0 + px < npix) {
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(f_hi + (p0 + px) * CF + 2 * f2));
+      const float2 l = __half22float2(*reinterpret_cast<const __half2*>(f_lo + (p0 + px) * CF + 2 * f2));
+      v.x = h.x + l.x; v.y = h.y + l.y;
+    }
+    sF[px * (CF + 1) + 2 * f2] = v.x; sF[px * (CF + 1) + 2 * f2 + 1] = v.y;
+  }
+  __syncthreads();
+  const int px = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int o = w; o < NO; o += 4) {
+    float acc = (o == 0) ? bp[0] : bd[o - 1];
+    const float* fr = sF + px * (CF + 1);
+#pragma unroll 8
+    for (int f = 0; f < CF; ++f) acc = fmaf(fr[f], sW[f * NO + o], acc);
+    if (o == 0) acc = 1.f / (1.f + expf(-acc));
+    sO[px * NO + o] = acc;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * R; e += blockDim.x) {
+    const int q = e / R, k = e % R;
+    if (p0 + q < npix) dist[(p0 + q) * R + k] = sO[q * NO + 1 + k];
+  }
+  if (threadIdx.x < 32 && p0 + threadIdx.x < npix) prob[p0 + threadIdx.x] = sO[threadIdx.x * NO];
+}
+
+// weights (3,3,Cin,Cout) fp32 -> [tap][Cout][Cin] fp16 hi / lo
+__global__ void k_split_weights(const float* __restrict__ w, int Cin, int Cout, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
+  const long long total = 9LL * Cin * Cout;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(e % Cin); long long r = e / Cin;
+    const int co = (int)(r % Cout); const int tap = (int)(r / Cout);
+    const float v = w[((size_t)tap * Cin + ci) * Cout + co];
+    const __half h = __float2half_rn(v);
+    w_hi[e] = h; w_lo[e] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_act_map(CUtensorMap* m, const __half* base, int n, int h, int w, int c, int kc) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { sdb::set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, 16, 8, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = (kc * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sdb::set_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r)); return 1; }
+  return 0;
+}
+static int make_w_map(CUtensorMap* m, const __half* base, int cin, int cout, int kc) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { sdb::set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
+  cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)cout, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = (kc * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sdb::set_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r)); return 1; }
+  return 0;
+}
+
+template <int N, int KC>
+static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                     const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+  using C = TcCfg<N, KC>;
+  static bool attr = false;
+  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
+  dim3 grid(cdiv(P.W, 16), cdiv(P.H, 8), n_img);
+  k_conv_tc<N, KC><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P);
+  sdb::g_launch_count++;
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static unsigned int* g_err_flag = nullptr;      // device flag shared by all launches
+
+}  // namespace
+
+// conv3x3 on split-fp16 activations.  src0 (optional, c_src0 channels) and src1 (c_src1 channels) are
+// [n,h,w,c] hi/lo planes; weights are the pre-split [9][cout][cin] planes; output hi/lo planes are
+// [n,h,w,cout] or, with up2x, [n,2h,2w,cout] with every pixel replicated 2x2 (nearest up-sampling).
+extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                              int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, const float* d_bias, int cout,
+                              int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cin = c_src0 + c_src1;
+  const int kc = (cin % 64 == 0 && (c_src0 % 64 == 0)) ? 64 : 32;
+  if (cin % kc || c_src0 % kc || c_src1 % kc) { sdb::set_error("conv3x3_tc: channel counts must be multiples of 32"); return 1; }
+  if (cout != 32 && cout != 64 && cout != 128 && cout != 256) { sdb::set_error("conv3x3_tc: cout must be 32/64/128/256"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
+  CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
+  if (make_act_map(&a1h, (const __half*)src1_hi, n, h, w, c_src1, kc) || make_act_map(&a1l, (const __half*)src1_lo, n, h, w, c_src1, kc)) return 1;
+  if (c_src0 > 0) {
+    if (make_act_map(&a0h, (const __half*)src0_hi, n, h, w, c_src0, kc) || make_act_map(&a0l, (const __half*)src0_lo, n, h, w, c_src0, kc)) return 1;
+  } else { a0h = a1h; a0l = a1l; }
+  if (make_w_map(&wh, (const __half*)w_hi, cin, cout, kc) || make_w_map(&wl, (const __half*)w_lo, cin, cout, kc)) return 1;
+  ConvParams P;
+  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag;
+#define SDB_TC(NN, KK) return launch_tc<NN, KK>(a0h, a0l, a1h, a1l, wh, wl, P, n, st)
+  if (kc == 64) {
+    if (cout == 32) SDB_TC(32, 64); if (cout == 64) SDB_TC(64, 64); if (cout == 128) SDB_TC(128, 64); SDB_TC(256, 64);
+  } else {
+    if (cout == 32) SDB_TC(32, 32); if (cout == 64) SDB_TC(64, 32); if (cout == 128) SDB_TC(128, 32); SDB_TC(256, 32);
+  }
+#undef SDB_TC
+}
+
+// non-zero when any tcgen05 conv launch since the last call hit a bounded-wait timeout (then results are invalid)
+extern "C" int sdb_tc_error_check(sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!g_err_flag) return 0;
+  unsigned int v = 0;
+  SDB_CUDA(cudaMemcpyAsync(&v, g_err_flag, 4, cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  if (v) { SDB_CUDA(cudaMemsetAsync(g_err_flag, 0, 4, st)); sdb::set_error("tcgen05 conv: pipeline wait timed out (code " + std::to_string(v) + ")"); return 1; }
+  return 0;
+}
+
+extern "C" int sdb_split_weights(const float* d_w, int cin, int cout, void* w_hi, void* w_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = 9LL * cin * cout;
+  SDB_LAUNCH(k_split_weights, (int)std::min<long long>(cdiv(total, 256), 1024), 256, 0, st, d_w, cin, cout, (__half*)w_hi, (__half*)w_lo);
+  return 0;
+}
+
+extern "C" int sdb_stem_split(const float* d_in, int n, int h, int w, int cin, const float* d_w, const float* d_b, int cout, int relu,
+                              void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cin > 4 || (cout != 32 && cout != 64)) { sdb::set_error("stem_split: cin <= 4 and cout in {32,64}"); return 1; }
+  const size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
+  const long long npix = (long long)n * h * w;
+  if (cout == 32) SDB_LAUNCH((k_stem_split<32>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_w, d_b, relu, (__half*)out_hi, (__half*)out_lo);
+  else SDB_LAUNCH((k_stem_split<64>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_w, d_b, relu, (__half*)out_hi, (__half*)out_lo);
+  return 0;
+}
+
+extern "C" int sdb_maxpool_split(const void* in_hi, const void* in_lo, int n, int h, int w, int c, void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((h & 1) || (w & 1) || (c & 1)) { sdb::set_error("maxpool_split: needs even h, w, c"); return 1; }
+  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 2);
+  SDB_LAUNCH(k_maxpool_split, (int)std::min<long long>(cdiv(total, 256), 148 * 16), 256, 0, st, (const __half*)in_hi, (const __half*)in_lo, n, h, w, c,
+             (__half*)out_hi, (__half*)out_lo);
+  return 0;
+}
+
+extern "C" int sdb_heads_split(const void* f_hi, const void* f_lo, long long npix, int cfeat, const float* d_wp, const float* d_bp,
+                               const float* d_wd, const float* d_bd, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfeat != 128) { sdb::set_error("heads_split: only 128 feature channels supported"); return 1; }
+  const int NO = n_rays + 1;
+  const size_t smem = (size_t)(128 * NO + 32 * 129 + 32 * NO) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_heads_split<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+  if (smem > 200 * 1024) { sdb::set_error("heads_split: n_rays too large"); return 1; }
+  SDB_LAUNCH((k_heads_split<128>), cdiv(npix, 32), 128, smem, st, (const __half*)f_hi, (const __half*)f_lo, npix, d_wp, d_bp, d_wd, d_bd, n_rays, d_prob, d_dist);
+  return 0;
+}

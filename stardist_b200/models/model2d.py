@@ -12,7 +12,8 @@ from ..nms import non_maximum_suppression, non_maximum_suppression_sparse
 from ..geometry.geom2d import polygons_to_label, dist_to_coord, dist_to_coord_device, paint_order
 from .base import StarDistBase
 from .config import Config2D
-from .unet_device import UNetDevice2D
+import os
+from .unet_device import UNetDevice2D, UNetDevice2DTC
 
 
 class StarDist2D(StarDistBase):
@@ -31,6 +32,11 @@ class StarDist2D(StarDistBase):
 
     def _build(self):
         self.config.backbone == 'unet' or _raise(NotImplementedError())
+        # default: tcgen05 tensor-core path; STARDIST_B200_UNET=simt selects the exact-fp32 CUDA-core
+        # kernels (also used automatically for layer shapes the tensor-core kernel does not cover)
+        mode = os.environ.get("STARDIST_B200_UNET", "tc").lower()
+        if mode != "simt" and UNetDevice2DTC.supported(self.config):
+            return UNetDevice2DTC(self.config, self.weights)
         return UNetDevice2D(self.config, self.weights)
 
     # ------------------------------------------------------------------ numpy-level (reference signature)

@@ -83,3 +83,102 @@ class UNetDevice2D:
         L.check(lib.sdb_heads_2d(L.ptr(feat), n * h * w, cf, L.ptr(wp), L.ptr(bp), L.ptr(wd), L.ptr(bd), R,
                                 L.ptr(prob), L.ptr(dist), L.stream_ptr()))
         return prob, dist
+
+
+class UNetDevice2DTC:
+    """tcgen05 / TMA / TMEM executor (csrc/unet_tc.cu).  Activations are [2, N, H, W, C] float16
+    tensors (plane 0 = hi, plane 1 = lo, value = hi + lo); convolutions run as three fp16 tensor-core
+    passes with fp32 accumulation in TMEM.  The Cin<=4 stem, 2x2 max-pooling and the 1x1 heads are
+    small CUDA-core kernels on the same split format; nearest up-sampling is written by the
+    producing convolution's epilogue."""
+
+    def __init__(self, config, weights, device=None):
+        lib = L.require_cuda()
+        self.config = config
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        self.layers = unet_layers(config)
+        if config.unet_batch_norm:
+            raise NotImplementedError("unet_batch_norm=True is not supported on this path")
+        if tuple(config.unet_kernel_size) != (3, 3) or tuple(config.unet_pool) != (2, 2):
+            raise NotImplementedError("only 3x3 kernels and 2x2 pooling are supported")
+        if config.n_classes is not None:
+            raise NotImplementedError("multi-class head is not supported yet")
+        self.w = {}
+        for name, (k, b) in weights.items():
+            kd = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float32)).to(self.device)
+            bd = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device)
+            ent = dict(k=kd, b=bd)
+            if k.ndim == 4 and k.shape[0] == 3 and k.shape[2] % 32 == 0:
+                cin, cout = k.shape[2], k.shape[3]
+                ws = torch.empty((2, 9, cout, cin), dtype=torch.float16, device=self.device)
+                L.check(lib.sdb_split_weights(L.ptr(kd), cin, cout, L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
+                ent['split'] = ws
+            self.w[name] = ent
+
+    @staticmethod
+    def supported(config):
+        ch = [l['cin'] for l in unet_layers(config) if l['kind'] == 'conv'] + [l['cout'] for l in unet_layers(config) if l['kind'] == 'conv']
+        first = next(l for l in unet_layers(config) if l['kind'] == 'conv')
+        ok_first = first['cin'] <= 4 and first['cout'] in (32, 64)
+        rest = [l for l in unet_layers(config) if l['kind'] == 'conv'][1:]
+        ok_rest = all(l['cin'] % 32 == 0 and l['cout'] in (32, 64, 128, 256) for l in rest)
+        return (ok_first and ok_rest and config.net_conv_after_unet == 128 and not config.unet_batch_norm
+                and tuple(config.unet_kernel_size) == (3, 3) and tuple(config.unet_pool) == (2, 2) and config.n_classes is None)
+
+    def forward(self, x):
+        lib = L.load()
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
+        st = L.stream_ptr()
+        n, h, w, _ = x.shape
+        layers = self.layers
+        skips = {}
+        lo = None          # (tensor [2,n,h,w,c]) up-sampled source waiting for its concat conv
+        cur = None         # current activation (split)
+        first = True
+        for i, l in enumerate(layers):
+            kind = l['kind']
+            if kind == 'conv':
+                relu = 1 if l['act'] == 'relu' else 0
+                if l['act'] not in ('relu', 'linear'):
+                    raise NotImplementedError("activation %s" % l['act'])
+                nxt = layers[i + 1]['kind'] if i + 1 < len(layers) else None
+                up2x = 1 if nxt == 'up' else 0
+                ent = self.w[l['name']]
+                cout = ent['k'].shape[-1]
+                if first:
+                    out = torch.empty((2, n, h, w, cout), dtype=torch.float16, device=x.device)
+                    L.check(lib.sdb_stem_split(L.ptr(x), n, h, w, x.shape[-1], L.ptr(ent['k']), L.ptr(ent['b']), cout, relu,
+                                               L.ptr(out[0]), L.ptr(out[1]), st))
+                    first = False
+                else:
+                    _, n_, hh, ww, c1 = cur.shape
+                    c0 = 0 if lo is None else lo.shape[-1]
+                    oh, ow = (2 * hh, 2 * ww) if up2x else (hh, ww)
+                    out = torch.empty((2, n_, oh, ow, cout), dtype=torch.float16, device=x.device)
+                    ws = ent['split']
+                    L.check(lib.sdb_conv3x3_tc(L.ptr(lo[0]) if lo is not None else L.ptr(None), L.ptr(lo[1]) if lo is not None else L.ptr(None), c0,
+                                               L.ptr(cur[0]), L.ptr(cur[1]), c1, n_, hh, ww, L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(ent['b']),
+                                               cout, relu, up2x, L.ptr(out[0]), L.ptr(out[1]), st))
+                    lo = None
+                cur = out
+            elif kind == 'pool':
+                if 'save_skip' in l:
+                    skips[l['save_skip']] = cur
+                _, n_, hh, ww, c = cur.shape
+                out = torch.empty((2, n_, hh // 2, ww // 2, c), dtype=torch.float16, device=x.device)
+                L.check(lib.sdb_maxpool_split(L.ptr(cur[0]), L.ptr(cur[1]), n_, hh, ww, c, L.ptr(out[0]), L.ptr(out[1]), st))
+                cur = out
+            elif kind == 'up':
+                lo = cur                        # already written at 2x resolution by its producer
+                cur = skips.pop(l['skip'])
+                assert lo.shape[2] == cur.shape[2] and lo.shape[3] == cur.shape[3]
+            elif kind == 'head':
+                break
+        _, n_, hh, ww, cf = cur.shape
+        R = self.config.n_rays
+        prob = torch.empty((n_, hh, ww), dtype=torch.float32, device=x.device)
+        dist = torch.empty((n_, hh, ww, R), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_heads_split(L.ptr(cur[0]), L.ptr(cur[1]), n_ * hh * ww, cf, L.ptr(self.w['prob']['k']), L.ptr(self.w['prob']['b']),
+                                   L.ptr(self.w['dist']['k']), L.ptr(self.w['dist']['b']), R, L.ptr(prob), L.ptr(dist), st))
+        L.check(lib.sdb_tc_error_check(st))
+        return prob, dist
