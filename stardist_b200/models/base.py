@@ -376,6 +376,81 @@ class StarDistBase:
                 return res, (prob, dist)
             return res
 
+    # ------------------------------------------------------------------ predict_instances_big
+    def predict_instances_big(self, img, axes, block_size, min_overlap, context=None,
+                              labels_out=None, labels_out_dtype=np.int32, show_progress=True, group=None, **kwargs):
+        """Predict instance segmentation from very large input images (base.py:838-983).
+
+        The image is covered by overlapping blocks (stardist_b200.big.BlockND.cover); every block is an
+        independent predict_instances call, objects are assigned to exactly one block
+        (filter_objects), label ids get a running offset in block-id order and later blocks overwrite
+        earlier ones inside overlaps.  Assumption (as in the reference): every object is smaller than
+        `min_overlap`, and min_overlap + 2*context < block_size.
+
+        With an initialised torch.distributed process group (one rank per GPU) the blocks are sharded
+        round-robin over the ranks and assembled on rank 0 (stardist_b200/parallel_big.py); the result
+        on rank 0 is identical to the single-process result."""
+        from ..big import _grid_divisible, BlockND, OBJECT_KEYS
+        from ..matching import relabel_sequential
+        from .. import parallel_big
+        n = img.ndim
+        axes = axes_check_and_normalize(axes, length=n)
+        grid = self._axes_div_by(axes)
+        axes_out = self.config.axes.replace('C', '')
+        shape_dict = dict(zip(axes, img.shape))
+        shape_out = tuple(shape_dict[a] for a in axes_out)
+        if context is None:
+            context = self._axes_tile_overlap(axes)
+        if np.isscalar(block_size): block_size = n * [block_size]
+        if np.isscalar(min_overlap): min_overlap = n * [min_overlap]
+        if np.isscalar(context): context = n * [context]
+        block_size, min_overlap, context = list(block_size), list(min_overlap), list(context)
+        assert n == len(block_size) == len(min_overlap) == len(context)
+        if 'C' in axes:
+            i = axes_dict(axes)['C']
+            block_size[i] = img.shape[i]
+            min_overlap[i] = context[i] = 0
+        block_size = tuple(_grid_divisible(g, v, name='block_size', verbose=False) for v, g, a in zip(block_size, grid, axes))
+        min_overlap = tuple(_grid_divisible(g, v, name='min_overlap', verbose=False) for v, g, a in zip(min_overlap, grid, axes))
+        context = tuple(_grid_divisible(g, v, name='context', verbose=False) for v, g, a in zip(context, grid, axes))
+        if show_progress:
+            print(f'effective: block_size={block_size}, min_overlap={min_overlap}, context={context}', flush=True)
+        blocks = BlockND.cover(img.shape, axes, block_size, min_overlap, context, grid)
+        want_labels = not (np.isscalar(labels_out) and bool(labels_out) is False)
+        if want_labels and labels_out is not None:
+            labels_out.shape == shape_out or _raise(ValueError(f"'labels_out' must have shape {shape_out} (axes {axes_out})."))
+        kwargs_override = dict(axes=axes, overlap_label=None, return_labels=True, return_predict=False)
+        for k, v in kwargs_override.items():
+            if k in kwargs and show_progress: print(f"changing '{k}' from {kwargs[k]} to {v}", flush=True)
+            kwargs[k] = v
+        kwargs.pop('show_tile_progress', None)
+
+        def process(block):
+            labels, polys = self.predict_instances(block.read(img, axes=axes), **kwargs)
+            labels = block.crop_context(labels, axes=axes_out)
+            labels, polys = block.filter_objects(labels, polys, axes=axes_out)
+            return labels, polys
+
+        rank, world = parallel_big.rank_world(group)
+        if world > 1:
+            return parallel_big.run_sharded(blocks, process, shape_out, axes_out, labels_out if want_labels else False,
+                                            labels_out_dtype, group=group)
+        if want_labels and labels_out is None:
+            labels_out = np.zeros(shape_out, dtype=labels_out_dtype)
+        polys_all = {}
+        label_offset = 1
+        for block in blocks:
+            labels, polys = process(block)
+            labels = relabel_sequential(labels, label_offset)[0]
+            if want_labels:
+                block.write(labels_out, labels, axes=axes_out)
+            for k, v in polys.items():
+                polys_all.setdefault(k, []).append(v)
+            label_offset += len(polys['prob'])
+            del labels
+        polys_all = {k: (np.concatenate(v) if k in OBJECT_KEYS else v[0]) for k, v in polys_all.items()}
+        return (labels_out if want_labels else None), polys_all
+
     # ------------------------------------------------------------------ misc
     def _compute_receptive_field(self, img_size=None):
         """base.py:1068-1098: empirical receptive field from the response to a unit impulse"""

@@ -1,0 +1,107 @@
+"""CPU tests of the big-image block logic (stardist_b200/big.py) and of the multi-rank assembly
+(stardist_b200/parallel_big.py, world_size 2 over gloo).  Mirrors the reference's tests/test_big.py:
+test_cover2D/3D (:52-76, reassembling a label image from blocks is the identity), test_edgecases (:79)."""
+import os, sys
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+from stardist_b200.big import Block, BlockND, NotFullyVisible
+from stardist_b200.matching import relabel_sequential
+
+
+def _label_image(shape, seed, rmax=6):
+    rng = np.random.default_rng(seed)
+    lbl = np.zeros(shape, np.int32)
+    k = 0
+    for _ in range(400):
+        c = [rng.integers(rmax + 1, s - rmax - 1) for s in shape]
+        r = rng.integers(2, rmax)
+        sl = tuple(slice(ci - r, ci + r + 1) for ci in c)
+        grids = np.ogrid[tuple(slice(-r, r + 1) for _ in shape)]
+        ball = sum(g * g for g in grids) <= r * r
+        if (lbl[sl][ball] > 0).any(): continue
+        k += 1; lbl[sl][ball] = k
+    return lbl
+
+
+def _process_factory(gt):
+    """fake predict_instances: the 'prediction' of a block is the GT labels inside its read region,
+    objects cut by the read region's border removed, relabelled 1..n with a matching polys dict"""
+    def process(block):
+        axes = block.axes
+        lab = block.read(gt, axes=axes).copy()
+        lab = relabel_sequential(lab)[0].astype(np.int32)
+        n = int(lab.max())
+        objs = ndi.find_objects(lab)
+        pts = np.array([[(s.start + s.stop) // 2 for s in sl] for sl in objs]).reshape(n, lab.ndim)
+        polys = dict(prob=np.linspace(1, .5, n).astype(np.float32), points=pts)
+        lab = block.crop_context(lab, axes=axes)
+        return block.filter_objects(lab, polys, axes=axes)
+    return process
+
+
+def _serial(blocks, process, shape, axes):
+    out = np.zeros(shape, np.int32); off = 1; pts = []
+    for b in blocks:
+        lab, polys = process(b)
+        lab = relabel_sequential(lab, off)[0] if lab.max() > 0 else lab
+        b.write(out, lab, axes=axes); pts.append(polys['points']); off += len(polys['prob'])
+    return out, np.concatenate(pts)
+
+
+@pytest.mark.parametrize("shape,axes,bs,mo,ctx,grid", [((160, 200), 'YX', 64, 16, 8, 1), ((150, 131), 'YX', 72, 18, 6, 3),
+                                                        ((48, 90, 70), 'ZYX', (32, 48, 40), (12, 16, 14), (2, 4, 2), (1, 2, 2))])
+def test_cover_reassembly_is_identity(shape, axes, bs, mo, ctx, grid):
+    gt = _label_image(shape, seed=1)
+    blocks = BlockND.cover(shape, axes, bs, mo, ctx, grid)
+    out, pts = _serial(blocks, _process_factory(gt), shape, axes)
+    assert np.array_equal(out > 0, gt > 0)
+    # same partition into objects: one-to-one map between label ids
+    pairs = np.unique(np.stack([gt[gt > 0], out[gt > 0]], 1), axis=0)
+    assert len(pairs) == gt.max() == len(np.unique(out)) - 1 == len(pts)
+
+
+def test_cover_edge_sizes():
+    for size in range(7800, 7810):
+        blocks = Block.cover(size, 1024, 128, 32, grid=8, verbose=False)
+        assert blocks[0].start == 0 and blocks[-1].end == size
+        w = [b.slice_write for b in blocks]
+        assert w[0].start == 0 and w[-1].stop == size and all(a.stop >= b.start for a, b in zip(w[:-1], w[1:]))
+
+
+def test_object_larger_than_overlap_raises():
+    gt = np.zeros((64, 200), np.int32); gt[20:40, 10:190] = 1
+    blocks = BlockND.cover(gt.shape, 'YX', (64, 80), (0, 16), (0, 4), 1)
+    with pytest.raises(RuntimeError):
+        _serial(blocks, _process_factory(gt), gt.shape, 'YX')
+
+
+def _worker(rank, world, port, shape, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from stardist_b200 import parallel_big
+    gt = _label_image(shape, seed=2)
+    blocks = BlockND.cover(shape, 'YX', 64, 16, 8, 1)
+    out, polys = parallel_big.run_sharded(blocks, _process_factory(gt), shape, 'YX', None, np.int32)
+    if rank == 0:
+        q.put((out, polys['points'], polys['prob']))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_sharded_assembly_two_ranks_equals_serial():
+    import torch.multiprocessing as mp
+    shape = (170, 210)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, shape, q)) for r in range(2)]
+    for p in procs: p.start()
+    out, pts, prob = q.get(timeout=120)
+    for p in procs: p.join(timeout=60)
+    assert all(p.exitcode == 0 for p in procs)
+    gt = _label_image(shape, seed=2)
+    blocks = BlockND.cover(shape, 'YX', 64, 16, 8, 1)
+    want, want_pts = _serial(blocks, _process_factory(gt), shape, 'YX')
+    assert np.array_equal(out, want) and np.array_equal(pts, want_pts) and len(prob) == len(pts)
