@@ -130,6 +130,13 @@ int sdb_conv3x3_2d(const float* d_in, const float* d_in_lo, int n, int h, int w,
 
 int sdb_maxpool2x2_2d(const float* d_in, int n, int h, int w, int c, float* d_out, sdb_stream_t stream);
 
+/* N-d variants (NDHWC): kz = 1 -> 2-D (d == 1), kz = 3 -> 3x3x3 with Keras kernels (3,3,3,Cin,Cout);
+ * (uz,uy,ux) = nearest up-sampling factors of the optional low-resolution source; pooling (pz,py,px). */
+int sdb_conv3_nd(const float* d_in, const float* d_in_lo, int n, int d, int h, int w, int cin_skip,
+                 int cin_lo, int uz, int uy, int ux, const float* d_weight, const float* d_bias, int cout,
+                 int kz, int relu, float* d_out, sdb_stream_t stream);
+int sdb_maxpool_nd(const float* d_in, int n, int d, int h, int w, int c, int pz, int py, int px, float* d_out, sdb_stream_t stream);
+
 /* 1x1 heads: prob = sigmoid(x.Wp+bp) [npix], dist = x.Wd+bd [npix*n_rays] */
 int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_wp, const float* d_bp,
                  const float* d_wd, const float* d_bd, int n_rays, float* d_prob, float* d_dist,

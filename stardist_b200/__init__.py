@@ -12,5 +12,5 @@ from .geometry import (ray_angles, dist_to_coord, polygons_to_label, polygons_to
                        polyhedron_to_label, dist_to_coord3D)
 from .rays3d import Rays_GoldenSpiral, Rays_Explicit, rays_from_json
 from .matching import relabel_sequential
-from .models import Config2D, StarDist2D
+from .models import Config2D, StarDist2D, Config3D, StarDist3D
 from .utils import normalize

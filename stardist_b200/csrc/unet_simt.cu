@@ -20,28 +20,34 @@ using sdb::cdiv;
 
 // ------------------------------------------------------------------------------------------
 // generic 3x3 conv: CTA tile 16x16 output pixels x COUT_T output channels, K chunk of 8 channels
-template <int COUT_T>
+// KZ = 1: 2-D 3x3 convolution (D must be 1); KZ = 3: 3-D 3x3x3 convolution over (D,H,W), weights
+// (kz,3,3,Cin,Cout).  The optional low-resolution source is read through nearest up-sampling by
+// (uz,uy,ux) (csbdeep UpSampling(pool)).
+template <int COUT_T, int KZ>
 __global__ void __launch_bounds__(COUT_T * 4)
-k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, int H, int W,
-          int c_skip, int c_lo, const float* __restrict__ wgt, const float* __restrict__ bias,
+k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, int D, int H, int W,
+          int c_skip, int c_lo, int uz, int uy, int ux, const float* __restrict__ wgt, const float* __restrict__ bias,
           int Cout, int relu, float* __restrict__ out) {
   constexpr int CK = 8, TH = 16, TW = 16, CG = COUT_T / 4, NT = 16 * CG;
   __shared__ __align__(16) float sA[CK][TH + 2][20];
   __shared__ __align__(16) float sB[9][CK][COUT_T];
   const int Cin = c_skip + c_lo;
   const int n_ct = Cout / COUT_T;
-  const int img = blockIdx.z / n_ct, n0 = (blockIdx.z % n_ct) * COUT_T;
+  const int zi = (blockIdx.z / n_ct) % D, img = (blockIdx.z / n_ct) / D, n0 = (blockIdx.z % n_ct) * COUT_T;
   const int ty0 = blockIdx.y * TH, tx0 = blockIdx.x * TW;
   const int t = threadIdx.x, cg = t % CG, pg = t / CG;
-  const float* skip_img = in_skip + (size_t)img * H * W * c_skip;
-  const float* lo_img = in_lo ? in_lo + (size_t)img * (H / 2) * (W / 2) * c_lo : nullptr;
-  const int Wlo = W / 2;
+  const int Dlo = D / uz, Hlo = H / uy, Wlo = W / ux;
 
   float acc[16][4];
 #pragma unroll
   for (int p = 0; p < 16; ++p) { acc[p][0] = acc[p][1] = acc[p][2] = acc[p][3] = 0.f; }
 
-  for (int c0 = 0; c0 < Cin; c0 += CK) {
+  for (int c0 = 0; c0 < Cin; c0 += CK)
+  for (int dz = 0; dz < KZ; ++dz) {
+    const int zz = zi + dz - KZ / 2;
+    if (zz < 0 || zz >= D) continue;                 // zero padding along z (block-uniform)
+    const float* skip_img = in_skip + ((size_t)img * D + zz) * H * W * c_skip;
+    const float* lo_img = in_lo ? in_lo + ((size_t)img * Dlo + zz / uz) * Hlo * Wlo * c_lo : nullptr;
     // ---- stage the (TH+2)x(TW+2) halo tile of CK channels, transposed to channel-major
     for (int e = t; e < (TH + 2) * (TW + 2) * (CK / 4); e += NT) {
       const int q = e % (CK / 4), p = e / (CK / 4);
@@ -50,7 +56,7 @@ k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, in
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
         const int c = c0 + 4 * q;
-        if (c < c_lo) v = *reinterpret_cast<const float4*>(lo_img + ((size_t)(gy >> 1) * Wlo + (gx >> 1)) * c_lo + c);
+        if (c < c_lo) v = *reinterpret_cast<const float4*>(lo_img + ((size_t)(gy / uy) * Wlo + (gx / ux)) * c_lo + c);
         else v = *reinterpret_cast<const float4*>(skip_img + ((size_t)gy * W + gx) * c_skip + (c - c_lo));
       }
       sA[4 * q + 0][ry][rx] = v.x; sA[4 * q + 1][ry][rx] = v.y;
@@ -60,7 +66,7 @@ k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, in
     for (int e = t; e < 9 * CK * (COUT_T / 4); e += NT) {
       const int co4 = e % (COUT_T / 4), r = e / (COUT_T / 4);
       const int ci = r % CK, tap = r / CK;
-      const float4 v = *reinterpret_cast<const float4*>(wgt + ((size_t)tap * Cin + c0 + ci) * Cout + n0 + 4 * co4);
+      const float4 v = *reinterpret_cast<const float4*>(wgt + ((size_t)(dz * 9 + tap) * Cin + c0 + ci) * Cout + n0 + 4 * co4);
       *reinterpret_cast<float4*>(&sB[tap][ci][4 * co4]) = v;
     }
     __syncthreads();
@@ -92,7 +98,7 @@ k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, in
   const int gy = ty0 + pg;
   if (gy >= H) return;
   const float4 bb = *reinterpret_cast<const float4*>(bias + n0 + 4 * cg);
-  float* orow = out + ((size_t)img * H * W + (size_t)gy * W) * Cout + n0 + 4 * cg;
+  float* orow = out + ((((size_t)img * D + zi) * H + gy) * (size_t)W) * Cout + n0 + 4 * cg;
 #pragma unroll
   for (int p = 0; p < 16; ++p) {
     const int gx = tx0 + p;
@@ -104,35 +110,39 @@ k_conv3x3(const float* __restrict__ in_skip, const float* __restrict__ in_lo, in
 }
 
 // ------------------------------------------------------------------------------------------
-// stem: Cin small (1..4), not a multiple of 8: one thread per output pixel, all Cout (<=64) in registers
-template <int COUT>
+// stem: Cin small (1..4), not a multiple of 8: one thread per output voxel, all Cout (<=64) in registers
+template <int COUT, int KZ>
 __global__ void __launch_bounds__(128)
-k_conv3x3_stem(const float* __restrict__ in, int N, int H, int W, int Cin, const float* __restrict__ wgt,
+k_conv3x3_stem(const float* __restrict__ in, int N, int D, int H, int W, int Cin, const float* __restrict__ wgt,
                const float* __restrict__ bias, int relu, float* __restrict__ out) {
-  extern __shared__ float sw[];     // [9*Cin][COUT] + bias[COUT]
-  for (int e = threadIdx.x; e < 9 * Cin * COUT; e += blockDim.x) sw[e] = wgt[e];
-  for (int e = threadIdx.x; e < COUT; e += blockDim.x) sw[9 * Cin * COUT + e] = bias[e];
+  extern __shared__ float sw[];     // [KZ*9*Cin][COUT] + bias[COUT]
+  for (int e = threadIdx.x; e < KZ * 9 * Cin * COUT; e += blockDim.x) sw[e] = wgt[e];
+  for (int e = threadIdx.x; e < COUT; e += blockDim.x) sw[KZ * 9 * Cin * COUT + e] = bias[e];
   __syncthreads();
-  const long long npix = (long long)N * H * W;
+  const long long npix = (long long)N * D * H * W;
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
-  const int x = (int)(p % W), y = (int)((p / W) % H);
-  const long long img = p / ((long long)W * H);
+  const int x = (int)(p % W), y = (int)((p / W) % H), z = (int)((p / ((long long)W * H)) % D);
+  const long long img = p / ((long long)W * H * D);
   float acc[COUT];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = sw[9 * Cin * COUT + o];
-  for (int dy = 0; dy < 3; ++dy) {
-    const int yy = y + dy - 1;
-    if (yy < 0 || yy >= H) continue;
-    for (int dx = 0; dx < 3; ++dx) {
-      const int xx = x + dx - 1;
-      if (xx < 0 || xx >= W) continue;
-      const float* ip = in + ((img * H + yy) * W + xx) * Cin;
-      for (int c = 0; c < Cin; ++c) {
-        const float v = ip[c];
-        const float* wr = sw + ((dy * 3 + dx) * Cin + c) * COUT;
+  for (int o = 0; o < COUT; ++o) acc[o] = sw[KZ * 9 * Cin * COUT + o];
+  for (int dz = 0; dz < KZ; ++dz) {
+    const int zz = z + dz - KZ / 2;
+    if (zz < 0 || zz >= D) continue;
+    for (int dy = 0; dy < 3; ++dy) {
+      const int yy = y + dy - 1;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < 3; ++dx) {
+        const int xx = x + dx - 1;
+        if (xx < 0 || xx >= W) continue;
+        const float* ip = in + (((img * D + zz) * H + yy) * W + xx) * Cin;
+        for (int c = 0; c < Cin; ++c) {
+          const float v = ip[c];
+          const float* wr = sw + (((dz * 3 + dy) * 3 + dx) * Cin + c) * COUT;
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
+          for (int o = 0; o < COUT; ++o) acc[o] = fmaf(v, wr[o], acc[o]);
+        }
       }
     }
   }
@@ -146,18 +156,20 @@ k_conv3x3_stem(const float* __restrict__ in, int N, int H, int W, int Cin, const
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void k_maxpool2x2(const float* __restrict__ in, int N, int H, int W, int C, float* __restrict__ out) {
-  const int Ho = H / 2, Wo = W / 2, C4 = C / 4;
-  const long long total = (long long)N * Ho * Wo * C4;
+__global__ void k_maxpool_nd(const float* __restrict__ in, int N, int D, int H, int W, int C, int pz, int py, int px,
+                             float* __restrict__ out) {
+  const int Do = D / pz, Ho = H / py, Wo = W / px, C4 = C / 4;
+  const long long total = (long long)N * Do * Ho * Wo * C4;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(e % C4); long long r = e / C4;
     const int xo = (int)(r % Wo); r /= Wo;
-    const int yo = (int)(r % Ho); const long long img = r / Ho;
-    const float4* b = reinterpret_cast<const float4*>(in + ((img * H + 2 * yo) * W + 2 * xo) * C) + c4;
-    const float4 v00 = b[0], v01 = b[C4], v10 = b[(size_t)W * C4], v11 = b[(size_t)W * C4 + C4];
-    float4 m;
-    m.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x)); m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
-    m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z)); m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+    const int yo = (int)(r % Ho); r /= Ho;
+    const int zo = (int)(r % Do); const long long img = r / Do;
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int a = 0; a < pz; ++a) for (int b = 0; b < py; ++b) for (int c = 0; c < px; ++c) {
+      const float4 v = reinterpret_cast<const float4*>(in + ((((img * D + zo * pz + a) * H + yo * py + b) * W) + xo * px + c) * (size_t)C)[c4];
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
     reinterpret_cast<float4*>(out)[e] = m;
   }
 }
@@ -206,39 +218,64 @@ k_heads(const float* __restrict__ feat, long long npix, const float* __restrict_
 
 }  // namespace
 
-extern "C" int sdb_conv3x3_2d(const float* d_in, const float* d_in_lo, int n, int h, int w, int cin_skip,
-                              int cin_lo, const float* d_weight, const float* d_bias, int cout, int relu,
-                              float* d_out, sdb_stream_t stream) {
+// N-d convolution entry point: kz = 1 (2-D, d must be 1) or 3 (3-D).  (uz,uy,ux): up-sampling factors of
+// the optional low-resolution source.
+extern "C" int sdb_conv3_nd(const float* d_in, const float* d_in_lo, int n, int d, int h, int w, int cin_skip,
+                            int cin_lo, int uz, int uy, int ux, const float* d_weight, const float* d_bias, int cout,
+                            int kz, int relu, float* d_out, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int cin = cin_skip + cin_lo;
-  if (d_in_lo == nullptr && cin_lo != 0) { sdb::set_error("conv3x3_2d: cin_lo without in_lo"); return 1; }
+  if (kz != 1 && kz != 3) { sdb::set_error("conv3_nd: kz must be 1 or 3"); return 1; }
+  if (kz == 1 && d != 1) { sdb::set_error("conv3_nd: 2-D convolution needs d == 1"); return 1; }
+  if (d_in_lo == nullptr && cin_lo != 0) { sdb::set_error("conv3_nd: cin_lo without in_lo"); return 1; }
   if (cin_lo == 0 && cin <= 4) {
-    const size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
-    const long long npix = (long long)n * h * w;
-    if (cout == 32) SDB_LAUNCH((k_conv3x3_stem<32>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_weight, d_bias, relu, d_out);
-    else if (cout == 64) SDB_LAUNCH((k_conv3x3_stem<64>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_weight, d_bias, relu, d_out);
-    else { sdb::set_error("conv3x3_2d: stem supports cout 32 or 64"); return 1; }
+    const size_t smem = (size_t)(kz * 9 * cin * cout + cout) * sizeof(float);
+    const long long npix = (long long)n * d * h * w;
+    if (cout != 32 && cout != 64) { sdb::set_error("conv3_nd: stem supports cout 32 or 64"); return 1; }
+    if (smem > 48 * 1024) { sdb::set_error("conv3_nd: stem weights exceed shared memory"); return 1; }
+    if (kz == 1) {
+      if (cout == 32) SDB_LAUNCH((k_conv3x3_stem<32, 1>), cdiv(npix, 128), 128, smem, st, d_in, n, d, h, w, cin, d_weight, d_bias, relu, d_out);
+      else SDB_LAUNCH((k_conv3x3_stem<64, 1>), cdiv(npix, 128), 128, smem, st, d_in, n, d, h, w, cin, d_weight, d_bias, relu, d_out);
+    } else {
+      if (cout == 32) SDB_LAUNCH((k_conv3x3_stem<32, 3>), cdiv(npix, 128), 128, smem, st, d_in, n, d, h, w, cin, d_weight, d_bias, relu, d_out);
+      else SDB_LAUNCH((k_conv3x3_stem<64, 3>), cdiv(npix, 128), 128, smem, st, d_in, n, d, h, w, cin, d_weight, d_bias, relu, d_out);
+    }
     return 0;
   }
-  if (cin_skip % 8 || cin_lo % 8 || cout % 32) { sdb::set_error("conv3x3_2d: channels must be multiples of 8 (in) / 32 (out)"); return 1; }
-  if (cin_lo && ((h & 1) || (w & 1))) { sdb::set_error("conv3x3_2d: upsampled input needs even h, w"); return 1; }
+  if (cin_skip % 8 || cin_lo % 8 || cout % 32) { sdb::set_error("conv3_nd: channels must be multiples of 8 (in) / 32 (out)"); return 1; }
+  if (cin_lo && (uz < 1 || uy < 1 || ux < 1 || d % uz || h % uy || w % ux)) { sdb::set_error("conv3_nd: size not divisible by the up-sampling factors"); return 1; }
+  if (!cin_lo) { uz = uy = ux = 1; }
   dim3 grid(cdiv(w, 16), cdiv(h, 16), 1);
+  const long long gz = (long long)n * d * (cout % 64 == 0 ? cout / 64 : cout / 32);
+  if (gz > 65535) { sdb::set_error("conv3_nd: grid.z too large (n*d*cout tiles > 65535)"); return 1; }
+  grid.z = (unsigned)gz;
   if (cout % 64 == 0) {
-    grid.z = n * (cout / 64);
-    SDB_LAUNCH((k_conv3x3<64>), grid, 256, 0, st, d_in, d_in_lo, h, w, cin_skip, cin_lo, d_weight, d_bias, cout, relu, d_out);
+    if (kz == 1) SDB_LAUNCH((k_conv3x3<64, 1>), grid, 256, 0, st, d_in, d_in_lo, d, h, w, cin_skip, cin_lo, uz, uy, ux, d_weight, d_bias, cout, relu, d_out);
+    else SDB_LAUNCH((k_conv3x3<64, 3>), grid, 256, 0, st, d_in, d_in_lo, d, h, w, cin_skip, cin_lo, uz, uy, ux, d_weight, d_bias, cout, relu, d_out);
   } else {
-    grid.z = n * (cout / 32);
-    SDB_LAUNCH((k_conv3x3<32>), grid, 128, 0, st, d_in, d_in_lo, h, w, cin_skip, cin_lo, d_weight, d_bias, cout, relu, d_out);
+    if (kz == 1) SDB_LAUNCH((k_conv3x3<32, 1>), grid, 128, 0, st, d_in, d_in_lo, d, h, w, cin_skip, cin_lo, uz, uy, ux, d_weight, d_bias, cout, relu, d_out);
+    else SDB_LAUNCH((k_conv3x3<32, 3>), grid, 128, 0, st, d_in, d_in_lo, d, h, w, cin_skip, cin_lo, uz, uy, ux, d_weight, d_bias, cout, relu, d_out);
   }
   return 0;
 }
 
-extern "C" int sdb_maxpool2x2_2d(const float* d_in, int n, int h, int w, int c, float* d_out, sdb_stream_t stream) {
+extern "C" int sdb_conv3x3_2d(const float* d_in, const float* d_in_lo, int n, int h, int w, int cin_skip,
+                              int cin_lo, const float* d_weight, const float* d_bias, int cout, int relu,
+                              float* d_out, sdb_stream_t stream) {
+  if (cin_lo && ((h & 1) || (w & 1))) { sdb::set_error("conv3x3_2d: upsampled input needs even h, w"); return 1; }
+  return sdb_conv3_nd(d_in, d_in_lo, n, 1, h, w, cin_skip, cin_lo, 1, 2, 2, d_weight, d_bias, cout, 1, relu, d_out, stream);
+}
+
+extern "C" int sdb_maxpool_nd(const float* d_in, int n, int d, int h, int w, int c, int pz, int py, int px, float* d_out, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if ((h & 1) || (w & 1) || (c & 3)) { sdb::set_error("maxpool2x2_2d: needs even h, w and c % 4 == 0"); return 1; }
-  const long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
-  SDB_LAUNCH(k_maxpool2x2, (int)std::min<long long>(cdiv(total, 256), 148 * 16), 256, 0, st, d_in, n, h, w, c, d_out);
+  if (pz < 1 || py < 1 || px < 1 || d % pz || h % py || w % px || (c & 3)) { sdb::set_error("maxpool_nd: sizes must be divisible by the pool and c % 4 == 0"); return 1; }
+  const long long total = (long long)n * (d / pz) * (h / py) * (w / px) * (c / 4);
+  SDB_LAUNCH(k_maxpool_nd, (int)std::min<long long>(cdiv(total, 256), 148 * 16), 256, 0, st, d_in, n, d, h, w, c, pz, py, px, d_out);
   return 0;
+}
+
+extern "C" int sdb_maxpool2x2_2d(const float* d_in, int n, int h, int w, int c, float* d_out, sdb_stream_t stream) {
+  return sdb_maxpool_nd(d_in, n, 1, h, w, c, 1, 2, 2, d_out, stream);
 }
 
 extern "C" int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_wp, const float* d_bp,

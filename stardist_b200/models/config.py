@@ -104,3 +104,72 @@ class Config2D(BaseConfig):
             raise ValueError(f"train_loss_weights {self.train_loss_weights} not compatible with n_classes ({self.n_classes})")
         if not len(self.train_class_weights) == (2 if self.n_classes is None else self.n_classes + 1):
             raise ValueError(f"train_class_weights {self.train_class_weights} not compatible with n_classes ({self.n_classes})")
+
+
+class Config3D(BaseConfig):
+    """Configuration for a :class:`StarDist3D` model (stardist/models/model3d.py:129-311)."""
+
+    def __init__(self, axes='ZYX', rays=None, n_channel_in=1, grid=(1, 1, 1), n_classes=None, anisotropy=None, backbone='unet', **kwargs):
+        from ..rays3d import Rays_GoldenSpiral, rays_from_json
+        if rays is None:
+            if 'rays_json' in kwargs:
+                rays = rays_from_json(kwargs['rays_json'])
+            elif 'n_rays' in kwargs:
+                rays = Rays_GoldenSpiral(kwargs['n_rays'])
+            else:
+                rays = Rays_GoldenSpiral(96)
+        elif np.isscalar(rays):
+            rays = Rays_GoldenSpiral(rays)
+        super().__init__(axes=axes, n_channel_in=n_channel_in, n_channel_out=1 + len(rays))
+        self.n_rays = len(rays)
+        self.grid = _normalize_grid(grid, 3)
+        self.anisotropy = anisotropy if anisotropy is None else tuple(anisotropy)
+        self.backbone = str(backbone).lower()
+        self.rays_json = rays.to_json()
+        self.n_classes = None if n_classes is None else int(n_classes)
+        if 'anisotropy' in self.rays_json['kwargs']:
+            if self.rays_json['kwargs']['anisotropy'] is None and self.anisotropy is not None:
+                self.rays_json['kwargs']['anisotropy'] = self.anisotropy
+                print("Changing 'anisotropy' of rays to %s" % str(anisotropy))
+            elif self.rays_json['kwargs']['anisotropy'] is not None and self.anisotropy is not None and \
+                    tuple(self.rays_json['kwargs']['anisotropy']) != tuple(self.anisotropy):
+                import warnings
+                warnings.warn("Mismatch of 'anisotropy' of rays and 'anisotropy'.")
+        if self.backbone == 'unet':
+            self.unet_n_depth = 2
+            self.unet_kernel_size = 3, 3, 3
+            self.unet_n_filter_base = 32
+            self.unet_n_conv_per_depth = 2
+            self.unet_pool = 2, 2, 2
+            self.unet_activation = 'relu'
+            self.unet_last_activation = 'relu'
+            self.unet_batch_norm = False
+            self.unet_dropout = 0.0
+            self.unet_prefix = ''
+            self.net_conv_after_unet = 128
+        elif self.backbone == 'resnet':
+            raise NotImplementedError("the ResNet backbone is not implemented on the B200 path yet (SURVEY 8f rank 1)")
+        else:
+            raise ValueError("backbone '%s' not supported." % self.backbone)
+        self.net_input_shape = None, None, None, self.n_channel_in
+        self.net_mask_shape = None, None, None, 1
+        self.train_patch_size = 128, 128, 128
+        self.train_background_reg = 1e-4
+        self.train_foreground_only = 0.9
+        self.train_sample_cache = True
+        self.train_dist_loss = 'mae'
+        self.train_loss_weights = (1, 0.2) if self.n_classes is None else (1, 0.2, 1)
+        self.train_class_weights = (1, 1) if self.n_classes is None else (1,) * (self.n_classes + 1)
+        self.train_epochs = 400
+        self.train_steps_per_epoch = 100
+        self.train_learning_rate = 0.0003
+        self.train_batch_size = 1
+        self.train_n_val_patches = None
+        self.train_tensorboard = True
+        self.train_reduce_lr = {'factor': 0.5, 'patience': 40, 'min_delta': 0}
+        self.use_gpu = False
+        for k in ('n_dim', 'n_channel_out', 'n_rays', 'rays_json'):
+            try: del kwargs[k]
+            except KeyError: pass
+        self.update_parameters(False, **kwargs)
+        self.grid = _normalize_grid(self.grid, 3)

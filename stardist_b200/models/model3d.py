@@ -1,0 +1,131 @@
+"""StarDist3D on the B200 path.
+
+Mirrors stardist/models/model3d.py: Config3D (:129-311, in config.py), StarDist3D._build_unet
+(:360-399 -> UNetDeviceND), _instances_from_prediction (:589-674), _axes_div_by (:677-691).
+"""
+import numpy as np
+import torch
+
+from .. import _lib as L
+from ..utils import axes_check_and_normalize, _raise
+from ..nms import non_maximum_suppression_3d, non_maximum_suppression_3d_sparse
+from ..geometry.geom3d import polyhedron_to_label
+from ..rays3d import rays_from_json
+from ..matching import relabel_sequential
+from .base import StarDistBase
+from .config import Config3D
+from .unet_device import UNetDeviceND
+
+
+class StarDist3D(StarDistBase):
+    """StarDist3D model (prediction only)."""
+
+    def __init__(self, config=Config3D(), name=None, basedir='.', **kwargs):
+        super().__init__(config, name=name, basedir=basedir, **kwargs)
+
+    def _build(self):
+        self.config.backbone == 'unet' or _raise(NotImplementedError(self.config.backbone))
+        return UNetDeviceND(self.config, self.weights)
+
+    def _finish_labels(self, labels, overlap_label):
+        # map the overlap_label to something positive and back (model3d.py:632-645)
+        if overlap_label is not None and overlap_label < 0 and (overlap_label in labels):
+            overlap_mask = (labels == overlap_label)
+            overlap_label2 = max(set(np.unique(labels)) - {overlap_label}) + 1
+            labels[overlap_mask] = overlap_label2
+            labels, fwd, bwd = relabel_sequential(labels)
+            labels[labels == fwd[overlap_label2]] = overlap_label
+        else:
+            labels, _, _ = relabel_sequential(labels)
+        return labels
+
+    def _instances_from_prediction(self, img_shape, prob, dist, points=None, prob_class=None, prob_thresh=None,
+                                   nms_thresh=None, overlap_label=None, return_labels=True, scale=None, **nms_kwargs):
+        if prob_thresh is None: prob_thresh = self.thresholds.prob
+        if nms_thresh is None: nms_thresh = self.thresholds.nms
+        if prob_class is not None: raise NotImplementedError("multi-class prediction is not supported yet")
+        rays = rays_from_json(self.config.rays_json)
+        if points is not None:
+            points, probi, disti, indsi = non_maximum_suppression_3d_sparse(dist, prob, points, rays, nms_thresh=nms_thresh, **nms_kwargs)
+        else:
+            points, probi, disti = non_maximum_suppression_3d(dist, prob, rays, grid=self.config.grid,
+                                                              prob_thresh=prob_thresh, nms_thresh=nms_thresh, **nms_kwargs)
+        verbose = nms_kwargs.get('verbose', False)
+        if scale is not None:
+            if not (isinstance(scale, dict) and 'X' in scale and 'Y' in scale and 'Z' in scale):
+                raise ValueError("scale must be a dictionary with entries for 'X', 'Y', and 'Z'")
+            rescale = (1 / scale['Z'], 1 / scale['Y'], 1 / scale['X'])
+            points = points * np.array(rescale).reshape(1, 3)
+            rays = rays.copy(scale=rescale)
+        if return_labels:
+            labels = polyhedron_to_label(disti, points, rays=rays, prob=probi, shape=img_shape, overlap_label=overlap_label, verbose=verbose)
+            labels = self._finish_labels(labels, overlap_label)
+        else:
+            labels = None
+        res_dict = dict(dist=disti, points=points, prob=probi, rays=rays, rays_vertices=rays.vertices, rays_faces=rays.faces)
+        return labels, res_dict
+
+    # ------------------------------------------------------------------ device-resident (sparse) path
+    def _instances_from_candidates_device(self, img_shape, cand, nms_thresh=None, scale=None, return_labels=True,
+                                          overlap_label=None, use_bbox=True, use_kdtree=True, verbose=False):
+        lib = L.require_cuda()
+        if nms_thresh is None: nms_thresh = self.thresholds.nms
+        rays = rays_from_json(self.config.rays_json)
+        n, R = cand['n'], self.config.n_rays
+        dev = cand['dist'].device
+        verts_d = torch.from_numpy(np.ascontiguousarray(rays.vertices, np.float32)).to(dev)
+        faces_d = torch.from_numpy(np.ascontiguousarray(rays.faces, np.int32)).to(dev)
+        keep = torch.zeros(n, dtype=torch.uint8, device=dev)
+        if n > 0:
+            L.check(lib.sdb_nms3d(L.ptr(cand['dist']), L.ptr(cand['points_f32']), L.ptr(verts_d), L.ptr(faces_d), n, R, int(faces_d.shape[0]),
+                                 float(np.float32(nms_thresh)), int(use_bbox), int(use_kdtree), int(verbose), L.ptr(keep), L.stream_ptr()))
+        self._mark('nms_end')
+        sel = torch.nonzero(keep, as_tuple=False).flatten()
+        disti_d = cand['dist'].index_select(0, sel).contiguous()
+        probi_d = cand['prob'].index_select(0, sel)
+        pts_d = cand['points_f32'].index_select(0, sel).contiguous()
+        nk = int(sel.numel())
+        points = pts_d.cpu().numpy().astype(np.int64)
+        if scale is not None:
+            if not (isinstance(scale, dict) and 'X' in scale and 'Y' in scale and 'Z' in scale):
+                raise ValueError("scale must be a dictionary with entries for 'X', 'Y', and 'Z'")
+            rescale = (1 / scale['Z'], 1 / scale['Y'], 1 / scale['X'])
+            points = points * np.array(rescale).reshape(1, 3)
+            rays = rays.copy(scale=rescale)
+            verts_d = torch.from_numpy(np.ascontiguousarray(rays.vertices, np.float32)).to(dev)
+            pts_d = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(dev)
+        labels = None
+        if return_labels:
+            if nk == 0:
+                labels = np.zeros(tuple(img_shape), np.uint16)      # geom3d.py:128-131
+            else:
+                # survivors arrive in descending (stable) score order == painting order (geom3d.py:176-180)
+                lab_ids = torch.arange(1, nk + 1, dtype=torch.int32, device=dev)
+                lab_d = torch.empty(tuple(int(s) for s in img_shape), dtype=torch.int32, device=dev)
+                if overlap_label is not None and int(overlap_label) == 0:
+                    raise ValueError("overlap_label == 0 is not supported")
+                L.check(lib.sdb_polyhedron_to_label(L.ptr(disti_d), L.ptr(pts_d), L.ptr(verts_d), L.ptr(faces_d), nk, R, int(faces_d.shape[0]),
+                                                   L.ptr(lab_ids), int(img_shape[0]), int(img_shape[1]), int(img_shape[2]), 0,
+                                                   1 if overlap_label is not None else 0, 0 if overlap_label is None else int(overlap_label),
+                                                   L.ptr(lab_d), L.stream_ptr()))
+                self._mark('label_end')
+                labels = self._finish_labels(lab_d.cpu().numpy(), overlap_label)
+        disti = disti_d.cpu().numpy()
+        probi = probi_d.cpu().numpy()
+        self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + disti.nbytes + points.nbytes + probi.nbytes + (0 if labels is None else labels.nbytes)
+        res_dict = dict(dist=disti, points=points, prob=probi, rays=rays, rays_vertices=rays.vertices, rays_faces=rays.faces)
+        return labels, res_dict
+
+    def _axes_div_by(self, query_axes):
+        self.config.backbone == 'unet' or _raise(NotImplementedError())
+        query_axes = axes_check_and_normalize(query_axes)
+        assert len(self.config.unet_pool) == len(self.config.grid)
+        div_by = dict(zip(
+            self.config.axes.replace('C', ''),
+            tuple(p ** self.config.unet_n_depth * g for p, g in zip(self.config.unet_pool, self.config.grid))
+        ))
+        return tuple(div_by.get(a, 1) for a in query_axes)
+
+    @property
+    def _config_class(self):
+        return Config3D

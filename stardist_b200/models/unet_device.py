@@ -11,10 +11,13 @@ from .. import _lib as L
 from .weights import unet_layers
 
 
-class UNetDevice2D:
+class UNetDeviceND:
+    """exact-fp32 CUDA-core executor (csrc/unet_simt.cu) for 2-D (NHWC) and 3-D (NDHWC) U-Nets"""
+
     def __init__(self, config, weights, device=None):
         L.require_cuda()
         self.config = config
+        self.nd = config.n_dim
         self.device = torch.device("cuda") if device is None else torch.device(device)
         self.layers = unet_layers(config)
         self.w = {}
@@ -23,66 +26,73 @@ class UNetDevice2D:
                             torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device))
         if config.unet_batch_norm:
             raise NotImplementedError("unet_batch_norm=True is not supported on this path")
-        if tuple(config.unet_kernel_size) != (3, 3) or tuple(config.unet_pool) != (2, 2):
-            raise NotImplementedError("only 3x3 kernels and 2x2 pooling are supported")
+        if tuple(config.unet_kernel_size) != (3,) * self.nd:
+            raise NotImplementedError("only 3^d kernels are supported")
         if config.n_classes is not None:
             raise NotImplementedError("multi-class head is not supported yet")
 
-    def _conv(self, x, x_lo, name, relu):
+    @staticmethod
+    def _dhw(x):
+        return (1,) + tuple(x.shape[1:3]) if x.dim() == 4 else tuple(x.shape[1:4])
+
+    def _conv(self, x, x_lo, name, relu, up):
         lib = L.load()
         k, b = self.w[name]
-        n, h, w, c_skip = x.shape
+        n = x.shape[0]; d, h, w = self._dhw(x); c_skip = x.shape[-1]
         c_lo = 0 if x_lo is None else x_lo.shape[-1]
         cout = k.shape[-1]
-        assert k.shape[2] == c_skip + c_lo, (name, k.shape, c_skip, c_lo)
-        out = torch.empty((n, h, w, cout), dtype=torch.float32, device=x.device)
-        L.check(lib.sdb_conv3x3_2d(L.ptr(x), L.ptr(x_lo), n, h, w, c_skip, c_lo, L.ptr(k), L.ptr(b), cout,
-                                  1 if relu else 0, L.ptr(out), L.stream_ptr()))
+        assert k.shape[-2] == c_skip + c_lo, (name, k.shape, c_skip, c_lo)
+        out = torch.empty(tuple(x.shape[:-1]) + (cout,), dtype=torch.float32, device=x.device)
+        uz, uy, ux = ((1,) + tuple(up)) if len(up) == 2 else tuple(up)
+        L.check(lib.sdb_conv3_nd(L.ptr(x), L.ptr(x_lo), n, d, h, w, c_skip, c_lo, int(uz), int(uy), int(ux), L.ptr(k), L.ptr(b), cout,
+                                1 if self.nd == 2 else 3, 1 if relu else 0, L.ptr(out), L.stream_ptr()))
         return out
 
-    def _pool(self, x):
+    def _pool(self, x, pool):
         lib = L.load()
-        n, h, w, c = x.shape
-        out = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=x.device)
-        L.check(lib.sdb_maxpool2x2_2d(L.ptr(x), n, h, w, c, L.ptr(out), L.stream_ptr()))
+        n = x.shape[0]; d, h, w = self._dhw(x); c = x.shape[-1]
+        pz, py, px = ((1,) + tuple(pool)) if len(pool) == 2 else tuple(pool)
+        osp = (h // py, w // px) if self.nd == 2 else (d // pz, h // py, w // px)
+        out = torch.empty((n,) + osp + (c,), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_maxpool_nd(L.ptr(x), n, d, h, w, c, int(pz), int(py), int(px), L.ptr(out), L.stream_ptr()))
         return out
 
     def forward(self, x):
-        """x: float32 [N,H,W,Cin] on the device -> (prob [N,H/g,W/g], dist [N,H/g,W/g,R])"""
+        """x: float32 [N,(D,)H,W,Cin] on the device -> (prob [N,...], dist [N,...,R])"""
         lib = L.load()
         assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
         skips = {}
-        lo = None
+        lo, up = None, (1,) * self.nd
         for l in self.layers:
             kind = l['kind']
             if kind == 'conv':
                 act = l['act']
                 if act not in ('relu', 'linear'):
                     raise NotImplementedError("activation %s" % act)
-                if lo is not None:
-                    x = self._conv(x, lo, l['name'], act == 'relu'); lo = None
-                else:
-                    x = self._conv(x, None, l['name'], act == 'relu')
+                x = self._conv(x, lo, l['name'], act == 'relu', up)
+                lo, up = None, (1,) * self.nd
             elif kind == 'pool':
-                if tuple(l['pool']) != (2, 2):
-                    raise NotImplementedError("anisotropic pooling")
                 if 'save_skip' in l:
                     skips[l['save_skip']] = x
-                x = self._pool(x)
+                x = self._pool(x, l['pool'])
             elif kind == 'up':
-                lo = x                      # consumed by the next conv together with the skip
+                lo, up = x, tuple(l['pool'])           # consumed by the next conv together with the skip
                 x = skips.pop(l['skip'])
             elif kind == 'head':
                 break
         feat = x
-        n, h, w, cf = feat.shape
+        cf = feat.shape[-1]
+        npix = int(np.prod(feat.shape[:-1]))
         R = self.config.n_rays
         (wp, bp), (wd, bd) = self.w['prob'], self.w['dist']
-        prob = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
-        dist = torch.empty((n, h, w, R), dtype=torch.float32, device=x.device)
-        L.check(lib.sdb_heads_2d(L.ptr(feat), n * h * w, cf, L.ptr(wp), L.ptr(bp), L.ptr(wd), L.ptr(bd), R,
+        prob = torch.empty(tuple(feat.shape[:-1]), dtype=torch.float32, device=x.device)
+        dist = torch.empty(tuple(feat.shape[:-1]) + (R,), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_heads_2d(L.ptr(feat), npix, cf, L.ptr(wp), L.ptr(bp), L.ptr(wd), L.ptr(bd), R,
                                 L.ptr(prob), L.ptr(dist), L.stream_ptr()))
         return prob, dist
+
+
+UNetDevice2D = UNetDeviceND
 
 
 class UNetDevice2DTC:

@@ -96,3 +96,41 @@ def test_empty_inputs_3d(sd):
     out = c_non_max_suppression_inds(np.zeros((0, 16), np.float32), np.zeros((0, 3), np.float32), v, f, np.zeros(0, np.float32), 1, 1, 0, np.float32(.4))
     assert out.shape == (0,)
     assert sd.polyhedron_to_label(np.zeros((0, 16)), np.zeros((0, 3)), rays, (5, 6, 7), verbose=False).shape == (5, 6, 7)
+
+
+def test_unet3d_forward_vs_torch_fp32(sd):
+    import torch
+    from oracle import unet_torch
+    cfg = sd.Config3D(n_rays=16, rays=None) if False else sd.Config3D(rays=sd.Rays_GoldenSpiral(16))
+    model = sd.StarDist3D(cfg, name=None, basedir=None)
+    rng = np.random.default_rng(3)
+    vol = rng.uniform(0, 1, (16, 32, 48)).astype(np.float32)
+    x = torch.from_numpy(vol[None, ..., None]).cuda()
+    prob, dist = model.net.forward(x)
+    rp, rd = unet_torch.forward(cfg, model.weights, vol[None, ..., None])
+    p, d = prob.cpu().numpy(), dist.cpu().numpy()
+    assert p.shape == rp.shape and d.shape == rd.shape
+    assert np.max(np.abs(p - rp)) <= 1e-5 * max(1.0, np.max(np.abs(rp)))
+    assert np.max(np.abs(d - rd)) <= 1e-5 * max(1e-3, np.max(np.abs(rd))) + 1e-7
+
+
+def test_predict_instances_3d_vs_oracle(sd):
+    if not ref_ext.available(): pytest.skip("oracle/_ref not present")
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import pipeline3d
+    rays = sd.Rays_GoldenSpiral(24)
+    cfg = sd.Config3D(rays=rays)
+    model = sd.StarDist3D(cfg, name=None, basedir=None)
+    # give the random-init net a usable dist head: bias 4.0 -> polyhedra of radius ~4 voxels
+    k, b = model.weights['dist']; model.weights['dist'] = (k, b + np.float32(4.0)); model._net = None
+    rng = np.random.default_rng(4)
+    vol = rng.uniform(0, 1, (20, 40, 36)).astype(np.float32)
+    prob, _ = model.predict(vol)
+    pthr = float(np.quantile(prob, 0.97))
+    labels, res = model.predict_instances(vol, prob_thresh=pthr, nms_thresh=0.3)
+    ref_labels, ref = pipeline3d.predict_instances(cfg, rays, vol, pthr, 0.3, cand_from=model)
+    assert labels.shape == vol.shape and len(res['prob']) > 2
+    assert np.array_equal(res['points'], ref['points'])
+    assert np.array_equal(res['prob'], ref['prob'])
+    assert np.array_equal(res['dist'], ref['dist'])
+    assert np.array_equal(labels, ref_labels)
