@@ -146,10 +146,11 @@ int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_
  * Activations are two fp16 planes (hi, lo) per tensor, hi = fp16(v), lo = fp16(v - hi); weights are
  * split the same way into [9][cout][cin] planes by sdb_split_weights.  fp32 accumulation in TMEM. */
 int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
-                   int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, const float* d_bias, int cout,
+                   int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
                    int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream);
 int sdb_tc_error_check(sdb_stream_t stream);
-int sdb_split_weights(const float* d_w, int cin, int cout, void* w_hi, void* w_lo, sdb_stream_t stream);
+/* w_scale: power of two the weights are multiplied by before the split (undone on the accumulator) */
+int sdb_split_weights(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream);
 int sdb_stem_split(const float* d_in, int n, int h, int w, int cin, const float* d_w, const float* d_b, int cout, int relu,
                    void* out_hi, void* out_lo, sdb_stream_t stream);
 int sdb_maxpool_split(const void* in_hi, const void* in_lo, int n, int h, int w, int c, void* out_hi, void* out_lo, sdb_stream_t stream);

@@ -34,9 +34,9 @@ def _declare(lib):
     lib.sdb_conv3_nd.argtypes = [P, P] + [c_int] * 9 + [P, P, c_int, c_int, c_int, P, P]
     lib.sdb_maxpool_nd.argtypes = [P] + [c_int] * 8 + [P, P]
     lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
-    lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int, P, P, P]
+    lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
     lib.sdb_tc_error_check.argtypes = [P]
-    lib.sdb_split_weights.argtypes = [P, c_int, c_int, P, P, P]
+    lib.sdb_split_weights.argtypes = [P, c_int, c_int, c_float, P, P, P]
     lib.sdb_stem_split.argtypes = [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P]
     lib.sdb_maxpool_split.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, P]
     lib.sdb_heads_split.argtypes = [P, P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]

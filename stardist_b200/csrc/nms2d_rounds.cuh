@@ -30,8 +30,16 @@ __device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSwe
 
 // counters: [0] undecided at round start, [1] pairs emitted this round, [2] pair tests (total),
 //           [3] slow-path pool overflows (fatal), [4] slow pairs this round, [5] sticky "pair list
-//           overflowed" flag: every later kernel of the batch becomes a no-op until the host recovers
-__global__ void k_frontier2(NmsArrays A, int round, unsigned int* __restrict__ counters) {
+//           overflowed" flag: every later kernel of the batch becomes a no-op until the host recovers,
+//           [6] candidates kept in this round (length of the kept list)
+//
+// K_frontier is PULL based with a per-candidate cursor: the 3x3 cell neighbourhood is scanned in a
+// fixed order and the scan resumes where it stopped in the previous round -- an item that did not
+// block once (h >= c, h decided, or h cannot reach c) never blocks later, so the total scan work over
+// all rounds is one pass over the neighbourhood.  K_pairs is PUSH based: one warp per candidate kept
+// in this round enumerates the undecided candidates it reaches (only ~n_kept * degree work in total).
+__global__ void k_frontier2(NmsArrays A, int round, int2* __restrict__ cursor, int* __restrict__ kept_list,
+                            unsigned int* __restrict__ counters) {
   if (counters[5]) return;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= A.n) return;
@@ -42,46 +50,67 @@ __global__ void k_frontier2(NmsArrays A, int round, unsigned int* __restrict__ c
   const int kept_now = ST_KEPT_BASE + round;
   int ccx = 0, ccy = 0;
   if (!A.G.all_pairs) { ccx = cell_of(cx, A.G.minx, A.G.cell, A.G.gx); ccy = cell_of(cy, A.G.miny, A.G.cell, A.G.gy); }
+  int2 cur = cursor[c];          // (neighbour cell 0..8, offset inside that cell)
   bool blocked = false;
-  for (int yy = max(ccy - 1, 0); yy <= min(ccy + 1, A.G.gy - 1) && !blocked; ++yy)
-    for (int xx = max(ccx - 1, 0); xx <= min(ccx + 1, A.G.gx - 1) && !blocked; ++xx) {
-      const int cell = yy * A.G.gx + xx;
-      const unsigned int e = A.cell_start[cell + 1];
-      for (unsigned int t = A.cell_start[cell]; t < e; ++t) {
-        const int h = A.items[t];
-        if (h >= c) continue;
-        const int sh = A.state[h];
-        if (sh != ST_UNDECIDED && sh != kept_now) continue;
-        if (reaches(A, h, c, cy, cx, bc)) { blocked = true; break; }
-      }
+  for (int k = cur.x; k < 9 && !blocked; ++k) {
+    const int yy = ccy + k / 3 - 1, xx = ccx + k % 3 - 1;
+    if (yy < 0 || yy >= A.G.gy || xx < 0 || xx >= A.G.gx) { cur.x = k + 1; cur.y = 0; continue; }
+    const int cell = yy * A.G.gx + xx;
+    const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
+    unsigned int t = b + (unsigned int)cur.y;
+    for (; t < e; ++t) {
+      const int h = A.items[t];
+      if (h >= c) continue;
+      const int sh = A.state[h];
+      if (sh != ST_UNDECIDED && sh != kept_now) continue;
+      if (reaches(A, h, c, cy, cx, bc)) { blocked = true; break; }
     }
-  if (!blocked) A.state[c] = kept_now;
+    if (blocked) { cur.x = k; cur.y = (int)(t - b); }
+    else { cur.x = k + 1; cur.y = 0; }
+  }
+  cursor[c] = cur;
+  if (!blocked) {
+    A.state[c] = kept_now;
+    kept_list[atomicAdd(&counters[6], 1u)] = c;
+  }
 }
 
-// emit (kept-now h, undecided c) pairs that the reference would test (:548-576)
-__global__ void k_pairs(NmsArrays A, int round, int2* __restrict__ pairs, unsigned int cap, unsigned int* __restrict__ counters) {
+// one warp per candidate kept in this round: emit the (h, c) pairs the reference would test (:548-576)
+__global__ void k_pairs(NmsArrays A, int round, const int* __restrict__ kept_list, int2* __restrict__ pairs, unsigned int cap,
+                        unsigned int* __restrict__ counters) {
   if (counters[5]) return;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.n) return;
-  if (A.state[c] != ST_UNDECIDED) return;
-  const float cy = A.points[2 * c], cx = A.points[2 * c + 1];
-  const int4 bc = A.bbox[c];
-  const int kept_now = ST_KEPT_BASE + round;
-  int ccx = 0, ccy = 0;
-  if (!A.G.all_pairs) { ccx = cell_of(cx, A.G.minx, A.G.cell, A.G.gx); ccy = cell_of(cy, A.G.miny, A.G.cell, A.G.gy); }
-  for (int yy = max(ccy - 1, 0); yy <= min(ccy + 1, A.G.gy - 1); ++yy)
-    for (int xx = max(ccx - 1, 0); xx <= min(ccx + 1, A.G.gx - 1); ++xx) {
-      const int cell = yy * A.G.gx + xx;
-      const unsigned int e = A.cell_start[cell + 1];
-      for (unsigned int t = A.cell_start[cell]; t < e; ++t) {
-        const int h = A.items[t];
-        if (h >= c) continue;
-        if (A.state[h] != kept_now) continue;
-        if (!reaches(A, h, c, cy, cx, bc)) continue;
-        const unsigned int k = atomicAdd(&counters[1], 1u);
-        if (k < cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
+  const unsigned int n_kept = counters[6];
+  const int lane = threadIdx.x & 31;
+  const unsigned int warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_kept; w += warps) {
+    const int h = kept_list[w];
+    const float hy = A.points[2 * h], hx = A.points[2 * h + 1];
+    const int4 bh = A.bbox[h];
+    const float rr = A.max_dist + A.radius[h];
+    int hcx = 0, hcy = 0;
+    if (!A.G.all_pairs) { hcx = cell_of(hx, A.G.minx, A.G.cell, A.G.gx); hcy = cell_of(hy, A.G.miny, A.G.cell, A.G.gy); }
+    for (int yy = max(hcy - 1, 0); yy <= min(hcy + 1, A.G.gy - 1); ++yy)
+      for (int xx = max(hcx - 1, 0); xx <= min(hcx + 1, A.G.gx - 1); ++xx) {
+        const int cell = yy * A.G.gx + xx;
+        const unsigned int e = A.cell_start[cell + 1];
+        for (unsigned int t = A.cell_start[cell] + lane; t < e; t += 32) {
+          const int c = A.items[t];
+          if (c <= h) continue;
+          if (A.state[c] != ST_UNDECIDED) continue;
+          if (!A.G.all_pairs) {
+            const float d0 = hy - A.points[2 * c], d1 = hx - A.points[2 * c + 1];
+            const float dd = d0 * d0 + d1 * d1;
+            if (!(dd < rr * rr)) continue;
+          }
+          if (A.use_bbox) {
+            const int4 bc = A.bbox[c];
+            if (!(bc.x <= bh.y && bh.x <= bc.y && bc.z <= bh.w && bh.z <= bc.w)) continue;
+          }
+          const unsigned int k = atomicAdd(&counters[1], 1u);
+          if (k < cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
+        }
       }
-    }
+  }
 }
 __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ counters) {
   if (counters[1] > cap) counters[5] = 1;
@@ -119,7 +148,7 @@ __global__ void __launch_bounds__(64) k_clip_slow(NmsArrays A, const int2* __res
 
 __global__ void k_reset_counters(unsigned int* counters) {
   if (counters[5]) return;
-  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; }
+  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; }
 }
 
 template <int NV>
@@ -129,13 +158,16 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
   const int n = A.n;
   constexpr int BATCH = 4;     // rounds launched per host synchronisation
   size_t cap = std::max<size_t>((size_t)n * 2, 1 << 15);
-  sdb::DevBuf b_pairs, b_slow;
+  sdb::DevBuf b_pairs, b_slow, b_cursor, b_kept;
+  SDB_CUDA(b_cursor.alloc((size_t)n * sizeof(int2), st));
+  SDB_CUDA(b_kept.alloc((size_t)n * sizeof(int), st));
+  SDB_CUDA(cudaMemsetAsync(b_cursor.p, 0, (size_t)n * sizeof(int2), st));
   SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
   SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
   SDB_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), st));
   int round = 0;
   auto launch_pair_stage = [&](int r) -> int {
-    SDB_LAUNCH(k_pairs, cdiv(n, 256), 256, 0, st, A, r, b_pairs.as<int2>(), (unsigned int)cap, d_counters);
+    SDB_LAUNCH(k_pairs, 148 * 8, 256, 0, st, A, r, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)cap, d_counters);
     SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
     // grid sized for the capacity; threads beyond counters[1] exit immediately
     SDB_LAUNCH((k_clip<NV>), cdiv(cap, 128), 128, 0, st, A, b_pairs.as<int2>(), (unsigned int)cap, b_slow.as<int2>(), d_counters);
@@ -146,7 +178,7 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     const int round0 = round;
     for (int b = 0; b < BATCH; ++b, ++round) {
       SDB_LAUNCH(k_reset_counters, 1, 32, 0, st, d_counters);
-      SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, d_counters);
+      SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), d_counters);
       if (launch_pair_stage(round)) return 1;
       SDB_CUDA(cudaMemcpyAsync(h_pin + 8 * b, d_counters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     }
@@ -161,7 +193,7 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
         cap = (size_t)c[1] + (size_t)c[1] / 2 + 1024;
         SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
         SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
-        const unsigned int zeros[8] = {c[0], 0, c[2], 0, 0, 0, 0, 0};
+        const unsigned int zeros[8] = {c[0], 0, c[2], 0, 0, 0, c[6], 0};
         SDB_CUDA(cudaMemcpyAsync(d_counters, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st));
         round = round0 + b;
         if (launch_pair_stage(round)) return 1;

@@ -42,6 +42,7 @@ struct ConvParams {
   int c_total;           // Cin
   int relu;
   int up2x;              // write every output pixel to the 2x2 block of a (2H, 2W) tensor
+  float acc_scale;       // 2^-k: the weights were multiplied by 2^k before the hi/lo split (keeps w_lo out of the fp16 subnormals)
   const float* bias;
   __half* out_hi; __half* out_lo;
   unsigned int* error_flag;
@@ -226,7 +227,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
           __align__(16) __half lo[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float v = __uint_as_float(r[j]) + __ldg(P.bias + c0 + j);
+            float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + c0 + j);
             if (P.relu) v = fmaxf(v, 0.f);
             const __half h = __float2half_rn(v);
             hi[j] = h;
@@ -379,12 +380,12 @@ k_heads_split(const __half* __restrict__ f_hi, const __half* __restrict__ f_lo, 
 }
 
 // weights (3,3,Cin,Cout) fp32 -> [tap][Cout][Cin] fp16 hi / lo
-__global__ void k_split_weights(const float* __restrict__ w, int Cin, int Cout, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
+__global__ void k_split_weights(const float* __restrict__ w, int Cin, int Cout, float scale, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
   const long long total = 9LL * Cin * Cout;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(e % Cin); long long r = e / Cin;
     const int co = (int)(r % Cout); const int tap = (int)(r / Cout);
-    const float v = w[((size_t)tap * Cin + ci) * Cout + co];
+    const float v = w[((size_t)tap * Cin + ci) * Cout + co] * scale;
     const __half h = __float2half_rn(v);
     w_hi[e] = h; w_lo[e] = __float2half_rn(v - __half2float(h));
   }
@@ -452,7 +453,7 @@ static unsigned int* g_err_flag = nullptr;      // device flag shared by all lau
 // [n,h,w,c] hi/lo planes; weights are the pre-split [9][cout][cin] planes; output hi/lo planes are
 // [n,h,w,cout] or, with up2x, [n,2h,2w,cout] with every pixel replicated 2x2 (nearest up-sampling).
 extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
-                              int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, const float* d_bias, int cout,
+                              int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
                               int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int cin = c_src0 + c_src1;
@@ -467,7 +468,7 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   } else { a0h = a1h; a0l = a1l; }
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, kc) || make_w_map(&wl, (const __half*)w_lo, cin, cout, kc)) return 1;
   ConvParams P;
-  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias;
+  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag;
 #define SDB_TC(NN, KK) return launch_tc<NN, KK>(a0h, a0l, a1h, a1l, wh, wl, P, n, st)
   if (kc == 64) {
@@ -489,10 +490,10 @@ extern "C" int sdb_tc_error_check(sdb_stream_t stream) {
   return 0;
 }
 
-extern "C" int sdb_split_weights(const float* d_w, int cin, int cout, void* w_hi, void* w_lo, sdb_stream_t stream) {
+extern "C" int sdb_split_weights(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = 9LL * cin * cout;
-  SDB_LAUNCH(k_split_weights, (int)std::min<long long>(cdiv(total, 256), 1024), 256, 0, st, d_w, cin, cout, (__half*)w_hi, (__half*)w_lo);
+  SDB_LAUNCH(k_split_weights, (int)std::min<long long>(cdiv(total, 256), 1024), 256, 0, st, d_w, cin, cout, w_scale, (__half*)w_hi, (__half*)w_lo);
   return 0;
 }
 

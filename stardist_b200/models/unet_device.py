@@ -95,6 +95,15 @@ class UNetDeviceND:
 UNetDevice2D = UNetDeviceND
 
 
+def tc_weight_scale(k):
+    """power of two that brings max|w| into [1024, 2048): the fp16 'lo' parts of all but negligible
+    weights then stay in the normal range (no precision loss), and products stay far from overflow"""
+    m = float(np.max(np.abs(k)))
+    if not np.isfinite(m) or m <= 0:
+        return 1.0
+    return float(2.0 ** (10 - int(np.floor(np.log2(m)))))
+
+
 class UNetDevice2DTC:
     """tcgen05 / TMA / TMEM executor (csrc/unet_tc.cu).  Activations are [2, N, H, W, C] float16
     tensors (plane 0 = hi, plane 1 = lo, value = hi + lo); convolutions run as three fp16 tensor-core
@@ -121,7 +130,8 @@ class UNetDevice2DTC:
             if k.ndim == 4 and k.shape[0] == 3 and k.shape[2] % 32 == 0:
                 cin, cout = k.shape[2], k.shape[3]
                 ws = torch.empty((2, 9, cout, cin), dtype=torch.float16, device=self.device)
-                L.check(lib.sdb_split_weights(L.ptr(kd), cin, cout, L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
+                ent['scale'] = tc_weight_scale(k)
+                L.check(lib.sdb_split_weights(L.ptr(kd), cin, cout, ent['scale'], L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
                 ent['split'] = ws
             self.w[name] = ent
 
@@ -167,7 +177,7 @@ class UNetDevice2DTC:
                     out = torch.empty((2, n_, oh, ow, cout), dtype=torch.float16, device=x.device)
                     ws = ent['split']
                     L.check(lib.sdb_conv3x3_tc(L.ptr(lo[0]) if lo is not None else L.ptr(None), L.ptr(lo[1]) if lo is not None else L.ptr(None), c0,
-                                               L.ptr(cur[0]), L.ptr(cur[1]), c1, n_, hh, ww, L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(ent['b']),
+                                               L.ptr(cur[0]), L.ptr(cur[1]), c1, n_, hh, ww, L.ptr(ws[0]), L.ptr(ws[1]), ent['scale'], L.ptr(ent['b']),
                                                cout, relu, up2x, L.ptr(out[0]), L.ptr(out[1]), st))
                     lo = None
                 cur = out

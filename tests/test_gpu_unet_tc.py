@@ -38,15 +38,17 @@ def test_conv3x3_tc_single_layer(h, w, c0, c1, cout, relu, up2x):
     k = (torch.randn((3, 3, cin, cout), generator=g) * (2.0 / (9 * cin)) ** 0.5).cuda()
     b = (torch.randn(cout, generator=g) * 0.1).cuda()
     xs = _split(x)                       # [2,n,h,w,cin]
-    x_eff = xs[0].float() + xs[1].float()
+    x_eff = xs[0].double() + xs[1].double()
     ws = torch.empty((2, 9, cout, cin), dtype=torch.float16, device='cuda')
-    L.check(lib.sdb_split_weights(L.ptr(k.contiguous()), cin, cout, L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
-    k_eff = (ws[0].float() + ws[1].float()).reshape(3, 3, cout, cin).permute(0, 1, 3, 2)
+    from stardist_b200.models.unet_device import tc_weight_scale
+    wsc = tc_weight_scale(k.cpu().numpy())
+    L.check(lib.sdb_split_weights(L.ptr(k.contiguous()), cin, cout, wsc, L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
+    k_eff = ((ws[0].double() + ws[1].double()) / wsc).reshape(3, 3, cout, cin).permute(0, 1, 3, 2)
     src1 = xs[..., c0:].contiguous(); src0 = xs[..., :c0].contiguous() if c0 else None
     oh, ow = (2 * h, 2 * w) if up2x else (h, w)
     out = torch.zeros((2, 2, oh, ow, cout), dtype=torch.float16, device='cuda')
     L.check(lib.sdb_conv3x3_tc(L.ptr(src0[0]) if c0 else L.ptr(None), L.ptr(src0[1]) if c0 else L.ptr(None), c0,
-                               L.ptr(src1[0]), L.ptr(src1[1]), c1, 2, h, w, L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(b), cout, relu, up2x,
+                               L.ptr(src1[0]), L.ptr(src1[1]), c1, 2, h, w, L.ptr(ws[0]), L.ptr(ws[1]), wsc, L.ptr(b), cout, relu, up2x,
                                L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
     L.check(lib.sdb_tc_error_check(L.stream_ptr()))
     got = (out[0].float() + out[1].float()).double()
