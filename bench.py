@@ -21,6 +21,7 @@ SHAPE = (1024, 1024)
 N_RAYS = 32
 PROB_THRESH = 0.5          # the reference's default thresholds (base.py:241)
 NMS_THRESH = 0.4
+REF_CROP = 512             # CPU arms time a 512x512 crop of the same image per step (bounded sample)
 
 
 class ClockSampler(threading.Thread):
@@ -72,6 +73,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")     # see cpu_baseline(): two OpenMP runtimes share the process
     import torch
     from stardist_b200.models.config import Config2D
     from oracle import pipeline2d
@@ -81,6 +83,7 @@ def run_reference(args):
     cfg = Config2D(n_rays=N_RAYS)
     w = bench_data.bench_weights_2d(cfg)
     img, _ = bench_data.synthetic_image(SHAPE, seed=0)
+    img = np.ascontiguousarray(img[:REF_CROP, :REF_CROP])      # bounded sample of the workload (one quarter of the image)
     pthr = PROB_THRESH
     def step():
         prob, dist, pads = pipeline2d.predict(cfg, w, img)
@@ -99,7 +102,7 @@ def run_reference(args):
         "config": {"workload": "StarDist2D predict_instances, 1024x1024, n_rays=32, seeded synthetic U-Net weights (configs[1])",
                    "prob_thresh": PROB_THRESH, "weights": "seeded Glorot body + fitted heads (bench_data.py)", "nms_thresh": NMS_THRESH},
         "cpu_baseline": {"value": v, "unit": "instances/s", "cores": cores, "kind": "reference",
-                         "sample": "%d full 1024^2 images; NMS = reference C++/OpenMP (oracle/_ref), U-Net = torch-CPU fp32 stand-in for TF-CPU, labels = numpy restatement" % args.steps},
+                         "sample": "%d steps of one %dx%d crop of the 1024^2 image; NMS = reference C++/OpenMP (oracle/_ref), U-Net = torch-CPU fp32 stand-in for TF-CPU, labels = numpy restatement" % (args.steps, REF_CROP, REF_CROP)},
         "e2e": {"value": v, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -218,19 +221,16 @@ def main():
 
 
 def cpu_baseline(cfg, weights, img, pthr):
-    """bounded CPU sample of the same workload: 2 full images through the oracle path"""
-    import torch
-    from oracle import pipeline2d
-    cores = os.cpu_count(); torch.set_num_threads(cores)
-    t0 = time.perf_counter(); n = 0; reps = 2
-    for _ in range(reps):
-        prob, dist, pads = pipeline2d.predict(cfg, weights, img)
-        pa, da, pts = pipeline2d.candidates(cfg, prob, dist, pads, img.shape, pthr)
-        labels, res = pipeline2d.instances(cfg, img.shape, pa, da, pts, NMS_THRESH)
-        n += len(res['prob'])
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "instances/s", "cores": cores, "kind": "reference",
-            "sample": "%d full 1024^2 images: torch-CPU fp32 U-Net (TF-CPU stand-in) + reference C++/OpenMP NMS (oracle/_ref) + numpy labels" % reps}
+    """bounded CPU sample of the same workload, timed in a fresh process (`--impl reference`) so that the
+    OpenMP runtime of the reference extension starts with OMP_WAIT_POLICY=PASSIVE (torch and the reference
+    C++ bring two OpenMP runtimes into one process; with the default spin-waiting they starve each other
+    on many-core hosts)"""
+    env = dict(os.environ); env.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"): env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)["cpu_baseline"]
 
 
 if __name__ == "__main__":

@@ -148,6 +148,11 @@ int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_
 int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
                    int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
                    int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream);
+/* halo-reuse variant: CTA tile 2 rows x 128 px, the halo is loaded once per 32-channel block and all nine
+ * taps address it through shifted UMMA descriptors (boff_mode: descriptor base-offset convention) */
+int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                    int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
+                    int relu, int up2x, int boff_mode, void* out_hi, void* out_lo, sdb_stream_t stream);
 int sdb_tc_error_check(sdb_stream_t stream);
 /* w_scale: power of two the weights are multiplied by before the split (undone on the accumulator) */
 int sdb_split_weights(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream);

@@ -203,10 +203,10 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   SDB_CUDA(b_items.alloc((size_t)n * sizeof(int), st));
   SDB_CUDA(b_state.alloc((size_t)n * sizeof(int), st));
   SDB_CUDA(b_slow.alloc((size_t)n * sizeof(int), st));
-  SDB_CUDA(b_counters.alloc(8 * sizeof(unsigned int), st));
+  SDB_CUDA(b_counters.alloc(16 * sizeof(unsigned int), st));
   SDB_CUDA(cudaMemsetAsync(b_counts.p, 0, (size_t)(n_cells + 1) * sizeof(unsigned int), st));
   SDB_CUDA(cudaMemsetAsync(b_state.p, 0, (size_t)n * sizeof(int), st));
-  SDB_CUDA(cudaMemsetAsync(b_counters.p, 0, 8 * sizeof(unsigned int), st));
+  SDB_CUDA(cudaMemsetAsync(b_counters.p, 0, 16 * sizeof(unsigned int), st));
   SDB_LAUNCH(k_cell_count, cdiv(n, 256), 256, 0, st, d_points, n, G, b_cellpt.as<int>(), b_counts.as<unsigned int>());
   SDB_LAUNCH(k_scan_tiles, n_tiles, SCAN_T, 0, st, b_counts.as<unsigned int>(), b_start.as<unsigned int>(), n_cells + 1, b_tiles.as<unsigned int>());
   SDB_LAUNCH(k_scan_sums, 1, 1024, 0, st, b_tiles.as<unsigned int>(), n_tiles);

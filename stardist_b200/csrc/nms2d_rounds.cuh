@@ -38,11 +38,16 @@ __device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSwe
 // block once (h >= c, h decided, or h cannot reach c) never blocks later, so the total scan work over
 // all rounds is one pass over the neighbourhood.  K_pairs is PUSH based: one warp per candidate kept
 // in this round enumerates the undecided candidates it reaches (only ~n_kept * degree work in total).
+// The undecided candidates are kept in a compacted list (double buffered: blocked candidates are
+// appended to list_out, counters[7] = its length; round 0 reads the identity list).
 __global__ void k_frontier2(NmsArrays A, int round, int2* __restrict__ cursor, int* __restrict__ kept_list,
-                            unsigned int* __restrict__ counters) {
+                            const int* __restrict__ list_in, unsigned int n_in_or_all, const unsigned int* __restrict__ n_in_dev,
+                            int* __restrict__ list_out, unsigned int* __restrict__ counters) {
   if (counters[5]) return;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.n) return;
+  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned int n_in = n_in_dev ? *n_in_dev : n_in_or_all;
+  if (i >= n_in) return;
+  const int c = list_in ? list_in[i] : (int)i;
   if (A.state[c] != ST_UNDECIDED) return;
   atomicAdd(&counters[0], 1u);
   const float cy = A.points[2 * c], cx = A.points[2 * c + 1];
@@ -72,6 +77,8 @@ __global__ void k_frontier2(NmsArrays A, int round, int2* __restrict__ cursor, i
   if (!blocked) {
     A.state[c] = kept_now;
     kept_list[atomicAdd(&counters[6], 1u)] = c;
+  } else {
+    list_out[atomicAdd(&counters[7], 1u)] = c;
   }
 }
 
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(64) k_clip_slow(NmsArrays A, const int2* __res
 
 __global__ void k_reset_counters(unsigned int* counters) {
   if (counters[5]) return;
-  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; }
+  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; counters[8] = counters[7]; counters[7] = 0; }
 }
 
 template <int NV>
@@ -158,13 +165,15 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
   const int n = A.n;
   constexpr int BATCH = 4;     // rounds launched per host synchronisation
   size_t cap = std::max<size_t>((size_t)n * 2, 1 << 15);
-  sdb::DevBuf b_pairs, b_slow, b_cursor, b_kept;
+  sdb::DevBuf b_pairs, b_slow, b_cursor, b_kept, b_list0, b_list1;
+  SDB_CUDA(b_list0.alloc((size_t)n * sizeof(int), st));
+  SDB_CUDA(b_list1.alloc((size_t)n * sizeof(int), st));
   SDB_CUDA(b_cursor.alloc((size_t)n * sizeof(int2), st));
   SDB_CUDA(b_kept.alloc((size_t)n * sizeof(int), st));
   SDB_CUDA(cudaMemsetAsync(b_cursor.p, 0, (size_t)n * sizeof(int2), st));
   SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
   SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
-  SDB_CUDA(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned int), st));
+  SDB_CUDA(cudaMemsetAsync(d_counters, 0, 16 * sizeof(unsigned int), st));
   int round = 0;
   auto launch_pair_stage = [&](int r) -> int {
     SDB_LAUNCH(k_pairs, 148 * 8, 256, 0, st, A, r, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)cap, d_counters);
@@ -178,7 +187,13 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     const int round0 = round;
     for (int b = 0; b < BATCH; ++b, ++round) {
       SDB_LAUNCH(k_reset_counters, 1, 32, 0, st, d_counters);
-      SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), d_counters);
+      {
+        // round r reads the list written by round r-1 (length saved in counters[8] by k_reset_counters)
+        int* lin = (round & 1) ? b_list1.as<int>() : b_list0.as<int>();
+        int* lout = (round & 1) ? b_list0.as<int>() : b_list1.as<int>();
+        if (round == 0) SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)nullptr, (unsigned int)n, (const unsigned int*)nullptr, lout, d_counters);
+        else SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)lin, 0u, (const unsigned int*)(d_counters + 8), lout, d_counters);
+      }
       if (launch_pair_stage(round)) return 1;
       SDB_CUDA(cudaMemcpyAsync(h_pin + 8 * b, d_counters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     }
@@ -193,7 +208,7 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
         cap = (size_t)c[1] + (size_t)c[1] / 2 + 1024;
         SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
         SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
-        const unsigned int zeros[8] = {c[0], 0, c[2], 0, 0, 0, c[6], 0};
+        const unsigned int zeros[8] = {c[0], 0, c[2], 0, 0, 0, c[6], c[7]};
         SDB_CUDA(cudaMemcpyAsync(d_counters, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st));
         round = round0 + b;
         if (launch_pair_stage(round)) return 1;

@@ -263,6 +263,204 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------- v2: halo-reuse strips
+// CTA tile = S image rows x 128 pixels.  For every 32-channel block the (S+2) x 130 pixel halo is
+// loaded ONCE (one 4-D TMA box per plane) and all 9 taps read it through shifted UMMA descriptors
+// (rows of a strip are contiguous 64-byte rows of the halo, so tap (dy,dx) is just a different start
+// address); only the weights are streamed per tap.  L2->SMEM traffic per output pixel drops ~4x
+// versus k_conv_tc, which was bound by exactly that traffic (profiles/r01b).  S strips share each
+// weight tile; accumulators: S x N TMEM columns.
+template <int N, int S>
+struct TcCfg2 {
+  static constexpr int KC = 32, ROWB = 64;
+  static constexpr int HROWS = (S + 2) * 130;
+  static constexpr int A_PLANE = ((HROWS * ROWB + 1023) / 1024) * 1024;
+  static constexpr int A_STAGE = 2 * A_PLANE;
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGE = 2 * N * ROWB;
+  static constexpr int B_STAGES = (N >= 256) ? 2 : 4;
+  static constexpr int SMEM = A_STAGES * A_STAGE + B_STAGES * B_STAGE + 1024 + 256;
+  static constexpr int TMEM_COLS = (S * N <= 32) ? 32 : (S * N <= 64 ? 64 : (S * N <= 128 ? 128 : (S * N <= 256 ? 256 : 512)));
+  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static_assert(S * N <= 512, "accumulators exceed TMEM");
+};
+
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, int boff_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;                      // SBO: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  if (boff_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
+  d |= (uint64_t)4 << 61;                               // SWIZZLE_64B
+  return d;
+}
+
+template <int N, int S>
+__global__ void __launch_bounds__(192, 1)
+k_conv_tc2(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
+           const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
+           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P, int boff_mode) {
+  using C = TcCfg2<N, S>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* smA = smem;
+  unsigned char* smB = smem + C::A_STAGES * C::A_STAGE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + C::B_STAGES * C::B_STAGE);
+  uint64_t* a_empty = a_full + C::A_STAGES;
+  uint64_t* b_full = a_empty + C::A_STAGES;
+  uint64_t* b_empty = b_full + C::B_STAGES;
+  uint64_t* accum_bar = b_empty + C::B_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = blockIdx.x * 128, y0 = blockIdx.y * S, img = blockIdx.z;
+  const int n_cb = P.c_total / C::KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      bool ok = true;
+      int bi = 0;
+      for (int cb = 0; cb < n_cb && ok; ++cb) {
+        const int sa = cb % C::A_STAGES;
+        if (cb >= C::A_STAGES && !mbar_wait(&a_empty[sa], ((cb / C::A_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 11u); break; }
+        const int ch = cb * C::KC;
+        unsigned char* sta = smA + sa * C::A_STAGE;
+        mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
+        if (ch < P.c_src0) {
+          tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+          tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+        } else {
+          tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+          tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+        }
+        for (int tap = 0; tap < 9; ++tap, ++bi) {
+          const int sb = bi % C::B_STAGES;
+          if (bi >= C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
+          unsigned char* stb = smB + sb * C::B_STAGE;
+          mbar_expect_tx(&b_full[sb], C::B_STAGE);
+          tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
+          tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[sb], ch, 0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      bool ok = true;
+      int bi = 0;
+      for (int cb = 0; cb < n_cb && ok; ++cb) {
+        const int sa = cb % C::A_STAGES;
+        if (!mbar_wait(&a_full[sa], (cb / C::A_STAGES) & 1)) { atomicExch(P.error_flag, 13u); break; }
+        const uint32_t a_hi = smem_u32(smA + sa * C::A_STAGE), a_lo = a_hi + C::A_PLANE;
+        for (int tap = 0; tap < 9; ++tap, ++bi) {
+          const int sb = bi % C::B_STAGES;
+          if (!mbar_wait(&b_full[sb], (bi / C::B_STAGES) & 1)) { atomicExch(P.error_flag, 14u); ok = false; break; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_hi = smem_u32(smB + sb * C::B_STAGE), b_lo = b_hi + N * C::ROWB;
+          const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            const uint32_t roff = (uint32_t)((s + dy) * 130 + dx) * C::ROWB;
+#pragma unroll
+            for (int ks = 0; ks < C::KC / 16; ++ks) {
+              const uint32_t koff = ks * 32;
+              const uint64_t dah = make_desc_sw64(a_hi + roff + koff, boff_mode), dal = make_desc_sw64(a_lo + roff + koff, boff_mode);
+              const uint64_t dbh = make_desc_sw64(b_hi + koff, 0), dbl = make_desc_sw64(b_lo + koff, 0);
+              const uint32_t acc = (cb | tap | ks) ? 1u : 0u;
+              umma_f16(tmem_base + s * N, dah, dbh, C::IDESC, acc);
+              umma_f16(tmem_base + s * N, dal, dbh, C::IDESC, 1u);
+              umma_f16(tmem_base + s * N, dah, dbl, C::IDESC, 1u);
+            }
+          }
+          tcgen05_commit(&b_empty[sb]);
+        }
+        tcgen05_commit(&a_empty[sa]);
+      }
+      tcgen05_commit(accum_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int x = x0 + m;
+    const bool ok = mbar_wait(accum_bar, 0);
+    if (!ok) atomicExch(P.error_flag, 15u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (ok) {
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {
+        const int y = y0 + s;
+        const bool in_img = (y < P.H) && (x < P.W);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * N + c0);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                       : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (in_img) {
+            __align__(16) __half hi[32];
+            __align__(16) __half lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + c0 + j);
+              if (P.relu) v = fmaxf(v, 0.f);
+              const __half h = __float2half_rn(v);
+              hi[j] = h;
+              lo[j] = __float2half_rn(v - __half2float(h));
+            }
+            if (!P.up2x) {
+              const size_t off = (((size_t)img * P.H + y) * P.W + x) * N + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            } else {
+              const int H2 = 2 * P.H, W2 = 2 * P.W;
+#pragma unroll
+              for (int rep = 0; rep < 4; ++rep) {
+                const size_t off = (((size_t)img * H2 + (2 * y + (rep >> 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                  reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------- small SIMT companions
 // stem: Cin (1..4) -> COUT, fp32 input, split fp16 output
 template <int COUT>
@@ -335,23 +533,27 @@ __global__ void k_maxpool_split(const __half* __restrict__ in_hi, const __half* 
   }
 }
 
-// heads on split features: prob = sigmoid(x.Wp+bp), dist = x.Wd+bd
+// heads on split features: prob = sigmoid(x.Wp+bp), dist = x.Wd+bd.
+// One thread per pixel keeps 32 output accumulators in registers per pass (feature value read once from
+// shared memory, weights as broadcast LDS.128), results staged through shared memory for coalesced stores.
 template <int CF>
 __global__ void __launch_bounds__(128)
 k_heads_split(const __half* __restrict__ f_hi, const __half* __restrict__ f_lo, long long npix, const float* __restrict__ wp,
               const float* __restrict__ bp, const float* __restrict__ wd, const float* __restrict__ bd, int R,
               float* __restrict__ prob, float* __restrict__ dist) {
-  extern __shared__ float sm[];
-  const int NO = R + 1;
-  float* sW = sm;
-  float* sF = sW + CF * NO;
-  float* sO = sF + 32 * (CF + 1);
-  for (int e = threadIdx.x; e < CF * NO; e += blockDim.x) {
-    const int f = e / NO, o = e % NO;
-    sW[e] = (o == 0) ? wp[f] : wd[(size_t)f * R + (o - 1)];
+  extern __shared__ __align__(16) float sm[];
+  const int NO = R + 1, NOP = (NO + 31) / 32 * 32;
+  float* sW = sm;                        // [CF][NOP]  (o = 0 prob, 1.. dist, zero padded)
+  float* sB = sW + CF * NOP;             // [NOP]
+  float* sF = sB + NOP;                  // [128][CF+1]
+  float* sO = sF + 128 * (CF + 1);       // [128][33]
+  for (int e = threadIdx.x; e < CF * NOP; e += blockDim.x) {
+    const int f = e / NOP, o = e % NOP;
+    sW[e] = (o == 0) ? wp[f] : (o < NO ? wd[(size_t)f * R + (o - 1)] : 0.f);
   }
-  const long long p0 = (long long)blockIdx.x * 32;
-  for (int e = threadIdx.x; e < 32 * (CF / 2); e += blockDim.x) {
+  for (int o = threadIdx.x; o < NOP; o += blockDim.x) sB[o] = (o == 0) ? bp[0] : (o < NO ? bd[o - 1] : 0.f);
+  const long long p0 = (long long)blockIdx.x * 128;
+  for (int e = threadIdx.x; e < 128 * (CF / 2); e += blockDim.x) {
     const int px = e / (CF / 2), f2 = e % (CF / 2);
     float2 v = make_float2(0.f, 0.f);
     if (p0 + px < npix) {
@@ -362,21 +564,36 @@ k_heads_split(const __half* __restrict__ f_hi, const __half* __restrict__ f_lo, 
     sF[px * (CF + 1) + 2 * f2] = v.x; sF[px * (CF + 1) + 2 * f2 + 1] = v.y;
   }
   __syncthreads();
-  const int px = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int o = w; o < NO; o += 4) {
-    float acc = (o == 0) ? bp[0] : bd[o - 1];
-    const float* fr = sF + px * (CF + 1);
-#pragma unroll 8
-    for (int f = 0; f < CF; ++f) acc = fmaf(fr[f], sW[f * NO + o], acc);
-    if (o == 0) acc = 1.f / (1.f + expf(-acc));
-    sO[px * NO + o] = acc;
+  const int px = threadIdx.x;
+  const float* fr = sF + px * (CF + 1);
+  for (int ob = 0; ob < NOP; ob += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = sB[ob + j];
+#pragma unroll 4
+    for (int f = 0; f < CF; ++f) {
+      const float a = fr[f];
+      const float4* w4 = reinterpret_cast<const float4*>(sW + f * NOP + ob);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w = w4[j];
+        acc[4 * j] = fmaf(a, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(a, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(a, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(a, w.w, acc[4 * j + 3]);
+      }
+    }
+    if (ob == 0) acc[0] = 1.f / (1.f + expf(-acc[0]));
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sO[px * 33 + j] = acc[j];
+    __syncthreads();
+    // coalesced stores: outputs ob..ob+31 of 128 pixels
+    for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+      const int q = e / 32, j = e % 32, o = ob + j;
+      if (p0 + q >= npix || o >= NO) continue;
+      const float v = sO[q * 33 + j];
+      if (o == 0) prob[p0 + q] = v; else dist[(p0 + q) * R + (o - 1)] = v;
+    }
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 32 * R; e += blockDim.x) {
-    const int q = e / R, k = e % R;
-    if (p0 + q < npix) dist[(p0 + q) * R + k] = sO[q * NO + 1 + k];
-  }
-  if (threadIdx.x < 32 && p0 + threadIdx.x < npix) prob[p0 + threadIdx.x] = sO[threadIdx.x * NO];
 }
 
 // weights (3,3,Cin,Cout) fp32 -> [tap][Cout][Cin] fp16 hi / lo
@@ -403,6 +620,20 @@ static EncodeTiledFn get_encode() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   }
   return fn;
+}
+
+static int make_act_map2(CUtensorMap* m, const __half* base, int n, int h, int w, int c, int rows) {
+  // v2: box = {32 channels, 130 x, rows y, 1}, 64-byte swizzle
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { sdb::set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {32, 130, (cuuint32_t)rows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sdb::set_error("cuTensorMapEncodeTiled(activation v2) failed: " + std::to_string((int)r)); return 1; }
+  return 0;
 }
 
 static int make_act_map(CUtensorMap* m, const __half* base, int n, int h, int w, int c, int kc) {
@@ -445,6 +676,19 @@ static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
   return 0;
 }
 
+template <int N, int S>
+static int launch_tc2(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, int boff_mode, cudaStream_t st) {
+  using C = TcCfg2<N, S>;
+  static bool attr = false;
+  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc2<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
+  dim3 grid(cdiv(P.W, 128), cdiv(P.H, S), n_img);
+  k_conv_tc2<N, S><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, boff_mode);
+  sdb::g_launch_count++;
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 static unsigned int* g_err_flag = nullptr;      // device flag shared by all launches
 
 }  // namespace
@@ -477,6 +721,32 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
     if (cout == 32) SDB_TC(32, 32); if (cout == 64) SDB_TC(64, 32); if (cout == 128) SDB_TC(128, 32); SDB_TC(256, 32);
   }
 #undef SDB_TC
+}
+
+// halo-reuse variant (k_conv_tc2): same contract as sdb_conv3x3_tc; boff_mode selects how the UMMA
+// descriptor's base-offset field is filled for tap-shifted (non swizzle-atom-aligned) start addresses
+extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                               int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
+                               int relu, int up2x, int boff_mode, void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cin = c_src0 + c_src1;
+  if (cin % 32 || c_src0 % 32 || c_src1 % 32) { sdb::set_error("conv3x3_tc2: channel counts must be multiples of 32"); return 1; }
+  if (cout != 32 && cout != 64 && cout != 128 && cout != 256) { sdb::set_error("conv3x3_tc2: cout must be 32/64/128/256"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
+  constexpr int S = 2;
+  CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
+  if (make_act_map2(&a1h, (const __half*)src1_hi, n, h, w, c_src1, S + 2) || make_act_map2(&a1l, (const __half*)src1_lo, n, h, w, c_src1, S + 2)) return 1;
+  if (c_src0 > 0) {
+    if (make_act_map2(&a0h, (const __half*)src0_hi, n, h, w, c_src0, S + 2) || make_act_map2(&a0l, (const __half*)src0_lo, n, h, w, c_src0, S + 2)) return 1;
+  } else { a0h = a1h; a0l = a1l; }
+  if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
+  ConvParams P;
+  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag;
+  if (cout == 32) return launch_tc2<32, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
+  if (cout == 64) return launch_tc2<64, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
+  if (cout == 128) return launch_tc2<128, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
+  return launch_tc2<256, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
 }
 
 // non-zero when any tcgen05 conv launch since the last call hit a bounded-wait timeout (then results are invalid)
@@ -521,11 +791,11 @@ extern "C" int sdb_heads_split(const void* f_hi, const void* f_lo, long long npi
                                const float* d_wd, const float* d_bd, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (cfeat != 128) { sdb::set_error("heads_split: only 128 feature channels supported"); return 1; }
-  const int NO = n_rays + 1;
-  const size_t smem = (size_t)(128 * NO + 32 * 129 + 32 * NO) * sizeof(float);
+  const int NO = n_rays + 1, NOP = (NO + 31) / 32 * 32;
+  const size_t smem = (size_t)(128 * NOP + NOP + 128 * 129 + 128 * 33) * sizeof(float);
   static bool attr = false;
   if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_heads_split<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
   if (smem > 200 * 1024) { sdb::set_error("heads_split: n_rays too large"); return 1; }
-  SDB_LAUNCH((k_heads_split<128>), cdiv(npix, 32), 128, smem, st, (const __half*)f_hi, (const __half*)f_lo, npix, d_wp, d_bp, d_wd, d_bd, n_rays, d_prob, d_dist);
+  SDB_LAUNCH((k_heads_split<128>), cdiv(npix, 128), 128, smem, st, (const __half*)f_hi, (const __half*)f_lo, npix, d_wp, d_bp, d_wd, d_bd, n_rays, d_prob, d_dist);
   return 0;
 }
