@@ -143,6 +143,7 @@ def main():
         model.predict_instances_device(x_dev, SHAPE, prob_thresh=pthr, nms_thresh=NMS_THRESH)
     sampler = ClockSampler(local); sampler.start()
     _lib.launch_count(reset=True)
+    _lib.profile_enable(True)
     barrier()
     n_inst = 0; dev_ms = 0.0; stage = {}
     for _ in range(args.steps):
@@ -158,6 +159,8 @@ def main():
                         ("cand_end", "nms_end", "nms"), ("nms_end", "label_end", "coord_label")):
             if a in ev and b in ev: stage[k] = stage.get(k, 0.0) + ev[a].elapsed_time(ev[b])
     launches = _lib.launch_count()
+    prof_clip = _lib.profile_get("nms2d_clip"); prof_conv = _lib.profile_get("conv_tc")
+    _lib.profile_enable(False)
     barrier()
     t = torch.tensor([dev_ms, float(n_inst)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -194,7 +197,14 @@ def main():
         fl = conv_flops(cfg, SHAPE)
         unet_ms = stage.get("unet", 0.0) / args.steps
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-        ach = fl / (unet_ms / 1000.0) / 1e12 if unet_ms > 0 else 0.0
+        peak_bw = peaks.get("hbm_gbs", 6650.0)
+        src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+        # dominant kernel of the step: the per-pair polygon clipping sweep of the NMS (k_clip).  Algorithmic
+        # bytes per tested pair: two 32-gon vertex rows (2 x R x 8 B) + areas/bbox/state (20 B) + pair index (8 B)
+        bytes_per_pair = 2 * N_RAYS * 8 + 28
+        clip_ms = prof_clip["ms"]; clip_launches = max(1, prof_clip["launches"])
+        clip_gbs = (prof_clip["units"] * bytes_per_pair) / (clip_ms / 1e3) / 1e9 if clip_ms > 0 else 0.0
+        conv_tfs = prof_conv["units"] / (prof_conv["ms"] / 1e3) / 1e12 if prof_conv["ms"] > 0 else 0.0
         out = {
             "metric": "instances/sec (predict_instances end-to-end)", "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms_max / args.steps,
@@ -206,9 +216,16 @@ def main():
             "clocks": clocks,
             "e2e": {"value": n_e2e / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "U-Net conv stack (all conv3x3 launches of one forward)",
-                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
-                         "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"},
+            "roofline": {"bound": "hbm", "kernel": "k_clip<32> (NMS pair clipping sweep; latency/divergence bound, not bandwidth bound)",
+                         "achieved": clip_gbs, "peak": peak_bw, "unit": "GB/s", "frac": clip_gbs / peak_bw if peak_bw else None,
+                         "traffic": None, "ms_per_step": clip_ms / args.steps, "launches_per_step": clip_launches / args.steps,
+                         "pairs_per_step": prof_clip["units"] / args.steps, "algorithmic_bytes_per_pair": bytes_per_pair, "peak_source": src + " hbm_gbs"},
+            "roofline_conv": {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 3x3 conv, all launches of the forward pass)",
+                              "achieved": conv_tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tfs / peak_tf if peak_tf else None,
+                              "traffic": None, "ms_per_step": prof_conv["ms"] / args.steps, "launches_per_step": prof_conv["launches"] / args.steps,
+                              "algorithmic_flop_per_step": prof_conv["units"] / args.steps, "issued_flop_factor": 3,
+                              "unet_forward_ms": unet_ms, "unet_algorithmic_tflops": fl / (unet_ms / 1e3) / 1e12 if unet_ms > 0 else None,
+                              "peak_source": src + " bf16_tflops_sustained"},
         }
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -36,6 +36,11 @@ int sdb_device_info(int* n_devices, int* sm_count, int* cc_major, int* cc_minor)
 /* number of kernel launches issued by this library since the last reset (bench "gpu_launches") */
 long long sdb_launch_count(int reset);
 
+/* optional live profiling with CUDA events on the launching stream (bench.py's roofline): names are
+ * "nms2d_clip" (units = polygon pairs tested) and "conv_tc" (units = algorithmic FLOPs) */
+int sdb_profile_enable(int on);
+int sdb_profile_get(const char* name, double* ms, long long* launches, double* units);
+
 /* ----------------------------------------------------------------------------- (1) host ABI */
 
 /* reference: stardist3d_lib.h:55-65 (identical signature) */
@@ -153,6 +158,10 @@ int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const v
 int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
                     int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
                     int relu, int up2x, int boff_mode, void* out_hi, void* out_lo, sdb_stream_t stream);
+/* 1x1 heads on the tensor cores (one tap, K = cfeat): head weights [1][np][cfeat] split fp16, row 0 = prob,
+ * rows 1..n_rays = dist, zero padded to np in {48, 80, 112, 144}; outputs fp32 */
+int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n, int h, int w, const void* w_hi, const void* w_lo,
+                 float w_scale, const float* d_bias, int np, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream);
 int sdb_tc_error_check(sdb_stream_t stream);
 /* w_scale: power of two the weights are multiplied by before the split (undone on the accumulator) */
 int sdb_split_weights(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream);

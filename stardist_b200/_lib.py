@@ -21,6 +21,8 @@ def _declare(lib):
     lib.sdb_launch_count.restype = c_longlong
     lib.sdb_launch_count.argtypes = [c_int]
     lib.sdb_device_info.argtypes = [POINTER(c_int)] * 4
+    lib.sdb_profile_enable.argtypes = [c_int]
+    lib.sdb_profile_get.argtypes = [c_char_p, POINTER(c_double), POINTER(c_longlong), POINTER(c_double)]
     lib._LIB_non_maximum_suppression_2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P]
     lib._LIB_polygons_to_label_2d.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
     lib.sdb_nms2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
@@ -36,6 +38,7 @@ def _declare(lib):
     lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
     lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
     lib.sdb_conv3x3_tc2.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, c_int, P, P, P]
+    lib.sdb_heads_tc.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, P, P, P]
     lib.sdb_tc_error_check.argtypes = [P]
     lib.sdb_split_weights.argtypes = [P, c_int, c_int, c_float, P, P, P]
     lib.sdb_stem_split.argtypes = [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P]
@@ -46,7 +49,7 @@ def _declare(lib):
     for name in ("_LIB_non_maximum_suppression_2d", "_LIB_polygons_to_label_2d", "sdb_nms2d",
                  "sdb_polygons_to_label_2d", "sdb_dist_to_coord_2d", "sdb_threshold_sort",
                  "sdb_gather_candidates", "sdb_conv3x3_2d", "sdb_maxpool2x2_2d", "sdb_heads_2d",
-                 "sdb_device_info", "sdb_conv3x3_tc", "sdb_conv3x3_tc2", "sdb_tc_error_check", "sdb_split_weights", "sdb_stem_split",
+                 "sdb_device_info", "sdb_conv3x3_tc", "sdb_conv3x3_tc2", "sdb_heads_tc", "sdb_tc_error_check", "sdb_split_weights", "sdb_stem_split",
                  "sdb_maxpool_split", "sdb_heads_split", "sdb_polyhedron_to_label", "sdb_nms3d", "sdb_conv3_nd", "sdb_maxpool_nd"):
         getattr(lib, name).restype = c_int
     # optional (added as the build widens)
@@ -77,6 +80,16 @@ def load():
 def check(rc):
     if rc != 0:
         raise StarDistB200Error(load().sdb_last_error().decode("utf-8", "replace"))
+
+def profile_enable(on=True):
+    load().sdb_profile_enable(1 if on else 0)
+
+
+def profile_get(name):
+    ms, n, u = c_double(0), c_longlong(0), c_double(0)
+    load().sdb_profile_get(name.encode(), ctypes.byref(ms), ctypes.byref(n), ctypes.byref(u))
+    return dict(ms=ms.value, launches=n.value, units=u.value)
+
 
 def launch_count(reset=False):
     return int(load().sdb_launch_count(1 if reset else 0))

@@ -14,6 +14,14 @@ extern long long g_launch_count;
 void ensure_runtime_init();
 unsigned int* pinned_scratch();     // 64 uint32, per process
 
+// optional live profiling of named kernels with CUDA events on the launching stream (bench.py's
+// roofline numbers): enabled through sdb_profile_enable(); record_begin/end bracket one launch
+struct ProfSpan { cudaEvent_t a, b; };
+bool profile_enabled();
+void profile_begin(const char* name, cudaStream_t st, ProfSpan* sp);
+void profile_end(const char* name, cudaStream_t st, ProfSpan* sp);
+void profile_add_units(const char* name, double units);     // e.g. pairs processed
+
 #define SDB_CUDA(call)                                                                      \
   do {                                                                                      \
     cudaError_t _e = (call);                                                                \

@@ -123,20 +123,26 @@ __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ co
   if (counters[1] > cap) counters[5] = 1;
 }
 
-// one pair per thread: every lane of a warp carries a clipping problem
+// One pair per thread.  The sweep is long, branchy, per-lane serial code: lanes of a warp that run
+// different pairs mostly serialise.  Pairs are therefore dealt round-robin over ALL resident warps
+// (pair p -> warp p % G, lane p / G): a round with few pairs runs one pair per warp at full single-thread
+// speed instead of 32 pairs in one warp (the small late rounds were latency bound at ~1 ms each).
 template <int NV>
 __global__ void __launch_bounds__(128) k_clip(NmsArrays A, const int2* __restrict__ pairs, unsigned int cap,
                                               int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
   if (counters[5]) return;
   const unsigned int n_pairs = counters[1];
-  const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_pairs) return;
-  const int2 pr = pairs[t];
-  if (A.state[pr.y] == ST_SUPPRESSED) return;          // already suppressed by another pair (benign race)
+  const unsigned int G = (gridDim.x * blockDim.x) >> 5;                       // warps in the grid
+  const unsigned int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp_g >= n_pairs) return;
   sdclip::ClipSweep<NV, 1> S;
-  const int r = pair_suppresses<NV, 1>(A, pr.x, pr.y, S);
-  if (r == 1) A.state[pr.y] = ST_SUPPRESSED;
-  else if (r < 0) { const unsigned int k = atomicAdd(&counters[4], 1u); slow_pairs[k] = pr; }
+  for (unsigned int t = lane * G + warp_g; t < n_pairs; t += 32 * G) {
+    const int2 pr = pairs[t];
+    if (A.state[pr.y] == ST_SUPPRESSED) continue;        // already suppressed by another pair (benign race)
+    const int r = pair_suppresses<NV, 1>(A, pr.x, pr.y, S);
+    if (r == 1) A.state[pr.y] = ST_SUPPRESSED;
+    else if (r < 0) { const unsigned int k = atomicAdd(&counters[4], 1u); slow_pairs[k] = pr; }
+  }
 }
 
 template <int NV>
@@ -179,7 +185,10 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     SDB_LAUNCH(k_pairs, 148 * 8, 256, 0, st, A, r, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)cap, d_counters);
     SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
     // grid sized for the capacity; threads beyond counters[1] exit immediately
-    SDB_LAUNCH((k_clip<NV>), cdiv(cap, 128), 128, 0, st, A, b_pairs.as<int2>(), (unsigned int)cap, b_slow.as<int2>(), d_counters);
+    sdb::ProfSpan sp;
+    sdb::profile_begin("nms2d_clip", st, &sp);
+    SDB_LAUNCH((k_clip<NV>), 148 * 7, 128, 0, st, A, b_pairs.as<int2>(), (unsigned int)cap, b_slow.as<int2>(), d_counters);
+    sdb::profile_end("nms2d_clip", st, &sp);
     SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
     return 0;
   };
@@ -219,7 +228,13 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       if (c[0] == 0) { done = true; break; }
     }
     if (verbose) printf("NMS2D(b200): rounds=%d undecided(last)=%u pair tests so far=%u\n", round, h_pin[8 * (BATCH - 1)], h_pin[8 * (BATCH - 1) + 2] + h_pin[8 * (BATCH - 1) + 1]);
-    if (done) break;
+    if (done) {
+      // pairs tested = counters[2] (accumulated by k_reset_counters) + the pairs of the last counted rounds
+      unsigned int tot = 0;
+      for (int b = 0; b < BATCH; ++b) { const unsigned int* c = h_pin + 8 * b; tot = c[2] + c[1]; if (c[0] == 0) break; }
+      sdb::profile_add_units("nms2d_clip", (double)tot);
+      break;
+    }
     if (round > 4 * n + 8) { sdb::set_error("nms2d: no progress"); return 1; }
   }
   return 0;

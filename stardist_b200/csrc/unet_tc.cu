@@ -46,6 +46,9 @@ struct ConvParams {
   const float* bias;
   __half* out_hi; __half* out_lo;
   unsigned int* error_flag;
+  int n_taps;            // 9 (3x3) or 1 (1x1 heads)
+  int heads_R;           // > 0: heads epilogue -> prob = sigmoid(ch 0), dist = ch 1..R, fp32 outputs
+  float* prob; float* dist;
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -112,6 +115,7 @@ struct TcCfg {
   static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  static constexpr int NPAD32 = (N + 31) / 32 * 32;
   static constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * ROWB;
   // instruction descriptor, kind::f16: D=F32 (bit 4), A=B=F16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
@@ -134,7 +138,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 8, img = blockIdx.z;
   const int n_cb = P.c_total / KC;
-  const int n_kb = 9 * n_cb;
+  const int n_kb = P.n_taps * n_cb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -160,7 +164,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
           if (!mbar_wait(&empty_bar[s], ((kb / C::STAGES) - 1) & 1)) { atomicExch(P.error_flag, 1u); break; }
         }
         const int tap = kb / n_cb, cb = kb % n_cb;
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int dy = (P.n_taps == 9) ? tap / 3 - 1 : 0, dx = (P.n_taps == 9) ? tap % 3 - 1 : 0;
         const int ch = cb * KC;
         unsigned char* st = smem + s * C::STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
@@ -210,7 +214,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (ok) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = 0; c0 < C::NPAD32; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -222,7 +226,18 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
                        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                      : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (in_img) {
+        if (in_img && P.heads_R > 0) {
+          // heads: channel 0 -> sigmoid -> prob, channels 1..R -> dist (fp32)
+          const size_t pix = ((size_t)img * P.H + y) * P.W + x;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ch = c0 + j;
+            if (ch > P.heads_R) break;
+            const float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + ch);
+            if (ch == 0) P.prob[pix] = 1.f / (1.f + expf(-v));
+            else P.dist[pix * P.heads_R + (ch - 1)] = v;
+          }
+        } else if (in_img) {
           __align__(16) __half hi[32];
           __align__(16) __half lo[32];
 #pragma unroll
@@ -649,10 +664,10 @@ static int make_act_map(CUtensorMap* m, const __half* base, int n, int h, int w,
   if (r != CUDA_SUCCESS) { sdb::set_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r)); return 1; }
   return 0;
 }
-static int make_w_map(CUtensorMap* m, const __half* base, int cin, int cout, int kc) {
+static int make_w_map(CUtensorMap* m, const __half* base, int cin, int cout, int kc, int n_taps = 9) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { sdb::set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
-  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, 9};
+  cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)n_taps};
   cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * cout * 2};
   cuuint32_t box[3] = {(cuuint32_t)kc, (cuuint32_t)cout, 1};
   cuuint32_t es[3] = {1, 1, 1};
@@ -670,7 +685,11 @@ static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
   static bool attr = false;
   if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
   dim3 grid(cdiv(P.W, 16), cdiv(P.H, 8), n_img);
+  sdb::ProfSpan sp;
+  sdb::profile_begin("conv_tc", st, &sp);
   k_conv_tc<N, KC><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P);
+  sdb::profile_end("conv_tc", st, &sp);
+  sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);     // algorithmic FLOPs
   sdb::g_launch_count++;
   SDB_CUDA(cudaGetLastError());
   return 0;
@@ -683,7 +702,11 @@ static int launch_tc2(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUte
   static bool attr = false;
   if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc2<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
   dim3 grid(cdiv(P.W, 128), cdiv(P.H, S), n_img);
+  sdb::ProfSpan sp;
+  sdb::profile_begin("conv_tc", st, &sp);
   k_conv_tc2<N, S><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, boff_mode);
+  sdb::profile_end("conv_tc", st, &sp);
+  sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);
   sdb::g_launch_count++;
   SDB_CUDA(cudaGetLastError());
   return 0;
@@ -713,7 +736,7 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, kc) || make_w_map(&wl, (const __half*)w_lo, cin, cout, kc)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
 #define SDB_TC(NN, KK) return launch_tc<NN, KK>(a0h, a0l, a1h, a1l, wh, wl, P, n, st)
   if (kc == 64) {
     if (cout == 32) SDB_TC(32, 64); if (cout == 64) SDB_TC(64, 64); if (cout == 128) SDB_TC(128, 64); SDB_TC(256, 64);
@@ -721,6 +744,28 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
     if (cout == 32) SDB_TC(32, 32); if (cout == 64) SDB_TC(64, 32); if (cout == 128) SDB_TC(128, 32); SDB_TC(256, 32);
   }
 #undef SDB_TC
+}
+
+// 1x1 heads on the tensor cores: features [n,h,w,cfeat] (split fp16) x head weights [1][NP][cfeat] (split fp16,
+// row 0 = prob, rows 1..R = dist, zero padded to NP in {48,80,112,144}) -> prob = sigmoid(.) [n,h,w], dist [n,h,w,R] fp32
+extern "C" int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n, int h, int w, const void* w_hi, const void* w_lo,
+                            float w_scale, const float* d_bias, int np, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cfeat % 64) { sdb::set_error("heads_tc: feature channels must be a multiple of 64"); return 1; }
+  if (n_rays + 1 > np) { sdb::set_error("heads_tc: padded head count too small"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
+  CUtensorMap ah, al, wh, wl;
+  if (make_act_map(&ah, (const __half*)f_hi, n, h, w, cfeat, 64) || make_act_map(&al, (const __half*)f_lo, n, h, w, cfeat, 64)) return 1;
+  if (make_w_map(&wh, (const __half*)w_hi, cfeat, np, 64, 1) || make_w_map(&wl, (const __half*)w_lo, cfeat, np, 64, 1)) return 1;
+  ConvParams P;
+  P.H = h; P.W = w; P.c_src0 = 0; P.c_total = cfeat; P.relu = 0; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
+  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
+  if (np == 48) return launch_tc<48, 64>(ah, al, ah, al, wh, wl, P, n, st);
+  if (np == 80) return launch_tc<80, 64>(ah, al, ah, al, wh, wl, P, n, st);
+  if (np == 112) return launch_tc<112, 64>(ah, al, ah, al, wh, wl, P, n, st);
+  if (np == 144) return launch_tc<144, 64>(ah, al, ah, al, wh, wl, P, n, st);
+  sdb::set_error("heads_tc: np must be one of 48, 80, 112, 144");
+  return 1;
 }
 
 // halo-reuse variant (k_conv_tc2): same contract as sdb_conv3x3_tc; boff_mode selects how the UMMA
@@ -742,7 +787,7 @@ extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_s
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
   if (cout == 32) return launch_tc2<32, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 64) return launch_tc2<64, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 128) return launch_tc2<128, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);

@@ -134,6 +134,26 @@ class UNetDevice2DTC:
                 L.check(lib.sdb_split_weights(L.ptr(kd), cin, cout, ent['scale'], L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
                 ent['split'] = ws
             self.w[name] = ent
+        # 1x1 heads as one tensor-core GEMM: rows = [prob | dist_0..R-1 | zero padding], K = feature channels
+        R = config.n_rays
+        kp, kd = self.w['prob']['k'], self.w['dist']['k']
+        cf = kp.shape[-2]
+        self.heads_np = next((v for v in (48, 80, 112, 144) if v >= R + 1), None)
+        if self.heads_np is not None and cf % 64 == 0:
+            Wf = torch.zeros((self.heads_np, cf), dtype=torch.float32, device=self.device)
+            Wf[0] = kp.reshape(cf, 1)[:, 0]
+            Wf[1:R + 1] = kd.reshape(cf, R).t()
+            sc = tc_weight_scale(Wf.cpu().numpy())
+            Ws = Wf * sc
+            hi = Ws.to(torch.float16)
+            lo = (Ws - hi.float()).to(torch.float16)
+            self.heads_w = torch.stack([hi, lo]).reshape(2, 1, self.heads_np, cf).contiguous()
+            self.heads_scale = sc
+            self.heads_b = torch.zeros(self.heads_np, dtype=torch.float32, device=self.device)
+            self.heads_b[0] = self.w['prob']['b'][0]
+            self.heads_b[1:R + 1] = self.w['dist']['b']
+        else:
+            self.heads_w = None
 
     @staticmethod
     def supported(config):
@@ -198,7 +218,11 @@ class UNetDevice2DTC:
         R = self.config.n_rays
         prob = torch.empty((n_, hh, ww), dtype=torch.float32, device=x.device)
         dist = torch.empty((n_, hh, ww, R), dtype=torch.float32, device=x.device)
-        L.check(lib.sdb_heads_split(L.ptr(cur[0]), L.ptr(cur[1]), n_ * hh * ww, cf, L.ptr(self.w['prob']['k']), L.ptr(self.w['prob']['b']),
-                                   L.ptr(self.w['dist']['k']), L.ptr(self.w['dist']['b']), R, L.ptr(prob), L.ptr(dist), st))
+        if self.heads_w is not None:
+            L.check(lib.sdb_heads_tc(L.ptr(cur[0]), L.ptr(cur[1]), cf, n_, hh, ww, L.ptr(self.heads_w[0]), L.ptr(self.heads_w[1]),
+                                    self.heads_scale, L.ptr(self.heads_b), self.heads_np, R, L.ptr(prob), L.ptr(dist), st))
+        else:
+            L.check(lib.sdb_heads_split(L.ptr(cur[0]), L.ptr(cur[1]), n_ * hh * ww, cf, L.ptr(self.w['prob']['k']), L.ptr(self.w['prob']['b']),
+                                       L.ptr(self.w['dist']['k']), L.ptr(self.w['dist']['b']), R, L.ptr(prob), L.ptr(dist), st))
         L.check(lib.sdb_tc_error_check(st))
         return prob, dist
