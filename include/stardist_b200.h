@@ -80,6 +80,12 @@ int _LIB_polygons_to_label_2d(
 int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys, int n_rays,
               float threshold, int use_bbox, int use_kdtree, int verbose,
               unsigned char* d_keep, sdb_stream_t stream);
+/* Pre-filter of the 2D pair test (csrc/polyfast.cuh): 0 = exact Clipper-equivalent sweep on every pair,
+ * 1 (default) = closed-form overlap integral with a conservative bound first, exact sweep for the rest,
+ * 2 = verify: both on every pair, disagreements are counted.  Results are identical in all modes.
+ * stats: out4 = {pairs tested, pairs that needed the exact sweep, verify mismatches, nms calls}. */
+int sdb_nms2d_set_filter(int mode);
+void sdb_nms2d_filter_stats(unsigned long long* out4, int reset);
 
 /* paint polygons (geom2d.py:149-197): d_rank[i] = paint rank of polygon i (0 = painted first;
  * a pixel takes the covering polygon of highest rank), d_id_by_rank[r] = value written for

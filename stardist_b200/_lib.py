@@ -26,6 +26,10 @@ def _declare(lib):
     lib._LIB_non_maximum_suppression_2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P]
     lib._LIB_polygons_to_label_2d.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
     lib.sdb_nms2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_nms2d_set_filter.argtypes = [c_int]
+    lib.sdb_nms2d_set_filter.restype = c_int
+    lib.sdb_nms2d_filter_stats.argtypes = [POINTER(ctypes.c_ulonglong), c_int]
+    lib.sdb_nms2d_filter_stats.restype = None
     lib.sdb_polygons_to_label_2d.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P, P]
     lib.sdb_dist_to_coord_2d.argtypes = [P, P, c_int, c_int, P, c_double, c_double, P, P]
     lib.sdb_threshold_sort.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int),
@@ -115,3 +119,14 @@ def stream_ptr(stream=None):
 
 def iarr(vals):
     return (c_int * len(vals))(*[int(v) for v in vals])
+
+
+def nms2d_set_filter(mode):
+    """0 = exact sweep on every pair, 1 = pre-filter + exact sweep (default), 2 = verify (both, count mismatches)."""
+    check(load().sdb_nms2d_set_filter(int(mode)))
+
+
+def nms2d_filter_stats(reset=False):
+    out = (ctypes.c_ulonglong * 4)()
+    load().sdb_nms2d_filter_stats(out, 1 if reset else 0)
+    return dict(pairs=int(out[0]), exact=int(out[1]), mismatches=int(out[2]), calls=int(out[3]))

@@ -24,6 +24,8 @@
 #include "../../include/stardist_b200.h"
 
 namespace sdnms {
+int g_filter_mode = 1;
+unsigned long long g_filter_stats[4] = {0, 0, 0, 0};
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -31,6 +33,7 @@ __global__ void k_precompute(const float* __restrict__ dist, const float* __rest
                              const float* __restrict__ sn, const float* __restrict__ cs,
                              int n, int R, int2* __restrict__ verts, int4* __restrict__ bbox,
                              float* __restrict__ radius, float* __restrict__ area,
+                             double* __restrict__ suf, double* __restrict__ sarea, float* __restrict__ maxlen,
                              unsigned int* __restrict__ stats /* [0]=max radius bits,[1..4]= minx,maxx,miny,maxy (int) */) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -60,6 +63,19 @@ __global__ void k_precompute(const float* __restrict__ dist, const float* __rest
   a = (float)(0.5 * (double)fabsf(a));
   area[i] = a;
   radius[i] = rmax;
+  if (suf) {
+    // pre-filter data (polyfast.cuh): suffix sums of F_k = ∫ x dy over edge k, ∮ x dy, longest edge
+    double s = 0; float ml = 0;
+    for (int k = R - 1; k >= 0; --k) {
+      const int2 p = v[k], q = v[(k + 1) % R];
+      suf[(size_t)i * R + k] = s;
+      s += 0.5 * (double)((long long)q.y - p.y) * (double)((long long)p.x + q.x);
+      const float ex = (float)(q.x - p.x), ey = (float)(q.y - p.y);
+      ml = fmaxf(ml, sqrtf(ex * ex + ey * ey));
+    }
+    sarea[i] = s;
+    maxlen[i] = ml * 1.000001f;
+  }
   // bbox_intersect() takes int parameters: the float bbox is truncated at the call (:114-120,575)
   int4 b; b.x = (int)bx1; b.y = (int)bx2; b.z = (int)by1; b.w = (int)by2;
   bbox[i] = b;
@@ -164,6 +180,13 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   const float ANGLE_PI = (float)(2 * M_PI / R);
   for (int k = 0; k < R; ++k) { float a = ANGLE_PI * k; tab[k] = sinf(a); tab[R + k] = cosf(a); }
 
+  const int filter = g_filter_mode;
+  sdb::DevBuf b_suf, b_sarea, b_maxlen;
+  if (filter) {
+    SDB_CUDA(b_suf.alloc((size_t)n * R * sizeof(double), st));
+    SDB_CUDA(b_sarea.alloc((size_t)n * sizeof(double), st));
+    SDB_CUDA(b_maxlen.alloc((size_t)n * sizeof(float), st));
+  }
   sdb::DevBuf b_tab, b_verts, b_bbox, b_radius, b_area, b_stats, b_cellpt, b_counts, b_start, b_tiles, b_items, b_state, b_slow, b_counters;
   SDB_CUDA(b_tab.alloc(2 * R * sizeof(float), st));
   SDB_CUDA(b_verts.alloc((size_t)n * R * sizeof(int2), st));
@@ -175,7 +198,8 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   const int init_stats[8] = {0, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0, 0, 0};
   SDB_CUDA(cudaMemcpyAsync(b_stats.p, init_stats, sizeof(init_stats), cudaMemcpyHostToDevice, st));
   SDB_LAUNCH(k_precompute, cdiv(n, 128), 128, 0, st, d_dist, d_points, b_tab.as<float>(), b_tab.as<float>() + R, n, R,
-             b_verts.as<int2>(), b_bbox.as<int4>(), b_radius.as<float>(), b_area.as<float>(), b_stats.as<unsigned int>());
+             b_verts.as<int2>(), b_bbox.as<int4>(), b_radius.as<float>(), b_area.as<float>(),
+             filter ? b_suf.as<double>() : (double*)nullptr, b_sarea.as<double>(), b_maxlen.as<float>(), b_stats.as<unsigned int>());
   int h_stats[8];
   SDB_CUDA(cudaMemcpyAsync(h_stats, b_stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
@@ -221,6 +245,12 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   A.cell_start = b_start.as<unsigned int>(); A.items = b_items.as<int>();
   A.state = b_state.as<int>(); A.n = n; A.R = R;
   A.max_dist = max_dist; A.threshold = threshold; A.use_bbox = use_bbox; A.G = G;
+  A.suf = b_suf.as<double>(); A.sarea = b_sarea.as<double>(); A.maxlen = b_maxlen.as<float>(); A.filter = filter;
+  {
+    double m = 0;
+    for (int k = 1; k <= 4; ++k) m = fmax(m, fabs((double)h_stats[k]));
+    A.max_abs_coord = m + (double)max_dist + 2.0;
+  }
 
   if (verbose) {
     printf("Non Maximum Suppression (2D, B200) ++++ \n");
@@ -235,6 +265,15 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   if (rc) return rc;
   SDB_LAUNCH(k_finish, cdiv(n, 256), 256, 0, st, b_state.as<int>(), n, d_keep);
   return 0;
+}
+
+extern "C" int sdb_nms2d_set_filter(int mode) {
+  if (mode < 0 || mode > 2) { sdb::set_error("nms2d: filter mode must be 0, 1 or 2"); return 1; }
+  g_filter_mode = mode;
+  return 0;
+}
+extern "C" void sdb_nms2d_filter_stats(unsigned long long* out4, int reset) {
+  for (int k = 0; k < 4; ++k) { out4[k] = g_filter_stats[k]; if (reset) g_filter_stats[k] = 0; }
 }
 
 extern "C" int _LIB_non_maximum_suppression_2d(const float* dist, const float* points, const int n_polys,

@@ -30,6 +30,12 @@ struct NmsArrays {
   float max_dist, threshold;
   int use_bbox;
   GridDesc G;
+  // pre-filter data (polyfast.cuh): per-edge suffix sums of F = ∫ x dy, per-polygon ∮ x dy and longest
+  // edge, largest |coordinate| over all polygons; filter: 0 = exact sweep only, 1 = filter + sweep for the
+  // undecided pairs, 2 = verify (both on every pair, disagreements counted)
+  const double* suf; const double* sarea; const float* maxlen;
+  double max_abs_coord;
+  int filter;
 };
 
 // would suppressor h (higher score) test candidate c ?  (stardist2d.cpp:548-549,572-576)
@@ -48,6 +54,10 @@ __device__ __forceinline__ bool reaches(const NmsArrays& A, int h, int c, float 
   return true;
 }
 
+
+// pre-filter mode and cumulative statistics (nms2d.cu)
+extern int g_filter_mode;
+extern unsigned long long g_filter_stats[4];   // pairs, pairs sent to the exact sweep, verify mismatches, calls
 
 // frontier-peeling rounds, instantiated per polygon capacity in nms2d_nv32.cu / nms2d_nv128.cu
 int run_rounds_nv32(NmsArrays A, int* d_slow, unsigned int* d_counters, cudaStream_t st, int verbose, unsigned int* h_pin);

@@ -4,6 +4,7 @@
 #pragma once
 #include "nms2d_common.cuh"
 #include "clip2d.cuh"
+#include "polyfast.cuh"
 #include <algorithm>
 
 namespace sdnms {
@@ -123,25 +124,87 @@ __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ co
   if (counters[1] > cap) counters[5] = 1;
 }
 
-// One pair per thread.  The sweep is long, branchy, per-lane serial code: lanes of a warp that run
-// different pairs mostly serialise.  Pairs are therefore dealt round-robin over ALL resident warps
-// (pair p -> warp p % G, lane p / G): a round with few pairs runs one pair per warp at full single-thread
-// speed instead of 32 pairs in one warp (the small late rounds were latency bound at ~1 ms each).
-template <int NV>
-__global__ void __launch_bounds__(128) k_clip(NmsArrays A, const int2* __restrict__ pairs, unsigned int cap,
-                                              int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
+// Pre-filter (polyfast.cuh): one WARP per pair.  Lane j owns edge j of the candidate's polygon (and j+32, ...
+// for n_rays > 32) and walks the suppressor's edges, which are warp-uniform loads; the closed-form overlap
+// integral and its bound decide most pairs, the rest is appended to the exact list (counters[9]).
+// verify != 0: nothing is decided here, the verdict is stored per pair for k_clip to compare.
+__global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restrict__ pairs, int2* __restrict__ xpairs,
+                                              signed char* __restrict__ verdict, int verify, unsigned int* __restrict__ counters) {
   if (counters[5]) return;
   const unsigned int n_pairs = counters[1];
+  const unsigned int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+  const int R = A.R;
+  for (unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_pairs; w += warps) {
+    const int2 pr = pairs[w];
+    const int h = pr.x, c = pr.y;
+    if (!verify && A.state[c] == ST_SUPPRESSED) continue;
+    const int2* __restrict__ va = A.verts + (size_t)h * R;
+    const int2* __restrict__ vb = A.verts + (size_t)c * R;
+    const double* __restrict__ sa = A.suf + (size_t)h * R;
+    const double* __restrict__ sb = A.suf + (size_t)c * R;
+    const int2 p0 = va[0], q0 = vb[0];
+    sdfast::Accum acc; acc.clear();
+    int wq = 0, wp = 0;
+    for (int j = lane; j < R; j += 32) {
+      const int j1 = (j + 1 == R) ? 0 : j + 1;
+      const int2 b0 = vb[j], b1 = vb[j1], a0 = va[j], a1 = va[j1];
+      sdfast::Edge f; f.x0 = b0.x; f.y0 = b0.y; f.x1 = b1.x; f.y1 = b1.y;
+      sdfast::Edge e2; e2.x0 = a0.x; e2.y0 = a0.y; e2.x1 = a1.x; e2.y1 = a1.y;
+      wq += sdfast::wind_Q_edge(f, p0.x, p0.y);
+      wp += sdfast::wind_P_edge(e2, q0.x, q0.y);
+      const sdfast::Box fb = sdfast::edge_box(f);
+      int2 prev = p0;
+      for (int i = 0; i < R; ++i) {
+        const int2 cur = va[(i + 1 == R) ? 0 : i + 1];      // warp-uniform
+        sdfast::Edge e; e.x0 = prev.x; e.y0 = prev.y; e.x1 = cur.x; e.y1 = cur.y;
+        sdfast::edge_pair(e, sa + i, f, fb, sb + j, acc);
+        prev = cur;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.I += __shfl_xor_sync(0xffffffffu, acc.I, o);
+      acc.len += __shfl_xor_sync(0xffffffffu, acc.len, o);
+      acc.K += __shfl_xor_sync(0xffffffffu, acc.K, o);
+      wq += __shfl_xor_sync(0xffffffffu, wq, o);
+      wp += __shfl_xor_sync(0xffffffffu, wp, o);
+    }
+    if (lane == 0) {
+      const double I = acc.I + (double)wq * A.sarea[h] + (double)wp * A.sarea[c];
+      const double bound = sdfast::clipper_bound(acc, (double)A.maxlen[h] + (double)A.maxlen[c], A.max_abs_coord, R);
+      const double den = fmin((double)A.area[h] + 1.e-10, (double)A.area[c] + 1.e-10);
+      const int d = sdfast::decide(I, bound, den, A.threshold);
+      if (verify) verdict[w] = (signed char)d;
+      else if (d == 1) A.state[c] = ST_SUPPRESSED;
+      else if (d < 0) xpairs[atomicAdd(&counters[9], 1u)] = pr;
+    }
+  }
+}
+
+// Exact sweep, one pair per thread.  The sweep is long, branchy, per-lane serial code: lanes of a warp that
+// run different pairs mostly serialise.  Pairs are therefore dealt round-robin over ALL resident warps
+// (pair p -> warp p % G, lane p / G): a round with few pairs runs one pair per warp at full single-thread
+// speed instead of 32 pairs in one warp.  n_list: &counters[1] (all pairs) or &counters[9] (pre-filtered).
+template <int NV>
+__global__ void __launch_bounds__(128) k_clip(NmsArrays A, const int2* __restrict__ pairs, const unsigned int* __restrict__ n_list,
+                                              const signed char* __restrict__ verdict,
+                                              int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
+  if (counters[5]) return;
+  const unsigned int n_pairs = *n_list;
   const unsigned int G = (gridDim.x * blockDim.x) >> 5;                       // warps in the grid
   const unsigned int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp_g >= n_pairs) return;
   sdclip::ClipSweep<NV, 1> S;
   for (unsigned int t = lane * G + warp_g; t < n_pairs; t += 32 * G) {
     const int2 pr = pairs[t];
-    if (A.state[pr.y] == ST_SUPPRESSED) continue;        // already suppressed by another pair (benign race)
+    if (!verdict && A.state[pr.y] == ST_SUPPRESSED) continue;        // already suppressed by another pair (benign race)
     const int r = pair_suppresses<NV, 1>(A, pr.x, pr.y, S);
     if (r == 1) A.state[pr.y] = ST_SUPPRESSED;
     else if (r < 0) { const unsigned int k = atomicAdd(&counters[4], 1u); slow_pairs[k] = pr; }
+    if (verdict && r >= 0) {
+      const int d = verdict[t];
+      if (d < 0) atomicAdd(&counters[9], 1u);            // would have gone to the exact sweep
+      else if (d != r) atomicAdd(&counters[10], 1u);     // the pre-filter would have decided wrongly
+    }
   }
 }
 
@@ -161,7 +224,8 @@ __global__ void __launch_bounds__(64) k_clip_slow(NmsArrays A, const int2* __res
 
 __global__ void k_reset_counters(unsigned int* counters) {
   if (counters[5]) return;
-  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; counters[8] = counters[7]; counters[7] = 0; }
+  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; counters[8] = counters[7]; counters[7] = 0;
+                        counters[12] += counters[9]; counters[9] = 0; }
 }
 
 template <int NV>
@@ -171,7 +235,14 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
   const int n = A.n;
   constexpr int BATCH = 4;     // rounds launched per host synchronisation
   size_t cap = std::max<size_t>((size_t)n * 2, 1 << 15);
-  sdb::DevBuf b_pairs, b_slow, b_cursor, b_kept, b_list0, b_list1;
+  sdb::DevBuf b_pairs, b_slow, b_cursor, b_kept, b_list0, b_list1, b_xpairs, b_verdict;
+  const int filter = A.filter;
+  auto alloc_filter_lists = [&]() -> int {
+    if (filter == 1) SDB_CUDA(b_xpairs.alloc(cap * sizeof(int2), st));
+    if (filter == 2) SDB_CUDA(b_verdict.alloc(cap, st));
+    return 0;
+  };
+  if (alloc_filter_lists()) return 1;
   SDB_CUDA(b_list0.alloc((size_t)n * sizeof(int), st));
   SDB_CUDA(b_list1.alloc((size_t)n * sizeof(int), st));
   SDB_CUDA(b_cursor.alloc((size_t)n * sizeof(int2), st));
@@ -186,8 +257,14 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
     // grid sized for the capacity; threads beyond counters[1] exit immediately
     sdb::ProfSpan sp;
+    if (filter) {
+      sdb::profile_begin("nms2d_fast", st, &sp);
+      SDB_LAUNCH(k_fast, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
+      sdb::profile_end("nms2d_fast", st, &sp);
+    }
     sdb::profile_begin("nms2d_clip", st, &sp);
-    SDB_LAUNCH((k_clip<NV>), 148 * 7, 128, 0, st, A, b_pairs.as<int2>(), (unsigned int)cap, b_slow.as<int2>(), d_counters);
+    if (filter == 1) SDB_LAUNCH((k_clip<NV>), 148 * 7, 128, 0, st, A, b_xpairs.as<int2>(), d_counters + 9, (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
+    else SDB_LAUNCH((k_clip<NV>), 148 * 7, 128, 0, st, A, b_pairs.as<int2>(), d_counters + 1, filter == 2 ? b_verdict.as<signed char>() : (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
     sdb::profile_end("nms2d_clip", st, &sp);
     SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
     return 0;
@@ -204,12 +281,12 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
         else SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)lin, 0u, (const unsigned int*)(d_counters + 8), lout, d_counters);
       }
       if (launch_pair_stage(round)) return 1;
-      SDB_CUDA(cudaMemcpyAsync(h_pin + 8 * b, d_counters, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      SDB_CUDA(cudaMemcpyAsync(h_pin + 16 * b, d_counters, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     }
     SDB_CUDA(cudaStreamSynchronize(st));
     bool done = false;
     for (int b = 0; b < BATCH; ++b) {
-      const unsigned int* c = h_pin + 8 * b;
+      const unsigned int* c = h_pin + 16 * b;
       if (c[3] != 0) { sdb::set_error("nms2d: polygon clipping pools overflowed in the slow path"); return 1; }
       if (c[5] != 0) {
         // pair list overflowed in round round0+b: its frontier marks are in place, the later kernels of
@@ -217,7 +294,8 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
         cap = (size_t)c[1] + (size_t)c[1] / 2 + 1024;
         SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
         SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
-        const unsigned int zeros[8] = {c[0], 0, c[2], 0, 0, 0, c[6], c[7]};
+        if (alloc_filter_lists()) return 1;
+        const unsigned int zeros[10] = {c[0], 0, c[2], 0, 0, 0, c[6], c[7], c[8], 0};
         SDB_CUDA(cudaMemcpyAsync(d_counters, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st));
         round = round0 + b;
         if (launch_pair_stage(round)) return 1;
@@ -227,12 +305,18 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       }
       if (c[0] == 0) { done = true; break; }
     }
-    if (verbose) printf("NMS2D(b200): rounds=%d undecided(last)=%u pair tests so far=%u\n", round, h_pin[8 * (BATCH - 1)], h_pin[8 * (BATCH - 1) + 2] + h_pin[8 * (BATCH - 1) + 1]);
+    if (verbose > 1)
+      for (int b = 0; b < BATCH; ++b) { const unsigned int* c = h_pin + 16 * b; printf("  round %d: undecided=%u kept=%u pairs=%u exact=%u slow=%u\n", round0 + b, c[0], c[6], c[1], c[9], c[4]); }
+    if (verbose) printf("NMS2D(b200): rounds=%d undecided(last)=%u pair tests so far=%u\n", round, h_pin[16 * (BATCH - 1)], h_pin[16 * (BATCH - 1) + 2] + h_pin[16 * (BATCH - 1) + 1]);
     if (done) {
       // pairs tested = counters[2] (accumulated by k_reset_counters) + the pairs of the last counted rounds
-      unsigned int tot = 0;
-      for (int b = 0; b < BATCH; ++b) { const unsigned int* c = h_pin + 8 * b; tot = c[2] + c[1]; if (c[0] == 0) break; }
-      sdb::profile_add_units("nms2d_clip", (double)tot);
+      unsigned int tot = 0, exact = 0, bad = 0;
+      for (int b = 0; b < BATCH; ++b) { const unsigned int* c = h_pin + 16 * b; tot = c[2] + c[1]; exact = c[12] + c[9]; bad = c[10]; if (c[0] == 0) break; }
+      if (!filter) exact = tot;
+      sdb::profile_add_units("nms2d_clip", (double)exact);
+      sdb::profile_add_units("nms2d_fast", (double)tot);
+      g_filter_stats[0] += tot; g_filter_stats[1] += exact; g_filter_stats[2] += bad; g_filter_stats[3] += 1;
+      if (verbose) printf("NMS2D(b200): pair tests=%u, exact sweeps=%u (filter mode %d), verify mismatches=%u\n", tot, exact, filter, bad);
       break;
     }
     if (round > 4 * n + 8) { sdb::set_error("nms2d: no progress"); return 1; }

@@ -64,6 +64,48 @@ int hc_clip_paths(const int32_t* a_xy, int na, const int32_t* b_xy, int nb,
 
 }
 
+// ---------------------------------------------------------------- fast overlap integral (polyfast.cuh)
+#include "../../stardist_b200/csrc/polyfast.cuh"
+extern "C" {
+// out: I (overlap integral), bound (clipper_bound), K (crossings)
+void hc_fast_batch(const int32_t* a_xy, const int32_t* b_xy, int n_pairs, int n,
+                   double* out_I, double* out_bound, int* out_K) {
+#pragma omp parallel
+  {
+    std::vector<sdfast::Edge> ea(n), eb(n);
+    std::vector<double> fa(n), fb(n);
+#pragma omp for schedule(dynamic, 256)
+    for (int p = 0; p < n_pairs; p++) {
+      const int32_t* A = a_xy + 2 * (long)p * n; const int32_t* B = b_xy + 2 * (long)p * n;
+      double maxlen_a = 0, maxlen_b = 0, maxc = 0;
+      for (int i = 0; i < n; i++) {
+        int k = (i + 1) % n;
+        ea[i] = {A[2*i], A[2*i+1], A[2*k], A[2*k+1]};
+        eb[i] = {B[2*i], B[2*i+1], B[2*k], B[2*k+1]};
+        maxlen_a = fmax(maxlen_a, hypot((double)ea[i].x1 - ea[i].x0, (double)ea[i].y1 - ea[i].y0));
+        maxlen_b = fmax(maxlen_b, hypot((double)eb[i].x1 - eb[i].x0, (double)eb[i].y1 - eb[i].y0));
+        maxc = fmax(maxc, fmax(fmax(fabs((double)A[2*i]), fabs((double)A[2*i+1])), fmax(fabs((double)B[2*i]), fabs((double)B[2*i+1]))));
+      }
+      double sa = 0, sb = 0;
+      for (int i = n - 1; i >= 0; i--) {
+        fa[i] = sa; sa += sdfast::edge_F(ea[i].x0, ea[i].y0, ea[i].x1, ea[i].y1);
+        fb[i] = sb; sb += sdfast::edge_F(eb[i].x0, eb[i].y0, eb[i].x1, eb[i].y1);
+      }
+      int wq = 0, wp = 0;
+      for (int i = 0; i < n; i++) { wq += sdfast::wind_Q_edge(eb[i], A[0], A[1]); wp += sdfast::wind_P_edge(ea[i], B[0], B[1]); }
+      sdfast::Accum acc; acc.clear();
+      for (int j = 0; j < n; j++) {
+        const sdfast::Box bx = sdfast::edge_box(eb[j]);
+        for (int i = 0; i < n; i++) sdfast::edge_pair(ea[i], &fa[i], eb[j], bx, &fb[j], acc);
+      }
+      out_I[p] = acc.I + wq * sa + wp * sb;
+      out_bound[p] = sdfast::clipper_bound(acc, maxlen_a + maxlen_b, maxc, n);
+      out_K[p] = acc.K;
+    }
+  }
+}
+}
+
 // ---------------------------------------------------------------- 3D geometry (geom3d.cuh)
 #include "../../stardist_b200/csrc/geom3d.cuh"
 #include "../../stardist_b200/csrc/nms3d_pair.cuh"

@@ -12,7 +12,12 @@ cand = model._predict_sparse_device(img, prob_thresh=0.5)
 print("candidates", cand['n'])
 lib = L.load()
 keep = torch.zeros(cand['n'], dtype=torch.uint8, device='cuda')
-for verbose in (0, 1, 0):
+ref = None
+for mode, verbose in ((0, 0), (0, 2), (0, 0), (1, 0), (1, 2), (1, 0), (1, 0), (2, 1)):
+    L.nms2d_set_filter(mode)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     L.check(lib.sdb_nms2d(L.ptr(cand['dist']), L.ptr(cand['points_f32']), cand['n'], 32, 0.4, 1, 1, verbose, L.ptr(keep), L.stream_ptr()))
-    torch.cuda.synchronize(); print("nms2d %.2f ms kept %d" % (1e3 * (time.perf_counter() - t0), int(keep.sum())))
+    torch.cuda.synchronize(); print("filter mode %d: nms2d %.2f ms kept %d" % (mode, 1e3 * (time.perf_counter() - t0), int(keep.sum())))
+    if ref is None: ref = keep.clone()
+    assert torch.equal(ref, keep), "filter mode changes the result"
+print(L.nms2d_filter_stats())
