@@ -160,6 +160,8 @@ def main():
             if a in ev and b in ev: stage[k] = stage.get(k, 0.0) + ev[a].elapsed_time(ev[b])
     launches = _lib.launch_count()
     prof_clip = _lib.profile_get("nms2d_clip"); prof_conv = _lib.profile_get("conv_tc")
+    prof_fast = _lib.profile_get("nms2d_fast")
+    prof_nms = {k: _lib.profile_get("nms2d_" + k) for k in ("frontier", "pairs", "fast", "clip")}
     _lib.profile_enable(False)
     barrier()
     t = torch.tensor([dev_ms, float(n_inst)], dtype=torch.float64, device="cuda")
@@ -199,12 +201,38 @@ def main():
         peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
         peak_bw = peaks.get("hbm_gbs", 6650.0)
         src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
-        # dominant kernel of the step: the per-pair polygon clipping sweep of the NMS (k_clip).  Algorithmic
-        # bytes per tested pair: two 32-gon vertex rows (2 x R x 8 B) + areas/bbox/state (20 B) + pair index (8 B)
-        bytes_per_pair = 2 * N_RAYS * 8 + 28
-        clip_ms = prof_clip["ms"]; clip_launches = max(1, prof_clip["launches"])
-        clip_gbs = (prof_clip["units"] * bytes_per_pair) / (clip_ms / 1e3) / 1e9 if clip_ms > 0 else 0.0
-        conv_tfs = prof_conv["units"] / (prof_conv["ms"] / 1e3) / 1e12 if prof_conv["ms"] > 0 else 0.0
+        # Kernel rooflines, all timed live with CUDA events on the launching stream (sdb_profile_*):
+        #  conv_tc   tcgen05 3x3 convolutions of the U-Net: tensor bound; algorithmic flop = 2*9*Cin*Cout*H*W per layer
+        #            (each is issued as 3 fp16 MMAs -- hi*hi + lo*hi + hi*lo -- to carry fp32 accuracy)
+        #  nms2d_fast  closed-form overlap integral, one warp per candidate pair: integer/fp64 ALU work on L1/L2-resident
+        #            rows; algorithmic bytes per pair = two vertex rows (2*R*8) + two suffix rows (2*R*8) + 28
+        #  nms2d_clip  exact Clipper-equivalent sweep for the pairs the filter leaves open: serial per-thread latency
+        bytes_fast = 4 * N_RAYS * 8 + 28
+        bytes_clip = 2 * N_RAYS * 8 + 28
+        def rl(prof, bound, kernel, units_to_alg, peak, unit, extra=None):
+            ms = prof["ms"]
+            ach = units_to_alg * prof["units"] / (ms / 1e3) / (1e12 if unit == "TFLOP/s" else 1e9) if ms > 0 else 0.0
+            d = {"bound": bound, "kernel": kernel, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak if peak else None,
+                 "traffic": None, "ms_per_step": ms / args.steps, "launches_per_step": prof["launches"] / args.steps}
+            if extra: d.update(extra)
+            return d
+        rls = {
+            "conv_tc": rl(prof_conv, "tensor", "k_conv_tc (tcgen05 3x3 conv + 1x1 heads, all launches of the forward pass)", 1.0, peak_tf, "TFLOP/s",
+                          {"algorithmic_flop_per_step": prof_conv["units"] / args.steps, "issued_flop_factor": 3, "unet_forward_ms": unet_ms,
+                           "unet_algorithmic_tflops": fl / (unet_ms / 1e3) / 1e12 if unet_ms > 0 else None, "peak_source": src + " bf16_tflops_sustained"}),
+            "nms2d_fast": rl(prof_fast, "hbm", "k_fast (NMS pair pre-filter, closed-form overlap integral; ALU bound on cache-resident rows)", bytes_fast, peak_bw, "GB/s",
+                             {"pairs_per_step": prof_fast["units"] / args.steps, "algorithmic_bytes_per_pair": bytes_fast, "peak_source": src + " hbm_gbs"}),
+            "nms2d_clip": rl(prof_clip, "hbm", "k_clip<32> (exact Clipper-equivalent sweep of the pairs the pre-filter leaves open; latency bound)", bytes_clip, peak_bw, "GB/s",
+                             {"pairs_per_step": prof_clip["units"] / args.steps, "algorithmic_bytes_per_pair": bytes_clip, "peak_source": src + " hbm_gbs"}),
+        }
+        try:
+            for k, v in json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).items():
+                if k in rls and rls[k]["launches_per_step"]:
+                    rls[k]["traffic"] = v["dram_bytes_per_step"] / rls[k]["launches_per_step"]   # per launch, like achieved
+                    rls[k]["traffic_source"] = v["source"]
+        except Exception:
+            pass
+        dominant = max(rls, key=lambda k: rls[k]["ms_per_step"])
         out = {
             "metric": "instances/sec (predict_instances end-to-end)", "value": value, "unit": "instances/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms_max / args.steps,
@@ -212,20 +240,13 @@ def main():
             "config": {"workload": "StarDist2D predict_instances, 1024x1024, n_rays=32, seeded synthetic U-Net weights (configs[1])",
                        "prob_thresh": PROB_THRESH, "weights": "seeded Glorot body + fitted heads (bench_data.py)", "nms_thresh": NMS_THRESH, "l2": "flushed (256 MiB write) between steps",
                        "instances_per_image": n_total / (args.steps * world),
-                       "stages_ms": {k: v / args.steps for k, v in stage.items()}},
+                       "stages_ms": {k: v / args.steps for k, v in stage.items()},
+                       "nms_kernels_ms": {k: v["ms"] / args.steps for k, v in prof_nms.items()}},
             "clocks": clocks,
             "e2e": {"value": n_e2e / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_clip<32> (NMS pair clipping sweep; latency/divergence bound, not bandwidth bound)",
-                         "achieved": clip_gbs, "peak": peak_bw, "unit": "GB/s", "frac": clip_gbs / peak_bw if peak_bw else None,
-                         "traffic": None, "ms_per_step": clip_ms / args.steps, "launches_per_step": clip_launches / args.steps,
-                         "pairs_per_step": prof_clip["units"] / args.steps, "algorithmic_bytes_per_pair": bytes_per_pair, "peak_source": src + " hbm_gbs"},
-            "roofline_conv": {"bound": "tensor", "kernel": "k_conv_tc (tcgen05 3x3 conv, all launches of the forward pass)",
-                              "achieved": conv_tfs, "peak": peak_tf, "unit": "TFLOP/s", "frac": conv_tfs / peak_tf if peak_tf else None,
-                              "traffic": None, "ms_per_step": prof_conv["ms"] / args.steps, "launches_per_step": prof_conv["launches"] / args.steps,
-                              "algorithmic_flop_per_step": prof_conv["units"] / args.steps, "issued_flop_factor": 3,
-                              "unet_forward_ms": unet_ms, "unet_algorithmic_tflops": fl / (unet_ms / 1e3) / 1e12 if unet_ms > 0 else None,
-                              "peak_source": src + " bf16_tflops_sustained"},
+            "roofline": dict(rls[dominant], name=dominant),
+            "roofline_other": {k: v for k, v in rls.items() if k != dominant},
         }
         if not args.no_cpu_baseline and world == 1:
             try:

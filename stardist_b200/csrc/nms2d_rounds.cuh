@@ -41,46 +41,57 @@ __device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSwe
 // in this round enumerates the undecided candidates it reaches (only ~n_kept * degree work in total).
 // The undecided candidates are kept in a compacted list (double buffered: blocked candidates are
 // appended to list_out, counters[7] = its length; round 0 reads the identity list).
-__global__ void k_frontier2(NmsArrays A, int round, int2* __restrict__ cursor, int* __restrict__ kept_list,
+__global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2* __restrict__ cursor, int* __restrict__ kept_list,
                             const int* __restrict__ list_in, unsigned int n_in_or_all, const unsigned int* __restrict__ n_in_dev,
                             int* __restrict__ list_out, unsigned int* __restrict__ counters) {
+  // one WARP per undecided candidate: the neighbourhood scan is a chain of dependent loads, so the lanes
+  // test 32 list items per step (a kept candidate scans its whole 3x3 neighbourhood: ~2000 items)
   if (counters[5]) return;
-  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned int n_in = n_in_dev ? *n_in_dev : n_in_or_all;
-  if (i >= n_in) return;
-  const int c = list_in ? list_in[i] : (int)i;
-  if (A.state[c] != ST_UNDECIDED) return;
-  atomicAdd(&counters[0], 1u);
-  const float cy = A.points[2 * c], cx = A.points[2 * c + 1];
-  const int4 bc = A.bbox[c];
+  const unsigned int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
   const int kept_now = ST_KEPT_BASE + round;
-  int ccx = 0, ccy = 0;
-  if (!A.G.all_pairs) { ccx = cell_of(cx, A.G.minx, A.G.cell, A.G.gx); ccy = cell_of(cy, A.G.miny, A.G.cell, A.G.gy); }
-  int2 cur = cursor[c];          // (neighbour cell 0..8, offset inside that cell)
-  bool blocked = false;
-  for (int k = cur.x; k < 9 && !blocked; ++k) {
-    const int yy = ccy + k / 3 - 1, xx = ccx + k % 3 - 1;
-    if (yy < 0 || yy >= A.G.gy || xx < 0 || xx >= A.G.gx) { cur.x = k + 1; cur.y = 0; continue; }
-    const int cell = yy * A.G.gx + xx;
-    const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
-    unsigned int t = b + (unsigned int)cur.y;
-    for (; t < e; ++t) {
-      const int h = A.items[t];
-      if (h >= c) continue;
-      const int sh = A.state[h];
-      if (sh != ST_UNDECIDED && sh != kept_now) continue;
-      if (reaches(A, h, c, cy, cx, bc)) { blocked = true; break; }
+  unsigned int n_undecided = 0;
+  for (unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_in; i += warps) {
+    const int c = list_in ? list_in[i] : (int)i;
+    if (A.state[c] != ST_UNDECIDED) continue;
+    ++n_undecided;
+    const float cy = A.points[2 * c], cx = A.points[2 * c + 1];
+    const int4 bc = A.bbox[c];
+    int ccx = 0, ccy = 0;
+    if (!A.G.all_pairs) { ccx = cell_of(cx, A.G.minx, A.G.cell, A.G.gx); ccy = cell_of(cy, A.G.miny, A.G.cell, A.G.gy); }
+    int2 cur = cursor[c];          // (neighbour cell 0..8, offset inside that cell)
+    bool blocked = false;
+    for (int k = cur.x; k < 9 && !blocked; ++k) {
+      const int yy = ccy + k / 3 - 1, xx = ccx + k % 3 - 1;
+      if (yy < 0 || yy >= A.G.gy || xx < 0 || xx >= A.G.gx) { cur.x = k + 1; cur.y = 0; continue; }
+      const int cell = yy * A.G.gx + xx;
+      const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
+      for (unsigned int t0 = b + (unsigned int)cur.y; t0 < e; t0 += 32) {
+        const unsigned int t = t0 + lane;
+        bool hit = false;
+        if (t < e) {
+          const int h = A.items[t];
+          if (h < c) {
+            const int sh = A.state[h];
+            if (sh == ST_UNDECIDED || sh == kept_now) hit = reaches(A, h, c, cy, cx, bc);
+          }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, hit);
+        if (m) { blocked = true; cur.x = k; cur.y = (int)(t0 + (unsigned int)(__ffs(m) - 1) - b); break; }
+      }
+      if (!blocked) { cur.x = k + 1; cur.y = 0; }
     }
-    if (blocked) { cur.x = k; cur.y = (int)(t - b); }
-    else { cur.x = k + 1; cur.y = 0; }
+    if (lane == 0) {
+      cursor[c] = cur;
+      if (!blocked) {
+        A.state[c] = kept_now;
+        kept_list[atomicAdd(&counters[6], 1u)] = c;
+      } else {
+        list_out[atomicAdd(&counters[7], 1u)] = c;
+      }
+    }
   }
-  cursor[c] = cur;
-  if (!blocked) {
-    A.state[c] = kept_now;
-    kept_list[atomicAdd(&counters[6], 1u)] = c;
-  } else {
-    list_out[atomicAdd(&counters[7], 1u)] = c;
-  }
+  if (lane == 0 && n_undecided) atomicAdd(&counters[0], n_undecided);
 }
 
 // one warp per candidate kept in this round: emit the (h, c) pairs the reference would test (:548-576)
@@ -253,10 +264,11 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
   SDB_CUDA(cudaMemsetAsync(d_counters, 0, 16 * sizeof(unsigned int), st));
   int round = 0;
   auto launch_pair_stage = [&](int r) -> int {
-    SDB_LAUNCH(k_pairs, 148 * 8, 256, 0, st, A, r, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)cap, d_counters);
-    SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
-    // grid sized for the capacity; threads beyond counters[1] exit immediately
     sdb::ProfSpan sp;
+    sdb::profile_begin("nms2d_pairs", st, &sp);
+    SDB_LAUNCH(k_pairs, 148 * 8, 256, 0, st, A, r, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)cap, d_counters);
+    sdb::profile_end("nms2d_pairs", st, &sp);
+    SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
     if (filter) {
       sdb::profile_begin("nms2d_fast", st, &sp);
       SDB_LAUNCH(k_fast, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
@@ -277,8 +289,11 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
         // round r reads the list written by round r-1 (length saved in counters[8] by k_reset_counters)
         int* lin = (round & 1) ? b_list1.as<int>() : b_list0.as<int>();
         int* lout = (round & 1) ? b_list0.as<int>() : b_list1.as<int>();
-        if (round == 0) SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)nullptr, (unsigned int)n, (const unsigned int*)nullptr, lout, d_counters);
-        else SDB_LAUNCH(k_frontier2, cdiv(n, 256), 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)lin, 0u, (const unsigned int*)(d_counters + 8), lout, d_counters);
+        sdb::ProfSpan spf;
+        sdb::profile_begin("nms2d_frontier", st, &spf);
+        if (round == 0) SDB_LAUNCH(k_frontier2, 148 * 8, 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)nullptr, (unsigned int)n, (const unsigned int*)nullptr, lout, d_counters);
+        else SDB_LAUNCH(k_frontier2, 148 * 8, 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)lin, 0u, (const unsigned int*)(d_counters + 8), lout, d_counters);
+        sdb::profile_end("nms2d_frontier", st, &spf);
       }
       if (launch_pair_stage(round)) return 1;
       SDB_CUDA(cudaMemcpyAsync(h_pin + 16 * b, d_counters, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));

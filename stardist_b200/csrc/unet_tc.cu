@@ -278,6 +278,212 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------- v3: persistent, pipelined across tiles
+// Same tile and operand layout as k_conv_tc, but
+//   * persistent: grid = #SMs, CTA i sweeps tiles i, i+grid, ... ; the TMA ring keeps running across tile
+//     boundaries, so the load latency of a tile hides behind the MMAs of the previous one;
+//   * two TMEM accumulator buffers: the MMA warp fills buffer (t+1)&1 while the epilogue warps drain t&1
+//     (k_conv_tc paid barrier-init + TMEM alloc + pipeline fill + drain per 128 pixels: ~2/3 of its time);
+//   * merged N: W_hi and W_lo tiles sit back to back in shared memory, so  A_hi x [W_hi | W_lo]  is ONE MMA
+//     of width 2N into 2N accumulator columns; the second MMA  A_lo x W_hi  accumulates into the first N.
+//     Two A reads per k-step instead of three (the MMA is shared-memory-read bound for N <= 64), the epilogue
+//     adds the two column groups.  Needs 4N <= 512 TMEM columns: N <= 128.
+template <int N, int KC>
+struct TcCfg3 {
+  static constexpr int ROWB = KC * 2;
+  static constexpr int A_BYTES = 128 * ROWB;
+  static constexpr int B_BYTES = N * ROWB;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int ACC_COLS = 2 * N;
+  static constexpr int TMEM_COLS = 4 * N;                  // 128 / 256 / 512: powers of two
+  static constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : 4u;
+  static constexpr uint32_t SBO = 8 * ROWB;
+  static constexpr uint32_t IDESC_N = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static_assert(N == 32 || N == 64 || N == 128, "merged-N variant: N in {32, 64, 128}");
+  static_assert(STAGES >= 2, "pipeline needs two stages");
+};
+
+#define SDB_TMEM_LD32(r, taddr)                                                                                        \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                               \
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"               \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+               : "r"(taddr))
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int N, int KC>
+__global__ void __launch_bounds__(192, 1)
+k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
+           const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
+           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P,
+           int tiles_x, int tiles_y, int n_tiles) {
+  using C = TcCfg3<N, KC>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* acc_full = empty_bar + C::STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cb = P.c_total / KC;
+  const int n_kb = 9 * n_cb;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+        const int y0 = (rem / tiles_x) * 8, x0 = (rem % tiles_x) * 16;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const uint32_t s = it % C::STAGES;
+          if (it >= (uint32_t)C::STAGES) {
+            if (!mbar_wait(&empty_bar[s], ((it / C::STAGES) - 1) & 1)) { atomicExch(P.error_flag, 1u); ok = false; break; }
+          }
+          const int tap = kb / n_cb, cb = kb - tap * n_cb;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const int ch = cb * KC;
+          unsigned char* st = smem + s * C::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
+          if (ch < P.c_src0) {
+            tma_load_4d(st, &tm_a0_hi, &full_bar[s], ch, x0 + dx, y0 + dy, img);
+            tma_load_4d(st + C::A_BYTES, &tm_a0_lo, &full_bar[s], ch, x0 + dx, y0 + dy, img);
+          } else {
+            tma_load_4d(st, &tm_a1_hi, &full_bar[s], ch - P.c_src0, x0 + dx, y0 + dy, img);
+            tma_load_4d(st + C::A_BYTES, &tm_a1_lo, &full_bar[s], ch - P.c_src0, x0 + dx, y0 + dy, img);
+          }
+          tma_load_3d(st + 2 * C::A_BYTES, &tm_w_hi, &full_bar[s], ch, 0, tap);
+          tma_load_3d(st + 2 * C::A_BYTES + C::B_BYTES, &tm_w_lo, &full_bar[s], ch, 0, tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, t = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
+        const uint32_t buf = t & 1;
+        if (t >= 2) {
+          if (!mbar_wait(&acc_empty[buf], ((t >> 1) - 1) & 1)) { atomicExch(P.error_flag, 4u); ok = false; break; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t d = tmem_base + buf * (uint32_t)C::ACC_COLS;
+        for (int kb = 0; kb < n_kb; ++kb, ++it) {
+          const uint32_t s = it % C::STAGES;
+          if (!mbar_wait(&full_bar[s], (it / C::STAGES) & 1)) { atomicExch(P.error_flag, 2u); ok = false; break; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(smem + s * C::STAGE_BYTES), a_lo = a_hi + C::A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * C::A_BYTES;          // W_hi rows, W_lo rows directly behind
+#pragma unroll
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            const uint32_t koff = ks * 32;
+            const uint64_t dah = make_desc(a_hi + koff, C::SBO, C::LAYOUT), dal = make_desc(a_lo + koff, C::SBO, C::LAYOUT);
+            const uint64_t dbh = make_desc(b_hi + koff, C::SBO, C::LAYOUT);
+            umma_f16(d, dah, dbh, C::IDESC_2N, (kb | ks) ? 1u : 0u);      // cols [0,N): hi*Whi, [N,2N): hi*Wlo
+            umma_f16(d, dal, dbh, C::IDESC_N, 1u);                         // cols [0,N) += lo*Whi
+          }
+          tcgen05_commit(&empty_bar[s]);
+        }
+        tcgen05_commit(&acc_full[buf]);        // (arrives even after a bail-out so the epilogue does not wait forever)
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> 4, tx = m & 15;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const uint32_t buf = t & 1;
+      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+      const int y = (rem / tiles_x) * 8 + ty, x = (rem % tiles_x) * 16 + tx;
+      const bool in_img = (y < P.H) && (x < P.W);
+      if (!mbar_wait(&acc_full[buf], (t >> 1) & 1)) { atomicExch(P.error_flag, 3u); break; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)C::ACC_COLS;
+#pragma unroll 1
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t r[32], r2[32];
+        SDB_TMEM_LD32(r, tbase + (uint32_t)c0);
+        SDB_TMEM_LD32(r2, tbase + (uint32_t)(N + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= N) {
+          // all TMEM reads of this tile are done: hand the buffer back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (in_img) {
+          __align__(16) __half hi[32];
+          __align__(16) __half lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float v = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) * P.acc_scale + __ldg(P.bias + c0 + j);
+            if (P.relu) v = fmaxf(v, 0.f);
+            const __half h = __float2half_rn(v);
+            hi[j] = h;
+            lo[j] = __float2half_rn(v - __half2float(h));
+          }
+          if (!P.up2x) {
+            const size_t off = (((size_t)img * P.H + y) * P.W + x) * N + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+              reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+            }
+          } else {
+            const int H2 = 2 * P.H, W2 = 2 * P.W;
+#pragma unroll
+            for (int rep = 0; rep < 4; ++rep) {
+              const size_t off = (((size_t)img * H2 + (2 * y + (rep >> 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------- v2: halo-reuse strips
 // CTA tile = S image rows x 128 pixels.  For every 32-channel block the (S+2) x 130 pixel halo is
 // loaded ONCE (one 4-D TMA box per plane) and all 9 taps read it through shifted UMMA descriptors
@@ -695,6 +901,29 @@ static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
   return 0;
 }
 
+static int g_tc_variant = 3;      // 1 = k_conv_tc (one tile per CTA), 3 = k_conv_tc3 (persistent, merged N) where applicable
+static int g_num_sms = 0;
+
+template <int N, int KC>
+static int launch_tc3(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+  using C = TcCfg3<N, KC>;
+  static bool attr = false;
+  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc3<N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
+  if (!g_num_sms) { int dev = 0; SDB_CUDA(cudaGetDevice(&dev)); SDB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const int tiles_x = cdiv(P.W, 16), tiles_y = cdiv(P.H, 8);
+  const int n_tiles = tiles_x * tiles_y * n_img;
+  const int grid = std::min(n_tiles, g_num_sms);
+  sdb::ProfSpan sp;
+  sdb::profile_begin("conv_tc", st, &sp);
+  k_conv_tc3<N, KC><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles);
+  sdb::profile_end("conv_tc", st, &sp);
+  sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);
+  sdb::g_launch_count++;
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int N, int S>
 static int launch_tc2(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
                       const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, int boff_mode, cudaStream_t st) {
@@ -737,6 +966,12 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
+#define SDB_TC3(NN, KK) return launch_tc3<NN, KK>(a0h, a0l, a1h, a1l, wh, wl, P, n, st)
+  if (g_tc_variant == 3 && cout <= 128) {
+    if (kc == 64) { if (cout == 32) SDB_TC3(32, 64); if (cout == 64) SDB_TC3(64, 64); SDB_TC3(128, 64); }
+    else { if (cout == 32) SDB_TC3(32, 32); if (cout == 64) SDB_TC3(64, 32); SDB_TC3(128, 32); }
+  }
+#undef SDB_TC3
 #define SDB_TC(NN, KK) return launch_tc<NN, KK>(a0h, a0l, a1h, a1l, wh, wl, P, n, st)
   if (kc == 64) {
     if (cout == 32) SDB_TC(32, 64); if (cout == 64) SDB_TC(64, 64); if (cout == 128) SDB_TC(128, 64); SDB_TC(256, 64);
@@ -792,6 +1027,13 @@ extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_s
   if (cout == 64) return launch_tc2<64, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 128) return launch_tc2<128, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   return launch_tc2<256, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
+}
+
+// A/B switch for tests and profiling: 1 = one-tile-per-CTA kernel, 3 = persistent kernel (default)
+extern "C" int sdb_tc_set_variant(int variant) {
+  if (variant != 1 && variant != 3) { sdb::set_error("tc_set_variant: 1 or 3"); return 1; }
+  g_tc_variant = variant;
+  return 0;
 }
 
 // non-zero when any tcgen05 conv launch since the last call hit a bounded-wait timeout (then results are invalid)
