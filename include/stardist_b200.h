@@ -168,8 +168,9 @@ int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const 
  * rows 1..n_rays = dist, zero padded to np in {48, 80, 112, 144}; outputs fp32 */
 int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n, int h, int w, const void* w_hi, const void* w_lo,
                  float w_scale, const float* d_bias, int np, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream);
-/* kernel variant of sdb_conv3x3_tc: 1 = one 8x16 tile per CTA, 3 (default) = persistent CTAs, double-buffered
- * TMEM accumulators, merged hi/lo weight tile (cout <= 128).  Results are identical up to fp32 summation order. */
+/* kernel variant of sdb_conv3x3_tc: 0 (default) = auto, 1 = one 8x16 tile per CTA, 3 = persistent CTAs with
+ * double-buffered TMEM accumulators and merged hi/lo weight tile, 4 = 3 + halo reuse (one box load per
+ * 32-channel block, taps as shifted descriptors).  Results are identical up to fp32 summation order. */
 int sdb_tc_set_variant(int variant);
 int sdb_tc_error_check(sdb_stream_t stream);
 /* w_scale: power of two the weights are multiplied by before the split (undone on the accumulator) */

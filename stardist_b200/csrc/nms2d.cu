@@ -154,6 +154,37 @@ __global__ void k_cell_fill(const int* __restrict__ cell_of_pt, int n, unsigned 
   items[pos] = i;
 }
 
+// sort every cell's item list by candidate index (= score order): the frontier scan of candidate c then only
+// walks the prefix h < c, which is EMPTY for the local maxima that used to scan their whole neighbourhood.
+// Rank by counting; a cell holds a few hundred items (cell edge = 2 max_dist).
+__global__ void __launch_bounds__(256) k_cell_sort(const unsigned int* __restrict__ cell_start, const int* __restrict__ items_in,
+                                                   int* __restrict__ items_out) {
+  const unsigned int b = cell_start[blockIdx.x], e = cell_start[blockIdx.x + 1];
+  __shared__ int sh[2048];
+  const unsigned int m = e - b;
+  if (m <= 2048) {
+    for (unsigned int i = threadIdx.x; i < m; i += blockDim.x) sh[i] = items_in[b + i];
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < m; i += blockDim.x) {
+      const int v = sh[i];
+      unsigned int r = 0;
+      for (unsigned int j = 0; j < m; ++j) r += (sh[j] < v) ? 1u : 0u;
+      items_out[b + r] = v;
+    }
+  } else {
+    for (unsigned int i = threadIdx.x; i < m; i += blockDim.x) {
+      const int v = items_in[b + i];
+      unsigned int r = 0;
+      for (unsigned int j = 0; j < m; ++j) r += (items_in[b + j] < v) ? 1u : 0u;
+      items_out[b + r] = v;
+    }
+  }
+}
+__global__ void k_iota(int* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
+}
+
 __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __restrict__ keep) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) keep[i] = (state[i] != ST_SUPPRESSED) ? 1 : 0;
@@ -237,7 +268,14 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   SDB_LAUNCH(k_scan_add, cdiv(n_cells + 1, 256), 256, 0, st, b_start.as<unsigned int>(), n_cells + 1, b_tiles.as<unsigned int>());
   // cursor = copy of starts (counts buffer reused)
   SDB_CUDA(cudaMemcpyAsync(b_counts.p, b_start.p, (size_t)(n_cells + 1) * sizeof(unsigned int), cudaMemcpyDeviceToDevice, st));
-  SDB_LAUNCH(k_cell_fill, cdiv(n, 256), 256, 0, st, b_cellpt.as<int>(), n, b_counts.as<unsigned int>(), b_items.as<int>());
+  sdb::DevBuf b_items_raw;
+  if (G.all_pairs) {
+    SDB_LAUNCH(k_iota, cdiv(n, 256), 256, 0, st, b_items.as<int>(), n);        // single cell: already sorted
+  } else {
+    SDB_CUDA(b_items_raw.alloc((size_t)n * sizeof(int), st));
+    SDB_LAUNCH(k_cell_fill, cdiv(n, 256), 256, 0, st, b_cellpt.as<int>(), n, b_counts.as<unsigned int>(), b_items_raw.as<int>());
+    SDB_LAUNCH(k_cell_sort, n_cells, 256, 0, st, b_start.as<unsigned int>(), b_items_raw.as<int>(), b_items.as<int>());
+  }
 
   NmsArrays A;
   A.points = d_points; A.radius = b_radius.as<float>(); A.area = b_area.as<float>();

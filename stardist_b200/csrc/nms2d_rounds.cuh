@@ -68,16 +68,17 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
       const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
       for (unsigned int t0 = b + (unsigned int)cur.y; t0 < e; t0 += 32) {
         const unsigned int t = t0 + lane;
-        bool hit = false;
+        bool hit = false, past = false;
         if (t < e) {
           const int h = A.items[t];
           if (h < c) {
             const int sh = A.state[h];
             if (sh == ST_UNDECIDED || sh == kept_now) hit = reaches(A, h, c, cy, cx, bc);
-          }
+          } else past = true;
         }
         const unsigned int m = __ballot_sync(0xffffffffu, hit);
         if (m) { blocked = true; cur.x = k; cur.y = (int)(t0 + (unsigned int)(__ffs(m) - 1) - b); break; }
+        if (__any_sync(0xffffffffu, past)) break;     // cell lists are sorted by index: nothing below c is left
       }
       if (!blocked) { cur.x = k + 1; cur.y = 0; }
     }
@@ -94,14 +95,13 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
   if (lane == 0 && n_undecided) atomicAdd(&counters[0], n_undecided);
 }
 
-// one warp per candidate kept in this round: emit the (h, c) pairs the reference would test (:548-576)
-__global__ void k_pairs(NmsArrays A, int round, const int* __restrict__ kept_list, int2* __restrict__ pairs, unsigned int cap,
+// one BLOCK per candidate kept in this round: emit the (h, c) pairs the reference would test (:548-576).
+// (A warp per h walked ~2000 neighbour items in 60 dependent steps: ~100 us per round regardless of the count.)
+__global__ void __launch_bounds__(256) k_pairs(NmsArrays A, int round, const int* __restrict__ kept_list, int2* __restrict__ pairs, unsigned int cap,
                         unsigned int* __restrict__ counters) {
   if (counters[5]) return;
   const unsigned int n_kept = counters[6];
-  const int lane = threadIdx.x & 31;
-  const unsigned int warps = (gridDim.x * blockDim.x) >> 5;
-  for (unsigned int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_kept; w += warps) {
+  for (unsigned int w = blockIdx.x; w < n_kept; w += gridDim.x) {
     const int h = kept_list[w];
     const float hy = A.points[2 * h], hx = A.points[2 * h + 1];
     const int4 bh = A.bbox[h];
@@ -112,7 +112,7 @@ __global__ void k_pairs(NmsArrays A, int round, const int* __restrict__ kept_lis
       for (int xx = max(hcx - 1, 0); xx <= min(hcx + 1, A.G.gx - 1); ++xx) {
         const int cell = yy * A.G.gx + xx;
         const unsigned int e = A.cell_start[cell + 1];
-        for (unsigned int t = A.cell_start[cell] + lane; t < e; t += 32) {
+        for (unsigned int t = A.cell_start[cell] + threadIdx.x; t < e; t += blockDim.x) {
           const int c = A.items[t];
           if (c <= h) continue;
           if (A.state[c] != ST_UNDECIDED) continue;
@@ -139,6 +139,7 @@ __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ co
 // for n_rays > 32) and walks the suppressor's edges, which are warp-uniform loads; the closed-form overlap
 // integral and its bound decide most pairs, the rest is appended to the exact list (counters[9]).
 // verify != 0: nothing is decided here, the verdict is stored per pair for k_clip to compare.
+template <typename T>
 __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restrict__ pairs, int2* __restrict__ xpairs,
                                               signed char* __restrict__ verdict, int verify, unsigned int* __restrict__ counters) {
   if (counters[5]) return;
@@ -163,12 +164,11 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
       sdfast::Edge e2; e2.x0 = a0.x; e2.y0 = a0.y; e2.x1 = a1.x; e2.y1 = a1.y;
       wq += sdfast::wind_Q_edge(f, p0.x, p0.y);
       wp += sdfast::wind_P_edge(e2, q0.x, q0.y);
-      const sdfast::Box fb = sdfast::edge_box(f);
       int2 prev = p0;
       for (int i = 0; i < R; ++i) {
         const int2 cur = va[(i + 1 == R) ? 0 : i + 1];      // warp-uniform
         sdfast::Edge e; e.x0 = prev.x; e.y0 = prev.y; e.x1 = cur.x; e.y1 = cur.y;
-        sdfast::edge_pair(e, sa + i, f, fb, sb + j, acc);
+        sdfast::edge_pair<T>(e, sa + i, f, sb + j, acc);
         prev = cur;
       }
     }
@@ -271,7 +271,8 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
     if (filter) {
       sdb::profile_begin("nms2d_fast", st, &sp);
-      SDB_LAUNCH(k_fast, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
+      if (A.max_abs_coord <= 8191.0) SDB_LAUNCH(k_fast<int32_t>, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
+      else SDB_LAUNCH(k_fast<long long>, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
       sdb::profile_end("nms2d_fast", st, &sp);
     }
     sdb::profile_begin("nms2d_clip", st, &sp);

@@ -297,13 +297,15 @@ struct TcCfg3 {
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int ACC_COLS = 2 * N;
-  static constexpr int TMEM_COLS = 4 * N;                  // 128 / 256 / 512: powers of two
+  static constexpr int ACC_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : 256));   // buffer stride
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr int NPAD32 = (N + 31) / 32 * 32;
   static constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * ROWB;
   static constexpr uint32_t IDESC_N = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  static_assert(N == 32 || N == 64 || N == 128, "merged-N variant: N in {32, 64, 128}");
+  static_assert(N % 16 == 0 && 2 * N <= 256, "merged-N variant: N multiple of 16, N <= 128");
+  static_assert((B_BYTES % 1024) == 0 || ROWB == 64, "W_lo tile must start on a swizzle-atom boundary");
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
 
@@ -338,7 +340,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cb = P.c_total / KC;
-  const int n_kb = 9 * n_cb;
+  const int n_kb = P.n_taps * n_cb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -370,7 +372,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
             if (!mbar_wait(&empty_bar[s], ((it / C::STAGES) - 1) & 1)) { atomicExch(P.error_flag, 1u); ok = false; break; }
           }
           const int tap = kb / n_cb, cb = kb - tap * n_cb;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          const int dy = (P.n_taps == 9) ? tap / 3 - 1 : 0, dx = (P.n_taps == 9) ? tap % 3 - 1 : 0;
           const int ch = cb * KC;
           unsigned char* st = smem + s * C::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], C::STAGE_BYTES);
@@ -432,16 +434,29 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)C::ACC_COLS;
 #pragma unroll 1
-      for (int c0 = 0; c0 < N; c0 += 32) {
+      for (int c0 = 0; c0 < C::NPAD32; c0 += 32) {
         uint32_t r[32], r2[32];
         SDB_TMEM_LD32(r, tbase + (uint32_t)c0);
         SDB_TMEM_LD32(r2, tbase + (uint32_t)(N + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= N) {
+        if (c0 + 32 >= C::NPAD32) {
           // all TMEM reads of this tile are done: hand the buffer back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        if (in_img && P.heads_R > 0) {
+          // heads: channel 0 -> sigmoid -> prob, channels 1..R -> dist (fp32)
+          const size_t pix = ((size_t)img * P.H + y) * P.W + x;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ch = c0 + j;
+            if (ch > P.heads_R) break;
+            const float v = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) * P.acc_scale + __ldg(P.bias + ch);
+            if (ch == 0) P.prob[pix] = 1.f / (1.f + expf(-v));
+            else P.dist[pix * P.heads_R + (ch - 1)] = v;
+          }
+          continue;
         }
         if (in_img) {
           __align__(16) __half hi[32];
@@ -640,6 +655,232 @@ k_conv_tc2(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                        : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (in_img) {
+            __align__(16) __half hi[32];
+            __align__(16) __half lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + c0 + j);
+              if (P.relu) v = fmaxf(v, 0.f);
+              const __half h = __float2half_rn(v);
+              hi[j] = h;
+              lo[j] = __float2half_rn(v - __half2float(h));
+            }
+            if (!P.up2x) {
+              const size_t off = (((size_t)img * P.H + y) * P.W + x) * N + c0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            } else {
+              const int H2 = 2 * P.H, W2 = 2 * P.W;
+#pragma unroll
+              for (int rep = 0; rep < 4; ++rep) {
+                const size_t off = (((size_t)img * H2 + (2 * y + (rep >> 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                  reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------- v4: persistent + halo reuse
+// k_conv_tc2's data movement (the (S+2) x 130 pixel halo of a 32-channel block is loaded ONCE, the nine taps
+// are shifted UMMA descriptors into it) with k_conv_tc3's schedule (persistent CTAs, TMA ring running across
+// tiles, two TMEM accumulator buffers, merged hi/lo weight tile where the columns allow it).  For the
+// high-resolution, few-channel layers (Cin <= 64) the per-tap A re-fetch of k_conv_tc/k_conv_tc3 made them
+// L2->SMEM bound (180 KB per 128 pixels at Cin = 32); here it is ~50 KB.
+//   tile = S = 2 image rows x 128 pixels; accumulators: S x (MERGE ? 2N : N) TMEM columns per buffer.
+template <int N>
+struct TcCfg4 {
+  static constexpr int S = 2, KC = 32, ROWB = 64;
+  static constexpr bool MERGE = (N <= 64);
+  static constexpr int HROWS = (S + 2) * 130;
+  static constexpr int A_PLANE = ((HROWS * ROWB + 1023) / 1024) * 1024;
+  static constexpr int A_STAGE = 2 * A_PLANE;
+  static constexpr int A_STAGES = 2;
+  static constexpr int B_STAGE = 2 * N * ROWB;
+  static constexpr int B_STAGES = (N >= 128) ? 4 : 6;
+  static constexpr int SMEM = A_STAGES * A_STAGE + B_STAGES * B_STAGE + 1024 + 256;
+  static constexpr int STRIP_COLS = MERGE ? 2 * N : N;
+  static constexpr int ACC_COLS = S * STRIP_COLS;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;           // 256 (N=32) / 512 (N=64, N=128)
+  static constexpr uint32_t IDESC_N = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static_assert(N == 32 || N == 64 || N == 128, "N in {32, 64, 128}");
+  static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(SMEM <= 227 * 1024, "shared memory");
+};
+
+template <int N>
+__global__ void __launch_bounds__(192, 1)
+k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
+           const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
+           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P,
+           int tiles_x, int tiles_y, int n_tiles) {
+  using C = TcCfg4<N>;
+  constexpr int S = C::S;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  unsigned char* smA = smem;
+  unsigned char* smB = smem + C::A_STAGES * C::A_STAGE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + C::B_STAGES * C::B_STAGE);
+  uint64_t* a_empty = a_full + C::A_STAGES;
+  uint64_t* b_full = a_empty + C::A_STAGES;
+  uint64_t* b_empty = b_full + C::B_STAGES;
+  uint64_t* acc_full = b_empty + C::B_STAGES;      // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cb = P.c_total / C::KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = tiles_x * tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+        const int y0 = (rem / tiles_x) * S, x0 = (rem % tiles_x) * 128;
+        for (int cb = 0; cb < n_cb && ok; ++cb, ++ai) {
+          const uint32_t sa = ai % C::A_STAGES;
+          if (ai >= (uint32_t)C::A_STAGES && !mbar_wait(&a_empty[sa], ((ai / C::A_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 11u); ok = false; break; }
+          const int ch = cb * C::KC;
+          unsigned char* sta = smA + sa * C::A_STAGE;
+          mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
+          if (ch < P.c_src0) {
+            tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+            tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+          } else {
+            tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+            tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+          }
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const uint32_t sb = bi % C::B_STAGES;
+            if (bi >= (uint32_t)C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
+            unsigned char* stb = smB + sb * C::B_STAGE;
+            mbar_expect_tx(&b_full[sb], C::B_STAGE);
+            tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
+            tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[sb], ch, 0, tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t ai = 0, bi = 0, t = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
+        const uint32_t buf = t & 1;
+        if (t >= 2) {
+          if (!mbar_wait(&acc_empty[buf], ((t >> 1) - 1) & 1)) { atomicExch(P.error_flag, 16u); ok = false; break; }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t d0 = tmem_base + buf * (uint32_t)C::ACC_COLS;
+        for (int cb = 0; cb < n_cb && ok; ++cb, ++ai) {
+          const uint32_t sa = ai % C::A_STAGES;
+          if (!mbar_wait(&a_full[sa], (ai / C::A_STAGES) & 1)) { atomicExch(P.error_flag, 13u); ok = false; break; }
+          const uint32_t a_hi = smem_u32(smA + sa * C::A_STAGE), a_lo = a_hi + C::A_PLANE;
+          for (int tap = 0; tap < 9; ++tap, ++bi) {
+            const uint32_t sb = bi % C::B_STAGES;
+            if (!mbar_wait(&b_full[sb], (bi / C::B_STAGES) & 1)) { atomicExch(P.error_flag, 14u); ok = false; break; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t b_hi = smem_u32(smB + sb * C::B_STAGE), b_lo = b_hi + N * C::ROWB;
+            const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+              const uint32_t roff = (uint32_t)((s + dy) * 130 + dx) * C::ROWB;
+              const uint32_t d = d0 + (uint32_t)(s * C::STRIP_COLS);
+#pragma unroll
+              for (int ks = 0; ks < C::KC / 16; ++ks) {
+                const uint32_t koff = ks * 32;
+                const uint64_t dah = make_desc_sw64(a_hi + roff + koff, 0), dal = make_desc_sw64(a_lo + roff + koff, 0);
+                const uint64_t dbh = make_desc_sw64(b_hi + koff, 0);
+                const uint32_t acc = (cb | tap | ks) ? 1u : 0u;
+                if (C::MERGE) {
+                  umma_f16(d, dah, dbh, C::IDESC_2N, acc);       // [0,N): hi*Whi   [N,2N): hi*Wlo
+                  umma_f16(d, dal, dbh, C::IDESC_N, 1u);         // [0,N) += lo*Whi
+                } else {
+                  const uint64_t dbl = make_desc_sw64(b_lo + koff, 0);
+                  umma_f16(d, dah, dbh, C::IDESC_N, acc);
+                  umma_f16(d, dal, dbh, C::IDESC_N, 1u);
+                  umma_f16(d, dah, dbl, C::IDESC_N, 1u);
+                }
+              }
+            }
+            tcgen05_commit(&b_empty[sb]);
+          }
+          tcgen05_commit(&a_empty[sa]);
+        }
+        tcgen05_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    uint32_t t = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+      const uint32_t buf = t & 1;
+      const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+      const int y0 = (rem / tiles_x) * S, x = (rem % tiles_x) * 128 + m;
+      if (!mbar_wait(&acc_full[buf], (t >> 1) & 1)) { atomicExch(P.error_flag, 15u); break; }
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)C::ACC_COLS;
+#pragma unroll 1
+      for (int s = 0; s < S; ++s) {
+        const int y = y0 + s;
+        const bool in_img = (y < P.H) && (x < P.W);
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
+          uint32_t r[32];
+          SDB_TMEM_LD32(r, tbase + (uint32_t)(s * C::STRIP_COLS + c0));
+          if (C::MERGE) {
+            uint32_t r2[32];
+            SDB_TMEM_LD32(r2, tbase + (uint32_t)(s * C::STRIP_COLS + N + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+          if (s == S - 1 && c0 + 32 >= N) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
           if (in_img) {
             __align__(16) __half hi[32];
             __align__(16) __half lo[32];
@@ -895,13 +1136,13 @@ static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
   sdb::profile_begin("conv_tc", st, &sp);
   k_conv_tc<N, KC><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P);
   sdb::profile_end("conv_tc", st, &sp);
-  sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);     // algorithmic FLOPs
+  sdb::profile_add_units("conv_tc", 2.0 * P.n_taps * P.c_total * (P.heads_R > 0 ? P.heads_R + 1 : N) * (double)P.H * P.W * n_img);     // algorithmic FLOPs
   sdb::g_launch_count++;
   SDB_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int g_tc_variant = 3;      // 1 = k_conv_tc (one tile per CTA), 3 = k_conv_tc3 (persistent, merged N) where applicable
+static int g_tc_variant = 0;      // 0 = auto (k_conv_tc4 for Cin <= 64, else k_conv_tc3, k_conv_tc for Cout = 256); 1 / 3 / 4 force a kernel where applicable
 static int g_num_sms = 0;
 
 template <int N, int KC>
@@ -917,6 +1158,26 @@ static int launch_tc3(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUte
   sdb::ProfSpan sp;
   sdb::profile_begin("conv_tc", st, &sp);
   k_conv_tc3<N, KC><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles);
+  sdb::profile_end("conv_tc", st, &sp);
+  sdb::profile_add_units("conv_tc", 2.0 * P.n_taps * P.c_total * (P.heads_R > 0 ? P.heads_R + 1 : N) * (double)P.H * P.W * n_img);
+  sdb::g_launch_count++;
+  SDB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int N>
+static int launch_tc4(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+  using C = TcCfg4<N>;
+  static bool attr = false;
+  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc4<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
+  if (!g_num_sms) { int dev = 0; SDB_CUDA(cudaGetDevice(&dev)); SDB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const int tiles_x = cdiv(P.W, 128), tiles_y = cdiv(P.H, C::S);
+  const int n_tiles = tiles_x * tiles_y * n_img;
+  const int grid = std::min(n_tiles, g_num_sms);
+  sdb::ProfSpan sp;
+  sdb::profile_begin("conv_tc", st, &sp);
+  k_conv_tc4<N><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles);
   sdb::profile_end("conv_tc", st, &sp);
   sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);
   sdb::g_launch_count++;
@@ -958,16 +1219,28 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   if (cout != 32 && cout != 64 && cout != 128 && cout != 256) { sdb::set_error("conv3x3_tc: cout must be 32/64/128/256"); return 1; }
   if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
   CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
+  ConvParams P;
+  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
+  if ((g_tc_variant == 4 || (g_tc_variant == 0 && cin <= 64 && w >= 96)) && cout <= 128) {
+    // halo-reuse persistent kernel: 32-channel blocks, (S+2) x 130 pixel boxes
+    constexpr int ROWS = TcCfg4<32>::S + 2;
+    if (make_act_map2(&a1h, (const __half*)src1_hi, n, h, w, c_src1, ROWS) || make_act_map2(&a1l, (const __half*)src1_lo, n, h, w, c_src1, ROWS)) return 1;
+    if (c_src0 > 0) {
+      if (make_act_map2(&a0h, (const __half*)src0_hi, n, h, w, c_src0, ROWS) || make_act_map2(&a0l, (const __half*)src0_lo, n, h, w, c_src0, ROWS)) return 1;
+    } else { a0h = a1h; a0l = a1l; }
+    if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
+    if (cout == 32) return launch_tc4<32>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
+    if (cout == 64) return launch_tc4<64>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
+    return launch_tc4<128>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
+  }
   if (make_act_map(&a1h, (const __half*)src1_hi, n, h, w, c_src1, kc) || make_act_map(&a1l, (const __half*)src1_lo, n, h, w, c_src1, kc)) return 1;
   if (c_src0 > 0) {
     if (make_act_map(&a0h, (const __half*)src0_hi, n, h, w, c_src0, kc) || make_act_map(&a0l, (const __half*)src0_lo, n, h, w, c_src0, kc)) return 1;
   } else { a0h = a1h; a0l = a1l; }
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, kc) || make_w_map(&wl, (const __half*)w_lo, cin, cout, kc)) return 1;
-  ConvParams P;
-  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
 #define SDB_TC3(NN, KK) return launch_tc3<NN, KK>(a0h, a0l, a1h, a1l, wh, wl, P, n, st)
-  if (g_tc_variant == 3 && cout <= 128) {
+  if ((g_tc_variant == 3 || g_tc_variant == 0 || g_tc_variant == 4) && cout <= 128) {
     if (kc == 64) { if (cout == 32) SDB_TC3(32, 64); if (cout == 64) SDB_TC3(64, 64); SDB_TC3(128, 64); }
     else { if (cout == 32) SDB_TC3(32, 32); if (cout == 64) SDB_TC3(64, 32); SDB_TC3(128, 32); }
   }
@@ -995,6 +1268,11 @@ extern "C" int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = 0; P.c_total = cfeat; P.relu = 0; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
+  if (g_tc_variant != 1) {
+    if (np == 48) return launch_tc3<48, 64>(ah, al, ah, al, wh, wl, P, n, st);
+    if (np == 80) return launch_tc3<80, 64>(ah, al, ah, al, wh, wl, P, n, st);
+    if (np == 112) return launch_tc3<112, 64>(ah, al, ah, al, wh, wl, P, n, st);
+  }
   if (np == 48) return launch_tc<48, 64>(ah, al, ah, al, wh, wl, P, n, st);
   if (np == 80) return launch_tc<80, 64>(ah, al, ah, al, wh, wl, P, n, st);
   if (np == 112) return launch_tc<112, 64>(ah, al, ah, al, wh, wl, P, n, st);
@@ -1031,7 +1309,7 @@ extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_s
 
 // A/B switch for tests and profiling: 1 = one-tile-per-CTA kernel, 3 = persistent kernel (default)
 extern "C" int sdb_tc_set_variant(int variant) {
-  if (variant != 1 && variant != 3) { sdb::set_error("tc_set_variant: 1 or 3"); return 1; }
+  if (variant != 0 && variant != 1 && variant != 3 && variant != 4) { sdb::set_error("tc_set_variant: 0 (auto), 1, 3 or 4"); return 1; }
   g_tc_variant = variant;
   return 0;
 }

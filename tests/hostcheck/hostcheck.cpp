@@ -94,10 +94,12 @@ void hc_fast_batch(const int32_t* a_xy, const int32_t* b_xy, int n_pairs, int n,
       int wq = 0, wp = 0;
       for (int i = 0; i < n; i++) { wq += sdfast::wind_Q_edge(eb[i], A[0], A[1]); wp += sdfast::wind_P_edge(ea[i], B[0], B[1]); }
       sdfast::Accum acc; acc.clear();
-      for (int j = 0; j < n; j++) {
-        const sdfast::Box bx = sdfast::edge_box(eb[j]);
-        for (int i = 0; i < n; i++) sdfast::edge_pair(ea[i], &fa[i], eb[j], bx, &fb[j], acc);
-      }
+      const bool small = maxc <= 8191.0;
+      for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+          if (small) sdfast::edge_pair<int32_t>(ea[i], &fa[i], eb[j], &fb[j], acc);
+          else sdfast::edge_pair<long long>(ea[i], &fa[i], eb[j], &fb[j], acc);
+        }
       out_I[p] = acc.I + wq * sa + wp * sb;
       out_bound[p] = sdfast::clipper_bound(acc, maxlen_a + maxlen_b, maxc, n);
       out_K[p] = acc.K;
