@@ -80,6 +80,15 @@ int _LIB_polygons_to_label_2d(
 int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys, int n_rays,
               float threshold, int use_bbox, int use_kdtree, int verbose,
               unsigned char* d_keep, sdb_stream_t stream);
+/* sdb_nms2d + the ordered list of survivors: d_kept_index[0..*h_n_kept) = indices with keep == 1, ascending
+ * (= descending score); d_keep may be NULL.  One 4-byte device->host read-back, stream synchronised on return. */
+int sdb_nms2d_survivors(const float* d_dist, const float* d_points, int n_polys, int n_rays,
+                        float threshold, int use_bbox, int use_kdtree, int verbose,
+                        unsigned char* d_keep, int* d_kept_index, int* h_n_kept, sdb_stream_t stream);
+/* Paint order of polygons_to_label (geom2d.py:191-197) for survivors listed by descending score (ties in the
+ * order np.argsort(prob, kind='stable')[::-1] leaves them): rank[i] = position of i in
+ * np.argsort(prob, kind='stable'), id_by_rank[rank[i]] = i + 1. */
+int sdb_paint_order_2d(const float* d_prob_desc, int n, int* d_rank, int* d_id_by_rank, sdb_stream_t stream);
 /* Pre-filter of the 2D pair test (csrc/polyfast.cuh): 0 = exact Clipper-equivalent sweep on every pair,
  * 1 (default) = closed-form overlap integral with a conservative bound first, exact sweep for the rest,
  * 2 = verify: both on every pair, disagreements are counted.  Results are identical in all modes.
@@ -168,6 +177,14 @@ int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const 
  * rows 1..n_rays = dist, zero padded to np in {48, 80, 112, 144}; outputs fp32 */
 int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n, int h, int w, const void* w_hi, const void* w_lo,
                  float w_scale, const float* d_bias, int np, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream);
+/* Last convolution of the backbone fused with the 1x1 heads (model2d.py:329-337: features conv3x3 + ReLU, then
+ * Conv2D(1,1,sigmoid) -> prob and Conv2D(n_rays,1,linear) -> dist): src as in sdb_conv3x3_tc, cout = 128,
+ * heads_w fp32 [128][36] (columns 0..n_rays-1 = dist kernels, column 32 = prob kernel, rest 0), heads_b fp32 [36];
+ * n_rays <= 32.  Outputs prob [n,h,w] and dist [n,h,w,n_rays] fp32; the feature map is not materialised. */
+int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                         int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias,
+                         int relu, const float* d_heads_w, const float* d_heads_b, int n_rays, float* d_prob, float* d_dist,
+                         sdb_stream_t stream);
 /* kernel variant of sdb_conv3x3_tc: 0 (default) = auto, 1 = one 8x16 tile per CTA, 3 = persistent CTAs with
  * double-buffered TMEM accumulators and merged hi/lo weight tile, 4 = 3 + halo reuse (one box load per
  * 32-channel block, taps as shifted descriptors).  Results are identical up to fp32 summation order. */

@@ -26,6 +26,10 @@ def _declare(lib):
     lib._LIB_non_maximum_suppression_2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P]
     lib._LIB_polygons_to_label_2d.argtypes = [P, P, c_int, c_int, c_int, c_int, P]
     lib.sdb_nms2d.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_nms2d_survivors.argtypes = [P, P, c_int, c_int, c_float, c_int, c_int, c_int, P, P, POINTER(c_int), P]
+    lib.sdb_nms2d_survivors.restype = c_int
+    lib.sdb_paint_order_2d.argtypes = [P, c_int, P, P, P]
+    lib.sdb_paint_order_2d.restype = c_int
     lib.sdb_nms2d_set_filter.argtypes = [c_int]
     lib.sdb_nms2d_set_filter.restype = c_int
     lib.sdb_nms2d_filter_stats.argtypes = [POINTER(ctypes.c_ulonglong), c_int]
@@ -43,6 +47,8 @@ def _declare(lib):
     lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
     lib.sdb_conv3x3_tc2.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, c_int, P, P, P]
     lib.sdb_heads_tc.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, P, P, P]
+    lib.sdb_conv3x3_heads_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, P, P, c_int, P, P, P]
+    lib.sdb_conv3x3_heads_tc.restype = c_int
     lib.sdb_tc_error_check.argtypes = [P]
     lib.sdb_tc_set_variant.argtypes = [c_int]
     lib.sdb_tc_set_variant.restype = c_int

@@ -185,9 +185,29 @@ __global__ void k_iota(int* __restrict__ out, int n) {
   if (i < n) out[i] = i;
 }
 
-__global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __restrict__ keep) {
+__global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __restrict__ keep, unsigned int* __restrict__ flag /*[n+1] or null*/) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keep[i] = (state[i] != ST_SUPPRESSED) ? 1 : 0;
+  if (i > n) return;
+  const unsigned int k = (i < n && state[i] != ST_SUPPRESSED) ? 1u : 0u;
+  if (i < n && keep) keep[i] = (unsigned char)k;
+  if (flag) flag[i] = k;
+}
+__global__ void k_scatter_kept(const unsigned int* __restrict__ flag, const unsigned int* __restrict__ pos, int n, int* __restrict__ kept_index) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) kept_index[pos[i]] = i;
+}
+// paint order of survivors listed by descending score with ties in list order reversed (= np.argsort(prob,
+// kind='stable')[::-1]): rank under np.argsort(prob_k, kind='stable') (geom2d.py:191), ids[rank] = index + 1
+__global__ void k_paint_order(const float* __restrict__ prob, int nk, int* __restrict__ rank, int* __restrict__ id_by_rank) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nk) return;
+  const float p = prob[i];
+  int s = i, e = i + 1;
+  while (s > 0 && prob[s - 1] == p) --s;
+  while (e < nk && prob[e] == p) ++e;
+  const int r = (nk - e) + (i - s);
+  rank[i] = r;
+  id_by_rank[r] = i + 1;
 }
 
 
@@ -200,8 +220,22 @@ using namespace sdnms;
 extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys, int n_rays,
                          float threshold, int use_bbox, int use_kdtree, int verbose,
                          unsigned char* d_keep, sdb_stream_t stream) {
+  return sdb_nms2d_survivors(d_dist, d_points, n_polys, n_rays, threshold, use_bbox, use_kdtree, verbose, d_keep, nullptr, nullptr, stream);
+}
+
+extern "C" int sdb_paint_order_2d(const float* d_prob_desc, int n, int* d_rank, int* d_id_by_rank, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  SDB_LAUNCH(k_paint_order, cdiv(n, 256), 256, 0, st, d_prob_desc, n, d_rank, d_id_by_rank);
+  return 0;
+}
+
+extern "C" int sdb_nms2d_survivors(const float* d_dist, const float* d_points, int n_polys, int n_rays,
+                                   float threshold, int use_bbox, int use_kdtree, int verbose,
+                                   unsigned char* d_keep, int* d_kept_index, int* h_n_kept, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int n = n_polys, R = n_rays;
+  if (h_n_kept) *h_n_kept = 0;
   if (n <= 0) return 0;
   if (R < 1 || R > 128) { sdb::set_error("nms2d: n_rays must be in [1,128]"); return 1; }
 
@@ -301,7 +335,24 @@ extern "C" int sdb_nms2d(const float* d_dist, const float* d_points, int n_polys
   if (R <= 32) rc = run_rounds_nv32(A, b_slow.as<int>(), b_counters.as<unsigned int>(), st, verbose, h_pin);
   else rc = run_rounds_nv128(A, b_slow.as<int>(), b_counters.as<unsigned int>(), st, verbose, h_pin);
   if (rc) return rc;
-  SDB_LAUNCH(k_finish, cdiv(n, 256), 256, 0, st, b_state.as<int>(), n, d_keep);
+  if (!d_kept_index) {
+    SDB_LAUNCH(k_finish, cdiv(n + 1, 256), 256, 0, st, b_state.as<int>(), n, d_keep, (unsigned int*)nullptr);
+    return 0;
+  }
+  // ordered list of survivors + their number on the host (one 4-byte read-back)
+  sdb::DevBuf b_flag, b_pos, b_ft;
+  const int nt = cdiv(n + 1, SCAN_TILE);
+  SDB_CUDA(b_flag.alloc((size_t)(n + 1) * sizeof(unsigned int), st));
+  SDB_CUDA(b_pos.alloc((size_t)(n + 1) * sizeof(unsigned int), st));
+  SDB_CUDA(b_ft.alloc((size_t)nt * sizeof(unsigned int), st));
+  SDB_LAUNCH(k_finish, cdiv(n + 1, 256), 256, 0, st, b_state.as<int>(), n, d_keep, b_flag.as<unsigned int>());
+  SDB_LAUNCH(k_scan_tiles, nt, SCAN_T, 0, st, b_flag.as<unsigned int>(), b_pos.as<unsigned int>(), n + 1, b_ft.as<unsigned int>());
+  SDB_LAUNCH(k_scan_sums, 1, 1024, 0, st, b_ft.as<unsigned int>(), nt);
+  SDB_LAUNCH(k_scan_add, cdiv(n + 1, 256), 256, 0, st, b_pos.as<unsigned int>(), n + 1, b_ft.as<unsigned int>());
+  SDB_LAUNCH(k_scatter_kept, cdiv(n, 256), 256, 0, st, b_flag.as<unsigned int>(), b_pos.as<unsigned int>(), n, d_kept_index);
+  SDB_CUDA(cudaMemcpyAsync(h_pin, b_pos.as<unsigned int>() + n, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  if (h_n_kept) *h_n_kept = (int)h_pin[0];
   return 0;
 }
 

@@ -62,7 +62,10 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
     int2 cur = cursor[c];          // (neighbour cell 0..8, offset inside that cell)
     bool blocked = false;
     for (int k = cur.x; k < 9 && !blocked; ++k) {
-      const int yy = ccy + k / 3 - 1, xx = ccx + k % 3 - 1;
+      // own cell first, then the edge neighbours, then the corners: a blocker is nearly always found among the
+      // first (= highest scored) items of the candidate's own cell
+      const int kk = (0x862075314 >> (4 * k)) & 15;       // k -> 4,1,3,5,7,0,2,6,8
+      const int yy = ccy + kk / 3 - 1, xx = ccx + kk % 3 - 1;
       if (yy < 0 || yy >= A.G.gy || xx < 0 || xx >= A.G.gx) { cur.x = k + 1; cur.y = 0; continue; }
       const int cell = yy * A.G.gx + xx;
       const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
@@ -191,21 +194,25 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
   }
 }
 
-// Exact sweep, one pair per thread.  The sweep is long, branchy, per-lane serial code: lanes of a warp that
-// run different pairs mostly serialise.  Pairs are therefore dealt round-robin over ALL resident warps
-// (pair p -> warp p % G, lane p / G): a round with few pairs runs one pair per warp at full single-thread
-// speed instead of 32 pairs in one warp.  n_list: &counters[1] (all pairs) or &counters[9] (pre-filtered).
+// Exact sweep: ONE PAIR PER WARP, executed by lane 0 with the sweep state (~8 KB of pools for 32-gons) in
+// SHARED memory.  The sweep is ~3e4 dependent, branchy instructions per pair: lanes running different pairs
+// serialise anyway (a 32-pairs-per-warp version was no faster in aggregate), and a single active lane in local
+// memory touches 4 bytes of every 128-byte line -- its 8 KB of state occupied ~70 KB of L1 and ran out of L2.
+// n_list: &counters[1] (all pairs) or &counters[9] (pairs the pre-filter left open).
+template <int NV> struct ClipCfg { static constexpr int WARPS = (NV <= 32) ? 4 : 1; };
+
 template <int NV>
-__global__ void __launch_bounds__(128) k_clip(NmsArrays A, const int2* __restrict__ pairs, const unsigned int* __restrict__ n_list,
+__global__ void __launch_bounds__(32 * ClipCfg<NV>::WARPS) k_clip(NmsArrays A, const int2* __restrict__ pairs, const unsigned int* __restrict__ n_list,
                                               const signed char* __restrict__ verdict,
                                               int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char clip_smem[];
   if (counters[5]) return;
   const unsigned int n_pairs = *n_list;
   const unsigned int G = (gridDim.x * blockDim.x) >> 5;                       // warps in the grid
   const unsigned int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp_g >= n_pairs) return;
-  sdclip::ClipSweep<NV, 1> S;
-  for (unsigned int t = lane * G + warp_g; t < n_pairs; t += 32 * G) {
+  if (warp_g >= n_pairs || lane != 0) return;
+  sdclip::ClipSweep<NV, 1>& S = *reinterpret_cast<sdclip::ClipSweep<NV, 1>*>(clip_smem + (size_t)(threadIdx.x >> 5) * sizeof(sdclip::ClipSweep<NV, 1>));
+  for (unsigned int t = warp_g; t < n_pairs; t += G) {
     const int2 pr = pairs[t];
     if (!verdict && A.state[pr.y] == ST_SUPPRESSED) continue;        // already suppressed by another pair (benign race)
     const int r = pair_suppresses<NV, 1>(A, pr.x, pr.y, S);
@@ -276,8 +283,15 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       sdb::profile_end("nms2d_fast", st, &sp);
     }
     sdb::profile_begin("nms2d_clip", st, &sp);
-    if (filter == 1) SDB_LAUNCH((k_clip<NV>), 148 * 7, 128, 0, st, A, b_xpairs.as<int2>(), d_counters + 9, (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
-    else SDB_LAUNCH((k_clip<NV>), 148 * 7, 128, 0, st, A, b_pairs.as<int2>(), d_counters + 1, filter == 2 ? b_verdict.as<signed char>() : (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
+    {
+      constexpr int CW = ClipCfg<NV>::WARPS;
+      const size_t csm = (size_t)CW * sizeof(sdclip::ClipSweep<NV, 1>);
+      static bool attr = false;
+      if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_clip<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm)); attr = true; }
+      const int cblocks = 148 * (NV <= 32 ? 6 : 4);
+      if (filter == 1) SDB_LAUNCH((k_clip<NV>), cblocks, 32 * CW, csm, st, A, b_xpairs.as<int2>(), d_counters + 9, (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
+      else SDB_LAUNCH((k_clip<NV>), cblocks, 32 * CW, csm, st, A, b_pairs.as<int2>(), d_counters + 1, filter == 2 ? b_verdict.as<signed char>() : (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
+    }
     sdb::profile_end("nms2d_clip", st, &sp);
     SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
     return 0;

@@ -49,6 +49,9 @@ struct ConvParams {
   int n_taps;            // 9 (3x3) or 1 (1x1 heads)
   int heads_R;           // > 0: heads epilogue -> prob = sigmoid(ch 0), dist = ch 1..R, fp32 outputs
   float* prob; float* dist;
+  // fused features -> heads (k_conv_tc4<128, true>): fp32 head weights [128][36] (columns 0..R-1 = dist, 32 = prob,
+  // zero padded) and biases [36]
+  const float* fuse_w; const float* fuse_b;
 };
 
 // ---------------------------------------------------------------------------------- PTX helpers
@@ -713,8 +716,11 @@ struct TcCfg4 {
   static constexpr int A_STAGE = 2 * A_PLANE;
   static constexpr int A_STAGES = 2;
   static constexpr int B_STAGE = 2 * N * ROWB;
-  static constexpr int B_STAGES = (N >= 128) ? 4 : 6;
-  static constexpr int SMEM = A_STAGES * A_STAGE + B_STAGES * B_STAGE + 1024 + 256;
+  // weight ring depth when the layer's weights do not stay resident (see WRES): the slot of a tap is recycled only
+  // after its MMAs retired (tcgen05.commit) plus a TMA round trip, ~2 us -- a shallow ring starves the tensor pipe
+  static constexpr int B_STAGES = (N >= 128) ? 4 : (N == 64 ? 10 : 12);
+  static constexpr int W_RESIDENT_MAX = 88 * 1024;         // 9 * n_cb * B_STAGE up to this size stays in shared memory
+  static constexpr int SMEM_FIXED = A_STAGES * A_STAGE + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int STRIP_COLS = MERGE ? 2 * N : N;
   static constexpr int ACC_COLS = S * STRIP_COLS;
   static constexpr int TMEM_COLS = 2 * ACC_COLS;           // 256 (N=32) / 512 (N=64, N=128)
@@ -722,36 +728,44 @@ struct TcCfg4 {
   static constexpr uint32_t IDESC_2N = (1u << 4) | ((uint32_t)((2 * N) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   static_assert(N == 32 || N == 64 || N == 128, "N in {32, 64, 128}");
   static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
-  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static_assert(SMEM_FIXED + B_STAGES * B_STAGE <= 227 * 1024, "shared memory");
 };
 
-template <int N>
-__global__ void __launch_bounds__(192, 1)
+// WRES: all 9 * n_cb weight tiles of the layer are loaded ONCE per (persistent) CTA and stay in shared memory.
+template <int N, bool FUSE, bool WRES>
+__global__ void __launch_bounds__(FUSE ? 320 : 192, 1)
 k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
            const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
            const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P,
-           int tiles_x, int tiles_y, int n_tiles) {
+           int tiles_x, int tiles_y, int n_tiles, int n_b_slots) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* smA = smem;
   unsigned char* smB = smem + C::A_STAGES * C::A_STAGE;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + C::B_STAGES * C::B_STAGE);
+  // n_b_slots = B_STAGES (ring) or 9 * n_cb (resident weights)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + (size_t)n_b_slots * C::B_STAGE);
   uint64_t* a_empty = a_full + C::A_STAGES;
-  uint64_t* b_full = a_empty + C::A_STAGES;
+  uint64_t* b_full = a_empty + C::A_STAGES;        // ring: [B_STAGES]; resident: [0] = "all weights landed"
   uint64_t* b_empty = b_full + C::B_STAGES;
   uint64_t* acc_full = b_empty + C::B_STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sHW = reinterpret_cast<float*>(smB + (size_t)n_b_slots * C::B_STAGE + 512);   // FUSE: [N][36] + [36] + [N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cb = P.c_total / C::KC;
 
+  if (FUSE) {
+    for (int e = threadIdx.x; e < N * 36; e += blockDim.x) sHW[e] = P.fuse_w[e];
+    for (int e = threadIdx.x; e < 36; e += blockDim.x) sHW[N * 36 + e] = P.fuse_b[e];
+    for (int e = threadIdx.x; e < N; e += blockDim.x) sHW[N * 36 + 36 + e] = P.bias[e];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], FUSE ? 8 : 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -770,6 +784,15 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
     if (lane == 0) {
       uint32_t ai = 0, bi = 0;
       bool ok = true;
+      if (WRES) {
+        mbar_expect_tx(&b_full[0], (uint32_t)(9 * n_cb) * C::B_STAGE);
+        for (int cb = 0; cb < n_cb; ++cb)
+          for (int tap = 0; tap < 9; ++tap) {
+            unsigned char* stb = smB + (size_t)(cb * 9 + tap) * C::B_STAGE;
+            tma_load_3d(stb, &tm_w_hi, &b_full[0], cb * C::KC, 0, tap);
+            tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[0], cb * C::KC, 0, tap);
+          }
+      }
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
         const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
         const int y0 = (rem / tiles_x) * S, x0 = (rem % tiles_x) * 128;
@@ -786,7 +809,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
             tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
             tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
           }
-          for (int tap = 0; tap < 9; ++tap, ++bi) {
+          if (!WRES) for (int tap = 0; tap < 9; ++tap, ++bi) {
             const uint32_t sb = bi % C::B_STAGES;
             if (bi >= (uint32_t)C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
             unsigned char* stb = smB + sb * C::B_STAGE;
@@ -802,6 +825,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
     if (lane == 0) {
       uint32_t ai = 0, bi = 0, t = 0;
       bool ok = true;
+      if (WRES && !mbar_wait(&b_full[0], 0)) { atomicExch(P.error_flag, 17u); ok = false; }
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
         const uint32_t buf = t & 1;
         if (t >= 2) {
@@ -814,10 +838,12 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           if (!mbar_wait(&a_full[sa], (ai / C::A_STAGES) & 1)) { atomicExch(P.error_flag, 13u); ok = false; break; }
           const uint32_t a_hi = smem_u32(smA + sa * C::A_STAGE), a_lo = a_hi + C::A_PLANE;
           for (int tap = 0; tap < 9; ++tap, ++bi) {
-            const uint32_t sb = bi % C::B_STAGES;
-            if (!mbar_wait(&b_full[sb], (bi / C::B_STAGES) & 1)) { atomicExch(P.error_flag, 14u); ok = false; break; }
+            const uint32_t sb = WRES ? (uint32_t)(cb * 9 + tap) : bi % C::B_STAGES;
+            if (!WRES) {
+              if (!mbar_wait(&b_full[sb], (bi / C::B_STAGES) & 1)) { atomicExch(P.error_flag, 14u); ok = false; break; }
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b_hi = smem_u32(smB + sb * C::B_STAGE), b_lo = b_hi + N * C::ROWB;
+            const uint32_t b_hi = smem_u32(smB + (size_t)sb * C::B_STAGE), b_lo = b_hi + N * C::ROWB;
             const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
@@ -840,7 +866,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
                 }
               }
             }
-            tcgen05_commit(&b_empty[sb]);
+            if (!WRES) tcgen05_commit(&b_empty[sb]);
           }
           tcgen05_commit(&a_empty[sa]);
         }
@@ -859,6 +885,59 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       if (!mbar_wait(&acc_full[buf], (t >> 1) & 1)) { atomicExch(P.error_flag, 15u); break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)C::ACC_COLS;
+      if (FUSE) {
+        // features (bias + ReLU, fp32 straight from the accumulators) -> 1x1 heads on the CUDA cores -> prob / dist.
+        // The 128-channel feature map never goes to HBM (it was 512 MB written + 512 MB read per 1024^2 image).
+        const float* sHB = sHW + N * 36;
+        const float* sFB = sHB + 36;
+        // eight epilogue warps: warps 2..5 take strip 0, warps 6..9 strip 1 (two warps per scheduler keep the
+        // FP32 pipe busy: 128 x 33 FMAs per pixel)
+        {
+          const int s = (warp - 2) >> 2;
+          const int y = y0 + s;
+          const bool in_img = (y < P.H) && (x < P.W);
+          float out[33];
+#pragma unroll
+          for (int o = 0; o < 33; ++o) out[o] = sHB[o];
+#pragma unroll 1
+          for (int c0 = 0; c0 < N; c0 += 32) {
+            uint32_t r[32];
+            SDB_TMEM_LD32(r, tbase + (uint32_t)(s * C::STRIP_COLS + c0));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (c0 + 32 >= N) {
+              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float f = __uint_as_float(r[j]) * P.acc_scale + sFB[c0 + j];
+              if (P.relu) f = fmaxf(f, 0.f);
+              const float4* w4 = reinterpret_cast<const float4*>(sHW + (c0 + j) * 36);
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) {
+                const float4 w = w4[qq];
+                out[4 * qq] = fmaf(f, w.x, out[4 * qq]); out[4 * qq + 1] = fmaf(f, w.y, out[4 * qq + 1]);
+                out[4 * qq + 2] = fmaf(f, w.z, out[4 * qq + 2]); out[4 * qq + 3] = fmaf(f, w.w, out[4 * qq + 3]);
+              }
+              out[32] = fmaf(f, sHW[(c0 + j) * 36 + 32], out[32]);
+            }
+          }
+          if (in_img) {
+            const size_t pix = ((size_t)img * P.H + y) * P.W + x;
+            P.prob[pix] = 1.f / (1.f + expf(-out[32]));
+            if (P.heads_R == 32) {
+              float4* d4 = reinterpret_cast<float4*>(P.dist + pix * 32);
+#pragma unroll
+              for (int qq = 0; qq < 8; ++qq) d4[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
+            } else {
+#pragma unroll
+              for (int o = 0; o < 32; ++o) if (o < P.heads_R) P.dist[pix * P.heads_R + o] = out[o];
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int s = 0; s < S; ++s) {
         const int y = y0 + s;
@@ -1144,6 +1223,7 @@ static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
 
 static int g_tc_variant = 0;      // 0 = auto (k_conv_tc4 for Cin <= 64, else k_conv_tc3, k_conv_tc for Cout = 256); 1 / 3 / 4 force a kernel where applicable
 static int g_num_sms = 0;
+static int g_tc_no_resident = 0;   // tests: force the weight ring in k_conv_tc4
 
 template <int N, int KC>
 static int launch_tc3(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
@@ -1165,24 +1245,37 @@ static int launch_tc3(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUte
   return 0;
 }
 
-template <int N>
-static int launch_tc4(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
-                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+template <int N, bool FUSE, bool WRES>
+static int launch_tc4_impl(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                           const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
   using C = TcCfg4<N>;
-  static bool attr = false;
-  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc4<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
+  const int n_cb = P.c_total / C::KC;
+  const int n_b_slots = WRES ? 9 * n_cb : C::B_STAGES;
+  const int smem = C::SMEM_FIXED + n_b_slots * C::B_STAGE + (FUSE ? (N * 36 + 36 + N) * 4 : 0);
+  if (smem > 227 * 1024) { sdb::set_error("conv_tc4: shared memory budget exceeded"); return 1; }
+  static int attr = 0;
+  if (attr < smem) { SDB_CUDA(cudaFuncSetAttribute((k_conv_tc4<N, FUSE, WRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
   if (!g_num_sms) { int dev = 0; SDB_CUDA(cudaGetDevice(&dev)); SDB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
   const int tiles_x = cdiv(P.W, 128), tiles_y = cdiv(P.H, C::S);
   const int n_tiles = tiles_x * tiles_y * n_img;
   const int grid = std::min(n_tiles, g_num_sms);
   sdb::ProfSpan sp;
   sdb::profile_begin("conv_tc", st, &sp);
-  k_conv_tc4<N><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles);
+  k_conv_tc4<N, FUSE, WRES><<<grid, FUSE ? 320 : 192, smem, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles, n_b_slots);
   sdb::profile_end("conv_tc", st, &sp);
-  sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);
+  sdb::profile_add_units("conv_tc", (2.0 * 9.0 * P.c_total * N + (FUSE ? 2.0 * N * (P.heads_R + 1) : 0.0)) * (double)P.H * P.W * n_img);
   sdb::g_launch_count++;
   SDB_CUDA(cudaGetLastError());
   return 0;
+}
+template <int N, bool FUSE = false>
+static int launch_tc4(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
+                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+  using C = TcCfg4<N>;
+  const int n_cb = P.c_total / C::KC;
+  if (!FUSE && 9 * n_cb * C::B_STAGE <= C::W_RESIDENT_MAX && !g_tc_no_resident)
+    return launch_tc4_impl<N, FUSE, true>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st);
+  return launch_tc4_impl<N, FUSE, false>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st);
 }
 
 template <int N, int S>
@@ -1221,7 +1314,7 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr;
   if ((g_tc_variant == 4 || (g_tc_variant == 0 && cin <= 64 && w >= 96)) && cout <= 128) {
     // halo-reuse persistent kernel: 32-channel blocks, (S+2) x 130 pixel boxes
     constexpr int ROWS = TcCfg4<32>::S + 2;
@@ -1267,7 +1360,7 @@ extern "C" int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n
   if (make_w_map(&wh, (const __half*)w_hi, cfeat, np, 64, 1) || make_w_map(&wl, (const __half*)w_lo, cfeat, np, 64, 1)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = 0; P.c_total = cfeat; P.relu = 0; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
+  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist; P.fuse_w = nullptr; P.fuse_b = nullptr;
   if (g_tc_variant != 1) {
     if (np == 48) return launch_tc3<48, 64>(ah, al, ah, al, wh, wl, P, n, st);
     if (np == 80) return launch_tc3<80, 64>(ah, al, ah, al, wh, wl, P, n, st);
@@ -1279,6 +1372,32 @@ extern "C" int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n
   if (np == 144) return launch_tc<144, 64>(ah, al, ah, al, wh, wl, P, n, st);
   sdb::set_error("heads_tc: np must be one of 48, 80, 112, 144");
   return 1;
+}
+
+// features conv (3x3, Cin <= 64 -> 128, bias, ReLU) fused with the 1x1 heads: prob = sigmoid(f . w_p + b_p),
+// dist_k = f . w_k + b_k computed on the fp32 accumulators in the epilogue; the feature map is never stored.
+// heads_w: fp32 [128][36] (columns 0..R-1 dist, column 32 prob, rest zero), heads_b: fp32 [36]; n_rays <= 32.
+extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                                    int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias,
+                                    int relu, const float* d_heads_w, const float* d_heads_b, int n_rays, float* d_prob, float* d_dist,
+                                    sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cin = c_src0 + c_src1, cout = 128;
+  if (cin % 32 || c_src0 % 32 || c_src1 % 32) { sdb::set_error("conv3x3_heads_tc: channel counts must be multiples of 32"); return 1; }
+  if (n_rays < 1 || n_rays > 32) { sdb::set_error("conv3x3_heads_tc: n_rays must be in [1,32]"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
+  CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
+  constexpr int ROWS = TcCfg4<128>::S + 2;
+  if (make_act_map2(&a1h, (const __half*)src1_hi, n, h, w, c_src1, ROWS) || make_act_map2(&a1l, (const __half*)src1_lo, n, h, w, c_src1, ROWS)) return 1;
+  if (c_src0 > 0) {
+    if (make_act_map2(&a0h, (const __half*)src0_hi, n, h, w, c_src0, ROWS) || make_act_map2(&a0l, (const __half*)src0_lo, n, h, w, c_src0, ROWS)) return 1;
+  } else { a0h = a1h; a0l = a1l; }
+  if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
+  ConvParams P;
+  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
+  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
+  P.fuse_w = d_heads_w; P.fuse_b = d_heads_b;
+  return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
 
 // halo-reuse variant (k_conv_tc2): same contract as sdb_conv3x3_tc; boff_mode selects how the UMMA
@@ -1300,7 +1419,7 @@ extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_s
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr;
   if (cout == 32) return launch_tc2<32, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 64) return launch_tc2<64, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 128) return launch_tc2<128, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);

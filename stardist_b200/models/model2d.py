@@ -80,12 +80,16 @@ class StarDist2D(StarDistBase):
         if overlap_label is not None: raise NotImplementedError("overlap_label not supported for 2D yet!")
         n, R = cand['n'], self.config.n_rays
         dev = cand['dist'].device
-        keep = torch.zeros(n, dtype=torch.uint8, device=dev)
+        import ctypes
+        nk_c = ctypes.c_int(0)
+        sel = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         if n > 0:
-            L.check(lib.sdb_nms2d(L.ptr(cand['dist']), L.ptr(cand['points_f32']), n, R, float(np.float32(nms_thresh)),
-                                 int(use_bbox), int(use_kdtree), int(verbose), L.ptr(keep), L.stream_ptr()))
+            L.check(lib.sdb_nms2d_survivors(L.ptr(cand['dist']), L.ptr(cand['points_f32']), n, R, float(np.float32(nms_thresh)),
+                                           int(use_bbox), int(use_kdtree), int(verbose), L.ptr(None), L.ptr(sel), ctypes.byref(nk_c),
+                                           L.stream_ptr()))
         self._mark('nms_end')
-        sel = torch.nonzero(keep, as_tuple=False).flatten()
+        nk = int(nk_c.value)
+        sel = sel[:nk]
         disti_d = cand['dist'].index_select(0, sel)
         probi_d = cand['prob'].index_select(0, sel)
         pts_d = cand['points_f32'].index_select(0, sel).to(torch.float64)   # integer pixel centres, exact
@@ -96,26 +100,24 @@ class StarDist2D(StarDistBase):
             pts_d = pts_d * torch.tensor(rescale, dtype=torch.float64, device=dev).reshape(1, 2)
         else:
             rescale = (1, 1)
-        nk = int(sel.numel())
-        probi = probi_d.cpu().numpy()
         coord_d = dist_to_coord_device(disti_d, pts_d, rescale)
         labels = None
         if return_labels:
-            # paint in ascending stable prob order, id = index + 1 (geom2d.py:191-197)
-            ind, rank = paint_order(probi)
-            ids = (ind + 1).astype(np.int32)
-            rank_d = torch.from_numpy(rank.astype(np.int32)).to(dev)
-            ids_d = torch.from_numpy(ids).to(dev)
+            # paint in ascending stable prob order, id = index + 1 (geom2d.py:191-197); survivors are listed by
+            # descending score, so the order is computed on the device (sdb_paint_order_2d)
+            rank_d = torch.empty(max(nk, 1), dtype=torch.int32, device=dev)
+            ids_d = torch.empty(max(nk, 1), dtype=torch.int32, device=dev)
+            L.check(lib.sdb_paint_order_2d(L.ptr(probi_d), nk, L.ptr(rank_d), L.ptr(ids_d), L.stream_ptr()))
             lab_d = torch.empty(tuple(int(s) for s in img_shape), dtype=torch.int32, device=dev)
             L.check(lib.sdb_polygons_to_label_2d(L.ptr(coord_d), L.ptr(rank_d), L.ptr(ids_d), nk, R,
                                                 int(img_shape[0]), int(img_shape[1]), L.ptr(lab_d), L.stream_ptr()))
             self._mark('label_end')
-            labels = lab_d.cpu().numpy()
-        coord = coord_d.cpu().numpy()
-        points = pts_d.cpu().numpy()
+        else:
+            lab_d = None
+        (labels, probi, coord, points), nbytes = self._to_host([lab_d, probi_d, coord_d, pts_d])
         if scale is None:
             points = points.astype(np.int64)
-        self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + coord.nbytes + points.nbytes + probi.nbytes + (0 if labels is None else labels.nbytes)
+        self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + nbytes
         res_dict = dict(coord=coord, points=points, prob=probi)
         return labels, res_dict
 

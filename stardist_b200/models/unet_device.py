@@ -5,6 +5,7 @@ Reference: `keras_model.predict(x[np.newaxis])` at stardist/models/base.py:408-4
 built in model2d.py:310-349.  The decoder's UpSampling+Concatenate is never materialised: the
 conv kernel reads [upsample(x_lo), skip] through its loader address math.
 """
+import os
 import numpy as np
 import torch
 from .. import _lib as L
@@ -154,6 +155,16 @@ class UNetDevice2DTC:
             self.heads_b[1:R + 1] = self.w['dist']['b']
         else:
             self.heads_w = None
+        # fused features+heads (sdb_conv3x3_heads_tc): fp32 head weights [cf][36], columns 0..R-1 dist, 32 prob
+        self.fuse_heads = (R <= 32 and cf == 128 and os.environ.get("STARDIST_B200_FUSE_HEADS", "1") != "0")
+        if self.fuse_heads:
+            Wh = torch.zeros((cf, 36), dtype=torch.float32, device=self.device)
+            Wh[:, :R] = kd.reshape(cf, R)
+            Wh[:, 32] = kp.reshape(cf)
+            bh = torch.zeros(36, dtype=torch.float32, device=self.device)
+            bh[:R] = self.w['dist']['b']
+            bh[32] = self.w['prob']['b'][0]
+            self.fuse_w, self.fuse_b = Wh.contiguous(), bh
 
     @staticmethod
     def supported(config):
@@ -194,8 +205,17 @@ class UNetDevice2DTC:
                     _, n_, hh, ww, c1 = cur.shape
                     c0 = 0 if lo is None else lo.shape[-1]
                     oh, ow = (2 * hh, 2 * ww) if up2x else (hh, ww)
-                    out = torch.empty((2, n_, oh, ow, cout), dtype=torch.float16, device=x.device)
                     ws = ent['split']
+                    if self.fuse_heads and l['name'] == 'features' and c1 + c0 <= 64 and cout == 128:
+                        R = self.config.n_rays
+                        prob = torch.empty((n_, hh, ww), dtype=torch.float32, device=x.device)
+                        dist = torch.empty((n_, hh, ww, R), dtype=torch.float32, device=x.device)
+                        L.check(lib.sdb_conv3x3_heads_tc(L.ptr(lo[0]) if lo is not None else L.ptr(None), L.ptr(lo[1]) if lo is not None else L.ptr(None), c0,
+                                                         L.ptr(cur[0]), L.ptr(cur[1]), c1, n_, hh, ww, L.ptr(ws[0]), L.ptr(ws[1]), ent['scale'], L.ptr(ent['b']),
+                                                         relu, L.ptr(self.fuse_w), L.ptr(self.fuse_b), R, L.ptr(prob), L.ptr(dist), st))
+                        L.check(lib.sdb_tc_error_check(st))
+                        return prob, dist
+                    out = torch.empty((2, n_, oh, ow, cout), dtype=torch.float16, device=x.device)
                     L.check(lib.sdb_conv3x3_tc(L.ptr(lo[0]) if lo is not None else L.ptr(None), L.ptr(lo[1]) if lo is not None else L.ptr(None), c0,
                                                L.ptr(cur[0]), L.ptr(cur[1]), c1, n_, hh, ww, L.ptr(ws[0]), L.ptr(ws[1]), ent['scale'], L.ptr(ent['b']),
                                                cout, relu, up2x, L.ptr(out[0]), L.ptr(out[1]), st))
