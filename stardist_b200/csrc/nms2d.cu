@@ -85,6 +85,104 @@ __global__ void k_precompute(const float* __restrict__ dist, const float* __rest
   atomicMin((int*)&stats[3], (int)floorf(cy)); atomicMax((int*)&stats[4], (int)floorf(cy));
 }
 
+// Same results as k_precompute, one WARP per polygon (lane = ray; coalesced vertex / suffix rows).  The float
+// shoelace sum keeps the reference's left-to-right order: the 32 cross products of a chunk are broadcast in turn.
+__global__ void __launch_bounds__(256) k_precompute_w(const float* __restrict__ dist, const float* __restrict__ points,
+                             const float* __restrict__ sn, const float* __restrict__ cs,
+                             int n, int R, int2* __restrict__ verts, int4* __restrict__ bbox,
+                             float* __restrict__ radius, float* __restrict__ area,
+                             double* __restrict__ suf, double* __restrict__ sarea, float* __restrict__ maxlen,
+                             unsigned int* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const float py = points[2 * i], px = points[2 * i + 1];
+  int2* v = verts + (size_t)i * R;
+  const int2 v0 = [&]() { const float d = dist[(size_t)i * R]; int2 q; q.x = (int)(long long)(px + d * cs[0]); q.y = (int)(long long)(py + d * sn[0]); return q; }();
+  float bx1 = 0, bx2 = 0, by1 = 0, by2 = 0, rmax = 0, a = 0, ml = 0;
+  bool first = true;
+  double s_total = 0;          // filled below (second sweep, right to left)
+  const int n_chunks = (R + 31) / 32;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int k = c * 32 + lane;
+    const bool act = k < R;
+    float x = 0, y = 0, d = 0;
+    int2 q = make_int2(0, 0);
+    if (act) {
+      d = dist[(size_t)i * R + k];
+      y = py + d * sn[k];
+      x = px + d * cs[k];
+      q.x = (int)(long long)x; q.y = (int)(long long)y;   // IntPoint(x,y): trunc toward zero
+      v[k] = q;
+    }
+    // float bbox / max radius: min and max are exact, any order
+    float lx1 = act ? x : INFINITY, lx2 = act ? x : -INFINITY, ly1 = act ? y : INFINITY, ly2 = act ? y : -INFINITY, lr = act ? d : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      lx1 = fminf(lx1, __shfl_xor_sync(0xffffffffu, lx1, o)); lx2 = fmaxf(lx2, __shfl_xor_sync(0xffffffffu, lx2, o));
+      ly1 = fminf(ly1, __shfl_xor_sync(0xffffffffu, ly1, o)); ly2 = fmaxf(ly2, __shfl_xor_sync(0xffffffffu, ly2, o));
+      lr = fmaxf(lr, __shfl_xor_sync(0xffffffffu, lr, o));
+    }
+    if (first) { bx1 = lx1; bx2 = lx2; by1 = ly1; by2 = ly2; first = false; }
+    else { bx1 = fminf(bx1, lx1); bx2 = fmaxf(bx2, lx2); by1 = fminf(by1, ly1); by2 = fmaxf(by2, ly2); }
+    rmax = fmaxf(rmax, lr);
+    // next vertex (wraps to vertex 0 at the end)
+    int2 qn;
+    qn.x = __shfl_down_sync(0xffffffffu, q.x, 1); qn.y = __shfl_down_sync(0xffffffffu, q.y, 1);
+    if (lane == 31 || k + 1 >= R) {
+      if (k + 1 >= R) qn = v0;
+      else {   // first vertex of the next chunk
+        const float dn = dist[(size_t)i * R + k + 1];
+        qn.x = (int)(long long)(px + dn * cs[k + 1]); qn.y = (int)(long long)(py + dn * sn[k + 1]);
+      }
+    }
+    const long long cr = act ? ((long long)q.x * (long long)qn.y - (long long)q.y * (long long)qn.x) : 0;
+    const float crf = (float)cr;
+    const int lim = min(32, R - c * 32);
+    for (int kk = 0; kk < lim; ++kk) a = a + __shfl_sync(0xffffffffu, crf, kk);      // area_from_path order (:128-138)
+    if (suf) {
+      const float ex = (float)(qn.x - q.x), ey = (float)(qn.y - q.y);
+      float l = act ? sqrtf(ex * ex + ey * ey) : 0.f;
+      for (int o = 16; o > 0; o >>= 1) l = fmaxf(l, __shfl_xor_sync(0xffffffffu, l, o));
+      ml = fmaxf(ml, l);
+    }
+  }
+  if (suf) {
+    // suffix sums of F_k = 0.5 (y_{k+1} - y_k)(x_k + x_{k+1}), right to left over the chunks
+    __syncwarp();              // the vertex row written above is read across lanes
+    double carry = 0;
+    for (int c = n_chunks - 1; c >= 0; --c) {
+      const int k = c * 32 + lane;
+      const bool act = k < R;
+      double F = 0;
+      if (act) {
+        const int2 p = v[k], q = (k + 1 == R) ? v0 : v[k + 1];      // own row, just written by this warp
+        F = 0.5 * (double)((long long)q.y - p.y) * (double)((long long)p.x + q.x);
+      }
+      // inclusive suffix scan inside the chunk
+      double inc = F;
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_down_sync(0xffffffffu, inc, o);
+        if (lane + o < 32) inc += t;
+      }
+      if (act) suf[(size_t)i * R + k] = carry + (inc - F);           // Σ over edges after k
+      carry += __shfl_sync(0xffffffffu, inc, 0);
+    }
+    s_total = carry;
+  }
+  if (lane == 0) {
+    a = (float)(0.5 * (double)fabsf(a));
+    area[i] = a;
+    radius[i] = rmax;
+    if (suf) { sarea[i] = s_total; maxlen[i] = ml * 1.000001f; }
+    int4 b; b.x = (int)bx1; b.y = (int)bx2; b.z = (int)by1; b.w = (int)by2;
+    bbox[i] = b;
+    atomicMax(&stats[0], __float_as_uint(rmax));
+    float cx = fminf(fmaxf(px, -1.0e9f), 1.0e9f), cy = fminf(fmaxf(py, -1.0e9f), 1.0e9f);
+    atomicMin((int*)&stats[1], (int)floorf(cx)); atomicMax((int*)&stats[2], (int)floorf(cx));
+    atomicMin((int*)&stats[3], (int)floorf(cy)); atomicMax((int*)&stats[4], (int)floorf(cy));
+  }
+}
+
 __global__ void k_cell_count(const float* __restrict__ points, int n, GridDesc G, int* __restrict__ cell_of_pt,
                              unsigned int* __restrict__ counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -262,7 +360,7 @@ extern "C" int sdb_nms2d_survivors(const float* d_dist, const float* d_points, i
   SDB_CUDA(cudaMemcpyAsync(b_tab.p, tab.data(), 2 * R * sizeof(float), cudaMemcpyHostToDevice, st));
   const int init_stats[8] = {0, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0, 0, 0};
   SDB_CUDA(cudaMemcpyAsync(b_stats.p, init_stats, sizeof(init_stats), cudaMemcpyHostToDevice, st));
-  SDB_LAUNCH(k_precompute, cdiv(n, 128), 128, 0, st, d_dist, d_points, b_tab.as<float>(), b_tab.as<float>() + R, n, R,
+  SDB_LAUNCH(k_precompute_w, cdiv((long long)n * 32, 256), 256, 0, st, d_dist, d_points, b_tab.as<float>(), b_tab.as<float>() + R, n, R,
              b_verts.as<int2>(), b_bbox.as<int4>(), b_radius.as<float>(), b_area.as<float>(),
              filter ? b_suf.as<double>() : (double*)nullptr, b_sarea.as<double>(), b_maxlen.as<float>(), b_stats.as<unsigned int>());
   int h_stats[8];

@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
     const int2 p0 = va[0], q0 = vb[0];
     sdfast::Accum acc; acc.clear();
     int wq = 0, wp = 0;
+    bool overflow = false;
     for (int j = lane; j < R; j += 32) {
       const int j1 = (j + 1 == R) ? 0 : j + 1;
       const int2 b0 = vb[j], b1 = vb[j1], a0 = va[j], a1 = va[j1];
@@ -167,14 +168,45 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
       sdfast::Edge e2; e2.x0 = a0.x; e2.y0 = a0.y; e2.x1 = a1.x; e2.y1 = a1.y;
       wq += sdfast::wind_Q_edge(f, p0.x, p0.y);
       wp += sdfast::wind_P_edge(e2, q0.x, q0.y);
+      // pass 1, branch free: which edges of P does f properly cross?  (at most two are remembered; a third sends
+      // the pair to the exact sweep.)  A crossing costs ~150 instructions; taken inside this loop it ran ~14 times
+      // per pair with one or two active lanes.
+      const T fx = (T)f.x1 - (T)f.x0, fy = (T)f.y1 - (T)f.y0;
+      const int tieQ = sdfast::tie_edge(fx, fy);
+      int cnt = 0, ci0 = -1, ci1 = -1;
       int2 prev = p0;
+      T o3 = fx * ((T)prev.y - (T)f.y0) - fy * ((T)prev.x - (T)f.x0);
       for (int i = 0; i < R; ++i) {
         const int2 cur = va[(i + 1 == R) ? 0 : i + 1];      // warp-uniform
-        sdfast::Edge e; e.x0 = prev.x; e.y0 = prev.y; e.x1 = cur.x; e.y1 = cur.y;
-        sdfast::edge_pair<T>(e, sa + i, f, sb + j, acc);
+        const T ex = (T)cur.x - (T)prev.x, ey = (T)cur.y - (T)prev.y;
+        const T o1 = ex * ((T)f.y0 - (T)prev.y) - ey * ((T)f.x0 - (T)prev.x);
+        const T o2 = ex * ((T)f.y1 - (T)prev.y) - ey * ((T)f.x1 - (T)prev.x);
+        const T o4 = fx * ((T)cur.y - (T)f.y0) - fy * ((T)cur.x - (T)f.x0);
+        const bool cross = sdfast::crossing_test(ex, ey, fx, fy, o1, o2, o3, o4, sdfast::tie_point(ex, ey), tieQ);
+        ci1 = (cross && cnt == 1) ? i : ci1;
+        ci0 = (cross && cnt == 0) ? i : ci0;
+        cnt += cross ? 1 : 0;
+        o3 = o4;                                            // orient(q0,q1,p1) of this edge = orient(q0,q1,p0) of the next
         prev = cur;
       }
+      overflow |= (cnt > 2);
+      // pass 2, lock step: every lane handles its first recorded crossing, then its second
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        const int i = c ? ci1 : ci0;
+        if (i >= 0) {
+          const int2 e0 = va[i], e1 = va[(i + 1 == R) ? 0 : i + 1];
+          sdfast::Edge e; e.x0 = e0.x; e.y0 = e0.y; e.x1 = e1.x; e.y1 = e1.y;
+          const T ex = (T)e.x1 - (T)e.x0, ey = (T)e.y1 - (T)e.y0;
+          const T o1 = ex * ((T)f.y0 - (T)e.y0) - ey * ((T)f.x0 - (T)e.x0);
+          const T o2 = ex * ((T)f.y1 - (T)e.y0) - ey * ((T)f.x1 - (T)e.x0);
+          const T q3 = fx * ((T)e.y0 - (T)f.y0) - fy * ((T)e.x0 - (T)f.x0);
+          const T q4 = fx * ((T)e.y1 - (T)f.y0) - fy * ((T)e.x1 - (T)f.x0);
+          sdfast::crossing_contrib(e, f, ex, ey, fx, fy, o1, o2, q3, q4, tieQ, sa[i], sb[j], acc);
+        }
+      }
     }
+    overflow = __any_sync(0xffffffffu, overflow);
     for (int o = 16; o > 0; o >>= 1) {
       acc.I += __shfl_xor_sync(0xffffffffu, acc.I, o);
       acc.len += __shfl_xor_sync(0xffffffffu, acc.len, o);
@@ -186,7 +218,7 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
       const double I = acc.I + (double)wq * A.sarea[h] + (double)wp * A.sarea[c];
       const double bound = sdfast::clipper_bound(acc, (double)A.maxlen[h] + (double)A.maxlen[c], A.max_abs_coord, R);
       const double den = fmin((double)A.area[h] + 1.e-10, (double)A.area[c] + 1.e-10);
-      const int d = sdfast::decide(I, bound, den, A.threshold);
+      const int d = overflow ? -1 : sdfast::decide(I, bound, den, A.threshold);
       if (verify) verdict[w] = (signed char)d;
       else if (d == 1) A.state[c] = ST_SUPPRESSED;
       else if (d < 0) xpairs[atomicAdd(&counters[9], 1u)] = pr;
