@@ -94,8 +94,10 @@ __global__ void __launch_bounds__(256) k_precompute_w(const float* __restrict__ 
                              double* __restrict__ suf, double* __restrict__ sarea, float* __restrict__ maxlen,
                              unsigned int* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= n) return;
+  // running statistics of this warp (one set of atomics per block at the end: one per polygon serialised on 5 words)
+  float st_r = 0.f; int st_x0 = INT32_MAX, st_x1 = INT32_MIN, st_y0 = INT32_MAX, st_y1 = INT32_MIN;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
   const float py = points[2 * i], px = points[2 * i + 1];
   int2* v = verts + (size_t)i * R;
   const int2 v0 = [&]() { const float d = dist[(size_t)i * R]; int2 q; q.x = (int)(long long)(px + d * cs[0]); q.y = (int)(long long)(py + d * sn[0]); return q; }();
@@ -176,10 +178,24 @@ __global__ void __launch_bounds__(256) k_precompute_w(const float* __restrict__ 
     if (suf) { sarea[i] = s_total; maxlen[i] = ml * 1.000001f; }
     int4 b; b.x = (int)bx1; b.y = (int)bx2; b.z = (int)by1; b.w = (int)by2;
     bbox[i] = b;
-    atomicMax(&stats[0], __float_as_uint(rmax));
+    st_r = fmaxf(st_r, rmax);
     float cx = fminf(fmaxf(px, -1.0e9f), 1.0e9f), cy = fminf(fmaxf(py, -1.0e9f), 1.0e9f);
-    atomicMin((int*)&stats[1], (int)floorf(cx)); atomicMax((int*)&stats[2], (int)floorf(cx));
-    atomicMin((int*)&stats[3], (int)floorf(cy)); atomicMax((int*)&stats[4], (int)floorf(cy));
+    st_x0 = min(st_x0, (int)floorf(cx)); st_x1 = max(st_x1, (int)floorf(cx));
+    st_y0 = min(st_y0, (int)floorf(cy)); st_y1 = max(st_y1, (int)floorf(cy));
+  }
+  }
+  __shared__ unsigned int sh_r; __shared__ int sh_b[4];
+  if (threadIdx.x == 0) { sh_r = 0u; sh_b[0] = INT32_MAX; sh_b[1] = INT32_MIN; sh_b[2] = INT32_MAX; sh_b[3] = INT32_MIN; }
+  __syncthreads();
+  if (lane == 0) {
+    atomicMax(&sh_r, __float_as_uint(st_r));
+    atomicMin(&sh_b[0], st_x0); atomicMax(&sh_b[1], st_x1); atomicMin(&sh_b[2], st_y0); atomicMax(&sh_b[3], st_y1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicMax(&stats[0], sh_r);
+    atomicMin((int*)&stats[1], sh_b[0]); atomicMax((int*)&stats[2], sh_b[1]);
+    atomicMin((int*)&stats[3], sh_b[2]); atomicMax((int*)&stats[4], sh_b[3]);
   }
 }
 
@@ -360,7 +376,7 @@ extern "C" int sdb_nms2d_survivors(const float* d_dist, const float* d_points, i
   SDB_CUDA(cudaMemcpyAsync(b_tab.p, tab.data(), 2 * R * sizeof(float), cudaMemcpyHostToDevice, st));
   const int init_stats[8] = {0, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0, 0, 0};
   SDB_CUDA(cudaMemcpyAsync(b_stats.p, init_stats, sizeof(init_stats), cudaMemcpyHostToDevice, st));
-  SDB_LAUNCH(k_precompute_w, cdiv((long long)n * 32, 256), 256, 0, st, d_dist, d_points, b_tab.as<float>(), b_tab.as<float>() + R, n, R,
+  SDB_LAUNCH(k_precompute_w, std::min(cdiv((long long)n * 32, 256), 148 * 16), 256, 0, st, d_dist, d_points, b_tab.as<float>(), b_tab.as<float>() + R, n, R,
              b_verts.as<int2>(), b_bbox.as<int4>(), b_radius.as<float>(), b_area.as<float>(),
              filter ? b_suf.as<double>() : (double*)nullptr, b_sarea.as<double>(), b_maxlen.as<float>(), b_stats.as<unsigned int>());
   int h_stats[8];

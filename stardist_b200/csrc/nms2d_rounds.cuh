@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
     int ccx = 0, ccy = 0;
     if (!A.G.all_pairs) { ccx = cell_of(cx, A.G.minx, A.G.cell, A.G.gx); ccy = cell_of(cy, A.G.miny, A.G.cell, A.G.gy); }
     int2 cur = cursor[c];          // (neighbour cell 0..8, offset inside that cell)
-    bool blocked = false;
+    bool blocked = false, first_step = true;
     for (int k = cur.x; k < 9 && !blocked; ++k) {
       // own cell first, then the edge neighbours, then the corners: a blocker is nearly always found among the
       // first (= highest scored) items of the candidate's own cell
@@ -69,7 +69,12 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
       if (yy < 0 || yy >= A.G.gy || xx < 0 || xx >= A.G.gx) { cur.x = k + 1; cur.y = 0; continue; }
       const int cell = yy * A.G.gx + xx;
       const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
-      for (unsigned int t0 = b + (unsigned int)cur.y; t0 < e; t0 += 32) {
+      // The scan is a chain of dependent L2 round trips (items -> state / centre / radius / bbox), ~1 us per step
+      // whatever its width: the first step of a candidate looks at 32 items (in round 0 that nearly always finds
+      // the blocker), later steps at 128 (4 per lane, loads in flight together).
+      unsigned int t0 = b + (unsigned int)cur.y;
+      if (first_step && t0 < e) {
+        first_step = false;
         const unsigned int t = t0 + lane;
         bool hit = false, past = false;
         if (t < e) {
@@ -80,7 +85,32 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
           } else past = true;
         }
         const unsigned int m = __ballot_sync(0xffffffffu, hit);
-        if (m) { blocked = true; cur.x = k; cur.y = (int)(t0 + (unsigned int)(__ffs(m) - 1) - b); break; }
+        if (m) { blocked = true; cur.x = k; cur.y = (int)(t0 + (unsigned int)(__ffs(m) - 1) - b); }
+        else if (__any_sync(0xffffffffu, past)) t0 = e;
+        else t0 += 32;
+      }
+      for (; t0 < e && !blocked; t0 += 128) {
+        int hs[4];
+        bool hit[4], past = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned int t = t0 + 32u * u + lane;
+          hs[u] = (t < e) ? A.items[t] : 0x7fffffff;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          hit[u] = false;
+          const int h = hs[u];
+          if (h < c) {
+            const int sh = A.state[h];
+            if (sh == ST_UNDECIDED || sh == kept_now) hit[u] = reaches(A, h, c, cy, cx, bc);
+          } else if (h != 0x7fffffff) past = true;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned int m = __ballot_sync(0xffffffffu, hit[u]);
+          if (m && !blocked) { blocked = true; cur.x = k; cur.y = (int)(t0 + 32u * u + (unsigned int)(__ffs(m) - 1) - b); }
+        }
         if (__any_sync(0xffffffffu, past)) break;     // cell lists are sorted by index: nothing below c is left
       }
       if (!blocked) { cur.x = k + 1; cur.y = 0; }

@@ -54,6 +54,11 @@ struct ConvParams {
   const float* fuse_w; const float* fuse_b;
 };
 
+// fused heads (k_conv_tc4<128, true>): head weights [128][36] fp32 in constant memory -- every thread reads the same
+// element, so they enter the FFMAs as constant-bank operands (from shared memory the broadcast LDS.128 traffic,
+// 4 register-write cycles each, made the epilogue 4x slower than the FP32 pipe allows)
+__constant__ float c_fuse_w[128 * 36];
+
 // ---------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -733,13 +738,14 @@ struct TcCfg4 {
 
 // WRES: all 9 * n_cb weight tiles of the layer are loaded ONCE per (persistent) CTA and stay in shared memory.
 template <int N, bool FUSE, bool WRES>
-__global__ void __launch_bounds__(FUSE ? 320 : 192, 1)
+__global__ void __launch_bounds__(FUSE ? 352 : 224, 1)
 k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
            const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
            const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P,
            int tiles_x, int tiles_y, int n_tiles, int n_b_slots) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
+  constexpr int W_WARP = FUSE ? 10 : 6;          // warps: 0 halo TMA, 1 MMA, 2.. epilogue (4 or 8), last: weight TMA
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* smA = smem;
@@ -782,7 +788,37 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t ai = 0, bi = 0;
+      uint32_t ai = 0;
+      bool ok = true;
+      // halos run ahead by A_STAGES work items (tile, channel block), independent of the weight ring
+      auto load_halo = [&](int tile, int cb, uint32_t a_idx) -> bool {
+        const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
+        const int y0 = (rem / tiles_x) * S, x0 = (rem % tiles_x) * 128;
+        const uint32_t sa = a_idx % C::A_STAGES;
+        if (a_idx >= (uint32_t)C::A_STAGES && !mbar_wait(&a_empty[sa], ((a_idx / C::A_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 11u); return false; }
+        const int ch = cb * C::KC;
+        unsigned char* sta = smA + sa * C::A_STAGE;
+        mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
+        if (ch < P.c_src0) {
+          tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+          tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+        } else {
+          tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+          tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+        }
+        return true;
+      };
+      int tile = blockIdx.x, cb = 0;
+      while (ok && tile < n_tiles) {
+        ok = load_halo(tile, cb, ai);
+        ++ai;
+        if (++cb == n_cb) { cb = 0; tile += (int)gridDim.x; }
+      }
+    }
+  } else if (warp == W_WARP) {
+    // ===================== TMA producer: weights (own warp: the halo requests must not queue behind ring waits) ==========
+    if (lane == 0) {
+      uint32_t bi = 0;
       bool ok = true;
       if (WRES) {
         mbar_expect_tx(&b_full[0], (uint32_t)(9 * n_cb) * C::B_STAGE);
@@ -792,32 +828,19 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
             tma_load_3d(stb, &tm_w_hi, &b_full[0], cb * C::KC, 0, tap);
             tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[0], cb * C::KC, 0, tap);
           }
-      }
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-        const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
-        const int y0 = (rem / tiles_x) * S, x0 = (rem % tiles_x) * 128;
-        for (int cb = 0; cb < n_cb && ok; ++cb, ++ai) {
-          const uint32_t sa = ai % C::A_STAGES;
-          if (ai >= (uint32_t)C::A_STAGES && !mbar_wait(&a_empty[sa], ((ai / C::A_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 11u); ok = false; break; }
-          const int ch = cb * C::KC;
-          unsigned char* sta = smA + sa * C::A_STAGE;
-          mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
-          if (ch < P.c_src0) {
-            tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, img);
-            tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, img);
-          } else {
-            tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
-            tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+      } else {
+        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
+          for (int cb = 0; cb < n_cb && ok; ++cb) {
+            const int ch = cb * C::KC;
+            for (int tap = 0; tap < 9; ++tap, ++bi) {
+              const uint32_t sb = bi % C::B_STAGES;
+              if (bi >= (uint32_t)C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
+              unsigned char* stb = smB + sb * C::B_STAGE;
+              mbar_expect_tx(&b_full[sb], C::B_STAGE);
+              tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
+              tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[sb], ch, 0, tap);
+            }
           }
-          if (!WRES) for (int tap = 0; tap < 9; ++tap, ++bi) {
-            const uint32_t sb = bi % C::B_STAGES;
-            if (bi >= (uint32_t)C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
-            unsigned char* stb = smB + sb * C::B_STAGE;
-            mbar_expect_tx(&b_full[sb], C::B_STAGE);
-            tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
-            tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[sb], ch, 0, tap);
-          }
-        }
       }
     }
   } else if (warp == 1) {
@@ -899,7 +922,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           float out[33];
 #pragma unroll
           for (int o = 0; o < 33; ++o) out[o] = sHB[o];
-#pragma unroll 1
+#pragma unroll
           for (int c0 = 0; c0 < N; c0 += 32) {
             uint32_t r[32];
             SDB_TMEM_LD32(r, tbase + (uint32_t)(s * C::STRIP_COLS + c0));
@@ -913,14 +936,8 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
             for (int j = 0; j < 32; ++j) {
               float f = __uint_as_float(r[j]) * P.acc_scale + sFB[c0 + j];
               if (P.relu) f = fmaxf(f, 0.f);
-              const float4* w4 = reinterpret_cast<const float4*>(sHW + (c0 + j) * 36);
 #pragma unroll
-              for (int qq = 0; qq < 8; ++qq) {
-                const float4 w = w4[qq];
-                out[4 * qq] = fmaf(f, w.x, out[4 * qq]); out[4 * qq + 1] = fmaf(f, w.y, out[4 * qq + 1]);
-                out[4 * qq + 2] = fmaf(f, w.z, out[4 * qq + 2]); out[4 * qq + 3] = fmaf(f, w.w, out[4 * qq + 3]);
-              }
-              out[32] = fmaf(f, sHW[(c0 + j) * 36 + 32], out[32]);
+              for (int o = 0; o < 33; ++o) out[o] = fmaf(f, c_fuse_w[(c0 + j) * 36 + o], out[o]);
             }
           }
           if (in_img) {
@@ -1261,7 +1278,7 @@ static int launch_tc4_impl(const CUtensorMap& a0h, const CUtensorMap& a0l, const
   const int grid = std::min(n_tiles, g_num_sms);
   sdb::ProfSpan sp;
   sdb::profile_begin("conv_tc", st, &sp);
-  k_conv_tc4<N, FUSE, WRES><<<grid, FUSE ? 320 : 192, smem, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles, n_b_slots);
+  k_conv_tc4<N, FUSE, WRES><<<grid, FUSE ? 352 : 224, smem, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles, n_b_slots);
   sdb::profile_end("conv_tc", st, &sp);
   sdb::profile_add_units("conv_tc", (2.0 * 9.0 * P.c_total * N + (FUSE ? 2.0 * N * (P.heads_R + 1) : 0.0)) * (double)P.H * P.W * n_img);
   sdb::g_launch_count++;
@@ -1397,6 +1414,7 @@ extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, in
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
   P.fuse_w = d_heads_w; P.fuse_b = d_heads_b;
+  SDB_CUDA(cudaMemcpyToSymbolAsync(c_fuse_w, d_heads_w, sizeof(float) * 128 * 36, 0, cudaMemcpyDeviceToDevice, st));
   return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
 
@@ -1430,6 +1448,69 @@ extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_s
 extern "C" int sdb_tc_set_variant(int variant) {
   if (variant != 0 && variant != 1 && variant != 3 && variant != 4) { sdb::set_error("tc_set_variant: 0 (auto), 1, 3 or 4"); return 1; }
   g_tc_variant = variant;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- TMA probe (profiling aid)
+// Persistent CTAs that only stream (rows x 130 pixel x box_c channel) halo boxes of an [n,h,w,c] fp16 tensor through
+// two shared-memory stages -- no MMA.  Measures what the TMA unit delivers for 64-byte vs 128-byte inner rows.
+__global__ void __launch_bounds__(64, 1) k_tma_probe(const __grid_constant__ CUtensorMap tm, int tiles_x, int tiles_y, int n_tiles, int rows,
+                                                     int stage_bytes, int box_bytes, int loads_per_tile, unsigned int* err) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int y0 = (tile / tiles_x) * (rows - 2), x0 = (tile % tiles_x) * 128;
+      const uint32_t s = it & 1;
+      if (it >= 2 && !mbar_wait(&full[s], ((it >> 1) - 1) & 1)) { atomicExch(err, 21u); break; }
+      mbar_expect_tx(&full[s], (uint32_t)(loads_per_tile * box_bytes));
+      for (int l = 0; l < loads_per_tile; ++l)
+        tma_load_4d(smem + s * stage_bytes + l * (((box_bytes + 1023) / 1024) * 1024), &tm, &full[s], 0, x0 - 1, y0 - 1, 0);
+    }
+    for (uint32_t k = (it >= 2 ? it - 2 : 0); k < it; ++k) mbar_wait(&full[k & 1], (k >> 1) & 1);
+  }
+}
+
+extern "C" int sdb_tma_probe(const void* d_act, int h, int w, int c, int box_c, int rows, int loads_per_tile, int reps, float* ms_out, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { sdb::set_error("cuTensorMapEncodeTiled entry point not available"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, 130, (cuuint32_t)rows, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = (box_c * 2 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)d_act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { sdb::set_error("tma_probe: cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
+  const int box_bytes = box_c * 2 * 130 * rows;
+  const int stage_bytes = loads_per_tile * (((box_bytes + 1023) / 1024) * 1024);
+  const int smem = 2 * stage_bytes + 1024 + 64;
+  if (smem > 227 * 1024) { sdb::set_error("tma_probe: stage too large"); return 1; }
+  SDB_CUDA(cudaFuncSetAttribute(k_tma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (!g_num_sms) { int dev = 0; SDB_CUDA(cudaGetDevice(&dev)); SDB_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev)); }
+  const int tiles_x = cdiv(w, 128), tiles_y = cdiv(h, rows - 2), n_tiles = tiles_x * tiles_y;
+  cudaEvent_t e0, e1;
+  SDB_CUDA(cudaEventCreate(&e0)); SDB_CUDA(cudaEventCreate(&e1));
+  k_tma_probe<<<std::min(n_tiles, g_num_sms), 64, smem, st>>>(m, tiles_x, tiles_y, n_tiles, rows, stage_bytes, box_bytes, loads_per_tile, g_err_flag);
+  SDB_CUDA(cudaEventRecord(e0, st));
+  for (int i = 0; i < reps; ++i)
+    k_tma_probe<<<std::min(n_tiles, g_num_sms), 64, smem, st>>>(m, tiles_x, tiles_y, n_tiles, rows, stage_bytes, box_bytes, loads_per_tile, g_err_flag);
+  SDB_CUDA(cudaEventRecord(e1, st));
+  SDB_CUDA(cudaEventSynchronize(e1));
+  float ms = 0; SDB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / reps;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
 }
 

@@ -230,9 +230,9 @@ class StarDistBase:
         x = resizer.before(x, axes_net, axes_net_div_by)
         if not _is_floatarray(x):
             warnings.warn("Predicting on non-float input... ( forgot to normalize? )")
-        if np.prod(n_tiles) > 1:
-            raise NotImplementedError("n_tiles > 1 is not implemented yet on the B200 path "
-                                      "(use predict_instances_big for large images)")
+        # tiles refer to the axes of the input image; the network sees them in axes_net order (base.py:419-424)
+        n_tiles = _permute_axes(np.empty(n_tiles, dtype=bool)).shape
+        n_tiles[channel] == 1 or _raise(ValueError("cannot tile the channel axis"))
         return x, axes, axes_net, axes_net_div_by, _permute_axes, resizer, n_tiles, grid, grid_dict, channel
 
     def _pinned(self, key, shape, dtype):
@@ -268,11 +268,47 @@ class StarDistBase:
         torch.cuda.current_stream().synchronize()
         return [None if p is None else p.numpy().copy() for p in pinned], sum(0 if p is None else p.numel() * p.element_size() for p in pinned)
 
-    def predict_direct_device(self, x_dev):
-        """x_dev [1,...,C] float32 device -> (prob [...], dist [..., R]) device tensors (padded, /grid)"""
-        prob, dist = self.net.forward(x_dev)
-        self._last = (prob[0], dist[0])
-        return prob[0], dist[0]
+    def predict_direct_device(self, x_dev, n_tiles=None):
+        """x_dev [1,...,C] float32 device -> (prob [...], dist [..., R]) device tensors (padded, /grid).
+        n_tiles (axes_net order, channel entry 1): run the network tile by tile (base.py:446-529)."""
+        if n_tiles is not None and int(np.prod(n_tiles)) > 1:
+            prob, dist = self._predict_tiled_device(x_dev, tuple(int(t) for i, t in enumerate(n_tiles) if i != len(n_tiles) - 1))
+        else:
+            prob, dist = self.net.forward(x_dev)
+            prob, dist = prob[0], dist[0]
+        self._last = (prob, dist)
+        return prob, dist
+
+    def _predict_tiled_device(self, x_dev, n_tiles_sp):
+        """The padded input is split into n_tiles blocks per spatial axis (block borders on multiples of
+        pool^depth*grid); every block is extended by the network's receptive-field radius (_axes_tile_overlap, as
+        the reference does), pushed through the network, and the block's own region of the prob/dist maps is kept.
+        Identical to the untiled maps: only zero padding further than the receptive field away differs."""
+        sp_axes = self.config.axes.replace('C', '')
+        sp = tuple(int(v) for v in x_dev.shape[1:-1])
+        nd = len(sp)
+        div = self._axes_div_by(sp_axes)
+        grid = tuple(self.config.grid)
+        ov = tuple(int(-(-o // d) * d) for o, d in zip(self._axes_tile_overlap(sp_axes), div))
+        R = self.config.n_rays
+        prob = torch.empty(tuple(s // g for s, g in zip(sp, grid)), dtype=torch.float32, device=x_dev.device)
+        dist = torch.empty(prob.shape + (R,), dtype=torch.float32, device=x_dev.device)
+        cuts = []
+        for s, d, n in zip(sp, div, n_tiles_sp):
+            units = s // d
+            n = max(1, min(int(n), units))
+            b = [round(i * units / n) * d for i in range(n + 1)]
+            cuts.append([(b[i], b[i + 1]) for i in range(n) if b[i + 1] > b[i]])
+        import itertools
+        for block in itertools.product(*cuts):
+            ext = tuple((max(0, a0 - o), min(s, a1 + o)) for (a0, a1), o, s in zip(block, ov, sp))
+            xt = x_dev[(slice(None),) + tuple(slice(e0, e1) for e0, e1 in ext) + (slice(None),)].contiguous()
+            p, d = self.net.forward(xt)
+            src = tuple(slice((a0 - e0) // g, (a1 - e0) // g) for (a0, a1), (e0, e1), g in zip(block, ext, grid))
+            dst = tuple(slice(a0 // g, a1 // g) for (a0, a1), g in zip(block, grid))
+            prob[dst] = p[0][src]
+            dist[dst] = d[0][src]
+        return prob, dist
 
     def _last_maps(self):
         """(tests) padded prob / dist maps of the most recent forward pass, as numpy"""
@@ -284,7 +320,7 @@ class StarDistBase:
         L.require_cuda()
         x, axes, axes_net, axes_net_div_by, _permute_axes, resizer, n_tiles, grid, grid_dict, channel = \
             self._predict_setup(img, axes, normalizer, n_tiles)
-        prob_d, dist_d = self.predict_direct_device(self._to_device(x))
+        prob_d, dist_d = self.predict_direct_device(self._to_device(x), n_tiles)
         sp_axes = axes_net.replace('C', '')
         crop = resizer.crop_slices(sp_axes, tuple(prob_d.shape))
         prob = prob_d[crop].contiguous().cpu().numpy()
@@ -301,9 +337,9 @@ class StarDistBase:
             self._predict_setup(img, axes, normalizer, n_tiles)
         sp_axes = axes_net.replace('C', '')
         bounds = resizer.point_bounds(sp_axes)
-        return self._candidates_from_device_input(self._to_device(x), bounds, prob_thresh=prob_thresh, b=b)
+        return self._candidates_from_device_input(self._to_device(x), bounds, prob_thresh=prob_thresh, b=b, n_tiles=n_tiles)
 
-    def _candidates_from_device_input(self, x_dev, bounds, prob_thresh=None, b=2):
+    def _candidates_from_device_input(self, x_dev, bounds, prob_thresh=None, b=2, n_tiles=None):
         """x_dev: padded, normalized input [1,...,C] float32 already in HBM; bounds = un-padded spatial
         extent (filter_points).  Network -> threshold/border mask -> score sort -> gather."""
         lib = L.require_cuda()
@@ -311,7 +347,7 @@ class StarDistBase:
             prob_thresh = self.thresholds.prob
         grid = tuple(self.config.grid)
         self._mark('net_begin')
-        prob_d, dist_d = self.predict_direct_device(x_dev)
+        prob_d, dist_d = self.predict_direct_device(x_dev, n_tiles)
         self._mark('net_end')
         nd = self.config.n_dim
         R = self.config.n_rays

@@ -153,3 +153,50 @@ def test_predict_instances_vs_oracle(sd, shape):
     if shape[0] % 8 == 0 and shape[1] % 8 == 0:
         l2, r2 = model.predict_instances(img, prob_thresh=pthr, nms_thresh=0.3, sparse=False)
         assert np.array_equal(labels, l2) and np.array_equal(res['points'], r2['points'])
+
+
+def test_nms2d_survivors_and_paint_order(sd):
+    """device-side survivor list + paint order (incl. tied scores) == numpy on the keep mask"""
+    import torch, ctypes
+    from stardist_b200 import _lib as L
+    from stardist_b200.geometry.geom2d import paint_order
+    lib = L.require_cuda()
+    rng = np.random.default_rng(5)
+    n, R = 6000, 32
+    pts = rng.integers(0, 200, (n, 2)).astype(np.float32)
+    dist = (9 * (1 + 0.2 * rng.uniform(-1, 1, (n, R)))).astype(np.float32)
+    prob = np.round(rng.uniform(0.5, 1, n), 2).astype(np.float32)          # many ties
+    o = np.argsort(prob, kind='stable')[::-1]
+    dist, pts, prob = np.ascontiguousarray(dist[o]), np.ascontiguousarray(pts[o]), np.ascontiguousarray(prob[o])
+    d_d, p_d = torch.from_numpy(dist).cuda(), torch.from_numpy(pts).cuda()
+    keep = torch.zeros(n, dtype=torch.uint8, device='cuda'); sel = torch.empty(n, dtype=torch.int32, device='cuda')
+    nk = ctypes.c_int(0)
+    L.check(lib.sdb_nms2d_survivors(L.ptr(d_d), L.ptr(p_d), n, R, 0.4, 1, 1, 0, L.ptr(keep), L.ptr(sel), ctypes.byref(nk), L.stream_ptr()))
+    keep_h = keep.cpu().numpy().astype(bool)
+    want = ref_ext.stardist2d().c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(0.4))
+    assert np.array_equal(keep_h, want)
+    assert nk.value == int(want.sum()) and np.array_equal(sel[:nk.value].cpu().numpy(), np.nonzero(want)[0])
+    pk = torch.from_numpy(prob[want]).cuda()
+    rank = torch.empty(nk.value, dtype=torch.int32, device='cuda'); ids = torch.empty(nk.value, dtype=torch.int32, device='cuda')
+    L.check(lib.sdb_paint_order_2d(L.ptr(pk), nk.value, L.ptr(rank), L.ptr(ids), L.stream_ptr()))
+    ind, rk = paint_order(prob[want])
+    assert np.array_equal(rank.cpu().numpy(), rk) and np.array_equal(ids.cpu().numpy(), ind + 1)
+
+
+@pytest.mark.parametrize("shape,n_tiles", [((200, 312), (2, 3)), ((136, 120), (1, 2)), ((264, 264), (4, 4))])
+def test_predict_n_tiles_equals_untiled(sd, shape, n_tiles):
+    """n_tiles (base.py:446-529): tile-by-tile network passes with receptive-field overlap give the same maps and
+    the same instances as the single pass"""
+    rng = np.random.default_rng(shape[0])
+    img = rng.uniform(0, 1, shape).astype(np.float32)
+    model = sd.StarDist2D(sd.Config2D(n_rays=32), name=None, basedir=None)
+    p1, d1 = model.predict(img)
+    p2, d2 = model.predict(img, n_tiles=n_tiles)
+    assert p1.shape == p2.shape == shape and d1.shape == d2.shape
+    assert np.array_equal(p1, p2) and np.array_equal(d1, d2)
+    thr = float(np.quantile(p1, 0.97))
+    l1, r1 = model.predict_instances(img, prob_thresh=thr, nms_thresh=0.4)
+    l2, r2 = model.predict_instances(img, prob_thresh=thr, nms_thresh=0.4, n_tiles=n_tiles)
+    assert np.array_equal(l1, l2) and np.array_equal(r1['points'], r2['points']) and np.array_equal(r1['coord'], r2['coord'])
+    with pytest.raises(ValueError):
+        model.predict(img[..., None], axes='YXC', n_tiles=(1, 1, 2))

@@ -134,3 +134,12 @@ def test_predict_instances_3d_vs_oracle(sd):
     assert np.array_equal(res['prob'], ref['prob'])
     assert np.array_equal(res['dist'], ref['dist'])
     assert np.array_equal(labels, ref_labels)
+
+
+def test_predict_3d_n_tiles_equals_untiled(sd):
+    rng = np.random.default_rng(9)
+    vol = rng.uniform(0, 1, (24, 72, 64)).astype(np.float32)
+    model = sd.StarDist3D(sd.Config3D(rays=sd.Rays_GoldenSpiral(12)), name=None, basedir=None)
+    p1, d1 = model.predict(vol)
+    p2, d2 = model.predict(vol, n_tiles=(1, 3, 2))
+    assert p1.shape == p2.shape and np.array_equal(p1, p2) and np.array_equal(d1, d2)

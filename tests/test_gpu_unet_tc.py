@@ -81,3 +81,56 @@ def test_unet_tc_vs_torch_fp32(shape, grid):
     simt = UNetDevice2D(cfg, model.weights)
     p2, d2 = simt.forward(x)
     assert torch.max(torch.abs(p2 - prob)).item() <= 1e-5
+
+
+@pytest.mark.parametrize("n_rays,fuse", [(16, "1"), (32, "0"), (64, "1"), (7, "1")])
+def test_unet_tc_head_variants(n_rays, fuse, monkeypatch):
+    """heads: fused into the features epilogue (n_rays <= 32, CUDA cores on the fp32 accumulators) or as the
+    separate tensor-core 1x1 kernel (n_rays > 32, or STARDIST_B200_FUSE_HEADS=0) -- both against torch-CPU fp32"""
+    import torch, stardist_b200 as sd
+    from stardist_b200.models.unet_device import UNetDevice2DTC
+    from oracle import unet_torch
+    monkeypatch.setenv("STARDIST_B200_FUSE_HEADS", fuse)
+    cfg = sd.Config2D(n_rays=n_rays)
+    model = sd.StarDist2D(cfg, name=None, basedir=None, seed=n_rays)
+    assert isinstance(model.net, UNetDevice2DTC)
+    assert model.net.fuse_heads == (fuse == "1" and n_rays <= 32)
+    rng = np.random.default_rng(n_rays)
+    img = rng.uniform(0, 1, (56, 264)).astype(np.float32)      # 264 = 2 tiles of 128 + a ragged one
+    x = torch.from_numpy(img[None, ..., None]).cuda()
+    prob, dist = model.net.forward(x)
+    rp, rd = unet_torch.forward(cfg, model.weights, img[None, ..., None])
+    p, d = prob.cpu().numpy(), dist.cpu().numpy()
+    assert p.shape == rp.shape and d.shape == rd.shape
+    assert np.max(np.abs(p - rp)) <= 1e-5 * max(1.0, np.max(np.abs(rp)))
+    assert np.max(np.abs(d - rd)) <= 1e-5 * max(1e-3, np.max(np.abs(rd))) + 1e-7
+
+
+@pytest.mark.parametrize("variant", [1, 3, 4])
+def test_conv_variants_agree(variant):
+    """the three tcgen05 conv kernels (one tile per CTA / persistent / persistent + halo reuse) on one layer"""
+    import torch
+    from stardist_b200 import _lib as L
+    from stardist_b200.models.unet_device import tc_weight_scale
+    lib = L.require_cuda()
+    g = torch.Generator(device='cpu').manual_seed(11)
+    h, w, cin, cout = 37, 300, 64, 64
+    x = torch.randn((1, h, w, cin), generator=g).cuda()
+    k = (torch.randn((3, 3, cin, cout), generator=g) * (2.0 / (9 * cin)) ** 0.5).cuda()
+    b = (torch.randn(cout, generator=g) * 0.1).cuda()
+    xs = _split(x); x_eff = xs[0].double() + xs[1].double()
+    ws = torch.empty((2, 9, cout, cin), dtype=torch.float16, device='cuda')
+    wsc = tc_weight_scale(k.cpu().numpy())
+    L.check(lib.sdb_split_weights(L.ptr(k.contiguous()), cin, cout, wsc, L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
+    k_eff = ((ws[0].double() + ws[1].double()) / wsc).reshape(3, 3, cout, cin).permute(0, 1, 3, 2)
+    out = torch.zeros((2, 1, h, w, cout), dtype=torch.float16, device='cuda')
+    try:
+        L.check(lib.sdb_tc_set_variant(variant))
+        L.check(lib.sdb_conv3x3_tc(L.ptr(None), L.ptr(None), 0, L.ptr(xs[0]), L.ptr(xs[1]), cin, 1, h, w, L.ptr(ws[0]), L.ptr(ws[1]), wsc,
+                                   L.ptr(b), cout, 1, 0, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
+        L.check(lib.sdb_tc_error_check(L.stream_ptr()))
+    finally:
+        L.check(lib.sdb_tc_set_variant(0))
+    got = (out[0].float() + out[1].float()).double()
+    want = _ref_conv(x_eff, k_eff, b, 1)
+    assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
