@@ -188,6 +188,8 @@ int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, int c_src0, c
 /* profiling aid: time persistent CTAs that only TMA-load (rows x 130 px x box_c channel) boxes of an [1,h,w,c] fp16
  * tensor (no MMA), loads_per_tile boxes per 128-pixel tile; ms_out = milliseconds per pass */
 int sdb_tma_probe(const void* d_act, int h, int w, int c, int box_c, int rows, int loads_per_tile, int reps, float* ms_out, sdb_stream_t stream);
+/* profiling aid: u64 [148][8] wait-cycle counters written by the halo-reuse conv (NULL disables) */
+int sdb_tc_set_debug(void* d_buf);
 /* kernel variant of sdb_conv3x3_tc: 0 (default) = auto, 1 = one 8x16 tile per CTA, 3 = persistent CTAs with
  * double-buffered TMEM accumulators and merged hi/lo weight tile, 4 = 3 + halo reuse (one box load per
  * 32-channel block, taps as shifted descriptors).  Results are identical up to fp32 summation order. */

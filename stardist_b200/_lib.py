@@ -51,6 +51,8 @@ def _declare(lib):
     lib.sdb_conv3x3_heads_tc.restype = c_int
     lib.sdb_tma_probe.argtypes = [P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), P]
     lib.sdb_tma_probe.restype = c_int
+    lib.sdb_tc_set_debug.argtypes = [P]
+    lib.sdb_tc_set_debug.restype = c_int
     lib.sdb_tc_error_check.argtypes = [P]
     lib.sdb_tc_set_variant.argtypes = [c_int]
     lib.sdb_tc_set_variant.restype = c_int

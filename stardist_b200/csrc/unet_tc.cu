@@ -52,6 +52,7 @@ struct ConvParams {
   // fused features -> heads (k_conv_tc4<128, true>): fp32 head weights [128][36] (columns 0..R-1 = dist, 32 = prob,
   // zero padded) and biases [36]
   const float* fuse_w; const float* fuse_b;
+  unsigned long long* dbg;      // optional [grid][8] wait-cycle counters of k_conv_tc4 (profiling aid), or nullptr
 };
 
 // fused heads (k_conv_tc4<128, true>): head weights [128][36] fp32 in constant memory -- every thread reads the same
@@ -94,6 +95,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// one elected lane of a fully converged warp (the compiler then issues the uniform-datapath UTCHMMA directly; inside an
+// `if (lane == 0)` region it wraps every MMA in an ELECT / BRA.U.ANY loop, ~60 cycles per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -111,6 +119,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
   d |= (uint64_t)1 << 46;                               // descriptor version (sm_100)
   d |= (uint64_t)layout_type << 61;
   return d;
+}
+
+static unsigned long long* g_tc_dbg = nullptr;
+__device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, unsigned long long& acc) {
+  const long long t0 = clock64();
+  const bool ok = mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+  return ok;
 }
 
 // ---------------------------------------------------------------------------------- the kernel
@@ -397,8 +413,8 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
       uint32_t it = 0, t = 0;
       bool ok = true;
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
@@ -414,17 +430,17 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = smem_u32(smem + s * C::STAGE_BYTES), a_lo = a_hi + C::A_BYTES;
           const uint32_t b_hi = a_hi + 2 * C::A_BYTES;          // W_hi rows, W_lo rows directly behind
+          // descriptors once per stage, then +2 per 16-element k-step (address field = addr >> 4)
+          const uint64_t dah0 = make_desc(a_hi, C::SBO, C::LAYOUT), dal0 = make_desc(a_lo, C::SBO, C::LAYOUT);
+          const uint64_t dbh0 = make_desc(b_hi, C::SBO, C::LAYOUT);
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks) {
-            const uint32_t koff = ks * 32;
-            const uint64_t dah = make_desc(a_hi + koff, C::SBO, C::LAYOUT), dal = make_desc(a_lo + koff, C::SBO, C::LAYOUT);
-            const uint64_t dbh = make_desc(b_hi + koff, C::SBO, C::LAYOUT);
-            umma_f16(d, dah, dbh, C::IDESC_2N, (kb | ks) ? 1u : 0u);      // cols [0,N): hi*Whi, [N,2N): hi*Wlo
-            umma_f16(d, dal, dbh, C::IDESC_N, 1u);                         // cols [0,N) += lo*Whi
+            if (elect_one()) umma_f16(d, dah0 + 2u * ks, dbh0 + 2u * ks, C::IDESC_2N, (kb | ks) ? 1u : 0u);      // cols [0,N): hi*Whi, [N,2N): hi*Wlo
+            if (elect_one()) umma_f16(d, dal0 + 2u * ks, dbh0 + 2u * ks, C::IDESC_N, 1u);                         // cols [0,N) += lo*Whi
           }
-          tcgen05_commit(&empty_bar[s]);
+          if (elect_one()) tcgen05_commit(&empty_bar[s]);
         }
-        tcgen05_commit(&acc_full[buf]);        // (arrives even after a bail-out so the epilogue does not wait forever)
+        if (elect_one()) tcgen05_commit(&acc_full[buf]);        // (arrives even after a bail-out so the epilogue does not wait forever)
       }
     }
   } else {
@@ -745,6 +761,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
            int tiles_x, int tiles_y, int n_tiles, int n_b_slots) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
+  constexpr int RING = FUSE ? 3 : C::B_STAGES;   // weight ring depth (the fused-heads variant needs the room for its exchange area)
   constexpr int W_WARP = FUSE ? 10 : 6;          // warps: 0 halo TMA, 1 MMA, 2.. epilogue (4 or 8), last: weight TMA
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -758,15 +775,14 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
   uint64_t* acc_full = b_empty + C::B_STAGES;      // [2]
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* sHW = reinterpret_cast<float*>(smB + (size_t)n_b_slots * C::B_STAGE + 512);   // FUSE: [N][36] + [36] + [N]
+  float* sHW = reinterpret_cast<float*>(smB + (size_t)n_b_slots * C::B_STAGE + 512);   // FUSE: biases + exchange area
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cb = P.c_total / C::KC;
 
-  if (FUSE) {
-    for (int e = threadIdx.x; e < N * 36; e += blockDim.x) sHW[e] = P.fuse_w[e];
-    for (int e = threadIdx.x; e < 36; e += blockDim.x) sHW[N * 36 + e] = P.fuse_b[e];
-    for (int e = threadIdx.x; e < N; e += blockDim.x) sHW[N * 36 + 36 + e] = P.bias[e];
+  if (FUSE) {      // head biases [36], feature biases [N], then the [128][2][33] exchange area (head weights: constant memory)
+    for (int e = threadIdx.x; e < 36; e += blockDim.x) sHW[e] = P.fuse_b[e];
+    for (int e = threadIdx.x; e < N; e += blockDim.x) sHW[36 + e] = P.bias[e];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -790,12 +806,13 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
     if (lane == 0) {
       uint32_t ai = 0;
       bool ok = true;
+      unsigned long long w_prod = 0;
       // halos run ahead by A_STAGES work items (tile, channel block), independent of the weight ring
       auto load_halo = [&](int tile, int cb, uint32_t a_idx) -> bool {
         const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
         const int y0 = (rem / tiles_x) * S, x0 = (rem % tiles_x) * 128;
         const uint32_t sa = a_idx % C::A_STAGES;
-        if (a_idx >= (uint32_t)C::A_STAGES && !mbar_wait(&a_empty[sa], ((a_idx / C::A_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 11u); return false; }
+        if (a_idx >= (uint32_t)C::A_STAGES && !mbar_wait_t(&a_empty[sa], ((a_idx / C::A_STAGES) - 1) & 1, w_prod)) { atomicExch(P.error_flag, 11u); return false; }
         const int ch = cb * C::KC;
         unsigned char* sta = smA + sa * C::A_STAGE;
         mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
@@ -814,6 +831,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
         ++ai;
         if (++cb == n_cb) { cb = 0; tile += (int)gridDim.x; }
       }
+      if (P.dbg) P.dbg[blockIdx.x * 8 + 6] = w_prod;
     }
   } else if (warp == W_WARP) {
     // ===================== TMA producer: weights (own warp: the halo requests must not queue behind ring waits) ==========
@@ -833,8 +851,8 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           for (int cb = 0; cb < n_cb && ok; ++cb) {
             const int ch = cb * C::KC;
             for (int tap = 0; tap < 9; ++tap, ++bi) {
-              const uint32_t sb = bi % C::B_STAGES;
-              if (bi >= (uint32_t)C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
+              const uint32_t sb = bi % RING;
+              if (bi >= (uint32_t)RING && !mbar_wait(&b_empty[sb], ((bi / RING) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
               unsigned char* stb = smB + sb * C::B_STAGE;
               mbar_expect_tx(&b_full[sb], C::B_STAGE);
               tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
@@ -844,29 +862,37 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
       uint32_t ai = 0, bi = 0, t = 0;
       bool ok = true;
+      unsigned long long w_m0 = 0, w_m1 = 0, w_m2 = 0;
+      const long long t_m = clock64();
       if (WRES && !mbar_wait(&b_full[0], 0)) { atomicExch(P.error_flag, 17u); ok = false; }
       for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++t) {
         const uint32_t buf = t & 1;
         if (t >= 2) {
-          if (!mbar_wait(&acc_empty[buf], ((t >> 1) - 1) & 1)) { atomicExch(P.error_flag, 16u); ok = false; break; }
+          if (!mbar_wait_t(&acc_empty[buf], ((t >> 1) - 1) & 1, w_m0)) { atomicExch(P.error_flag, 16u); ok = false; break; }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t d0 = tmem_base + buf * (uint32_t)C::ACC_COLS;
         for (int cb = 0; cb < n_cb && ok; ++cb, ++ai) {
           const uint32_t sa = ai % C::A_STAGES;
-          if (!mbar_wait(&a_full[sa], (ai / C::A_STAGES) & 1)) { atomicExch(P.error_flag, 13u); ok = false; break; }
+          if (!mbar_wait_t(&a_full[sa], (ai / C::A_STAGES) & 1, w_m1)) { atomicExch(P.error_flag, 13u); ok = false; break; }
           const uint32_t a_hi = smem_u32(smA + sa * C::A_STAGE), a_lo = a_hi + C::A_PLANE;
+          // The issuing thread is the bottleneck of the few-channel layers (72..108 MMAs per 256-pixel tile): build the
+          // descriptors once per stage and add compile-time offsets (the address field is (addr >> 4) in the low
+          // 14 bits; shared memory ends below 256 KB, so the addition never carries out of it).
+          const uint64_t dA_hi = make_desc_sw64(a_hi, 0), dA_lo = make_desc_sw64(a_lo, 0);
+#pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bi) {
-            const uint32_t sb = WRES ? (uint32_t)(cb * 9 + tap) : bi % C::B_STAGES;
+            const uint32_t sb = WRES ? (uint32_t)(cb * 9 + tap) : bi % RING;
             if (!WRES) {
-              if (!mbar_wait(&b_full[sb], (bi / C::B_STAGES) & 1)) { atomicExch(P.error_flag, 14u); ok = false; break; }
+              if (!mbar_wait_t(&b_full[sb], (bi / RING) & 1, w_m2)) { atomicExch(P.error_flag, 14u); ok = false; break; }
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b_hi = smem_u32(smB + (size_t)sb * C::B_STAGE), b_lo = b_hi + N * C::ROWB;
+            const uint64_t dB_hi = make_desc_sw64(smem_u32(smB + (size_t)sb * C::B_STAGE), 0);
+            constexpr uint32_t B_LO = (uint32_t)(N * C::ROWB) >> 4;
             const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
@@ -874,82 +900,110 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
               const uint32_t d = d0 + (uint32_t)(s * C::STRIP_COLS);
 #pragma unroll
               for (int ks = 0; ks < C::KC / 16; ++ks) {
-                const uint32_t koff = ks * 32;
-                const uint64_t dah = make_desc_sw64(a_hi + roff + koff, 0), dal = make_desc_sw64(a_lo + roff + koff, 0);
-                const uint64_t dbh = make_desc_sw64(b_hi + koff, 0);
+                const uint32_t aoff = (roff + ks * 32) >> 4, boff = (uint32_t)(ks * 32) >> 4;
+                const uint64_t dah = dA_hi + aoff, dal = dA_lo + aoff, dbh = dB_hi + boff;
                 const uint32_t acc = (cb | tap | ks) ? 1u : 0u;
                 if (C::MERGE) {
-                  umma_f16(d, dah, dbh, C::IDESC_2N, acc);       // [0,N): hi*Whi   [N,2N): hi*Wlo
-                  umma_f16(d, dal, dbh, C::IDESC_N, 1u);         // [0,N) += lo*Whi
+                  if (elect_one()) umma_f16(d, dah, dbh, C::IDESC_2N, acc);       // [0,N): hi*Whi   [N,2N): hi*Wlo
+                  if (elect_one()) umma_f16(d, dal, dbh, C::IDESC_N, 1u);         // [0,N) += lo*Whi
                 } else {
-                  const uint64_t dbl = make_desc_sw64(b_lo + koff, 0);
-                  umma_f16(d, dah, dbh, C::IDESC_N, acc);
-                  umma_f16(d, dal, dbh, C::IDESC_N, 1u);
-                  umma_f16(d, dah, dbl, C::IDESC_N, 1u);
+                  const uint64_t dbl = dbh + B_LO;
+                  if (elect_one()) umma_f16(d, dah, dbh, C::IDESC_N, acc);
+                  if (elect_one()) umma_f16(d, dal, dbh, C::IDESC_N, 1u);
+                  if (elect_one()) umma_f16(d, dah, dbl, C::IDESC_N, 1u);
                 }
               }
             }
-            if (!WRES) tcgen05_commit(&b_empty[sb]);
+            if (!WRES && elect_one()) tcgen05_commit(&b_empty[sb]);
           }
-          tcgen05_commit(&a_empty[sa]);
+          if (!ok) break;
+          if (elect_one()) tcgen05_commit(&a_empty[sa]);
         }
-        tcgen05_commit(&acc_full[buf]);
+        if (elect_one()) tcgen05_commit(&acc_full[buf]);
       }
+      if (P.dbg && lane == 0) { P.dbg[blockIdx.x * 8 + 0] = w_m0; P.dbg[blockIdx.x * 8 + 1] = w_m1; P.dbg[blockIdx.x * 8 + 2] = w_m2;
+                   P.dbg[blockIdx.x * 8 + 3] = (unsigned long long)(clock64() - t_m); }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;
     const int m = q * 32 + lane;
     uint32_t t = 0;
+    unsigned long long w_e = 0;
+    const long long t_e = clock64();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
       const uint32_t buf = t & 1;
       const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
       const int y0 = (rem / tiles_x) * S, x = (rem % tiles_x) * 128 + m;
-      if (!mbar_wait(&acc_full[buf], (t >> 1) & 1)) { atomicExch(P.error_flag, 15u); break; }
+      if (!mbar_wait_t(&acc_full[buf], (t >> 1) & 1, w_e)) {
+        atomicExch(P.error_flag, 15u);
+        if (FUSE) asm volatile("trap;");      // the fused epilogue meets at named barriers: abort rather than hang
+        break;
+      }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)C::ACC_COLS;
       if (FUSE) {
         // features (bias + ReLU, fp32 straight from the accumulators) -> 1x1 heads on the CUDA cores -> prob / dist.
         // The 128-channel feature map never goes to HBM (it was 512 MB written + 512 MB read per 1024^2 image).
-        const float* sHB = sHW + N * 36;
+        // Eight epilogue warps: warps 2..5 take feature channels 0..63, warps 6..9 channels 64..127, each for BOTH
+        // strips of its pixel column, so every head weight fetched (LDCU, the limiter of this loop) feeds two FFMAs;
+        // the two partial sums per pixel meet in shared memory.
+        const float* sHB = sHW;
         const float* sFB = sHB + 36;
-        // eight epilogue warps: warps 2..5 take strip 0, warps 6..9 strip 1 (two warps per scheduler keep the
-        // FP32 pipe busy: 128 x 33 FMAs per pixel)
-        {
-          const int s = (warp - 2) >> 2;
-          const int y = y0 + s;
-          const bool in_img = (y < P.H) && (x < P.W);
-          float out[33];
+        float* sX = sHW + 36 + N;              // [128 pixels][2 strips][33] partial sums of the upper half
+        const int half = (warp - 2) >> 2;
+        float out0[33], out1[33];
 #pragma unroll
-          for (int o = 0; o < 33; ++o) out[o] = sHB[o];
+        for (int o = 0; o < 33; ++o) { out0[o] = half ? 0.f : sHB[o]; out1[o] = out0[o]; }
 #pragma unroll
-          for (int c0 = 0; c0 < N; c0 += 32) {
-            uint32_t r[32];
-            SDB_TMEM_LD32(r, tbase + (uint32_t)(s * C::STRIP_COLS + c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c0 + 32 >= N) {
-              asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            }
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c0 = half * 64 + cc * 32;
+          uint32_t r0[32], r1[32];
+          SDB_TMEM_LD32(r0, tbase + (uint32_t)c0);
+          SDB_TMEM_LD32(r1, tbase + (uint32_t)(C::STRIP_COLS + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (cc == 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float f = __uint_as_float(r[j]) * P.acc_scale + sFB[c0 + j];
-              if (P.relu) f = fmaxf(f, 0.f);
+          for (int j = 0; j < 32; ++j) {
+            const float fb = sFB[c0 + j];
+            float f0 = __uint_as_float(r0[j]) * P.acc_scale + fb, f1 = __uint_as_float(r1[j]) * P.acc_scale + fb;
+            if (P.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
 #pragma unroll
-              for (int o = 0; o < 33; ++o) out[o] = fmaf(f, c_fuse_w[(c0 + j) * 36 + o], out[o]);
+            for (int o = 0; o < 33; ++o) {
+              const float w = c_fuse_w[(half * 64 + cc * 32 + j) * 36 + o];
+              out0[o] = fmaf(f0, w, out0[o]); out1[o] = fmaf(f1, w, out1[o]);
             }
           }
-          if (in_img) {
-            const size_t pix = ((size_t)img * P.H + y) * P.W + x;
-            P.prob[pix] = 1.f / (1.f + expf(-out[32]));
-            if (P.heads_R == 32) {
-              float4* d4 = reinterpret_cast<float4*>(P.dist + pix * 32);
+        }
+        // combine the halves: the upper half parks its sums, the lower half adds and stores
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // previous tile's exchange fully consumed
+        if (half) {
 #pragma unroll
-              for (int qq = 0; qq < 8; ++qq) d4[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
-            } else {
+          for (int o = 0; o < 33; ++o) { sX[(m * 2 + 0) * 33 + o] = out0[o]; sX[(m * 2 + 1) * 33 + o] = out1[o]; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (!half) {
 #pragma unroll
-              for (int o = 0; o < 32; ++o) if (o < P.heads_R) P.dist[pix * P.heads_R + o] = out[o];
+          for (int s = 0; s < S; ++s) {
+            const int y = y0 + s;
+            float* out = s ? out1 : out0;
+#pragma unroll
+            for (int o = 0; o < 33; ++o) out[o] += sX[(m * 2 + s) * 33 + o];
+            if ((y < P.H) && (x < P.W)) {
+              const size_t pix = ((size_t)img * P.H + y) * P.W + x;
+              P.prob[pix] = 1.f / (1.f + expf(-out[32]));
+              if (P.heads_R == 32) {
+                float4* d4 = reinterpret_cast<float4*>(P.dist + pix * 32);
+#pragma unroll
+                for (int qq = 0; qq < 8; ++qq) d4[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
+              } else {
+#pragma unroll
+                for (int o = 0; o < 32; ++o) if (o < P.heads_R) P.dist[pix * P.heads_R + o] = out[o];
+              }
             }
           }
         }
@@ -1011,6 +1065,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
         }
       }
     }
+    if (P.dbg && threadIdx.x == 64) { P.dbg[blockIdx.x * 8 + 4] = w_e; P.dbg[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_e); }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -1267,8 +1322,8 @@ static int launch_tc4_impl(const CUtensorMap& a0h, const CUtensorMap& a0l, const
                            const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
   using C = TcCfg4<N>;
   const int n_cb = P.c_total / C::KC;
-  const int n_b_slots = WRES ? 9 * n_cb : C::B_STAGES;
-  const int smem = C::SMEM_FIXED + n_b_slots * C::B_STAGE + (FUSE ? (N * 36 + 36 + N) * 4 : 0);
+  const int n_b_slots = WRES ? 9 * n_cb : (FUSE ? 3 : C::B_STAGES);
+  const int smem = C::SMEM_FIXED + n_b_slots * C::B_STAGE + (FUSE ? (36 + N + 128 * 2 * 33) * 4 : 0);
   if (smem > 227 * 1024) { sdb::set_error("conv_tc4: shared memory budget exceeded"); return 1; }
   static int attr = 0;
   if (attr < smem) { SDB_CUDA(cudaFuncSetAttribute((k_conv_tc4<N, FUSE, WRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
@@ -1331,7 +1386,7 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg;
   if ((g_tc_variant == 4 || (g_tc_variant == 0 && cin <= 64 && w >= 96)) && cout <= 128) {
     // halo-reuse persistent kernel: 32-channel blocks, (S+2) x 130 pixel boxes
     constexpr int ROWS = TcCfg4<32>::S + 2;
@@ -1377,7 +1432,7 @@ extern "C" int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n
   if (make_w_map(&wh, (const __half*)w_hi, cfeat, np, 64, 1) || make_w_map(&wl, (const __half*)w_lo, cfeat, np, 64, 1)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = 0; P.c_total = cfeat; P.relu = 0; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist; P.fuse_w = nullptr; P.fuse_b = nullptr;
+  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = nullptr;
   if (g_tc_variant != 1) {
     if (np == 48) return launch_tc3<48, 64>(ah, al, ah, al, wh, wl, P, n, st);
     if (np == 80) return launch_tc3<80, 64>(ah, al, ah, al, wh, wl, P, n, st);
@@ -1413,7 +1468,7 @@ extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, in
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
-  P.fuse_w = d_heads_w; P.fuse_b = d_heads_b;
+  P.fuse_w = d_heads_w; P.fuse_b = d_heads_b; P.dbg = g_tc_dbg;
   SDB_CUDA(cudaMemcpyToSymbolAsync(c_fuse_w, d_heads_w, sizeof(float) * 128 * 36, 0, cudaMemcpyDeviceToDevice, st));
   return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
@@ -1437,7 +1492,7 @@ extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_s
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg;
   if (cout == 32) return launch_tc2<32, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 64) return launch_tc2<64, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
   if (cout == 128) return launch_tc2<128, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
@@ -1513,6 +1568,10 @@ extern "C" int sdb_tma_probe(const void* d_act, int h, int w, int c, int box_c, 
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
 }
+
+// profiling aid: device buffer [148][8] of u64 that k_conv_tc4 launches fill with wait-cycle counters
+// (0 acc_empty, 1 a_full, 2 b_full, 3 MMA-warp total, 4 acc_full, 5 epilogue total, 6 a_empty), or NULL to disable
+extern "C" int sdb_tc_set_debug(void* d_buf) { g_tc_dbg = (unsigned long long*)d_buf; return 0; }
 
 // non-zero when any tcgen05 conv launch since the last call hit a bounded-wait timeout (then results are invalid)
 extern "C" int sdb_tc_error_check(sdb_stream_t stream) {

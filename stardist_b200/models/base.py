@@ -283,7 +283,8 @@ class StarDistBase:
         """The padded input is split into n_tiles blocks per spatial axis (block borders on multiples of
         pool^depth*grid); every block is extended by the network's receptive-field radius (_axes_tile_overlap, as
         the reference does), pushed through the network, and the block's own region of the prob/dist maps is kept.
-        Identical to the untiled maps: only zero padding further than the receptive field away differs."""
+        Same maps as the single pass up to float summation order (small tiles may select another conv kernel
+        variant): only zero padding further than the receptive field away differs."""
         sp_axes = self.config.axes.replace('C', '')
         sp = tuple(int(v) for v in x_dev.shape[1:-1])
         nd = len(sp)
