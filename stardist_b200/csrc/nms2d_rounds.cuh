@@ -141,11 +141,23 @@ __global__ void __launch_bounds__(256) k_pairs(NmsArrays A, int round, const int
     const float rr = A.max_dist + A.radius[h];
     int hcx = 0, hcy = 0;
     if (!A.G.all_pairs) { hcx = cell_of(hx, A.G.minx, A.G.cell, A.G.gx); hcy = cell_of(hy, A.G.miny, A.G.cell, A.G.gy); }
-    for (int yy = max(hcy - 1, 0); yy <= min(hcy + 1, A.G.gy - 1); ++yy)
-      for (int xx = max(hcx - 1, 0); xx <= min(hcx + 1, A.G.gx - 1); ++xx) {
-        const int cell = yy * A.G.gx + xx;
-        const unsigned int e = A.cell_start[cell + 1];
-        for (unsigned int t = A.cell_start[cell] + threadIdx.x; t < e; t += blockDim.x) {
+    // the (up to) nine neighbour cells as one flat index range: their item loads are independent, so all threads of
+    // the block walk the concatenation instead of nine short dependent passes
+    unsigned int beg[9], pre[10];
+    pre[0] = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int yy = hcy + k / 3 - 1, xx = hcx + k % 3 - 1;
+      unsigned int b = 0, e = 0;
+      if (yy >= 0 && yy < A.G.gy && xx >= 0 && xx < A.G.gx) { const int cell = yy * A.G.gx + xx; b = A.cell_start[cell]; e = A.cell_start[cell + 1]; }
+      beg[k] = b; pre[k + 1] = pre[k] + (e - b);
+    }
+    for (unsigned int u = threadIdx.x; u < pre[9]; u += blockDim.x) {
+      unsigned int t = 0;
+#pragma unroll
+      for (int q = 0; q < 9; ++q) if (u >= pre[q] && u < pre[q + 1]) t = beg[q] + (u - pre[q]);     // static indices: registers
+      {
+        {
           const int c = A.items[t];
           if (c <= h) continue;
           if (A.state[c] != ST_UNDECIDED) continue;
@@ -158,10 +170,11 @@ __global__ void __launch_bounds__(256) k_pairs(NmsArrays A, int round, const int
             const int4 bc = A.bbox[c];
             if (!(bc.x <= bh.y && bh.x <= bc.y && bc.z <= bh.w && bh.z <= bc.w)) continue;
           }
-          const unsigned int k = atomicAdd(&counters[1], 1u);
-          if (k < cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
+          const unsigned int k2 = atomicAdd(&counters[1], 1u);
+          if (k2 < cap) { int2 pr; pr.x = h; pr.y = c; pairs[k2] = pr; }
         }
       }
+    }
   }
 }
 __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ counters) {

@@ -55,11 +55,6 @@ struct ConvParams {
   unsigned long long* dbg;      // optional [grid][8] wait-cycle counters of k_conv_tc4 (profiling aid), or nullptr
 };
 
-// fused heads (k_conv_tc4<128, true>): head weights [128][36] fp32 in constant memory -- every thread reads the same
-// element, so they enter the FFMAs as constant-bank operands (from shared memory the broadcast LDS.128 traffic,
-// 4 register-write cycles each, made the epilogue 4x slower than the FP32 pipe allows)
-__constant__ float c_fuse_w[128 * 36];
-
 // ---------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -101,6 +96,16 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
 }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -761,7 +766,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
            int tiles_x, int tiles_y, int n_tiles, int n_b_slots) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
-  constexpr int RING = FUSE ? 3 : C::B_STAGES;   // weight ring depth (the fused-heads variant needs the room for its exchange area)
+  constexpr int RING = C::B_STAGES;              // weight ring depth
   constexpr int W_WARP = FUSE ? 10 : 6;          // warps: 0 halo TMA, 1 MMA, 2.. epilogue (4 or 8), last: weight TMA
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -780,9 +785,10 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cb = P.c_total / C::KC;
 
-  if (FUSE) {      // head biases [36], feature biases [N], then the [128][2][33] exchange area (head weights: constant memory)
+  if (FUSE) {      // head biases [36], feature biases [N], head weights [N][36]
     for (int e = threadIdx.x; e < 36; e += blockDim.x) sHW[e] = P.fuse_b[e];
     for (int e = threadIdx.x; e < N; e += blockDim.x) sHW[36 + e] = P.bias[e];
+    for (int e = threadIdx.x; e < N * 36; e += blockDim.x) sHW[36 + N + e] = P.fuse_w[e];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -945,65 +951,61 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       if (FUSE) {
         // features (bias + ReLU, fp32 straight from the accumulators) -> 1x1 heads on the CUDA cores -> prob / dist.
         // The 128-channel feature map never goes to HBM (it was 512 MB written + 512 MB read per 1024^2 image).
-        // Eight epilogue warps: warps 2..5 take feature channels 0..63, warps 6..9 channels 64..127, each for BOTH
-        // strips of its pixel column, so every head weight fetched (LDCU, the limiter of this loop) feeds two FFMAs;
-        // the two partial sums per pixel meet in shared memory.
-        const float* sHB = sHW;
-        const float* sFB = sHB + 36;
-        float* sX = sHW + 36 + N;              // [128 pixels][2 strips][33] partial sums of the upper half
-        const int half = (warp - 2) >> 2;
-        float out0[33], out1[33];
+        // Eight epilogue warps; warps 2..5 compute dist 0..15, warps 6..9 dist 16..31 and prob, each for BOTH strips
+        // of its pixel column: one LDS.128 of head weights (shared memory, warp-wide broadcast) feeds 8 FFMAs.
+        // (Head weights in constant memory ran 5x slower: the 18 KB table misses the per-SMSP constant cache.)
+        const float* sHB = sHW;                      // [36] head biases
+        const float* sFB = sHW + 36;                 // [N] feature biases
+        const float* sW = sHW + 36 + N;              // [N][36] head weights
+        const uint32_t sFB_s = smem_u32(sFB), sW_s = smem_u32(sW);
+        const int grp = (warp - 2) >> 2;
+        float o0[17], o1[17];
 #pragma unroll
-        for (int o = 0; o < 33; ++o) { out0[o] = half ? 0.f : sHB[o]; out1[o] = out0[o]; }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c0 = half * 64 + cc * 32;
+        for (int o = 0; o < 16; ++o) { o0[o] = sHB[grp * 16 + o]; o1[o] = o0[o]; }
+        o0[16] = grp ? sHB[32] : 0.f; o1[16] = o0[16];
+#pragma unroll 1
+        for (int c0 = 0; c0 < N; c0 += 32) {
           uint32_t r0[32], r1[32];
           SDB_TMEM_LD32(r0, tbase + (uint32_t)c0);
           SDB_TMEM_LD32(r1, tbase + (uint32_t)(C::STRIP_COLS + c0));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (cc == 1) {
+          if (c0 + 32 >= N) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float fb = sFB[c0 + j];
+            // explicit ld.shared: the dynamic carve-up hides the address space from the compiler (generic LD.E otherwise)
+            const float fb = lds32(sFB_s + 4u * (uint32_t)(c0 + j));
             float f0 = __uint_as_float(r0[j]) * P.acc_scale + fb, f1 = __uint_as_float(r1[j]) * P.acc_scale + fb;
             if (P.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+            const uint32_t wrow = sW_s + 4u * (uint32_t)((c0 + j) * 36 + grp * 16);
 #pragma unroll
-            for (int o = 0; o < 33; ++o) {
-              const float w = c_fuse_w[(half * 64 + cc * 32 + j) * 36 + o];
-              out0[o] = fmaf(f0, w, out0[o]); out1[o] = fmaf(f1, w, out1[o]);
+            for (int qq = 0; qq < 4; ++qq) {
+              const float4 w = lds128(wrow + 16u * qq);
+              o0[4 * qq] = fmaf(f0, w.x, o0[4 * qq]); o0[4 * qq + 1] = fmaf(f0, w.y, o0[4 * qq + 1]);
+              o0[4 * qq + 2] = fmaf(f0, w.z, o0[4 * qq + 2]); o0[4 * qq + 3] = fmaf(f0, w.w, o0[4 * qq + 3]);
+              o1[4 * qq] = fmaf(f1, w.x, o1[4 * qq]); o1[4 * qq + 1] = fmaf(f1, w.y, o1[4 * qq + 1]);
+              o1[4 * qq + 2] = fmaf(f1, w.z, o1[4 * qq + 2]); o1[4 * qq + 3] = fmaf(f1, w.w, o1[4 * qq + 3]);
             }
+            if (grp) { const float w = lds32(sW_s + 4u * (uint32_t)((c0 + j) * 36 + 32)); o0[16] = fmaf(f0, w, o0[16]); o1[16] = fmaf(f1, w, o1[16]); }
           }
         }
-        // combine the halves: the upper half parks its sums, the lower half adds and stores
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // previous tile's exchange fully consumed
-        if (half) {
 #pragma unroll
-          for (int o = 0; o < 33; ++o) { sX[(m * 2 + 0) * 33 + o] = out0[o]; sX[(m * 2 + 1) * 33 + o] = out1[o]; }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (!half) {
+        for (int s = 0; s < S; ++s) {
+          const int y = y0 + s;
+          const float* out = s ? o1 : o0;
+          if ((y < P.H) && (x < P.W)) {
+            const size_t pix = ((size_t)img * P.H + y) * P.W + x;
+            if (grp) P.prob[pix] = 1.f / (1.f + expf(-out[16]));
+            if (P.heads_R == 32) {
+              float4* d4 = reinterpret_cast<float4*>(P.dist + pix * 32 + grp * 16);
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            const int y = y0 + s;
-            float* out = s ? out1 : out0;
+              for (int qq = 0; qq < 4; ++qq) d4[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
+            } else {
 #pragma unroll
-            for (int o = 0; o < 33; ++o) out[o] += sX[(m * 2 + s) * 33 + o];
-            if ((y < P.H) && (x < P.W)) {
-              const size_t pix = ((size_t)img * P.H + y) * P.W + x;
-              P.prob[pix] = 1.f / (1.f + expf(-out[32]));
-              if (P.heads_R == 32) {
-                float4* d4 = reinterpret_cast<float4*>(P.dist + pix * 32);
-#pragma unroll
-                for (int qq = 0; qq < 8; ++qq) d4[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
-              } else {
-#pragma unroll
-                for (int o = 0; o < 32; ++o) if (o < P.heads_R) P.dist[pix * P.heads_R + o] = out[o];
-              }
+              for (int o = 0; o < 16; ++o) if (grp * 16 + o < P.heads_R) P.dist[pix * P.heads_R + grp * 16 + o] = out[o];
             }
           }
         }
@@ -1322,8 +1324,8 @@ static int launch_tc4_impl(const CUtensorMap& a0h, const CUtensorMap& a0l, const
                            const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
   using C = TcCfg4<N>;
   const int n_cb = P.c_total / C::KC;
-  const int n_b_slots = WRES ? 9 * n_cb : (FUSE ? 3 : C::B_STAGES);
-  const int smem = C::SMEM_FIXED + n_b_slots * C::B_STAGE + (FUSE ? (36 + N + 128 * 2 * 33) * 4 : 0);
+  const int n_b_slots = WRES ? 9 * n_cb : C::B_STAGES;
+  const int smem = C::SMEM_FIXED + n_b_slots * C::B_STAGE + (FUSE ? (36 + N + N * 36) * 4 : 0);
   if (smem > 227 * 1024) { sdb::set_error("conv_tc4: shared memory budget exceeded"); return 1; }
   static int attr = 0;
   if (attr < smem) { SDB_CUDA(cudaFuncSetAttribute((k_conv_tc4<N, FUSE, WRES>), cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr = smem; }
@@ -1469,7 +1471,6 @@ extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, in
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
   P.fuse_w = d_heads_w; P.fuse_b = d_heads_b; P.dbg = g_tc_dbg;
-  SDB_CUDA(cudaMemcpyToSymbolAsync(c_fuse_w, d_heads_w, sizeof(float) * 128 * 36, 0, cudaMemcpyDeviceToDevice, st));
   return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
 

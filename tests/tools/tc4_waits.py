@@ -30,3 +30,21 @@ def run(h, w, c0, c1, cout):
 for cfg in [(1024, 1024, 0, 32, 32), (1024, 1024, 32, 32, 32), (1024, 1024, 0, 32, 128), (512, 512, 0, 64, 64)]:
     run(*cfg)
 L.check(lib.sdb_tc_error_check(L.stream_ptr()))
+
+# fused features + heads
+h = w = 1024; cin = 32
+xs = torch.randn((2, 1, h, w, cin), device='cuda').half()
+ws = torch.randn((2, 9, 128, cin), device='cuda').half()
+b = torch.zeros(128, device='cuda'); hw = torch.randn((128, 36), device='cuda') * 0.05; hb = torch.zeros(36, device='cuda')
+prob = torch.empty((1, h, w), device='cuda'); dist = torch.empty((1, h, w, 32), device='cuda')
+def fused():
+    L.check(lib.sdb_conv3x3_heads_tc(L.ptr(None), L.ptr(None), 0, L.ptr(xs[0]), L.ptr(xs[1]), cin, 1, h, w, L.ptr(ws[0]), L.ptr(ws[1]), 1.0, L.ptr(b),
+                                     1, L.ptr(hw), L.ptr(hb), 32, L.ptr(prob), L.ptr(dist), L.stream_ptr()))
+for _ in range(2): fused()
+L.check(lib.sdb_tc_set_debug(L.ptr(dbg))); dbg.zero_()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record(); fused(); e1.record(); torch.cuda.synchronize()
+L.check(lib.sdb_tc_set_debug(L.ptr(None)))
+d = dbg.double().mean(0).cpu().numpy(); tiles = 8 * 512 / 148.0
+print("fused 32->128+heads: %.1f us | " % (1e3 * e0.elapsed_time(e1)) + "  ".join("%s %.0f" % (n, v / tiles) for n, v in zip(names[:7], d[:7])) + "  (cycles per tile)")
+L.check(lib.sdb_tc_error_check(L.stream_ptr()))
