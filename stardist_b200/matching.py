@@ -30,3 +30,67 @@ def relabel_sequential(label_field, offset=1):
     inverse_map[offset:] = labels0
     relabeled = forward_map[label_field]
     return relabeled, forward_map, inverse_map
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Detection metrics (stardist/matching.py:109-232).  Host-side evaluation helper: pairs ground-truth and predicted
+# objects by an optimal assignment on the IoU (or IoT / IoP) matrix and counts tp / fp / fn at a threshold.
+def _overlap_matrix(a, b):
+    """counts[i, j] = number of pixels with label i in a and j in b (labels already sequential, 0 = background)"""
+    na, nb = int(a.max()) + 1, int(b.max()) + 1
+    flat = a.ravel().astype(np.int64) * nb + b.ravel().astype(np.int64)
+    return np.bincount(flat, minlength=na * nb).reshape(na, nb)
+
+
+def _ratio(num, den):
+    out = np.zeros(np.broadcast(num, den).shape, np.float32)
+    np.divide(num, den, out=out, where=np.abs(den) > 1e-10)
+    return out
+
+
+def _criterion_scores(overlap, criterion):
+    if overlap.sum() == 0:
+        return overlap.astype(np.float32)
+    n_pred = overlap.sum(axis=0, keepdims=True)
+    n_true = overlap.sum(axis=1, keepdims=True)
+    if criterion == 'iou':
+        return _ratio(overlap, n_pred + n_true - overlap)
+    if criterion == 'iot':
+        return _ratio(overlap, n_true)
+    if criterion == 'iop':
+        return _ratio(overlap, n_pred)
+    raise ValueError("Matching criterion '%s' not supported." % criterion)
+
+
+def matching(y_true, y_pred, thresh=0.5, criterion='iou'):
+    """Matching(criterion, thresh, fp, tp, fn, precision, recall, accuracy, f1, n_true, n_pred, mean_true_score,
+    mean_matched_score, panoptic_quality) between two label images (stardist/matching.py:109-232)."""
+    from collections import namedtuple
+    from scipy.optimize import linear_sum_assignment
+    for name, y in (('y_true', y_true), ('y_pred', y_pred)):
+        if not (isinstance(y, np.ndarray) and np.issubdtype(y.dtype, np.integer) and (y.size == 0 or y.min() >= 0)):
+            raise ValueError("%s must be an array of non-negative integers." % name)
+    if y_true.shape != y_pred.shape:
+        raise ValueError("y_true and y_pred have different shapes")
+    thr = 0.0 if thresh is None else float(thresh)
+    yt = relabel_sequential(y_true)[0]
+    yp = relabel_sequential(y_pred)[0]
+    scores = _criterion_scores(_overlap_matrix(yt, yp), criterion)[1:, 1:]
+    n_true, n_pred = scores.shape
+    n_matched = min(n_true, n_pred)
+    tp, sum_matched = 0, 0.0
+    if n_matched > 0:
+        # maximise the number of pairs above the threshold, ties broken by the summed score (:185-190)
+        costs = -(scores >= thr).astype(float) - scores / (2 * n_matched)
+        ti, pi = linear_sum_assignment(costs)
+        ok = scores[ti, pi] >= thr
+        tp = int(np.count_nonzero(ok))
+        sum_matched = float(np.sum(scores[ti, pi][ok]))
+    fp, fn = n_pred - tp, n_true - tp
+    div = lambda a, b: (a / b) if abs(b) > 1e-10 else 0.0
+    fields = dict(criterion=criterion, thresh=thr, fp=fp, tp=tp, fn=fn,
+                  precision=(tp / (tp + fp) if tp > 0 else 0), recall=(tp / (tp + fn) if tp > 0 else 0),
+                  accuracy=(tp / (tp + fp + fn) if tp > 0 else 0), f1=((2 * tp) / (2 * tp + fp + fn) if tp > 0 else 0),
+                  n_true=n_true, n_pred=n_pred, mean_true_score=div(sum_matched, n_true),
+                  mean_matched_score=div(sum_matched, tp), panoptic_quality=div(sum_matched, tp + fp / 2 + fn / 2))
+    return namedtuple('Matching', fields.keys())(*fields.values())

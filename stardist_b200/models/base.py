@@ -129,13 +129,34 @@ class StarDistBase:
         # weights: explicit dict > <logdir>/weights.npz > seeded Glorot-uniform (Keras default init)
         if weights is None and self.logdir is not None and (self.logdir / 'weights.npz').exists():
             weights = load_weights_npz(self.logdir / 'weights.npz')
+        if weights is None and self.logdir is not None:
+            # Keras checkpoints of a trained reference model (csbdeep BaseModel._find_and_load_weights: best, then last)
+            for fname in (getattr(config, 'train_checkpoint', None) or 'weights_best.h5', 'weights_best.h5', 'weights_last.h5'):
+                if fname and (self.logdir / fname).exists():
+                    from ..io import h5lite
+                    weights = h5lite.read_keras_weights(str(self.logdir / fname))
+                    break
         if weights is None:
-            if self.logdir is not None and any((self.logdir / f).exists() for f in ('weights_best.h5', 'weights_last.h5')):
-                warnings.warn("Keras .h5 weights found but no HDF5 reader is available on this path; using random-init weights")
             weights = glorot_uniform_weights(config, seed=seed)
+        else:
+            self._check_weights(config, weights)
         self.weights = weights
         self._net = None
         self._stats = {}
+
+    @staticmethod
+    def _check_weights(config, weights):
+        """every conv / head layer of the architecture must be present with the expected kernel shape"""
+        from .weights import unet_layers
+        for l in unet_layers(config):
+            if l['kind'] not in ('conv', 'head'):
+                continue
+            if l['name'] not in weights:
+                raise ValueError("weights for layer '%s' are missing" % l['name'])
+            k = np.asarray(weights[l['name']][0])
+            want = tuple(l['k']) + (l['cin'], l['cout'])
+            if tuple(k.shape) != want:
+                raise ValueError("layer '%s': kernel shape %s, expected %s" % (l['name'], tuple(k.shape), want))
 
     # ------------------------------------------------------------------ properties
     @property

@@ -128,3 +128,68 @@ def test_unet_topology_param_counts():
     from stardist_b200.models.weights import glorot_uniform_weights, count_params
     assert count_params(glorot_uniform_weights(Config2D())) == 1406689
     assert count_params(glorot_uniform_weights(Config2D(grid=(2, 2)))) == 1425185  # == 2D_demo weights file
+
+
+def test_oracle_reproduces_reference_2d_demo_test():
+    """The reference pins its shipped 2D_demo model on its test image to matching(...) == (fp 5, tp 114, fn 11)
+    (stardist tests/test_model2D.py:92-106).  The oracle (torch-CPU U-Net restatement + reference C++ NMS + numpy label
+    painting) with those weights must reproduce exactly that: this pins the network restatement to a reference test."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import demo2d
+    from oracle import pipeline2d, ref_ext
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    import stardist_b200 as sd
+    from stardist_b200.utils import normalize
+    from stardist_b200.matching import matching
+    kwargs, weights, thr, img, mask = demo2d.load()
+    cfg = sd.Config2D(**kwargs)
+    assert sum(k.size + b.size for k, b in weights.values()) == 1425185
+    x = normalize(img, 1, 99.8)
+    labels, res = pipeline2d.predict_instances(cfg, weights, x, thr['prob'], thr['nms'])
+    assert labels.shape == img.shape and labels.max() == len(res['prob']) == len(res['points'])
+    st = matching(mask, labels, thresh=0.5)
+    assert (st.fp, st.tp, st.fn) == demo2d.REFERENCE_TEST_STATS
+
+
+def test_h5lite_reads_the_reference_weight_file():
+    """pure-Python HDF5 subset reader == the frozen fixture (only where /root/reference is mounted)"""
+    import sys, os
+    path = "/root/reference/models/examples/2D_demo/weights_best.h5"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import demo2d
+    from stardist_b200.io import h5lite
+    w = h5lite.read_keras_weights(path)
+    _, weights, _, _, _ = demo2d.load()
+    assert sorted(w) == sorted(weights)
+    for n in w:
+        assert np.array_equal(w[n][0], weights[n][0]) and np.array_equal(w[n][1], weights[n][1])
+    with pytest.raises(h5lite.H5Error):
+        h5lite.read_datasets(os.path.abspath(__file__))
+
+
+def test_matching_metrics():
+    from stardist_b200.matching import matching
+    y = np.zeros((100, 100), np.uint16); y[10:20, 10:20] = 1
+    st = matching(y, np.roll(y, 5, axis=0))
+    assert (st.fp, st.tp, st.fn) == (1, 0, 1) and st.n_true == 1 and st.n_pred == 1
+    st = matching(y, np.roll(y, 2, axis=0))
+    assert (st.fp, st.tp, st.fn) == (0, 1, 0) and abs(st.mean_matched_score - 80 / 120) < 1e-6
+
+
+def test_model_folder_with_keras_checkpoint_loads():
+    """StarDist2D(None, name, basedir) on a reference model folder: config.json + thresholds.json + weights_best.h5"""
+    import os
+    if not os.path.exists("/root/reference/models/examples/2D_demo/weights_best.h5"):
+        pytest.skip("reference tree not mounted")
+    import stardist_b200 as sd
+    m = sd.StarDist2D(None, name='2D_demo', basedir='/root/reference/models/examples')
+    assert tuple(m.config.grid) == (2, 2) and m.config.n_rays == 32
+    assert abs(m.thresholds.prob - 0.4861655269131771) < 1e-12 and m.thresholds.nms == 0.5
+    assert m.weights['conv2d_1'][0].shape == (3, 3, 1, 32) and m.weights['dist'][0].shape == (1, 1, 128, 32)
+    with pytest.raises(ValueError):
+        sd.StarDist2D(sd.Config2D(n_rays=16), name=None, basedir=None, weights=m.weights)
+

@@ -204,3 +204,29 @@ def test_predict_n_tiles_equals_untiled(sd, shape, n_tiles):
     assert np.mean(l1 != l2) < 5e-3
     with pytest.raises(ValueError):
         model.predict(img[..., None], axes='YXC', n_tiles=(1, 1, 2))
+
+
+def test_reference_2d_demo_model_reproduces_reference_test(sd):
+    """The reference's shipped `2D_demo` weights (tests/golden/demo2d.npz) on its test image through the product path:
+    matching(mask, labels, 0.5) must give the numbers the reference's own test pins, (fp, tp, fn) == (5, 114, 11)
+    (stardist tests/test_model2D.py:92-106), and the instances must equal the CPU oracle's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import demo2d
+    from stardist_b200.utils import normalize
+    from stardist_b200.matching import matching
+    kwargs, weights, thr, img, mask = demo2d.load()
+    cfg = sd.Config2D(**kwargs)
+    model = sd.StarDist2D(cfg, name=None, basedir=None, weights=weights)
+    model.thresholds = dict(prob=thr['prob'], nms=thr['nms'])
+    x = normalize(img, 1, 99.8)
+    prob, dist = model.predict(x, n_tiles=(2, 3))
+    assert prob.shape == dist.shape[:2] and dist.shape[-1] == cfg.n_rays
+    labels, polygons = model.predict_instances(x)
+    assert labels.shape == img.shape[:2]
+    assert labels.max() == len(polygons['coord']) == len(polygons['points']) == len(polygons['prob'])
+    st = matching(mask, labels, thresh=0.5)
+    assert (st.fp, st.tp, st.fn) == demo2d.REFERENCE_TEST_STATS
+    ref_labels, ref = pipeline2d.predict_instances(cfg, weights, x, thr['prob'], thr['nms'])
+    assert np.array_equal(polygons['points'], ref['points'])
+    assert np.mean(labels != ref_labels) < 1e-3
+
