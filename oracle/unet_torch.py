@@ -1,5 +1,6 @@
 """torch-CPU fp32 restatement of the reference network (stand-in for TF/Keras + csbdeep, which
-cannot be installed here).  TEST INFRASTRUCTURE ONLY.  [parity UNPINNED at tensor level]
+cannot be installed here).  TEST INFRASTRUCTURE ONLY.  [parity: pinned at whole-pipeline level for 2D by the
+reference's own test numbers on its shipped 2D_demo weights (tests/test_cpu_oracle.py); UNPINNED at tensor level]
 
 Follows model2d.py:310-349 / model3d.py:360-399 and csbdeep's unet_block topology:
 conv(padding='same')+bias+ReLU, MaxPooling, UpSampling (nearest), Concatenate([up, skip]),
