@@ -168,11 +168,6 @@ int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_
 int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
                    int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
                    int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream);
-/* halo-reuse variant: CTA tile 2 rows x 128 px, the halo is loaded once per 32-channel block and all nine
- * taps address it through shifted UMMA descriptors (boff_mode: descriptor base-offset convention) */
-int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
-                    int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
-                    int relu, int up2x, int boff_mode, void* out_hi, void* out_lo, sdb_stream_t stream);
 /* 1x1 heads on the tensor cores (one tap, K = cfeat): head weights [1][np][cfeat] split fp16, row 0 = prob,
  * rows 1..n_rays = dist, zero padded to np in {48, 80, 112, 144}; outputs fp32 */
 int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n, int h, int w, const void* w_hi, const void* w_lo,

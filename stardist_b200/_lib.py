@@ -45,7 +45,6 @@ def _declare(lib):
     lib.sdb_maxpool_nd.argtypes = [P] + [c_int] * 8 + [P, P]
     lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
     lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
-    lib.sdb_conv3x3_tc2.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, c_int, P, P, P]
     lib.sdb_heads_tc.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, P, P, P]
     lib.sdb_conv3x3_heads_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, P, P, c_int, P, P, P]
     lib.sdb_conv3x3_heads_tc.restype = c_int
@@ -65,7 +64,7 @@ def _declare(lib):
     for name in ("_LIB_non_maximum_suppression_2d", "_LIB_polygons_to_label_2d", "sdb_nms2d",
                  "sdb_polygons_to_label_2d", "sdb_dist_to_coord_2d", "sdb_threshold_sort",
                  "sdb_gather_candidates", "sdb_conv3x3_2d", "sdb_maxpool2x2_2d", "sdb_heads_2d",
-                 "sdb_device_info", "sdb_conv3x3_tc", "sdb_conv3x3_tc2", "sdb_heads_tc", "sdb_tc_error_check", "sdb_split_weights", "sdb_stem_split",
+                 "sdb_device_info", "sdb_conv3x3_tc", "sdb_heads_tc", "sdb_tc_error_check", "sdb_split_weights", "sdb_stem_split",
                  "sdb_maxpool_split", "sdb_heads_split", "sdb_polyhedron_to_label", "sdb_nms3d", "sdb_conv3_nd", "sdb_maxpool_nd"):
         getattr(lib, name).restype = c_int
     # optional (added as the build widens)

@@ -11,16 +11,22 @@
 // in TMEM (each fp16 x fp16 product is exact in fp32; the dropped lo*Wlo term is ~2^-22).
 // Compared with 3xTF32 this doubles the MMA rate (kind::f16) and needs no in-kernel split pass.
 //
-// Mapping: CTA tile = 8x16 output pixels (M = 128, one TMEM lane per pixel) x all Cout (N <= 256).
-//   K loop over (tap, channel block): the A operand of a tap is ONE 4-D TMA box load
-//   {KC channels, 16 x, 8 y, 1 image} at coordinates shifted by the tap; out-of-bounds
-//   elements are zero-filled by TMA == the 'same' zero padding.  Rows of KC fp16 (128 B or 64 B)
-//   land in the K-major SWIZZLE_128B / SWIZZLE_64B layout that the UMMA descriptor expects.
+// Three kernels share the operand layout (K-major SWIZZLE_128B / SWIZZLE_64B rows written by TMA, one TMEM lane per
+// output pixel, M = 128):
+//   k_conv_tc  : one 8x16-pixel tile per CTA; K loop over (tap, channel block), the A operand of a tap is one 4-D TMA box
+//                {KC channels, 16 x, 8 y, 1 image} at tap-shifted coordinates (out-of-bounds elements are zero-filled by
+//                TMA == the 'same' zero padding).  Kept for Cout = 256.
+//   k_conv_tc3 : the same tiles, persistent CTAs, TMA ring running across tiles, two TMEM accumulator buffers, merged
+//                hi/lo weight tile (two MMAs per k-step instead of three); also the 1x1 heads for n_rays > 32.
+//   k_conv_tc4 : persistent, tile = 2 image rows x 128 pixels, halo loaded once per 32-channel block and the nine taps
+//                addressed by shifted descriptors, weights resident in shared memory where they fit; optionally the
+//                1x1 heads fused into the epilogue (the network's last convolution).  Used for Cin <= 64.
 //   B operand = weights [tap][Cout][Cin] (K-major), 3-D TMA box {KC, N, 1}.
-//   The decoder's Concatenate([UpSampling(x), skip]) is two activation sources on the K axis; the
-//   up-sampled source is materialised by its producer's epilogue (each pixel written 2x2).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer (one elected
-//   lane), warps 2..5 = epilogue (tcgen05.ld -> bias/ReLU -> hi/lo split -> 16 B global stores).
+//   The decoder's Concatenate([UpSampling(x), skip]) is two activation sources on the K axis; the up-sampled source is
+//   materialised by its producer's epilogue (each pixel written 2x2).
+// Warp roles: warp 0 = TMA producer (halos / operand tiles), warp 1 = TMEM alloc + MMA issue (one elected lane of the
+//   converged warp), warps 2.. = epilogue (tcgen05.ld -> bias/ReLU -> hi/lo split -> 16 B global stores, or the fused heads),
+//   k_conv_tc4: last warp = weight TMA.
 // All mbarrier waits are bounded (a hang would cost a GPU-box strike): on timeout an error flag is
 // raised and the kernel drains.
 #include <cuda.h>
@@ -528,207 +534,23 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
   }
 }
 
-// ---------------------------------------------------------------------------------- v2: halo-reuse strips
-// CTA tile = S image rows x 128 pixels.  For every 32-channel block the (S+2) x 130 pixel halo is
-// loaded ONCE (one 4-D TMA box per plane) and all 9 taps read it through shifted UMMA descriptors
-// (rows of a strip are contiguous 64-byte rows of the halo, so tap (dy,dx) is just a different start
-// address); only the weights are streamed per tap.  L2->SMEM traffic per output pixel drops ~4x
-// versus k_conv_tc, which was bound by exactly that traffic (profiles/r01b).  S strips share each
-// weight tile; accumulators: S x N TMEM columns.
-template <int N, int S>
-struct TcCfg2 {
-  static constexpr int KC = 32, ROWB = 64;
-  static constexpr int HROWS = (S + 2) * 130;
-  static constexpr int A_PLANE = ((HROWS * ROWB + 1023) / 1024) * 1024;
-  static constexpr int A_STAGE = 2 * A_PLANE;
-  static constexpr int A_STAGES = 2;
-  static constexpr int B_STAGE = 2 * N * ROWB;
-  static constexpr int B_STAGES = (N >= 256) ? 2 : 4;
-  static constexpr int SMEM = A_STAGES * A_STAGE + B_STAGES * B_STAGE + 1024 + 256;
-  static constexpr int TMEM_COLS = (S * N <= 32) ? 32 : (S * N <= 64 ? 64 : (S * N <= 128 ? 128 : (S * N <= 256 ? 256 : 512)));
-  static constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  static_assert(S * N <= 512, "accumulators exceed TMEM");
-};
-
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, int boff_mode) {
+// K-major SWIZZLE_64B descriptor (rows of 64 bytes, 8-row atoms of 512 B).  Tap-shifted start addresses are multiples
+// of 64 B, not of the atom: the swizzle is a function of the absolute shared-memory address bits, which TMA (writer) and
+// the MMA (reader) both apply, so no base-offset correction is needed (validated against fp64 convolutions).
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr, int /*unused*/) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(512 >> 4) << 32;                      // SBO: 8 rows x 64 B
   d |= (uint64_t)1 << 46;
-  if (boff_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;
   d |= (uint64_t)4 << 61;                               // SWIZZLE_64B
   return d;
 }
 
-template <int N, int S>
-__global__ void __launch_bounds__(192, 1)
-k_conv_tc2(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
-           const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
-           const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P, int boff_mode) {
-  using C = TcCfg2<N, S>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* smA = smem;
-  unsigned char* smB = smem + C::A_STAGES * C::A_STAGE;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smB + C::B_STAGES * C::B_STAGE);
-  uint64_t* a_empty = a_full + C::A_STAGES;
-  uint64_t* b_full = a_empty + C::A_STAGES;
-  uint64_t* b_empty = b_full + C::B_STAGES;
-  uint64_t* accum_bar = b_empty + C::B_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = blockIdx.x * 128, y0 = blockIdx.y * S, img = blockIdx.z;
-  const int n_cb = P.c_total / C::KC;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < C::A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    mbar_init(accum_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      bool ok = true;
-      int bi = 0;
-      for (int cb = 0; cb < n_cb && ok; ++cb) {
-        const int sa = cb % C::A_STAGES;
-        if (cb >= C::A_STAGES && !mbar_wait(&a_empty[sa], ((cb / C::A_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 11u); break; }
-        const int ch = cb * C::KC;
-        unsigned char* sta = smA + sa * C::A_STAGE;
-        mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
-        if (ch < P.c_src0) {
-          tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, img);
-          tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, img);
-        } else {
-          tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
-          tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
-        }
-        for (int tap = 0; tap < 9; ++tap, ++bi) {
-          const int sb = bi % C::B_STAGES;
-          if (bi >= C::B_STAGES && !mbar_wait(&b_empty[sb], ((bi / C::B_STAGES) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
-          unsigned char* stb = smB + sb * C::B_STAGE;
-          mbar_expect_tx(&b_full[sb], C::B_STAGE);
-          tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
-          tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[sb], ch, 0, tap);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      bool ok = true;
-      int bi = 0;
-      for (int cb = 0; cb < n_cb && ok; ++cb) {
-        const int sa = cb % C::A_STAGES;
-        if (!mbar_wait(&a_full[sa], (cb / C::A_STAGES) & 1)) { atomicExch(P.error_flag, 13u); break; }
-        const uint32_t a_hi = smem_u32(smA + sa * C::A_STAGE), a_lo = a_hi + C::A_PLANE;
-        for (int tap = 0; tap < 9; ++tap, ++bi) {
-          const int sb = bi % C::B_STAGES;
-          if (!mbar_wait(&b_full[sb], (bi / C::B_STAGES) & 1)) { atomicExch(P.error_flag, 14u); ok = false; break; }
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t b_hi = smem_u32(smB + sb * C::B_STAGE), b_lo = b_hi + N * C::ROWB;
-          const int dy = tap / 3, dx = tap % 3;
-#pragma unroll
-          for (int s = 0; s < S; ++s) {
-            const uint32_t roff = (uint32_t)((s + dy) * 130 + dx) * C::ROWB;
-#pragma unroll
-            for (int ks = 0; ks < C::KC / 16; ++ks) {
-              const uint32_t koff = ks * 32;
-              const uint64_t dah = make_desc_sw64(a_hi + roff + koff, boff_mode), dal = make_desc_sw64(a_lo + roff + koff, boff_mode);
-              const uint64_t dbh = make_desc_sw64(b_hi + koff, 0), dbl = make_desc_sw64(b_lo + koff, 0);
-              const uint32_t acc = (cb | tap | ks) ? 1u : 0u;
-              umma_f16(tmem_base + s * N, dah, dbh, C::IDESC, acc);
-              umma_f16(tmem_base + s * N, dal, dbh, C::IDESC, 1u);
-              umma_f16(tmem_base + s * N, dah, dbl, C::IDESC, 1u);
-            }
-          }
-          tcgen05_commit(&b_empty[sb]);
-        }
-        tcgen05_commit(&a_empty[sa]);
-      }
-      tcgen05_commit(accum_bar);
-    }
-  } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int x = x0 + m;
-    const bool ok = mbar_wait(accum_bar, 0);
-    if (!ok) atomicExch(P.error_flag, 15u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (ok) {
-#pragma unroll 1
-      for (int s = 0; s < S; ++s) {
-        const int y = y0 + s;
-        const bool in_img = (y < P.H) && (x < P.W);
-#pragma unroll 1
-        for (int c0 = 0; c0 < N; c0 += 32) {
-          uint32_t r[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * N + c0);
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                       : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (in_img) {
-            __align__(16) __half hi[32];
-            __align__(16) __half lo[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + c0 + j);
-              if (P.relu) v = fmaxf(v, 0.f);
-              const __half h = __float2half_rn(v);
-              hi[j] = h;
-              lo[j] = __float2half_rn(v - __half2float(h));
-            }
-            if (!P.up2x) {
-              const size_t off = (((size_t)img * P.H + y) * P.W + x) * N + c0;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
-                reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
-              }
-            } else {
-              const int H2 = 2 * P.H, W2 = 2 * P.W;
-#pragma unroll
-              for (int rep = 0; rep < 4; ++rep) {
-                const size_t off = (((size_t)img * H2 + (2 * y + (rep >> 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
-                  reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
-                }
-              }
-            }
-          }
-        }
-      }
-    }
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
-  }
-}
-
 // ---------------------------------------------------------------------------------- v4: persistent + halo reuse
-// k_conv_tc2's data movement (the (S+2) x 130 pixel halo of a 32-channel block is loaded ONCE, the nine taps
-// are shifted UMMA descriptors into it) with k_conv_tc3's schedule (persistent CTAs, TMA ring running across
+// Data movement: the (S+2) x 130 pixel halo of a 32-channel block is loaded ONCE (one 4-D TMA box per plane) and the
+// nine taps are shifted UMMA descriptors into it (rows of a strip are contiguous 64-byte rows of the halo, so tap
+// (dy,dx) is just a different start address); schedule as in k_conv_tc3 (persistent CTAs, TMA ring running across
 // tiles, two TMEM accumulator buffers, merged hi/lo weight tile where the columns allow it).  For the
 // high-resolution, few-channel layers (Cin <= 64) the per-tap A re-fetch of k_conv_tc/k_conv_tc3 made them
 // L2->SMEM bound (180 KB per 128 pixels at Cin = 32); here it is ~50 KB.
@@ -1352,23 +1174,6 @@ static int launch_tc4(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUte
   return launch_tc4_impl<N, FUSE, false>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st);
 }
 
-template <int N, int S>
-static int launch_tc2(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
-                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, int boff_mode, cudaStream_t st) {
-  using C = TcCfg2<N, S>;
-  static bool attr = false;
-  if (!attr) { SDB_CUDA(cudaFuncSetAttribute(k_conv_tc2<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM)); attr = true; }
-  dim3 grid(cdiv(P.W, 128), cdiv(P.H, S), n_img);
-  sdb::ProfSpan sp;
-  sdb::profile_begin("conv_tc", st, &sp);
-  k_conv_tc2<N, S><<<grid, 192, C::SMEM, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, boff_mode);
-  sdb::profile_end("conv_tc", st, &sp);
-  sdb::profile_add_units("conv_tc", 2.0 * 9.0 * P.c_total * N * (double)P.H * P.W * n_img);
-  sdb::g_launch_count++;
-  SDB_CUDA(cudaGetLastError());
-  return 0;
-}
-
 static unsigned int* g_err_flag = nullptr;      // device flag shared by all launches
 
 }  // namespace
@@ -1474,33 +1279,7 @@ extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, in
   return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
 
-// halo-reuse variant (k_conv_tc2): same contract as sdb_conv3x3_tc; boff_mode selects how the UMMA
-// descriptor's base-offset field is filled for tap-shifted (non swizzle-atom-aligned) start addresses
-extern "C" int sdb_conv3x3_tc2(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
-                               int c_src1, int n, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
-                               int relu, int up2x, int boff_mode, void* out_hi, void* out_lo, sdb_stream_t stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  const int cin = c_src0 + c_src1;
-  if (cin % 32 || c_src0 % 32 || c_src1 % 32) { sdb::set_error("conv3x3_tc2: channel counts must be multiples of 32"); return 1; }
-  if (cout != 32 && cout != 64 && cout != 128 && cout != 256) { sdb::set_error("conv3x3_tc2: cout must be 32/64/128/256"); return 1; }
-  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
-  constexpr int S = 2;
-  CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
-  if (make_act_map2(&a1h, (const __half*)src1_hi, n, h, w, c_src1, S + 2) || make_act_map2(&a1l, (const __half*)src1_lo, n, h, w, c_src1, S + 2)) return 1;
-  if (c_src0 > 0) {
-    if (make_act_map2(&a0h, (const __half*)src0_hi, n, h, w, c_src0, S + 2) || make_act_map2(&a0l, (const __half*)src0_lo, n, h, w, c_src0, S + 2)) return 1;
-  } else { a0h = a1h; a0l = a1l; }
-  if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32)) return 1;
-  ConvParams P;
-  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg;
-  if (cout == 32) return launch_tc2<32, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
-  if (cout == 64) return launch_tc2<64, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
-  if (cout == 128) return launch_tc2<128, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
-  return launch_tc2<256, S>(a0h, a0l, a1h, a1l, wh, wl, P, n, boff_mode, st);
-}
-
-// A/B switch for tests and profiling: 1 = one-tile-per-CTA kernel, 3 = persistent kernel (default)
+// A/B switch for tests and profiling: 0 = auto (default), 1 = one tile per CTA, 3 = persistent, 4 = persistent + halo reuse
 extern "C" int sdb_tc_set_variant(int variant) {
   if (variant != 0 && variant != 1 && variant != 3 && variant != 4) { sdb::set_error("tc_set_variant: 0 (auto), 1, 3 or 4"); return 1; }
   g_tc_variant = variant;

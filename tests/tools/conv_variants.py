@@ -1,5 +1,5 @@
-"""experiment: does the halo-reuse tcgen05 conv (k_conv_tc2) agree with a float64 convolution, and which
-UMMA base-offset convention is right for tap-shifted descriptors?"""
+"""the three tcgen05 conv kernels (one tile per CTA / persistent / persistent + halo reuse) against a float64 convolution of
+the same split operands, and their timings on the layer shapes of the 1024x1024 forward pass"""
 import sys, os, time
 import numpy as np, torch, torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -28,11 +28,8 @@ def run(h, w, c0, c1, cout, relu, up2x, mode):
     out = torch.zeros((2, 2, oh, ow, cout), dtype=torch.float16, device='cuda')
     args = (L.ptr(src0[0]) if c0 else L.ptr(None), L.ptr(src0[1]) if c0 else L.ptr(None), c0, L.ptr(src1[0]), L.ptr(src1[1]), c1,
             2, h, w, L.ptr(ws[0]), L.ptr(ws[1]), wsc, L.ptr(b), cout, relu, up2x)
-    if mode < 0:
-        L.check(lib.sdb_tc_set_variant(-mode))
-        L.check(lib.sdb_conv3x3_tc(*args, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
-    else:
-        L.check(lib.sdb_conv3x3_tc2(*args, mode, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
+    L.check(lib.sdb_tc_set_variant(-mode))
+    L.check(lib.sdb_conv3x3_tc(*args, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
     L.check(lib.sdb_tc_error_check(L.stream_ptr()))
     got = out[0].double() + out[1].double()
     y = F.conv2d(x_eff.permute(0, 3, 1, 2), k_eff.permute(3, 2, 0, 1), b.double(), padding=1)
@@ -58,10 +55,8 @@ def bench(h, w, c0, c1, cout, mode, reps=5):
     args = (L.ptr(src0[0]) if c0 else L.ptr(None), L.ptr(src0[1]) if c0 else L.ptr(None), c0, L.ptr(src1[0]), L.ptr(src1[1]), c1,
             1, h, w, L.ptr(ws[0]), L.ptr(ws[1]), 1.0, L.ptr(b), cout, 1, 0)
     def go():
-        if mode < 0:
-            L.check(lib.sdb_tc_set_variant(-mode))
-            L.check(lib.sdb_conv3x3_tc(*args, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
-        else: L.check(lib.sdb_conv3x3_tc2(*args, mode, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
+        L.check(lib.sdb_tc_set_variant(-mode))
+        L.check(lib.sdb_conv3x3_tc(*args, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
     for _ in range(2): go()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
