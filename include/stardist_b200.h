@@ -156,6 +156,11 @@ int sdb_conv3_nd(const float* d_in, const float* d_in_lo, int n, int d, int h, i
                  int cin_lo, int uz, int uy, int ux, const float* d_weight, const float* d_bias, int cout,
                  int kz, int relu, float* d_out, sdb_stream_t stream);
 int sdb_maxpool_nd(const float* d_in, int n, int d, int h, int w, int c, int pz, int py, int px, float* d_out, sdb_stream_t stream);
+/* ResNet backbone (model3d.py:402-447): convolution with arbitrary kernel extent and strides under TensorFlow's
+ * padding='same' rule (asymmetric: pad_before = pad_total / 2), fp32 CUDA cores; residual add (+ ReLU). */
+int sdb_conv_generic_nd(const float* d_in, int n, int d, int h, int w, int cin, const float* d_w, const float* d_b, int cout,
+                        int kz, int ky, int kx, int sz, int sy, int sx, int relu, float* d_out, sdb_stream_t stream);
+int sdb_add_act(const float* d_a, const float* d_b, long long n, int relu, float* d_out, sdb_stream_t stream);
 
 /* 1x1 heads: prob = sigmoid(x.Wp+bp) [npix], dist = x.Wd+bd [npix*n_rays] */
 int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_wp, const float* d_bp,

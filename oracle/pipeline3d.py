@@ -49,7 +49,25 @@ def instances(config, rays, img_shape, proba, dista, points, nms_thresh):
     return labels, dict(dist=disti, points=points, prob=probi)
 
 
-def predict_instances(config, rays, img, prob_thresh, nms_thresh, cand_from):
-    prob, dist = cand_from._last_maps()
+def predict(config, weights, img):
+    """img [D,H,W] (single channel) -> prob / dist of the reflect-padded volume (base.py:371-443; the volume is padded
+    at the end to a multiple of pool^depth*grid for the U-Net, of grid for the ResNet, model3d.py:676-688)"""
+    if getattr(config, 'backbone', 'unet') == 'resnet':
+        div = tuple(config.grid)
+    else:
+        div = tuple(p ** config.unet_n_depth * g for p, g in zip(config.unet_pool, config.grid))
+    x = np.asarray(img, np.float32)
+    x = np.pad(x, [(0, (d - s % d) % d) for s, d in zip(x.shape, div)], mode='reflect')
+    prob, dist = unet_torch.forward(config, weights, x[np.newaxis, ..., np.newaxis])
+    return prob[0], dist[0]
+
+
+def predict_instances(config, rays, img, prob_thresh, nms_thresh, cand_from=None, weights=None):
+    """cand_from: a product model whose device prob/dist maps are used (integer post-processing compared on identical
+    floats); otherwise the torch-CPU network runs on `weights`"""
+    if cand_from is not None:
+        prob, dist = cand_from._last_maps()
+    else:
+        prob, dist = predict(config, weights, img)
     proba, dista, points = candidates(config, prob, dist, img.shape, prob_thresh)
     return instances(config, rays, img.shape, proba, dista, points, nms_thresh)

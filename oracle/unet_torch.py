@@ -12,8 +12,52 @@ import torch
 import torch.nn.functional as F
 
 
+def _conv_same_tf(t, kt, bt, stride):
+    """TensorFlow padding='same' for arbitrary strides: out = ceil(in/s), pad_total = max((out-1)*s + k - in, 0),
+    pad_before = pad_total // 2 (the remainder goes behind) -- asymmetric for even inputs with stride 2."""
+    pads = []
+    for dim in reversed(range(3)):            # F.pad wants the last dimension first
+        n_in, k, s = t.shape[2 + dim], kt.shape[2 + dim], stride[dim]
+        n_out = -(-n_in // s)
+        total = max((n_out - 1) * s + k - n_in, 0)
+        pads += [total // 2, total - total // 2]
+    return F.conv3d(F.pad(t, pads), kt, bt, stride=tuple(stride))
+
+
+def forward_resnet(config, weights, x, dtype=torch.float32):
+    """ResNet backbone (model3d.py:402-447 + csbdeep resnet_block): x numpy [N,D,H,W,Cin] -> (prob, dist) numpy"""
+    from stardist_b200.models.weights import resnet_layers
+    t = torch.from_numpy(np.ascontiguousarray(x)).to(dtype).permute(0, 4, 1, 2, 3).contiguous()
+
+    def W(name):
+        k, b = weights[name]
+        return torch.from_numpy(k).to(dtype).permute(4, 3, 0, 1, 2).contiguous(), torch.from_numpy(b).to(dtype)
+
+    block_in = shortcut = None
+    for l in resnet_layers(config):
+        if l['kind'] == 'block_begin':
+            block_in, shortcut = t, None
+        elif l['kind'] == 'conv':
+            kt, bt = W(l['name'])
+            y = _conv_same_tf(block_in if l['src'] == 'block_in' else t, kt, bt, l['stride'])
+            if l['act'] == 'relu': y = F.relu(y)
+            if l['dst'] == 'shortcut': shortcut = y
+            else: t = y
+        elif l['kind'] == 'block_end':
+            t = (block_in if shortcut is None else shortcut) + t
+            if l['act'] == 'relu': t = F.relu(t)
+        elif l['kind'] == 'head':
+            break
+    kp, bp = W('prob'); kd, bd = W('dist')
+    prob = torch.sigmoid(F.conv3d(t, kp, bp))[:, 0]
+    dist = F.conv3d(t, kd, bd).permute(0, 2, 3, 4, 1)
+    return prob.float().numpy(), dist.float().numpy()
+
+
 def forward(config, weights, x, dtype=torch.float32, return_features=False):
     """x: numpy [N, *spatial, Cin] channels-last -> (prob [N,*sp/g], dist [N,*sp/g,R]) numpy"""
+    if getattr(config, 'backbone', 'unet') == 'resnet':
+        return forward_resnet(config, weights, x, dtype=dtype)
     from stardist_b200.models.weights import unet_layers
     nd = config.n_dim
     conv = F.conv2d if nd == 2 else F.conv3d

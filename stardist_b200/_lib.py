@@ -43,6 +43,10 @@ def _declare(lib):
     lib.sdb_maxpool2x2_2d.argtypes = [P, c_int, c_int, c_int, c_int, P, P]
     lib.sdb_conv3_nd.argtypes = [P, P] + [c_int] * 9 + [P, P, c_int, c_int, c_int, P, P]
     lib.sdb_maxpool_nd.argtypes = [P] + [c_int] * 8 + [P, P]
+    lib.sdb_conv_generic_nd.argtypes = [P] + [c_int] * 5 + [P, P] + [c_int] * 8 + [P, P]
+    lib.sdb_conv_generic_nd.restype = c_int
+    lib.sdb_add_act.argtypes = [P, P, c_longlong, c_int, P, P]
+    lib.sdb_add_act.restype = c_int
     lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
     lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
     lib.sdb_heads_tc.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, P, P, P]

@@ -216,6 +216,55 @@ k_heads(const float* __restrict__ feat, long long npix, const float* __restrict_
   if (threadIdx.x < 32 && p0 + threadIdx.x < npix) prob[p0 + threadIdx.x] = sO[threadIdx.x * NO];
 }
 
+
+// ---------------------------------------------------------------------------------- generic convolution (ResNet backbone)
+// Arbitrary odd/even kernel extent and stride with TensorFlow's padding='same' rule (stardist/models/model3d.py:402-447
+// builds the ResNet from Conv3D(7^3), Conv3D(3^3, strides=pool) and Conv3D(1^3, strides=pool) layers):
+//   out = ceil(in / stride),  pad_total = max((out - 1) * stride + k - in, 0),  pad_before = pad_total / 2  (rest behind).
+// One thread per (output voxel, output channel); consecutive threads = consecutive channels (coalesced weights, broadcast
+// activations).  Functional path for the few layers the 3x3x3 stride-1 kernel does not cover; not tuned.
+struct GenericConv {
+  int n, d, h, w, cin, cout;
+  int kz, ky, kx, sz, sy, sx;
+  int od, oh, ow, pz, py, px;
+  int relu;
+};
+__global__ void __launch_bounds__(256) k_conv_generic(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                      GenericConv P, float* __restrict__ out) {
+  const long long total = (long long)P.n * P.od * P.oh * P.ow * P.cout;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(e % P.cout);
+    long long v = e / P.cout;
+    const int ox = (int)(v % P.ow); v /= P.ow;
+    const int oy = (int)(v % P.oh); v /= P.oh;
+    const int oz = (int)(v % P.od); const int img = (int)(v / P.od);
+    float acc = bias[co];
+    for (int a = 0; a < P.kz; ++a) {
+      const int iz = oz * P.sz - P.pz + a;
+      if (iz < 0 || iz >= P.d) continue;
+      for (int b = 0; b < P.ky; ++b) {
+        const int iy = oy * P.sy - P.py + b;
+        if (iy < 0 || iy >= P.h) continue;
+        for (int c = 0; c < P.kx; ++c) {
+          const int ix = ox * P.sx - P.px + c;
+          if (ix < 0 || ix >= P.w) continue;
+          const float* ip = in + ((((size_t)img * P.d + iz) * P.h + iy) * P.w + ix) * P.cin;
+          const float* wp = wgt + ((size_t)((a * P.ky + b) * P.kx + c) * P.cin) * P.cout + co;
+          for (int ci = 0; ci < P.cin; ++ci) acc = fmaf(ip[ci], wp[(size_t)ci * P.cout], acc);
+        }
+      }
+    }
+    if (P.relu) acc = fmaxf(acc, 0.f);
+    out[e] = acc;
+  }
+}
+__global__ void k_add_act(const float* __restrict__ a, const float* __restrict__ b, long long n, int relu, float* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float v = a[e] + b[e];
+    out[e] = relu ? fmaxf(v, 0.f) : v;
+  }
+}
+
 }  // namespace
 
 // N-d convolution entry point: kz = 1 (2-D, d must be 1) or 3 (3-D).  (uz,uy,ux): up-sampling factors of
@@ -289,5 +338,28 @@ extern "C" int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, cons
   if (!attr_set) { SDB_CUDA(cudaFuncSetAttribute(k_heads<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
   if (smem > 200 * 1024) { sdb::set_error("heads_2d: n_rays too large"); return 1; }
   SDB_LAUNCH((k_heads<128>), cdiv(npix, 32), 128, smem, st, d_feat, npix, d_wp, d_bp, d_wd, d_bd, n_rays, d_prob, d_dist);
+  return 0;
+}
+
+// generic N-d convolution with TF 'same' padding and strides; in [n,d,h,w,cin] fp32, weights (kz,ky,kx,cin,cout), out
+// [n,ceil(d/sz),ceil(h/sy),ceil(w/sx),cout].  2-D: d = kz = sz = 1.
+extern "C" int sdb_conv_generic_nd(const float* d_in, int n, int d, int h, int w, int cin, const float* d_w, const float* d_b, int cout,
+                                   int kz, int ky, int kx, int sz, int sy, int sx, int relu, float* d_out, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0 || d <= 0 || h <= 0 || w <= 0 || cin <= 0 || cout <= 0 || kz <= 0 || ky <= 0 || kx <= 0 || sz <= 0 || sy <= 0 || sx <= 0) {
+    sdb::set_error("conv_generic_nd: bad arguments"); return 1;
+  }
+  GenericConv P;
+  P.n = n; P.d = d; P.h = h; P.w = w; P.cin = cin; P.cout = cout; P.kz = kz; P.ky = ky; P.kx = kx; P.sz = sz; P.sy = sy; P.sx = sx; P.relu = relu;
+  P.od = (d + sz - 1) / sz; P.oh = (h + sy - 1) / sy; P.ow = (w + sx - 1) / sx;
+  P.pz = std::max((P.od - 1) * sz + kz - d, 0) / 2; P.py = std::max((P.oh - 1) * sy + ky - h, 0) / 2; P.px = std::max((P.ow - 1) * sx + kx - w, 0) / 2;
+  const long long total = (long long)n * P.od * P.oh * P.ow * cout;
+  SDB_LAUNCH(k_conv_generic, (int)std::min<long long>(sdb::cdiv(total, 256), 148 * 64), 256, 0, st, d_in, d_w, d_b, P, d_out);
+  return 0;
+}
+extern "C" int sdb_add_act(const float* d_a, const float* d_b, long long n, int relu, float* d_out, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  SDB_LAUNCH(k_add_act, (int)std::min<long long>(sdb::cdiv(n, 256), 148 * 32), 256, 0, st, d_a, d_b, n, relu, d_out);
   return 0;
 }

@@ -147,8 +147,8 @@ class StarDistBase:
     @staticmethod
     def _check_weights(config, weights):
         """every conv / head layer of the architecture must be present with the expected kernel shape"""
-        from .weights import unet_layers
-        for l in unet_layers(config):
+        from .weights import net_layers
+        for l in net_layers(config):
             if l['kind'] not in ('conv', 'head'):
                 continue
             if l['name'] not in weights:

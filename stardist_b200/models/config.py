@@ -147,8 +147,15 @@ class Config3D(BaseConfig):
             self.unet_dropout = 0.0
             self.unet_prefix = ''
             self.net_conv_after_unet = 128
-        elif self.backbone == 'resnet':
-            raise NotImplementedError("the ResNet backbone is not implemented on the B200 path yet (SURVEY 8f rank 1)")
+        elif self.backbone == 'resnet':      # model3d.py:256-264
+            self.resnet_n_blocks = 4
+            self.resnet_kernel_size = 3, 3, 3
+            self.resnet_kernel_init = 'he_normal'
+            self.resnet_n_filter_base = 32
+            self.resnet_n_conv_per_block = 3
+            self.resnet_activation = 'relu'
+            self.resnet_batch_norm = False
+            self.net_conv_after_resnet = 128
         else:
             raise ValueError("backbone '%s' not supported." % self.backbone)
         self.net_input_shape = None, None, None, self.n_channel_in

@@ -14,7 +14,7 @@ from ..rays3d import rays_from_json
 from ..matching import relabel_sequential
 from .base import StarDistBase
 from .config import Config3D
-from .unet_device import UNetDeviceND
+from .unet_device import UNetDeviceND, ResNetDeviceND
 
 
 class StarDist3D(StarDistBase):
@@ -24,6 +24,8 @@ class StarDist3D(StarDistBase):
         super().__init__(config, name=name, basedir=basedir, **kwargs)
 
     def _build(self):
+        if self.config.backbone == 'resnet':
+            return ResNetDeviceND(self.config, self.weights)
         self.config.backbone == 'unet' or _raise(NotImplementedError(self.config.backbone))
         return UNetDeviceND(self.config, self.weights)
 
@@ -117,6 +119,10 @@ class StarDist3D(StarDistBase):
         return labels, res_dict
 
     def _axes_div_by(self, query_axes):
+        if self.config.backbone == 'resnet':      # model3d.py:686-688
+            query_axes = axes_check_and_normalize(query_axes)
+            grid_dict = dict(zip(self.config.axes.replace('C', ''), self.config.grid))
+            return tuple(grid_dict.get(a, 1) for a in query_axes)
         self.config.backbone == 'unet' or _raise(NotImplementedError())
         query_axes = axes_check_and_normalize(query_axes)
         assert len(self.config.unet_pool) == len(self.config.grid)

@@ -9,7 +9,7 @@ import os
 import numpy as np
 import torch
 from .. import _lib as L
-from .weights import unet_layers
+from .weights import unet_layers, resnet_layers
 
 
 class UNetDeviceND:
@@ -94,6 +94,73 @@ class UNetDeviceND:
 
 
 UNetDevice2D = UNetDeviceND
+
+
+class ResNetDeviceND(UNetDeviceND):
+    """3-D ResNet backbone (stardist/models/model3d.py:402-447, csbdeep resnet_block) on the fp32 CUDA-core kernels:
+    the stride-1 3^3 convolutions run on the tiled kernel of the U-Net path (sdb_conv3_nd), the 7^3 stem, the strided
+    3^3 convolution that opens a pooling block and the strided 1^3 shortcut projection on the generic kernel
+    (sdb_conv_generic_nd, TensorFlow 'same' padding), the residual sum on sdb_add_act."""
+
+    def __init__(self, config, weights, device=None):
+        L.require_cuda()
+        self.config = config
+        self.nd = config.n_dim
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        self.layers = resnet_layers(config)
+        self.w = {}
+        for name, (k, b) in weights.items():
+            self.w[name] = (torch.from_numpy(np.ascontiguousarray(k, dtype=np.float32)).to(self.device),
+                            torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device))
+        if config.n_classes is not None:
+            raise NotImplementedError("multi-class head is not supported yet")
+
+    def _conv_any(self, x, l):
+        lib = L.load()
+        k, b = self.w[l['name']]
+        relu = l['act'] == 'relu'
+        if l['act'] not in ('relu', 'linear'):
+            raise NotImplementedError("activation %s" % l['act'])
+        if tuple(l['k']) == (3, 3, 3) and tuple(l['stride']) == (1, 1, 1) and l['cin'] > 4:
+            return self._conv(x, None, l['name'], relu, (1, 1, 1))
+        n, d, h, w, cin = x.shape
+        kz, ky, kx = l['k']; sz, sy, sx = l['stride']
+        cout = k.shape[-1]
+        out = torch.empty((n, -(-d // sz), -(-h // sy), -(-w // sx), cout), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_conv_generic_nd(L.ptr(x), n, d, h, w, cin, L.ptr(k), L.ptr(b), cout, kz, ky, kx, sz, sy, sx,
+                                       1 if relu else 0, L.ptr(out), L.stream_ptr()))
+        return out
+
+    def forward(self, x):
+        lib = L.load()
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.dim() == 5
+        block_in = shortcut = None
+        for l in self.layers:
+            kind = l['kind']
+            if kind == 'block_begin':
+                block_in, shortcut = x, None
+            elif kind == 'conv':
+                y = self._conv_any(block_in if l['src'] == 'block_in' else x, l)
+                if l['dst'] == 'shortcut': shortcut = y
+                else: x = y
+            elif kind == 'block_end':
+                s = block_in if shortcut is None else shortcut
+                assert s.shape == x.shape
+                out = torch.empty_like(x)
+                L.check(lib.sdb_add_act(L.ptr(s), L.ptr(x), x.numel(), 1 if l['act'] == 'relu' else 0, L.ptr(out), L.stream_ptr()))
+                x, block_in, shortcut = out, None, None
+            elif kind == 'head':
+                break
+        feat = x
+        cf = feat.shape[-1]
+        npix = int(np.prod(feat.shape[:-1]))
+        R = self.config.n_rays
+        (wp, bp), (wd, bd) = self.w['prob'], self.w['dist']
+        prob = torch.empty(tuple(feat.shape[:-1]), dtype=torch.float32, device=x.device)
+        dist = torch.empty(tuple(feat.shape[:-1]) + (R,), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_heads_2d(L.ptr(feat), npix, cf, L.ptr(wp), L.ptr(bp), L.ptr(wd), L.ptr(bd), R,
+                                L.ptr(prob), L.ptr(dist), L.stream_ptr()))
+        return prob, dist
 
 
 def tc_weight_scale(k):

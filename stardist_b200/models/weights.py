@@ -63,11 +63,70 @@ def unet_layers(config):
     return layers
 
 
+def resnet_layers(config):
+    """Layer list of the 3-D ResNet backbone (stardist/models/model3d.py:402-447 + csbdeep.internals.blocks.resnet_block):
+      conv 7^3 (linear), conv 3^3 (linear), resnet_n_blocks x block(n_filter, pool), features conv 3^3 (+act), heads.
+      block: x = conv(k, strides=pool) + act; (n_conv_per_block - 2) x [conv(k) + act]; conv(k);
+             shortcut = conv(1^3, strides=pool)(inp) if pool > 1 or the channel count changes else inp;  out = act(shortcut + x)
+    Keras auto-names the convolutions conv3d_1, conv3d_2, ... in creation order (the projection after the main path).
+    entries: kind 'conv' (name, cin, cout, k, stride, act, src: 'cur' | 'block_in', dst: 'cur' | 'shortcut'),
+             'block_begin', 'block_end' (act), 'head'."""
+    nd = config.n_dim
+    nd == 3 or _raise_value("the ResNet backbone exists for 3-D models only")
+    if config.resnet_batch_norm:
+        raise NotImplementedError("resnet_batch_norm=True is not supported on this path")
+    k = tuple(int(v) for v in config.resnet_kernel_size)
+    act = config.resnet_activation
+    n_conv = int(config.resnet_n_conv_per_block)
+    n_conv >= 2 or _raise_value("required: resnet_n_conv_per_block >= 2")
+    layers, c, idx = [], config.n_channel_in, 0
+    nf = int(config.resnet_n_filter_base)
+
+    def conv(cin, cout, kk, stride=(1, 1, 1), a='linear', src='cur', dst='cur', name=None):
+        nonlocal idx
+        if name is None:
+            idx += 1
+            name = 'conv3d_%d' % idx
+        layers.append(dict(name=name, kind='conv', cin=cin, cout=cout, k=tuple(kk), stride=tuple(int(v) for v in stride), act=a, src=src, dst=dst))
+
+    conv(c, nf, (7, 7, 7)); conv(nf, nf, (3, 3, 3)); c = nf
+    pooled = np.array([1, 1, 1])
+    for _ in range(int(config.resnet_n_blocks)):
+        pool = 1 + (np.asarray(config.grid) > pooled)
+        pooled = pooled * pool
+        if any(p > 1 for p in pool):
+            nf *= 2
+        layers.append(dict(name='block_begin', kind='block_begin'))
+        conv(c, nf, k, stride=pool, a=act)
+        for _ in range(n_conv - 2):
+            conv(nf, nf, k, a=act)
+        conv(nf, nf, k)
+        if any(p != 1 for p in pool) or nf != c:
+            conv(c, nf, (1, 1, 1), stride=pool, src='block_in', dst='shortcut')
+        layers.append(dict(name='block_end', kind='block_end', act=act))
+        c = nf
+    if config.net_conv_after_resnet > 0:
+        conv(c, int(config.net_conv_after_resnet), k, a=act, name='features')
+        c = int(config.net_conv_after_resnet)
+    layers.append(dict(name='prob', kind='head', cin=c, cout=1, k=(1,) * nd, act='sigmoid'))
+    layers.append(dict(name='dist', kind='head', cin=c, cout=config.n_rays, k=(1,) * nd, act='linear'))
+    return layers
+
+
+def _raise_value(msg):
+    raise ValueError(msg)
+
+
+def net_layers(config):
+    """layer list of the configured backbone"""
+    return resnet_layers(config) if getattr(config, 'backbone', 'unet') == 'resnet' else unet_layers(config)
+
+
 def glorot_uniform_weights(config, seed=0):
     """dict name -> (kernel float32 (k..., Cin, Cout), bias float32 (Cout,)), seeded"""
     rng = np.random.default_rng(seed)
     w = {}
-    for l in unet_layers(config):
+    for l in net_layers(config):
         if l['kind'] not in ('conv', 'head'):
             continue
         k, cin, cout = l['k'], l['cin'], l['cout']

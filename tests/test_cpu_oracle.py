@@ -192,4 +192,36 @@ def test_model_folder_with_keras_checkpoint_loads():
     assert m.weights['conv2d_1'][0].shape == (3, 3, 1, 32) and m.weights['dist'][0].shape == (1, 1, 128, 32)
     with pytest.raises(ValueError):
         sd.StarDist2D(sd.Config2D(n_rays=16), name=None, basedir=None, weights=m.weights)
+    m3 = sd.StarDist3D(None, name='3D_demo', basedir='/root/reference/models/examples')
+    assert m3.config.backbone == 'resnet' and tuple(m3.config.grid) == (1, 2, 2) and m3.config.n_rays == 96
+    assert m3._axes_div_by('ZYX') == (1, 2, 2) and m3.weights['conv3d_1'][0].shape == (7, 7, 7, 1, 32)
+
+
+def test_oracle_reproduces_reference_3d_demo_test():
+    """3D_demo (ResNet backbone, 96 anisotropic rays, grid (1,2,2)) on the reference's test volume: the reference pins
+    matching(...) == (fp 0, tp 30, fn 21) (stardist tests/test_model3D.py:85-96); the oracle (torch-CPU ResNet restatement +
+    reference C++ NMS / polyhedron_to_label) must reproduce it."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import demo3d
+    from oracle import pipeline3d, ref_ext
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    import stardist_b200 as sd
+    from stardist_b200.utils import normalize
+    from stardist_b200.matching import matching
+    from stardist_b200.rays3d import rays_from_json
+    rays_json, kwargs, weights, thr, img, mask = demo3d.load()
+    rays = rays_from_json(rays_json)
+    cfg = sd.Config3D(rays=rays, **kwargs)
+    assert cfg.backbone == 'resnet' and sum(k.size + b.size for k, b in weights.values()) == 1547201
+    old = os.environ.get("OMP_NUM_THREADS")
+    os.environ["OMP_NUM_THREADS"] = "1"          # the reference's 3D NMS has a racy anisotropy sum
+    try:
+        labels, res = pipeline3d.predict_instances(cfg, rays, normalize(img, 1, 99.8), thr['prob'], thr['nms'], weights=weights)
+    finally:
+        if old is None: os.environ.pop("OMP_NUM_THREADS", None)
+        else: os.environ["OMP_NUM_THREADS"] = old
+    st = matching(mask, labels, thresh=0.5)
+    assert labels.shape == img.shape and (st.fp, st.tp, st.fn) == demo3d.REFERENCE_TEST_STATS
 

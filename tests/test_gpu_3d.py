@@ -143,3 +143,51 @@ def test_predict_3d_n_tiles_equals_untiled(sd):
     p1, d1 = model.predict(vol)
     p2, d2 = model.predict(vol, n_tiles=(1, 3, 2))
     assert p1.shape == p2.shape and np.array_equal(p1, p2) and np.array_equal(d1, d2)     # one (CUDA-core) kernel: bitwise
+
+
+def test_resnet_forward_vs_torch_fp32(sd):
+    """ResNet backbone (7^3 stem, strided block, 1^3 strided shortcut, residual adds) against the torch-CPU restatement,
+    odd sizes (TensorFlow 'same' padding is asymmetric for even inputs with stride 2)"""
+    import torch
+    from oracle import unet_torch
+    rays = sd.Rays_GoldenSpiral(8)
+    for shape, grid in (((9, 20, 22), (1, 2, 2)), ((8, 17, 12), (2, 2, 2)), ((7, 9, 11), (1, 1, 1))):
+        cfg = sd.Config3D(rays=rays, backbone='resnet', grid=grid, resnet_n_blocks=3)
+        model = sd.StarDist3D(cfg, name=None, basedir=None)
+        rng = np.random.default_rng(shape[1])
+        vol = rng.uniform(0, 1, shape).astype(np.float32)
+        x = torch.from_numpy(vol[None, ..., None]).cuda()
+        prob, dist = model.net.forward(x)
+        rp, rd = unet_torch.forward(cfg, model.weights, vol[None, ..., None])
+        p, d = prob.cpu().numpy(), dist.cpu().numpy()
+        assert p.shape == rp.shape and d.shape == rd.shape
+        assert np.max(np.abs(p - rp)) <= 1e-5 * max(1.0, np.max(np.abs(rp)))
+        assert np.max(np.abs(d - rd)) <= 1e-5 * max(1e-3, np.max(np.abs(rd))) + 1e-6
+
+
+def test_reference_3d_demo_model_reproduces_reference_test(sd):
+    """The reference's shipped 3D_demo checkpoint (tests/golden/demo3d.npz) on its test volume through the product path:
+    (fp, tp, fn) == (0, 30, 21) as pinned by stardist tests/test_model3D.py:85-96, instances equal to the CPU oracle's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import demo3d
+    from oracle import pipeline3d
+    from stardist_b200.utils import normalize
+    from stardist_b200.matching import matching
+    from stardist_b200.rays3d import rays_from_json
+    rays_json, kwargs, weights, thr, img, mask = demo3d.load()
+    rays = rays_from_json(rays_json)
+    cfg = sd.Config3D(rays=rays, **kwargs)
+    model = sd.StarDist3D(cfg, name=None, basedir=None, weights=weights)
+    model.thresholds = dict(prob=thr['prob'], nms=thr['nms'])
+    x = normalize(img, 1, 99.8)
+    prob, dist = model.predict(x, n_tiles=(1, 2, 2))
+    assert prob.shape == dist.shape[:3] and dist.shape[-1] == cfg.n_rays
+    labels, res = model.predict_instances(x)
+    assert labels.shape == img.shape[:3]
+    st = matching(mask, labels, thresh=0.5)
+    assert (st.fp, st.tp, st.fn) == demo3d.REFERENCE_TEST_STATS
+    os.environ["OMP_NUM_THREADS"] = "1"
+    ref_labels, ref = pipeline3d.predict_instances(cfg, rays, x, thr['prob'], thr['nms'], weights=weights)
+    assert np.array_equal(res['points'], ref['points'])
+    assert np.mean(labels != ref_labels) < 2e-3
+
