@@ -328,7 +328,7 @@ __device__ int hull_planes_warp(const double* pts, int n, Plane* out, int max_pl
   return nf;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counters, unsigned int pair_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned int n_pairs = min(counters[1], pair_cap);
@@ -343,8 +343,9 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
   uint32_t* edge_done = reinterpret_cast<uint32_t*>(smem_raw + off);
   off += (size_t)((A.R * A.R + 31) / 32) * 4;
   int16_t* stack = reinterpret_cast<int16_t*>(smem_raw + off);     // [3*4R]
-  __shared__ double red[4];
+  __shared__ double red[16];          // one slot per warp (up to 512 threads)
   __shared__ int sh_i[4];
+  __shared__ int sh_cnt;              // S5: running count of voxels inside both polyhedra
   __shared__ float c1[3], c2[3];
   for (int j = threadIdx.x; j < 3 * A.F; j += blockDim.x) sfaces[j] = A.faces[j];
 
@@ -393,7 +394,8 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       __syncthreads();
       if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
       __syncthreads();
-      m = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+      m = 0;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmax(m, red[i]);
       L = 4.0 * m + 1.0;
     }
     if (!infeasible) {
@@ -446,21 +448,35 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
     const int Nz = bb[1] - bb[0] + 1, Ny = bb[3] - bb[2] + 1, Nx = bb[5] - bb[4] + 1;
     const long long nv = (long long)Nz * Ny * Nx;
     const float overlap_maximal = (float)(den * (double)A.threshold);      // (A_min+1e-10)*threshold passed as float
-    int cnt = 0;
-    int first_hit = 0;
-    for (long long q = threadIdx.x; q < nv; q += blockDim.x) {
-      const int x = (int)(q % Nx), y = (int)((q / Nx) % Ny), z = (int)(q / ((long long)Nx * Ny));
-      const float fz = (float)(z + bb[0]), fy = (float)(y + bb[2]), fx = (float)(x + bb[4]);
-      if (sd3::inside_polyhedron(fz, fy, fx, c1, pv1, sfaces, A.F) && sd3::inside_polyhedron(fz, fy, fx, c2, pv2, sfaces, A.F)) {
-        cnt++; if (q == 0) first_hit = 1;
-      }
-    }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    // The reference loop returns as soon as the running count exceeds overlap_maximal (:1305-1330); the outcome only
+    // depends on min(full count, stop), so the block stops once its shared count reaches `stop`.
+    const long long stop_ll = (overlap_maximal < 0.f) ? 1 : (long long)floorf(overlap_maximal) + 1;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh_i[threadIdx.x >> 5] = cnt;
+    if (threadIdx.x == 0) { sh_cnt = 0; sh_i[3] = 0; }
+    __syncthreads();
+    int cnt = 0;
+    for (long long q0 = 0; q0 < nv; q0 += (long long)blockDim.x * 8) {
+      if ((long long)(*(volatile int*)&sh_cnt) >= stop_ll) break;
+      int local = 0;
+#pragma unroll 1
+      for (int u = 0; u < 8; ++u) {
+        const long long q = q0 + (long long)u * blockDim.x + threadIdx.x;
+        if (q >= nv) break;
+        const int x = (int)(q % Nx), y = (int)((q / Nx) % Ny), z = (int)(q / ((long long)Nx * Ny));
+        const float fz = (float)(z + bb[0]), fy = (float)(y + bb[2]), fx = (float)(x + bb[4]);
+        if (sd3::inside_polyhedron(fz, fy, fx, c1, pv1, sfaces, A.F) && sd3::inside_polyhedron(fz, fy, fx, c2, pv2, sfaces, A.F)) {
+          local++; if (q == 0) sh_i[3] = 1;
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+      if ((threadIdx.x & 31) == 0 && local) atomicAdd(&sh_cnt, local);
+      cnt += local;
+    }
+    (void)cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
-      const int full = sh_i[0] + sh_i[1] + sh_i[2] + sh_i[3];
+      const int full = sh_cnt;
+      const int first_hit = sh_i[3];
       // early exit emulation: the serial loop returns the first running count with (float)res > overlap_maximal
       int res;
       if (overlap_maximal < 0.f) res = (nv > 0) ? first_hit : 0;
@@ -555,7 +571,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
     SDB_LAUNCH(k_frontier, cdiv(n, 256), 256, 0, st, A, round, b_counters.as<unsigned int>());
     for (;;) {
       SDB_LAUNCH(k_pretest, cdiv(n, 128), 128, 0, st, A, round, b_pairs.as<int2>(), (unsigned int)pair_cap, b_counters.as<unsigned int>());
-      SDB_LAUNCH(k_heavy, 148 * 4, 128, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap);
+      SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap);
       if (cudaMemcpyAsync(h_pin, b_counters.p, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         sdb::set_error(std::string("nms3d: round failed: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; break;
       }
