@@ -161,6 +161,11 @@ int sdb_maxpool_nd(const float* d_in, int n, int d, int h, int w, int c, int pz,
 int sdb_conv_generic_nd(const float* d_in, int n, int d, int h, int w, int cin, const float* d_w, const float* d_b, int cout,
                         int kz, int ky, int kx, int sz, int sy, int sx, int relu, float* d_out, sdb_stream_t stream);
 int sdb_add_act(const float* d_a, const float* d_b, long long n, int relu, float* d_out, sdb_stream_t stream);
+/* multi-class head (model2d.py:339-347): prob_class = softmax over n_out = n_classes + 1 outputs of a 1x1 convolution of
+ * fp32 features [npix, cfeat] with weights [cfeat][n_out]; sdb_merge_split: split fp16 planes (hi, lo) -> fp32. */
+int sdb_class_head(const float* d_feat, long long npix, int cfeat, const float* d_w, const float* d_b, int n_out, float* d_out,
+                   sdb_stream_t stream);
+int sdb_merge_split(const void* d_hi, const void* d_lo, long long n, float* d_out, sdb_stream_t stream);
 
 /* 1x1 heads: prob = sigmoid(x.Wp+bp) [npix], dist = x.Wd+bd [npix*n_rays] */
 int sdb_heads_2d(const float* d_feat, long long npix, int cfeat, const float* d_wp, const float* d_bp,

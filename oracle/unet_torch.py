@@ -33,12 +33,13 @@ def forward_resnet(config, weights, x, dtype=torch.float32):
         k, b = weights[name]
         return torch.from_numpy(k).to(dtype).permute(4, 3, 0, 1, 2).contiguous(), torch.from_numpy(b).to(dtype)
 
-    block_in = shortcut = None
+    block_in = shortcut = base = None
     for l in resnet_layers(config):
         if l['kind'] == 'block_begin':
             block_in, shortcut = t, None
         elif l['kind'] == 'conv':
             kt, bt = W(l['name'])
+            if l['name'] == 'features': base = t
             y = _conv_same_tf(block_in if l['src'] == 'block_in' else t, kt, bt, l['stride'])
             if l['act'] == 'relu': y = F.relu(y)
             if l['dst'] == 'shortcut': shortcut = y
@@ -51,6 +52,8 @@ def forward_resnet(config, weights, x, dtype=torch.float32):
     kp, bp = W('prob'); kd, bd = W('dist')
     prob = torch.sigmoid(F.conv3d(t, kp, bp))[:, 0]
     dist = F.conv3d(t, kd, bd).permute(0, 2, 3, 4, 1)
+    if getattr(config, 'n_classes', None) is not None:
+        return prob.float().numpy(), dist.float().numpy(), _class_branch(config, W, F.conv3d, base, 3)
     return prob.float().numpy(), dist.float().numpy()
 
 
@@ -72,9 +75,11 @@ def forward(config, weights, x, dtype=torch.float32, return_features=False):
         return kt, torch.from_numpy(b).to(dtype)
 
     skips = {}
+    base = None
     for l in unet_layers(config):
         if l['kind'] == 'conv':
             kt, b = W(l['name'])
+            if l['name'] == 'features': base = t
             t = conv(t, kt, b, padding='same')
             if l['act'] == 'relu': t = F.relu(t)
         elif l['kind'] == 'pool':
@@ -92,4 +97,17 @@ def forward(config, weights, x, dtype=torch.float32, return_features=False):
     dist = conv(t, kd, bd)
     prob = prob[:, 0].numpy()
     dist = dist.permute(0, *range(2, nd + 2), 1).contiguous().numpy()
+    if getattr(config, 'n_classes', None) is not None:
+        return prob.astype(np.float32), dist.astype(np.float32), _class_branch(config, W, conv, t if base is None else base, nd)
     return prob.astype(np.float32), dist.astype(np.float32)
+
+
+def _class_branch(config, W, conv, base, nd):
+    """prob_class = softmax(conv1(features_class(backbone output)))  (model2d.py:339-347)"""
+    t = base
+    if 'features_class' in [l['name'] for l in __import__('stardist_b200.models.weights', fromlist=['net_layers']).net_layers(config)]:
+        kt, b = W('features_class')
+        t = F.relu(conv(t, kt, b, padding='same'))
+    kc, bc = W('prob_class')
+    pc = torch.softmax(conv(t, kc, bc), dim=1)
+    return pc.permute(0, *range(2, nd + 2), 1).contiguous().numpy().astype(np.float32)

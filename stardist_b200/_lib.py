@@ -47,6 +47,10 @@ def _declare(lib):
     lib.sdb_conv_generic_nd.restype = c_int
     lib.sdb_add_act.argtypes = [P, P, c_longlong, c_int, P, P]
     lib.sdb_add_act.restype = c_int
+    lib.sdb_class_head.argtypes = [P, c_longlong, c_int, P, P, c_int, P, P]
+    lib.sdb_class_head.restype = c_int
+    lib.sdb_merge_split.argtypes = [P, P, c_longlong, P, P]
+    lib.sdb_merge_split.restype = c_int
     lib.sdb_heads_2d.argtypes = [P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
     lib.sdb_conv3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
     lib.sdb_heads_tc.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, P, P, P]

@@ -50,31 +50,33 @@ __global__ void k_pad_keys(u64* keys, unsigned int n, unsigned int n_pad) {
 }
 
 // ---- bitonic sort, ascending, length n_pad (power of two) -------------------------------
-constexpr int BT = 512;             // threads per block
-constexpr int BTILE = 2 * BT;       // elements per block-local tile (8 KB of smem)
+constexpr int BT = 1024;            // threads per block
+constexpr int BTILE = 4 * BT;       // elements per block-local tile (32 KB of smem): 4096 -> 21 global steps for 2^18 keys
+constexpr int BPAIRS = BTILE / (2 * BT);   // compare-exchange pairs per thread and step
 
 __device__ __forceinline__ void cmpx(u64& a, u64& b, bool up) {
   if ((a > b) == up) { u64 t = a; a = b; b = t; }
 }
 
 // sort each BTILE tile completely (all stages k <= BTILE)
-__global__ void k_bitonic_local_sort(u64* __restrict__ keys) {
+__global__ void __launch_bounds__(BT) k_bitonic_local_sort(u64* __restrict__ keys) {
   __shared__ u64 sh[BTILE];
   const unsigned int base = blockIdx.x * BTILE;
-  sh[threadIdx.x] = keys[base + threadIdx.x];
-  sh[threadIdx.x + BT] = keys[base + threadIdx.x + BT];
+  for (int e = threadIdx.x; e < BTILE; e += BT) sh[e] = keys[base + e];
   __syncthreads();
   for (unsigned int k = 2; k <= BTILE; k <<= 1) {
     for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-      const unsigned int t = threadIdx.x;
-      const unsigned int i = 2 * t - (t & (j - 1));       // lower index of the pair
-      const bool up = (((base + i) & k) == 0);
-      cmpx(sh[i], sh[i + j], up);
+#pragma unroll
+      for (int q = 0; q < BPAIRS; ++q) {
+        const unsigned int t = threadIdx.x + q * BT;
+        const unsigned int i = 2 * t - (t & (j - 1));       // lower index of the pair
+        const bool up = (((base + i) & k) == 0);
+        cmpx(sh[i], sh[i + j], up);
+      }
       __syncthreads();
     }
   }
-  keys[base + threadIdx.x] = sh[threadIdx.x];
-  keys[base + threadIdx.x + BT] = sh[threadIdx.x + BT];
+  for (int e = threadIdx.x; e < BTILE; e += BT) keys[base + e] = sh[e];
 }
 // one global compare-exchange step (j >= BTILE)
 __global__ void k_bitonic_global_step(u64* __restrict__ keys, unsigned int k, unsigned int j, unsigned int n_half) {
@@ -86,21 +88,22 @@ __global__ void k_bitonic_global_step(u64* __restrict__ keys, unsigned int k, un
   if ((a > b) == up) { keys[i] = b; keys[i + j] = a; }
 }
 // finish stage k inside tiles: steps j = BTILE/2 .. 1
-__global__ void k_bitonic_local_merge(u64* __restrict__ keys, unsigned int k) {
+__global__ void __launch_bounds__(BT) k_bitonic_local_merge(u64* __restrict__ keys, unsigned int k) {
   __shared__ u64 sh[BTILE];
   const unsigned int base = blockIdx.x * BTILE;
-  sh[threadIdx.x] = keys[base + threadIdx.x];
-  sh[threadIdx.x + BT] = keys[base + threadIdx.x + BT];
+  for (int e = threadIdx.x; e < BTILE; e += BT) sh[e] = keys[base + e];
   __syncthreads();
   for (unsigned int j = BTILE >> 1; j > 0; j >>= 1) {
-    const unsigned int t = threadIdx.x;
-    const unsigned int i = 2 * t - (t & (j - 1));
-    const bool up = (((base + i) & k) == 0);
-    cmpx(sh[i], sh[i + j], up);
+#pragma unroll
+    for (int q = 0; q < BPAIRS; ++q) {
+      const unsigned int t = threadIdx.x + q * BT;
+      const unsigned int i = 2 * t - (t & (j - 1));
+      const bool up = (((base + i) & k) == 0);
+      cmpx(sh[i], sh[i + j], up);
+    }
     __syncthreads();
   }
-  keys[base + threadIdx.x] = sh[threadIdx.x];
-  keys[base + threadIdx.x + BT] = sh[threadIdx.x + BT];
+  for (int e = threadIdx.x; e < BTILE; e += BT) keys[base + e] = sh[e];
 }
 
 __global__ void k_emit_sorted(const u64* __restrict__ keys, unsigned int n, const float* __restrict__ prob,

@@ -9,6 +9,7 @@
 // These kernels are the exact-fp32 baseline path (used for the Cin=1 stem, small layers and as
 // the in-repo cross-check of the tcgen05 path in unet_tc.cu).  The decoder's upsample+concat is
 // folded into the loader's address math: no up-sampled or concatenated tensor is materialised.
+#include <cuda_fp16.h>
 #include <vector>
 #include <algorithm>
 #include "common.cuh"
@@ -265,6 +266,37 @@ __global__ void k_add_act(const float* __restrict__ a, const float* __restrict__
   }
 }
 
+
+// ---------------------------------------------------------------------------------- multi-class head
+// prob_class = softmax(features_class . W + b) over n_classes + 1 outputs per pixel (model2d.py:339-347,
+// model3d.py:436-444); one thread per pixel, C <= 32.
+__global__ void k_class_head(const float* __restrict__ feat, long long npix, int cf, const float* __restrict__ w /*[cf][C]*/,
+                             const float* __restrict__ b, int C, float* __restrict__ out /*[npix][C]*/) {
+  extern __shared__ float sw[];          // [cf][C] + [C]
+  for (int e = threadIdx.x; e < cf * C; e += blockDim.x) sw[e] = w[e];
+  for (int e = threadIdx.x; e < C; e += blockDim.x) sw[cf * C + e] = b[e];
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float acc[32];
+  for (int o = 0; o < C; ++o) acc[o] = sw[cf * C + o];
+  const float* f = feat + p * cf;
+  for (int k = 0; k < cf; ++k) {
+    const float v = f[k];
+    for (int o = 0; o < C; ++o) acc[o] = fmaf(v, sw[k * C + o], acc[o]);
+  }
+  float m = acc[0];
+  for (int o = 1; o < C; ++o) m = fmaxf(m, acc[o]);
+  float sum = 0.f;
+  for (int o = 0; o < C; ++o) { acc[o] = expf(acc[o] - m); sum += acc[o]; }
+  for (int o = 0; o < C; ++o) out[p * C + o] = acc[o] / sum;
+}
+// split fp16 activation planes (hi, lo) -> fp32
+__global__ void k_merge_split(const __half* __restrict__ hi, const __half* __restrict__ lo, long long n, float* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    out[e] = __half2float(hi[e]) + __half2float(lo[e]);
+}
+
 }  // namespace
 
 // N-d convolution entry point: kz = 1 (2-D, d must be 1) or 3 (3-D).  (uz,uy,ux): up-sampling factors of
@@ -361,5 +393,22 @@ extern "C" int sdb_add_act(const float* d_a, const float* d_b, long long n, int 
   cudaStream_t st = (cudaStream_t)stream;
   if (n <= 0) return 0;
   SDB_LAUNCH(k_add_act, (int)std::min<long long>(sdb::cdiv(n, 256), 148 * 32), 256, 0, st, d_a, d_b, n, relu, d_out);
+  return 0;
+}
+
+extern "C" int sdb_class_head(const float* d_feat, long long npix, int cfeat, const float* d_w, const float* d_b, int n_out, float* d_out,
+                              sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (npix <= 0) return 0;
+  if (n_out < 1 || n_out > 32) { sdb::set_error("class_head: n_classes + 1 must be in [1,32]"); return 1; }
+  const size_t smem = (size_t)(cfeat * n_out + n_out) * sizeof(float);
+  if (smem > 48 * 1024) { sdb::set_error("class_head: weight table too large"); return 1; }
+  SDB_LAUNCH(k_class_head, sdb::cdiv(npix, 128), 128, smem, st, d_feat, npix, cfeat, d_w, d_b, n_out, d_out);
+  return 0;
+}
+extern "C" int sdb_merge_split(const void* d_hi, const void* d_lo, long long n, float* d_out, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  SDB_LAUNCH(k_merge_split, (int)std::min<long long>(sdb::cdiv(n, 256), 148 * 32), 256, 0, st, (const __half*)d_hi, (const __half*)d_lo, n, d_out);
   return 0;
 }

@@ -149,7 +149,7 @@ class StarDistBase:
         """every conv / head layer of the architecture must be present with the expected kernel shape"""
         from .weights import net_layers
         for l in net_layers(config):
-            if l['kind'] not in ('conv', 'head'):
+            if l['kind'] not in ('conv', 'head', 'conv_class', 'head_class'):
                 continue
             if l['name'] not in weights:
                 raise ValueError("weights for layer '%s' are missing" % l['name'])
@@ -297,6 +297,8 @@ class StarDistBase:
         else:
             prob, dist = self.net.forward(x_dev)
             prob, dist = prob[0], dist[0]
+            pc = getattr(self.net, 'prob_class', None)
+            self._last_class = None if pc is None else pc[0]      # multi-class models: [..., n_classes+1] softmax map
         self._last = (prob, dist)
         return prob, dist
 
@@ -315,6 +317,9 @@ class StarDistBase:
         R = self.config.n_rays
         prob = torch.empty(tuple(s // g for s, g in zip(sp, grid)), dtype=torch.float32, device=x_dev.device)
         dist = torch.empty(prob.shape + (R,), dtype=torch.float32, device=x_dev.device)
+        pclass = None
+        if self._is_multiclass():
+            pclass = torch.empty(prob.shape + (self.config.n_classes + 1,), dtype=torch.float32, device=x_dev.device)
         cuts = []
         for s, d, n in zip(sp, div, n_tiles_sp):
             units = s // d
@@ -330,6 +335,9 @@ class StarDistBase:
             dst = tuple(slice(a0 // g, a1 // g) for (a0, a1), g in zip(block, grid))
             prob[dst] = p[0][src]
             dist[dst] = d[0][src]
+            if pclass is not None:
+                pclass[dst] = self.net.prob_class[0][src]
+        self._last_class = pclass
         return prob, dist
 
     def _last_maps(self):
@@ -348,6 +356,8 @@ class StarDistBase:
         prob = prob_d[crop].contiguous().cpu().numpy()
         dist = dist_d[crop + (slice(None),)].contiguous()
         dist = torch.clamp_min(dist, 1e-3).cpu().numpy()   # np.maximum(1e-3, dist), base.py:517
+        if self._is_multiclass():                           # (prob, dist, prob_class), base.py:476-477,524-527
+            return prob, dist, self._last_class[crop + (slice(None),)].contiguous().cpu().numpy()
         return prob, dist
 
     # ------------------------------------------------------------------ predict_sparse
@@ -396,7 +406,11 @@ class StarDistBase:
         L.check(lib.sdb_gather_candidates(L.ptr(dist_d), L.ptr(sidx), n, R, nd, L.iarr(shape), L.iarr(grid),
                                          L.ptr(dist_s), L.ptr(pts_f), L.stream_ptr()))
         self._mark('cand_end')
-        return dict(prob=sprob, dist=dist_s, points_f32=pts_f, n=n)
+        cand = dict(prob=sprob, dist=dist_s, points_f32=pts_f, n=n)
+        if self._is_multiclass():                           # prob_class[inds] of the candidates, base.py:595-614
+            pc = self._last_class
+            cand['prob_class'] = pc.reshape(-1, pc.shape[-1]).index_select(0, sidx.long())
+        return cand
 
     def predict_instances_device(self, x_dev, img_shape, prob_thresh=None, nms_thresh=None, return_labels=True, **nms_kwargs):
         """predict_instances for an input that is already resident in HBM (padded, normalized,
@@ -453,12 +467,13 @@ class StarDistBase:
                                                          return_labels=return_labels, overlap_label=overlap_label, **nms_kwargs)
             return res
         else:
-            prob, dist = self.predict(img, axes=axes, normalizer=normalizer, n_tiles=n_tiles)
-            res = self._instances_from_prediction(_shape_inst, prob, dist, points=None, prob_thresh=prob_thresh,
-                                                  nms_thresh=nms_thresh, scale=scale_dict, return_labels=return_labels,
-                                                  overlap_label=overlap_label, **nms_kwargs)
+            pred = self.predict(img, axes=axes, normalizer=normalizer, n_tiles=n_tiles)
+            prob, dist = pred[0], pred[1]
+            res = self._instances_from_prediction(_shape_inst, prob, dist, points=None, prob_class=(pred[2] if len(pred) > 2 else None),
+                                                  prob_thresh=prob_thresh, nms_thresh=nms_thresh, scale=scale_dict,
+                                                  return_labels=return_labels, overlap_label=overlap_label, **nms_kwargs)
             if return_predict:
-                return res, (prob, dist)
+                return res, tuple(pred)
             return res
 
     # ------------------------------------------------------------------ predict_instances_big

@@ -49,12 +49,16 @@ class StarDist2D(StarDistBase):
         if prob_thresh is None: prob_thresh = self.thresholds.prob
         if nms_thresh is None: nms_thresh = self.thresholds.nms
         if overlap_label is not None: raise NotImplementedError("overlap_label not supported for 2D yet!")
-        if prob_class is not None: raise NotImplementedError("multi-class prediction is not supported yet")
         if points is not None:
             points, probi, disti, indsi = non_maximum_suppression_sparse(dist, prob, points, nms_thresh=nms_thresh, **nms_kwargs)
+            if prob_class is not None:
+                prob_class = np.asarray(prob_class)[indsi]
         else:
             points, probi, disti = non_maximum_suppression(dist, prob, grid=self.config.grid,
                                                            prob_thresh=prob_thresh, nms_thresh=nms_thresh, **nms_kwargs)
+            if prob_class is not None:                      # model2d.py:533-535
+                inds = tuple(p // g for p, g in zip(points.T, self.config.grid))
+                prob_class = np.asarray(prob_class)[inds]
         if scale is not None:
             if not (isinstance(scale, dict) and 'X' in scale and 'Y' in scale):
                 raise ValueError("scale must be a dictionary with entries for 'X' and 'Y'")
@@ -68,6 +72,9 @@ class StarDist2D(StarDistBase):
             labels = None
         coord = dist_to_coord(disti, points, scale_dist=rescale)
         res_dict = dict(coord=coord, points=points, prob=probi)
+        if prob_class is not None:                          # model2d.py:556-560
+            prob_class = np.asarray(prob_class)
+            res_dict.update(dict(class_prob=prob_class, class_id=np.argmax(prob_class, axis=-1)))
         return labels, res_dict
 
     # ------------------------------------------------------------------ device-resident (sparse) path
@@ -114,11 +121,14 @@ class StarDist2D(StarDistBase):
             self._mark('label_end')
         else:
             lab_d = None
-        (labels, probi, coord, points), nbytes = self._to_host([lab_d, probi_d, coord_d, pts_d])
+        pc_d = cand['prob_class'].index_select(0, sel) if 'prob_class' in cand else None
+        (labels, probi, coord, points, prob_class), nbytes = self._to_host([lab_d, probi_d, coord_d, pts_d, pc_d])
         if scale is None:
             points = points.astype(np.int64)
         self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + nbytes
         res_dict = dict(coord=coord, points=points, prob=probi)
+        if prob_class is not None:                          # model2d.py:556-560
+            res_dict.update(dict(class_prob=prob_class, class_id=np.argmax(prob_class, axis=-1)))
         return labels, res_dict
 
     def _axes_div_by(self, query_axes):

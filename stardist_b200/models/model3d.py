@@ -45,13 +45,17 @@ class StarDist3D(StarDistBase):
                                    nms_thresh=None, overlap_label=None, return_labels=True, scale=None, **nms_kwargs):
         if prob_thresh is None: prob_thresh = self.thresholds.prob
         if nms_thresh is None: nms_thresh = self.thresholds.nms
-        if prob_class is not None: raise NotImplementedError("multi-class prediction is not supported yet")
         rays = rays_from_json(self.config.rays_json)
         if points is not None:
             points, probi, disti, indsi = non_maximum_suppression_3d_sparse(dist, prob, points, rays, nms_thresh=nms_thresh, **nms_kwargs)
+            if prob_class is not None:
+                prob_class = np.asarray(prob_class)[indsi]
         else:
             points, probi, disti = non_maximum_suppression_3d(dist, prob, rays, grid=self.config.grid,
                                                               prob_thresh=prob_thresh, nms_thresh=nms_thresh, **nms_kwargs)
+            if prob_class is not None:                      # model3d.py:612-614
+                inds = tuple(p // g for p, g in zip(points.T, self.config.grid))
+                prob_class = np.asarray(prob_class)[inds]
         verbose = nms_kwargs.get('verbose', False)
         if scale is not None:
             if not (isinstance(scale, dict) and 'X' in scale and 'Y' in scale and 'Z' in scale):
@@ -65,6 +69,9 @@ class StarDist3D(StarDistBase):
         else:
             labels = None
         res_dict = dict(dist=disti, points=points, prob=probi, rays=rays, rays_vertices=rays.vertices, rays_faces=rays.faces)
+        if prob_class is not None:                          # model3d.py:663-667
+            prob_class = np.asarray(prob_class)
+            res_dict.update(dict(class_prob=prob_class, class_id=np.argmax(prob_class, axis=-1)))
         return labels, res_dict
 
     # ------------------------------------------------------------------ device-resident (sparse) path
@@ -116,6 +123,9 @@ class StarDist3D(StarDistBase):
         probi = probi_d.cpu().numpy()
         self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + disti.nbytes + points.nbytes + probi.nbytes + (0 if labels is None else labels.nbytes)
         res_dict = dict(dist=disti, points=points, prob=probi, rays=rays, rays_vertices=rays.vertices, rays_faces=rays.faces)
+        if 'prob_class' in cand:                            # model3d.py:663-667
+            prob_class = cand['prob_class'].index_select(0, sel).cpu().numpy()
+            res_dict.update(dict(class_prob=prob_class, class_id=np.argmax(prob_class, axis=-1)))
         return labels, res_dict
 
     def _axes_div_by(self, query_axes):

@@ -29,8 +29,6 @@ class UNetDeviceND:
             raise NotImplementedError("unet_batch_norm=True is not supported on this path")
         if tuple(config.unet_kernel_size) != (3,) * self.nd:
             raise NotImplementedError("only 3^d kernels are supported")
-        if config.n_classes is not None:
-            raise NotImplementedError("multi-class head is not supported yet")
 
     @staticmethod
     def _dhw(x):
@@ -49,6 +47,23 @@ class UNetDeviceND:
                                 1 if self.nd == 2 else 3, 1 if relu else 0, L.ptr(out), L.stream_ptr()))
         return out
 
+    def _class_branch(self, base):
+        """prob_class [N,...,n_classes+1] from the backbone output `base` (fp32, channels last), or None"""
+        if self.config.n_classes is None:
+            return None
+        lib = L.load()
+        x = base
+        if 'features_class' in self.w:
+            k = self.w['features_class'][0]
+            act = self.config.unet_activation if getattr(self.config, 'backbone', 'unet') == 'unet' else self.config.resnet_activation
+            x = self._conv(base, None, 'features_class', act == 'relu', (1,) * self.nd)
+        wc, bc = self.w['prob_class']
+        C = int(wc.shape[-1]); cf = int(x.shape[-1])
+        npix = int(np.prod(x.shape[:-1]))
+        out = torch.empty(tuple(x.shape[:-1]) + (C,), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_class_head(L.ptr(x), npix, cf, L.ptr(wc.reshape(cf, C).contiguous()), L.ptr(bc), C, L.ptr(out), L.stream_ptr()))
+        return out
+
     def _pool(self, x, pool):
         lib = L.load()
         n = x.shape[0]; d, h, w = self._dhw(x); c = x.shape[-1]
@@ -64,12 +79,14 @@ class UNetDeviceND:
         assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
         skips = {}
         lo, up = None, (1,) * self.nd
+        base = None
         for l in self.layers:
             kind = l['kind']
             if kind == 'conv':
                 act = l['act']
                 if act not in ('relu', 'linear'):
                     raise NotImplementedError("activation %s" % act)
+                if l['name'] == 'features': base = x
                 x = self._conv(x, lo, l['name'], act == 'relu', up)
                 lo, up = None, (1,) * self.nd
             elif kind == 'pool':
@@ -90,6 +107,7 @@ class UNetDeviceND:
         dist = torch.empty(tuple(feat.shape[:-1]) + (R,), dtype=torch.float32, device=x.device)
         L.check(lib.sdb_heads_2d(L.ptr(feat), npix, cf, L.ptr(wp), L.ptr(bp), L.ptr(wd), L.ptr(bd), R,
                                 L.ptr(prob), L.ptr(dist), L.stream_ptr()))
+        self.prob_class = self._class_branch(feat if base is None else base)
         return prob, dist
 
 
@@ -112,8 +130,6 @@ class ResNetDeviceND(UNetDeviceND):
         for name, (k, b) in weights.items():
             self.w[name] = (torch.from_numpy(np.ascontiguousarray(k, dtype=np.float32)).to(self.device),
                             torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device))
-        if config.n_classes is not None:
-            raise NotImplementedError("multi-class head is not supported yet")
 
     def _conv_any(self, x, l):
         lib = L.load()
@@ -134,12 +150,13 @@ class ResNetDeviceND(UNetDeviceND):
     def forward(self, x):
         lib = L.load()
         assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.dim() == 5
-        block_in = shortcut = None
+        block_in = shortcut = base = None
         for l in self.layers:
             kind = l['kind']
             if kind == 'block_begin':
                 block_in, shortcut = x, None
             elif kind == 'conv':
+                if l['name'] == 'features': base = x
                 y = self._conv_any(block_in if l['src'] == 'block_in' else x, l)
                 if l['dst'] == 'shortcut': shortcut = y
                 else: x = y
@@ -160,6 +177,7 @@ class ResNetDeviceND(UNetDeviceND):
         dist = torch.empty(tuple(feat.shape[:-1]) + (R,), dtype=torch.float32, device=x.device)
         L.check(lib.sdb_heads_2d(L.ptr(feat), npix, cf, L.ptr(wp), L.ptr(bp), L.ptr(wd), L.ptr(bd), R,
                                 L.ptr(prob), L.ptr(dist), L.stream_ptr()))
+        self.prob_class = self._class_branch(feat if base is None else base)
         return prob, dist
 
 
@@ -188,9 +206,9 @@ class UNetDevice2DTC:
             raise NotImplementedError("unet_batch_norm=True is not supported on this path")
         if tuple(config.unet_kernel_size) != (3, 3) or tuple(config.unet_pool) != (2, 2):
             raise NotImplementedError("only 3x3 kernels and 2x2 pooling are supported")
-        if config.n_classes is not None:
-            raise NotImplementedError("multi-class head is not supported yet")
         self.w = {}
+        self._simt = None
+        self.prob_class = None
         for name, (k, b) in weights.items():
             kd = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float32)).to(self.device)
             bd = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device)
@@ -233,6 +251,19 @@ class UNetDevice2DTC:
             bh[32] = self.w['prob']['b'][0]
             self.fuse_w, self.fuse_b = Wh.contiguous(), bh
 
+    def _class_branch_split(self, base_split):
+        """multi-class branch of the tensor-core executor: the backbone output (split fp16 planes) is merged to fp32 and
+        runs through the CUDA-core 3x3 convolution + softmax head (classification models only; not on the bench path)"""
+        if self.config.n_classes is None:
+            return None
+        lib = L.load()
+        if self._simt is None:
+            self._simt = UNetDeviceND(self.config, {k: (v['k'].cpu().numpy(), v['b'].cpu().numpy()) for k, v in self.w.items()
+                                                   if k in ('features_class', 'prob_class')})
+        base = torch.empty(tuple(base_split.shape[1:]), dtype=torch.float32, device=base_split.device)
+        L.check(lib.sdb_merge_split(L.ptr(base_split[0]), L.ptr(base_split[1]), base.numel(), L.ptr(base), L.stream_ptr()))
+        return self._simt._class_branch(base)
+
     @staticmethod
     def supported(config):
         ch = [l['cin'] for l in unet_layers(config) if l['kind'] == 'conv'] + [l['cout'] for l in unet_layers(config) if l['kind'] == 'conv']
@@ -241,7 +272,7 @@ class UNetDevice2DTC:
         rest = [l for l in unet_layers(config) if l['kind'] == 'conv'][1:]
         ok_rest = all(l['cin'] % 32 == 0 and l['cout'] in (32, 64, 128, 256) for l in rest)
         return (ok_first and ok_rest and config.net_conv_after_unet == 128 and not config.unet_batch_norm
-                and tuple(config.unet_kernel_size) == (3, 3) and tuple(config.unet_pool) == (2, 2) and config.n_classes is None)
+                and tuple(config.unet_kernel_size) == (3, 3) and tuple(config.unet_pool) == (2, 2))
 
     def forward(self, x):
         lib = L.load()
@@ -273,6 +304,8 @@ class UNetDevice2DTC:
                     c0 = 0 if lo is None else lo.shape[-1]
                     oh, ow = (2 * hh, 2 * ww) if up2x else (hh, ww)
                     ws = ent['split']
+                    if l['name'] == 'features':
+                        self.prob_class = self._class_branch_split(cur) if lo is None else None
                     if self.fuse_heads and l['name'] == 'features' and c1 + c0 <= 64 and cout == 128:
                         R = self.config.n_rays
                         prob = torch.empty((n_, hh, ww), dtype=torch.float32, device=x.device)

@@ -55,12 +55,29 @@ def unet_layers(config):
         layers.append(dict(name='up_level_%d_no_%d' % (n, nconv), kind='conv', cin=c_in, cout=base * 2 ** max(0, n - 1), k=k,
                            act=last_act, cin_lo=(c if nconv == 1 else 0)))
         c = base * 2 ** max(0, n - 1)
+    c_base = c
     if config.net_conv_after_unet > 0:
         layers.append(dict(name='features', kind='conv', cin=c, cout=config.net_conv_after_unet, k=k, act=config.unet_activation))
         c = config.net_conv_after_unet
     layers.append(dict(name='prob', kind='head', cin=c, cout=1, k=(1,) * nd, act='sigmoid'))
     layers.append(dict(name='dist', kind='head', cin=c, cout=config.n_rays, k=(1,) * nd, act='linear'))
+    layers += _class_layers(config, c_base, config.net_conv_after_unet, k, config.unet_activation)
     return layers
+
+
+def _class_layers(config, c_base, n_after, k, act):
+    """extra classification branch of multi-class models (model2d.py:339-347, model3d.py:388-396 / :436-444):
+    features_class = conv(k)(backbone output) [if net_conv_after_* > 0], prob_class = softmax(conv 1^d, n_classes + 1).
+    Kinds 'conv_class' / 'head_class' so that the single-class executors skip them."""
+    if getattr(config, 'n_classes', None) is None:
+        return []
+    nd = config.n_dim
+    out, c = [], c_base
+    if n_after > 0:
+        out.append(dict(name='features_class', kind='conv_class', cin=c_base, cout=int(n_after), k=tuple(k), act=act))
+        c = int(n_after)
+    out.append(dict(name='prob_class', kind='head_class', cin=c, cout=int(config.n_classes) + 1, k=(1,) * nd, act='softmax'))
+    return out
 
 
 def resnet_layers(config):
@@ -105,11 +122,13 @@ def resnet_layers(config):
             conv(c, nf, (1, 1, 1), stride=pool, src='block_in', dst='shortcut')
         layers.append(dict(name='block_end', kind='block_end', act=act))
         c = nf
+    c_base = c
     if config.net_conv_after_resnet > 0:
         conv(c, int(config.net_conv_after_resnet), k, a=act, name='features')
         c = int(config.net_conv_after_resnet)
     layers.append(dict(name='prob', kind='head', cin=c, cout=1, k=(1,) * nd, act='sigmoid'))
     layers.append(dict(name='dist', kind='head', cin=c, cout=config.n_rays, k=(1,) * nd, act='linear'))
+    layers += _class_layers(config, c_base, int(config.net_conv_after_resnet), k, act)
     return layers
 
 
@@ -127,7 +146,7 @@ def glorot_uniform_weights(config, seed=0):
     rng = np.random.default_rng(seed)
     w = {}
     for l in net_layers(config):
-        if l['kind'] not in ('conv', 'head'):
+        if l['kind'] not in ('conv', 'head', 'conv_class', 'head_class'):
             continue
         k, cin, cout = l['k'], l['cin'], l['cout']
         rf = int(np.prod(k))

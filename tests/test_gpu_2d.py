@@ -230,3 +230,27 @@ def test_reference_2d_demo_model_reproduces_reference_test(sd):
     assert np.array_equal(polygons['points'], ref['points'])
     assert np.mean(labels != ref_labels) < 1e-3
 
+
+
+@pytest.mark.parametrize("grid", [(1, 1), (2, 2)])
+def test_multiclass_head(sd, grid):
+    """n_classes: extra features_class conv + softmax head (model2d.py:339-347); predict returns (prob, dist, prob_class),
+    predict_instances adds class_prob / class_id of the survivors (model2d.py:556-560), sparse == dense path"""
+    rng = np.random.default_rng(11)
+    img = rng.uniform(0, 1, (80, 144)).astype(np.float32)      # divisible by 8 * grid: the oracle gets the unpadded image
+    cfg = sd.Config2D(n_rays=32, grid=grid, n_classes=3)
+    model = sd.StarDist2D(cfg, name=None, basedir=None)
+    assert 'features_class' in model.weights and model.weights['prob_class'][0].shape[-1] == 4
+    prob, dist, pc = model.predict(img)
+    rp, rd, rpc = unet_torch.forward(cfg, model.weights, img[None, ..., None])
+    assert pc.shape == prob.shape + (4,)
+    assert np.max(np.abs(prob - rp[0])) <= 1e-5 and np.max(np.abs(pc - rpc[0])) <= 1e-5
+    assert np.allclose(pc.sum(-1), 1, atol=1e-5)
+    thr = float(np.quantile(prob, 0.95))
+    labels, res = model.predict_instances(img, prob_thresh=thr, nms_thresh=0.4)
+    assert res['class_prob'].shape == (len(res['prob']), 4)
+    pts = res['points'] // np.array(grid)
+    assert np.array_equal(res['class_prob'], pc[pts[:, 0], pts[:, 1]])
+    assert np.array_equal(res['class_id'], np.argmax(res['class_prob'], -1))
+    labels2, res2 = model.predict_instances(img, prob_thresh=thr, nms_thresh=0.4, sparse=False)
+    assert np.array_equal(labels, labels2) and np.array_equal(res['class_id'], res2['class_id'])

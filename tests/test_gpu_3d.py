@@ -191,3 +191,21 @@ def test_reference_3d_demo_model_reproduces_reference_test(sd):
     assert np.array_equal(res['points'], ref['points'])
     assert np.mean(labels != ref_labels) < 2e-3
 
+
+
+def test_multiclass_head_3d(sd):
+    from oracle import unet_torch
+    rng = np.random.default_rng(12)
+    vol = rng.uniform(0, 1, (16, 40, 32)).astype(np.float32)
+    for backbone in ('unet', 'resnet'):
+        cfg = sd.Config3D(rays=sd.Rays_GoldenSpiral(12), n_classes=2, backbone=backbone)
+        model = sd.StarDist3D(cfg, name=None, basedir=None)
+        prob, dist, pc = model.predict(vol)
+        rp, rd, rpc = unet_torch.forward(cfg, model.weights, vol[None, ..., None])
+        assert pc.shape == prob.shape + (3,) and np.max(np.abs(pc - rpc[0])) <= 1e-5
+        k, b = model.weights['dist']; model.weights['dist'] = (k, b + np.float32(3.0)); model._net = None
+        prob, dist, pc = model.predict(vol)
+        labels, res = model.predict_instances(vol, prob_thresh=float(np.quantile(prob, 0.97)), nms_thresh=0.3)
+        assert res['class_prob'].shape == (len(res['prob']), 3)
+        p = res['points']
+        assert np.array_equal(res['class_prob'], pc[p[:, 0], p[:, 1], p[:, 2]])
