@@ -254,3 +254,28 @@ def test_multiclass_head(sd, grid):
     assert np.array_equal(res['class_id'], np.argmax(res['class_prob'], -1))
     labels2, res2 = model.predict_instances(img, prob_thresh=thr, nms_thresh=0.4, sparse=False)
     assert np.array_equal(labels, labels2) and np.array_equal(res['class_id'], res2['class_id'])
+
+
+def test_cli_predict_on_model_folder(sd, tmp_path):
+    """python -m stardist_b200.scripts.predict on a model folder (config.json + thresholds.json + weights.npz) and a TIFF:
+    the written label image equals predict_instances on the same normalised input; ROI set has one entry per instance"""
+    import json, zipfile
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import demo2d
+    from stardist_b200.io import tiff
+    from stardist_b200.utils import normalize
+    from stardist_b200.scripts import predict as cli
+    kwargs, weights, thr, img, mask = demo2d.load()
+    folder = tmp_path / "demo_model"; folder.mkdir()
+    cfg = sd.Config2D(**kwargs)
+    json.dump({k: v for k, v in vars(cfg).items() if isinstance(v, (int, float, str, bool, list, tuple, type(None), dict))}, open(folder / "config.json", "w"))
+    json.dump(thr, open(folder / "thresholds.json", "w"))
+    np.savez(folder / "weights.npz", **{n + "/kernel": k for n, (k, b) in weights.items()}, **{n + "/bias": b for n, (k, b) in weights.items()})
+    tiff.imwrite(tmp_path / "nuclei.tif", img)
+    written = cli.main(["-i", str(tmp_path / "nuclei.tif"), "-m", str(folder), "-o", str(tmp_path / "out"), "--n_tiles", "2", "2", "--rois"])
+    labels = tiff.imread(written[0])
+    model = sd.StarDist2D(None, name="demo_model", basedir=str(tmp_path))
+    ref_labels, res = model.predict_instances(normalize(img, 1, 99.8), n_tiles=(2, 2))
+    assert np.array_equal(labels, ref_labels) and labels.max() == len(res['prob'])
+    with zipfile.ZipFile(str(tmp_path / "out" / "nuclei.stardist.rois.zip")) as z:
+        assert len(z.namelist()) == len(res['prob'])
