@@ -48,3 +48,26 @@ def test_cli_parser():
     from stardist_b200.scripts.predict import build_parser
     a = build_parser().parse_args(["-i", "x.tif", "y.tif", "-m", "model", "--n_tiles", "2", "3", "--pnorm", "2", "99", "--rois"])
     assert a.input == ["x.tif", "y.tif"] and a.n_tiles == [2, 3] and a.pnorm == [2.0, 99.0] and a.rois and a.outname == "{img}.stardist.tif"
+
+
+def test_export_to_obj_file3D(tmp_path):
+    """text identical to stardist/geometry/geom3d.py:277-347 (compiled in isolation where the reference tree is mounted)"""
+    import stardist_b200 as sd
+    from stardist_b200.io import obj
+    rays = sd.Rays_GoldenSpiral(12)
+    rng = np.random.default_rng(0)
+    polys = dict(dist=rng.uniform(2, 6, (4, 12)).astype(np.float32), points=rng.integers(5, 40, (4, 3)),
+                 rays_vertices=rays.vertices, rays_faces=rays.faces)
+    text = obj.export_to_obj_file3D(polys, fname=str(tmp_path / "m.obj"))
+    assert open(tmp_path / "m.obj").read() == text
+    assert text.count("\nv ") + text.startswith("v ") == 4 * 12 and text.count("f ") == 4 * len(rays.faces) and text.startswith("o poly_0\n")
+    with pytest.raises(ValueError):
+        obj.export_to_obj_file3D(dict(dist=polys["dist"]))
+    ref_src = "/root/reference/stardist/geometry/geom3d.py"
+    if not os.path.exists(ref_src):
+        return
+    fns = [n for n in ast.parse(open(ref_src).read()).body if isinstance(n, ast.FunctionDef) and n.name in ("dist_to_coord3D", "export_to_obj_file3D")]
+    ns = {"np": np, "tqdm": (lambda x: x)}
+    exec(compile(ast.Module(body=fns, type_ignores=[]), "ref_geom3d", "exec"), ns)
+    for kw in (dict(), dict(single_mesh=False), dict(uv_map=True, scale=(2, 1, 0.5)), dict(scale=0.01)):
+        assert obj.export_to_obj_file3D(polys, **kw) == ns["export_to_obj_file3D"](dict(polys), **kw)
