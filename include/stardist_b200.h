@@ -195,6 +195,17 @@ int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, int c_src0, c
 int sdb_tma_probe(const void* d_act, int h, int w, int c, int box_c, int rows, int loads_per_tile, int reps, float* ms_out, sdb_stream_t stream);
 /* profiling aid: u64 [148][8] wait-cycle counters written by the halo-reuse conv (NULL disables) */
 int sdb_tc_set_debug(void* d_buf);
+/* 3-D U-Net on the tensor cores (model3d.py:360-399): 3x3x3 convolution of ONE volume [d,h,w,c] in split fp16 planes
+ * (k_conv_tc4 with the z planes as the tensor map's image axis; weights [27][cout][cin] from sdb_split_weights_3d,
+ * tap = dz*9 + dy*3 + dx; up2x: 0 none, 2 = nearest 2x2x2 up-sampling written by the epilogue), max-pooling on split
+ * planes, and the fp32 -> split conversion behind the CUDA-core stem. */
+int sdb_conv3x3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                     int c_src1, int d, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
+                     int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream);
+int sdb_split_weights_3d(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream);
+int sdb_maxpool3d_split(const void* in_hi, const void* in_lo, int d, int h, int w, int c, int pz, int py, int px,
+                        void* out_hi, void* out_lo, sdb_stream_t stream);
+int sdb_split_f32(const float* d_in, long long n, void* out_hi, void* out_lo, sdb_stream_t stream);
 /* kernel variant of sdb_conv3x3_tc: 0 (default) = auto, 1 = one 8x16 tile per CTA, 3 = persistent CTAs with
  * double-buffered TMEM accumulators and merged hi/lo weight tile, 4 = 3 + halo reuse (one box load per
  * 32-channel block, taps as shifted descriptors).  Results are identical up to fp32 summation order. */

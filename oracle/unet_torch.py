@@ -97,9 +97,10 @@ def forward(config, weights, x, dtype=torch.float32, return_features=False):
     dist = conv(t, kd, bd)
     prob = prob[:, 0].numpy()
     dist = dist.permute(0, *range(2, nd + 2), 1).contiguous().numpy()
+    odt = np.float64 if dtype == torch.float64 else np.float32       # float64 evaluations keep their precision
     if getattr(config, 'n_classes', None) is not None:
-        return prob.astype(np.float32), dist.astype(np.float32), _class_branch(config, W, conv, t if base is None else base, nd)
-    return prob.astype(np.float32), dist.astype(np.float32)
+        return prob.astype(odt), dist.astype(odt), _class_branch(config, W, conv, t if base is None else base, nd)
+    return prob.astype(odt), dist.astype(odt)
 
 
 def _class_branch(config, W, conv, base, nd):

@@ -60,6 +60,14 @@ def _declare(lib):
     lib.sdb_tma_probe.restype = c_int
     lib.sdb_tc_set_debug.argtypes = [P]
     lib.sdb_tc_set_debug.restype = c_int
+    lib.sdb_conv3x3x3_tc.argtypes = [P, P, c_int, P, P, c_int, c_int, c_int, c_int, P, P, c_float, P, c_int, c_int, c_int, P, P, P]
+    lib.sdb_conv3x3x3_tc.restype = c_int
+    lib.sdb_split_weights_3d.argtypes = [P, c_int, c_int, c_float, P, P, P]
+    lib.sdb_split_weights_3d.restype = c_int
+    lib.sdb_maxpool3d_split.argtypes = [P, P] + [c_int] * 7 + [P, P, P]
+    lib.sdb_maxpool3d_split.restype = c_int
+    lib.sdb_split_f32.argtypes = [P, c_longlong, P, P, P]
+    lib.sdb_split_f32.restype = c_int
     lib.sdb_tc_error_check.argtypes = [P]
     lib.sdb_tc_set_variant.argtypes = [c_int]
     lib.sdb_tc_set_variant.restype = c_int

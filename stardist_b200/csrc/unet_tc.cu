@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(FUSE ? 352 : 224, 1)
 k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ CUtensorMap tm_a0_lo,
            const __grid_constant__ CUtensorMap tm_a1_hi, const __grid_constant__ CUtensorMap tm_a1_lo,
            const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo, ConvParams P,
-           int tiles_x, int tiles_y, int n_tiles, int n_b_slots) {
+           int tiles_x, int tiles_y, int n_tiles, int n_b_slots, int n_dz) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
   constexpr int RING = C::B_STAGES;              // weight ring depth
@@ -636,28 +636,31 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       bool ok = true;
       unsigned long long w_prod = 0;
       // halos run ahead by A_STAGES work items (tile, channel block), independent of the weight ring
-      auto load_halo = [&](int tile, int cb, uint32_t a_idx) -> bool {
+      // 3-D (n_dz == 3): the "image" coordinate of the tensor map is the z plane of ONE volume; plane z of the output
+      // accumulates the 3x3 taps of planes z-1, z, z+1 (planes outside the volume are out of bounds = zero filled)
+      auto load_halo = [&](int tile, int cb, int dz, uint32_t a_idx) -> bool {
         const int img = tile / tiles_per_img, rem = tile - img * tiles_per_img;
         const int y0 = (rem / tiles_x) * S, x0 = (rem % tiles_x) * 128;
+        const int plane = img + dz - (n_dz == 3 ? 1 : 0);
         const uint32_t sa = a_idx % C::A_STAGES;
         if (a_idx >= (uint32_t)C::A_STAGES && !mbar_wait_t(&a_empty[sa], ((a_idx / C::A_STAGES) - 1) & 1, w_prod)) { atomicExch(P.error_flag, 11u); return false; }
         const int ch = cb * C::KC;
         unsigned char* sta = smA + sa * C::A_STAGE;
         mbar_expect_tx(&a_full[sa], 2 * C::HROWS * C::ROWB);
         if (ch < P.c_src0) {
-          tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, img);
-          tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, img);
+          tma_load_4d(sta, &tm_a0_hi, &a_full[sa], ch, x0 - 1, y0 - 1, plane);
+          tma_load_4d(sta + C::A_PLANE, &tm_a0_lo, &a_full[sa], ch, x0 - 1, y0 - 1, plane);
         } else {
-          tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
-          tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, img);
+          tma_load_4d(sta, &tm_a1_hi, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, plane);
+          tma_load_4d(sta + C::A_PLANE, &tm_a1_lo, &a_full[sa], ch - P.c_src0, x0 - 1, y0 - 1, plane);
         }
         return true;
       };
-      int tile = blockIdx.x, cb = 0;
+      int tile = blockIdx.x, cb = 0, dz = 0;
       while (ok && tile < n_tiles) {
-        ok = load_halo(tile, cb, ai);
+        ok = load_halo(tile, cb, dz, ai);
         ++ai;
-        if (++cb == n_cb) { cb = 0; tile += (int)gridDim.x; }
+        if (++dz == n_dz) { dz = 0; if (++cb == n_cb) { cb = 0; tile += (int)gridDim.x; } }
       }
       if (P.dbg) P.dbg[blockIdx.x * 8 + 6] = w_prod;
     }
@@ -667,10 +670,10 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       uint32_t bi = 0;
       bool ok = true;
       if (WRES) {
-        mbar_expect_tx(&b_full[0], (uint32_t)(9 * n_cb) * C::B_STAGE);
+        mbar_expect_tx(&b_full[0], (uint32_t)(9 * n_dz * n_cb) * C::B_STAGE);
         for (int cb = 0; cb < n_cb; ++cb)
-          for (int tap = 0; tap < 9; ++tap) {
-            unsigned char* stb = smB + (size_t)(cb * 9 + tap) * C::B_STAGE;
+          for (int tap = 0; tap < 9 * n_dz; ++tap) {
+            unsigned char* stb = smB + (size_t)(cb * 9 * n_dz + tap) * C::B_STAGE;
             tma_load_3d(stb, &tm_w_hi, &b_full[0], cb * C::KC, 0, tap);
             tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[0], cb * C::KC, 0, tap);
           }
@@ -678,7 +681,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
           for (int cb = 0; cb < n_cb && ok; ++cb) {
             const int ch = cb * C::KC;
-            for (int tap = 0; tap < 9; ++tap, ++bi) {
+            for (int tap = 0; tap < 9 * n_dz; ++tap, ++bi) {       // tap index = dz * 9 + (dy * 3 + dx)
               const uint32_t sb = bi % RING;
               if (bi >= (uint32_t)RING && !mbar_wait(&b_empty[sb], ((bi / RING) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
               unsigned char* stb = smB + sb * C::B_STAGE;
@@ -704,7 +707,8 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t d0 = tmem_base + buf * (uint32_t)C::ACC_COLS;
-        for (int cb = 0; cb < n_cb && ok; ++cb, ++ai) {
+        for (int cbz = 0; cbz < n_cb * n_dz && ok; ++cbz, ++ai) {
+          const int cb = cbz / n_dz, dz = cbz - cb * n_dz;
           const uint32_t sa = ai % C::A_STAGES;
           if (!mbar_wait_t(&a_full[sa], (ai / C::A_STAGES) & 1, w_m1)) { atomicExch(P.error_flag, 13u); ok = false; break; }
           const uint32_t a_hi = smem_u32(smA + sa * C::A_STAGE), a_lo = a_hi + C::A_PLANE;
@@ -714,7 +718,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           const uint64_t dA_hi = make_desc_sw64(a_hi, 0), dA_lo = make_desc_sw64(a_lo, 0);
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bi) {
-            const uint32_t sb = WRES ? (uint32_t)(cb * 9 + tap) : bi % RING;
+            const uint32_t sb = WRES ? (uint32_t)((cb * n_dz + dz) * 9 + tap) : bi % RING;
             if (!WRES) {
               if (!mbar_wait_t(&b_full[sb], (bi / RING) & 1, w_m2)) { atomicExch(P.error_flag, 14u); ok = false; break; }
             }
@@ -730,7 +734,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
               for (int ks = 0; ks < C::KC / 16; ++ks) {
                 const uint32_t aoff = (roff + ks * 32) >> 4, boff = (uint32_t)(ks * 32) >> 4;
                 const uint64_t dah = dA_hi + aoff, dal = dA_lo + aoff, dbh = dB_hi + boff;
-                const uint32_t acc = (cb | tap | ks) ? 1u : 0u;
+                const uint32_t acc = (cbz | tap | ks) ? 1u : 0u;
                 if (C::MERGE) {
                   if (elect_one()) umma_f16(d, dah, dbh, C::IDESC_2N, acc);       // [0,N): hi*Whi   [N,2N): hi*Wlo
                   if (elect_one()) umma_f16(d, dal, dbh, C::IDESC_N, 1u);         // [0,N) += lo*Whi
@@ -874,10 +878,13 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
                 reinterpret_cast<uint4*>(P.out_lo + off)[j] = reinterpret_cast<const uint4*>(lo)[j];
               }
             } else {
+              // nearest up-sampling written by the producer: 2x2 pixels, and both planes 2z, 2z+1 for a volume (up2x == 2)
               const int H2 = 2 * P.H, W2 = 2 * P.W;
-#pragma unroll
-              for (int rep = 0; rep < 4; ++rep) {
-                const size_t off = (((size_t)img * H2 + (2 * y + (rep >> 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
+              const int nrep = (P.up2x == 2) ? 8 : 4;
+#pragma unroll 1
+              for (int rep = 0; rep < nrep; ++rep) {
+                const size_t plane = (P.up2x == 2) ? (size_t)(2 * img + (rep >> 2)) : (size_t)img;
+                const size_t off = ((plane * H2 + (2 * y + ((rep >> 1) & 1))) * W2 + (2 * x + (rep & 1))) * N + c0;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   reinterpret_cast<uint4*>(P.out_hi + off)[j] = reinterpret_cast<const uint4*>(hi)[j];
@@ -1033,9 +1040,42 @@ k_heads_split(const __half* __restrict__ f_hi, const __half* __restrict__ f_lo, 
   }
 }
 
+// (pz,py,px) max-pooling of one volume on split planes (3-D U-Net)
+__global__ void k_maxpool3d_split(const __half* __restrict__ in_hi, const __half* __restrict__ in_lo, int D, int H, int W, int C,
+                                  int pz, int py, int px, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int Do = D / pz, Ho = H / py, Wo = W / px, C2 = C / 2;
+  const long long total = (long long)Do * Ho * Wo * C2;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c2 = (int)(e % C2); long long r = e / C2;
+    const int xo = (int)(r % Wo); r /= Wo;
+    const int yo = (int)(r % Ho); const int zo = (int)(r / Ho);
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int a = 0; a < pz; ++a)
+      for (int b = 0; b < py; ++b)
+        for (int c = 0; c < px; ++c) {
+          const size_t off = ((((size_t)zo * pz + a) * H + (size_t)yo * py + b) * W + (size_t)xo * px + c) * C + 2 * c2;
+          const float2 h = __half22float2(*reinterpret_cast<const __half2*>(in_hi + off));
+          const float2 l = __half22float2(*reinterpret_cast<const __half2*>(in_lo + off));
+          m0 = fmaxf(m0, h.x + l.x); m1 = fmaxf(m1, h.y + l.y);
+        }
+    const __half h0 = __float2half_rn(m0), h1 = __float2half_rn(m1);
+    const size_t o = (size_t)e * 2;
+    *reinterpret_cast<__half2*>(out_hi + o) = __halves2half2(h0, h1);
+    *reinterpret_cast<__half2*>(out_lo + o) = __halves2half2(__float2half_rn(m0 - __half2float(h0)), __float2half_rn(m1 - __half2float(h1)));
+  }
+}
+// fp32 -> split fp16 planes (output of the CUDA-core stem of the 3-D network)
+__global__ void k_split_f32(const float* __restrict__ in, long long n, __half* __restrict__ hi, __half* __restrict__ lo) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float v = in[e];
+    const __half h = __float2half_rn(v);
+    hi[e] = h; lo[e] = __float2half_rn(v - __half2float(h));
+  }
+}
+
 // weights (3,3,Cin,Cout) fp32 -> [tap][Cout][Cin] fp16 hi / lo
-__global__ void k_split_weights(const float* __restrict__ w, int Cin, int Cout, float scale, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
-  const long long total = 9LL * Cin * Cout;
+__global__ void k_split_weights(const float* __restrict__ w, int n_taps, int Cin, int Cout, float scale, __half* __restrict__ w_hi, __half* __restrict__ w_lo) {
+  const long long total = (long long)n_taps * Cin * Cout;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(e % Cin); long long r = e / Cin;
     const int co = (int)(r % Cout); const int tap = (int)(r / Cout);
@@ -1143,10 +1183,10 @@ static int launch_tc3(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUte
 
 template <int N, bool FUSE, bool WRES>
 static int launch_tc4_impl(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
-                           const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+                           const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st, int n_dz) {
   using C = TcCfg4<N>;
   const int n_cb = P.c_total / C::KC;
-  const int n_b_slots = WRES ? 9 * n_cb : C::B_STAGES;
+  const int n_b_slots = WRES ? 9 * n_dz * n_cb : C::B_STAGES;
   const int smem = C::SMEM_FIXED + n_b_slots * C::B_STAGE + (FUSE ? (36 + N + N * 36) * 4 : 0);
   if (smem > 227 * 1024) { sdb::set_error("conv_tc4: shared memory budget exceeded"); return 1; }
   static int attr = 0;
@@ -1157,21 +1197,21 @@ static int launch_tc4_impl(const CUtensorMap& a0h, const CUtensorMap& a0l, const
   const int grid = std::min(n_tiles, g_num_sms);
   sdb::ProfSpan sp;
   sdb::profile_begin("conv_tc", st, &sp);
-  k_conv_tc4<N, FUSE, WRES><<<grid, FUSE ? 352 : 224, smem, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles, n_b_slots);
+  k_conv_tc4<N, FUSE, WRES><<<grid, FUSE ? 352 : 224, smem, st>>>(a0h, a0l, a1h, a1l, wh, wl, P, tiles_x, tiles_y, n_tiles, n_b_slots, n_dz);
   sdb::profile_end("conv_tc", st, &sp);
-  sdb::profile_add_units("conv_tc", (2.0 * 9.0 * P.c_total * N + (FUSE ? 2.0 * N * (P.heads_R + 1) : 0.0)) * (double)P.H * P.W * n_img);
+  sdb::profile_add_units("conv_tc", (2.0 * 9.0 * n_dz * P.c_total * N + (FUSE ? 2.0 * N * (P.heads_R + 1) : 0.0)) * (double)P.H * P.W * n_img);
   sdb::g_launch_count++;
   SDB_CUDA(cudaGetLastError());
   return 0;
 }
 template <int N, bool FUSE = false>
 static int launch_tc4(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUtensorMap& a1h, const CUtensorMap& a1l,
-                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st) {
+                      const CUtensorMap& wh, const CUtensorMap& wl, const ConvParams& P, int n_img, cudaStream_t st, int n_dz = 1) {
   using C = TcCfg4<N>;
   const int n_cb = P.c_total / C::KC;
-  if (!FUSE && 9 * n_cb * C::B_STAGE <= C::W_RESIDENT_MAX && !g_tc_no_resident)
-    return launch_tc4_impl<N, FUSE, true>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st);
-  return launch_tc4_impl<N, FUSE, false>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st);
+  if (!FUSE && 9 * n_dz * n_cb * C::B_STAGE <= C::W_RESIDENT_MAX && !g_tc_no_resident)
+    return launch_tc4_impl<N, FUSE, true>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st, n_dz);
+  return launch_tc4_impl<N, FUSE, false>(a0h, a0l, a1h, a1l, wh, wl, P, n_img, st, n_dz);
 }
 
 static unsigned int* g_err_flag = nullptr;      // device flag shared by all launches
@@ -1279,6 +1319,32 @@ extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, in
   return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
 
+// 3x3x3 convolution of ONE volume [d,h,w,c] (split fp16 planes) on the tensor cores: k_conv_tc4 with the z planes as the
+// tensor map's image axis and 27 weight taps [27][cout][cin] (tap = dz*9 + dy*3 + dx).  up2x: 0 none, 2 = nearest 2x2x2.
+extern "C" int sdb_conv3x3x3_tc(const void* src0_hi, const void* src0_lo, int c_src0, const void* src1_hi, const void* src1_lo,
+                                int c_src1, int d, int h, int w, const void* w_hi, const void* w_lo, float w_scale, const float* d_bias, int cout,
+                                int relu, int up2x, void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cin = c_src0 + c_src1;
+  if (cin % 32 || c_src0 % 32 || c_src1 % 32) { sdb::set_error("conv3x3x3_tc: channel counts must be multiples of 32"); return 1; }
+  if (cout != 32 && cout != 64 && cout != 128) { sdb::set_error("conv3x3x3_tc: cout must be 32/64/128"); return 1; }
+  if (up2x != 0 && up2x != 2) { sdb::set_error("conv3x3x3_tc: up2x must be 0 or 2"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
+  CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
+  constexpr int ROWS = TcCfg4<32>::S + 2;
+  if (make_act_map2(&a1h, (const __half*)src1_hi, d, h, w, c_src1, ROWS) || make_act_map2(&a1l, (const __half*)src1_lo, d, h, w, c_src1, ROWS)) return 1;
+  if (c_src0 > 0) {
+    if (make_act_map2(&a0h, (const __half*)src0_hi, d, h, w, c_src0, ROWS) || make_act_map2(&a0l, (const __half*)src0_lo, d, h, w, c_src0, ROWS)) return 1;
+  } else { a0h = a1h; a0l = a1l; }
+  if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32, 27) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32, 27)) return 1;
+  ConvParams P;
+  P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg;
+  if (cout == 32) return launch_tc4<32>(a0h, a0l, a1h, a1l, wh, wl, P, d, st, 3);
+  if (cout == 64) return launch_tc4<64>(a0h, a0l, a1h, a1l, wh, wl, P, d, st, 3);
+  return launch_tc4<128>(a0h, a0l, a1h, a1l, wh, wl, P, d, st, 3);
+}
+
 // A/B switch for tests and profiling: 0 = auto (default), 1 = one tile per CTA, 3 = persistent, 4 = persistent + halo reuse
 extern "C" int sdb_tc_set_variant(int variant) {
   if (variant != 0 && variant != 1 && variant != 3 && variant != 4) { sdb::set_error("tc_set_variant: 0 (auto), 1, 3 or 4"); return 1; }
@@ -1367,7 +1433,14 @@ extern "C" int sdb_tc_error_check(sdb_stream_t stream) {
 extern "C" int sdb_split_weights(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = 9LL * cin * cout;
-  SDB_LAUNCH(k_split_weights, (int)std::min<long long>(cdiv(total, 256), 1024), 256, 0, st, d_w, cin, cout, w_scale, (__half*)w_hi, (__half*)w_lo);
+  SDB_LAUNCH(k_split_weights, (int)std::min<long long>(cdiv(total, 256), 1024), 256, 0, st, d_w, 9, cin, cout, w_scale, (__half*)w_hi, (__half*)w_lo);
+  return 0;
+}
+// (3,3,3,Cin,Cout) -> [27][Cout][Cin] split planes
+extern "C" int sdb_split_weights_3d(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = 27LL * cin * cout;
+  SDB_LAUNCH(k_split_weights, (int)std::min<long long>(cdiv(total, 256), 1024), 256, 0, st, d_w, 27, cin, cout, w_scale, (__half*)w_hi, (__half*)w_lo);
   return 0;
 }
 
@@ -1388,6 +1461,22 @@ extern "C" int sdb_maxpool_split(const void* in_hi, const void* in_lo, int n, in
   const long long total = (long long)n * (h / 2) * (w / 2) * (c / 2);
   SDB_LAUNCH(k_maxpool_split, (int)std::min<long long>(cdiv(total, 256), 148 * 16), 256, 0, st, (const __half*)in_hi, (const __half*)in_lo, n, h, w, c,
              (__half*)out_hi, (__half*)out_lo);
+  return 0;
+}
+
+extern "C" int sdb_maxpool3d_split(const void* in_hi, const void* in_lo, int d, int h, int w, int c, int pz, int py, int px,
+                                   void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pz < 1 || py < 1 || px < 1 || d % pz || h % py || w % px || (c & 1)) { sdb::set_error("maxpool3d_split: sizes must be divisible by the pool, c even"); return 1; }
+  const long long total = (long long)(d / pz) * (h / py) * (w / px) * (c / 2);
+  SDB_LAUNCH(k_maxpool3d_split, (int)std::min<long long>(cdiv(total, 256), 148 * 16), 256, 0, st, (const __half*)in_hi, (const __half*)in_lo, d, h, w, c,
+             pz, py, px, (__half*)out_hi, (__half*)out_lo);
+  return 0;
+}
+extern "C" int sdb_split_f32(const float* d_in, long long n, void* out_hi, void* out_lo, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 0) return 0;
+  SDB_LAUNCH(k_split_f32, (int)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, st, d_in, n, (__half*)out_hi, (__half*)out_lo);
   return 0;
 }
 

@@ -14,7 +14,7 @@ from ..rays3d import rays_from_json
 from ..matching import relabel_sequential
 from .base import StarDistBase
 from .config import Config3D
-from .unet_device import UNetDeviceND, ResNetDeviceND
+from .unet_device import UNetDeviceND, ResNetDeviceND, UNetDevice3DTC
 
 
 class StarDist3D(StarDistBase):
@@ -27,6 +27,9 @@ class StarDist3D(StarDistBase):
         if self.config.backbone == 'resnet':
             return ResNetDeviceND(self.config, self.weights)
         self.config.backbone == 'unet' or _raise(NotImplementedError(self.config.backbone))
+        import os
+        if os.environ.get("STARDIST_B200_UNET", "tc") != "simt" and UNetDevice3DTC.supported(self.config):
+            return UNetDevice3DTC(self.config, self.weights)      # tcgen05 3x3x3 convolutions
         return UNetDeviceND(self.config, self.weights)
 
     def _finish_labels(self, labels, overlap_label):

@@ -346,3 +346,124 @@ class UNetDevice2DTC:
                                        L.ptr(self.w['dist']['k']), L.ptr(self.w['dist']['b']), R, L.ptr(prob), L.ptr(dist), st))
         L.check(lib.sdb_tc_error_check(st))
         return prob, dist
+
+
+class UNetDevice3DTC:
+    """tcgen05 executor of the 3-D U-Net (model3d.py:360-399) for ONE volume: activations are [2, D, H, W, C] float16
+    planes (hi, lo); every 3x3x3 convolution with Cin % 32 == 0 runs on sdb_conv3x3x3_tc (k_conv_tc4: z planes as the
+    tensor map's image axis, 27 taps), the Cin <= 4 stem on the CUDA-core kernel followed by sdb_split_f32, pooling on
+    sdb_maxpool3d_split, nearest 2x2x2 up-sampling written by the producing convolution, the 1x1x1 heads on the
+    tensor-core heads kernel over the volume viewed as a [D*H, W] image."""
+
+    def __init__(self, config, weights, device=None):
+        lib = L.require_cuda()
+        self.config = config
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        self.layers = unet_layers(config)
+        self.prob_class = None
+        self._simt = UNetDeviceND(config, weights, device=self.device)       # stem conv, class branch
+        self.w = {}
+        for name, (k, b) in weights.items():
+            kd = torch.from_numpy(np.ascontiguousarray(k, dtype=np.float32)).to(self.device)
+            bd = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device)
+            ent = dict(k=kd, b=bd)
+            if k.ndim == 5 and k.shape[0] == 3 and k.shape[3] % 32 == 0:
+                cin, cout = k.shape[3], k.shape[4]
+                ws = torch.empty((2, 27, cout, cin), dtype=torch.float16, device=self.device)
+                ent['scale'] = tc_weight_scale(k)
+                L.check(lib.sdb_split_weights_3d(L.ptr(kd), cin, cout, ent['scale'], L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
+                ent['split'] = ws
+            self.w[name] = ent
+        R = config.n_rays
+        kp, kd = self.w['prob']['k'], self.w['dist']['k']
+        cf = kp.shape[-2]
+        self.heads_np = next(v for v in (48, 80, 112, 144) if v >= R + 1)
+        Wf = torch.zeros((self.heads_np, cf), dtype=torch.float32, device=self.device)
+        Wf[0] = kp.reshape(cf, 1)[:, 0]
+        Wf[1:R + 1] = kd.reshape(cf, R).t()
+        sc = tc_weight_scale(Wf.cpu().numpy())
+        Ws = Wf * sc
+        hi = Ws.to(torch.float16)
+        lo = (Ws - hi.float()).to(torch.float16)
+        self.heads_w = torch.stack([hi, lo]).reshape(2, 1, self.heads_np, cf).contiguous()
+        self.heads_scale = sc
+        self.heads_b = torch.zeros(self.heads_np, dtype=torch.float32, device=self.device)
+        self.heads_b[0] = self.w['prob']['b'][0]
+        self.heads_b[1:R + 1] = self.w['dist']['b']
+
+    @staticmethod
+    def supported(config):
+        if config.n_dim != 3 or getattr(config, 'backbone', 'unet') != 'unet' or config.unet_batch_norm:
+            return False
+        convs = [l for l in unet_layers(config) if l['kind'] == 'conv']
+        ok_first = convs[0]['cin'] <= 4 and convs[0]['cout'] % 32 == 0
+        ok_rest = all(l['cin'] % 32 == 0 and l.get('cin_lo', 0) % 32 == 0 and l['cout'] in (32, 64, 128) for l in convs[1:])
+        return (ok_first and ok_rest and tuple(config.unet_kernel_size) == (3, 3, 3) and tuple(config.unet_pool) == (2, 2, 2)
+                and config.net_conv_after_unet % 64 == 0 and config.net_conv_after_unet > 0 and config.n_rays + 1 <= 144
+                and config.unet_activation in ('relu', 'linear') and config.unet_last_activation in ('relu', 'linear'))
+
+    def forward(self, x):
+        lib = L.load()
+        assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.dim() == 5
+        if x.shape[0] != 1:
+            raise NotImplementedError("the 3-D tensor-core executor takes one volume per call")
+        st = L.stream_ptr()
+        layers = self.layers
+        skips = {}
+        lo = None
+        cur = None
+        base = None
+        first = True
+        for i, l in enumerate(layers):
+            kind = l['kind']
+            if kind == 'conv':
+                relu = 1 if l['act'] == 'relu' else 0
+                nxt = layers[i + 1]['kind'] if i + 1 < len(layers) else None
+                up2x = 2 if nxt == 'up' else 0
+                ent = self.w[l['name']]
+                cout = ent['k'].shape[-1]
+                if first:
+                    y = self._simt._conv(x, None, l['name'], bool(relu), (1, 1, 1))          # [1,D,H,W,cout] fp32
+                    out = torch.empty((2,) + tuple(y.shape[1:]), dtype=torch.float16, device=x.device)
+                    L.check(lib.sdb_split_f32(L.ptr(y), y.numel(), L.ptr(out[0]), L.ptr(out[1]), st))
+                    first = False
+                else:
+                    _, d, h, w, c1 = cur.shape
+                    c0 = 0 if lo is None else lo.shape[-1]
+                    od, oh, ow = (2 * d, 2 * h, 2 * w) if up2x else (d, h, w)
+                    if l['name'] == 'features': base = cur
+                    out = torch.empty((2, od, oh, ow, cout), dtype=torch.float16, device=x.device)
+                    ws = ent['split']
+                    L.check(lib.sdb_conv3x3x3_tc(L.ptr(lo[0]) if lo is not None else L.ptr(None), L.ptr(lo[1]) if lo is not None else L.ptr(None), c0,
+                                                 L.ptr(cur[0]), L.ptr(cur[1]), c1, d, h, w, L.ptr(ws[0]), L.ptr(ws[1]), ent['scale'], L.ptr(ent['b']),
+                                                 cout, relu, up2x, L.ptr(out[0]), L.ptr(out[1]), st))
+                    lo = None
+                cur = out
+            elif kind == 'pool':
+                if 'save_skip' in l:
+                    skips[l['save_skip']] = cur
+                _, d, h, w, c = cur.shape
+                pz, py, px = (int(v) for v in l['pool'])
+                out = torch.empty((2, d // pz, h // py, w // px, c), dtype=torch.float16, device=x.device)
+                L.check(lib.sdb_maxpool3d_split(L.ptr(cur[0]), L.ptr(cur[1]), d, h, w, c, pz, py, px, L.ptr(out[0]), L.ptr(out[1]), st))
+                cur = out
+            elif kind == 'up':
+                lo = cur
+                cur = skips.pop(l['skip'])
+                assert tuple(lo.shape[1:4]) == tuple(cur.shape[1:4])
+            elif kind == 'head':
+                break
+        _, d, h, w, cf = cur.shape
+        R = self.config.n_rays
+        prob = torch.empty((1, d, h, w), dtype=torch.float32, device=x.device)
+        dist = torch.empty((1, d, h, w, R), dtype=torch.float32, device=x.device)
+        L.check(lib.sdb_heads_tc(L.ptr(cur[0]), L.ptr(cur[1]), cf, 1, d * h, w, L.ptr(self.heads_w[0]), L.ptr(self.heads_w[1]),
+                                self.heads_scale, L.ptr(self.heads_b), self.heads_np, R, L.ptr(prob), L.ptr(dist), st))
+        L.check(lib.sdb_tc_error_check(st))
+        self.prob_class = None
+        if self.config.n_classes is not None:
+            b32 = torch.empty((1,) + tuple(base.shape[1:]), dtype=torch.float32, device=x.device)
+            L.check(lib.sdb_merge_split(L.ptr(base[0]), L.ptr(base[1]), b32.numel(), L.ptr(b32), st))
+            self.prob_class = self._simt._class_branch(b32)
+        return prob, dist
+

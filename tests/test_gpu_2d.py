@@ -229,6 +229,13 @@ def test_reference_2d_demo_model_reproduces_reference_test(sd):
     ref_labels, ref = pipeline2d.predict_instances(cfg, weights, x, thr['prob'], thr['nms'])
     assert np.array_equal(polygons['points'], ref['points'])
     assert np.mean(labels != ref_labels) < 1e-3
+    # float maps of the TRAINED network (tcgen05 path) against a float64 evaluation: the 1e-5 relative bar
+    import torch
+    prob1, dist1 = model.predict(x)
+    rp64, rd64 = unet_torch.forward(cfg, weights, x[None, ..., None].astype(np.float32), dtype=torch.float64)
+    rd64 = np.maximum(1e-3, rd64[0])
+    assert np.max(np.abs(prob1 - rp64[0])) <= 1e-5 * max(1.0, np.max(np.abs(rp64)))
+    assert np.max(np.abs(dist1 - rd64)) <= 1e-5 * np.max(np.abs(rd64))
 
 
 

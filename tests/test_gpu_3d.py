@@ -98,9 +98,10 @@ def test_empty_inputs_3d(sd):
     assert sd.polyhedron_to_label(np.zeros((0, 16)), np.zeros((0, 3)), rays, (5, 6, 7), verbose=False).shape == (5, 6, 7)
 
 
-def test_unet3d_forward_vs_torch_fp32(sd):
+def test_unet3d_forward_vs_torch_fp32(sd, monkeypatch):
     import torch
     from oracle import unet_torch
+    monkeypatch.setenv("STARDIST_B200_UNET", "simt")        # the exact-fp32 CUDA-core executor
     cfg = sd.Config3D(n_rays=16, rays=None) if False else sd.Config3D(rays=sd.Rays_GoldenSpiral(16))
     model = sd.StarDist3D(cfg, name=None, basedir=None)
     rng = np.random.default_rng(3)
@@ -142,7 +143,8 @@ def test_predict_3d_n_tiles_equals_untiled(sd):
     model = sd.StarDist3D(sd.Config3D(rays=sd.Rays_GoldenSpiral(12)), name=None, basedir=None)
     p1, d1 = model.predict(vol)
     p2, d2 = model.predict(vol, n_tiles=(1, 3, 2))
-    assert p1.shape == p2.shape and np.array_equal(p1, p2) and np.array_equal(d1, d2)     # one (CUDA-core) kernel: bitwise
+    assert p1.shape == p2.shape
+    assert np.max(np.abs(p1 - p2)) <= 1e-5 and np.max(np.abs(d1 - d2)) <= 1e-5 * max(1e-3, np.max(np.abs(d1))) + 1e-7
 
 
 def test_resnet_forward_vs_torch_fp32(sd):
@@ -209,3 +211,61 @@ def test_multiclass_head_3d(sd):
         assert res['class_prob'].shape == (len(res['prob']), 3)
         p = res['points']
         assert np.array_equal(res['class_prob'], pc[p[:, 0], p[:, 1], p[:, 2]])
+
+
+@pytest.mark.parametrize("d,h,w,c0,c1,cout,relu,up2x", [(5, 12, 40, 0, 32, 32, 1, 0), (4, 9, 130, 0, 64, 64, 1, 0), (3, 6, 20, 32, 32, 32, 0, 0),
+                                                        (4, 8, 16, 0, 64, 32, 1, 2), (6, 10, 24, 0, 32, 128, 1, 0), (2, 5, 200, 64, 64, 64, 1, 0)])
+def test_conv3x3x3_tc_single_layer(d, h, w, c0, c1, cout, relu, up2x):
+    """tcgen05 3x3x3 convolution (z planes as the tensor map's image axis, 27 taps) vs a float64 conv3d of the same split
+    operands; two-source (concat) inputs and the 2x2x2 up-sampling epilogue"""
+    import torch, torch.nn.functional as F
+    from stardist_b200 import _lib as L
+    from stardist_b200.models.unet_device import tc_weight_scale
+    lib = L.require_cuda()
+    g = torch.Generator(device='cpu').manual_seed(d * 131 + w + cout)
+    cin = c0 + c1
+    x = torch.randn((d, h, w, cin), generator=g).cuda()
+    k = (torch.randn((3, 3, 3, cin, cout), generator=g) * (2.0 / (27 * cin)) ** 0.5).cuda()
+    b = (torch.randn(cout, generator=g) * 0.1).cuda()
+    hi = x.to(torch.float16); lo = (x - hi.float()).to(torch.float16)
+    xs = torch.stack([hi, lo]).contiguous()
+    x_eff = xs[0].double() + xs[1].double()
+    ws = torch.empty((2, 27, cout, cin), dtype=torch.float16, device='cuda')
+    wsc = tc_weight_scale(k.cpu().numpy())
+    L.check(lib.sdb_split_weights_3d(L.ptr(k.contiguous()), cin, cout, wsc, L.ptr(ws[0]), L.ptr(ws[1]), L.stream_ptr()))
+    k_eff = ((ws[0].double() + ws[1].double()) / wsc).reshape(3, 3, 3, cout, cin)          # [dz,dy,dx,cout,cin]
+    src1 = xs[..., c0:].contiguous(); src0 = xs[..., :c0].contiguous() if c0 else None
+    od, oh, ow = (2 * d, 2 * h, 2 * w) if up2x else (d, h, w)
+    out = torch.zeros((2, od, oh, ow, cout), dtype=torch.float16, device='cuda')
+    L.check(lib.sdb_conv3x3x3_tc(L.ptr(src0[0]) if c0 else L.ptr(None), L.ptr(src0[1]) if c0 else L.ptr(None), c0, L.ptr(src1[0]), L.ptr(src1[1]), c1,
+                                 d, h, w, L.ptr(ws[0]), L.ptr(ws[1]), wsc, L.ptr(b), cout, relu, up2x, L.ptr(out[0]), L.ptr(out[1]), L.stream_ptr()))
+    L.check(lib.sdb_tc_error_check(L.stream_ptr()))
+    got = out[0].double() + out[1].double()
+    y = F.conv3d(x_eff.permute(3, 0, 1, 2)[None], k_eff.permute(3, 4, 0, 1, 2), b.double(), padding=1)[0]
+    if relu: y = F.relu(y)
+    want = y.permute(1, 2, 3, 0)
+    if up2x: want = want.repeat_interleave(2, 0).repeat_interleave(2, 1).repeat_interleave(2, 2)
+    assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+def test_unet3d_tc_vs_torch_fp32(sd):
+    """3-D U-Net on the tensor cores against a float64 evaluation.  prob: 3e-7 of its scale.  dist of a RANDOM-INIT net is a
+    near-cancelling sum (max ~0.07 from O(1) features): the split-fp16 / TMEM-accumulated path leaves ~9e-7 absolute, i.e.
+    1.3e-5 of that tiny scale (tests/tools/unet3d_tc_error.py; CUDA-core fp32: 1.2e-6, torch-CPU fp32: 6e-7) -- the bound is
+    1e-5 of max(map scale, feature scale 1) and 2e-5 of the map scale itself."""
+    import torch
+    from oracle import unet_torch
+    from stardist_b200.models.unet_device import UNetDevice3DTC
+    for shape, grid in (((16, 32, 48), (1, 1, 1)), ((8, 24, 136), (1, 2, 2))):
+        cfg = sd.Config3D(rays=sd.Rays_GoldenSpiral(96), grid=grid)
+        model = sd.StarDist3D(cfg, name=None, basedir=None)
+        assert isinstance(model.net, UNetDevice3DTC)
+        rng = np.random.default_rng(shape[2])
+        vol = rng.uniform(0, 1, shape).astype(np.float32)
+        prob, dist = model.net.forward(torch.from_numpy(vol[None, ..., None]).cuda())
+        rp64, rd64 = unet_torch.forward(cfg, model.weights, vol[None, ..., None], dtype=torch.float64)
+        p, dd = prob.cpu().numpy().astype(np.float64), dist.cpu().numpy().astype(np.float64)
+        assert p.shape == rp64.shape and dd.shape == rd64.shape
+        assert np.max(np.abs(p - rp64)) <= 1e-5 * max(1.0, np.max(np.abs(rp64)))
+        err, scale = float(np.max(np.abs(dd - rd64))), float(np.max(np.abs(rd64)))
+        assert err <= 1e-5 * max(1.0, scale) and err <= 2e-5 * scale, (err, scale)
