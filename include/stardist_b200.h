@@ -119,6 +119,14 @@ int sdb_polyhedron_to_label(const float* d_dist, const float* d_points, const fl
                             int use_overlap_label, int overlap_label, int* d_result,
                             sdb_stream_t stream);
 
+/* relabel_sequential on a device label map (stardist/matching.py:319-406; callers model3d.py:645, base.py:959):
+ * labels occurring in d_labels[n] (values in [0, max_label], 16-byte aligned) are renumbered offset, offset+1, ...
+ * in ascending order, 0 stays 0, in place.  d_forward_map: scratch of max_label + 3 ints; on return [0..max_label]
+ * holds the forward map (matching.py:399-401).  *h_count = number of distinct non-zero labels.  Negative labels
+ * are an error like in the reference (matching.py:374).  Synchronises the stream once (count read-back). */
+int sdb_relabel_sequential(int* d_labels, long long n, int max_label, int offset, int* d_forward_map,
+                           int* h_count, sdb_stream_t stream);
+
 /* 3D NMS on device arrays (see _LIB_non_maximum_suppression_sparse); d_keep is uint8[n_polys]. */
 int sdb_nms3d(const float* d_dist, const float* d_points, const float* d_verts, const int* d_faces,
               int n_polys, int n_rays, int n_faces, float threshold, int use_bbox, int use_kdtree,

@@ -190,6 +190,105 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// relabel_sequential (stardist/matching.py:319-406; caller model3d.py:645): the labels that occur in the map
+// are renumbered offset, offset+1, ... in ascending order, 0 stays 0.  Three passes: presence flags (one int per
+// label, benign store race), a single-CTA scan of the flags into the forward map, and -- only if some label is
+// missing or offset != 1 -- the rewrite of the map.  Integer work, bit-exact.
+namespace {
+__global__ void __launch_bounds__(256) k_mark_labels(const int* __restrict__ lab, long long n, int max_label,
+                                                     int* __restrict__ present, int* __restrict__ bad) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  const int4* lab4 = reinterpret_cast<const int4*>(lab);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int4 v = lab4[i];
+    const int a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (a[k] < 0 || a[k] > max_label) *bad = 1;
+      else if (a[k] > 0) present[a[k]] = 1;
+    }
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int v = lab[i];
+    if (v < 0 || v > max_label) *bad = 1;
+    else if (v > 0) present[v] = 1;
+  }
+}
+
+// present[1..max_label] (0/1) -> forward map in place; count[0] = number of labels present
+__global__ void __launch_bounds__(1024) k_scan_labels(int* __restrict__ present, int max_label, int offset, int* __restrict__ count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 1; base <= max_label; base += 1024) {
+    const int idx = base + tid;
+    const int f = (idx <= max_label) ? (present[idx] != 0) : 0;
+    int incl = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += t; }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int before = carry + (wid ? s_warp[wid - 1] : 0) + incl - f;      // labels present below idx
+    if (idx <= max_label) present[idx] = f ? offset + before : 0;
+    __syncthreads();
+    if (tid == 0) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (tid == 0) { present[0] = 0; count[0] = s_carry; }
+}
+
+__global__ void __launch_bounds__(256) k_apply_labels(int* __restrict__ lab, long long n, const int* __restrict__ fwd) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  int4* lab4 = reinterpret_cast<int4*>(lab);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int4 v = lab4[i];
+    if ((v.x | v.y | v.z | v.w) == 0) continue;
+    v.x = __ldg(fwd + v.x); v.y = __ldg(fwd + v.y); v.z = __ldg(fwd + v.z); v.w = __ldg(fwd + v.w);
+    lab4[i] = v;
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int v = lab[i];
+    if (v) lab[i] = __ldg(fwd + v);
+  }
+}
+}  // namespace
+
+extern "C" int sdb_relabel_sequential(int* d_labels, long long n, int max_label, int offset, int* d_forward_map,
+                                      int* h_count, sdb_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (offset <= 0) { sdb::set_error("relabel_sequential: offset must be strictly positive"); return 1; }   // matching.py:372
+  if (max_label < 0 || n < 0) { sdb::set_error("relabel_sequential: negative size"); return 1; }
+  if ((reinterpret_cast<uintptr_t>(d_labels) & 15) != 0) { sdb::set_error("relabel_sequential: label map must be 16-byte aligned"); return 1; }
+  // d_forward_map: max_label + 3 ints; [max_label+1] = count, [max_label+2] = out-of-range flag
+  SDB_CUDA(cudaMemsetAsync(d_forward_map, 0, (size_t)(max_label + 3) * sizeof(int), st));
+  int* d_count = d_forward_map + max_label + 1;
+  int* d_bad = d_forward_map + max_label + 2;
+  const int grid = (int)std::min<long long>(std::max<long long>(cdiv(n >> 2, 256), 1), 148 * 8);
+  if (n > 0) SDB_LAUNCH(k_mark_labels, grid, 256, 0, st, d_labels, n, max_label, d_forward_map, d_bad);
+  SDB_LAUNCH(k_scan_labels, 1, 1024, 0, st, d_forward_map, max_label, offset, d_count);
+  int h[2] = {0, 0};
+  SDB_CUDA(cudaMemcpyAsync(h, d_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  SDB_CUDA(cudaStreamSynchronize(st));
+  if (h[1]) { sdb::set_error("relabel_sequential: label outside [0, max_label] (negative values cannot be relabelled, matching.py:374)"); return 1; }
+  if (h_count) *h_count = h[0];
+  if (n > 0 && !(h[0] == max_label && offset == 1))                       // otherwise the map is already sequential
+    SDB_LAUNCH(k_apply_labels, grid, 256, 0, st, d_labels, n, d_forward_map);
+  return 0;
+}
+
 // reference C ABI (stardist3d_lib.h:67-82): host pointers, result int32[nz*ny*nx] zero-initialised by the caller
 extern "C" void _LIB_polyhedron_to_label(const float* dist, const float* points, const float* verts, const int* faces,
                                          const int n_polys, const int n_rays, const int n_faces, const int* labels,

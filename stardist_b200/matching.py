@@ -32,6 +32,30 @@ def relabel_sequential(label_field, offset=1):
     return relabeled, forward_map, inverse_map
 
 
+def relabel_sequential_device(label_field, offset=1, max_label=None):
+    """relabel_sequential (stardist/matching.py:319-406) on a device int32 label map, IN PLACE (sdb_relabel_sequential).
+    Returns (label_field, forward_map[max_label + 1] device int32, n_labels).  `max_label`: an upper bound of the values
+    (default: computed on the device).  No CPU fallback: raises without the CUDA library."""
+    import ctypes, torch
+    from . import _lib as L
+    lib = L.require_cuda()
+    if not (isinstance(label_field, torch.Tensor) and label_field.is_cuda and label_field.dtype == torch.int32 and label_field.is_contiguous()):
+        raise ValueError("relabel_sequential_device expects a contiguous CUDA int32 tensor")
+    if int(offset) <= 0:
+        raise ValueError("Offset must be strictly positive.")
+    if max_label is None:
+        max_label = int(label_field.max()) if label_field.numel() else 0
+    fwd = torch.empty(int(max_label) + 3, dtype=torch.int32, device=label_field.device)
+    cnt = ctypes.c_int(0)
+    rc = lib.sdb_relabel_sequential(L.ptr(label_field), label_field.numel(), int(max_label), int(offset), L.ptr(fwd), ctypes.byref(cnt), L.stream_ptr())
+    if rc != 0:
+        msg = L.load().sdb_last_error().decode('utf-8', 'replace')
+        if 'negative' in msg:
+            raise ValueError("Cannot relabel array that contains negative values.")
+        L.check(rc)
+    return label_field, fwd[:int(max_label) + 1], int(cnt.value)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Detection metrics (stardist/matching.py:109-232).  Host-side evaluation helper: pairs ground-truth and predicted
 # objects by an optimal assignment on the IoU (or IoT / IoP) matrix and counts tp / fp / fn at a threshold.

@@ -3,6 +3,7 @@
 Mirrors stardist/models/model3d.py: Config3D (:129-311, in config.py), StarDist3D._build_unet
 (:360-399 -> UNetDeviceND), _instances_from_prediction (:589-674), _axes_div_by (:677-691).
 """
+import ctypes
 import numpy as np
 import torch
 
@@ -49,6 +50,22 @@ class StarDist3D(StarDistBase):
         if prob_thresh is None: prob_thresh = self.thresholds.prob
         if nms_thresh is None: nms_thresh = self.thresholds.nms
         rays = rays_from_json(self.config.rays_json)
+        if points is not None and np.issubdtype(np.asarray(points).dtype, np.integer):
+            # sparse candidates (model3d.py:601-606): sort on the host like nms.py:313 (stable), then the device-resident
+            # path (NMS, label rendering and relabel_sequential without intermediate host copies)
+            prob, dist, points = np.asarray(prob), np.asarray(dist), np.asarray(points)
+            assert dist.ndim == 2 and prob.ndim == 1 and points.ndim == 2 and dist.shape[-1] == len(rays) \
+                and points.shape[-1] == 3 and len(prob) == len(dist) == len(points)
+            from ..nms import _argsort_desc
+            order = _argsort_desc(prob)
+            dev = self.net.device
+            up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a[order], dt)).to(dev)
+            cand = dict(n=len(order), prob=up(prob, np.float32), dist=up(dist, np.float32), points_f32=up(points, np.float32))
+            if prob_class is not None:
+                cand['prob_class'] = up(np.asarray(prob_class), np.float32)
+            kw = {k: nms_kwargs[k] for k in ('use_bbox', 'use_kdtree', 'verbose') if k in nms_kwargs}
+            return self._instances_from_candidates_device(img_shape, cand, nms_thresh=nms_thresh, scale=scale, return_labels=return_labels,
+                                                          overlap_label=overlap_label, **kw)
         if points is not None:
             points, probi, disti, indsi = non_maximum_suppression_3d_sparse(dist, prob, points, rays, nms_thresh=nms_thresh, **nms_kwargs)
             if prob_class is not None:
@@ -107,6 +124,7 @@ class StarDist3D(StarDistBase):
             verts_d = torch.from_numpy(np.ascontiguousarray(rays.vertices, np.float32)).to(dev)
             pts_d = torch.from_numpy(np.ascontiguousarray(points, np.float32)).to(dev)
         labels = None
+        lab_host = None
         if return_labels:
             if nk == 0:
                 labels = np.zeros(tuple(img_shape), np.uint16)      # geom3d.py:128-131
@@ -121,9 +139,17 @@ class StarDist3D(StarDistBase):
                                                    1 if overlap_label is not None else 0, 0 if overlap_label is None else int(overlap_label),
                                                    L.ptr(lab_d), L.stream_ptr()))
                 self._mark('label_end')
-                labels = self._finish_labels(lab_d.cpu().numpy(), overlap_label)
-        disti = disti_d.cpu().numpy()
-        probi = probi_d.cpu().numpy()
+                if overlap_label is None:
+                    # relabel_sequential (model3d.py:645) on the device: ids are 1..nk, polyhedra that painted no voxel drop out
+                    fwd = torch.empty(nk + 3, dtype=torch.int32, device=dev)
+                    cnt = ctypes.c_int(0)
+                    L.check(lib.sdb_relabel_sequential(L.ptr(lab_d), lab_d.numel(), nk, 1, L.ptr(fwd), ctypes.byref(cnt), L.stream_ptr()))
+                    lab_host = lab_d
+                else:
+                    labels = self._finish_labels(lab_d.cpu().numpy(), overlap_label)
+        (lab_np, disti, probi), _ = self._to_host([lab_host, disti_d, probi_d])
+        if lab_np is not None:
+            labels = lab_np
         self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + disti.nbytes + points.nbytes + probi.nbytes + (0 if labels is None else labels.nbytes)
         res_dict = dict(dist=disti, points=points, prob=probi, rays=rays, rays_vertices=rays.vertices, rays_faces=rays.faces)
         if 'prob_class' in cand:                            # model3d.py:663-667

@@ -225,3 +225,19 @@ def test_oracle_reproduces_reference_3d_demo_test():
     st = matching(mask, labels, thresh=0.5)
     assert labels.shape == img.shape and (st.fp, st.tp, st.fn) == demo3d.REFERENCE_TEST_STATS
 
+
+
+def test_relabel_sequential_reference_docstring_vectors():
+    """the known answers in the reference's docstring (stardist/matching.py:363-381)"""
+    from stardist_b200.matching import relabel_sequential
+    lf = np.array([1, 1, 5, 5, 8, 99, 42])
+    relab, fw, inv = relabel_sequential(lf)
+    assert relab.tolist() == [1, 1, 2, 2, 3, 5, 4]
+    assert np.flatnonzero(fw).tolist() == [1, 5, 8, 42, 99] and fw[[1, 5, 8, 42, 99]].tolist() == [1, 2, 3, 4, 5] and len(fw) == 100
+    assert inv.tolist() == [0, 1, 5, 8, 42, 99]
+    assert (fw[lf] == relab).all() and (inv[relab] == lf).all()
+    assert relabel_sequential(lf, offset=5)[0].tolist() == [5, 5, 6, 6, 7, 9, 8]
+    with pytest.raises(ValueError):
+        relabel_sequential(lf, offset=0)
+    with pytest.raises(ValueError):
+        relabel_sequential(np.array([1, -1]))

@@ -269,3 +269,77 @@ def test_unet3d_tc_vs_torch_fp32(sd):
         assert np.max(np.abs(p - rp64)) <= 1e-5 * max(1.0, np.max(np.abs(rp64)))
         err, scale = float(np.max(np.abs(dd - rd64))), float(np.max(np.abs(rd64)))
         assert err <= 1e-5 * max(1.0, scale) and err <= 2e-5 * scale, (err, scale)
+
+
+@pytest.mark.parametrize("n,max_label,offset,density", [(0, 0, 1, 0.0), (1, 5, 1, 1.0), (1003, 17, 1, 0.5), (4096, 3000, 7, 0.2),
+                                                         (100003, 5000, 1, 0.9), (65536, 40, 1, 1.0), (300001, 70000, 3, 0.3)])
+def test_relabel_sequential_device_matches_host(sd, n, max_label, offset, density):
+    """sdb_relabel_sequential == relabel_sequential (stardist/matching.py:319-406), bit-exact: relabelled map, forward map, count"""
+    import torch
+    from stardist_b200.matching import relabel_sequential, relabel_sequential_device
+    rng = np.random.default_rng(n + max_label)
+    present = np.flatnonzero(rng.uniform(size=max_label + 1) < density)
+    present = present[present > 0]
+    lab = (rng.choice(present, n) if len(present) else np.zeros(n, np.int64)).astype(np.int32)
+    lab[rng.uniform(size=n) < 0.4] = 0
+    t = torch.from_numpy(lab.copy()).cuda()
+    out, fwd, cnt = relabel_sequential_device(t, offset=offset, max_label=max_label)
+    if n == 0:
+        assert cnt == 0; return
+    want, wfwd, winv = relabel_sequential(lab, offset)
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert cnt == len(winv) - offset
+    assert np.array_equal(fwd.cpu().numpy()[:len(wfwd)], wfwd) and not fwd.cpu().numpy()[len(wfwd):].any()
+    # already sequential input with offset 1: untouched
+    t2 = torch.from_numpy(want.astype(np.int32)).cuda() if offset == 1 else None
+    if t2 is not None:
+        out2, _, cnt2 = relabel_sequential_device(t2)
+        assert cnt2 == cnt and np.array_equal(out2.cpu().numpy(), want)
+
+
+def test_relabel_sequential_device_rejects_negative(sd):
+    import torch
+    from stardist_b200.matching import relabel_sequential_device
+    t = torch.tensor([0, 3, -1, 2], dtype=torch.int32, device="cuda")
+    with pytest.raises(ValueError):
+        relabel_sequential_device(t, max_label=3)
+
+
+def test_instances_from_prediction_sparse_points_3d(sd, g3):
+    """StarDist3D._instances_from_prediction(points=...) (model3d.py:601-606, device-resident route) == golden NMS decisions
+    + polyhedron_to_label + host relabel_sequential"""
+    from stardist_b200.geometry.geom3d import polyhedron_to_label
+    from stardist_b200.matching import relabel_sequential
+    name = "r32_noise01_thr01"
+    shape, noise, n_rays, pthr, nthr, seed, aniso = cases.NMS3D_CASES[name]
+    prob, dist = cases.create_random_data_3d(shape, noise, n_rays, seed)
+    mask = prob > pthr
+    m2 = np.zeros_like(mask); m2[2:-2, 2:-2, 2:-2] = True
+    mask &= m2
+    points = np.stack(np.where(mask), axis=1)
+    d = np.ascontiguousarray(dist[mask], np.float32); s = np.ascontiguousarray(prob[mask], np.float32)
+    rays = cases.rays_golden_spiral(n_rays, aniso)
+    model = sd.StarDist3D(sd.Config3D(rays=rays), name=None, basedir=None)
+    labels, res = model._instances_from_prediction(shape, s, d, points=points, nms_thresh=float(nthr))
+    ind = np.argsort(s, kind='stable')[::-1]
+    keep = np.unpackbits(g3[name + "/keep"])[:len(d)].astype(bool)
+    assert np.array_equal(res['points'], points[ind][keep])
+    assert np.array_equal(res['prob'], s[ind][keep]) and np.array_equal(res['dist'], d[ind][keep])
+    want = polyhedron_to_label(d[ind][keep], points[ind][keep], rays=rays, prob=s[ind][keep], shape=shape)
+    want = relabel_sequential(want)[0]
+    assert labels.dtype == np.int32 and np.array_equal(labels, want)
+
+
+def test_relabel_sequential_device_reference_docstring_vectors(sd):
+    """the known answers in the reference's docstring (stardist/matching.py:363-381) through sdb_relabel_sequential"""
+    import torch
+    from stardist_b200.matching import relabel_sequential_device
+    lf = [1, 1, 5, 5, 8, 99, 42]
+    out, fw, n = relabel_sequential_device(torch.tensor(lf, dtype=torch.int32, device="cuda"))
+    assert out.cpu().tolist() == [1, 1, 2, 2, 3, 5, 4] and n == 5
+    fw = fw.cpu().numpy()
+    assert len(fw) == 100 and np.flatnonzero(fw).tolist() == [1, 5, 8, 42, 99] and fw[[1, 5, 8, 42, 99]].tolist() == [1, 2, 3, 4, 5]
+    out5, _, _ = relabel_sequential_device(torch.tensor(lf, dtype=torch.int32, device="cuda"), offset=5)
+    assert out5.cpu().tolist() == [5, 5, 6, 6, 7, 9, 8]
+    with pytest.raises(ValueError):
+        relabel_sequential_device(torch.tensor(lf, dtype=torch.int32, device="cuda"), offset=0)
