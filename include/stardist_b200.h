@@ -218,6 +218,10 @@ int sdb_split_f32(const float* d_in, long long n, void* out_hi, void* out_lo, sd
  * double-buffered TMEM accumulators and merged hi/lo weight tile, 4 = 3 + halo reuse (one box load per
  * 32-channel block, taps as shifted descriptors).  Results are identical up to fp32 summation order. */
 int sdb_tc_set_variant(int variant);
+/* 1 (default): the small split-fp16 products (lo*Whi, hi*Wlo) accumulate in their own TMEM columns, the main accumulator
+ * takes one truncating tensor-core add per k-step; 0: all products into one accumulator (the round-1 scheme, kept for A/B
+ * error measurements: tests/tools/tc_split_error.py).  Applies to every tcgen05 convolution except k_conv_tc4<128>. */
+int sdb_tc_set_split_acc(int on);
 int sdb_tc_error_check(sdb_stream_t stream);
 /* w_scale: power of two the weights are multiplied by before the split (undone on the accumulator) */
 int sdb_split_weights(const float* d_w, int cin, int cout, float w_scale, void* w_hi, void* w_lo, sdb_stream_t stream);

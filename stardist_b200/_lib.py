@@ -71,6 +71,8 @@ def _declare(lib):
     lib.sdb_tc_error_check.argtypes = [P]
     lib.sdb_tc_set_variant.argtypes = [c_int]
     lib.sdb_tc_set_variant.restype = c_int
+    lib.sdb_tc_set_split_acc.argtypes = [c_int]
+    lib.sdb_tc_set_split_acc.restype = c_int
     lib.sdb_split_weights.argtypes = [P, c_int, c_int, c_float, P, P, P]
     lib.sdb_stem_split.argtypes = [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P]
     lib.sdb_maxpool_split.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, P]

@@ -58,6 +58,8 @@ struct ConvParams {
   // fused features -> heads (k_conv_tc4<128, true>): fp32 head weights [128][36] (columns 0..R-1 = dist, 32 = prob,
   // zero padded) and biases [36]
   const float* fuse_w; const float* fuse_b;
+  int split_acc;         // 1: the two small products (lo*Whi, hi*Wlo) accumulate in their own TMEM columns, so the main
+                         // accumulator takes one truncating add per k-step instead of two or three (network floats)
   unsigned long long* dbg;      // optional [grid][8] wait-cycle counters of k_conv_tc4 (profiling aid), or nullptr
 };
 
@@ -140,6 +142,16 @@ __device__ __forceinline__ bool mbar_wait_t(uint64_t* bar, uint32_t parity, unsi
   return ok;
 }
 
+#define SDB_TMEM_LD32(r, taddr)                                                                                        \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                               \
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"               \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
+                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
+                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
+               : "r"(taddr))
+
 // ---------------------------------------------------------------------------------- the kernel
 template <int N, int KC>
 struct TcCfg {
@@ -150,6 +162,7 @@ struct TcCfg {
   static constexpr int STAGES = (STAGE_BYTES * 4 <= 200 * 1024) ? 4 : ((STAGE_BYTES * 3 <= 200 * 1024) ? 3 : 2);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256));
+  static constexpr int TMEM_ALLOC = 2 * TMEM_COLS;         // second half: correction accumulator (split_acc)
   static constexpr int NPAD32 = (N + 31) / 32 * 32;
   static constexpr uint32_t LAYOUT = (ROWB == 128) ? 2u : 4u;
   static constexpr uint32_t SBO = 8 * ROWB;
@@ -182,7 +195,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_ALLOC) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -229,9 +242,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
           const uint32_t koff = ks * 32;      // 16 fp16 = 32 B along K inside the swizzled row
           const uint64_t dah = make_desc(a_hi + koff, C::SBO, C::LAYOUT), dal = make_desc(a_lo + koff, C::SBO, C::LAYOUT);
           const uint64_t dbh = make_desc(b_hi + koff, C::SBO, C::LAYOUT), dbl = make_desc(b_lo + koff, C::SBO, C::LAYOUT);
-          umma_f16(tmem_base, dah, dbh, C::IDESC, (kb | ks) ? 1u : 0u);
-          umma_f16(tmem_base, dal, dbh, C::IDESC, 1u);
-          umma_f16(tmem_base, dah, dbl, C::IDESC, 1u);
+          const uint32_t first = (kb | ks) ? 1u : 0u;
+          const uint32_t dcorr = tmem_base + (P.split_acc ? (uint32_t)C::TMEM_COLS : 0u);
+          umma_f16(tmem_base, dah, dbh, C::IDESC, first);
+          umma_f16(dcorr, dal, dbh, C::IDESC, P.split_acc ? first : 1u);
+          umma_f16(dcorr, dah, dbl, C::IDESC, 1u);
         }
         tcgen05_commit(&empty_bar[s]);       // frees the smem stage when these MMAs retire
       }
@@ -260,6 +275,13 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
                        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                      : "r"(taddr));
+        if (P.split_acc) {                       // warp-uniform: add the correction accumulator
+          uint32_t r2[32];
+          SDB_TMEM_LD32(r2, taddr + (uint32_t)C::TMEM_COLS);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (in_img && P.heads_R > 0) {
           // heads: channel 0 -> sigmoid -> prob, channels 1..R -> dist (fp32)
@@ -309,7 +331,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_ALLOC) : "memory");
   }
 }
 
@@ -329,9 +351,15 @@ struct TcCfg3 {
   static constexpr int A_BYTES = 128 * ROWB;
   static constexpr int B_BYTES = N * ROWB;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  // N = 48 / 80 / 112 are the padded 1x1 head counts: their epilogue stages the dist rows of a tile in shared memory
+  // (per warp 32 pixels x HSTRIDE floats) and writes them out as contiguous 512-byte warp stores.  HSTRIDE % 32 == 20:
+  // the per-pixel float4 writes of a quarter warp fall into distinct banks.
+  static constexpr bool HEADN = (N == 48 || N == 80 || N == 112);
+  static constexpr int HSTRIDE = N + 4;
+  static constexpr int HSTAGE_BYTES = HEADN ? 4 * 32 * HSTRIDE * 4 : 0;
+  static constexpr int STAGES_RAW = (200 * 1024 - HSTAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + HSTAGE_BYTES;
   static constexpr int ACC_COLS = (2 * N <= 32) ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : 256));   // buffer stride
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
   static constexpr int NPAD32 = (N + 31) / 32 * 32;
@@ -343,16 +371,6 @@ struct TcCfg3 {
   static_assert((B_BYTES % 1024) == 0 || ROWB == 64, "W_lo tile must start on a swizzle-atom boundary");
   static_assert(STAGES >= 2, "pipeline needs two stages");
 };
-
-#define SDB_TMEM_LD32(r, taddr)                                                                                        \
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                               \
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                               \
-               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"               \
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),       \
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), \
-                 "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), \
-                 "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) \
-               : "r"(taddr))
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -435,6 +453,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t d = tmem_base + buf * (uint32_t)C::ACC_COLS;
+        const uint32_t dsplit = P.split_acc ? (uint32_t)N : 0u;
         for (int kb = 0; kb < n_kb; ++kb, ++it) {
           const uint32_t s = it % C::STAGES;
           if (!mbar_wait(&full_bar[s], (it / C::STAGES) & 1)) { atomicExch(P.error_flag, 2u); ok = false; break; }
@@ -447,7 +466,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
 #pragma unroll
           for (int ks = 0; ks < KC / 16; ++ks) {
             if (elect_one()) umma_f16(d, dah0 + 2u * ks, dbh0 + 2u * ks, C::IDESC_2N, (kb | ks) ? 1u : 0u);      // cols [0,N): hi*Whi, [N,2N): hi*Wlo
-            if (elect_one()) umma_f16(d, dal0 + 2u * ks, dbh0 + 2u * ks, C::IDESC_N, 1u);                         // cols [0,N) += lo*Whi
+            if (elect_one()) umma_f16(d + dsplit, dal0 + 2u * ks, dbh0 + 2u * ks, C::IDESC_N, 1u);                // lo*Whi -> cols [0,N), or [N,2N) with split_acc
           }
           if (elect_one()) tcgen05_commit(&empty_bar[s]);
         }
@@ -468,6 +487,60 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
       if (!mbar_wait(&acc_full[buf], (t >> 1) & 1)) { atomicExch(P.error_flag, 3u); break; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)C::ACC_COLS;
+      if (C::HEADN && P.heads_R > 0 && (P.heads_R & 3) == 0) {
+        // ---- 1x1 heads, coalesced: channel 0 -> sigmoid -> prob; channels 1..R -> dist rows staged per warp in shared
+        // memory (thread = pixel writes float4 pieces of ITS row), then the warp streams the two 16-pixel image rows it
+        // owns -- 16 * R contiguous floats each in HBM -- as 512-byte stores.  (One scalar store per (pixel, ray) was
+        // 32 four-byte pieces 4*R bytes apart per instruction: 1.1 TB/s on the 3-D heads, profiles/r01x.)
+        const int R = P.heads_R, R4 = R >> 2;
+        float* stg = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256) + (size_t)q * 32 * C::HSTRIDE;
+        float* myrow = stg + lane * C::HSTRIDE;
+        float c29 = 0.f, c30 = 0.f, c31 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::NPAD32; c0 += 32) {
+          uint32_t r[32], r2[32];
+          SDB_TMEM_LD32(r, tbase + (uint32_t)c0);
+          SDB_TMEM_LD32(r2, tbase + (uint32_t)(N + c0));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 32 >= C::NPAD32) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int ch = c0 + j;
+            v[j] = (ch <= R) ? (__uint_as_float(r[j]) + __uint_as_float(r2[j])) * P.acc_scale + __ldg(P.bias + ch) : 0.f;
+          }
+          if (c0 == 0) {
+            if (in_img) P.prob[((size_t)img * P.H + y) * P.W + x] = 1.f / (1.f + expf(-v[0]));
+          } else if (c0 - 1 < R) {                 // dist c0-4 .. c0-1: three carried values + channel c0
+            *reinterpret_cast<float4*>(myrow + c0 - 4) = make_float4(c29, c30, c31, v[0]);
+          }
+#pragma unroll
+          for (int g = 0; g < 7; ++g)               // dist c0+4g .. c0+4g+3 = channels c0+4g+1 .. c0+4g+4
+            if (c0 + 4 * g + 3 < R) *reinterpret_cast<float4*>(myrow + c0 + 4 * g) = make_float4(v[4 * g + 1], v[4 * g + 2], v[4 * g + 3], v[4 * g + 4]);
+          c29 = v[29]; c30 = v[30]; c31 = v[31];
+        }
+        __syncwarp();
+        const int ty0 = (rem / tiles_x) * 8 + 2 * q, x0 = (rem % tiles_x) * 16;
+        const int nx = min(16, P.W - x0);
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+          const int yy = ty0 + rr;
+          if (yy >= P.H) break;
+          float4* g = reinterpret_cast<float4*>(P.dist + (((size_t)img * P.H + yy) * P.W + x0) * R);
+          const float* srow = stg + rr * 16 * C::HSTRIDE;
+          const int n4 = nx * R4;
+          for (int f = lane; f < n4; f += 32) {
+            const int px = f / R4, k4 = f - px * R4;
+            g[f] = *reinterpret_cast<const float4*>(srow + px * C::HSTRIDE + 4 * k4);
+          }
+        }
+        __syncwarp();                              // the staging rows are rewritten by the next tile
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < C::NPAD32; c0 += 32) {
         uint32_t r[32], r2[32];
@@ -707,6 +780,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t d0 = tmem_base + buf * (uint32_t)C::ACC_COLS;
+        const uint32_t dsplit = (C::MERGE && P.split_acc) ? (uint32_t)N : 0u;
         for (int cbz = 0; cbz < n_cb * n_dz && ok; ++cbz, ++ai) {
           const int cb = cbz / n_dz, dz = cbz - cb * n_dz;
           const uint32_t sa = ai % C::A_STAGES;
@@ -737,7 +811,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
                 const uint32_t acc = (cbz | tap | ks) ? 1u : 0u;
                 if (C::MERGE) {
                   if (elect_one()) umma_f16(d, dah, dbh, C::IDESC_2N, acc);       // [0,N): hi*Whi   [N,2N): hi*Wlo
-                  if (elect_one()) umma_f16(d, dal, dbh, C::IDESC_N, 1u);         // [0,N) += lo*Whi
+                  if (elect_one()) umma_f16(d + dsplit, dal, dbh, C::IDESC_N, 1u);   // lo*Whi -> [0,N), or [N,2N) with split_acc
                 } else {
                   const uint64_t dbl = dbh + B_LO;
                   if (elect_one()) umma_f16(d, dah, dbh, C::IDESC_N, acc);
@@ -1157,6 +1231,7 @@ static int launch_tc(const CUtensorMap& a0h, const CUtensorMap& a0l, const CUten
   return 0;
 }
 
+static int g_tc_split_acc = 1;   // see ConvParams::split_acc / sdb_tc_set_split_acc
 static int g_tc_variant = 0;      // 0 = auto (k_conv_tc4 for Cin <= 64, else k_conv_tc3, k_conv_tc for Cout = 256); 1 / 3 / 4 force a kernel where applicable
 static int g_num_sms = 0;
 static int g_tc_no_resident = 0;   // tests: force the weight ring in k_conv_tc4
@@ -1233,7 +1308,7 @@ extern "C" int sdb_conv3x3_tc(const void* src0_hi, const void* src0_lo, int c_sr
   CUtensorMap a0h, a0l, a1h, a1l, wh, wl;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg; P.split_acc = g_tc_split_acc;
   if ((g_tc_variant == 4 || (g_tc_variant == 0 && cin <= 64 && w >= 96)) && cout <= 128) {
     // halo-reuse persistent kernel: 32-channel blocks, (S+2) x 130 pixel boxes
     constexpr int ROWS = TcCfg4<32>::S + 2;
@@ -1279,7 +1354,7 @@ extern "C" int sdb_heads_tc(const void* f_hi, const void* f_lo, int cfeat, int n
   if (make_w_map(&wh, (const __half*)w_hi, cfeat, np, 64, 1) || make_w_map(&wl, (const __half*)w_lo, cfeat, np, 64, 1)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = 0; P.c_total = cfeat; P.relu = 0; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = nullptr;
+  P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 1; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = nullptr; P.split_acc = g_tc_split_acc;
   if (g_tc_variant != 1) {
     if (np == 48) return launch_tc3<48, 64>(ah, al, ah, al, wh, wl, P, n, st);
     if (np == 80) return launch_tc3<80, 64>(ah, al, ah, al, wh, wl, P, n, st);
@@ -1315,7 +1390,7 @@ extern "C" int sdb_conv3x3_heads_tc(const void* src0_hi, const void* src0_lo, in
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = 0; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
   P.out_hi = nullptr; P.out_lo = nullptr; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = n_rays; P.prob = d_prob; P.dist = d_dist;
-  P.fuse_w = d_heads_w; P.fuse_b = d_heads_b; P.dbg = g_tc_dbg;
+  P.fuse_w = d_heads_w; P.fuse_b = d_heads_b; P.dbg = g_tc_dbg; P.split_acc = g_tc_split_acc;
   return launch_tc4<128, true>(a0h, a0l, a1h, a1l, wh, wl, P, n, st);
 }
 
@@ -1339,7 +1414,7 @@ extern "C" int sdb_conv3x3x3_tc(const void* src0_hi, const void* src0_lo, int c_
   if (make_w_map(&wh, (const __half*)w_hi, cin, cout, 32, 27) || make_w_map(&wl, (const __half*)w_lo, cin, cout, 32, 27)) return 1;
   ConvParams P;
   P.H = h; P.W = w; P.c_src0 = c_src0; P.c_total = cin; P.relu = relu; P.up2x = up2x; P.bias = d_bias; P.acc_scale = 1.0f / w_scale;
-  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg;
+  P.out_hi = (__half*)out_hi; P.out_lo = (__half*)out_lo; P.error_flag = g_err_flag; P.n_taps = 9; P.heads_R = 0; P.prob = nullptr; P.dist = nullptr; P.fuse_w = nullptr; P.fuse_b = nullptr; P.dbg = g_tc_dbg; P.split_acc = g_tc_split_acc;
   if (cout == 32) return launch_tc4<32>(a0h, a0l, a1h, a1l, wh, wl, P, d, st, 3);
   if (cout == 64) return launch_tc4<64>(a0h, a0l, a1h, a1l, wh, wl, P, d, st, 3);
   return launch_tc4<128>(a0h, a0l, a1h, a1l, wh, wl, P, d, st, 3);
@@ -1417,6 +1492,7 @@ extern "C" int sdb_tma_probe(const void* d_act, int h, int w, int c, int box_c, 
 
 // profiling aid: device buffer [148][8] of u64 that k_conv_tc4 launches fill with wait-cycle counters
 // (0 acc_empty, 1 a_full, 2 b_full, 3 MMA-warp total, 4 acc_full, 5 epilogue total, 6 a_empty), or NULL to disable
+extern "C" int sdb_tc_set_split_acc(int on) { g_tc_split_acc = on ? 1 : 0; return 0; }
 extern "C" int sdb_tc_set_debug(void* d_buf) { g_tc_dbg = (unsigned long long*)d_buf; return 0; }
 
 // non-zero when any tcgen05 conv launch since the last call hit a bounded-wait timeout (then results are invalid)
