@@ -250,8 +250,8 @@ def test_conv3x3x3_tc_single_layer(d, h, w, c0, c1, cout, relu, up2x):
 
 def test_unet3d_tc_vs_torch_fp32(sd):
     """3-D U-Net on the tensor cores against a float64 evaluation.  prob: 3e-7 of its scale.  dist of a RANDOM-INIT net is a
-    near-cancelling sum (max ~0.07 from O(1) features): the split-fp16 / TMEM-accumulated path leaves ~9e-7 absolute, i.e.
-    1.3e-5 of that tiny scale (tests/tools/unet3d_tc_error.py; CUDA-core fp32: 1.2e-6, torch-CPU fp32: 6e-7) -- the bound is
+    near-cancelling sum (max ~0.07 from O(1) features): the split-fp16 / TMEM-accumulated path leaves ~6e-7 absolute, i.e.
+    7e-6 of that tiny scale with split_acc (1.2e-5 without; tests/tools/tc_split_error.py) -- the bound is
     1e-5 of max(map scale, feature scale 1) and 2e-5 of the map scale itself."""
     import torch
     from oracle import unet_torch
