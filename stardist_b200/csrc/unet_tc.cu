@@ -639,7 +639,12 @@ struct TcCfg4 {
   static constexpr int B_STAGE = 2 * N * ROWB;
   // weight ring depth when the layer's weights do not stay resident (see WRES): the slot of a tap is recycled only
   // after its MMAs retired (tcgen05.commit) plus a TMA round trip, ~2 us -- a shallow ring starves the tensor pipe
-  static constexpr int B_STAGES = (N >= 128) ? 4 : (N == 64 ? 10 : 12);
+  // Ring slots are handed over in groups of BG consecutive taps (one mbarrier wait + one tcgen05.commit per group): with a
+  // wait and a commit per tap the issuing thread spent ~220 of ~650 cycles per tap on them (N = 32, tests/tools/tc4_waits_3d.py).
+  static constexpr int BG = (N >= 128) ? 1 : 3;
+  static constexpr int B_STAGES = (N >= 128) ? 4 : (N == 64 ? 9 : 21);    // N = 32: only the 3-D layers (27 taps x 4 KB > W_RESIDENT_MAX) use the ring
+  static constexpr int B_GROUPS = B_STAGES / BG;
+  static_assert(B_STAGES % BG == 0 && 9 % BG == 0 && B_GROUPS >= 2, "weight ring groups");
   static constexpr int W_RESIDENT_MAX = 88 * 1024;         // 9 * n_cb * B_STAGE up to this size stays in shared memory
   static constexpr int SMEM_FIXED = A_STAGES * A_STAGE + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int STRIP_COLS = MERGE ? 2 * N : N;
@@ -661,7 +666,8 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
            int tiles_x, int tiles_y, int n_tiles, int n_b_slots, int n_dz) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
-  constexpr int RING = C::B_STAGES;              // weight ring depth
+  constexpr int RING = C::B_STAGES;              // weight ring depth (slots)
+  constexpr int RG = C::B_GROUPS;                // ... in groups of C::BG taps
   constexpr int W_WARP = FUSE ? 10 : 6;          // warps: 0 halo TMA, 1 MMA, 2.. epilogue (4 or 8), last: weight TMA
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -754,13 +760,16 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
         for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x)
           for (int cb = 0; cb < n_cb && ok; ++cb) {
             const int ch = cb * C::KC;
-            for (int tap = 0; tap < 9 * n_dz; ++tap, ++bi) {       // tap index = dz * 9 + (dy * 3 + dx)
-              const uint32_t sb = bi % RING;
-              if (bi >= (uint32_t)RING && !mbar_wait(&b_empty[sb], ((bi / RING) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
-              unsigned char* stb = smB + sb * C::B_STAGE;
-              mbar_expect_tx(&b_full[sb], C::B_STAGE);
-              tma_load_3d(stb, &tm_w_hi, &b_full[sb], ch, 0, tap);
-              tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[sb], ch, 0, tap);
+            for (int tap = 0; tap < 9 * n_dz; tap += C::BG, ++bi) {       // tap index = dz * 9 + (dy * 3 + dx); bi counts groups
+              const uint32_t gs = bi % RG;
+              if (bi >= (uint32_t)RG && !mbar_wait(&b_empty[gs], ((bi / RG) - 1) & 1)) { atomicExch(P.error_flag, 12u); ok = false; break; }
+              mbar_expect_tx(&b_full[gs], (uint32_t)C::BG * C::B_STAGE);
+#pragma unroll
+              for (int k = 0; k < C::BG; ++k) {
+                unsigned char* stb = smB + (size_t)(gs * C::BG + k) * C::B_STAGE;
+                tma_load_3d(stb, &tm_w_hi, &b_full[gs], ch, 0, tap + k);
+                tma_load_3d(stb + N * C::ROWB, &tm_w_lo, &b_full[gs], ch, 0, tap + k);
+              }
             }
           }
       }
@@ -792,9 +801,10 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           const uint64_t dA_hi = make_desc_sw64(a_hi, 0), dA_lo = make_desc_sw64(a_lo, 0);
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++bi) {
-            const uint32_t sb = WRES ? (uint32_t)((cb * n_dz + dz) * 9 + tap) : bi % RING;
-            if (!WRES) {
-              if (!mbar_wait_t(&b_full[sb], (bi / RING) & 1, w_m2)) { atomicExch(P.error_flag, 14u); ok = false; break; }
+            const uint32_t bgi = bi / C::BG, gs = bgi % RG;            // ring mode: group index and its slot group
+            const uint32_t sb = WRES ? (uint32_t)((cb * n_dz + dz) * 9 + tap) : gs * C::BG + bi % C::BG;
+            if (!WRES && bi % C::BG == 0) {
+              if (!mbar_wait_t(&b_full[gs], (bgi / RG) & 1, w_m2)) { atomicExch(P.error_flag, 14u); ok = false; break; }
             }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t dB_hi = make_desc_sw64(smem_u32(smB + (size_t)sb * C::B_STAGE), 0);
@@ -820,7 +830,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
                 }
               }
             }
-            if (!WRES && elect_one()) tcgen05_commit(&b_empty[sb]);
+            if (!WRES && bi % C::BG == C::BG - 1 && elect_one()) tcgen05_commit(&b_empty[gs]);
           }
           if (!ok) break;
           if (elect_one()) tcgen05_commit(&a_empty[sa]);
