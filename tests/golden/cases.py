@@ -82,3 +82,15 @@ def nms3d_inputs(name):
     d, s, points = d[ind], s[ind], points[ind]
     return (np.ascontiguousarray(d, np.float32), np.ascontiguousarray(points, np.float32), np.ascontiguousarray(s, np.float32),
             rays_golden_spiral(n_rays, aniso), np.float32(nthr), shape)
+
+
+# ---------------------------------------------------------------------------------- reference tests/test_nms3D.py:60-83
+NMS3D_ACCURACY_CASES = [(noise, n_rays) for noise in (0, .2, .6, .9) for n_rays in (32, 65, 100)]
+
+
+def nms3d_accuracy_inputs(noise, n_rays):
+    """two polyhedra 3 voxels apart -> dist f64[2,R], points int[2,3], prob, rays, shape (test_nms_accuracy)"""
+    rays = rays_golden_spiral(n_rays)
+    dist = 10 * (1 + noise * np.sin(2 * np.pi * rays.vertices[:, :2].T))
+    points = np.array([(20, 20, 20), (20, 20, 20 + 3)])
+    return dist, points, np.array([1, .5]), rays, (40, 55, 66)

@@ -121,4 +121,36 @@ float hc_overlap_convex(const float* pv1, const float* c1, const float* pv2, con
                         int n_rays) {
   return sd3::overlap_convex_volume(pv1, c1, pv2, c2, n_rays);
 }
+
+// host restatement of k_paint3d (label3d.cu), render mode "full", ONE polyhedron: the same header functions in the same
+// order -- vertices and integer bbox in float, kernel half-spaces in double, then inside_polyhedron -- so that the
+// device rendering rule can be compared with the reference's c_polyhedron_to_label on the CPU box.
+void hc_paint3d(const float* dist, const float* center, const float* verts, const int* faces, int n_rays, int n_faces,
+                int nz, int ny, int nx, unsigned char* out) {
+  std::vector<float> pv(3 * (size_t)n_rays);
+  std::vector<double> hs(4 * (size_t)n_faces);
+  int z1 = INT32_MAX, z2 = -1, y1 = INT32_MAX, y2 = -1, x1 = INT32_MAX, x2 = -1;
+  for (int j = 0; j < n_rays; ++j) {
+    pv[3 * j] = center[0] + dist[j] * verts[3 * j];
+    pv[3 * j + 1] = center[1] + dist[j] * verts[3 * j + 1];
+    pv[3 * j + 2] = center[2] + dist[j] * verts[3 * j + 2];
+    const int iz = sd3::round_to_int(center[0] + dist[j] * verts[3 * j]);
+    const int iy = sd3::round_to_int(center[1] + dist[j] * verts[3 * j + 1]);
+    const int ix = sd3::round_to_int(center[2] + dist[j] * verts[3 * j + 2]);
+    z1 = std::min(z1, iz); z2 = std::max(z2, iz); y1 = std::min(y1, iy); y2 = std::max(y2, iy); x1 = std::min(x1, ix); x2 = std::max(x2, ix);
+  }
+  z1 = std::max(0, z1); z2 = std::min(nz - 1, z2); y1 = std::max(0, y1); y2 = std::min(ny - 1, y2); x1 = std::max(0, x1); x2 = std::min(nx - 1, x2);
+  for (int f = 0; f < n_faces; ++f)
+    sd3::build_halfspace(&pv[3 * faces[3 * f]], &pv[3 * faces[3 * f + 1]], &pv[3 * faces[3 * f + 2]], &hs[4 * f]);
+  for (int z = z1; z <= z2; ++z)
+    for (int y = y1; y <= y2; ++y)
+      for (int x = x1; x <= x2; ++x) {
+        const float fz = (float)z, fy = (float)y, fx = (float)x;
+        bool ker = true;
+        for (int f = 0; f < n_faces && ker; ++f)
+          if (hs[4 * f] * fz + hs[4 * f + 1] * fy + hs[4 * f + 2] * fx + hs[4 * f + 3] > 0) ker = false;
+        if (ker || sd3::inside_polyhedron(fz, fy, fx, center, pv.data(), faces, n_faces))
+          out[((size_t)z * ny + y) * nx + x] = 1;
+      }
+}
 }

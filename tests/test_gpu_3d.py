@@ -343,3 +343,29 @@ def test_relabel_sequential_device_reference_docstring_vectors(sd):
     assert out5.cpu().tolist() == [5, 5, 6, 6, 7, 9, 8]
     with pytest.raises(ValueError):
         relabel_sequential_device(torch.tensor(lf, dtype=torch.int32, device="cuda"), offset=0)
+
+
+@pytest.mark.parametrize("noise,n_rays", cases.NMS3D_ACCURACY_CASES)
+def test_reference_nms_accuracy_property(sd, noise, n_rays):
+    """the reference's own test_nms_accuracy (tests/test_nms3D.py:60-83) through the product path (list / float64 inputs
+    as there): rendered IoU of two polyhedra, NMS at 0.95*iou keeps one, at 1.05*iou keeps both.  With oracle/_ref the rendered
+    masks are compared with the reference's: the polar rays of the golden spiral get dist == 10.0 exactly here (sin(2 pi * +-1),
+    sin(0)), so each polyhedron has vertices ON the voxel lattice -- the documented hull-facet caveat (DESIGN.md 5, 3D labels:
+    the reference ANDs a Qhull hull test whose last-bit plane rounding decides such a voxel).  Measured on B200: exactly one
+    voxel of 2.9-5.1 k differs in 8 of the 12 cases, none in the others; the bound is the documented 0.1 %."""
+    from stardist_b200.geometry.geom3d import polyhedron_to_label
+    from stardist_b200.nms import non_maximum_suppression_3d_sparse
+    dist, points, prob, rays, shape = cases.nms3d_accuracy_inputs(noise, n_rays)
+    pts = [tuple(int(v) for v in p) for p in points]
+    mask1 = polyhedron_to_label([dist[0]], [pts[0]], rays, shape=shape, verbose=False)
+    mask2 = polyhedron_to_label([dist[1]], [pts[1]], rays, shape=shape, verbose=False)
+    iou = np.count_nonzero(mask1 * mask2) / min(np.count_nonzero(mask1), np.count_nonzero(mask2) + 1e-10)
+    sup1 = non_maximum_suppression_3d_sparse(dist, [1, .5], pts, rays=rays, nms_thresh=0.95 * iou, verbose=False)[0]
+    sup2 = non_maximum_suppression_3d_sparse(dist, [1, .5], pts, rays=rays, nms_thresh=1.05 * iou, verbose=False)[0]
+    assert len(sup1) == 1 and len(sup2) == 2
+    if ref_ext.available():
+        from oracle import pipeline3d
+        for m, k in ((mask1, 0), (mask2, 1)):
+            ref = pipeline3d.polyhedron_to_label(dist[k:k + 1], points[k:k + 1], rays, shape, prob[k:k + 1])
+            diff = np.count_nonzero((m > 0) != (ref > 0))
+            assert diff <= 1e-3 * np.count_nonzero(ref), (diff, np.count_nonzero(ref))
