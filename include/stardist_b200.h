@@ -119,6 +119,11 @@ int sdb_polyhedron_to_label(const float* d_dist, const float* d_points, const fl
                             int use_overlap_label, int overlap_label, int* d_result,
                             sdb_stream_t stream);
 
+/* k_heavy volume stages (S3 kernel / S4 hull intersection): 0 (default) = per-(k, j) plane scaling as validated on B200,
+ * 1 = planes scaled once per pair + early-out for non-cutting planes (sd3::face_cone_volume_n; bit-identical results on the
+ * host build, not yet run on a GPU -- experimental until then). */
+int sdb_nms3d_set_variant(int norm_planes);
+
 /* relabel_sequential on a device label map (stardist/matching.py:319-406; callers model3d.py:645, base.py:959):
  * labels occurring in d_labels[n] (values in [0, max_label], 16-byte aligned) are renumbered offset, offset+1, ...
  * in ascending order, 0 stays 0, in place.  d_forward_map: scratch of max_label + 3 ints; on return [0..max_label]

@@ -78,6 +78,8 @@ def _declare(lib):
     lib.sdb_maxpool_split.argtypes = [P, P, c_int, c_int, c_int, c_int, P, P, P]
     lib.sdb_heads_split.argtypes = [P, P, c_longlong, c_int, P, P, P, P, c_int, P, P, P]
     lib.sdb_polyhedron_to_label.argtypes = [P, P, P, P, c_int, c_int, c_int, P, c_int, c_int, c_int, c_int, c_int, c_int, P, P]
+    lib.sdb_nms3d_set_variant.argtypes = [c_int]
+    lib.sdb_nms3d_set_variant.restype = c_int
     lib.sdb_relabel_sequential.argtypes = [P, c_longlong, c_int, c_int, P, POINTER(c_int), P]
     lib.sdb_relabel_sequential.restype = c_int
     lib.sdb_nms3d.argtypes = [P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P]

@@ -292,6 +292,92 @@ SD3_HD inline double face_cone_volume(const PlaneAt& planes, int n, int k, const
   return fabs(area2) * 0.5 * h / 3.0;
 }
 
+// ---- the same volume with the per-plane work hoisted out of the (k, j) loop -----------------------------------------
+// face_cone_volume re-derives  n/|n|, d/|n|  of plane j (one sqrt, four divisions) for every (k, j) pair and takes
+// another square root for the parallel test: ~2F * 2F * (2 sqrt + 4 div) in double per pair of polyhedra.
+// normalized_plane() performs exactly those operations ONCE per plane; face_cone_volume_n() consumes the results.
+// Every double it produces is bit-identical to face_cone_volume's (tests/test_cpu_oracle.py compares the two on fuzzed
+// pairs, host build):
+//   * the scaled plane is the same four IEEE operations on the same operands;
+//   * `sqrt(s) < 1e-12` is replaced by `s < 1e-24`: sqrt is correctly rounded (host libm, CUDA sqrt.rn.f64), hence monotone,
+//     and 1e-24 (= 0x1.357c299a88ea7p-80) is the smallest double whose square root is not below 1e-12;
+//   * a plane with no polygon vertex on its outer side leaves Sutherland-Hodgman's output equal to its input (same
+//     vertices, same order), so that pass -- the common case once the face has shrunk -- is skipped.
+// A plane with !(|n| > 0) is stored as all zeros and skipped (face_cone_volume: `continue` / `return 0`).
+SD3_HD inline Plane normalized_plane(const Plane& P) {
+  const double len = sqrt(P.n0 * P.n0 + P.n1 * P.n1 + P.n2 * P.n2);
+  Plane Q;
+  if (!(len > 0)) { Q.n0 = 0; Q.n1 = 0; Q.n2 = 0; Q.d = 0; return Q; }
+  Q.n0 = P.n0 / len; Q.n1 = P.n1 / len; Q.n2 = P.n2 / len; Q.d = P.d / len;
+  return Q;
+}
+
+template <typename PlaneAt>
+SD3_HD inline double face_cone_volume_n(const PlaneAt& planes /* normalized_plane() of each */, int n, int k, const double* p,
+                                        double L, int* overflow) {
+  const Plane Pk = planes(k);
+  if (Pk.n0 == 0 && Pk.n1 == 0 && Pk.n2 == 0) return 0.0;
+  const double nz = Pk.n0, ny = Pk.n1, nx = Pk.n2, dk = Pk.d;
+  const double sdist = nz * p[0] + ny * p[1] + nx * p[2] + dk;      // < 0
+  const double h = -sdist;
+  const double q0 = p[0] - sdist * nz, q1 = p[1] - sdist * ny, q2 = p[2] - sdist * nx;   // foot point
+  double u0, u1, u2;
+  if (fabs(nz) <= fabs(ny) && fabs(nz) <= fabs(nx)) { u0 = 0; u1 = -nx; u2 = ny; }
+  else if (fabs(ny) <= fabs(nx)) { u0 = -nx; u1 = 0; u2 = nz; }
+  else { u0 = -ny; u1 = nz; u2 = 0; }
+  const double ul = sqrt(u0 * u0 + u1 * u1 + u2 * u2);
+  u0 /= ul; u1 /= ul; u2 /= ul;
+  const double v0 = ny * u2 - nx * u1, v1 = nx * u0 - nz * u2, v2 = nz * u1 - ny * u0;
+  double pa[SD3_MAXPOLY], pb[SD3_MAXPOLY], qa[SD3_MAXPOLY], qb[SD3_MAXPOLY];
+  int m = 4;
+  pa[0] = -L; pb[0] = -L; pa[1] = L; pb[1] = -L; pa[2] = L; pb[2] = L; pa[3] = -L; pb[3] = L;
+  const double eps_dup = 1e-9;
+  for (int j = 0; j < n && m > 0; ++j) {
+    if (j == k) continue;
+    const Plane Pj = planes(j);
+    if (Pj.n0 == 0 && Pj.n1 == 0 && Pj.n2 == 0) continue;
+    const double a0 = Pj.n0, a1 = Pj.n1, a2 = Pj.n2, dj = Pj.d;
+    const double A = a0 * u0 + a1 * u1 + a2 * u2;
+    const double B = a0 * v0 + a1 * v1 + a2 * v2;
+    const double C = a0 * q0 + a1 * q1 + a2 * q2 + dj;
+    if (A * A + B * B < 1e-24) {
+      if (C > eps_dup * (1.0 + fabs(dj))) { m = 0; break; }
+      if (fabs(C) <= eps_dup * (1.0 + fabs(dj)) && (a0 * nz + a1 * ny + a2 * nx) > 0 && j < k) { m = 0; break; }
+      continue;
+    }
+    bool any_out = false;
+    for (int t = 0; t < m; ++t) any_out = any_out || (A * pa[t] + B * pb[t] + C > 0);
+    if (!any_out) continue;
+    int mo = 0;
+    double sa = pa[m - 1], sb = pb[m - 1];
+    double fs = A * sa + B * sb + C;
+    for (int t = 0; t < m; ++t) {
+      const double ea = pa[t], eb = pb[t];
+      const double fe = A * ea + B * eb + C;
+      if (fe <= 0) {
+        if (fs > 0) {
+          const double w = fs / (fs - fe);
+          if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else *overflow = 1;
+        }
+        if (mo < SD3_MAXPOLY) { qa[mo] = ea; qb[mo] = eb; mo++; } else *overflow = 1;
+      } else if (fs <= 0) {
+        const double w = fs / (fs - fe);
+        if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else *overflow = 1;
+      }
+      sa = ea; sb = eb; fs = fe;
+    }
+    m = mo;
+    for (int t = 0; t < m; ++t) { pa[t] = qa[t]; pb[t] = qb[t]; }
+  }
+  if (m < 3) return 0.0;
+  double area2 = 0;
+  for (int t = 0; t < m; ++t) {
+    const int t2 = (t + 1 == m) ? 0 : t + 1;
+    area2 += pa[t] * pb[t2] - pa[t2] * pb[t];
+  }
+  return fabs(area2) * 0.5 * h / 3.0;
+}
+
 // Convex hull facet planes (outward, unit normal) of n points (double, [n][3]) by gift wrapping.
 // out: up to max_planes planes; returns the number of facets, or -1 on failure (degenerate input).
 // scratch: edge_done bit matrix n*n bits (uint32 words), stack of directed edges (int16 triples).

@@ -43,6 +43,7 @@ struct Arr {
   float* aniso;          // [3]
   const unsigned int* cell_start; const int* items; int* state;
   float max_dist, threshold; int use_bbox;
+  int norm_planes;       // k_heavy: S3/S4 volumes on pre-normalised planes (face_cone_volume_n; bit-identical, see geom3d.cuh)
   Grid3 G;
 };
 
@@ -401,7 +402,14 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
     if (!infeasible) {
       PlaneAt PA{planes};
       double part = 0; int ovf = 0;
-      for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+      if (A.norm_planes) {
+        // (block-uniform branch) scale every plane once instead of once per (k, j) pair
+        for (int k = threadIdx.x; k < np; k += blockDim.x) planes[k] = sd3::normalized_plane(planes[k]);
+        __syncthreads();
+        for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume_n(PA, np, k, p, L, &ovf);
+      } else {
+        for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+      }
       vol_kernel = (float)block_sum(part, red);     // NOTE: summation order differs from the serial host version (ulp-level in double)
     }
     float iou = (float)((double)vol_kernel / den);
@@ -434,7 +442,13 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         if (!inf2) {
           PlaneAt PA{planes};
           double part = 0; int ovf = 0;
-          for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+          if (A.norm_planes) {
+            for (int k = threadIdx.x; k < np; k += blockDim.x) planes[k] = sd3::normalized_plane(planes[k]);
+            __syncthreads();
+            for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume_n(PA, np, k, p, L, &ovf);
+          } else {
+            for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+          }
           vol_convex = (float)block_sum(part, red);
         }
       }
@@ -499,6 +513,12 @@ __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __
 
 }  // namespace
 
+// 0 (default): face_cone_volume as validated on the GPU in round 1; 1: face_cone_volume_n on pre-normalised planes.
+// The two are bit-identical functions (host build, 7 500 fuzzed pairs: tests/test_cpu_oracle.py); the switch exists because
+// variant 1 has not been run on a GPU yet (tests/test_gpu_3d.py runs it under STARDIST_B200_EXPERIMENTAL=1).
+static int g_nms3d_norm_planes = 0;
+extern "C" int sdb_nms3d_set_variant(int norm_planes) { g_nms3d_norm_planes = norm_planes ? 1 : 0; return 0; }
+
 extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float* d_verts, const int* d_faces,
                          int n_polys, int n_rays, int n_faces, float threshold, int use_bbox, int use_kdtree,
                          int verbose, unsigned char* d_keep, sdb_stream_t stream) {
@@ -519,7 +539,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   A.dist = d_dist; A.points = d_points; A.verts = d_verts; A.faces = d_faces; A.n = n; A.R = n_rays; A.F = n_faces;
   A.volume = b_vol.as<float>(); A.bbox = b_bbox.as<int>(); A.r_outer = b_ro.as<float>(); A.r_outer_iso = b_roi.as<float>();
   A.r_inner_iso = b_rii.as<float>(); A.aniso_terms = b_terms.as<float>(); A.aniso = b_aniso.as<float>();
-  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox;
+  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox; A.norm_planes = g_nms3d_norm_planes;
   A.cell_start = nullptr; A.items = nullptr; A.max_dist = 0; memset(&A.G, 0, sizeof(A.G));
   SDB_LAUNCH(k_pre1, cdiv(n, 128), 128, 0, st, A, b_stats.as<unsigned int>());
   SDB_LAUNCH(k_aniso, 3, 256, 0, st, A);

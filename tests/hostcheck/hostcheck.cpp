@@ -121,6 +121,35 @@ float hc_overlap_convex(const float* pv1, const float* c1, const float* pv2, con
                         int n_rays) {
   return sd3::overlap_convex_volume(pv1, c1, pv2, c2, n_rays);
 }
+float hc_overlap_kernel_n(const float* pv1, const float* c1, const float* pv2, const float* c2,
+                          const int* faces, int n_rays, int n_faces) {
+  return sd3::overlap_kernel_volume_n(pv1, c1, pv2, c2, faces, n_rays, n_faces);
+}
+float hc_overlap_convex_n(const float* pv1, const float* c1, const float* pv2, const float* c2, int n_rays) {
+  return sd3::overlap_convex_volume_n(pv1, c1, pv2, c2, n_rays);
+}
+// double results (before the float rounding) of both formulations, for a stricter comparison
+void hc_overlap_kernel_pair(const float* pv1, const float* c1, const float* pv2, const float* c2, const int* faces, int n_rays,
+                            int n_faces, double* out2) {
+  using namespace sd3;
+  std::vector<Plane> planes(2 * (size_t)n_faces), pn(2 * (size_t)n_faces);
+  for (int i = 0; i < n_faces; ++i) {
+    double hs[4];
+    build_halfspace(&pv1[3 * faces[3 * i]], &pv1[3 * faces[3 * i + 1]], &pv1[3 * faces[3 * i + 2]], hs);
+    planes[2 * i] = Plane{hs[0], hs[1], hs[2], hs[3]};
+    build_halfspace(&pv2[3 * faces[3 * i]], &pv2[3 * faces[3 * i + 1]], &pv2[3 * faces[3 * i + 2]], hs);
+    planes[2 * i + 1] = Plane{hs[0], hs[1], hs[2], hs[3]};
+  }
+  double p[3];
+  for (int k = 0; k < 3; ++k) p[k] = .5 * (double)(c1[k] + c2[k]);
+  const int n = 2 * n_faces;
+  const double L = extent_bound(pv1, pv2, n_rays, p);
+  for (int i = 0; i < n; ++i) pn[i] = normalized_plane(planes[i]);
+  PlaneArray PA{planes.data()}, PN{pn.data()};
+  double a = 0, b = 0; int ovf = 0;
+  for (int k = 0; k < n; ++k) { a += face_cone_volume(PA, n, k, p, L, &ovf); b += face_cone_volume_n(PN, n, k, p, L, &ovf); }
+  out2[0] = a; out2[1] = b;
+}
 
 // host restatement of k_paint3d (label3d.cu), render mode "full", ONE polyhedron: the same header functions in the same
 // order -- vertices and integer bbox in float, kernel half-spaces in double, then inside_polyhedron -- so that the

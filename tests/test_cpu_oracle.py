@@ -304,3 +304,39 @@ def test_device_render_rule_equals_reference_off_lattice():
             ours = _hc_paint3d(hc, dist, point, rays, shape)
             ref = pipeline3d.polyhedron_to_label(dist[None], point[None], rays, shape, np.ones(1))
             assert np.count_nonzero(ref) > 100 and np.array_equal(ours > 0, ref > 0)
+
+
+def test_face_cone_volume_n_bit_identical_to_face_cone_volume():
+    """geom3d.cuh: the S3 / S4 volume stages on pre-normalised planes (face_cone_volume_n: planes scaled once, squared
+    parallel test, non-cutting planes skipped) against the GPU-validated formulation, host build: identical float bits of both
+    stages and identical raw double sums, on star polyhedra incl. integer centres, equal shapes and coincident centres"""
+    import math
+    hc = _hostcheck()
+    for f in (hc.hc_overlap_kernel, hc.hc_overlap_convex, hc.hc_overlap_kernel_n, hc.hc_overlap_convex_n): f.restype = ctypes.c_float
+    P = ctypes.c_void_p
+    # sqrt(s) < 1e-12  <=>  s < 1e-24 for correctly rounded sqrt: check the doubles around the threshold
+    x = np.float64(1e-24)
+    assert math.sqrt(float(x)) >= 1e-12 and math.sqrt(float(np.nextafter(x, 0))) < 1e-12
+    n_pos = 0; tot = 0
+    for n_rays, aniso in ((96, None), (96, (2, 1, 1)), (32, None), (65, None)):
+        r = cases.rays_golden_spiral(n_rays, aniso)
+        verts = np.ascontiguousarray(r.vertices, np.float32); faces = np.ascontiguousarray(r.faces, np.int32)
+        for radius, noise, sep, seed in ((10, .2, 12, 0), (10, .6, 8, 1), (5, .05, 3, 2), (20, .9, 25, 3)):
+            rng = np.random.default_rng(seed * 7 + n_rays)
+            for it in range(60):
+                c1 = rng.uniform(20, 60, 3).astype(np.float32); c2 = (c1 + rng.uniform(-sep, sep, 3)).astype(np.float32)
+                if it % 5 == 0: c1 = np.round(c1); c2 = np.round(c2)
+                d1 = (radius * (1 + noise * rng.uniform(-1, 1, n_rays))).astype(np.float32)
+                d2 = (radius * (1 + noise * rng.uniform(-1, 1, n_rays))).astype(np.float32)
+                if it % 7 == 0: d2 = d1.copy()
+                if it % 11 == 0: c2 = c1.copy()
+                pv1 = (c1[None] + d1[:, None] * verts).astype(np.float32); pv2 = (c2[None] + d2[:, None] * verts).astype(np.float32)
+                a = (P(pv1.ctypes.data), P(c1.ctypes.data), P(pv2.ctypes.data), P(c2.ctypes.data), P(faces.ctypes.data), n_rays, len(faces))
+                k0, k1 = hc.hc_overlap_kernel(*a), hc.hc_overlap_kernel_n(*a)
+                v0, v1 = hc.hc_overlap_convex(*a[:4], n_rays), hc.hc_overlap_convex_n(*a[:4], n_rays)
+                out = np.zeros(2); hc.hc_overlap_kernel_pair(*a, P(out.ctypes.data))
+                assert np.float32(k0).view(np.int32) == np.float32(k1).view(np.int32)
+                assert np.float32(v0).view(np.int32) == np.float32(v1).view(np.int32)
+                assert out[0] == out[1] or (np.isnan(out[0]) and np.isnan(out[1]))
+                tot += 1; n_pos += k0 > 0
+    assert n_pos > tot // 10

@@ -369,3 +369,21 @@ def test_reference_nms_accuracy_property(sd, noise, n_rays):
             ref = pipeline3d.polyhedron_to_label(dist[k:k + 1], points[k:k + 1], rays, shape, prob[k:k + 1])
             diff = np.count_nonzero((m > 0) != (ref > 0))
             assert diff <= 1e-3 * np.count_nonzero(ref), (diff, np.count_nonzero(ref))
+
+
+@pytest.mark.skipif(os.environ.get("STARDIST_B200_EXPERIMENTAL", "0") != "1",
+                    reason="sdb_nms3d_set_variant(1): bit-identical on the host build (test_face_cone_volume_n_...), not yet run on a GPU")
+@pytest.mark.parametrize("name", list(cases.NMS3D_CASES))
+def test_nms3d_golden_normalised_planes_variant(sd, g3, name):
+    from stardist_b200 import _lib
+    from stardist_b200.lib.stardist3d import c_non_max_suppression_inds
+    d, p, s, rays, thr, shape = cases.nms3d_inputs(name)
+    v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
+    lib = _lib.load()
+    lib.sdb_nms3d_set_variant(1)
+    try:
+        keep = c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, thr)
+    finally:
+        lib.sdb_nms3d_set_variant(0)
+    want = np.unpackbits(g3[name + "/keep"])[:len(d)].astype(bool)
+    assert np.array_equal(keep, want), "%d decisions differ" % int((keep != want).sum())

@@ -26,6 +26,7 @@ ap.add_argument("--cpu", action="store_true")
 ap.add_argument("--skip-r1", action="store_true")
 ap.add_argument("--only-net", action="store_true", help="stop after the timed network passes (profiling)")
 ap.add_argument("--json", default=None)
+ap.add_argument("--nms3d-variant", type=int, default=0, help="sdb_nms3d_set_variant: 1 = S3/S4 volumes on pre-normalised planes")
 args = ap.parse_args()
 D, H, W = args.shape
 cd, ch, cw = args.cell
@@ -33,6 +34,9 @@ assert D % cd == 0 and H % ch == 0 and W % cw == 0
 n_rays = args.n_rays
 out = dict(shape=[D, H, W], n_rays=n_rays, cell=[cd, ch, cw])
 
+from stardist_b200 import _lib as _L
+_L.require_cuda().sdb_nms3d_set_variant(args.nms3d_variant)
+out['nms3d_variant'] = args.nms3d_variant
 rng = np.random.default_rng(0)
 rays = sd.Rays_GoldenSpiral(n_rays)
 cfg = sd.Config3D(rays=rays)
