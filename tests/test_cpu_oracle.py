@@ -340,3 +340,18 @@ def test_face_cone_volume_n_bit_identical_to_face_cone_volume():
                 assert out[0] == out[1] or (np.isnan(out[0]) and np.isnan(out[1]))
                 tot += 1; n_pos += k0 > 0
     assert n_pos > tot // 10
+
+
+def test_stage_fill_matches_numpy_cast():
+    """StarDistBase._stage_fill (host image -> float32 staging buffer): torch's parallel copy and the numpy fallback give the
+    same float32 values as x.astype(np.float32) for contiguous / strided / float64 / integer / byte-swapped inputs"""
+    import torch
+    from stardist_b200.models.base import StarDistBase
+    rng = np.random.default_rng(0)
+    base = rng.uniform(-3, 3, (70, 300, 40))
+    inputs = [base.astype(np.float32), base, base.astype(np.float32)[::-1, ::2], base[:, :, ::-1], np.asfortranarray(base.astype(np.float32)),
+              (base * 1000).astype(np.uint16), (base * 10).astype(np.int8), base.astype('>f4'), base.astype(np.float16), base[:3, :5, :7].astype(np.float32)]
+    for x in inputs:
+        stage = torch.full((1,) + x.shape, np.nan, dtype=torch.float32)
+        StarDistBase._stage_fill(stage, x)
+        assert np.array_equal(stage.numpy()[0], x.astype(np.float32)), (x.dtype, x.strides)
