@@ -352,7 +352,7 @@ def test_reference_nms_accuracy_property(sd, noise, n_rays):
     masks are compared with the reference's: the polar rays of the golden spiral get dist == 10.0 exactly here (sin(2 pi * +-1),
     sin(0)), so each polyhedron has vertices ON the voxel lattice -- the documented hull-facet caveat (DESIGN.md 5, 3D labels:
     the reference ANDs a Qhull hull test whose last-bit plane rounding decides such a voxel).  Measured on B200: exactly one
-    voxel of 2.9-5.1 k differs in 8 of the 12 cases, none in the others; the bound is the documented 0.1 %."""
+    voxel of 2.9-5.1 k differs in 8 of the 12 cases, none in the others; the bound asserted here is 0.1 % (these polyhedra have radius ~10)."""
     from stardist_b200.geometry.geom3d import polyhedron_to_label
     from stardist_b200.nms import non_maximum_suppression_3d_sparse
     dist, points, prob, rays, shape = cases.nms3d_accuracy_inputs(noise, n_rays)
