@@ -151,6 +151,89 @@ void hc_overlap_kernel_pair(const float* pv1, const float* c1, const float* pv2,
   out2[0] = a; out2[1] = b;
 }
 
+// Serial host restatement of nms3d.cu (k_pre1 / k_aniso / k_pre2 / k_frontier+k_pretest as the greedy loop they resolve /
+// k_heavy) with the SAME header arithmetic (geom3d.cuh, nms3d_pair.cuh): pins S1, S2, S5, the radius query and the anisotropy
+// on the CPU box against the reference's c_non_max_suppression_inds for ray counts the GPU goldens do not cover.
+// norm_planes: use the *_n volume stages (sdb_nms3d_set_variant(1)).
+void hc_nms3d_serial(const float* dist, const float* points, const float* verts, const int* faces, int n, int R, int F,
+                     float threshold, int use_bbox, int use_kdtree, int norm_planes, unsigned char* keep, int* stage_counts /*[5]*/) {
+  using namespace sd3;
+  std::vector<float> volume(n), r_outer(n), r_outer_iso(n), r_inner_iso(n), terms(3 * (size_t)n);
+  std::vector<int> bbox(6 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const float* d = dist + (size_t)i * R; const float* c = points + 3 * i;
+    volume[i] = polyhedron_volume(d, verts, faces, F);
+    polyhedron_bbox(d, c, verts, R, &bbox[6 * i]);
+    terms[i] = (float)(bbox[6 * i + 1] - bbox[6 * i]) / n;
+    terms[n + i] = (float)(bbox[6 * i + 3] - bbox[6 * i + 2]) / n;
+    terms[2 * (size_t)n + i] = (float)(bbox[6 * i + 5] - bbox[6 * i + 4]) / n;
+    r_outer[i] = bounding_radius_outer(d, R);
+  }
+  float an[3];
+  for (int a = 0; a < 3; ++a) { float acc = 0.f; for (int i = 0; i < n; ++i) acc = acc + terms[(size_t)a * n + i]; an[a] = acc; }
+  { const float tmp = fmaxf(fmaxf(an[0], an[1]), an[2]); const float a0 = an[0], a1 = an[1], a2 = an[2]; an[0] = tmp / a0; an[1] = tmp / a1; an[2] = tmp / a2; }
+  float max_dist = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float* d = dist + (size_t)i * R;
+    r_outer_iso[i] = bounding_radius_outer_isotropic(d, verts, R, an);
+    r_inner_iso[i] = bounding_radius_inner_isotropic(d, verts, faces, F, an);
+    max_dist = fmaxf(max_dist, r_outer[i]);
+  }
+  std::vector<unsigned char> sup(n, 0);
+  std::vector<float> pv1(3 * (size_t)R), pv2(3 * (size_t)R);
+  for (int k = 0; k < 5; ++k) stage_counts[k] = 0;
+  for (int h = 0; h < n; ++h) {
+    if (sup[h]) continue;
+    const float* ph = points + 3 * h; const float* d1 = dist + (size_t)h * R;
+    for (int j = 0; j < R; ++j) for (int k = 0; k < 3; ++k) pv1[3 * j + k] = ph[k] + d1[j] * verts[3 * j + k];
+    for (int c = h + 1; c < n; ++c) {
+      if (sup[c]) continue;
+      const float* pc = points + 3 * c;
+      if (use_kdtree) {
+        const float d0 = ph[0] - pc[0], dd1 = ph[1] - pc[1], d2 = ph[2] - pc[2];
+        const float dd = d0 * d0 + dd1 * dd1 + d2 * d2;
+        const float rr = max_dist + r_outer[h];
+        if (!(dd < rr * rr)) continue;
+      }
+      stage_counts[0]++;
+      const float A_min = fminf(volume[h], volume[c]);
+      float A_inter = fminf(intersect_sphere_isotropic(r_outer_iso[h], ph, r_outer_iso[c], pc, an), intersect_bbox(&bbox[6 * h], &bbox[6 * c]));
+      float iou = (float)fmin(1.0, (double)A_inter / ((double)A_min + 1e-10));
+      if (use_bbox && (((double)A_inter < 1.e-10) || (iou <= threshold))) continue;
+      stage_counts[1]++;
+      A_inter = intersect_sphere_isotropic(r_inner_iso[h], ph, r_inner_iso[c], pc, an);
+      iou = (float)fmax(0.0, (double)A_inter / ((double)A_min + 1e-10));
+      if (iou > threshold) { sup[c] = 1; continue; }
+      stage_counts[2]++;
+      const float* d2p = dist + (size_t)c * R;
+      for (int j = 0; j < R; ++j) for (int k = 0; k < 3; ++k) pv2[3 * j + k] = pc[k] + d2p[j] * verts[3 * j + k];
+      const double den = (double)A_min + 1e-10;
+      const float vk = norm_planes ? overlap_kernel_volume_n(pv1.data(), ph, pv2.data(), pc, faces, R, F)
+                                   : overlap_kernel_volume(pv1.data(), ph, pv2.data(), pc, faces, R, F);
+      iou = (float)((double)vk / den);
+      if (iou > threshold) { sup[c] = 1; continue; }
+      stage_counts[3]++;
+      const float vc = norm_planes ? overlap_convex_volume_n(pv1.data(), ph, pv2.data(), pc, R) : overlap_convex_volume(pv1.data(), ph, pv2.data(), pc, R);
+      iou = (float)((double)vc / den);
+      if (iou <= threshold) continue;
+      stage_counts[4]++;
+      // S5 exactly as the reference loop (:608-636): count voxels of bbox(h) inside both, return early once res > overlap_maximal
+      const int* bb = &bbox[6 * h];
+      const int Nz = bb[1] - bb[0] + 1, Ny = bb[3] - bb[2] + 1, Nx = bb[5] - bb[4] + 1;
+      const float overlap_maximal = (float)(den * (double)threshold);
+      int res = 0; bool stop = false;
+      for (int z = 0; z < Nz && !stop; ++z) for (int y = 0; y < Ny && !stop; ++y) for (int x = 0; x < Nx; ++x) {
+        const float fz = (float)(z + bb[0]), fy = (float)(y + bb[2]), fx = (float)(x + bb[4]);
+        res += (inside_polyhedron(fz, fy, fx, ph, pv1.data(), faces, F) && inside_polyhedron(fz, fy, fx, pc, pv2.data(), faces, F)) ? 1 : 0;
+        if ((float)res > overlap_maximal) { stop = true; break; }
+      }
+      const float iou5 = (float)((double)(float)res / den);
+      if (iou5 > threshold) sup[c] = 1;
+    }
+  }
+  for (int i = 0; i < n; ++i) keep[i] = !sup[i];
+}
+
 // host restatement of k_paint3d (label3d.cu), render mode "full", ONE polyhedron: the same header functions in the same
 // order -- vertices and integer bbox in float, kernel half-spaces in double, then inside_polyhedron -- so that the
 // device rendering rule can be compared with the reference's c_polyhedron_to_label on the CPU box.
