@@ -666,8 +666,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
            int tiles_x, int tiles_y, int n_tiles, int n_b_slots, int n_dz) {
   using C = TcCfg4<N>;
   constexpr int S = C::S;
-  constexpr int RING = C::B_STAGES;              // weight ring depth (slots)
-  constexpr int RG = C::B_GROUPS;                // ... in groups of C::BG taps
+  constexpr int RG = C::B_GROUPS;                // weight ring depth in groups of C::BG taps
   constexpr int W_WARP = FUSE ? 10 : 6;          // warps: 0 halo TMA, 1 MMA, 2.. epilogue (4 or 8), last: weight TMA
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
