@@ -90,13 +90,14 @@ def _worker(rank, world, port, shape, q):
     dist.barrier(); dist.destroy_process_group()
 
 
-def test_sharded_assembly_two_ranks_equals_serial():
+@pytest.mark.parametrize("world,shape", [(2, (170, 210)), (8, (170, 210)), (4, (70, 100))])
+def test_sharded_assembly_two_ranks_equals_serial(world, shape):
+    """world 2 and 8 (the box size), and more ranks than blocks ((70, 100) has 2 blocks for 4 ranks: idle ranks)"""
     import torch.multiprocessing as mp
-    shape = (170, 210)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, shape, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, q)) for r in range(world)]
     for p in procs: p.start()
     out, pts, prob = q.get(timeout=120)
     for p in procs: p.join(timeout=60)
