@@ -370,3 +370,25 @@ def test_serial_host_nms3d_equals_reference_beyond_the_goldens():
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["cases"] == 4 and out["candidates"] > 400 and out["mismatches"] == 0
     assert all(c > 50 for c in out["stage_counts"])           # every stage of the cascade is exercised
+
+
+def test_ray_classes_equal_reference(golden_dir):
+    """stardist_b200.rays3d vs tests/golden/rays3d.npz (the reference's stardist/rays3d.py, imported standalone by
+    make_rays3d.py): vertices bit-equal (float32), faces equal, volume / surface / dist_loss_weights / copy(scale) to 1e-12,
+    for every ray class rays_from_json can name"""
+    import json
+    import stardist_b200 as sd
+    g = np.load(os.path.join(golden_dir, "rays3d.npz"))
+    specs = json.loads(bytes(g["specs"]).decode())
+    assert len(specs) == 42
+    for i, (name, kw) in enumerate(specs):
+        kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in kw.items()}
+        r = getattr(sd, name)(**kw)
+        assert r.vertices.dtype == np.float32 and np.array_equal(r.vertices, g["%d/vertices" % i]), (name, kw)
+        assert np.array_equal(r.faces, g["%d/faces" % i]), (name, kw)
+        d = g["%d/dist" % i]
+        assert np.allclose(r.volume(d), g["%d/volume" % i], rtol=1e-12, atol=0) and np.allclose(r.surface(d), g["%d/surface" % i], rtol=1e-12, atol=0)
+        assert np.allclose(r.dist_loss_weights((2, 1, 1)), g["%d/weights" % i], rtol=1e-12, atol=0)
+        assert np.array_equal(r.copy(scale=(.5, 1, 2)).vertices, g["%d/scaled" % i])
+        r2 = sd.rays_from_json(json.loads(json.dumps(r.to_json())))               # config.json round trip
+        assert type(r2) is type(r) and np.array_equal(r2.vertices, r.vertices) and np.array_equal(r2.faces, r.faces)
