@@ -106,3 +106,46 @@ def test_sharded_assembly_two_ranks_equals_serial(world, shape):
     blocks = BlockND.cover(shape, 'YX', 64, 16, 8, 1)
     want, want_pts = _serial(blocks, _process_factory(gt), shape, 'YX')
     assert np.array_equal(out, want) and np.array_equal(pts, want_pts) and len(prob) == len(pts)
+
+
+def test_block_covers_equal_the_reference(golden_dir):
+    """Block.cover / BlockND.cover vs tests/golden/big_cover.npz (the reference's stardist/big.py run by make_big_cover.py on
+    the parameter sets of its own tests, tests/test_big.py:50-83, incl. the 7800..8000 edge sizes, and on configs[3] / [4]):
+    identical read / crop / write slices for every block, same block order"""
+    import json
+    from stardist_b200.big import Block
+    g = np.load(os.path.join(golden_dir, "big_cover.npz"))
+    BIG = 10 ** 9
+    for i, (size, bs, mo, ctx, grid) in enumerate(json.loads(bytes(g["cases_1d"]).decode())):
+        blocks = Block.cover(size, bs, mo, ctx, grid, verbose=False)
+        got = np.array([[b.start, b.end, b.slice_read.start, b.slice_read.stop, b.slice_crop_context.start,
+                         b.slice_crop_context.stop if b.slice_crop_context.stop is not None else BIG,
+                         b.slice_write.start, b.slice_write.stop, int(b.at_begin), int(b.at_end)] for b in blocks], np.int64)
+        assert np.array_equal(got, g["1d/%d" % i]), (size, bs, mo, ctx, grid)
+    for i, (shape, axes, bs, mo, ctx, grid) in enumerate(json.loads(bytes(g["cases_nd"]).decode())):
+        tup = lambda v: tuple(v) if isinstance(v, list) else v
+        blocks = BlockND.cover(tuple(shape), axes, tup(bs), tup(mo), tup(ctx), tup(grid))
+        rows = []
+        for b in blocks:
+            row = [b.id]
+            for sl in (b.slice_read(), b.slice_crop_context(), b.slice_write()):
+                for s in sl: row += [s.start if s.start is not None else 0, s.stop if s.stop is not None else BIG]
+            rows.append(row)
+        assert np.array_equal(np.array(rows, np.int64), g["nd/%d" % i]), (shape, axes, bs, mo, ctx, grid)
+
+
+def test_block_responsibility_equals_the_reference(golden_dir):
+    """Block.is_responsible (big.py:89-122) on a lattice of query intervals per block vs the reference's decisions
+    (tests/golden/big_cover.npz 'resp/*': 1 responsible, 0 not, 2 / 3 = NotFullyVisible(False / True))"""
+    import json
+    from stardist_b200.big import Block, NotFullyVisible
+    g = np.load(os.path.join(golden_dir, "big_cover.npz"))
+    n = 0
+    for i, (size, bs, mo, ctx, grid) in enumerate(json.loads(bytes(g["cases_1d"]).decode())):
+        blocks = Block.cover(size, bs, mo, ctx, grid, verbose=False)
+        for k, a, e, want in g["resp/%d" % i]:
+            try: got = int(bool(blocks[k].is_responsible((int(a), int(e)))))
+            except NotFullyVisible as ex: got = 3 if ex.args[0] else 2
+            assert got == want, (size, bs, mo, ctx, grid, k, a, e, got, want)
+            n += 1
+    assert n > 50000
