@@ -108,10 +108,12 @@ def matching(y_true, y_pred, thresh=0.5, criterion='iou'):
         costs = -(scores >= thr).astype(float) - scores / (2 * n_matched)
         ti, pi = linear_sum_assignment(costs)
         ok = scores[ti, pi] >= thr
-        tp = int(np.count_nonzero(ok))
-        sum_matched = float(np.sum(scores[ti, pi][ok]))
+        tp = np.count_nonzero(ok)                      # numpy integer scalar, as in the reference: float32 / np.int64 -> float64 below
+        sum_matched = np.sum(scores[ti, pi][ok])       # stays float32 like the reference's (matching.py:190): the means below are float32 quotients
     fp, fn = n_pred - tp, n_true - tp
-    div = lambda a, b: (a / b) if abs(b) > 1e-10 else 0.0
+    div = lambda a, b: (a / b) if np.abs(b) > 1e-10 else 0.0       # _safe_divide on scalars (matching.py:55-58)
+    # scalar types follow the reference's expressions (matching.py:180-196) so that the float results are the same numbers:
+    # sum (float32) / n_true (int) stays float32, / tp (numpy int) and / (tp + fp/2 + fn/2) are float64 quotients
     fields = dict(criterion=criterion, thresh=thr, fp=fp, tp=tp, fn=fn,
                   precision=(tp / (tp + fp) if tp > 0 else 0), recall=(tp / (tp + fn) if tp > 0 else 0),
                   accuracy=(tp / (tp + fp + fn) if tp > 0 else 0), f1=((2 * tp) / (2 * tp + fp + fn) if tp > 0 else 0),

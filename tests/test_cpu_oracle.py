@@ -392,3 +392,67 @@ def test_ray_classes_equal_reference(golden_dir):
         assert np.array_equal(r.copy(scale=(.5, 1, 2)).vertices, g["%d/scaled" % i])
         r2 = sd.rays_from_json(json.loads(json.dumps(r.to_json())))               # config.json round trip
         assert type(r2) is type(r) and np.array_equal(r2.vertices, r.vertices) and np.array_equal(r2.faces, r.faces)
+
+
+HOSTFUNC_NMS2D = ["r32_356x299", "r11_114x217", "r32_grid16", "r64_small"]
+HOSTFUNC_NMS3D = ["r14_thr02", "r32_noise01_thr01", "r96_aniso_thr03"]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", HOSTFUNC_NMS2D)
+def test_oracle_host_glue_2d_equals_reference_modules(golden_dir, name):
+    """oracle/nms_np.py and oracle/geom2d_np.py against the outputs of the reference's OWN nms.py / geom2d.py
+    (tests/golden/hostfuncs.npz, produced by make_hostfuncs.py from /root/reference): dense and sparse 2-D NMS front-ends
+    (points, prob, dist, original indices) bit-equal, dist_to_coord bit-equal (float32)"""
+    g = np.load(os.path.join(golden_dir, "hostfuncs.npz"))
+    shape, radius, noise, n_rays, grid, pthr, nthr, seed = cases.NMS2D_CASES[name]
+    prob, dist = cases.create_random_data_2d(shape, radius, noise, n_rays, seed)
+    prob = prob[::grid[0], ::grid[1]]; dist = dist[::grid[0], ::grid[1]]
+    p, pr, d = nms_np.non_maximum_suppression(dist, prob, grid=grid, b=2, nms_thresh=nthr, prob_thresh=pthr)
+    k = "nms2d/%s/" % name
+    assert np.array_equal(p, g[k + "points"]) and np.array_equal(pr, g[k + "prob"]) and np.array_equal(d, g[k + "dist"])
+    mask = nms_np._ind_prob_thresh(prob, pthr, b=2)
+    pts = np.stack(np.where(mask), 1) * np.array(grid).reshape(1, 2)
+    ps, prs, ds, inds = nms_np.non_maximum_suppression_sparse(dist[mask], prob[mask], pts, nms_thresh=nthr)
+    assert np.array_equal(ps, g[k + "sparse_points"]) and np.array_equal(inds, g[k + "sparse_inds"])
+    for key, sc in (("coord", (1, 1)), ("coord_scaled", (2, .5))):
+        c = geom2d_np.dist_to_coord(d, p, scale_dist=sc)
+        assert c.dtype == g[k + key].dtype and np.array_equal(c, g[k + key])
+
+
+@needs_ref
+@pytest.mark.parametrize("name", HOSTFUNC_NMS3D)
+def test_oracle_host_glue_3d_equals_reference_modules(golden_dir, name):
+    """3-D: sparse NMS front-end (nms.py:285-384) and polyhedron_to_label (geom3d.py:100-198) of the reference vs the oracle"""
+    from oracle import pipeline3d
+    g = np.load(os.path.join(golden_dir, "hostfuncs.npz"))
+    shape, noise, n_rays, pthr, nthr, seed, aniso = cases.NMS3D_CASES[name]
+    prob, dist = cases.create_random_data_3d(shape, noise, n_rays, seed)
+    rays = cases.rays_golden_spiral(n_rays, aniso)
+    mask = nms_np._ind_prob_thresh(prob, pthr, b=2)
+    pts = np.stack(np.where(mask), 1)
+    ps, prs, ds, inds = nms_np.non_maximum_suppression_3d_sparse(dist[mask], prob[mask], pts, rays, nms_thresh=nthr)
+    k = "nms3d/%s/" % name
+    assert np.array_equal(ps, g[k + "sparse_points"]) and np.array_equal(inds, g[k + "sparse_inds"])
+    assert np.array_equal(ps, g[k + "points"]) and np.array_equal(prs, g[k + "prob"]) and np.array_equal(ds, g[k + "dist"])   # dense == sparse
+    lab = pipeline3d.polyhedron_to_label(ds, ps, rays, shape, prs)
+    assert np.array_equal(lab, g[k + "labels"])
+
+
+def test_matching_and_relabel_equal_reference_modules(golden_dir):
+    """stardist_b200.matching (matching, relabel_sequential) and utils._normalize_grid against the reference's matching.py /
+    utils.py outputs on three label-image pairs x 3 criteria x 3 thresholds"""
+    from stardist_b200.matching import matching, relabel_sequential
+    from stardist_b200.utils import _normalize_grid
+    g = np.load(os.path.join(golden_dir, "hostfuncs.npz"))
+    for seed in (0, 1, 2):
+        a, b = g["match/%d/a" % seed], g["match/%d/b" % seed]
+        for crit in ("iou", "iot", "iop"):
+            for thr in (0.3, 0.5, 0.9):
+                m = matching(a, b, thresh=thr, criterion=crit)
+                got = np.array([m.fp, m.tp, m.fn, m.precision, m.recall, m.accuracy, m.f1, m.n_true, m.n_pred,
+                                m.mean_true_score, m.mean_matched_score, m.panoptic_quality], np.float64)
+                assert np.array_equal(got, g["match/%d/%s/%.1f" % (seed, crit, thr)]), (seed, crit, thr)
+        rl, fw, inv = relabel_sequential(b, offset=3)
+        assert np.array_equal(rl, g["relabel/%d/out" % seed]) and np.array_equal(fw, g["relabel/%d/fw" % seed]) and np.array_equal(inv, g["relabel/%d/inv" % seed])
+    assert np.array_equal(np.array([_normalize_grid((2, 2, 2), 3), _normalize_grid([1, 2, 4], 3)]), g["normalize_grid"])
