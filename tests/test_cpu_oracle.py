@@ -456,3 +456,46 @@ def test_matching_and_relabel_equal_reference_modules(golden_dir):
         rl, fw, inv = relabel_sequential(b, offset=3)
         assert np.array_equal(rl, g["relabel/%d/out" % seed]) and np.array_equal(fw, g["relabel/%d/fw" % seed]) and np.array_equal(inv, g["relabel/%d/inv" % seed])
     assert np.array_equal(np.array([_normalize_grid((2, 2, 2), 3), _normalize_grid([1, 2, 4], 3)]), g["normalize_grid"])
+
+
+@needs_ref
+def test_product_nms_front_end_equals_reference_modules(golden_dir, monkeypatch):
+    """stardist_b200/nms.py (the host glue in front of the device kernels) with its two C entry points replaced by the
+    reference's compiled extensions: dense and sparse, 2-D and 3-D front-ends return what the reference's own nms.py returned
+    (tests/golden/hostfuncs.npz) -- the host logic is device independent, so this pins it on the CPU"""
+    import stardist_b200.lib.stardist2d as l2, stardist_b200.lib.stardist3d as l3
+    from stardist_b200 import nms
+    monkeypatch.setattr(l2, "c_non_max_suppression_inds", ref_ext.stardist2d().c_non_max_suppression_inds)
+    monkeypatch.setattr(l3, "c_non_max_suppression_inds", ref_ext.stardist3d().c_non_max_suppression_inds)
+    g = np.load(os.path.join(golden_dir, "hostfuncs.npz"))
+    for name in HOSTFUNC_NMS2D:
+        shape, radius, noise, n_rays, grid, pthr, nthr, seed = cases.NMS2D_CASES[name]
+        prob, dist = cases.create_random_data_2d(shape, radius, noise, n_rays, seed)
+        prob = prob[::grid[0], ::grid[1]]; dist = dist[::grid[0], ::grid[1]]
+        k = "nms2d/%s/" % name
+        p, pr, d = nms.non_maximum_suppression(dist, prob, grid=grid, b=2, nms_thresh=nthr, prob_thresh=pthr)
+        assert p.dtype == g[k + "points"].dtype and np.array_equal(p, g[k + "points"]) and np.array_equal(pr, g[k + "prob"]) and np.array_equal(d, g[k + "dist"])
+        mask = nms._ind_prob_thresh(prob, pthr, b=2)
+        pts = np.stack(np.where(mask), 1) * np.array(grid).reshape(1, 2)
+        ps, prs, ds, inds = nms.non_maximum_suppression_sparse(dist[mask], prob[mask], pts, nms_thresh=nthr)
+        assert np.array_equal(ps, g[k + "sparse_points"]) and np.array_equal(inds, g[k + "sparse_inds"]) and np.array_equal(ds, g[k + "dist"])
+    for name in HOSTFUNC_NMS3D[:2]:
+        shape, noise, n_rays, pthr, nthr, seed, aniso = cases.NMS3D_CASES[name]
+        prob, dist = cases.create_random_data_3d(shape, noise, n_rays, seed)
+        rays = cases.rays_golden_spiral(n_rays, aniso)
+        k = "nms3d/%s/" % name
+        p, pr, d = nms.non_maximum_suppression_3d(dist, prob, rays, grid=(1, 1, 1), b=2, nms_thresh=nthr, prob_thresh=pthr)
+        assert p.dtype == g[k + "points"].dtype and np.array_equal(p, g[k + "points"]) and np.array_equal(pr, g[k + "prob"]) and np.array_equal(d, g[k + "dist"])
+        mask = nms._ind_prob_thresh(prob, pthr, b=2)
+        pts = np.stack(np.where(mask), 1)
+        ps, prs, ds, inds = nms.non_maximum_suppression_3d_sparse(dist[mask], prob[mask], pts, rays, nms_thresh=nthr)
+        assert np.array_equal(ps, g[k + "sparse_points"]) and np.array_equal(inds, g[k + "sparse_inds"]) and np.array_equal(prs, g[k + "prob"])
+    # border handling of _ind_prob_thresh (nms.py:6-17): scalar, per-axis pairs, zero margins, None
+    prob = np.random.default_rng(0).uniform(size=(9, 11))
+    for b in (2, ((1, 0), (0, 3)), 0, None, ((0, 0), (2, 2))):
+        want = prob > .3
+        if b is not None:
+            bb = ((b, b),) * 2 if np.isscalar(b) else b
+            inner = np.zeros_like(want); inner[tuple(slice(lo if lo > 0 else None, -hi if hi > 0 else None) for lo, hi in bb)] = True
+            want &= inner
+        assert np.array_equal(nms._ind_prob_thresh(prob, .3, b=b), want)
