@@ -44,3 +44,51 @@ def load(modname):
     """e.g. load('stardist.nms') -> the reference's module object"""
     setup()
     return importlib.import_module(modname)
+
+
+class _Any:
+    """absorbs any construction / call / attribute access (keras layers, tensorflow symbols at import time)"""
+    def __init__(self, *a, **k): pass
+    def __call__(self, *a, **k): return _Any()
+    def __getattr__(self, n): return _Any()
+
+
+class _BaseConfig:
+    """the few attributes csbdeep.models.BaseConfig.__init__ provides that the reference's Config2D / Config3D read back"""
+    def __init__(self, axes='YX', n_channel_in=1, n_channel_out=1, allow_new_parameters=False, **kwargs):
+        ax = ''.join(a for a in str(axes).upper() if a != 'C')
+        self.n_dim = len(ax); self.axes = ax + 'C'
+        self.n_channel_in = int(max(1, n_channel_in)); self.n_channel_out = int(max(1, n_channel_out))
+        self.train_checkpoint = 'weights_best.h5'; self.train_checkpoint_last = 'weights_last.h5'; self.train_checkpoint_epoch = 'weights_now.h5'
+        for k, v in kwargs.items(): setattr(self, k, v)
+
+    def update_parameters(self, allow_new=False, **kwargs):
+        for k, v in kwargs.items(): setattr(self, k, v)
+
+    def is_valid(self, return_invalid=False):
+        return (True, ()) if return_invalid else True
+
+
+def load_models():
+    """-> (stardist.models.model2d, stardist.models.model3d) of the reference; only their pure host logic is usable
+    (e.g. StarDist2D._instances_from_prediction called on a stand-in `self` with .config.grid and .thresholds)"""
+    setup()
+    for name in ("csbdeep.models.base_model", "csbdeep.internals.predict", "csbdeep.internals.train", "csbdeep.data", "csbdeep.internals",
+                 "tensorflow", "csbdeep.internals.blocks", "csbdeep.internals.nets", "csbdeep.models", "csbdeep.utils.tf", "csbdeep.internals.probability"):
+        sys.modules[name] = _Stub(name)
+    sys.modules["csbdeep.models.base_model"].BaseModel = type("BaseModel", (object,), {})
+    sys.modules["csbdeep.models"].BaseConfig = _BaseConfig
+    sys.modules["csbdeep.data"].Resizer = type("Resizer", (object,), {})
+    sys.modules["csbdeep.internals.train"].RollingSequence = type("RollingSequence", (object,), {})
+    tfm = sys.modules["csbdeep.utils.tf"]
+
+    def keras_import(sub=None, *names):
+        if not names:
+            k = _Any(); k.__dict__['__version__'] = '2.15.0'
+            return k
+        cls = [type(n, (object,), {}) for n in names]
+        return cls[0] if len(cls) == 1 else tuple(cls)
+    tfm.keras_import = keras_import; tfm.IS_TF_1 = False; tfm.IS_KERAS_3_PLUS = False; tfm.BACKEND = _Any(); tfm.export_SavedModel = _Any()
+    tfm.CARETensorBoard = type("CARETensorBoard", (object,), {}); tfm.CARETensorBoardImage = type("CARETensorBoardImage", (object,), {})
+    cu = sys.modules["csbdeep.utils"]; cu.backend_channels_last = lambda: True; cu.load_json = None; cu.save_json = None; cu.normalize = None
+    return importlib.import_module("stardist.models.model2d"), importlib.import_module("stardist.models.model3d")

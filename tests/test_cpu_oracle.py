@@ -499,3 +499,82 @@ def test_product_nms_front_end_equals_reference_modules(golden_dir, monkeypatch)
             inner = np.zeros_like(want); inner[tuple(slice(lo if lo > 0 else None, -hi if hi > 0 else None) for lo, hi in bb)] = True
             want &= inner
         assert np.array_equal(nms._ind_prob_thresh(prob, .3, b=b), want)
+
+
+def _jsonable(v):
+    if isinstance(v, (tuple, list)): return [_jsonable(x) for x in v]
+    if isinstance(v, dict): return {str(k): _jsonable(x) for k, x in v.items()}
+    if isinstance(v, np.integer): return int(v)
+    if isinstance(v, np.floating): return float(v)
+    if isinstance(v, np.ndarray): return _jsonable(v.tolist())
+    return v
+
+
+def test_config_classes_equal_reference(golden_dir):
+    """Config2D / Config3D: every attribute (names and values, incl. the derived ones -- n_channel_out, rays_json, net_input_shape,
+    train_* defaults) equals the reference classes' for 4 + 4 keyword sets (tests/golden/models_host.json, produced by importing
+    stardist/models/model2d.py / model3d.py with keras / csbdeep stubbed); _axes_div_by too"""
+    import json, types
+    import stardist_b200 as sd
+    meta = json.load(open(os.path.join(golden_dir, "models_host.json")))
+    tup = lambda kw: {k: (tuple(v) if isinstance(v, list) else v) for k, v in kw.items()}
+    for i, (kw, want) in enumerate(meta["cfg2d"]):
+        cfg = sd.Config2D(**tup(kw))
+        assert _jsonable(vars(cfg)) == want, (kw, {k: (v, want.get(k)) for k, v in _jsonable(vars(cfg)).items() if want.get(k) != v})
+        assert _jsonable(sd.StarDist2D._axes_div_by(types.SimpleNamespace(config=cfg), "YXC")) == meta["div_by"]["2d/%d" % i]
+    for i, (kw, want) in enumerate(meta["cfg3d"]):
+        k = tup(kw); n = k.pop("n_rays", 96)
+        cfg = sd.Config3D(rays=sd.Rays_GoldenSpiral(n, anisotropy=k.get("anisotropy")), **k)
+        assert _jsonable(vars(cfg)) == want, (kw, {a: (v, want.get(a)) for a, v in _jsonable(vars(cfg)).items() if want.get(a) != v})
+        assert _jsonable(sd.StarDist3D._axes_div_by(types.SimpleNamespace(config=cfg), "ZYXC")) == meta["div_by"]["3d/%d" % i]
+
+
+@needs_ref
+def test_instances_from_prediction_glue_equals_reference_classes(golden_dir, monkeypatch):
+    """StarDist2D / StarDist3D._instances_from_prediction (numpy-level glue: dense / sparse, grid, scale, multi-class) against
+    the reference classes' own methods (tests/golden/models_host.npz).  The device-backed leaves are replaced by their pinned
+    CPU equivalents: the C entry points by the reference extensions, dist_to_coord by the oracle's (== reference, hostfuncs.npz)."""
+    import types
+    import stardist_b200 as sd
+    import stardist_b200.lib.stardist2d as l2, stardist_b200.lib.stardist3d as l3
+    from stardist_b200.models import model2d as pm2
+    monkeypatch.setattr(l2, "c_non_max_suppression_inds", ref_ext.stardist2d().c_non_max_suppression_inds)
+    monkeypatch.setattr(l3, "c_non_max_suppression_inds", ref_ext.stardist3d().c_non_max_suppression_inds)
+    monkeypatch.setattr(l3, "c_polyhedron_to_label", ref_ext.stardist3d().c_polyhedron_to_label)
+    monkeypatch.setattr(pm2, "dist_to_coord", geom2d_np.dist_to_coord)
+    g = np.load(os.path.join(golden_dir, "models_host.npz"))
+    thr = types.SimpleNamespace(prob=0.9, nms=0.3)
+
+    def same(res, prefix, keys):
+        for k in keys:
+            a, b = np.asarray(res[k]), g[prefix + k]
+            assert a.shape == b.shape and np.array_equal(a, b), (prefix, k)
+
+    shape, radius, noise, n_rays, grid, pthr, nthr, seed = cases.NMS2D_CASES["r32_356x299"]
+    prob, dist = cases.create_random_data_2d(shape, radius, noise, n_rays, seed)
+    fake = types.SimpleNamespace(config=types.SimpleNamespace(grid=(1, 1)), thresholds=thr)
+    _, res = sd.StarDist2D._instances_from_prediction(fake, shape, prob, dist, return_labels=False)
+    same(res, "2d/dense/", ("coord", "points", "prob"))
+    fake2 = types.SimpleNamespace(config=types.SimpleNamespace(grid=(2, 2)), thresholds=thr)
+    _, res = sd.StarDist2D._instances_from_prediction(fake2, shape, prob[::2, ::2], dist[::2, ::2], prob_class=g["2d/grid_scale_class/prob_class_in"],
+                                                      return_labels=False, scale=dict(X=.5, Y=2.))
+    same(res, "2d/grid_scale_class/", ("coord", "points", "prob", "class_prob", "class_id"))
+    mask = prob > 0.92
+    _, res = sd.StarDist2D._instances_from_prediction(fake, shape, prob[mask], dist[mask], points=np.stack(np.where(mask), 1),
+                                                      prob_class=g["2d/sparse_class/prob_class_in"], nms_thresh=0.4, return_labels=False)
+    same(res, "2d/sparse_class/", ("coord", "points", "prob", "class_prob", "class_id"))
+
+    shape, noise, n_rays, pthr, nthr, seed, aniso = cases.NMS3D_CASES["r32_noise01_thr01"]
+    prob, dist = cases.create_random_data_3d(shape, noise, n_rays, seed)
+    rays = sd.Rays_GoldenSpiral(n_rays)
+    fake3 = sd.StarDist3D.__new__(sd.StarDist3D)
+    fake3.config = types.SimpleNamespace(grid=(1, 1, 1), rays_json=rays.to_json()); fake3.thresholds = dict(prob=float(pthr), nms=float(nthr))
+    labels, res = sd.StarDist3D._instances_from_prediction(fake3, shape, prob, dist)
+    assert labels.dtype == g["3d/dense/labels"].dtype and np.array_equal(labels, g["3d/dense/labels"])
+    same(res, "3d/dense/", ("dist", "points", "prob"))
+    mask = prob > pthr
+    mask[:2] = mask[-2:] = False; mask[:, :2] = mask[:, -2:] = False; mask[:, :, :2] = mask[:, :, -2:] = False
+    pts = np.stack(np.where(mask), 1).astype(np.float64)       # float points: the numpy-level path (integer points go to the device path)
+    labels, res = sd.StarDist3D._instances_from_prediction(fake3, shape, prob[mask], dist[mask], points=pts, nms_thresh=0.2, scale=dict(Z=1., Y=.5, X=2.))
+    assert np.array_equal(labels, g["3d/sparse_scale/labels"])
+    same(res, "3d/sparse_scale/", ("dist", "points", "prob", "rays_vertices"))
