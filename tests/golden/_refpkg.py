@@ -4,6 +4,7 @@ dependencies (tensorflow / csbdeep / scikit-image): `stardist` and its sub-packa
 the pure-numpy code paths use, and stardist.lib.stardist2d / stardist3d are the reference's own compiled extensions from
 oracle/_ref.  Only used by the make_*.py fixture generators (build container; the fixtures travel, this does not)."""
 import importlib, os, sys, types
+import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = "/root/reference/stardist"
@@ -13,6 +14,20 @@ class _Stub(types.ModuleType):
     def __getattr__(self, name):
         if name.startswith("__"): raise AttributeError(name)
         return lambda *a, **k: (_ for _ in ()).throw(RuntimeError("stubbed third-party function %s.%s called" % (self.__name__, name)))
+
+
+class _Region:
+    def __init__(self, label, sl, image):
+        self.label = label; self.slice = sl; self.image = image
+        self.bbox = tuple(s.start for s in sl) + tuple(s.stop for s in sl)
+
+
+def _regionprops(label_image):
+    """stand-in for skimage.measure.regionprops restricted to what stardist/big.py reads (label, bbox, image): one region
+    per label present, ascending label order, bbox = (min_0, min_1[, min_2], max_0, max_1[, max_2]) half open"""
+    from scipy.ndimage import find_objects
+    label_image = np.asarray(label_image)
+    return [_Region(i + 1, sl, label_image[sl] == i + 1) for i, sl in enumerate(find_objects(label_image)) if sl is not None]
 
 
 def setup():
@@ -25,6 +40,7 @@ def setup():
     sys.modules["csbdeep.utils"].__path__ = []
     import pathlib
     sys.modules["csbdeep.utils.six"].Path = pathlib.Path
+    sys.modules["skimage.measure"].regionprops = _regionprops
     cu = sys.modules["csbdeep.utils"]
     cu._raise = U._raise; cu.axes_check_and_normalize = U.axes_check_and_normalize; cu.axes_dict = U.axes_dict
     for pkg, sub in (("stardist", ""), ("stardist.geometry", "geometry"), ("stardist.lib", "lib"), ("stardist.models", "models")):

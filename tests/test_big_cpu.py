@@ -149,3 +149,25 @@ def test_block_responsibility_equals_the_reference(golden_dir):
             assert got == want, (size, bs, mo, ctx, grid, k, a, e, got, want)
             n += 1
     assert n > 50000
+
+
+def test_block_pipeline_equals_the_reference(golden_dir):
+    """BlockND.read / crop_context / filter_objects / translate_coordinates / write, block by block, against the reference's
+    own big.py on three synthetic label images (tests/golden/big_blocks.npz, make_big_blocks.py): the same objects survive in
+    every block, with the same translated points, and the re-assembled image equals the input"""
+    sys.path.insert(0, golden_dir)
+    import make_big_blocks as mk
+    g = np.load(os.path.join(golden_dir, "big_blocks.npz"))
+    for ci, (shape, axes, bs, mo, ctx, grid, n, rmax, seed) in enumerate(mk.CASES):
+        lab = g["%d/label" % ci]
+        blocks = BlockND.cover(shape, axes, bs, mo, ctx, grid)
+        result = np.zeros_like(lab)
+        for b in blocks:
+            local, polys, ids = mk.block_inputs(b, lab, axes)
+            kept, polys_out = b.filter_objects(b.crop_context(local, axes=axes), polys, axes=axes)
+            assert np.array_equal(kept, g["%d/%d/kept" % (ci, b.id)])
+            for k in ("points", "prob", "dist"):
+                assert np.array_equal(polys_out[k], g["%d/%d/%s" % (ci, b.id, k)]), (ci, b.id, k)
+            assert np.array_equal(polys_out["rays_faces"], np.arange(6))
+            b.write(result, np.where(kept > 0, b.crop_context(b.read(lab, axes=axes), axes=axes), 0), axes=axes)
+        assert np.array_equal(result, g["%d/reassembled" % ci]) and np.array_equal(result, lab)
