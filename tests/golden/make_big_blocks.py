@@ -61,3 +61,46 @@ if __name__ == "__main__":
         print(ci, shape, len(blocks), "blocks, objects", int(lab.max()), "reassembled == label:", bool(np.array_equal(result, lab)))
     np.savez_compressed(os.path.join(HERE, "big_blocks.npz"), **out)
     print(os.path.getsize(os.path.join(HERE, "big_blocks.npz")), "bytes")
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# predict_instances_big (stardist/models/base.py:838-983) on a stand-in model: `img` IS a label image, predict_instances returns
+# the objects visible in the block (renumbered 1..n) with their polys -- the bookkeeping under test is the reference's / ours.
+class FakeModel:
+    def __init__(self, axes_out, grid, overlap):
+        import types
+        self._axes_out = axes_out + 'C'; self.config = types.SimpleNamespace(axes=axes_out + 'C')
+        self._grid = dict(zip(axes_out, grid)); self._overlap = dict(zip(axes_out, overlap))
+
+    def _axes_div_by(self, axes): return tuple(self._grid.get(a, 1) for a in axes)
+    def _axes_tile_overlap(self, axes): return tuple(self._overlap.get(a, 0) for a in axes)
+
+    def predict_instances(self, x, axes=None, **kwargs):
+        ids = np.unique(x); ids = ids[ids > 0]
+        local = np.zeros(x.shape, np.int32)
+        for j, i in enumerate(ids, 1): local[x == i] = j
+        pts = np.array([np.round(np.mean(np.argwhere(local == j), 0)) for j in range(1, len(ids) + 1)]).reshape(len(ids), x.ndim)
+        polys = dict(points=pts, prob=(ids % 97 / 97.0).astype(np.float32), dist=np.tile(ids[:, None].astype(np.float32), (1, 5)), rays_faces=np.arange(6))
+        return local, polys
+
+
+BIG_CASES = [(0, dict(block_size=96, min_overlap=24, context=8), (1, 1), (6, 6)), (1, dict(block_size=(128, 100), min_overlap=(24, 26), context=None), (4, 2), (16, 4)),
+             (2, dict(block_size=(24, 48, 56), min_overlap=(10, 16, 16), context=(2, 8, 4)), (1, 2, 2), (2, 8, 4))]
+
+
+def run_big(method, label, axes, kw, grid, overlap):
+    m = FakeModel(axes, grid, overlap)
+    return method(m, label, axes=axes, show_progress=False, **{k: v for k, v in kw.items()})
+
+
+if __name__ == "__main__":
+    m2, _ = _refpkg.load_models()
+    base = sys.modules["stardist.models.base"]
+    g = dict(np.load(os.path.join(HERE, "big_blocks.npz")))
+    for ci, kw, grid, overlap in BIG_CASES:
+        shape, axes = CASES[ci][0], CASES[ci][1]
+        labels_out, polys = run_big(base.StarDistBase.predict_instances_big, g["%d/label" % ci], axes, kw, grid, overlap)
+        g["big/%d/labels" % ci] = labels_out
+        for k in ("points", "prob", "dist", "rays_faces"): g["big/%d/%s" % (ci, k)] = polys[k]
+        print("predict_instances_big", ci, labels_out.dtype, int(labels_out.max()), len(polys["prob"]))
+    np.savez_compressed(os.path.join(HERE, "big_blocks.npz"), **g)

@@ -171,3 +171,20 @@ def test_block_pipeline_equals_the_reference(golden_dir):
             assert np.array_equal(polys_out["rays_faces"], np.arange(6))
             b.write(result, np.where(kept > 0, b.crop_context(b.read(lab, axes=axes), axes=axes), 0), axes=axes)
         assert np.array_equal(result, g["%d/reassembled" % ci]) and np.array_equal(result, lab)
+
+
+def test_predict_instances_big_bookkeeping_equals_the_reference(golden_dir):
+    """StarDistBase.predict_instances_big (block cover, per-block predict_instances, crop, responsibility filter, running label
+    offset, ordered write, poly concatenation; base.py:838-983) against the REFERENCE method run on the same stand-in model
+    (tests/golden/big_blocks.npz 'big/*', make_big_blocks.py: context=None, per-axis grids, 2-D and 3-D)"""
+    sys.path.insert(0, golden_dir)
+    import make_big_blocks as mk
+    from stardist_b200.models.base import StarDistBase
+    g = np.load(os.path.join(golden_dir, "big_blocks.npz"))
+    for ci, kw, grid, overlap in mk.BIG_CASES:
+        axes = mk.CASES[ci][1]
+        labels_out, polys = mk.run_big(StarDistBase.predict_instances_big, g["%d/label" % ci], axes, kw, grid, overlap)
+        assert labels_out.dtype == g["big/%d/labels" % ci].dtype and np.array_equal(labels_out, g["big/%d/labels" % ci])
+        for k in ("points", "prob", "dist", "rays_faces"):
+            assert np.array_equal(polys[k], g["big/%d/%s" % (ci, k)]), (ci, k)
+        assert set(polys) == {"points", "prob", "dist", "rays_faces"}
