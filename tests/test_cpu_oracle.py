@@ -349,8 +349,9 @@ def test_stage_fill_matches_numpy_cast():
     from stardist_b200.models.base import StarDistBase
     rng = np.random.default_rng(0)
     base = rng.uniform(-3, 3, (70, 300, 40))
+    big = rng.uniform(-3, 3, (1 << 23) + 5).astype(np.float32)      # above the threshold of the torch path
     inputs = [base.astype(np.float32), base, base.astype(np.float32)[::-1, ::2], base[:, :, ::-1], np.asfortranarray(base.astype(np.float32)),
-              (base * 1000).astype(np.uint16), (base * 10).astype(np.int8), base.astype('>f4'), base.astype(np.float16), base[:3, :5, :7].astype(np.float32)]
+              big, big.astype(np.float64)[::-1], (base * 1000).astype(np.uint16), (base * 10).astype(np.int8), base.astype('>f4'), base.astype(np.float16), base[:3, :5, :7].astype(np.float32)]
     for x in inputs:
         stage = torch.full((1,) + x.shape, np.nan, dtype=torch.float32)
         StarDistBase._stage_fill(stage, x)
