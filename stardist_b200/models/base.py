@@ -270,7 +270,7 @@ class StarDistBase:
 
     @staticmethod
     def _stage_fill(stage, x):
-        """host array x (any dtype / strides) -> float32 staging tensor stage[0] (same shape).  Float arrays go through torch's
+        """host array x (any dtype / strides) -> float32 staging tensor stage[0] (same shape).  Large float arrays go through torch's
         multi-threaded copy (a 134 MB volume: 3-6 ms instead of 27-38 ms with np.copyto on 8 cores), everything else, and
         anything torch refuses (byte-swapped, unsupported dtypes), through numpy; both are IEEE conversions to float32."""
         if x.dtype in (np.float32, np.float64) and x.size >= (1 << 23):      # volumes; a 1024^2 image stays on the single memcpy
