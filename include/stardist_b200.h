@@ -236,6 +236,17 @@ int sdb_maxpool_split(const void* in_hi, const void* in_lo, int n, int h, int w,
 int sdb_heads_split(const void* f_hi, const void* f_lo, long long npix, int cfeat, const float* d_wp, const float* d_bp,
                     const float* d_wd, const float* d_bd, int n_rays, float* d_prob, float* d_dist, sdb_stream_t stream);
 
+/* ---- predict_instances_big on the device (stardist/big.py:340-413 filter_objects, :319-326 write; base.py:959) ---- */
+/* per-label bounding boxes of a C-contiguous int32 label tile (ndim 2 or 3): d_bbox int32[(max_label+1)*6] =
+ * {min0,min1,min2,max0,max1,max2} (inclusive; 2-D tiles use columns 1,2,4,5), absent labels keep {INT_MAX.., -1..};
+ * d_bad[0] != 0 when a value lies outside [0, max_label].  Replaces skimage.measure.regionprops (big.py:373). */
+int sdb_label_bbox(const int* d_labels, int ndim, const int* shape, int max_label, int* d_bbox, int* d_bad, sdb_stream_t stream);
+/* in place labels[i] = lut[labels[i]] for non-zero entries (foreign objects -> 0, kept objects -> 1..n_kept) */
+int sdb_label_remap(int* d_labels, long long n, const int* d_lut, sdb_stream_t stream);
+/* BlockND.write with the running label offset folded in: dst[origin+idx] = tile[idx] + add where tile[idx] > 0 */
+int sdb_label_write(const int* d_tile, int ndim, const int* tile_shape, int add, int* d_dst, const int* dst_shape,
+                    const int* origin, sdb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,7 +81,62 @@ def star_dist(lbl, n_rays=32):
     return dist
 
 
-def calibrated_weights(config, seed=0, calib_shape=(512, 512), ridge=1e-3):
+def ellipsoid_labels(shape, seed=0, fill=0.30, rmin=5, rmax=9, aniso=(0.6, 1, 1)):
+    """non-overlapping random ellipsoids (semi-axes U[rmin,rmax] * aniso), kept a margin away from the faces"""
+    rng = np.random.default_rng(seed)
+    lbl = np.zeros(shape, np.int32)
+    target = fill * np.prod(shape)
+    filled, k = 0, 0
+    for _ in range(400000):
+        if filled >= target: break
+        r = rng.uniform(rmin, rmax, 3) * np.array(aniso)
+        m = np.ceil(r).astype(int) + 1
+        c = np.array([rng.integers(m[i], shape[i] - m[i]) for i in range(3)])
+        sl = tuple(slice(c[i] - m[i], c[i] + m[i] + 1) for i in range(3))
+        zz, yy, xx = np.mgrid[-m[0]:m[0] + 1, -m[1]:m[1] + 1, -m[2]:m[2] + 1]
+        el = (zz / r[0]) ** 2 + (yy / r[1]) ** 2 + (xx / r[2]) ** 2 <= 1
+        if (lbl[sl][el] > 0).any(): continue
+        k += 1
+        lbl[sl][el] = k
+        filled += el.sum()
+    return lbl
+
+
+def star_dist3d(lbl, rays_vertices):
+    """3-D star distances by unit-step ray marching along the (un-normalised) ray vertices until the label changes
+    (stardist/lib/stardist3d_impl.cpp _COMMON_star_dist3D semantics incl. the half-step correction), vectorised over
+    the foreground voxels; distances are in units of |vertex| like the reference's"""
+    D, H, W = lbl.shape
+    R = len(rays_vertices)
+    zs, ys, xs = np.nonzero(lbl)
+    val = lbl[zs, ys, xs]
+    dist = np.zeros(lbl.shape + (R,), np.float32)
+    for k in range(R):
+        dz, dy, dx = (np.float32(v) for v in rays_vertices[k])
+        z = np.zeros(len(zs), np.float32); y = np.zeros(len(zs), np.float32); x = np.zeros(len(zs), np.float32)
+        alive = np.ones(len(zs), bool)
+        res = np.zeros(len(zs), np.float32)
+        for _ in range(4 * max(D, H, W)):
+            if not alive.any(): break
+            z[alive] += dz; y[alive] += dy; x[alive] += dx
+            ii = np.rint(zs + z).astype(int); jj = np.rint(ys + y).astype(int); kk = np.rint(xs + x).astype(int)
+            out = alive & ((ii < 0) | (ii >= D) | (jj < 0) | (jj >= H) | (kk < 0) | (kk >= W))
+            inb = alive & ~out
+            diff = np.zeros_like(alive)
+            diff[inb] = lbl[ii[inb], jj[inb], kk[inb]] != val[inb]
+            stop = out | diff
+            if stop.any():
+                res[stop] = np.sqrt(x[stop] ** 2 + y[stop] ** 2 + z[stop] ** 2) / np.float32(np.sqrt(dz * dz + dy * dy + dx * dx)) - np.float32(0.5)
+                alive &= ~stop
+        dist[zs, ys, xs, k] = np.maximum(res, 0)
+    return dist
+
+
+def volume_from_labels(lbl, seed=0):
+    return image_from_labels(lbl, seed)
+
+
+def calibrated_weights(config, seed=0, calib_shape=None, ridge=1e-3):
     """Glorot-uniform U-Net body (seeded) + heads fitted by ridge regression so that the network
     output on synthetic cell images resembles a trained StarDist (prob ~ edt_prob, dist ~ star_dist).
     A random-init net gives noise-like dist (negative -> clamped to 1e-3 -> degenerate polygons, no
@@ -90,11 +145,18 @@ def calibrated_weights(config, seed=0, calib_shape=(512, 512), ridge=1e-3):
     from stardist_b200.models.weights import glorot_uniform_weights
     from . import unet_torch
     w = glorot_uniform_weights(config, seed=seed)
-    lbl = ellipse_labels(calib_shape, seed=seed + 17)
+    if config.n_dim == 2:
+        lbl = ellipse_labels(calib_shape or (512, 512), seed=seed + 17)
+    else:
+        lbl = ellipsoid_labels(calib_shape or (48, 128, 128), seed=seed + 17)
     img = image_from_labels(lbl, seed + 17)
     F = unet_torch.forward(config, w, img[None, ..., None], return_features=True)[0]      # [H,W,128]
     P = np.clip(edt_prob(lbl), 0.02, 0.98)
-    D = star_dist(lbl, config.n_rays)
+    if config.n_dim == 2:
+        D = star_dist(lbl, config.n_rays)
+    else:
+        from stardist_b200.rays3d import rays_from_json
+        D = star_dist3d(lbl, rays_from_json(config.rays_json).vertices)
     X = F.reshape(-1, F.shape[-1]).astype(np.float64)
     X1 = np.concatenate([X, np.ones((len(X), 1))], 1)
     Y = np.concatenate([np.log(P / (1 - P)).reshape(-1, 1), D.reshape(-1, config.n_rays)], 1).astype(np.float64)

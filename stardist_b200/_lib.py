@@ -83,6 +83,12 @@ def _declare(lib):
     lib.sdb_relabel_sequential.argtypes = [P, c_longlong, c_int, c_int, P, POINTER(c_int), P]
     lib.sdb_relabel_sequential.restype = c_int
     lib.sdb_nms3d.argtypes = [P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_label_bbox.argtypes = [P, c_int, POINTER(c_int), c_int, P, P, P]
+    lib.sdb_label_bbox.restype = c_int
+    lib.sdb_label_remap.argtypes = [P, c_longlong, P, P]
+    lib.sdb_label_remap.restype = c_int
+    lib.sdb_label_write.argtypes = [P, c_int, POINTER(c_int), c_int, P, POINTER(c_int), POINTER(c_int), P]
+    lib.sdb_label_write.restype = c_int
     for name in ("_LIB_non_maximum_suppression_2d", "_LIB_polygons_to_label_2d", "sdb_nms2d",
                  "sdb_polygons_to_label_2d", "sdb_dist_to_coord_2d", "sdb_threshold_sort",
                  "sdb_gather_candidates", "sdb_conv3x3_2d", "sdb_maxpool2x2_2d", "sdb_heads_2d",

@@ -85,6 +85,18 @@ class Block:
             return False
         return True
 
+    def responsible_many(self, bmin, bmax):
+        """vectorised is_responsible for arrays of boxes (bmin inclusive, bmax exclusive, relative to the block without
+        context): returns (mine bool[n], invisible bool[n]); invisible marks the boxes for which is_responsible raises"""
+        bmin, bmax = np.asarray(bmin), np.asarray(bmax)
+        r_end = self.size - self.context_start - self.context_end
+        span = (bmin == 0) & (bmax >= self.resp_start)
+        invisible = span & ((bmax == r_end) | (not self.at_begin))
+        mine = ~(bmax < self.resp_start)
+        if not self.at_end:
+            mine &= ~(bmax == r_end)
+        return mine, invisible
+
     def __repr__(self):
         w = self.slice_write
         return (f'Block({self.start:03}:{self.end:03}, write={w.start:03}:{w.stop:03}, '
@@ -193,6 +205,22 @@ class BlockND:
 
     def is_responsible(self, slices, axes=None):
         return all(t.is_responsible((s.start, s.stop)) for t, s in zip(self.blocks_for_axes(axes), slices))
+
+    def responsible_many(self, bmin, bmax, axes=None):
+        """is_responsible for n boxes at once: bmin / bmax int arrays [n, ndim] (max exclusive).  Returns
+        (mine bool[n], invisible bool[n]) with the evaluation order of `all(t.is_responsible(...) for t in blocks)`:
+        an axis is only looked at while all previous axes answered True, so `invisible` (the NotFullyVisible cases of
+        big.py:89-122) is raised by the first axis that objects before any axis has answered False."""
+        blocks = self.blocks_for_axes(axes)
+        bmin, bmax = np.asarray(bmin), np.asarray(bmax)
+        n = len(bmin)
+        alive = np.ones(n, bool)          # no axis has answered False (or raised) yet
+        invisible = np.zeros(n, bool)
+        for k, t in enumerate(blocks):
+            m, inv = t.responsible_many(bmin[:, k], bmax[:, k])
+            invisible |= alive & inv
+            alive &= m & ~inv
+        return alive, invisible
 
     def __repr__(self):
         return 'BlockND(%s|%s)' % (self.id, ','.join(f'{a}={t.start:03}:{t.end:03}' for t, a in zip(self.blocks, self.axes)))

@@ -33,6 +33,9 @@ constexpr int RANK_NONE = 0x7fffffff;
 struct PaintArgs {
   const float* dist; const float* points; const float* verts; const int* faces;
   int n_polys, n_rays, n_faces, nz, ny, nx, mode;
+  // sequential variant (labels == 0 among the inputs, or overlap_label == 0): one launch per polyhedron, the reference's
+  // update rule applied in place (stardist3d_impl.cpp:1508-1517)
+  int poly0; int* direct; const int* labels; int use_overlap, overlap_label;
 };
 
 // render_mode 2 only: hull facet planes per polyhedron (one thread each; gift wrapping is serial)
@@ -58,7 +61,7 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
   __shared__ int bbox[6];
   __shared__ float center[3];
   __shared__ int n_hull;
-  const int i = blockIdx.x;
+  const int i = blockIdx.x + A.poly0;
   const float* d = A.dist + (size_t)i * A.n_rays;
   if (threadIdx.x < 3) center[threadIdx.x] = A.points[3 * i + threadIdx.x];
   __syncthreads();
@@ -117,7 +120,11 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
         debug_img[((size_t)z * A.ny + y) * A.nx + x] = 1;
       continue;
     }
-    if (inside) {
+    if (inside && A.direct) {
+      const size_t off = ((size_t)z * A.ny + y) * A.nx + x;
+      const int cur = A.direct[off];
+      A.direct[off] = cur == 0 ? A.labels[i] : (A.use_overlap ? A.overlap_label : cur);
+    } else if (inside) {
       const size_t off = ((size_t)z * A.ny + y) * A.nx + x;
       const int old = atomicMin(&rank_img[off], i);
       if (second_img) {
@@ -145,6 +152,11 @@ __global__ void k_finalize3d(int* __restrict__ out, const int* __restrict__ rank
   }
 }
 
+__global__ void k_count_zero(const int* __restrict__ labels, int n, int* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && labels[i] == 0) *flag = 1;
+}
+
 __global__ void k_fill(int* p, long long n, int v) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -162,6 +174,35 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
   const long long nvox = (long long)nz * ny * nx;
   const int fb = (int)std::min<long long>(cdiv(nvox, 256), 148 * 16);
   if (nvox == 0) return 0;
+  // labels == 0 ("paints nothing, and is painted over") and overlap_label == 0 make the reference's in-place rule order
+  // dependent beyond "first cover wins": detect them (one 4-byte read-back) and run the polyhedra one launch at a time
+  bool sequential = use_overlap_label && overlap_label == 0;
+  if (!sequential && n_polys > 0 && render_mode != 4) {
+    sdb::DevBuf b_z;
+    SDB_CUDA(b_z.alloc(4, st));
+    SDB_CUDA(cudaMemsetAsync(b_z.p, 0, 4, st));
+    SDB_LAUNCH(k_count_zero, cdiv(n_polys, 256), 256, 0, st, d_labels, n_polys, b_z.as<int>());
+    int hz = 0;
+    SDB_CUDA(cudaMemcpyAsync(&hz, b_z.p, 4, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaStreamSynchronize(st));
+    sequential = hz != 0;
+  }
+  if (sequential && render_mode != 4) {
+    SDB_CUDA(cudaMemsetAsync(d_result, 0, (size_t)nvox * sizeof(int), st));
+    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode, 0, d_result, d_labels, use_overlap_label, overlap_label};
+    const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double);
+    sdb::DevBuf b_hull, b_hcnt;
+    if (render_mode == 2) {
+      SDB_CUDA(b_hull.alloc((size_t)n_polys * n_faces * 4 * sizeof(double), st));
+      SDB_CUDA(b_hcnt.alloc((size_t)n_polys * sizeof(int), st));
+      SDB_LAUNCH(k_hull3d, cdiv(n_polys, 32), 32, 0, st, A, b_hull.as<double>(), b_hcnt.as<int>());
+    }
+    for (int i = 0; i < n_polys; ++i) {
+      A.poly0 = i;
+      SDB_LAUNCH(k_paint3d, 1, 256, smem, st, A, nullptr, nullptr, nullptr, b_hull.as<double>(), b_hcnt.as<int>());
+    }
+    return 0;
+  }
   sdb::DevBuf b_rank, b_second, b_debug;
   SDB_CUDA(b_rank.alloc((size_t)nvox * sizeof(int), st));
   SDB_LAUNCH(k_fill, fb, 256, 0, st, b_rank.as<int>(), nvox, RANK_NONE);
@@ -174,7 +215,7 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
     SDB_CUDA(cudaMemsetAsync(b_debug.p, 0, (size_t)nvox * sizeof(int), st));
   }
   if (n_polys > 0) {
-    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode};
+    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode, 0, nullptr, d_labels, use_overlap_label, overlap_label};
     const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double);
     sdb::DevBuf b_hull, b_hcnt;
     if (render_mode == 2) {
@@ -182,8 +223,11 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
       SDB_CUDA(b_hcnt.alloc((size_t)n_polys * sizeof(int), st));
       SDB_LAUNCH(k_hull3d, cdiv(n_polys, 32), 32, 0, st, A, b_hull.as<double>(), b_hcnt.as<int>());
     }
+    sdb::ProfSpan sp;
+    sdb::profile_begin("nms3d_paint", st, &sp);
     SDB_LAUNCH(k_paint3d, n_polys, 256, smem, st, A, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
                render_mode == 4 ? b_debug.as<int>() : nullptr, b_hull.as<double>(), b_hcnt.as<int>());
+    sdb::profile_end("nms3d_paint", st, &sp);
   }
   SDB_LAUNCH(k_finalize3d, fb, 256, 0, st, d_result, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
              render_mode == 4 ? b_debug.as<int>() : nullptr, nvox, d_labels, use_overlap_label, overlap_label, render_mode);
@@ -295,12 +339,18 @@ extern "C" void _LIB_polyhedron_to_label(const float* dist, const float* points,
                                          const int nz, const int ny, const int nx, const int render_mode,
                                          const int verbose, const int use_overlap_label, const int overlap_label,
                                          int* result) {
-  auto fail = [&](const char* what) { fprintf(stderr, "stardist_b200: _LIB_polyhedron_to_label failed: %s: %s\n", what, sdb_last_error()); abort(); };
+  // void signature (stardist3d_lib.h:67-82): on failure the result is zeroed and the message stays in sdb_last_error();
+  // the host process is never aborted
+  const long long nvox = (long long)nz * ny * nx;
+  auto fail = [&](const char* what) {
+    fprintf(stderr, "stardist_b200: _LIB_polyhedron_to_label failed: %s: %s\n", what, sdb_last_error());
+    for (long long i = 0; i < nvox; ++i) result[i] = 0;
+    cudaGetLastError();
+  };
   cudaStream_t st = 0;
   sdb::DevBuf d_dist, d_points, d_verts, d_faces, d_labels, d_out;
-  const long long nvox = (long long)nz * ny * nx;
   if (d_dist.alloc((size_t)n_polys * n_rays * 4, st) || d_points.alloc((size_t)n_polys * 12, st) || d_verts.alloc((size_t)n_rays * 12, st) ||
-      d_faces.alloc((size_t)n_faces * 12, st) || d_labels.alloc((size_t)n_polys * 4, st) || d_out.alloc((size_t)nvox * 4, st)) fail("alloc");
+      d_faces.alloc((size_t)n_faces * 12, st) || d_labels.alloc((size_t)n_polys * 4, st) || d_out.alloc((size_t)nvox * 4, st)) { sdb::set_error("device allocation failed"); return fail("alloc"); }
   if (n_polys > 0) {
     cudaMemcpyAsync(d_dist.p, dist, (size_t)n_polys * n_rays * 4, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_points.p, points, (size_t)n_polys * 12, cudaMemcpyHostToDevice, st);
@@ -310,6 +360,9 @@ extern "C" void _LIB_polyhedron_to_label(const float* dist, const float* points,
   cudaMemcpyAsync(d_faces.p, faces, (size_t)n_faces * 12, cudaMemcpyHostToDevice, st);
   if (verbose >= 1) printf("+++++++++++++++ polyhedra to label (B200) +++++++++++++++ \nn_polys = %d n_rays = %d n_faces = %d nz,ny,nx = %d %d %d\n", n_polys, n_rays, n_faces, nz, ny, nx);
   if (sdb_polyhedron_to_label(d_dist.as<float>(), d_points.as<float>(), d_verts.as<float>(), d_faces.as<int>(), n_polys, n_rays, n_faces,
-                              d_labels.as<int>(), nz, ny, nx, render_mode, use_overlap_label, overlap_label, d_out.as<int>(), (sdb_stream_t)st)) fail("kernel");
-  if (cudaMemcpyAsync(result, d_out.p, (size_t)nvox * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("copy back");
+                              d_labels.as<int>(), nz, ny, nx, render_mode, use_overlap_label, overlap_label, d_out.as<int>(), (sdb_stream_t)st)) return fail("kernel");
+  if (cudaMemcpyAsync(result, d_out.p, (size_t)nvox * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    sdb::set_error("copy back failed"); return fail("copy back");
+  }
+  sdb::set_error("");
 }

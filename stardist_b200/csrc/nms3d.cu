@@ -588,10 +588,17 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   int rc = 0;
   for (int round = 0;; ++round) {
     SDB_LAUNCH(k_reset, 1, 32, 0, st, b_counters.as<unsigned int>());
+    sdb::ProfSpan sp;
+    sdb::profile_begin("nms3d_frontier", st, &sp);
     SDB_LAUNCH(k_frontier, cdiv(n, 256), 256, 0, st, A, round, b_counters.as<unsigned int>());
+    sdb::profile_end("nms3d_frontier", st, &sp);
     for (;;) {
+      sdb::profile_begin("nms3d_pretest", st, &sp);
       SDB_LAUNCH(k_pretest, cdiv(n, 128), 128, 0, st, A, round, b_pairs.as<int2>(), (unsigned int)pair_cap, b_counters.as<unsigned int>());
+      sdb::profile_end("nms3d_pretest", st, &sp);
+      sdb::profile_begin("nms3d_heavy", st, &sp);
       SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap);
+      sdb::profile_end("nms3d_heavy", st, &sp);
       if (cudaMemcpyAsync(h_pin, b_counters.p, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         sdb::set_error(std::string("nms3d: round failed: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; break;
       }
@@ -622,16 +629,26 @@ extern "C" void _LIB_non_maximum_suppression_sparse(const float* scores, const f
                                                     bool* result) {
   (void)scores;     // not used by the reference either (the arrays arrive sorted)
   if (n_polys <= 0) return;
-  auto fail = [&](const char* what) { fprintf(stderr, "stardist_b200: _LIB_non_maximum_suppression_sparse failed: %s: %s\n", what, sdb_last_error()); abort(); };
+  // The reference signature returns void (stardist3d_lib.h:55-65).  A failure must not take the host process down (the
+  // consumer may be a JVM): the result is zeroed (nothing kept), the message is left in sdb_last_error() and one line goes
+  // to stderr; callers that can should use the int-returning sdb_nms3d / check sdb_last_error().
+  auto fail = [&](const char* what) {
+    fprintf(stderr, "stardist_b200: _LIB_non_maximum_suppression_sparse failed: %s: %s\n", what, sdb_last_error());
+    for (int i = 0; i < n_polys; ++i) result[i] = false;
+    cudaGetLastError();
+  };
   cudaStream_t st = 0;
   sdb::DevBuf d_dist, d_points, d_verts, d_faces, d_keep;
   if (d_dist.alloc((size_t)n_polys * n_rays * 4, st) || d_points.alloc((size_t)n_polys * 12, st) || d_verts.alloc((size_t)n_rays * 12, st) ||
-      d_faces.alloc((size_t)n_faces * 12, st) || d_keep.alloc((size_t)n_polys, st)) fail("alloc");
+      d_faces.alloc((size_t)n_faces * 12, st) || d_keep.alloc((size_t)n_polys, st)) { sdb::set_error("device allocation failed"); return fail("alloc"); }
   cudaMemcpyAsync(d_dist.p, dist, (size_t)n_polys * n_rays * 4, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_points.p, points, (size_t)n_polys * 12, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_verts.p, verts, (size_t)n_rays * 12, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(d_faces.p, faces, (size_t)n_faces * 12, cudaMemcpyHostToDevice, st);
   if (sdb_nms3d(d_dist.as<float>(), d_points.as<float>(), d_verts.as<float>(), d_faces.as<int>(), n_polys, n_rays, n_faces,
-                threshold, use_bbox, use_kdtree, verbose, d_keep.as<unsigned char>(), (sdb_stream_t)st)) fail("kernel");
-  if (cudaMemcpyAsync(result, d_keep.p, (size_t)n_polys, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("copy back");
+                threshold, use_bbox, use_kdtree, verbose, d_keep.as<unsigned char>(), (sdb_stream_t)st)) return fail("kernel");
+  if (cudaMemcpyAsync(result, d_keep.p, (size_t)n_polys, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+    sdb::set_error("copy back failed"); return fail("copy back");
+  }
+  sdb::set_error("");
 }

@@ -301,6 +301,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) {
             float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + c0 + j);
             if (P.relu) v = fmaxf(v, 0.f);
+            if (!(fabsf(v) <= 65504.f)) atomicOr(P.error_flag, 0x80000000u);      // fp16 range of the hi plane exceeded (or NaN)
             const __half h = __float2half_rn(v);
             hi[j] = h;
             lo[j] = __float2half_rn(v - __half2float(h));
@@ -573,6 +574,7 @@ k_conv_tc3(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
           for (int j = 0; j < 32; ++j) {
             float v = (__uint_as_float(r[j]) + __uint_as_float(r2[j])) * P.acc_scale + __ldg(P.bias + c0 + j);
             if (P.relu) v = fmaxf(v, 0.f);
+            if (!(fabsf(v) <= 65504.f)) atomicOr(P.error_flag, 0x80000000u);      // fp16 range of the hi plane exceeded (or NaN)
             const __half h = __float2half_rn(v);
             hi[j] = h;
             lo[j] = __float2half_rn(v - __half2float(h));
@@ -949,6 +951,7 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
             for (int j = 0; j < 32; ++j) {
               float v = __uint_as_float(r[j]) * P.acc_scale + __ldg(P.bias + c0 + j);
               if (P.relu) v = fmaxf(v, 0.f);
+              if (!(fabsf(v) <= 65504.f)) atomicOr(P.error_flag, 0x80000000u);
               const __half h = __float2half_rn(v);
               hi[j] = h;
               lo[j] = __float2half_rn(v - __half2float(h));
@@ -993,7 +996,8 @@ k_conv_tc4(const __grid_constant__ CUtensorMap tm_a0_hi, const __grid_constant__
 template <int COUT>
 __global__ void __launch_bounds__(128)
 k_stem_split(const float* __restrict__ in, int N_, int H, int W, int Cin, const float* __restrict__ wgt,
-             const float* __restrict__ bias, int relu, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+             const float* __restrict__ bias, int relu, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+             unsigned int* __restrict__ err) {
   extern __shared__ float sw[];
   for (int e = threadIdx.x; e < 9 * Cin * COUT; e += blockDim.x) sw[e] = wgt[e];
   for (int e = threadIdx.x; e < COUT; e += blockDim.x) sw[9 * Cin * COUT + e] = bias[e];
@@ -1027,6 +1031,7 @@ k_stem_split(const float* __restrict__ in, int N_, int H, int W, int Cin, const 
   for (int o = 0; o < COUT; ++o) {
     float v = acc[o];
     if (relu) v = fmaxf(v, 0.f);
+    if (!(fabsf(v) <= 65504.f)) atomicOr(err, 0x80000000u);
     const __half h = __float2half_rn(v);
     hi[o] = h; lo[o] = __float2half_rn(v - __half2float(h));
   }
@@ -1148,9 +1153,10 @@ __global__ void k_maxpool3d_split(const __half* __restrict__ in_hi, const __half
   }
 }
 // fp32 -> split fp16 planes (output of the CUDA-core stem of the 3-D network)
-__global__ void k_split_f32(const float* __restrict__ in, long long n, __half* __restrict__ hi, __half* __restrict__ lo) {
+__global__ void k_split_f32(const float* __restrict__ in, long long n, __half* __restrict__ hi, __half* __restrict__ lo, unsigned int* __restrict__ err) {
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const float v = in[e];
+    if (!(fabsf(v) <= 65504.f)) atomicOr(err, 0x80000000u);
     const __half h = __float2half_rn(v);
     hi[e] = h; lo[e] = __float2half_rn(v - __half2float(h));
   }
@@ -1511,7 +1517,12 @@ extern "C" int sdb_tc_error_check(sdb_stream_t stream) {
   unsigned int v = 0;
   SDB_CUDA(cudaMemcpyAsync(&v, g_err_flag, 4, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
-  if (v) { SDB_CUDA(cudaMemsetAsync(g_err_flag, 0, 4, st)); sdb::set_error("tcgen05 conv: pipeline wait timed out (code " + std::to_string(v) + ")"); return 1; }
+  if (v) {
+    SDB_CUDA(cudaMemsetAsync(g_err_flag, 0, 4, st));
+    if (v & 0x7fffffffu) { sdb::set_error("tcgen05 conv: pipeline wait timed out (code " + std::to_string(v & 0x7fffffffu) + ")"); return 1; }
+    sdb::set_error("tcgen05 conv: fp16 overflow -- an activation exceeded 65504 (or is NaN) in the split-fp16 representation; normalise the input or use the fp32 CUDA-core path");
+    return 2;
+  }
   return 0;
 }
 
@@ -1533,10 +1544,11 @@ extern "C" int sdb_stem_split(const float* d_in, int n, int h, int w, int cin, c
                               void* out_hi, void* out_lo, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (cin > 4 || (cout != 32 && cout != 64)) { sdb::set_error("stem_split: cin <= 4 and cout in {32,64}"); return 1; }
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
   const size_t smem = (size_t)(9 * cin * cout + cout) * sizeof(float);
   const long long npix = (long long)n * h * w;
-  if (cout == 32) SDB_LAUNCH((k_stem_split<32>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_w, d_b, relu, (__half*)out_hi, (__half*)out_lo);
-  else SDB_LAUNCH((k_stem_split<64>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_w, d_b, relu, (__half*)out_hi, (__half*)out_lo);
+  if (cout == 32) SDB_LAUNCH((k_stem_split<32>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_w, d_b, relu, (__half*)out_hi, (__half*)out_lo, g_err_flag);
+  else SDB_LAUNCH((k_stem_split<64>), cdiv(npix, 128), 128, smem, st, d_in, n, h, w, cin, d_w, d_b, relu, (__half*)out_hi, (__half*)out_lo, g_err_flag);
   return 0;
 }
 
@@ -1560,8 +1572,9 @@ extern "C" int sdb_maxpool3d_split(const void* in_hi, const void* in_lo, int d, 
 }
 extern "C" int sdb_split_f32(const float* d_in, long long n, void* out_hi, void* out_lo, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (!g_err_flag) { SDB_CUDA(cudaMalloc(&g_err_flag, 4)); SDB_CUDA(cudaMemset(g_err_flag, 0, 4)); }
   if (n <= 0) return 0;
-  SDB_LAUNCH(k_split_f32, (int)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, st, d_in, n, (__half*)out_hi, (__half*)out_lo);
+  SDB_LAUNCH(k_split_f32, (int)std::min<long long>(cdiv(n, 256), 148 * 32), 256, 0, st, d_in, n, (__half*)out_hi, (__half*)out_lo, g_err_flag);
   return 0;
 }
 

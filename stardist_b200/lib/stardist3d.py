@@ -24,6 +24,13 @@ def _chk(a, dtype, ndim, name):
     return np.ascontiguousarray(a)
 
 
+def _raise_on_error(lib):
+    """the reference-signature entry points return void: a failure zeroes the result and leaves its message behind"""
+    msg = lib.sdb_last_error()
+    if msg:
+        raise L.StarDistB200Error(msg.decode("utf-8", "replace"))
+
+
 def c_non_max_suppression_inds(dist, points, verts, faces, scores, use_bbox, use_kdtree, verbose, thresh):
     dist = _chk(dist, np.float32, 2, "dist"); points = _chk(points, np.float32, 2, "points")
     verts = _chk(verts, np.float32, 2, "verts"); faces = _chk(faces, np.int32, 2, "faces")
@@ -31,6 +38,8 @@ def c_non_max_suppression_inds(dist, points, verts, faces, scores, use_bbox, use
     n, R = dist.shape
     if points.shape != (n, 3) or verts.shape != (R, 3) or faces.shape[1] != 3 or len(scores) != n:
         raise ValueError("inconsistent shapes")
+    if R > 256 or len(faces) > 512 or R < 4:
+        raise ValueError("stardist_b200: between 4 and 256 rays and at most 512 faces are supported (got %d / %d)" % (R, len(faces)))
     lib = L.require_cuda()
     result = np.zeros(n, np.bool_)
     f = lib._LIB_non_maximum_suppression_sparse
@@ -39,6 +48,7 @@ def c_non_max_suppression_inds(dist, points, verts, faces, scores, use_bbox, use
     if n > 0:
         f(L.ptr(scores), L.ptr(dist), L.ptr(points), n, R, len(faces), L.ptr(verts), L.ptr(faces), float(thresh),
           int(use_bbox), int(use_kdtree), int(verbose), L.ptr(result))
+        _raise_on_error(lib)
     return result
 
 
@@ -48,10 +58,8 @@ def c_polyhedron_to_label(dist, points, verts, faces, labels, render_mode, verbo
     labels = _chk(labels, np.int32, 1, "labels")
     n, R = dist.shape
     nz, ny, nx = (int(s) for s in shape)
-    if np.any(labels == 0):
-        raise ValueError("labels must be non-zero (0 is the background)")
-    if int(use_overlap_label) and int(overlap_label) == 0:
-        raise ValueError("overlap_label == 0 is not supported")
+    if R > 256 or len(faces) > 512:      # static shared-memory limits of the kernels (the reference has none)
+        raise ValueError("stardist_b200: at most 256 rays / 512 faces are supported (got %d / %d)" % (R, len(faces)))
     lib = L.require_cuda()
     result = np.zeros((nz, ny, nx), np.int32)
     f = lib._LIB_polyhedron_to_label
@@ -59,4 +67,5 @@ def c_polyhedron_to_label(dist, points, verts, faces, labels, render_mode, verbo
     f.argtypes = [_P, _P, _P, _P] + [ctypes.c_int] * 3 + [_P] + [ctypes.c_int] * 7 + [_P]
     f(L.ptr(dist), L.ptr(points), L.ptr(verts), L.ptr(faces), n, R, len(faces), L.ptr(labels), nz, ny, nx,
       int(render_mode), int(verbose), int(use_overlap_label), int(overlap_label), L.ptr(result))
+    _raise_on_error(lib)
     return result

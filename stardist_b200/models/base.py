@@ -289,9 +289,10 @@ class StarDistBase:
         self._stats['h2d_bytes'] = self._stats.get('h2d_bytes', 0) + stage.numel() * 4
         return stage.to(self.net.device, non_blocking=True)
 
-    def _to_host(self, tensors):
+    def _to_host(self, tensors, copy_threads=False):
         """device tensors -> numpy arrays: asynchronous copies into persistent pinned buffers, ONE stream
-        synchronisation for all of them, then a host copy into fresh arrays; returns (arrays, bytes)"""
+        synchronisation for all of them, then a host copy into fresh arrays (copy_threads: through torch's
+        multi-threaded copy, for the large label maps of predict_instances_big); returns (arrays, bytes)"""
         pinned = []
         for i, t in enumerate(tensors):
             if t is None:
@@ -300,7 +301,13 @@ class StarDistBase:
             p.copy_(t, non_blocking=True)
             pinned.append(p)
         torch.cuda.current_stream().synchronize()
-        return [None if p is None else p.numpy().copy() for p in pinned], sum(0 if p is None else p.numel() * p.element_size() for p in pinned)
+        def host_copy(p):
+            if copy_threads and p.numel() >= (1 << 22):
+                out = torch.empty(p.shape, dtype=p.dtype)
+                out.copy_(p)
+                return out.numpy()
+            return p.numpy().copy()
+        return [None if p is None else host_copy(p) for p in pinned], sum(0 if p is None else p.numel() * p.element_size() for p in pinned)
 
     def predict_direct_device(self, x_dev, n_tiles=None):
         """x_dev [1,...,C] float32 device -> (prob [...], dist [..., R]) device tensors (padded, /grid).
@@ -413,6 +420,7 @@ class StarDistBase:
                                       L.iarr([s[1] for s in bs]), float(np.float32(prob_thresh)), L.ptr(sidx), L.ptr(sprob),
                                       npix, ctypes.byref(cnt), L.stream_ptr()))
         n = int(cnt.value)
+        self._last_n_cand = n
         sidx, sprob = sidx[:n], sprob[:n]
         dist_s = torch.empty((n, R), dtype=torch.float32, device=prob_d.device)
         pts_f = torch.empty((n, nd), dtype=torch.float32, device=prob_d.device)
@@ -444,7 +452,7 @@ class StarDistBase:
     # ------------------------------------------------------------------ predict_instances
     def predict_instances(self, img, axes=None, normalizer=None, sparse=True, prob_thresh=None, nms_thresh=None,
                           scale=None, n_tiles=None, show_tile_progress=True, verbose=False, return_labels=True,
-                          predict_kwargs=None, nms_kwargs=None, overlap_label=None, return_predict=False):
+                          predict_kwargs=None, nms_kwargs=None, overlap_label=None, return_predict=False, _device_labels=False):
         """Predict instance segmentation from input image (base.py:645-790).
 
         Returns (labels, dict(coord|dist, points, prob, ...)) [, (prob, dist) when return_predict]."""
@@ -476,6 +484,8 @@ class StarDistBase:
         scale_dict = None if scale is None else dict(zip(_axes, scale))
         if sparse:
             cand = self._predict_sparse_device(img, prob_thresh=prob_thresh, axes=axes, normalizer=normalizer, n_tiles=n_tiles)
+            if _device_labels:
+                nms_kwargs = dict(nms_kwargs, device_labels=True)
             res = self._instances_from_candidates_device(_shape_inst, cand, nms_thresh=nms_thresh, scale=scale_dict,
                                                          return_labels=return_labels, overlap_label=overlap_label, **nms_kwargs)
             return res
@@ -545,6 +555,22 @@ class StarDistBase:
             return labels, polys
 
         rank, world = parallel_big.rank_world(group)
+        if StarDistBase._big_on_device(img, axes, shape_out, want_labels, kwargs, group) and hasattr(self, '_process_block_device'):
+            # device-resident pipeline: label tiles stay in HBM from the painting kernel to the assembled map
+            def process_device(block):
+                return self._process_block_device(block, img, axes, axes_out, kwargs)
+            labels_d, polys_all = parallel_big.run_sharded_device(blocks, process_device, shape_out, axes_out, want_labels, group=group)
+            if rank != 0:
+                return None, None
+            if not want_labels:
+                return None, polys_all
+            (lab_np,), nbytes = self._to_host([labels_d], copy_threads=True)
+            self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + nbytes
+            if labels_out is None:
+                labels_out = lab_np if lab_np.dtype == np.dtype(labels_out_dtype) else lab_np.astype(labels_out_dtype)
+            else:
+                labels_out[...] = lab_np
+            return labels_out, polys_all
         if world > 1:
             return parallel_big.run_sharded(blocks, process, shape_out, axes_out, labels_out if want_labels else False,
                                             labels_out_dtype, group=group)
@@ -563,6 +589,61 @@ class StarDistBase:
             del labels
         polys_all = {k: (np.concatenate(v) if k in OBJECT_KEYS else v[0]) for k, v in polys_all.items()}
         return (labels_out if want_labels else None), polys_all
+
+    @staticmethod
+    def _big_on_device(img, axes, shape_out, want_labels, kwargs, group):
+        """the device-resident block pipeline applies to the default (sparse) predict_instances arguments, a CUDA device,
+        a NCCL (or no) process group and an assembled label map that fits next to the per-block working set"""
+        import os
+        if os.environ.get("STARDIST_B200_BIG", "device") != "device" or not torch.cuda.is_available():
+            return False
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_backend(group) != "nccl":
+            return False
+        if kwargs.get('sparse', True) is False or kwargs.get('scale') is not None or kwargs.get('return_labels') is False:
+            return False
+        free, _ = torch.cuda.mem_get_info()
+        return int(np.prod(shape_out)) * 4 * 2 < 0.5 * free
+
+    def _process_block_device(self, block, img, axes, axes_out, kwargs):
+        """One block of predict_instances_big without leaving HBM: predict_instances (label image kept on the device) ->
+        crop_context -> filter_objects (per-label bounding boxes by sdb_label_bbox, the responsibility rule of
+        big.py:89-122 vectorised on the small box table, foreign objects removed and ids compacted by sdb_label_remap).
+        Returns (tile int32 device tensor with ids 1..n_kept in ascending order of the original ids, polys dict (host,
+        global coordinates), n_kept) -- the same objects BlockND.filter_objects + relabel_sequential keep."""
+        import ctypes
+        from ..big import OBJECT_KEYS, COORD_KEYS
+        lib = L.require_cuda()
+        lab_d, polys = self.predict_instances(block.read(img, axes=axes), _device_labels=True, **kwargs)
+        nd = lab_d.dim()
+        tile = lab_d[block.slice_crop_context(axes_out)].contiguous()
+        nk = len(polys['prob'])
+        dev = tile.device
+        bbox_d = torch.empty((nk + 1) * 6 + 1, dtype=torch.int32, device=dev)
+        L.check(lib.sdb_label_bbox(L.ptr(tile), nd, L.iarr(tile.shape), nk, L.ptr(bbox_d), L.ptr(bbox_d[(nk + 1) * 6:]), L.stream_ptr()))
+        bb = bbox_d.cpu().numpy()
+        if bb[-1]:
+            raise L.StarDistB200Error("predict_instances_big: label outside [0, n_objects] in a block")
+        bb = bb[:-1].reshape(nk + 1, 6)[1:]
+        bmin, bmax = bb[:, 3 - nd:3], bb[:, 6 - nd:6] + 1
+        present = bmax[:, -1] > bmin[:, -1]
+        ids = np.nonzero(present)[0]                       # object index = label - 1
+        mine, invisible = block.responsible_many(bmin[ids], bmax[ids], axes_out)
+        if invisible.any():                                # big.py:377-381
+            i = int(np.nonzero(invisible)[0][0])
+            shape_object = tuple(int(b - a) for a, b in zip(bmin[ids[i]], bmax[ids[i]]))
+            shape_min_overlap = tuple(t.min_overlap for t in block.blocks_for_axes(axes_out))
+            raise RuntimeError(f"Found object of shape {shape_object}, which violates the assumption of being smaller than 'min_overlap' {shape_min_overlap}. Increase 'min_overlap' to avoid this problem.")
+        ind = ids[mine]
+        lut = np.zeros(nk + 1, np.int32)
+        lut[ind + 1] = np.arange(1, len(ind) + 1, dtype=np.int32)
+        lut_d = torch.from_numpy(lut).to(dev, non_blocking=True)
+        L.check(lib.sdb_label_remap(L.ptr(tile), tile.numel(), L.ptr(lut_d), L.stream_ptr()))
+        out = {k: (v[ind] if k in OBJECT_KEYS else v) for k, v in polys.items()}
+        for k in COORD_KEYS:
+            if k in out:
+                out[k] = block.translate_coordinates(out[k], axes=axes_out)
+        return tile, out, len(ind)
 
     # ------------------------------------------------------------------ misc
     def _compute_receptive_field(self, img_size=None):

@@ -79,9 +79,10 @@ class StarDist2D(StarDistBase):
 
     # ------------------------------------------------------------------ device-resident (sparse) path
     def _instances_from_candidates_device(self, img_shape, cand, nms_thresh=None, scale=None, return_labels=True,
-                                          overlap_label=None, use_bbox=True, use_kdtree=True, verbose=False):
+                                          overlap_label=None, use_bbox=True, use_kdtree=True, verbose=False, device_labels=False):
         """Same result as _instances_from_prediction(points=...) but on tensors that stay in HBM:
-        NMS -> survivors -> dist_to_coord -> label painting; one D2H of the results at the end."""
+        NMS -> survivors -> dist_to_coord -> label painting; one D2H of the results at the end.
+        device_labels: return the label image as a device tensor (predict_instances_big keeps it in HBM)."""
         lib = L.require_cuda()
         if nms_thresh is None: nms_thresh = self.thresholds.nms
         if overlap_label is not None: raise NotImplementedError("overlap_label not supported for 2D yet!")
@@ -122,7 +123,9 @@ class StarDist2D(StarDistBase):
         else:
             lab_d = None
         pc_d = cand['prob_class'].index_select(0, sel) if 'prob_class' in cand else None
-        (labels, probi, coord, points, prob_class), nbytes = self._to_host([lab_d, probi_d, coord_d, pts_d, pc_d])
+        (labels, probi, coord, points, prob_class), nbytes = self._to_host([None if device_labels else lab_d, probi_d, coord_d, pts_d, pc_d])
+        if device_labels:
+            labels = lab_d
         if scale is None:
             points = points.astype(np.int64)
         self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + nbytes

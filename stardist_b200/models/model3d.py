@@ -96,7 +96,7 @@ class StarDist3D(StarDistBase):
 
     # ------------------------------------------------------------------ device-resident (sparse) path
     def _instances_from_candidates_device(self, img_shape, cand, nms_thresh=None, scale=None, return_labels=True,
-                                          overlap_label=None, use_bbox=True, use_kdtree=True, verbose=False):
+                                          overlap_label=None, use_bbox=True, use_kdtree=True, verbose=False, device_labels=False):
         lib = L.require_cuda()
         if nms_thresh is None: nms_thresh = self.thresholds.nms
         rays = rays_from_json(self.config.rays_json)
@@ -132,8 +132,6 @@ class StarDist3D(StarDistBase):
                 # survivors arrive in descending (stable) score order == painting order (geom3d.py:176-180)
                 lab_ids = torch.arange(1, nk + 1, dtype=torch.int32, device=dev)
                 lab_d = torch.empty(tuple(int(s) for s in img_shape), dtype=torch.int32, device=dev)
-                if overlap_label is not None and int(overlap_label) == 0:
-                    raise ValueError("overlap_label == 0 is not supported")
                 L.check(lib.sdb_polyhedron_to_label(L.ptr(disti_d), L.ptr(pts_d), L.ptr(verts_d), L.ptr(faces_d), nk, R, int(faces_d.shape[0]),
                                                    L.ptr(lab_ids), int(img_shape[0]), int(img_shape[1]), int(img_shape[2]), 0,
                                                    1 if overlap_label is not None else 0, 0 if overlap_label is None else int(overlap_label),
@@ -147,10 +145,12 @@ class StarDist3D(StarDistBase):
                     lab_host = lab_d
                 else:
                     labels = self._finish_labels(lab_d.cpu().numpy(), overlap_label)
-        (lab_np, disti, probi), _ = self._to_host([lab_host, disti_d, probi_d])
+        (lab_np, disti, probi), _ = self._to_host([None if device_labels else lab_host, disti_d, probi_d])
         if lab_np is not None:
             labels = lab_np
-        self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + disti.nbytes + points.nbytes + probi.nbytes + (0 if labels is None else labels.nbytes)
+        if device_labels:
+            labels = lab_host if lab_host is not None else (None if labels is None else torch.from_numpy(np.ascontiguousarray(labels, np.int32)).to(dev))
+        self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + disti.nbytes + points.nbytes + probi.nbytes + (0 if (labels is None or device_labels) else labels.nbytes)
         res_dict = dict(dist=disti, points=points, prob=probi, rays=rays, rays_vertices=rays.vertices, rays_faces=rays.faces)
         if 'prob_class' in cand:                            # model3d.py:663-667
             prob_class = cand['prob_class'].index_select(0, sel).cpu().numpy()

@@ -271,10 +271,13 @@ class UNetDevice2DTC:
         ok_first = first['cin'] <= 4 and first['cout'] in (32, 64)
         rest = [l for l in unet_layers(config) if l['kind'] == 'conv'][1:]
         ok_rest = all(l['cin'] % 32 == 0 and l['cout'] in (32, 64, 128, 256) for l in rest)
-        return (ok_first and ok_rest and config.net_conv_after_unet == 128 and not config.unet_batch_norm
+        # every pooling layer -- incl. the grid stem's, which follows config.grid and may be (2,1) / (1,2) -- must be 2x2:
+        # sdb_maxpool_split pools both axes (anisotropic grids run on the generic CUDA-core executor)
+        ok_pool = all(tuple(l['pool']) == (2, 2) for l in unet_layers(config) if l['kind'] == 'pool')
+        return (ok_first and ok_rest and ok_pool and config.net_conv_after_unet == 128 and not config.unet_batch_norm
                 and tuple(config.unet_kernel_size) == (3, 3) and tuple(config.unet_pool) == (2, 2))
 
-    def forward(self, x):
+    def _forward_tc(self, x):
         lib = L.load()
         assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous()
         st = L.stream_ptr()
@@ -402,7 +405,7 @@ class UNetDevice3DTC:
                 and config.net_conv_after_unet % 64 == 0 and config.net_conv_after_unet > 0 and config.n_rays + 1 <= 144
                 and config.unet_activation in ('relu', 'linear') and config.unet_last_activation in ('relu', 'linear'))
 
-    def forward(self, x):
+    def _forward_tc(self, x):
         lib = L.load()
         assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.dim() == 5
         if x.shape[0] != 1:
@@ -467,3 +470,25 @@ class UNetDevice3DTC:
             self.prob_class = self._simt._class_branch(b32)
         return prob, dist
 
+
+def _forward_guarded(self, x):
+    """tensor-core forward pass; if an activation left the fp16 range of the split representation (|v| > 65504: raw
+    16-bit images, un-normalised floats -- the reference only warns about those, base.py:414) the pass is repeated on the
+    exact-fp32 CUDA-core executor, which has float32's range like the reference network"""
+    try:
+        return self._forward_tc(x)
+    except L.StarDistB200Error as e:
+        if 'fp16 overflow' not in str(e):
+            raise
+    import warnings
+    warnings.warn("stardist_b200: activations exceed the fp16 range of the tensor-core path (un-normalised input?); "
+                  "running this prediction on the fp32 CUDA-core kernels instead")
+    if getattr(self, '_fp32', None) is None:
+        self._fp32 = UNetDeviceND(self.config, {k: (v['k'].cpu().numpy(), v['b'].cpu().numpy()) for k, v in self.w.items()})
+    out = self._fp32.forward(x)
+    self.prob_class = self._fp32.prob_class
+    return out
+
+
+UNetDevice2DTC.forward = _forward_guarded
+UNetDevice3DTC.forward = _forward_guarded

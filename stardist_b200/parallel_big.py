@@ -114,3 +114,93 @@ def run_sharded(blocks, process, shape_out, axes_out, labels_out, labels_out_dty
         return None, None
     polys_all = {k: (np.concatenate(v) if k in OBJECT_KEYS else v[0]) for k, v in polys_all.items()}
     return (labels_out if want_labels else None), polys_all
+
+
+def block_offsets(counts):
+    """label offsets of base.py:959,972: 1 + exclusive scan of the per-block object counts in block-id order"""
+    counts = np.asarray(counts, dtype=np.int64)
+    return 1 + np.concatenate([[0], np.cumsum(counts)[:-1]]) if len(counts) else np.zeros(0, np.int64)
+
+
+def run_sharded_device(blocks, process_device, shape_out, axes_out, want_labels=True, group=None):
+    """Device-resident assembly of predict_instances_big.
+
+    process_device(block) -> (tile int32 CUDA tensor of the block's write region with ids 1..n_kept, polys dict, n_kept).
+    Rank r owns the blocks r, r+W, ... (no data-path collective while they are processed).  Then
+      * all-reduce(SUM) of the per-block object counts -> exclusive scan = label offsets (base.py:959,972),
+      * the owners' tiles travel device-to-device to rank 0 (batched NCCL send/recv over NVLink, straight out of and into
+        HBM; no host staging), rank 0 scatters every tile into the device-resident global map in block-id order with the
+        offset folded in (sdb_label_write; later blocks win inside overlaps, big.py:319-326),
+      * the polygon dicts (a few hundred bytes per object) are gathered with gather_object and concatenated in id order.
+    Returns (labels int32 CUDA tensor | None, polys_all) on rank 0, (None, None) elsewhere.  world == 1: same code
+    path without the collectives."""
+    import ctypes
+    from . import _lib as L
+    lib = L.require_cuda()
+    rank, world = rank_world(group)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    nb = len(blocks)
+    nd = len(shape_out)
+    mine = {}
+    counts = torch.zeros(nb, dtype=torch.int64)
+    glob = None
+    if rank == 0 and want_labels:
+        glob = torch.zeros(tuple(int(s) for s in shape_out), dtype=torch.int32, device=dev)
+    offsets_known = world == 1
+    running = 1
+    for b in blocks:
+        if b.id % world != rank:
+            continue
+        tile, polys, n_kept = process_device(b)
+        counts[b.id] = n_kept
+        if offsets_known:
+            # single process: the running offset is known, write at once and drop the tile
+            if want_labels:
+                origin = [s.start for s in b.slice_write(axes_out)]
+                L.check(lib.sdb_label_write(L.ptr(tile), nd, L.iarr(tile.shape), running - 1, L.ptr(glob), L.iarr(shape_out),
+                                           L.iarr(origin), L.stream_ptr()))
+            running += n_kept
+            mine[b.id] = (None, polys)
+        else:
+            mine[b.id] = (tile if want_labels else None, polys)
+    if world > 1:
+        counts_d = counts.to(dev)
+        dist.all_reduce(counts_d, op=dist.ReduceOp.SUM, group=group)
+        counts = counts_d.cpu()
+    offsets = block_offsets(counts.numpy())
+    if world > 1 and want_labels:
+        ops, remote = [], {}
+        if rank == 0:
+            for b in blocks:
+                owner = b.id % world
+                if owner != 0:
+                    shp = tuple(s.stop - s.start for s in b.slice_write(axes_out))
+                    remote[b.id] = torch.empty(shp, dtype=torch.int32, device=dev)
+                    ops.append(dist.P2POp(dist.irecv, remote[b.id], owner, group=group))
+        else:
+            for bid in sorted(mine):
+                ops.append(dist.P2POp(dist.isend, mine[bid][0], 0, group=group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if rank == 0:
+            for b in blocks:
+                tile = mine[b.id][0] if b.id % world == 0 else remote[b.id]
+                origin = [s.start for s in b.slice_write(axes_out)]
+                L.check(lib.sdb_label_write(L.ptr(tile), nd, L.iarr(tile.shape), int(offsets[b.id]) - 1, L.ptr(glob), L.iarr(shape_out),
+                                           L.iarr(origin), L.stream_ptr()))
+    polys_by_block = {bid: p for bid, (_, p) in mine.items()}
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(polys_by_block, gathered, dst=0, group=group)
+        if rank != 0:
+            return None, None
+        polys_by_block = {}
+        for d in gathered:
+            polys_by_block.update(d)
+    polys_all = {}
+    for b in blocks:
+        for k, v in polys_by_block[b.id].items():
+            polys_all.setdefault(k, []).append(v)
+    polys_all = {k: (np.concatenate(v) if k in OBJECT_KEYS else v[0]) for k, v in polys_all.items()}
+    return glob, polys_all

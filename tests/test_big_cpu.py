@@ -188,3 +188,30 @@ def test_predict_instances_big_bookkeeping_equals_the_reference(golden_dir):
         for k in ("points", "prob", "dist", "rays_faces"):
             assert np.array_equal(polys[k], g["big/%d/%s" % (ci, k)]), (ci, k)
         assert set(polys) == {"points", "prob", "dist", "rays_faces"}
+
+
+def test_vectorised_responsibility_equals_scalar_rule():
+    """BlockND.responsible_many (used by the device block pipeline) == all(t.is_responsible(...)) incl. the
+    NotFullyVisible cases and the short-circuit order over the axes (big.py:89-122, :340-345)"""
+    import numpy as np
+    from stardist_b200.big import BlockND, NotFullyVisible
+    rng = np.random.default_rng(0)
+    n_checked = 0
+    for shape, axes, bs, mo, ctx in [((700, 640), 'YX', 256, 48, 16), ((150, 120, 130), 'ZYX', (64, 48, 56), (16, 8, 16), (8, 8, 4))]:
+        for b in BlockND.cover(shape, axes, bs, mo, ctx, 1):
+            wshape = [s.stop - s.start for s in b.slice_crop_context()]
+            n = 400
+            lo = np.stack([rng.integers(0, w, n) for w in wshape], 1)
+            lo[rng.random(lo.shape) < 0.3] = 0
+            hi = np.stack([np.minimum(w, lo[:, k] + 1 + rng.integers(0, 40, n)) for k, w in enumerate(wshape)], 1)
+            hi = np.where(rng.random(hi.shape) < 0.25, np.array(wshape)[None], hi)
+            mine, inv = b.responsible_many(lo, hi)
+            for i in range(n):
+                sl = tuple(slice(int(a), int(c)) for a, c in zip(lo[i], hi[i]))
+                try:
+                    r, e = b.is_responsible(sl), False
+                except NotFullyVisible:
+                    r, e = False, True
+                assert e == inv[i] and (e or r == mine[i])
+                n_checked += 1
+    assert n_checked > 10000

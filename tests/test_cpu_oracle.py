@@ -7,6 +7,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases
 from oracle import ref_ext, geom2d_np, nms_np
 
@@ -579,3 +580,34 @@ def test_instances_from_prediction_glue_equals_reference_classes(golden_dir, mon
     labels, res = sd.StarDist3D._instances_from_prediction(fake3, shape, prob[mask], dist[mask], points=pts, nms_thresh=0.2, scale=dict(Z=1., Y=.5, X=2.))
     assert np.array_equal(labels, g["3d/sparse_scale/labels"])
     same(res, "3d/sparse_scale/", ("dist", "points", "prob", "rays_vertices"))
+
+
+def test_render_rule_differs_from_reference_only_on_exact_hull_facets():
+    """DESIGN 5 (3-D labels): the product's rule kernel || polyhedron (host build of k_paint3d's rule) vs the reference's
+    kernel || (hull && polyhedron) on lattice-aligned polyhedra: every differing voxel lies EXACTLY (rational arithmetic,
+    tests/hullcheck.py) on a facet of the convex hull and is labelled by the product only -- no tolerance"""
+    import ctypes, hullcheck
+    from oracle import pipeline3d, ref_ext
+    if not ref_ext.available():
+        pytest.skip("oracle/_ref not built")
+    so = os.path.join(ROOT, "tests", "hostcheck", "_build", "libhostcheck.so")
+    if not os.path.exists(so):
+        pytest.skip("hostcheck library not built")
+    hc = ctypes.CDLL(so)
+    hc.hc_paint3d.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int] * 5 + [ctypes.c_void_p]
+    rng = np.random.default_rng(1)
+    shape = (40, 44, 48)
+    n_diff = 0
+    for gen in (lambda n: np.full(n, rng.integers(4, 14)).astype(np.float32), lambda n: rng.integers(4, 14, n).astype(np.float32),
+                lambda n: (rng.integers(8, 28, n) / 2).astype(np.float32)):
+        for n_rays, aniso in ((32, None), (64, (2, 1, 1)), (96, None)):
+            rays = cases.rays_golden_spiral(n_rays, aniso)
+            v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
+            for _ in range(3):
+                dist = gen(n_rays); point = np.array([rng.integers(14, 26), rng.integers(14, 30), rng.integers(14, 34)])
+                d = np.ascontiguousarray(dist, np.float32); c = np.ascontiguousarray(point, np.float32); ours = np.zeros(shape, np.uint8)
+                hc.hc_paint3d(d.ctypes.data, c.ctypes.data, v.ctypes.data, f.ctypes.data, len(v), len(f), shape[0], shape[1], shape[2], ours.ctypes.data)
+                ref = pipeline3d.polyhedron_to_label(dist[None], point[None], rays, shape, np.ones(1))
+                n_diff += hullcheck.assert_only_exact_hull_boundary_voxels_differ((ours > 0).astype(np.int32), (ref > 0).astype(np.int32), dist[None],
+                                                                                  point[None].astype(np.float32), rays.vertices)
+    assert n_diff > 0        # the lattice-aligned families do hit the caveat

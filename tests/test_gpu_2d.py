@@ -286,3 +286,46 @@ def test_cli_predict_on_model_folder(sd, tmp_path):
     assert np.array_equal(labels, ref_labels) and labels.max() == len(res['prob'])
     with zipfile.ZipFile(str(tmp_path / "out" / "nuclei.stardist.rois.zip")) as z:
         assert len(z.namelist()) == len(res['prob'])
+
+
+@pytest.mark.parametrize("grid", [(2, 1), (1, 2), (4, 2)])
+def test_anisotropic_grid_vs_oracle(sd, grid):
+    """grids with different factors per axis (valid in the reference: the grid stem pools (2,1) / (1,2), model2d.py:316-325)
+    must not run on the 2x2-only tensor-core executor: maps equal the torch restatement, instances equal the oracle's"""
+    import torch
+    from stardist_b200.models.unet_device import UNetDevice2DTC
+    cfg = sd.Config2D(n_rays=32, grid=grid)
+    assert not UNetDevice2DTC.supported(cfg)
+    model = sd.StarDist2D(cfg, name=None, basedir=None)
+    rng = np.random.default_rng(5)
+    img = rng.uniform(0, 1, (96, 128)).astype(np.float32)
+    prob, dist = model.net.forward(torch.from_numpy(img[None, ..., None]).cuda())
+    rp, rd = unet_torch.forward(cfg, model.weights, img[None, ..., None])
+    assert tuple(prob.shape) == rp.shape == (1, 96 // grid[0], 128 // grid[1])
+    assert np.max(np.abs(prob.cpu().numpy() - rp)) <= 1e-5 and np.max(np.abs(dist.cpu().numpy() - rd)) <= 1e-5 * max(1e-3, np.max(np.abs(rd))) + 1e-7
+    pthr = pipeline2d.quantile_prob_thresh(model, img, 0.9)
+    labels, res = model.predict_instances(img, prob_thresh=pthr, nms_thresh=0.3)
+    ref_labels, ref = pipeline2d.predict_instances(cfg, model.weights, img, pthr, 0.3, cand_from=model)
+    assert len(res['prob']) > 0 and np.array_equal(res['points'], ref['points']) and np.array_equal(labels, ref_labels)
+
+
+def test_unnormalised_uint16_input_does_not_overflow_silently(sd):
+    """raw 16-bit input drives activations past the fp16 range of the tensor-core representation; the pass must be
+    repeated on the fp32 kernels (with a warning) and give the finite maps of the fp32 reference network"""
+    import torch, warnings
+    cfg = sd.Config2D(n_rays=32)
+    model = sd.StarDist2D(cfg, name=None, basedir=None)
+    rng = np.random.default_rng(6)
+    img = rng.integers(0, 65535, (64, 96)).astype(np.uint16)
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        prob, dist = model.predict(img)
+    assert any("fp16 range" in str(w.message) for w in wlist)
+    rp, rd = unet_torch.forward(cfg, model.weights, img.astype(np.float32)[None, ..., None])
+    assert np.isfinite(dist).all() and np.isfinite(prob).all()
+    assert np.max(np.abs(dist - np.maximum(1e-3, rd[0]))) <= 1e-4 * np.max(np.abs(rd))
+    # a normalised image afterwards runs on the tensor cores again, no warning
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        model.predict(rng.uniform(0, 1, (64, 96)).astype(np.float32))
+    assert not any("fp16 range" in str(w.message) for w in wlist)

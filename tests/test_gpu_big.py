@@ -33,3 +33,74 @@ def test_predict_instances_big_equals_whole_2d():
         i = np.lexsort(tuple(p['points'].T)); return p['points'][i], p['prob'][i], p['coord'][i]
     for x, y in zip(srt(polys), srt(pb)):
         assert np.allclose(x, y, atol=1e-2)
+
+
+def test_device_block_pipeline_equals_host_pipeline_2d(monkeypatch):
+    """the device-resident block pipeline (sdb_label_bbox / remap / write) reproduces the host pipeline
+    (BlockND.filter_objects + relabel_sequential + BlockND.write, pinned against the reference's big.py) bit for bit"""
+    import stardist_b200 as sd, bench_data
+    cfg = sd.Config2D(n_rays=32)
+    model = sd.StarDist2D(cfg, name=None, basedir=None, weights=bench_data.bench_weights_2d(cfg))
+    img, _ = bench_data.synthetic_image((1024, 896), seed=5)
+    kw = dict(axes='YX', block_size=384, min_overlap=64, context=48, show_progress=False)
+    monkeypatch.setenv("STARDIST_B200_BIG", "host")
+    lh, ph = model.predict_instances_big(img, **kw)
+    monkeypatch.setenv("STARDIST_B200_BIG", "device")
+    ld, pd_ = model.predict_instances_big(img, **kw)
+    assert ld.dtype == lh.dtype and np.array_equal(ld, lh)
+    assert set(pd_) == set(ph)
+    for k in ph:
+        assert np.array_equal(np.asarray(pd_[k]), np.asarray(ph[k])), k
+    # labels_out given by the caller
+    out = np.zeros(img.shape, np.int32)
+    l2, _ = model.predict_instances_big(img, labels_out=out, **kw)
+    assert l2 is out and np.array_equal(out, lh)
+
+
+def test_device_block_pipeline_equals_host_pipeline_3d(monkeypatch):
+    import stardist_b200 as sd, bench_data
+    cfg = bench_data.bench_config_3d(96)
+    model = sd.StarDist3D(cfg, name=None, basedir=None, weights=bench_data.bench_weights_3d(cfg))
+    vol, _ = bench_data.synthetic_volume((64, 128, 128), seed=2, cell=(64, 128, 128))
+    kw = dict(axes='ZYX', block_size=(48, 96, 96), min_overlap=(16, 24, 24), context=(8, 16, 16), show_progress=False,
+              prob_thresh=0.7, nms_thresh=0.3)
+    monkeypatch.setenv("STARDIST_B200_BIG", "host")
+    lh, ph = model.predict_instances_big(vol, **kw)
+    monkeypatch.setenv("STARDIST_B200_BIG", "device")
+    ld, pd_ = model.predict_instances_big(vol, **kw)
+    assert len(ph['prob']) > 20
+    assert np.array_equal(ld, lh)
+    for k in ('prob', 'points', 'dist'):
+        assert np.array_equal(pd_[k], ph[k]), k
+
+
+def test_label_bbox_kernel_equals_find_objects():
+    """sdb_label_bbox == scipy.ndimage.find_objects (== skimage regionprops bbox, big.py:373) incl. absent labels"""
+    import torch
+    from scipy import ndimage as ndi
+    from stardist_b200 import _lib as L
+    lib = L.require_cuda()
+    rng = np.random.default_rng(0)
+    for shape in ((257, 301), (33, 70, 45)):
+        lab = np.zeros(shape, np.int32)
+        nlab = 60
+        for i in range(1, nlab + 1):
+            if i % 7 == 0: continue                        # absent labels
+            c = [rng.integers(0, s) for s in shape]
+            r = [rng.integers(1, 12) for _ in shape]
+            sl = tuple(slice(max(0, a - b), a + b) for a, b in zip(c, r))
+            m = rng.random(lab[sl].shape) < 0.6
+            lab[sl][m] = i
+        t = torch.from_numpy(lab).cuda()
+        bb = torch.empty((nlab + 1) * 6 + 1, dtype=torch.int32, device='cuda')
+        L.check(lib.sdb_label_bbox(L.ptr(t), t.dim(), L.iarr(t.shape), nlab, L.ptr(bb), L.ptr(bb[(nlab + 1) * 6:]), L.stream_ptr()))
+        bb = bb.cpu().numpy()
+        assert bb[-1] == 0
+        bb = bb[:-1].reshape(nlab + 1, 6)
+        nd = len(shape)
+        for i, sl in enumerate(ndi.find_objects(lab, max_label=nlab), 1):
+            lo, hi = bb[i, 3 - nd:3], bb[i, 6 - nd:6]
+            if sl is None:
+                assert (hi < lo).all()
+            else:
+                assert tuple(lo) == tuple(s.start for s in sl) and tuple(hi + 1) == tuple(s.stop for s in sl), (i, lo, hi, sl)
