@@ -247,6 +247,18 @@ int sdb_label_remap(int* d_labels, long long n, const int* d_lut, sdb_stream_t s
 int sdb_label_write(const int* d_tile, int ndim, const int* tile_shape, int add, int* d_dst, const int* dst_shape,
                     const int* origin, sdb_stream_t stream);
 
+/* ---- the steps in front of the network: csbdeep.utils.normalize / PercentileNormalizer and the `scale=` zoom ---- */
+/* exact order statistics of the region [0,valid) of a C-contiguous float32 array: h_out[q] = sorted(region)[ranks[q]], <= 8 ranks */
+int sdb_select_ranks(const float* d_x, int ndim, const int* shape, const int* valid, const long long* ranks, int n_ranks,
+                     float* h_out, sdb_stream_t stream);
+/* in place x = (x - mi) / den in float32 (den = ma - mi + eps computed by the caller in float32), optional clip to [0,1] */
+int sdb_normalize_mi_ma(float* d_x, long long n, float mi, float den, int clip, sdb_stream_t stream);
+/* scipy.ndimage.zoom(x, zoom, order=1) (stardist/models/base.py:735) for ndim 2 / 3; out_shape = round(in_shape * zoom) */
+int sdb_zoom_linear(const float* d_in, int ndim, const int* in_shape, const int* out_shape, float* d_out, sdb_stream_t stream);
+/* numpy.pad(mode='reflect') at the end of each spatial axis of a channels-last array (StarDistPadAndCropResizer.before) */
+int sdb_pad_reflect_end(const float* d_in, int ndim, const int* in_shape, const int* out_shape, int channels, float* d_out,
+                        sdb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

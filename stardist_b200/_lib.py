@@ -83,6 +83,14 @@ def _declare(lib):
     lib.sdb_relabel_sequential.argtypes = [P, c_longlong, c_int, c_int, P, POINTER(c_int), P]
     lib.sdb_relabel_sequential.restype = c_int
     lib.sdb_nms3d.argtypes = [P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_select_ranks.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_longlong), c_int, POINTER(c_float), P]
+    lib.sdb_select_ranks.restype = c_int
+    lib.sdb_normalize_mi_ma.argtypes = [P, c_longlong, c_float, c_float, c_int, P]
+    lib.sdb_normalize_mi_ma.restype = c_int
+    lib.sdb_zoom_linear.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), P, P]
+    lib.sdb_zoom_linear.restype = c_int
+    lib.sdb_pad_reflect_end.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), c_int, P, P]
+    lib.sdb_pad_reflect_end.restype = c_int
     lib.sdb_label_bbox.argtypes = [P, c_int, POINTER(c_int), c_int, P, P, P]
     lib.sdb_label_bbox.restype = c_int
     lib.sdb_label_remap.argtypes = [P, c_longlong, P, P]

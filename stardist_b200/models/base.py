@@ -57,6 +57,16 @@ class StarDistPadAndCropResizer:
         self.grid = grid
         self.kwargs = kwargs
 
+    def plan(self, shape, axes, axes_div_by):
+        """the bookkeeping of before() for an array of the given shape, without touching data (the device path pads in HBM)"""
+        assert all(a % g == 0 for g, a in zip((self.grid.get(a, 1) for a in axes), axes_div_by))
+        axes = axes_check_and_normalize(axes, len(shape))
+        self.pad = {a: (0, (div_n - s % div_n) % div_n) for a, div_n, s in zip(axes, axes_div_by, shape)}
+        self.padded_shape = {a: s + self.pad[a][1] for a, s in zip(axes, shape)}
+        if 'C' in self.padded_shape:
+            del self.padded_shape['C']
+        return tuple(s + self.pad[a][1] for a, s in zip(axes, shape))
+
     def before(self, x, axes, axes_div_by):
         assert all(a % g == 0 for g, a in zip((self.grid.get(a, 1) for a in axes), axes_div_by))
         axes = axes_check_and_normalize(axes, x.ndim)
@@ -223,7 +233,27 @@ class StarDistBase:
         hasattr(normalizer, 'before') or _raise(ValueError("normalizer must provide .before(x, axes)"))
         return normalizer
 
-    def _predict_setup(self, img, axes, normalizer, n_tiles):
+    def _device_prep_plan(self, x, axes_net, normalizer, zoom):
+        """Can normalisation / zoom / reflect padding of this input run in HBM (stardist_b200/prep.py)?  Conditions: single
+        input channel, a dtype whose values the float32 upload preserves, no normaliser or this module's PercentileNormalizer
+        with its plain arguments.  Returns the plan (dict) or None (host path, as the reference does it)."""
+        import os
+        from .. import prep
+        if os.environ.get("STARDIST_B200_PREP", "device") != "device" or not torch.cuda.is_available():
+            return None
+        if not isinstance(x, np.ndarray) or x.dtype not in prep.EXACT_IN_F32 or self.config.n_channel_in != 1 or x.shape[-1] != 1:
+            return None
+        norm = None
+        if isinstance(normalizer, PercentileNormalizer):
+            kw = dict(normalizer.kwargs)
+            if type(normalizer) is not PercentileNormalizer or set(kw) - {'clip', 'eps'} or np.dtype(normalizer.dtype) != np.float32:
+                return None
+            norm = (normalizer.pmin, normalizer.pmax, bool(kw.get('clip', False)), kw.get('eps', 1e-20))
+        elif not isinstance(normalizer, NoNormalizer):
+            return None
+        return dict(norm=norm, zoom=None if zoom is None else tuple(zoom), src_dtype=x.dtype)
+
+    def _predict_setup(self, img, axes, normalizer, n_tiles, _zoom=None):
         """ Shared setup code between `predict` and `predict_sparse` (base.py:371-443) """
         if n_tiles is None:
             n_tiles = [1] * img.ndim
@@ -247,10 +277,28 @@ class StarDistBase:
         grid_dict = dict(zip(axes_net.replace('C', ''), grid))
         normalizer = self._check_normalizer(normalizer)
         resizer = StarDistPadAndCropResizer(grid=grid_dict)
-        x = normalizer.before(x, axes_net)
-        x = resizer.before(x, axes_net, axes_net_div_by)
-        if not _is_floatarray(x):
-            warnings.warn("Predicting on non-float input... ( forgot to normalize? )")
+        self._dev_prep = None
+        zoom_net = None
+        if _zoom is not None:                      # per image axis -> network axis order (the channel factor is 1)
+            zd = dict(zip(axes, _zoom))
+            zoom_net = tuple(zd.get(a, 1) for a in axes_net)
+        plan = self._device_prep_plan(x, axes_net, normalizer, zoom_net)
+        if plan is not None and (plan['norm'] is not None or plan['zoom'] is not None or
+                                 any(s % d for s, d in zip(x.shape, axes_net_div_by))):
+            # normalisation / zoom / padding happen in HBM after the upload (_to_device); only the bookkeeping here
+            shape_z = tuple(x.shape) if zoom_net is None else tuple(int(round(s * z)) for s, z in zip(x.shape, zoom_net))
+            plan.update(normalizer=normalizer, shape_z=shape_z, padded=resizer.plan(shape_z, axes_net, axes_net_div_by))
+            self._dev_prep = plan
+            if plan['norm'] is None and not _is_floatarray(x):
+                warnings.warn("Predicting on non-float input... ( forgot to normalize? )")
+        else:
+            if _zoom is not None:
+                from scipy import ndimage as ndi
+                x = ndi.zoom(x, zoom_net, order=1)
+            x = normalizer.before(x, axes_net)
+            x = resizer.before(x, axes_net, axes_net_div_by)
+            if not _is_floatarray(x):
+                warnings.warn("Predicting on non-float input... ( forgot to normalize? )")
         # tiles refer to the axes of the input image; the network sees them in axes_net order (base.py:419-424)
         n_tiles = _permute_axes(np.empty(n_tiles, dtype=bool)).shape
         n_tiles[channel] == 1 or _raise(ValueError("cannot tile the channel axis"))
@@ -287,7 +335,21 @@ class StarDistBase:
         stage = self._pinned('in', (1,) + x.shape, torch.float32)
         self._stage_fill(stage, x)
         self._stats['h2d_bytes'] = self._stats.get('h2d_bytes', 0) + stage.numel() * 4
-        return stage.to(self.net.device, non_blocking=True)
+        x_dev = stage.to(self.net.device, non_blocking=True)
+        plan, self._dev_prep = getattr(self, '_dev_prep', None), None
+        if plan is None:
+            return x_dev
+        from .. import prep
+        t = x_dev[0, ..., 0]                                  # single channel: the spatial array, contiguous
+        if plan['zoom'] is not None:
+            t = prep.zoom_device(t, plan['zoom'][:-1])
+        if plan['norm'] is not None:
+            pmin, pmax, clip, eps = plan['norm']
+            mi, ma = prep.normalize_device(t, tuple(t.shape), pmin, pmax, plan['src_dtype'], clip=clip, eps=eps)
+            nz = plan['normalizer']                            # PercentileNormalizer.before leaves mi / ma behind
+            nz.mi = np.asarray(mi, np.float32).reshape((1,) * x.ndim); nz.ma = np.asarray(ma, np.float32).reshape((1,) * x.ndim)
+        t = prep.pad_reflect_end_device(t.unsqueeze(-1), plan['padded'][:-1])
+        return t.unsqueeze(0)
 
     def _to_host(self, tensors, copy_threads=False):
         """device tensors -> numpy arrays: asynchronous copies into persistent pinned buffers, ONE stream
@@ -381,12 +443,12 @@ class StarDistBase:
         return prob, dist
 
     # ------------------------------------------------------------------ predict_sparse
-    def _predict_sparse_device(self, img, prob_thresh=None, axes=None, normalizer=None, n_tiles=None, b=2):
+    def _predict_sparse_device(self, img, prob_thresh=None, axes=None, normalizer=None, n_tiles=None, b=2, _zoom=None):
         """device-resident sparse prediction (base.py:541-633): returns dict of device tensors
         prob[n], dist[n,R], points_f32[n,nd] (for the NMS kernels), sorted by score."""
         L.require_cuda()
         x, axes, axes_net, axes_net_div_by, _permute_axes, resizer, n_tiles, grid, grid_dict, channel = \
-            self._predict_setup(img, axes, normalizer, n_tiles)
+            self._predict_setup(img, axes, normalizer, n_tiles, _zoom=_zoom)
         sp_axes = axes_net.replace('C', '')
         bounds = resizer.point_bounds(sp_axes)
         return self._candidates_from_device_input(self._to_device(x), bounds, prob_thresh=prob_thresh, b=b, n_tiles=n_tiles)
@@ -480,10 +542,12 @@ class StarDistBase:
                 (s in (1, None) or a in 'XYZ') or warnings.warn(f"replacing scale value {s} for non-spatial axis {a} with 1")
             scale = tuple(s if a in 'XYZ' else 1 for s, a in zip(scale, _axes))
             verbose and print(f"scaling image by factors {scale} for axes {_axes}")
-            img = ndi.zoom(img, scale, order=1)
+            if not sparse:
+                img = ndi.zoom(img, scale, order=1)
         scale_dict = None if scale is None else dict(zip(_axes, scale))
         if sparse:
-            cand = self._predict_sparse_device(img, prob_thresh=prob_thresh, axes=axes, normalizer=normalizer, n_tiles=n_tiles)
+            # the zoom (ndi.zoom(img, scale, order=1), base.py:735) runs in HBM when the input qualifies (_device_prep_plan)
+            cand = self._predict_sparse_device(img, prob_thresh=prob_thresh, axes=axes, normalizer=normalizer, n_tiles=n_tiles, _zoom=scale)
             if _device_labels:
                 nms_kwargs = dict(nms_kwargs, device_labels=True)
             res = self._instances_from_candidates_device(_shape_inst, cand, nms_thresh=nms_thresh, scale=scale_dict,

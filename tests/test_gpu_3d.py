@@ -176,7 +176,6 @@ def test_reference_3d_demo_model_reproduces_reference_test(sd):
     """The reference's shipped 3D_demo checkpoint (tests/golden/demo3d.npz) on its test volume through the product path:
     (fp, tp, fn) == (0, 30, 21) as pinned by stardist tests/test_model3D.py:85-96, instances equal to the CPU oracle's."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
-sys.path.insert(0, os.path.join(ROOT, "tests"))
     import demo3d
     from oracle import pipeline3d
     from stardist_b200.utils import normalize
