@@ -329,3 +329,78 @@ def test_unnormalised_uint16_input_does_not_overflow_silently(sd):
         warnings.simplefilter("always")
         model.predict(rng.uniform(0, 1, (64, 96)).astype(np.float32))
     assert not any("fp16 range" in str(w.message) for w in wlist)
+
+
+def test_device_percentile_normalisation_is_numpy_exact(sd):
+    """csbdeep.utils.normalize(x, pmin, pmax) on the device -- mi / ma are np.percentile's bits (exact order
+    statistics by radix select + numpy's own interpolation), the normalised array equals the numpy restatement bit for bit"""
+    import torch
+    from stardist_b200 import prep
+    from stardist_b200.utils import normalize
+    rng = np.random.default_rng(7)
+    for dtype, shape, valid in ((np.float32, (301, 257), (301, 257)), (np.uint16, (128, 200), (128, 200)), (np.float32, (40, 64, 72), (37, 64, 70)),
+                                (np.uint8, (77, 91), (77, 91))):
+        if np.dtype(dtype).kind == 'f':
+            x = rng.normal(0.3, 1.0, shape).astype(dtype); x[rng.random(shape) < 0.01] *= 50
+        else:
+            x = rng.integers(0, np.iinfo(dtype).max, shape).astype(dtype)
+        xv = x[tuple(slice(0, v) for v in valid)]
+        t = torch.from_numpy(x.astype(np.float32)).cuda()
+        for ps in ((1, 99.8), (2, 99.8), (0, 100), (50, 50.5), (3, 99.9)):
+            got = prep.percentiles_device(t, valid, ps, x.dtype)
+            want = [np.percentile(xv, p) for p in ps]
+            for g, w in zip(got, want):
+                assert np.asarray(g).dtype == np.asarray(w).dtype and np.array_equal(g, w), (dtype, ps, g, w)
+        if valid == shape:
+            t2 = t.clone()
+            prep.normalize_device(t2, shape, 1, 99.8, x.dtype)
+            assert np.array_equal(t2.cpu().numpy(), normalize(x, 1, 99.8))
+            t3 = t.clone()
+            prep.normalize_device(t3, shape, 2, 99, x.dtype, clip=True, eps=1e-3)
+            assert np.array_equal(t3.cpu().numpy(), normalize(x, 2, 99, clip=True, eps=1e-3))
+
+
+def test_device_zoom_and_reflect_pad_vs_scipy_numpy(sd):
+    """ndi.zoom(img, scale, order=1) (stardist/models/base.py:735) and np.pad(mode='reflect') at the end on the device"""
+    import torch
+    from scipy import ndimage as ndi
+    from stardist_b200 import prep
+    rng = np.random.default_rng(8)
+    worst = 0.0
+    for it in range(40):
+        nd = 2 if it % 3 else 3
+        shp = tuple(int(v) for v in rng.integers(5, 90 if nd == 2 else 30, nd))
+        sc = tuple(float(v) for v in rng.choice([0.5, 0.75, 1.3, 2.0, 1.7, 0.33, 3.0, 1.0, 0.9], nd))
+        x = rng.uniform(0, 1, shp).astype(np.float32)
+        want = ndi.zoom(x, sc, order=1)
+        got = prep.zoom_device(torch.from_numpy(x).cuda(), sc).cpu().numpy()
+        assert got.shape == want.shape
+        worst = max(worst, float(np.abs(got - want).max()))
+        pads = [int(v) for v in rng.integers(0, min(shp) - 1, nd)]
+        out_sp = [s + p for s, p in zip(shp, pads)]
+        xc = np.stack([x, 2 * x], -1)
+        wantp = np.pad(xc, [(0, p) for p in pads] + [(0, 0)], mode='reflect')
+        gotp = prep.pad_reflect_end_device(torch.from_numpy(xc).cuda(), out_sp).cpu().numpy()
+        assert np.array_equal(gotp, wantp)
+    assert worst <= 1e-6, worst       # float tolerance (bit-equal in 299 of 300 cases of the numpy emulation of this rule)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_predict_instances_with_device_normaliser_and_scale_equals_host_path(sd, dtype, monkeypatch):
+    """normalizer=PercentileNormalizer / scale= handled in HBM give the labels of the host (numpy / scipy) preparation"""
+    import bench_data
+    from stardist_b200.models.base import PercentileNormalizer
+    cfg = sd.Config2D(n_rays=32)
+    model = sd.StarDist2D(cfg, name=None, basedir=None, weights=bench_data.bench_weights_2d(cfg))
+    img, _ = bench_data.synthetic_image((250, 333), seed=4)
+    raw = (np.clip(img, 0, 1.5) * 20000 + 300).astype(dtype)
+    for kw in (dict(), dict(scale=1.5), dict(scale=(0.75, 1.25))):
+        monkeypatch.setenv("STARDIST_B200_PREP", "host")
+        lh, rh = model.predict_instances(raw, normalizer=PercentileNormalizer(1, 99.8), **kw)
+        monkeypatch.setenv("STARDIST_B200_PREP", "device")
+        ld, rd = model.predict_instances(raw, normalizer=PercentileNormalizer(1, 99.8), **kw)
+        assert len(rh['prob']) > 20
+        if 'scale' in kw:       # zoom: float tolerance 1e-6 on the input -> allow a handful of borderline candidates
+            assert abs(len(rd['prob']) - len(rh['prob'])) <= 2 and np.mean(ld != lh) < 2e-3
+        else:
+            assert np.array_equal(ld, lh) and np.array_equal(rd['points'], rh['points']) and np.array_equal(rd['coord'], rh['coord'])
