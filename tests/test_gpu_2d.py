@@ -228,7 +228,12 @@ def test_reference_2d_demo_model_reproduces_reference_test(sd):
     assert (st.fp, st.tp, st.fn) == demo2d.REFERENCE_TEST_STATS
     ref_labels, ref = pipeline2d.predict_instances(cfg, weights, x, thr['prob'], thr['nms'])
     assert np.array_equal(polygons['points'], ref['points'])
-    assert np.mean(labels != ref_labels) < 1e-3
+    assert np.mean(labels != ref_labels) < 1e-3          # the oracle ran its own (torch-CPU) network: float-induced tolerance
+    # the integer path on the trained model's real maps: same floats in (cand_from=model), bit-equal results out
+    labels2, polygons2 = model.predict_instances(x)
+    ex_labels, ex = pipeline2d.predict_instances(cfg, weights, x, thr['prob'], thr['nms'], cand_from=model)
+    assert np.array_equal(polygons2['points'], ex['points']) and np.array_equal(polygons2['prob'], ex['prob'])
+    assert np.array_equal(polygons2['coord'].view(np.int32), ex['coord'].view(np.int32)) and np.array_equal(labels2, ex_labels)
     # float maps of the TRAINED network (tcgen05 path) against a float64 evaluation: the 1e-5 relative bar
     import torch
     prob1, dist1 = model.predict(x)

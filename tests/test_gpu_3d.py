@@ -196,7 +196,12 @@ def test_reference_3d_demo_model_reproduces_reference_test(sd):
     os.environ["OMP_NUM_THREADS"] = "1"
     ref_labels, ref = pipeline3d.predict_instances(cfg, rays, x, thr['prob'], thr['nms'], weights=weights)
     assert np.array_equal(res['points'], ref['points'])
-    assert np.mean(labels != ref_labels) < 2e-3
+    assert np.mean(labels != ref_labels) < 2e-3          # the oracle ran its own (torch-CPU) network: float-induced tolerance
+    # the integer path on the trained model's real maps (cand_from=model): bit-equal
+    labels2, res2 = model.predict_instances(x)
+    ex_labels, ex = pipeline3d.predict_instances(cfg, rays, x, thr['prob'], thr['nms'], cand_from=model)
+    assert np.array_equal(res2['points'], ex['points']) and np.array_equal(res2['prob'], ex['prob']) and np.array_equal(res2['dist'], ex['dist'])
+    assert np.array_equal(labels2, ex_labels)
 
 
 
