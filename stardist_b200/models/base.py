@@ -149,6 +149,8 @@ class StarDistBase:
         if weights is None:
             weights = glorot_uniform_weights(config, seed=seed)
         else:
+            from .weights import canonicalize_auto_names
+            weights = canonicalize_auto_names(config, weights)
             self._check_weights(config, weights)
         self.weights = weights
         self._net = None

@@ -129,10 +129,20 @@ class StarDist3D(StarDistBase):
             if nk == 0:
                 labels = np.zeros(tuple(img_shape), np.uint16)      # geom3d.py:128-131
             else:
-                # survivors arrive in descending (stable) score order == painting order (geom3d.py:176-180)
-                lab_ids = torch.arange(1, nk + 1, dtype=torch.int32, device=dev)
+                # painting order of geom3d.polyhedron_to_label (geom3d.py:176-180): argsort(prob, stable)[::-1] of the survivor
+                # list.  The list is already score-descending; only runs of TIED scores come out reversed by that rule
+                # (e.g. a saturated sigmoid), and the dense path applies it -- same rule here so sparse == dense.
+                probi_h = probi_d.cpu().numpy()
+                order = np.argsort(probi_h, kind='stable')[::-1]
                 lab_d = torch.empty(tuple(int(s) for s in img_shape), dtype=torch.int32, device=dev)
-                L.check(lib.sdb_polyhedron_to_label(L.ptr(disti_d), L.ptr(pts_d), L.ptr(verts_d), L.ptr(faces_d), nk, R, int(faces_d.shape[0]),
+                if np.array_equal(order, np.arange(nk)):
+                    lab_ids = torch.arange(1, nk + 1, dtype=torch.int32, device=dev)
+                    dist_paint, pts_paint = disti_d, pts_d
+                else:
+                    order_d = torch.from_numpy(np.ascontiguousarray(order)).to(dev)
+                    lab_ids = (order_d + 1).to(torch.int32)
+                    dist_paint, pts_paint = disti_d.index_select(0, order_d).contiguous(), pts_d.index_select(0, order_d).contiguous()
+                L.check(lib.sdb_polyhedron_to_label(L.ptr(dist_paint), L.ptr(pts_paint), L.ptr(verts_d), L.ptr(faces_d), nk, R, int(faces_d.shape[0]),
                                                    L.ptr(lab_ids), int(img_shape[0]), int(img_shape[1]), int(img_shape[2]), 0,
                                                    1 if overlap_label is not None else 0, 0 if overlap_label is None else int(overlap_label),
                                                    L.ptr(lab_d), L.stream_ptr()))

@@ -158,3 +158,30 @@ def glorot_uniform_weights(config, seed=0):
 
 def count_params(weights):
     return int(sum(k.size + b.size for k, b in weights.values()))
+
+
+
+def canonicalize_auto_names(config, weights):
+    """Keras names un-named layers `conv2d`, `conv2d_1`, ... with a per-session counter (tf.keras 2.x starts without a
+    suffix and keeps counting across models), and `load_weights` binds them by topology order, not by name.  The grid stem
+    (model2d.py:316-325) and every ResNet convolution (csbdeep resnet_block) are such layers.  If the checkpoint's
+    auto-named convolution groups do not carry exactly the names this architecture expects, they are re-bound
+    positionally: sorted by their numeric suffix (creation order) and matched against the expected auto-named layers in
+    topology order, with a kernel-shape check."""
+    import re
+    pat = re.compile(r'^conv%dd(?:_(\d+))?$' % config.n_dim)
+    expected = [l for l in net_layers(config) if l['kind'] in ('conv', 'conv_class') and pat.match(l['name'])]
+    if not expected or all(l['name'] in weights for l in expected):
+        return weights
+    have = sorted((k for k in weights if pat.match(k)), key=lambda k: int(pat.match(k).group(1) or 0))
+    if len(have) != len(expected):
+        raise ValueError("checkpoint holds %d auto-named convolution layers %s, the architecture needs %d"
+                         % (len(have), have[:4], len(expected)))
+    out = {k: v for k, v in weights.items() if not pat.match(k)}
+    for l, k in zip(expected, have):
+        want = tuple(l['k']) + (l['cin'], l['cout'])
+        if tuple(np.asarray(weights[k][0]).shape) != want:
+            raise ValueError("auto-named layer '%s' (position of '%s'): kernel shape %s, expected %s"
+                             % (k, l['name'], tuple(np.asarray(weights[k][0]).shape), want))
+        out[l['name']] = weights[k]
+    return out

@@ -611,3 +611,21 @@ def test_render_rule_differs_from_reference_only_on_exact_hull_facets():
                 n_diff += hullcheck.assert_only_exact_hull_boundary_voxels_differ((ours > 0).astype(np.int32), (ref > 0).astype(np.int32), dist[None],
                                                                                   point[None].astype(np.float32), rays.vertices)
     assert n_diff > 0        # the lattice-aligned families do hit the caveat
+
+
+def test_auto_named_keras_layers_are_bound_positionally():
+    """tf.keras 2.x names un-named convolutions conv2d, conv2d_1, ... (session counter); checkpoints bind by order"""
+    from stardist_b200 import Config2D, Config3D
+    from stardist_b200.models.weights import glorot_uniform_weights, canonicalize_auto_names
+    for cfg, pre in ((Config2D(grid=(2, 2)), 'conv2d'), (Config3D(backbone='resnet', grid=(1, 2, 2)), 'conv3d')):
+        w = glorot_uniform_weights(cfg, seed=0)
+        names = sorted([k for k in w if k.startswith(pre)], key=lambda s: int(s.split('_')[1]))
+        for start in (0, 7):
+            w2 = {k: v for k, v in w.items() if not k.startswith(pre)}
+            for i, old in enumerate(names):
+                w2[pre if (start + i) == 0 else '%s_%d' % (pre, start + i)] = w[old]
+            c = canonicalize_auto_names(cfg, w2)
+            assert all(np.array_equal(c[k][0], w[k][0]) for k in names)
+        w3 = dict(w); w3.pop(names[0])
+        with pytest.raises(ValueError):
+            canonicalize_auto_names(cfg, w3)

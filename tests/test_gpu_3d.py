@@ -465,3 +465,21 @@ def test_c_entry_points_raise_instead_of_aborting(sd):
     fn.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p] * 2 + [ctypes.c_float] + [ctypes.c_int] * 3 + [ctypes.c_void_p]
     fn(L.ptr(np.ones(2, np.float32)), L.ptr(d), L.ptr(p), 2, 300, len(f), L.ptr(v), L.ptr(f), 0.4, 1, 1, 0, L.ptr(res))
     assert not res.any() and b"unsupported" in lib.sdb_last_error()
+
+
+def test_tied_scores_sparse_equals_dense_3d(sd):
+    """overlapping survivors with EQUAL scores: the device (sparse) path paints in the order geom3d.polyhedron_to_label
+    defines (argsort(prob, stable)[::-1]), so sparse == dense also on ties"""
+    rays = sd.Rays_GoldenSpiral(32)
+    cfg = sd.Config3D(rays=rays)
+    model = sd.StarDist3D(cfg, name=None, basedir=None)
+    shape = (24, 40, 40)
+    rng = np.random.default_rng(3)
+    pts = np.array([[12, 12, 12], [12, 15, 14], [12, 26, 26], [12, 24, 29], [10, 20, 20]])
+    prob = np.array([.9, .9, .9, .9, .5], np.float32)            # two tied, overlapping pairs
+    dist = (7 * (1 + .1 * rng.uniform(-1, 1, (5, 32)))).astype(np.float32)
+    l_sparse, r_sparse = model._instances_from_prediction(shape, prob, dist, points=pts, nms_thresh=0.9)
+    from stardist_b200.geometry.geom3d import polyhedron_to_label
+    from stardist_b200.matching import relabel_sequential
+    want = relabel_sequential(polyhedron_to_label(r_sparse['dist'], r_sparse['points'], rays, shape, prob=r_sparse['prob'], verbose=False))[0]
+    assert len(r_sparse['prob']) == 5 and np.array_equal(l_sparse, want)
