@@ -5,62 +5,53 @@ Mirrors stardist/geometry/geom3d.py: polyhedron_to_label (:100-198), dist_to_coo
 import numpy as np
 
 
+RENDER_MODES = ("full", "kernel", "hull", "bbox", "debug")      # index = render_mode of the C entry point
+
+
+def _as_rows(a, what):
+    """one polyhedron may be given as a flat vector"""
+    a = np.asanyarray(a)
+    return a.reshape(1, -1) if a.ndim == 1 else a
+
+
 def polyhedron_to_label(dist, points, rays, shape, prob=None, thr=-np.inf, labels=None, mode="full", verbose=True, overlap_label=None):
-    """creates labeled image from stardist representations (see the reference docstring)
+    """Label image of shape `shape` from star-convex polyhedra (API of stardist/geometry/geom3d.py:100-198).
 
-    mode: "full", "kernel", "hull", "bbox" or "debug"
-    """
+    dist (n, n_rays) ray lengths, points (n, 3) centres, rays a Rays object; prob (n,) scores (default all one) select the
+    polyhedra with prob >= thr and fix the painting order -- descending score, the first polyhedron covering a voxel wins;
+    labels (n,) ids to write (default 1..n); mode one of RENDER_MODES; overlap_label: value for voxels covered more than once.
+    Rendering: csrc/label3d.cu through the reference-signature entry point."""
     from ..lib.stardist3d import c_polyhedron_to_label
-    if len(points) == 0:
-        if verbose:
-            print("warning: empty list of points (returning background-only image)")
+    n = len(points)
+    if n == 0:
+        verbose and print("warning: empty list of points (returning background-only image)")
         return np.zeros(shape, np.uint16)
-    dist = np.asanyarray(dist)
-    points = np.asanyarray(points)
-    if dist.ndim == 1:
-        dist = dist.reshape(1, -1)
-    if points.ndim == 1:
-        points = points.reshape(1, -1)
-    if labels is None:
-        labels = np.arange(1, len(points) + 1)
-    labels = np.asanyarray(labels)
-    if np.amin(dist) <= 0:
-        raise ValueError("distance array should be positive!")
-    prob = np.ones(len(points)) if prob is None else np.asanyarray(prob)
-    if dist.ndim != 2:
-        raise ValueError("dist should be 2 dimensional but has shape %s" % str(dist.shape))
-    if dist.shape[1] != len(rays):
-        raise ValueError("inconsistent number of rays!")
-    if len(prob) != len(points):
-        raise ValueError("len(prob) != len(points)")
-    if len(labels) != len(points):
-        raise ValueError("len(labels) != len(points)")
-    modes = {"full": 0, "kernel": 1, "hull": 2, "bbox": 3, "debug": 4}
-    if mode not in modes:
-        raise KeyError("Unknown render mode '%s' , allowed:  %s" % (mode, tuple(modes.keys())))
-    lbl = np.zeros(shape, np.uint16)
-    # filter points
-    ind = np.where(prob >= thr)[0]
-    if len(ind) == 0:
-        if verbose:
-            print("warning: no points found with probability>= {thr:.4f} (returning background-only image)".format(thr=thr))
-        return lbl
-    prob = prob[ind]
-    points = points[ind]
-    dist = dist[ind]
-    labels = labels[ind]
-    # sort points with decreasing probability (stable definition of the reference's argsort()[::-1])
-    ind = np.argsort(prob, kind='stable')[::-1]
-    points = points[ind]
-    dist = dist[ind]
-    labels = labels[ind]
-
-    def _prep(x, dtype):
-        return np.ascontiguousarray(x.astype(dtype, copy=False))
-    return c_polyhedron_to_label(_prep(dist, np.float32), _prep(points, np.float32), _prep(rays.vertices, np.float32),
-                                 _prep(rays.faces, np.int32), _prep(labels, np.int32), np.int32(modes[mode]),
-                                 np.int32(verbose), np.int32(overlap_label is not None),
-                                 np.int32(0 if overlap_label is None else overlap_label), shape)
+    dist, points = _as_rows(dist, "dist"), _as_rows(points, "points")
+    labels = np.arange(1, n + 1) if labels is None else np.asanyarray(labels)
+    prob = np.ones(n) if prob is None else np.asanyarray(prob)
+    # argument checks, with the reference's messages
+    problems = (
+        (np.amin(dist) <= 0, ValueError("distance array should be positive!")),
+        (dist.ndim != 2, ValueError("dist should be 2 dimensional but has shape %s" % str(dist.shape))),
+        (dist.ndim == 2 and dist.shape[1] != len(rays), ValueError("inconsistent number of rays!")),
+        (len(prob) != n, ValueError("len(prob) != len(points)")),
+        (len(labels) != n, ValueError("len(labels) != len(points)")),
+        (mode not in RENDER_MODES, KeyError("Unknown render mode '%s' , allowed:  %s" % (mode, RENDER_MODES))),
+    )
+    for failed, err in problems:
+        if failed:
+            raise err
+    # selection and painting order in one index vector: the survivors of the threshold, best score first
+    # (the reference's argsort()[::-1] is unstable on ties; defined here as the stable sort, see DESIGN.md)
+    chosen = np.flatnonzero(prob >= thr)
+    if chosen.size == 0:
+        verbose and print("warning: no points found with probability>= {thr:.4f} (returning background-only image)".format(thr=thr))
+        return np.zeros(shape, np.uint16)
+    chosen = chosen[np.argsort(prob[chosen], kind='stable')[::-1]]
+    return c_polyhedron_to_label(np.ascontiguousarray(dist[chosen], np.float32), np.ascontiguousarray(points[chosen], np.float32),
+                                 np.ascontiguousarray(rays.vertices, np.float32), np.ascontiguousarray(rays.faces, np.int32),
+                                 np.ascontiguousarray(labels[chosen], np.int32), np.int32(RENDER_MODES.index(mode)), np.int32(verbose),
+                                 np.int32(overlap_label is not None), np.int32(0 if overlap_label is None else overlap_label), shape)
 
 
 def dist_to_coord3D(dist, points, rays_vertices):
