@@ -94,6 +94,9 @@ int sdb_paint_order_2d(const float* d_prob_desc, int n, int* d_rank, int* d_id_b
  * 2 = verify: both on every pair, disagreements are counted.  Results are identical in all modes.
  * stats: out4 = {pairs tested, pairs that needed the exact sweep, verify mismatches, nms calls}. */
 int sdb_nms2d_set_filter(int mode);
+/* 1 (default): frontier rounds >= 1 run inside one cooperative kernel with on-device termination; 0: host-driven rounds.
+ * Results are identical. */
+int sdb_nms2d_set_tail(int on);
 void sdb_nms2d_filter_stats(unsigned long long* out4, int reset);
 
 /* paint polygons (geom2d.py:149-197): d_rank[i] = paint rank of polygon i (0 = painted first;

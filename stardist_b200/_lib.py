@@ -32,6 +32,8 @@ def _declare(lib):
     lib.sdb_paint_order_2d.restype = c_int
     lib.sdb_nms2d_set_filter.argtypes = [c_int]
     lib.sdb_nms2d_set_filter.restype = c_int
+    lib.sdb_nms2d_set_tail.argtypes = [c_int]
+    lib.sdb_nms2d_set_tail.restype = c_int
     lib.sdb_nms2d_filter_stats.argtypes = [POINTER(ctypes.c_ulonglong), c_int]
     lib.sdb_nms2d_filter_stats.restype = None
     lib.sdb_polygons_to_label_2d.argtypes = [P, P, P, c_int, c_int, c_int, c_int, P, P]

@@ -26,6 +26,7 @@
 namespace sdnms {
 int g_filter_mode = 1;
 unsigned long long g_filter_stats[4] = {0, 0, 0, 0};
+int g_tail_mode = 1;
 namespace {
 
 // ------------------------------------------------------------------------------------------
@@ -475,6 +476,7 @@ extern "C" int sdb_nms2d_set_filter(int mode) {
   g_filter_mode = mode;
   return 0;
 }
+extern "C" int sdb_nms2d_set_tail(int on) { g_tail_mode = on ? 1 : 0; return 0; }
 extern "C" void sdb_nms2d_filter_stats(unsigned long long* out4, int reset) {
   for (int k = 0; k < 4; ++k) { out4[k] = g_filter_stats[k]; if (reset) g_filter_stats[k] = 0; }
 }

@@ -57,6 +57,7 @@ __device__ __forceinline__ bool reaches(const NmsArrays& A, int h, int c, float 
 
 // pre-filter mode and cumulative statistics (nms2d.cu)
 extern int g_filter_mode;
+extern int g_tail_mode;      // 1 (default): rounds >= 1 in one cooperative launch (k_tail); 0: host loop only
 extern unsigned long long g_filter_stats[4];   // pairs, pairs sent to the exact sweep, verify mismatches, calls
 
 // frontier-peeling rounds, instantiated per polygon capacity in nms2d_nv32.cu / nms2d_nv128.cu

@@ -6,6 +6,7 @@
 #include "clip2d.cuh"
 #include "polyfast.cuh"
 #include <algorithm>
+#include <cooperative_groups.h>
 
 namespace sdnms {
 namespace {
@@ -41,9 +42,11 @@ __device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSwe
 // in this round enumerates the undecided candidates it reaches (only ~n_kept * degree work in total).
 // The undecided candidates are kept in a compacted list (double buffered: blocked candidates are
 // appended to list_out, counters[7] = its length; round 0 reads the identity list).
-__global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2* __restrict__ cursor, int* __restrict__ kept_list,
-                            const int* __restrict__ list_in, unsigned int n_in_or_all, const unsigned int* __restrict__ n_in_dev,
-                            int* __restrict__ list_out, unsigned int* __restrict__ counters) {
+// (device function shared by the stand-alone kernel and the tail kernel k_tail; the arrays written during the rounds carry
+// no __restrict__ / const-cache qualifiers: inside k_tail they are re-read after grid-wide barriers)
+__device__ __forceinline__ void d_frontier2(const NmsArrays& A, int round, int2* cursor, int* kept_list,
+                            const int* list_in, unsigned int n_in_or_all, const unsigned int* n_in_dev,
+                            int* list_out, unsigned int* counters) {
   // one WARP per undecided candidate: the neighbourhood scan is a chain of dependent loads, so the lanes
   // test 32 list items per step (a kept candidate scans its whole 3x3 neighbourhood: ~2000 items)
   if (counters[5]) return;
@@ -127,11 +130,14 @@ __global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2*
   }
   if (lane == 0 && n_undecided) atomicAdd(&counters[0], n_undecided);
 }
+__global__ void __launch_bounds__(256) k_frontier2(NmsArrays A, int round, int2* cursor, int* kept_list, const int* list_in, unsigned int n_in_or_all,
+                                                   const unsigned int* n_in_dev, int* list_out, unsigned int* counters) {
+  d_frontier2(A, round, cursor, kept_list, list_in, n_in_or_all, n_in_dev, list_out, counters);
+}
 
 // one BLOCK per candidate kept in this round: emit the (h, c) pairs the reference would test (:548-576).
 // (A warp per h walked ~2000 neighbour items in 60 dependent steps: ~100 us per round regardless of the count.)
-__global__ void __launch_bounds__(256) k_pairs(NmsArrays A, int round, const int* __restrict__ kept_list, int2* __restrict__ pairs, unsigned int cap,
-                        unsigned int* __restrict__ counters) {
+__device__ __forceinline__ void d_pairs(const NmsArrays& A, int round, const int* kept_list, int2* pairs, unsigned int cap, unsigned int* counters) {
   if (counters[5]) return;
   const unsigned int n_kept = counters[6];
   for (unsigned int w = blockIdx.x; w < n_kept; w += gridDim.x) {
@@ -177,6 +183,9 @@ __global__ void __launch_bounds__(256) k_pairs(NmsArrays A, int round, const int
     }
   }
 }
+__global__ void __launch_bounds__(256) k_pairs(NmsArrays A, int round, const int* kept_list, int2* pairs, unsigned int cap, unsigned int* counters) {
+  d_pairs(A, round, kept_list, pairs, cap, counters);
+}
 __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ counters) {
   if (counters[1] > cap) counters[5] = 1;
 }
@@ -186,8 +195,7 @@ __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ co
 // integral and its bound decide most pairs, the rest is appended to the exact list (counters[9]).
 // verify != 0: nothing is decided here, the verdict is stored per pair for k_clip to compare.
 template <typename T>
-__global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restrict__ pairs, int2* __restrict__ xpairs,
-                                              signed char* __restrict__ verdict, int verify, unsigned int* __restrict__ counters) {
+__device__ __forceinline__ void d_fast(const NmsArrays& A, const int2* pairs, int2* xpairs, signed char* verdict, int verify, unsigned int* counters) {
   if (counters[5]) return;
   const unsigned int n_pairs = counters[1];
   const unsigned int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
@@ -269,6 +277,11 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
   }
 }
 
+template <typename T>
+__global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* pairs, int2* xpairs, signed char* verdict, int verify, unsigned int* counters) {
+  d_fast<T>(A, pairs, xpairs, verdict, verify, counters);
+}
+
 // Exact sweep: ONE PAIR PER WARP, executed by lane 0 with the sweep state (~8 KB of pools for 32-gons) in
 // SHARED memory.  The sweep is ~3e4 dependent, branchy instructions per pair: lanes running different pairs
 // serialise anyway (a 32-pairs-per-warp version was no faster in aggregate), and a single active lane in local
@@ -277,10 +290,8 @@ __global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* __restric
 template <int NV> struct ClipCfg { static constexpr int WARPS = (NV <= 32) ? 4 : 1; };
 
 template <int NV>
-__global__ void __launch_bounds__(32 * ClipCfg<NV>::WARPS) k_clip(NmsArrays A, const int2* __restrict__ pairs, const unsigned int* __restrict__ n_list,
-                                              const signed char* __restrict__ verdict,
-                                              int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
-  extern __shared__ __align__(16) unsigned char clip_smem[];
+__device__ __forceinline__ void d_clip(const NmsArrays& A, const int2* pairs, const unsigned int* n_list, const signed char* verdict,
+                                       int2* slow_pairs, unsigned int* counters, unsigned char* clip_smem) {
   if (counters[5]) return;
   const unsigned int n_pairs = *n_list;
   const unsigned int G = (gridDim.x * blockDim.x) >> 5;                       // warps in the grid
@@ -302,6 +313,13 @@ __global__ void __launch_bounds__(32 * ClipCfg<NV>::WARPS) k_clip(NmsArrays A, c
 }
 
 template <int NV>
+__global__ void __launch_bounds__(32 * ClipCfg<NV>::WARPS) k_clip(NmsArrays A, const int2* pairs, const unsigned int* n_list, const signed char* verdict,
+                                                                  int2* slow_pairs, unsigned int* counters) {
+  extern __shared__ __align__(16) unsigned char clip_smem_k[];
+  d_clip<NV>(A, pairs, n_list, verdict, slow_pairs, counters, clip_smem_k);
+}
+
+template <int NV>
 __global__ void __launch_bounds__(64) k_clip_slow(NmsArrays A, const int2* __restrict__ slow_pairs, unsigned int* __restrict__ counters) {
   if (counters[5]) return;
   const unsigned int n_slow = counters[4];
@@ -315,10 +333,58 @@ __global__ void __launch_bounds__(64) k_clip_slow(NmsArrays A, const int2* __res
   }
 }
 
+__device__ __forceinline__ void d_reset_counters(unsigned int* counters) {
+  counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; counters[8] = counters[7]; counters[7] = 0;
+  counters[12] += counters[9]; counters[9] = 0;
+}
 __global__ void k_reset_counters(unsigned int* counters) {
   if (counters[5]) return;
-  if (threadIdx.x == 0) { counters[2] += counters[1]; counters[0] = 0; counters[1] = 0; counters[4] = 0; counters[6] = 0; counters[8] = counters[7]; counters[7] = 0;
-                        counters[12] += counters[9]; counters[9] = 0; }
+  if (threadIdx.x == 0) d_reset_counters(counters);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tail of the frontier peeling in ONE cooperative launch.  Round 0 carries the bulk of the work (all candidates scanned,
+// ~70 % of the pair tests) and runs as full-occupancy kernels; the rounds after it touch a few thousand candidates each
+// and were dominated by launch gaps and host round trips (7 launches per round, a synchronisation every 4 rounds).
+// Here the phases of a round are separated by grid-wide barriers, the termination test (no undecided candidate left)
+// is evaluated on the device, and the host reads the counters once at the end.  The kernel hands back to the host loop
+// (which knows how to grow the pair list / run the slow exact path) by leaving: counters[5] set (pair list overflow),
+// counters[4] != 0 (pairs for the slow path) or simply counters[0] != 0 after max_rounds; counters[13] = round in progress.
+struct TailCtx {
+  int2* cursor; int* kept; int* list0; int* list1; int2* pairs; int2* xpairs; int2* slow;
+  unsigned int* counters; unsigned int cap; int round0, max_rounds, filter;
+};
+
+template <int NV>
+__global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char tail_smem[];
+  unsigned int* cnt = C.counters;
+  volatile unsigned int* vc = cnt;
+  if (vc[5] || vc[3] || vc[4]) return;                  // round 0 left work for the host (uniform: nothing writes before the first barrier)
+  const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  for (int round = C.round0; round < C.round0 + C.max_rounds; ++round) {
+    if (lead) { d_reset_counters(cnt); cnt[13] = (unsigned int)round; }
+    grid.sync();
+    int* lin = (round & 1) ? C.list1 : C.list0;
+    int* lout = (round & 1) ? C.list0 : C.list1;
+    d_frontier2(A, round, C.cursor, C.kept, lin, 0u, cnt + 8, lout, cnt);
+    grid.sync();
+    if (vc[0] == 0) break;                                // no undecided candidate was left: done
+    d_pairs(A, round, C.kept, C.pairs, C.cap, cnt);
+    grid.sync();
+    if (vc[1] > C.cap) { if (lead) cnt[5] = 1; break; }   // pair list overflow: the host grows it and redoes this round's pair stage
+    if (C.filter == 1) {
+      d_fast<int32_t>(A, C.pairs, C.xpairs, nullptr, 0, cnt);
+      grid.sync();
+      d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem);
+    } else {
+      d_clip<NV>(A, C.pairs, cnt + 1, nullptr, C.slow, cnt, tail_smem);
+    }
+    grid.sync();
+    if (vc[4] != 0) break;                                // pool overflow in the fast sweep: slow exact path on the host loop
+  }
 }
 
 template <int NV>
@@ -326,7 +392,7 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
                unsigned int* h_pin /* pinned [8*BATCH] */) {
   (void)d_slow_unused;
   const int n = A.n;
-  constexpr int BATCH = 4;     // rounds launched per host synchronisation
+  constexpr int BATCH = 4;     // rounds launched per host synchronisation (host loop)
   size_t cap = std::max<size_t>((size_t)n * 2, 1 << 15);
   sdb::DevBuf b_pairs, b_slow, b_cursor, b_kept, b_list0, b_list1, b_xpairs, b_verdict;
   const int filter = A.filter;
@@ -345,6 +411,22 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
   SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
   SDB_CUDA(cudaMemsetAsync(d_counters, 0, 16 * sizeof(unsigned int), st));
   int round = 0;
+  auto launch_frontier = [&](int r) -> int {
+    SDB_LAUNCH(k_reset_counters, 1, 32, 0, st, d_counters);
+    // round r reads the list written by round r-1 (length saved in counters[8] by k_reset_counters)
+    int* lin = (r & 1) ? b_list1.as<int>() : b_list0.as<int>();
+    int* lout = (r & 1) ? b_list0.as<int>() : b_list1.as<int>();
+    sdb::ProfSpan spf;
+    sdb::profile_begin("nms2d_frontier", st, &spf);
+    if (r == 0) SDB_LAUNCH(k_frontier2, 148 * 8, 256, 0, st, A, r, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)nullptr, (unsigned int)n, (const unsigned int*)nullptr, lout, d_counters);
+    else SDB_LAUNCH(k_frontier2, 148 * 8, 256, 0, st, A, r, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)lin, 0u, (const unsigned int*)(d_counters + 8), lout, d_counters);
+    sdb::profile_end("nms2d_frontier", st, &spf);
+    return 0;
+  };
+  auto launch_clip_slow = [&]() -> int {
+    SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
+    return 0;
+  };
   auto launch_pair_stage = [&](int r) -> int {
     sdb::ProfSpan sp;
     sdb::profile_begin("nms2d_pairs", st, &sp);
@@ -368,62 +450,94 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       else SDB_LAUNCH((k_clip<NV>), cblocks, 32 * CW, csm, st, A, b_pairs.as<int2>(), d_counters + 1, filter == 2 ? b_verdict.as<signed char>() : (const signed char*)nullptr, b_slow.as<int2>(), d_counters);
     }
     sdb::profile_end("nms2d_clip", st, &sp);
-    SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
+    return launch_clip_slow();
+  };
+  // pair list overflowed in round r: its frontier marks are in place, the later kernels of the round were no-ops.
+  // Grow the lists, clear the flag, redo the pair stage of that round (c = the counters read back).
+  auto recover_overflow = [&](const unsigned int* c, int r) -> int {
+    cap = (size_t)c[1] + (size_t)c[1] / 2 + 1024;
+    SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
+    SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
+    if (alloc_filter_lists()) return 1;
+    const unsigned int zeros[10] = {c[0], 0, c[2], 0, 0, 0, c[6], c[7], c[8], 0};
+    SDB_CUDA(cudaMemcpyAsync(d_counters, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st));
+    if (launch_pair_stage(r)) return 1;
+    SDB_CUDA(cudaStreamSynchronize(st));
     return 0;
   };
+  auto finish_stats = [&](const unsigned int* c) {
+    // pairs tested = counters[2] (accumulated by the counter reset) + the pairs of the last counted round
+    unsigned int tot = c[2] + c[1], exact = c[12] + c[9], bad = c[10];
+    if (!filter) exact = tot;
+    sdb::profile_add_units("nms2d_clip", (double)exact);
+    sdb::profile_add_units("nms2d_fast", (double)tot);
+    g_filter_stats[0] += tot; g_filter_stats[1] += exact; g_filter_stats[2] += bad; g_filter_stats[3] += 1;
+    if (verbose) printf("NMS2D(b200): pair tests=%u, exact sweeps=%u (filter mode %d), verify mismatches=%u\n", tot, exact, filter, bad);
+  };
+
+  // ---- round 0 as full-occupancy kernels, the remaining rounds in one cooperative launch (k_tail)
+  if (g_tail_mode && NV <= 32 && filter != 2 && A.max_abs_coord <= 8191.0) {
+    static int tail_blocks = -1;
+    const size_t tsm = (size_t)8 * sizeof(sdclip::ClipSweep<NV, 1>);
+    if (tail_blocks < 0) {
+      int dev = 0, coop = 0, sms = 0, per_sm = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (coop && cudaFuncSetAttribute(k_tail<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<NV>, 256, tsm) == cudaSuccess && per_sm > 0)
+        tail_blocks = sms * std::min(per_sm, 2);
+      else { tail_blocks = 0; cudaGetLastError(); }
+    }
+    if (tail_blocks > 0) {
+      if (launch_frontier(0) || launch_pair_stage(0)) return 1;
+      TailCtx C{b_cursor.as<int2>(), b_kept.as<int>(), b_list0.as<int>(), b_list1.as<int>(), b_pairs.as<int2>(), b_xpairs.as<int2>(), b_slow.as<int2>(),
+                d_counters, (unsigned int)cap, 1, 4 * n + 8, filter};
+      void* args[] = {(void*)&A, (void*)&C};
+      sdb::ProfSpan spt;
+      sdb::profile_begin("nms2d_tail", st, &spt);
+      SDB_CUDA(cudaLaunchCooperativeKernel((const void*)k_tail<NV>, dim3(tail_blocks), dim3(256), args, tsm, st));
+      sdb::g_launch_count++;
+      sdb::profile_end("nms2d_tail", st, &spt);
+      SDB_CUDA(cudaMemcpyAsync(h_pin, d_counters, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      SDB_CUDA(cudaStreamSynchronize(st));
+      const unsigned int* c = h_pin;
+      const int r = (int)c[13];                      // round in progress when the tail kernel left (0: it never started)
+      if (verbose) printf("NMS2D(b200): tail kernel left in round %d: undecided=%u overflow=%u slow=%u\n", r, c[0], c[5], c[4]);
+      if (c[3] != 0) { sdb::set_error("nms2d: polygon clipping pools overflowed in the slow path"); return 1; }
+      if (c[5] != 0) { if (recover_overflow(c, r)) return 1; round = r + 1; }
+      else if (c[4] != 0 && r > 0) { if (launch_clip_slow()) return 1; round = r + 1; }     // (round 0 ran its slow path already)
+      else if (r > 0 && c[0] == 0) { finish_stats(c); return 0; }
+      else round = r + 1;
+      // anything else continues in the host loop below from `round`
+    }
+  }
+
   for (;;) {
     const int round0 = round;
     for (int b = 0; b < BATCH; ++b, ++round) {
-      SDB_LAUNCH(k_reset_counters, 1, 32, 0, st, d_counters);
-      {
-        // round r reads the list written by round r-1 (length saved in counters[8] by k_reset_counters)
-        int* lin = (round & 1) ? b_list1.as<int>() : b_list0.as<int>();
-        int* lout = (round & 1) ? b_list0.as<int>() : b_list1.as<int>();
-        sdb::ProfSpan spf;
-        sdb::profile_begin("nms2d_frontier", st, &spf);
-        if (round == 0) SDB_LAUNCH(k_frontier2, 148 * 8, 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)nullptr, (unsigned int)n, (const unsigned int*)nullptr, lout, d_counters);
-        else SDB_LAUNCH(k_frontier2, 148 * 8, 256, 0, st, A, round, b_cursor.as<int2>(), b_kept.as<int>(), (const int*)lin, 0u, (const unsigned int*)(d_counters + 8), lout, d_counters);
-        sdb::profile_end("nms2d_frontier", st, &spf);
-      }
+      if (launch_frontier(round)) return 1;
       if (launch_pair_stage(round)) return 1;
       SDB_CUDA(cudaMemcpyAsync(h_pin + 16 * b, d_counters, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     }
     SDB_CUDA(cudaStreamSynchronize(st));
     bool done = false;
+    const unsigned int* c_done = nullptr;
     for (int b = 0; b < BATCH; ++b) {
       const unsigned int* c = h_pin + 16 * b;
       if (c[3] != 0) { sdb::set_error("nms2d: polygon clipping pools overflowed in the slow path"); return 1; }
       if (c[5] != 0) {
-        // pair list overflowed in round round0+b: its frontier marks are in place, the later kernels of
-        // the batch were no-ops.  Grow the list, clear the flag, redo the pair stage of that round.
-        cap = (size_t)c[1] + (size_t)c[1] / 2 + 1024;
-        SDB_CUDA(b_pairs.alloc(cap * sizeof(int2), st));
-        SDB_CUDA(b_slow.alloc(cap * sizeof(int2), st));
-        if (alloc_filter_lists()) return 1;
-        const unsigned int zeros[10] = {c[0], 0, c[2], 0, 0, 0, c[6], c[7], c[8], 0};
-        SDB_CUDA(cudaMemcpyAsync(d_counters, zeros, sizeof(zeros), cudaMemcpyHostToDevice, st));
         round = round0 + b;
-        if (launch_pair_stage(round)) return 1;
-        SDB_CUDA(cudaStreamSynchronize(st));
+        if (recover_overflow(c, round)) return 1;
         round += 1;
         break;
       }
-      if (c[0] == 0) { done = true; break; }
+      if (c[0] == 0) { done = true; c_done = c; break; }
     }
     if (verbose > 1)
       for (int b = 0; b < BATCH; ++b) { const unsigned int* c = h_pin + 16 * b; printf("  round %d: undecided=%u kept=%u pairs=%u exact=%u slow=%u\n", round0 + b, c[0], c[6], c[1], c[9], c[4]); }
     if (verbose) printf("NMS2D(b200): rounds=%d undecided(last)=%u pair tests so far=%u\n", round, h_pin[16 * (BATCH - 1)], h_pin[16 * (BATCH - 1) + 2] + h_pin[16 * (BATCH - 1) + 1]);
-    if (done) {
-      // pairs tested = counters[2] (accumulated by k_reset_counters) + the pairs of the last counted rounds
-      unsigned int tot = 0, exact = 0, bad = 0;
-      for (int b = 0; b < BATCH; ++b) { const unsigned int* c = h_pin + 16 * b; tot = c[2] + c[1]; exact = c[12] + c[9]; bad = c[10]; if (c[0] == 0) break; }
-      if (!filter) exact = tot;
-      sdb::profile_add_units("nms2d_clip", (double)exact);
-      sdb::profile_add_units("nms2d_fast", (double)tot);
-      g_filter_stats[0] += tot; g_filter_stats[1] += exact; g_filter_stats[2] += bad; g_filter_stats[3] += 1;
-      if (verbose) printf("NMS2D(b200): pair tests=%u, exact sweeps=%u (filter mode %d), verify mismatches=%u\n", tot, exact, filter, bad);
-      break;
-    }
+    if (done) { finish_stats(c_done); break; }
     if (round > 4 * n + 8) { sdb::set_error("nms2d: no progress"); return 1; }
   }
   return 0;

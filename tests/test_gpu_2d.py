@@ -409,3 +409,43 @@ def test_predict_instances_with_device_normaliser_and_scale_equals_host_path(sd,
             assert abs(len(rd['prob']) - len(rh['prob'])) <= 2 and np.mean(ld != lh) < 2e-3
         else:
             assert np.array_equal(ld, lh) and np.array_equal(rd['points'], rh['points']) and np.array_equal(rd['coord'], rh['coord'])
+
+
+def test_polygon_order_property_through_product(sd):
+    """the reference's test_polygon_order_2D (tests/test_big.py:202-214): with nms_thresh=0 no survivor is occluded, so the
+    pixels labelled i are exactly polygon i rendered on its own.  (The single-polygon raster rule itself restates
+    skimage.draw.polygon, which is not installable here: 2-D label painting stays 'parity unpinned', see README / DESIGN.)"""
+    import bench_data
+    from stardist_b200.geometry.geom2d import polygons_to_label_coord
+    cfg = sd.Config2D(n_rays=32)
+    model = sd.StarDist2D(cfg, name=None, basedir=None, weights=bench_data.bench_weights_2d(cfg))
+    img, _ = bench_data.synthetic_image((384, 416), seed=9)
+    labels, polys = model.predict_instances(img, nms_thresh=0)
+    assert len(polys['coord']) > 30
+    for i, coord in enumerate(polys['coord'], start=1):
+        alone = polygons_to_label_coord(coord[None], shape=labels.shape)
+        assert np.array_equal(alone > 0, labels == i), i
+
+
+@pytest.mark.parametrize("n,R,radius,noise,thr,seed", [(20000, 32, 8, .2, .4, 0), (3000, 32, 1.5, .9, .3, 2), (40000, 32, 10, .1, .4, 5),
+                                                       (6000, 16, 9, .3, .2, 6)])
+def test_nms2d_tail_kernel_equals_host_rounds_and_reference(sd, n, R, radius, noise, thr, seed):
+    """frontier rounds >= 1 inside one cooperative kernel (k_tail, on-device termination) vs the host-driven rounds vs the
+    reference C++: identical keep masks; the small initial pair list forces the overflow / hand-back path as well"""
+    from stardist_b200 import _lib
+    from stardist_b200.lib.stardist2d import c_non_max_suppression_inds
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    pts = rng.integers(0, 400, (n, 2)).astype(np.float32)
+    dist = np.maximum(np.float32(1e-3), (radius * (1 + noise * rng.uniform(-1, 1, (n, R)))).astype(np.float32))
+    want = ref_ext.stardist2d().c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr)) if ref_ext.available() else None
+    try:
+        lib.sdb_nms2d_set_tail(0)
+        host = c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr))
+        lib.sdb_nms2d_set_tail(1)
+        tail = c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr))
+    finally:
+        lib.sdb_nms2d_set_tail(1)
+    assert np.array_equal(tail, host)
+    if want is not None:
+        assert np.array_equal(tail, want)
