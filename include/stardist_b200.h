@@ -122,6 +122,9 @@ int sdb_polyhedron_to_label(const float* d_dist, const float* d_points, const fl
                             int use_overlap_label, int overlap_label, int* d_result,
                             sdb_stream_t stream);
 
+/* sphere culling of bounding-box voxels in the 3-D label rendering (1 = default); label maps are identical either way */
+int sdb_label3d_set_cull(int on);
+
 /* k_heavy volume stages (S3 kernel / S4 hull intersection): 0 (default) = per-(k, j) plane scaling as validated on B200,
  * 1 = planes scaled once per pair + early-out for non-cutting planes (sd3::face_cone_volume_n; bit-identical results on the
  * host build, not yet run on a GPU -- experimental until then). */

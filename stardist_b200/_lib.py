@@ -32,6 +32,8 @@ def _declare(lib):
     lib.sdb_paint_order_2d.restype = c_int
     lib.sdb_nms2d_set_filter.argtypes = [c_int]
     lib.sdb_nms2d_set_filter.restype = c_int
+    lib.sdb_label3d_set_cull.argtypes = [c_int]
+    lib.sdb_label3d_set_cull.restype = c_int
     lib.sdb_nms2d_set_tail.argtypes = [c_int]
     lib.sdb_nms2d_set_tail.restype = c_int
     lib.sdb_nms2d_filter_stats.argtypes = [POINTER(ctypes.c_ulonglong), c_int]

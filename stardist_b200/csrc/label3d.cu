@@ -29,6 +29,7 @@ namespace {
 using sdb::cdiv;
 constexpr int MAXR = sd3::SD3_MAX_RAYS, MAXF = sd3::SD3_MAX_FACES;
 constexpr int RANK_NONE = 0x7fffffff;
+__device__ int g_cull3d = 1;      // sphere culling in k_paint3d (sdb_label3d_set_cull; results identical)
 
 struct PaintArgs {
   const float* dist; const float* points; const float* verts; const int* faces;
@@ -93,6 +94,35 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
       sd3::build_halfspace(&pv[3 * sfaces[3 * f]], &pv[3 * sfaces[3 * f + 1]], &pv[3 * sfaces[3 * f + 2]], &hs[4 * f]);
   }
   __syncthreads();
+  // Sphere culling of the bounding box (render modes "full" / "kernel"), exactness preserving by margin:
+  //  * a voxel farther from the centre than every vertex (+ margin) lies outside the polyhedron -- every tetrahedron
+  //    (centre, A, B, C) is inside that ball -- so the kernel planes and the float determinants reject it anyway;
+  //  * a voxel inside the ball inscribed in the kernel planes (the planes as built above, in double; - margin) satisfies
+  //    every plane inequality, i.e. point_in_halfspaces(kernel) is true and the voxel is labelled in both modes.
+  // The margins (1e-3 relative + 0.05 voxel) are ~1e4 x the rounding of the tests they short-cut.  Switched off for
+  // polyhedra with a near-degenerate face (|normal| < 1e-6 r^2), where the determinant signs are noise-dominated.
+  __shared__ double cull_out2, cull_in2;
+  if (threadIdx.x == 0) {
+    double r2 = 0, rho = 1e300, nmin = 1e300;
+    for (int j = 0; j < A.n_rays; ++j) {
+      const double a = (double)pv[3 * j] - center[0], b = (double)pv[3 * j + 1] - center[1], c = (double)pv[3 * j + 2] - center[2];
+      r2 = fmax(r2, a * a + b * b + c * c);
+    }
+    if (A.mode <= 1) {
+      for (int f = 0; f < A.n_faces; ++f) {
+        const double nn = sqrt(hs[4 * f] * hs[4 * f] + hs[4 * f + 1] * hs[4 * f + 1] + hs[4 * f + 2] * hs[4 * f + 2]);
+        const double v = hs[4 * f] * center[0] + hs[4 * f + 1] * center[1] + hs[4 * f + 2] * center[2] + hs[4 * f + 3];
+        nmin = fmin(nmin, nn);
+        rho = fmin(rho, nn > 0 ? -v / nn : -1.0);
+      }
+    }
+    const double r = sqrt(r2);
+    const bool ok = g_cull3d && A.mode <= 1 && nmin >= 1e-6 * r2 && r2 > 0;
+    const double ro = r * 1.001 + 0.05, ri = rho * 0.999 - 0.05;
+    cull_out2 = ok ? ro * ro : 1e300;
+    cull_in2 = (ok && ri > 0) ? ri * ri : -1.0;
+  }
+  __syncthreads();
   const int bz = bbox[1] - bbox[0] + 1, by = bbox[3] - bbox[2] + 1, bx = bbox[5] - bbox[4] + 1;
   if (bz <= 0 || by <= 0 || bx <= 0) return;
   const long long nvox = (long long)bz * by * bx;
@@ -100,12 +130,19 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
     const int x = bbox[4] + (int)(q % bx), y = bbox[2] + (int)((q / bx) % by), z = bbox[0] + (int)(q / ((long long)bx * by));
     const float fz = (float)z, fy = (float)y, fx = (float)x;
     bool inside = false;
+    {
+      const double a = (double)z - center[0], b = (double)y - center[1], c = (double)x - center[2];
+      const double d2 = a * a + b * b + c * c;
+      if (d2 > cull_out2) continue;
+      if (d2 < cull_in2) inside = true;
+    }
     auto in_planes = [&](int cnt) {
       for (int f = 0; f < cnt; ++f)
         if (hs[4 * f] * fz + hs[4 * f + 1] * fy + hs[4 * f + 2] * fx + hs[4 * f + 3] > 0) return false;
       return true;
     };
-    if (A.mode == 0) inside = in_planes(A.n_faces) || sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces);
+    if (inside) { /* inside the kernel's inscribed ball: labelled in modes "full" and "kernel" */ }
+    else if (A.mode == 0) inside = in_planes(A.n_faces) || sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces);
     else if (A.mode == 1) inside = in_planes(A.n_faces);
     else if (A.mode == 2) inside = (n_hull >= 4) && in_planes(n_hull);
     else if (A.mode == 3) inside = true;
@@ -231,6 +268,13 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
   }
   SDB_LAUNCH(k_finalize3d, fb, 256, 0, st, d_result, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
              render_mode == 4 ? b_debug.as<int>() : nullptr, nvox, d_labels, use_overlap_label, overlap_label, render_mode);
+  return 0;
+}
+
+// sphere culling of the bounding-box voxels in k_paint3d: 1 (default) on, 0 off -- identical label maps (tests)
+extern "C" int sdb_label3d_set_cull(int on) {
+  const int v = on ? 1 : 0;
+  SDB_CUDA(cudaMemcpyToSymbol(g_cull3d, &v, sizeof(int)));
   return 0;
 }
 

@@ -483,3 +483,32 @@ def test_tied_scores_sparse_equals_dense_3d(sd):
     from stardist_b200.matching import relabel_sequential
     want = relabel_sequential(polyhedron_to_label(r_sparse['dist'], r_sparse['points'], rays, shape, prob=r_sparse['prob'], verbose=False))[0]
     assert len(r_sparse['prob']) == 5 and np.array_equal(l_sparse, want)
+
+
+def test_paint3d_sphere_culling_is_result_neutral(sd):
+    """k_paint3d skips bounding-box voxels outside the vertex ball / inside the kernel's inscribed ball (margins far above
+    the rounding of the tests they short-cut): label maps with and without the culling are identical, incl. degenerate
+    polyhedra (rays clamped to 1e-3), strong anisotropy and the reference's lattice-aligned test shapes"""
+    from stardist_b200 import _lib
+    from stardist_b200.lib.stardist3d import c_polyhedron_to_label
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    shape = (36, 48, 52)
+    sets = []
+    for n_rays, aniso in ((32, None), (96, (2, 1, 1)), (64, (1, 1.5, 4))):
+        rays, d, p = _random_polyhedra(rng, 50, n_rays, shape, aniso)
+        d2 = d.copy(); d2[rng.random(d2.shape) < 0.3] = 1e-3          # spikes / collapsed rays
+        d3 = np.full_like(d, 5.0)                                       # lattice aligned
+        sets += [(rays, d, p), (rays, d2, p), (rays, d3, p), (rays, (d * 0.05).astype(np.float32), p)]
+    for rays, d, p in sets:
+        v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
+        lab = np.arange(1, len(d) + 1, dtype=np.int32)
+        for mode, ov in ((0, 0), (1, 0), (0, 1)):
+            try:
+                lib.sdb_label3d_set_cull(0)
+                a = c_polyhedron_to_label(d, p, v, f, lab, mode, 0, ov, -1, shape)
+                lib.sdb_label3d_set_cull(1)
+                b = c_polyhedron_to_label(d, p, v, f, lab, mode, 0, ov, -1, shape)
+            finally:
+                lib.sdb_label3d_set_cull(1)
+            assert np.array_equal(a, b), (mode, ov, int((a != b).sum()))
