@@ -233,6 +233,10 @@ def main():
     from stardist_b200 import Config2D, StarDist2D, StarDist3D, _lib
     import bench_data
     warm = max(3, args.warmup)
+    if os.environ.get("STARDIST_B200_NMS3D_VARIANT"):
+        _lib.load().sdb_nms3d_set_variant(int(os.environ["STARDIST_B200_NMS3D_VARIANT"]))
+    if os.environ.get("STARDIST_B200_NMS2D_TAIL"):
+        _lib.load().sdb_nms2d_set_tail(int(os.environ["STARDIST_B200_NMS2D_TAIL"]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -306,7 +310,7 @@ def main():
     dev_ms, n_inst, n_cand, stage = time_device(model, x_dev, SHAPE, PROB_THRESH, NMS_THRESH, args.steps)
     launches = _lib.launch_count()
     prof_conv = _lib.profile_get("conv_tc")
-    prof_nms = {k: _lib.profile_get("nms2d_" + k) for k in ("frontier", "pairs", "fast", "clip")}
+    prof_nms = {k: _lib.profile_get("nms2d_" + k) for k in ("frontier", "pairs", "fast", "clip", "tail")}
     _lib.profile_enable(False)
     barrier()
     (dev_ms_max, _, _), (_, n_total, _) = reduce_max_sum([dev_ms, float(n_inst), 0.0])

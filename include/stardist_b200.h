@@ -129,6 +129,10 @@ int sdb_label3d_set_cull(int on);
  * 1 = planes scaled once per pair + early-out for non-cutting planes (sd3::face_cone_volume_n; bit-identical results on the
  * host build, not yet run on a GPU -- experimental until then). */
 int sdb_nms3d_set_variant(int norm_planes);
+/* 1 (default): a rigorous lower bound of the kernel-intersection volume (ray-wise distances to the 2F planes from the centre
+ * midpoint, fan of tetrahedra) decides `iou > threshold` of stage S3 before the volume itself is computed; 0: always the
+ * volume.  Decisions are identical (margin 1e-5 relative). */
+int sdb_nms3d_set_s3_bound(int on);
 
 /* relabel_sequential on a device label map (stardist/matching.py:319-406; callers model3d.py:645, base.py:959):
  * labels occurring in d_labels[n] (values in [0, max_label], 16-byte aligned) are renumbered offset, offset+1, ...

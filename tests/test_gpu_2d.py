@@ -314,14 +314,14 @@ def test_anisotropic_grid_vs_oracle(sd, grid):
     assert len(res['prob']) > 0 and np.array_equal(res['points'], ref['points']) and np.array_equal(labels, ref_labels)
 
 
-def test_unnormalised_uint16_input_does_not_overflow_silently(sd):
+def test_unnormalised_input_does_not_overflow_silently(sd):
     """raw 16-bit input drives activations past the fp16 range of the tensor-core representation; the pass must be
     repeated on the fp32 kernels (with a warning) and give the finite maps of the fp32 reference network"""
     import torch, warnings
     cfg = sd.Config2D(n_rays=32)
     model = sd.StarDist2D(cfg, name=None, basedir=None)
     rng = np.random.default_rng(6)
-    img = rng.integers(0, 65535, (64, 96)).astype(np.uint16)
+    img = (rng.integers(0, 65535, (64, 96)).astype(np.float32) * 64)         # e.g. a 22-bit sensor / un-normalised float data
     with warnings.catch_warnings(record=True) as wlist:
         warnings.simplefilter("always")
         prob, dist = model.predict(img)

@@ -111,3 +111,12 @@ def test_device_nms3d_fuzz_vs_reference(sd, case):
     got = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
     assert len(d) > 200
     assert np.array_equal(got, want), "%d of %d decisions differ" % (int((got != want).sum()), len(d))
+    # the S3 lower-bound short cut off: same decisions
+    from stardist_b200 import _lib
+    lib = _lib.load()
+    try:
+        lib.sdb_nms3d_set_s3_bound(0)
+        got0 = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
+    finally:
+        lib.sdb_nms3d_set_s3_bound(1)
+    assert np.array_equal(got0, want)
