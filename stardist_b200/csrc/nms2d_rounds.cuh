@@ -46,7 +46,7 @@ __device__ int pair_suppresses(const NmsArrays& A, int h, int c, sdclip::ClipSwe
 // no __restrict__ / const-cache qualifiers: inside k_tail they are re-read after grid-wide barriers)
 __device__ __forceinline__ void d_frontier2(const NmsArrays& A, int round, int2* cursor, int* kept_list,
                             const int* list_in, unsigned int n_in_or_all, const unsigned int* n_in_dev,
-                            int* list_out, unsigned int* counters) {
+                            int* list_out, unsigned int* counters, const int* pend = nullptr) {
   // one WARP per undecided candidate: the neighbourhood scan is a chain of dependent loads, so the lanes
   // test 32 list items per step (a kept candidate scans its whole 3x3 neighbourhood: ~2000 items)
   if (counters[5]) return;
@@ -120,6 +120,9 @@ __device__ __forceinline__ void d_frontier2(const NmsArrays& A, int round, int2*
     }
     if (lane == 0) {
       cursor[c] = cur;
+      // (k_tail only) a candidate with open pairs -- tests against kept polygons the pre-filter left to the exact sweep,
+      // not yet run -- stays undecided: it keeps blocking what it reaches and is looked at again after the next flush
+      if (!blocked && pend && pend[c] > 0) blocked = true;
       if (!blocked) {
         A.state[c] = kept_now;
         kept_list[atomicAdd(&counters[6], 1u)] = c;
@@ -195,7 +198,8 @@ __global__ void k_check_overflow(unsigned int cap, unsigned int* __restrict__ co
 // integral and its bound decide most pairs, the rest is appended to the exact list (counters[9]).
 // verify != 0: nothing is decided here, the verdict is stored per pair for k_clip to compare.
 template <typename T>
-__device__ __forceinline__ void d_fast(const NmsArrays& A, const int2* pairs, int2* xpairs, signed char* verdict, int verify, unsigned int* counters) {
+__device__ __forceinline__ void d_fast(const NmsArrays& A, const int2* pairs, int2* xpairs, signed char* verdict, int verify, unsigned int* counters,
+                                       int* pend = nullptr) {
   if (counters[5]) return;
   const unsigned int n_pairs = counters[1];
   const unsigned int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
@@ -272,7 +276,7 @@ __device__ __forceinline__ void d_fast(const NmsArrays& A, const int2* pairs, in
       const int d = overflow ? -1 : sdfast::decide(I, bound, den, A.threshold);
       if (verify) verdict[w] = (signed char)d;
       else if (d == 1) A.state[c] = ST_SUPPRESSED;
-      else if (d < 0) xpairs[atomicAdd(&counters[9], 1u)] = pr;
+      else if (d < 0) { xpairs[atomicAdd(&counters[9], 1u)] = pr; if (pend) atomicAdd(&pend[c], 1); }
     }
   }
 }
@@ -291,7 +295,7 @@ template <int NV> struct ClipCfg { static constexpr int WARPS = (NV <= 32) ? 4 :
 
 template <int NV>
 __device__ __forceinline__ void d_clip(const NmsArrays& A, const int2* pairs, const unsigned int* n_list, const signed char* verdict,
-                                       int2* slow_pairs, unsigned int* counters, unsigned char* clip_smem) {
+                                       int2* slow_pairs, unsigned int* counters, unsigned char* clip_smem, int* pend = nullptr) {
   if (counters[5]) return;
   const unsigned int n_pairs = *n_list;
   const unsigned int G = (gridDim.x * blockDim.x) >> 5;                       // warps in the grid
@@ -300,6 +304,7 @@ __device__ __forceinline__ void d_clip(const NmsArrays& A, const int2* pairs, co
   sdclip::ClipSweep<NV, 1>& S = *reinterpret_cast<sdclip::ClipSweep<NV, 1>*>(clip_smem + (size_t)(threadIdx.x >> 5) * sizeof(sdclip::ClipSweep<NV, 1>));
   for (unsigned int t = warp_g; t < n_pairs; t += G) {
     const int2 pr = pairs[t];
+    if (pend) atomicSub(&pend[pr.y], 1);                             // this open pair is resolved by the end of the phase
     if (!verdict && A.state[pr.y] == ST_SUPPRESSED) continue;        // already suppressed by another pair (benign race)
     const int r = pair_suppresses<NV, 1>(A, pr.x, pr.y, S);
     if (r == 1) A.state[pr.y] = ST_SUPPRESSED;
@@ -351,9 +356,10 @@ __global__ void k_reset_counters(unsigned int* counters) {
 // (which knows how to grow the pair list / run the slow exact path) by leaving: counters[5] set (pair list overflow),
 // counters[4] != 0 (pairs for the slow path) or simply counters[0] != 0 after max_rounds; counters[13] = round in progress.
 struct TailCtx {
-  int2* cursor; int* kept; int* list0; int* list1; int2* pairs; int2* xpairs; int2* slow;
+  int2* cursor; int* kept; int* list0; int* list1; int2* pairs; int2* xpairs; int2* slow; int* pend;
   unsigned int* counters; unsigned int cap; int round0, max_rounds, filter;
 };
+constexpr unsigned int TAIL_FLUSH_MIN = 1024;     // open pairs that make an exact-sweep phase worth its ~0.2 ms latency
 
 template <int NV>
 __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
@@ -364,26 +370,59 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
   volatile unsigned int* vc = cnt;
   if (vc[5] || vc[3] || vc[4]) return;                  // round 0 left work for the host (uniform: nothing writes before the first barrier)
   const bool lead = blockIdx.x == 0 && threadIdx.x == 0;
+  // The exact sweep costs ~0.2 ms of pure latency per phase whatever the number of pairs (one 3e4-instruction dependent
+  // chain per pair).  With the pre-filter on, pairs it leaves open are therefore DEFERRED: the candidate is marked pending
+  // (d_frontier2 will not keep it, it goes on blocking what it reaches) and the open pairs of several rounds are swept
+  // together -- when enough have accumulated, when the frontier cannot advance without them, or before leaving.
+  int* pend = C.filter == 1 ? C.pend : nullptr;
   for (int round = C.round0; round < C.round0 + C.max_rounds; ++round) {
-    if (lead) { d_reset_counters(cnt); cnt[13] = (unsigned int)round; }
+    if (lead) {
+      cnt[2] += cnt[1]; cnt[0] = 0; cnt[1] = 0; cnt[4] = 0; cnt[6] = 0; cnt[8] = cnt[7]; cnt[7] = 0;      // d_reset_counters without the open list
+      if (!pend) { cnt[12] += cnt[9]; cnt[9] = 0; }
+      cnt[13] = (unsigned int)round;
+    }
     grid.sync();
     int* lin = (round & 1) ? C.list1 : C.list0;
     int* lout = (round & 1) ? C.list0 : C.list1;
-    d_frontier2(A, round, C.cursor, C.kept, lin, 0u, cnt + 8, lout, cnt);
+    d_frontier2(A, round, C.cursor, C.kept, lin, 0u, cnt + 8, lout, cnt, pend);
     grid.sync();
-    if (vc[0] == 0) break;                                // no undecided candidate was left: done
+    if (vc[0] == 0) break;                                // no undecided candidate was left: done (nothing can be pending)
+    bool leave = false;
     d_pairs(A, round, C.kept, C.pairs, C.cap, cnt);
     grid.sync();
-    if (vc[1] > C.cap) { if (lead) cnt[5] = 1; break; }   // pair list overflow: the host grows it and redoes this round's pair stage
+    // pair list overflow: the host grows it and redoes this round's pair stage (the flag is raised on the way out, after
+    // the open pairs have been swept: every phase is a no-op once counters[5] is set)
+    const bool overflow = vc[1] > C.cap;
     if (C.filter == 1) {
-      d_fast<int32_t>(A, C.pairs, C.xpairs, nullptr, 0, cnt);
-      grid.sync();
-      d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem);
+      if (!overflow && vc[9] + vc[1] > C.cap) {           // the open list could overflow: sweep what is there first
+        d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
+        grid.sync();
+        if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
+        grid.sync();
+      }
+      if (!overflow) {
+        d_fast<int32_t>(A, C.pairs, C.xpairs, nullptr, 0, cnt, pend);
+        grid.sync();
+      }
+      // flush: enough open pairs, or no candidate was kept in this round (the frontier is waiting for them), or leaving
+      const bool must_leave = overflow || vc[4] != 0;
+      const unsigned int n_open = vc[9];
+      if (n_open > 0 && (must_leave || n_open >= TAIL_FLUSH_MIN || vc[6] == 0)) {
+        d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
+        grid.sync();
+        if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
+        grid.sync();
+      }
+      leave = must_leave || vc[4] != 0;                   // (a flush that produced slow pairs has swept everything: nothing is pending)
     } else {
-      d_clip<NV>(A, C.pairs, cnt + 1, nullptr, C.slow, cnt, tail_smem);
+      if (!overflow) {
+        d_clip<NV>(A, C.pairs, cnt + 1, nullptr, C.slow, cnt, tail_smem);
+        grid.sync();
+      }
+      leave = overflow || vc[4] != 0;                     // pool overflow in the fast sweep: slow exact path on the host loop
     }
-    grid.sync();
-    if (vc[4] != 0) break;                                // pool overflow in the fast sweep: slow exact path on the host loop
+    if (overflow && lead) cnt[5] = 1;
+    if (leave) break;
   }
 }
 
@@ -491,8 +530,11 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     }
     if (tail_blocks > 0) {
       if (launch_frontier(0) || launch_pair_stage(0)) return 1;
+      sdb::DevBuf b_pend;
+      SDB_CUDA(b_pend.alloc((size_t)n * sizeof(int), st));
+      SDB_CUDA(cudaMemsetAsync(b_pend.p, 0, (size_t)n * sizeof(int), st));
       TailCtx C{b_cursor.as<int2>(), b_kept.as<int>(), b_list0.as<int>(), b_list1.as<int>(), b_pairs.as<int2>(), b_xpairs.as<int2>(), b_slow.as<int2>(),
-                d_counters, (unsigned int)cap, 1, 4 * n + 8, filter};
+                b_pend.as<int>(), d_counters, (unsigned int)cap, 1, 4 * n + 8, filter};
       void* args[] = {(void*)&A, (void*)&C};
       sdb::ProfSpan spt;
       sdb::profile_begin("nms2d_tail", st, &spt);
