@@ -162,6 +162,13 @@ int sdb_gather_candidates(const float* d_dist, const int* d_index, int n, int n_
                           const int* shape, const int* grid, float* d_out_dist,
                           float* d_out_points, sdb_stream_t stream);
 
+/* sparse candidate store (large volumes: the dense dist map is never written, SURVEY H7 / base.py:580-593) */
+int sdb_count_above(const float* d_prob, long long n, float thresh, int* h_count, sdb_stream_t stream);
+int sdb_store_rows_above(const float* d_prob, const float* d_dist, long long n, int n_rays, float thresh, long long flat0,
+                         int row0, int capacity, float* d_store, int* d_slot, sdb_stream_t stream);
+int sdb_gather_candidates_slots(const float* d_store, const int* d_slot, const int* d_index, int n, int n_rays, int ndim,
+                                const int* shape, const int* grid, float* d_out_dist, float* d_out_points, sdb_stream_t stream);
+
 /* ---- U-Net forward building blocks (NHWC float32; see stardist_b200/csrc/unet*.cu) ---- */
 
 /* 3x3 'same' convolution + bias + optional ReLU.  The input may be the channel concatenation

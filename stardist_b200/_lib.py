@@ -89,6 +89,12 @@ def _declare(lib):
     lib.sdb_relabel_sequential.argtypes = [P, c_longlong, c_int, c_int, P, POINTER(c_int), P]
     lib.sdb_relabel_sequential.restype = c_int
     lib.sdb_nms3d.argtypes = [P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_count_above.argtypes = [P, c_longlong, c_float, POINTER(c_int), P]
+    lib.sdb_count_above.restype = c_int
+    lib.sdb_store_rows_above.argtypes = [P, P, c_longlong, c_int, c_float, c_longlong, c_int, c_int, P, P, P]
+    lib.sdb_store_rows_above.restype = c_int
+    lib.sdb_gather_candidates_slots.argtypes = [P, P, P, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), P, P, P]
+    lib.sdb_gather_candidates_slots.restype = c_int
     lib.sdb_select_ranks.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_longlong), c_int, POINTER(c_float), P]
     lib.sdb_select_ranks.restype = c_int
     lib.sdb_normalize_mi_ma.argtypes = [P, c_longlong, c_float, c_float, c_int, P]

@@ -463,7 +463,18 @@ class StarDistBase:
             prob_thresh = self.thresholds.prob
         grid = tuple(self.config.grid)
         self._mark('net_begin')
-        prob_d, dist_d = self.predict_direct_device(x_dev, n_tiles)
+        sparse_store = None
+        if self._use_sparse_forward(x_dev, n_tiles):
+            # large volumes: features + heads slab by slab, only the dist rows above the threshold are kept
+            try:
+                prob_d, store_d, slot_d = self.net.forward_candidates(x_dev, np.float32(prob_thresh))
+                prob_d, dist_d, sparse_store = prob_d[0], None, (store_d, slot_d)
+                self._last, self._last_class = (prob_d, None), None
+            except L.StarDistB200Error as e:
+                if 'fp16 overflow' not in str(e):
+                    raise
+        if sparse_store is None:
+            prob_d, dist_d = self.predict_direct_device(x_dev, n_tiles)
         self._mark('net_end')
         nd = self.config.n_dim
         R = self.config.n_rays
@@ -488,14 +499,31 @@ class StarDistBase:
         sidx, sprob = sidx[:n], sprob[:n]
         dist_s = torch.empty((n, R), dtype=torch.float32, device=prob_d.device)
         pts_f = torch.empty((n, nd), dtype=torch.float32, device=prob_d.device)
-        L.check(lib.sdb_gather_candidates(L.ptr(dist_d), L.ptr(sidx), n, R, nd, L.iarr(shape), L.iarr(grid),
-                                         L.ptr(dist_s), L.ptr(pts_f), L.stream_ptr()))
+        if sparse_store is not None:
+            L.check(lib.sdb_gather_candidates_slots(L.ptr(sparse_store[0]), L.ptr(sparse_store[1]), L.ptr(sidx), n, R, nd, L.iarr(shape), L.iarr(grid),
+                                                   L.ptr(dist_s), L.ptr(pts_f), L.stream_ptr()))
+        else:
+            L.check(lib.sdb_gather_candidates(L.ptr(dist_d), L.ptr(sidx), n, R, nd, L.iarr(shape), L.iarr(grid),
+                                             L.ptr(dist_s), L.ptr(pts_f), L.stream_ptr()))
         self._mark('cand_end')
         cand = dict(prob=sprob, dist=dist_s, points_f32=pts_f, n=n)
         if self._is_multiclass():                           # prob_class[inds] of the candidates, base.py:595-614
             pc = self._last_class
             cand['prob_class'] = pc.reshape(-1, pc.shape[-1]).index_select(0, sidx.long())
         return cand
+
+    def _use_sparse_forward(self, x_dev, n_tiles):
+        """slab-wise sparse forward (UNetDevice3DTC.forward_candidates): STARDIST_B200_SPARSE_FORWARD = 1 / 0 / auto
+        (default: volumes of 2^24 voxels and more, where features + dense dist would take tens of GB)"""
+        import os
+        mode = os.environ.get("STARDIST_B200_SPARSE_FORWARD", "auto")
+        if mode == "0" or not hasattr(self.net, 'forward_candidates') or self._is_multiclass():
+            return False
+        if n_tiles is not None and int(np.prod(n_tiles)) > 1:
+            return False
+        if tuple(self.config.grid) != (1,) * self.config.n_dim or x_dev.shape[0] != 1:
+            return False
+        return mode == "1" or int(np.prod(x_dev.shape[1:-1])) >= (1 << 24)
 
     def predict_instances_device(self, x_dev, img_shape, prob_thresh=None, nms_thresh=None, return_labels=True, **nms_kwargs):
         """predict_instances for an input that is already resident in HBM (padded, normalized,

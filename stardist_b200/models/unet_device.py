@@ -405,7 +405,7 @@ class UNetDevice3DTC:
                 and config.net_conv_after_unet % 64 == 0 and config.net_conv_after_unet > 0 and config.n_rays + 1 <= 144
                 and config.unet_activation in ('relu', 'linear') and config.unet_last_activation in ('relu', 'linear'))
 
-    def _forward_tc(self, x):
+    def _forward_tc(self, x, stop_before_features=False):
         lib = L.load()
         assert x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and x.dim() == 5
         if x.shape[0] != 1:
@@ -434,7 +434,10 @@ class UNetDevice3DTC:
                     _, d, h, w, c1 = cur.shape
                     c0 = 0 if lo is None else lo.shape[-1]
                     od, oh, ow = (2 * d, 2 * h, 2 * w) if up2x else (d, h, w)
-                    if l['name'] == 'features': base = cur
+                    if l['name'] == 'features':
+                        base = cur
+                        if stop_before_features and lo is None:
+                            return cur, ent, relu                      # forward_candidates runs features + heads slab by slab
                     out = torch.empty((2, od, oh, ow, cout), dtype=torch.float16, device=x.device)
                     ws = ent['split']
                     L.check(lib.sdb_conv3x3x3_tc(L.ptr(lo[0]) if lo is not None else L.ptr(None), L.ptr(lo[1]) if lo is not None else L.ptr(None), c0,
@@ -469,6 +472,59 @@ class UNetDevice3DTC:
             L.check(lib.sdb_merge_split(L.ptr(base[0]), L.ptr(base[1]), b32.numel(), L.ptr(b32), st))
             self.prob_class = self._simt._class_branch(b32)
         return prob, dist
+
+    def forward_candidates(self, x, prob_thresh, slab=16):
+        """Sparse forward pass for large volumes (the reference's own per-tile sparse gather base.py:580-593):
+        the 128-channel `features` map (17 GB at 128x512x512) and the dense dist map (12.9 GB) are never materialised.
+        The last two layers run over z-slabs of `slab` planes (+1 halo plane each side for the 3x3x3 convolution); of every
+        slab only the prob planes (into the full prob map) and the dist rows of voxels with prob > prob_thresh (into a compact
+        store) survive.  Returns (prob [1,D,H,W], store [n_rows,R] float32, slot int32[D*H*W]) with store[slot[flat]] =
+        dist row of voxel `flat` for every voxel above the threshold; values are those of forward() (same kernels)."""
+        import ctypes
+        lib = L.load()
+        st = L.stream_ptr()
+        r = self._forward_tc(x, stop_before_features=True)
+        if not (isinstance(r, tuple) and len(r) == 3 and isinstance(r[1], dict)):
+            raise NotImplementedError("forward_candidates: architecture without a plain `features` layer")
+        cur, ent, relu = r
+        _, D, H, W, c1 = cur.shape
+        R = self.config.n_rays
+        cf = int(ent['k'].shape[-1])
+        ws = ent['split']
+        dev = x.device
+        prob = torch.empty((1, D, H, W), dtype=torch.float32, device=dev)
+        slot = torch.empty(D * H * W, dtype=torch.int32, device=dev)
+        thr = float(np.float32(prob_thresh))
+        stores, rows = [], 0
+        plane = H * W
+        feat = torch.empty((2, min(D, slab + 2), H, W, cf), dtype=torch.float16, device=dev)
+        dist_slab = torch.empty((min(D, slab), H, W, R), dtype=torch.float32, device=dev)
+        for z0 in range(0, D, slab):
+            s = min(slab, D - z0)
+            za, zb = max(0, z0 - 1), min(D, z0 + s + 1)
+            sd = zb - za
+            f = feat[:, :sd]
+            if sd != feat.shape[1]:
+                f = torch.empty((2, sd, H, W, cf), dtype=torch.float16, device=dev)
+            L.check(lib.sdb_conv3x3x3_tc(L.ptr(None), L.ptr(None), 0, L.ptr(cur[0, za:zb]), L.ptr(cur[1, za:zb]), c1, sd, H, W,
+                                         L.ptr(ws[0]), L.ptr(ws[1]), ent['scale'], L.ptr(ent['b']), cf, relu, 0, L.ptr(f[0]), L.ptr(f[1]), st))
+            o = z0 - za
+            pslab = prob[0, z0:z0 + s]
+            L.check(lib.sdb_heads_tc(L.ptr(f[0, o:o + s]), L.ptr(f[1, o:o + s]), cf, 1, s * H, W, L.ptr(self.heads_w[0]), L.ptr(self.heads_w[1]),
+                                    self.heads_scale, L.ptr(self.heads_b), self.heads_np, R, L.ptr(pslab), L.ptr(dist_slab), st))
+            cnt = ctypes.c_int(0)
+            L.check(lib.sdb_count_above(L.ptr(pslab), s * plane, thr, ctypes.byref(cnt), st))
+            n = int(cnt.value)
+            if n > 0:
+                store = torch.empty((n, R), dtype=torch.float32, device=dev)
+                L.check(lib.sdb_store_rows_above(L.ptr(pslab), L.ptr(dist_slab), s * plane, R, thr, z0 * plane, rows, n, L.ptr(store), L.ptr(slot), st))
+                # rows of this slab are numbered from `rows` in the concatenated store; the kernel numbers them from 0
+                stores.append(store)
+                rows += n
+        L.check(lib.sdb_tc_error_check(st))
+        self.prob_class = None
+        store = torch.cat(stores) if stores else torch.empty((0, R), dtype=torch.float32, device=dev)
+        return prob, store, slot
 
 
 def _forward_guarded(self, x):
