@@ -661,8 +661,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       SDB_CUDA(cudaMemcpyAsync(b_counters.as<unsigned int>() + 1, &zero, 4, cudaMemcpyHostToDevice, st));
     }
     if (rc) break;
-    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u, convex %u, render %u so far)\n",
-                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[6], h_pin[7]);
+    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u [decided by the lower bound: %u], convex %u, render %u so far)\n",
+                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[3], h_pin[6], h_pin[7]);
     if (h_pin[0] == 0) break;
     if (round > 4 * n + 8) { sdb::set_error("nms3d: no progress"); rc = 1; break; }
   }

@@ -27,7 +27,7 @@ def _virtual_index(n, p, dt):
         return int(vi), int(vi), None
     prev, nxt = F._get_indexes(np.empty(n, np.bool_), vi, n)
     gamma = F._get_gamma(vi, prev, F._QuantileMethods['linear'])
-    return int(prev), int(nxt), gamma
+    return int(prev) % n, int(nxt) % n, gamma          # numpy addresses the last element as -1 at the upper bound
 
 
 def percentiles_device(x_dev, valid_shape, ps, src_dtype):
