@@ -376,12 +376,16 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
   // together -- when enough have accumulated, when the frontier cannot advance without them, or before leaving.
   int* pend = C.filter == 1 ? C.pend : nullptr;
   for (int round = C.round0; round < C.round0 + C.max_rounds; ++round) {
+    // barrier BEFORE the counters are reset: the decisions at the end of the previous round (flush / leave) read
+    // counters[4], [6], [9] after that round's last barrier -- every block must have taken them before they change
+    grid.sync();
     if (lead) {
       cnt[2] += cnt[1]; cnt[0] = 0; cnt[1] = 0; cnt[4] = 0; cnt[6] = 0; cnt[8] = cnt[7]; cnt[7] = 0;      // d_reset_counters without the open list
       if (!pend) { cnt[12] += cnt[9]; cnt[9] = 0; }
       cnt[13] = (unsigned int)round;
     }
     grid.sync();
+    const unsigned int n_open_start = vc[9];              // open pairs carried over; nothing changes it before this round's d_fast
     int* lin = (round & 1) ? C.list1 : C.list0;
     int* lout = (round & 1) ? C.list0 : C.list1;
     d_frontier2(A, round, C.cursor, C.kept, lin, 0u, cnt + 8, lout, cnt, pend);
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
     // the open pairs have been swept: every phase is a no-op once counters[5] is set)
     const bool overflow = vc[1] > C.cap;
     if (C.filter == 1) {
-      if (!overflow && vc[9] + vc[1] > C.cap) {           // the open list could overflow: sweep what is there first
+      if (!overflow && n_open_start + vc[1] > C.cap) {    // the open list could overflow: sweep what is there first (both values are stable here)
         d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
         grid.sync();
         if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
