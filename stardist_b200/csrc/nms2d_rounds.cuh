@@ -6,7 +6,6 @@
 #include "clip2d.cuh"
 #include "polyfast.cuh"
 #include <algorithm>
-#include <cooperative_groups.h>
 
 namespace sdnms {
 namespace {
@@ -357,14 +356,45 @@ __global__ void k_reset_counters(unsigned int* counters) {
 // counters[4] != 0 (pairs for the slow path) or simply counters[0] != 0 after max_rounds; counters[13] = round in progress.
 struct TailCtx {
   int2* cursor; int* kept; int* list0; int* list1; int2* pairs; int2* xpairs; int2* slow; int* pend;
-  unsigned int* counters; unsigned int cap; int round0, max_rounds, filter;
+  unsigned int* counters; unsigned int* bar; unsigned int cap; int round0, max_rounds, filter;
+};
+
+// Grid-wide barrier of the cooperative launch (all blocks are resident): arrival counter + generation word, with a bounded
+// wait -- if the blocks ever disagree on the control flow, the kernel gives up (bar[2] = 1, every block returns) instead of
+// hanging the device; the host then reports an error.  bar = {count, generation, abort}, zeroed by the host.
+struct GridBarrier {
+  unsigned int* bar; bool dead;
+  __device__ GridBarrier(unsigned int* b) : bar(b), dead(false) {}
+  __device__ void sync() {
+    __shared__ int s_dead;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      volatile unsigned int* vb = bar;
+      int d = dead || vb[2] != 0;
+      if (!d) {
+        __threadfence();
+        const unsigned int gen = vb[1];
+        if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) { bar[0] = 0; __threadfence(); atomicAdd(&bar[1], 1u); }
+        else {
+          const long long t0 = clock64();
+          while (vb[1] == gen) {
+            if (vb[2] != 0) { d = 1; break; }
+            if (clock64() - t0 > 3000000000LL) { atomicExch(&bar[2], 1u); d = 1; break; }      // ~1.5 s at 1.9 GHz
+          }
+        }
+        __threadfence();
+      }
+      s_dead = d;
+    }
+    __syncthreads();
+    dead = dead || s_dead != 0;
+  }
 };
 constexpr unsigned int TAIL_FLUSH_MIN = 1024;     // open pairs that make an exact-sweep phase worth its ~0.2 ms latency
 
 template <int NV>
 __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+  GridBarrier grid(C.bar);
   extern __shared__ __align__(16) unsigned char tail_smem[];
   unsigned int* cnt = C.counters;
   volatile unsigned int* vc = cnt;
@@ -378,50 +408,50 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
   for (int round = C.round0; round < C.round0 + C.max_rounds; ++round) {
     // barrier BEFORE the counters are reset: the decisions at the end of the previous round (flush / leave) read
     // counters[4], [6], [9] after that round's last barrier -- every block must have taken them before they change
-    grid.sync();
+    grid.sync(); if (grid.dead) return;
     if (lead) {
       cnt[2] += cnt[1]; cnt[0] = 0; cnt[1] = 0; cnt[4] = 0; cnt[6] = 0; cnt[8] = cnt[7]; cnt[7] = 0;      // d_reset_counters without the open list
       if (!pend) { cnt[12] += cnt[9]; cnt[9] = 0; }
       cnt[13] = (unsigned int)round;
     }
-    grid.sync();
+    grid.sync(); if (grid.dead) return;
     const unsigned int n_open_start = vc[9];              // open pairs carried over; nothing changes it before this round's d_fast
     int* lin = (round & 1) ? C.list1 : C.list0;
     int* lout = (round & 1) ? C.list0 : C.list1;
     d_frontier2(A, round, C.cursor, C.kept, lin, 0u, cnt + 8, lout, cnt, pend);
-    grid.sync();
+    grid.sync(); if (grid.dead) return;
     if (vc[0] == 0) break;                                // no undecided candidate was left: done (nothing can be pending)
     bool leave = false;
     d_pairs(A, round, C.kept, C.pairs, C.cap, cnt);
-    grid.sync();
+    grid.sync(); if (grid.dead) return;
     // pair list overflow: the host grows it and redoes this round's pair stage (the flag is raised on the way out, after
     // the open pairs have been swept: every phase is a no-op once counters[5] is set)
     const bool overflow = vc[1] > C.cap;
     if (C.filter == 1) {
       if (!overflow && n_open_start + vc[1] > C.cap) {    // the open list could overflow: sweep what is there first (both values are stable here)
         d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
-        grid.sync();
+        grid.sync(); if (grid.dead) return;
         if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
-        grid.sync();
+        grid.sync(); if (grid.dead) return;
       }
       if (!overflow) {
         d_fast<int32_t>(A, C.pairs, C.xpairs, nullptr, 0, cnt, pend);
-        grid.sync();
+        grid.sync(); if (grid.dead) return;
       }
       // flush: enough open pairs, or no candidate was kept in this round (the frontier is waiting for them), or leaving
       const bool must_leave = overflow || vc[4] != 0;
       const unsigned int n_open = vc[9];
       if (n_open > 0 && (must_leave || n_open >= TAIL_FLUSH_MIN || vc[6] == 0)) {
         d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
-        grid.sync();
+        grid.sync(); if (grid.dead) return;
         if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
-        grid.sync();
+        grid.sync(); if (grid.dead) return;
       }
       leave = must_leave || vc[4] != 0;                   // (a flush that produced slow pairs has swept everything: nothing is pending)
     } else {
       if (!overflow) {
         d_clip<NV>(A, C.pairs, cnt + 1, nullptr, C.slow, cnt, tail_smem);
-        grid.sync();
+        grid.sync(); if (grid.dead) return;
       }
       leave = overflow || vc[4] != 0;                     // pool overflow in the fast sweep: slow exact path on the host loop
     }
@@ -537,8 +567,11 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       sdb::DevBuf b_pend;
       SDB_CUDA(b_pend.alloc((size_t)n * sizeof(int), st));
       SDB_CUDA(cudaMemsetAsync(b_pend.p, 0, (size_t)n * sizeof(int), st));
+      sdb::DevBuf b_bar;
+      SDB_CUDA(b_bar.alloc(4 * sizeof(unsigned int), st));
+      SDB_CUDA(cudaMemsetAsync(b_bar.p, 0, 4 * sizeof(unsigned int), st));
       TailCtx C{b_cursor.as<int2>(), b_kept.as<int>(), b_list0.as<int>(), b_list1.as<int>(), b_pairs.as<int2>(), b_xpairs.as<int2>(), b_slow.as<int2>(),
-                b_pend.as<int>(), d_counters, (unsigned int)cap, 1, 4 * n + 8, filter};
+                b_pend.as<int>(), d_counters, b_bar.as<unsigned int>(), (unsigned int)cap, 1, 4 * n + 8, filter};
       void* args[] = {(void*)&A, (void*)&C};
       sdb::ProfSpan spt;
       sdb::profile_begin("nms2d_tail", st, &spt);
@@ -546,7 +579,9 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       sdb::g_launch_count++;
       sdb::profile_end("nms2d_tail", st, &spt);
       SDB_CUDA(cudaMemcpyAsync(h_pin, d_counters, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+      SDB_CUDA(cudaMemcpyAsync(h_pin + 16, b_bar.p, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
       SDB_CUDA(cudaStreamSynchronize(st));
+      if (h_pin[16 + 2] != 0) { sdb::set_error("nms2d: grid barrier of the tail kernel timed out (inconsistent control flow)"); return 1; }
       const unsigned int* c = h_pin;
       const int r = (int)c[13];                      // round in progress when the tail kernel left (0: it never started)
       if (verbose) printf("NMS2D(b200): tail kernel left in round %d: undecided=%u overflow=%u slow=%u\n", r, c[0], c[5], c[4]);
