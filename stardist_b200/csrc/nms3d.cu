@@ -178,47 +178,78 @@ __device__ __forceinline__ void for_neighbors(const Arr& A, int c, F&& f) {
       }
 }
 
-__global__ void k_frontier(Arr A, int round, unsigned int* __restrict__ counters) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.n) return;
-  if (A.state[c] != ST_UNDECIDED) return;
-  atomicAdd(&counters[0], 1u);
+// counters: [0] undecided at round start, [1] heavy pairs emitted, [3] S3 pairs decided by the lower bound, [4] pair tests,
+//           [5] S3, [6] S4, [7] S5 evaluations, [8] candidates kept in this round, [9] length of the undecided list written by
+//           this round, [10] length of the list this round reads
+// k_frontier is pull based over the COMPACTED list of undecided candidates (double buffered; round 0 reads the identity):
+// a candidate without an undecided / just-kept neighbour of higher score that reaches it is kept and appended to kept_list.
+__global__ void __launch_bounds__(256) k_frontier(Arr A, int round, const int* __restrict__ list_in, int n_all, int* __restrict__ list_out,
+                                                  int* __restrict__ kept_list, unsigned int* __restrict__ counters) {
+  const unsigned int n_in = list_in ? counters[10] : (unsigned int)n_all;
   const int kept_now = ST_KEPT_BASE + round;
-  bool blocked = false;
-  for_neighbors(A, c, [&](int h, const float* pc) {
-    const int sh = A.state[h];
-    if (sh != ST_UNDECIDED && sh != kept_now) return true;
-    if (reaches(A, h, pc)) { blocked = true; return false; }
-    return true;
-  });
-  if (!blocked) A.state[c] = kept_now;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+    const int c = list_in ? list_in[i] : (int)i;
+    if (A.state[c] != ST_UNDECIDED) continue;
+    atomicAdd(&counters[0], 1u);
+    bool blocked = false;
+    for_neighbors(A, c, [&](int h, const float* pc) {
+      const int sh = A.state[h];
+      if (sh != ST_UNDECIDED && sh != kept_now) return true;
+      if (reaches(A, h, pc)) { blocked = true; return false; }
+      return true;
+    });
+    if (!blocked) { A.state[c] = kept_now; kept_list[atomicAdd(&counters[8], 1u)] = c; }
+    else list_out[atomicAdd(&counters[9], 1u)] = c;
+  }
 }
 
-// S1 + S2 for every (kept-now h, undecided c); emits pairs that need the heavy stages
-__global__ void k_pretest(Arr A, int round, int2* __restrict__ pairs, unsigned int pair_cap, unsigned int* __restrict__ counters) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.n) return;
-  if (A.state[c] != ST_UNDECIDED) return;
-  const int kept_now = ST_KEPT_BASE + round;
+// S1 + S2 for every (h kept in this round, undecided c > h that h reaches); emits the pairs that need the heavy stages.
+// Push based: one block per kept polyhedron walks its 27 cells once -- the work is (kept polyhedra) x (neighbourhood) over
+// the whole run instead of (undecided candidates) x (neighbourhood) per round.
+__global__ void __launch_bounds__(128) k_pretest(Arr A, int round, const int* __restrict__ kept_list, int2* __restrict__ pairs, unsigned int pair_cap,
+                                                 unsigned int* __restrict__ counters) {
+  const unsigned int n_kept = counters[8];
   const float an[3] = {A.aniso[0], A.aniso[1], A.aniso[2]};
-  for_neighbors(A, c, [&](int h, const float* pc) {
-    if (A.state[h] != kept_now) return true;
-    if (!reaches(A, h, pc)) return true;
-    atomicAdd(&counters[4], 1u);
-    const float A_min = fminf(A.volume[h], A.volume[c]);
-    // S1 (:1213-1228)
-    float A_inter = fminf(sd3::intersect_sphere_isotropic(A.r_outer_iso[h], A.points + 3 * h, A.r_outer_iso[c], pc, an),
-                          sd3::intersect_bbox(A.bbox + 6 * h, A.bbox + 6 * c));
-    float iou = (float)fmin(1.0, (double)A_inter / ((double)A_min + 1e-10));
-    if (A.use_bbox && (((double)A_inter < 1.e-10) || (iou <= A.threshold))) return true;
-    // S2 (:1232-1248)
-    A_inter = sd3::intersect_sphere_isotropic(A.r_inner_iso[h], A.points + 3 * h, A.r_inner_iso[c], pc, an);
-    iou = (float)fmax(0.0, (double)A_inter / ((double)A_min + 1e-10));
-    if (iou > A.threshold) { A.state[c] = ST_SUPPRESSED; return false; }
-    const unsigned int k = atomicAdd(&counters[1], 1u);
-    if (k < pair_cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
-    return true;
-  });
+  for (unsigned int w = blockIdx.x; w < n_kept; w += gridDim.x) {
+    const int h = kept_list[w];
+    const float* ph = A.points + 3 * h;
+    const float rr = A.max_dist + A.r_outer[h];
+    int cz = 0, cy = 0, cx = 0;
+    if (!A.G.all_pairs) {
+      cz = cell_of(ph[0], A.G.mn[0], A.G.cell, A.G.g[0]); cy = cell_of(ph[1], A.G.mn[1], A.G.cell, A.G.g[1]);
+      cx = cell_of(ph[2], A.G.mn[2], A.G.cell, A.G.g[2]);
+    }
+    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, A.G.g[0] - 1); ++zz)
+      for (int yy = max(cy - 1, 0); yy <= min(cy + 1, A.G.g[1] - 1); ++yy)
+        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, A.G.g[2] - 1); ++xx) {
+          const int cell = (zz * A.G.g[1] + yy) * A.G.g[2] + xx;
+          const unsigned int e = A.cell_start[cell + 1];
+          for (unsigned int t = A.cell_start[cell] + threadIdx.x; t < e; t += blockDim.x) {
+            const int c = A.items[t];
+            if (c <= h) continue;
+            if (A.state[c] != ST_UNDECIDED) continue;
+            const float* pc = A.points + 3 * c;
+            if (!A.G.all_pairs) {
+              const float d0 = ph[0] - pc[0], d1 = ph[1] - pc[1], d2 = ph[2] - pc[2];
+              const float dd = d0 * d0 + d1 * d1 + d2 * d2;
+              if (!(dd < rr * rr)) continue;                       // reaches(A, h, pc)
+            }
+            atomicAdd(&counters[4], 1u);
+            const float A_min = fminf(A.volume[h], A.volume[c]);
+            // S1 (:1213-1228)
+            float A_inter = fminf(sd3::intersect_sphere_isotropic(A.r_outer_iso[h], ph, A.r_outer_iso[c], pc, an),
+                                  sd3::intersect_bbox(A.bbox + 6 * h, A.bbox + 6 * c));
+            float iou = (float)fmin(1.0, (double)A_inter / ((double)A_min + 1e-10));
+            if (A.use_bbox && (((double)A_inter < 1.e-10) || (iou <= A.threshold))) continue;
+            // S2 (:1232-1248)
+            A_inter = sd3::intersect_sphere_isotropic(A.r_inner_iso[h], ph, A.r_inner_iso[c], pc, an);
+            iou = (float)fmax(0.0, (double)A_inter / ((double)A_min + 1e-10));
+            if (iou > A.threshold) { A.state[c] = ST_SUPPRESSED; continue; }
+            const unsigned int k = atomicAdd(&counters[1], 1u);
+            if (k < pair_cap) { int2 pr; pr.x = h; pr.y = c; pairs[k] = pr; }
+          }
+        }
+  }
 }
 
 // ---- heavy stages: one CTA (128 threads) per pair ------------------------------------------
@@ -553,7 +584,9 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
   }
 }
 
-__global__ void k_reset(unsigned int* counters) { if (threadIdx.x < 2) counters[threadIdx.x] = 0; }
+__global__ void k_reset(unsigned int* counters) {
+  if (threadIdx.x == 0) { counters[0] = 0; counters[1] = 0; counters[10] = counters[9]; counters[9] = 0; counters[8] = 0; }
+}
 __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __restrict__ keep) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) keep[i] = (state[i] != ST_SUPPRESSED) ? 1 : 0;
@@ -576,15 +609,16 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   const int n = n_polys;
   if (n <= 0) return 0;
   if (n_rays < 4 || n_rays > MAXR || n_faces > MAXF || n_faces < 1) { sdb::set_error("nms3d: unsupported n_rays / n_faces"); return 1; }
-  sdb::DevBuf b_vol, b_bbox, b_ro, b_roi, b_rii, b_terms, b_aniso, b_stats, b_cellpt, b_counts, b_start, b_items, b_state, b_pairs, b_counters;
+  sdb::DevBuf b_vol, b_bbox, b_ro, b_roi, b_rii, b_terms, b_aniso, b_stats, b_cellpt, b_counts, b_start, b_items, b_state, b_pairs, b_counters, b_list0, b_list1, b_kept;
+  SDB_CUDA(b_list0.alloc((size_t)n * 4, st)); SDB_CUDA(b_list1.alloc((size_t)n * 4, st)); SDB_CUDA(b_kept.alloc((size_t)n * 4, st));
   SDB_CUDA(b_vol.alloc((size_t)n * 4, st)); SDB_CUDA(b_bbox.alloc((size_t)n * 24, st)); SDB_CUDA(b_ro.alloc((size_t)n * 4, st));
   SDB_CUDA(b_roi.alloc((size_t)n * 4, st)); SDB_CUDA(b_rii.alloc((size_t)n * 4, st)); SDB_CUDA(b_terms.alloc((size_t)n * 12, st));
   SDB_CUDA(b_aniso.alloc(16, st)); SDB_CUDA(b_stats.alloc(32, st)); SDB_CUDA(b_state.alloc((size_t)n * 4, st));
-  SDB_CUDA(b_counters.alloc(32, st));
+  SDB_CUDA(b_counters.alloc(64, st));
   const int init_stats[8] = {0, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN, 0};
   SDB_CUDA(cudaMemcpyAsync(b_stats.p, init_stats, sizeof(init_stats), cudaMemcpyHostToDevice, st));
   SDB_CUDA(cudaMemsetAsync(b_state.p, 0, (size_t)n * 4, st));
-  SDB_CUDA(cudaMemsetAsync(b_counters.p, 0, 32, st));
+  SDB_CUDA(cudaMemsetAsync(b_counters.p, 0, 64, st));
   Arr A;
   A.dist = d_dist; A.points = d_points; A.verts = d_verts; A.faces = d_faces; A.n = n; A.R = n_rays; A.F = n_faces;
   A.volume = b_vol.as<float>(); A.bbox = b_bbox.as<int>(); A.r_outer = b_ro.as<float>(); A.r_outer_iso = b_roi.as<float>();
@@ -640,16 +674,20 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
     SDB_LAUNCH(k_reset, 1, 32, 0, st, b_counters.as<unsigned int>());
     sdb::ProfSpan sp;
     sdb::profile_begin("nms3d_frontier", st, &sp);
-    SDB_LAUNCH(k_frontier, cdiv(n, 256), 256, 0, st, A, round, b_counters.as<unsigned int>());
+    {
+      const int* lin = round == 0 ? (const int*)nullptr : ((round & 1) ? b_list1.as<int>() : b_list0.as<int>());
+      int* lout = (round & 1) ? b_list0.as<int>() : b_list1.as<int>();
+      SDB_LAUNCH(k_frontier, std::min(cdiv(n, 256), 148 * 8), 256, 0, st, A, round, lin, n, lout, b_kept.as<int>(), b_counters.as<unsigned int>());
+    }
     sdb::profile_end("nms3d_frontier", st, &sp);
     for (;;) {
       sdb::profile_begin("nms3d_pretest", st, &sp);
-      SDB_LAUNCH(k_pretest, cdiv(n, 128), 128, 0, st, A, round, b_pairs.as<int2>(), (unsigned int)pair_cap, b_counters.as<unsigned int>());
+      SDB_LAUNCH(k_pretest, 148 * 8, 128, 0, st, A, round, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)pair_cap, b_counters.as<unsigned int>());
       sdb::profile_end("nms3d_pretest", st, &sp);
       sdb::profile_begin("nms3d_heavy", st, &sp);
       SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap);
       sdb::profile_end("nms3d_heavy", st, &sp);
-      if (cudaMemcpyAsync(h_pin, b_counters.p, 32, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
+      if (cudaMemcpyAsync(h_pin, b_counters.p, 64, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         sdb::set_error(std::string("nms3d: round failed: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; break;
       }
       if (h_pin[1] <= pair_cap) break;
