@@ -133,6 +133,9 @@ int sdb_nms3d_set_variant(int norm_planes);
  * midpoint, fan of tetrahedra) decides `iou > threshold` of stage S3 before the volume itself is computed; 0: always the
  * volume.  Decisions are identical (margin 1e-5 relative). */
 int sdb_nms3d_set_s3_bound(int on);
+/* 1 (default): the heavy stages run as three launches per round -- S3 for all pairs, hull facets of the polyhedra that stay open
+ * (one warp each), S4 + S5 with those facets; 0: one launch doing everything per pair.  Decisions identical. */
+int sdb_nms3d_set_split(int on);
 
 /* relabel_sequential on a device label map (stardist/matching.py:319-406; callers model3d.py:645, base.py:959):
  * labels occurring in d_labels[n] (values in [0, max_label], 16-byte aligned) are renumbered offset, offset+1, ...

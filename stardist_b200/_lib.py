@@ -32,6 +32,8 @@ def _declare(lib):
     lib.sdb_paint_order_2d.restype = c_int
     lib.sdb_nms2d_set_filter.argtypes = [c_int]
     lib.sdb_nms2d_set_filter.restype = c_int
+    lib.sdb_nms3d_set_split.argtypes = [c_int]
+    lib.sdb_nms3d_set_split.restype = c_int
     lib.sdb_nms3d_set_s3_bound.argtypes = [c_int]
     lib.sdb_nms3d_set_s3_bound.restype = c_int
     lib.sdb_label3d_set_cull.argtypes = [c_int]

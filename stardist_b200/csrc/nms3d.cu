@@ -361,10 +361,47 @@ __device__ int hull_planes_warp(const double* pts, int n, Plane* out, int max_pl
   return nf;
 }
 
+struct HeavyCtx {
+  int stage; int2* list4; int* slot; int* uniq; Plane* hull_planes; int* hull_n; int hull_cap;
+};
+
+// hull facet planes of the polyhedra registered by the S3 launch: ONE WARP per polyhedron (gift wrapping is a serial chain of
+// pivots; 4 warps per block, each with its own points / edge bit map / stack in shared memory)
+__global__ void __launch_bounds__(128) k_hulls(Arr A, HeavyCtx X, const unsigned int* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char hsm[];
+  const int wpb = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_warp = (size_t)3 * A.R * sizeof(double) + (size_t)((A.R * A.R + 31) / 32) * 4 + (size_t)3 * 4 * A.R * 2 + 16;
+  unsigned char* base = hsm + (size_t)wid * ((per_warp + 15) / 16 * 16);
+  double* pts = reinterpret_cast<double*>(base);
+  uint32_t* edge_done = reinterpret_cast<uint32_t*>(base + (size_t)3 * A.R * sizeof(double));
+  int16_t* stack = reinterpret_cast<int16_t*>(base + (size_t)3 * A.R * sizeof(double) + (size_t)((A.R * A.R + 31) / 32) * 4);
+  const unsigned int n_uniq = min(counters[12], (unsigned int)X.hull_cap);
+  for (unsigned int u = blockIdx.x * wpb + wid; u < n_uniq; u += gridDim.x * wpb) {
+    const int i = X.uniq[u];
+    const float* d = A.dist + (size_t)i * A.R;
+    const float c0 = A.points[3 * i], c1 = A.points[3 * i + 1], c2 = A.points[3 * i + 2];
+    __syncwarp();
+    for (int j = lane; j < A.R; j += 32) {
+      pts[3 * j] = (double)(c0 + d[j] * A.verts[3 * j]);
+      pts[3 * j + 1] = (double)(c1 + d[j] * A.verts[3 * j + 1]);
+      pts[3 * j + 2] = (double)(c2 + d[j] * A.verts[3 * j + 2]);
+    }
+    __syncwarp();
+    const int nf = hull_planes_warp(pts, A.R, X.hull_planes + (size_t)u * A.F, A.F, edge_done, stack, 4 * A.R);
+    if (lane == 0) X.hull_n[u] = nf;
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(512)
-k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counters, unsigned int pair_cap) {
+k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counters, unsigned int pair_cap, HeavyCtx X) {
+  // X.stage 0: all stages for the pairs of k_pretest (single launch);  1: S3 only, the pairs it leaves open go to X.list4 and
+  // their polyhedra are registered for k_hulls;  2: S4 + S5 for X.list4 with the hull facets k_hulls computed (one warp per
+  // polyhedron, all warps of the device busy -- inside this kernel the gift wrapping occupies 1 warp of 16)
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const unsigned int n_pairs = min(counters[1], pair_cap);
+  const int stage = X.stage;
+  if (stage == 2) pairs = X.list4;
+  const unsigned int n_pairs = stage == 2 ? min(counters[11], pair_cap) : min(counters[1], pair_cap);
   float* pv1 = reinterpret_cast<float*>(smem_raw);                 // [R][3]
   float* pv2 = pv1 + 3 * A.R;
   int* sfaces = reinterpret_cast<int*>(pv2 + 3 * A.R);             // [F][3]
@@ -399,24 +436,9 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
     __syncthreads();
     const float A_min = fminf(A.volume[h], A.volume[c]);
     const double den = (double)A_min + 1e-10;
-    atomicAdd(&counters[5], threadIdx.x == 0 ? 1u : 0u);
-
-    // ---- S3: kernel ∩ kernel (:1261-1277) ------------------------------------------------
-    for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
-      double hs[4];
-      sd3::build_halfspace(&pv1[3 * sfaces[3 * f]], &pv1[3 * sfaces[3 * f + 1]], &pv1[3 * sfaces[3 * f + 2]], hs);
-      Plane P; P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f] = P;
-      sd3::build_halfspace(&pv2[3 * sfaces[3 * f]], &pv2[3 * sfaces[3 * f + 1]], &pv2[3 * sfaces[3 * f + 2]], hs);
-      P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f + 1] = P;
-    }
-    __syncthreads();
     double p[3];
     for (int k = 0; k < 3; ++k) p[k] = .5 * (double)(c1[k] + c2[k]);
     int np = 2 * A.F;
-    int infeasible = 0;
-    for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) infeasible = 1;
-    infeasible = __syncthreads_or(infeasible);
-    float vol_kernel = 0.f;
     double L = 0;
     {
       double m = 0;
@@ -431,6 +453,23 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmax(m, red[i]);
       L = 4.0 * m + 1.0;
     }
+    float iou = 0.f;
+    if (stage != 2) {
+    atomicAdd(&counters[5], threadIdx.x == 0 ? 1u : 0u);
+
+    // ---- S3: kernel ∩ kernel (:1261-1277) ------------------------------------------------
+    for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
+      double hs[4];
+      sd3::build_halfspace(&pv1[3 * sfaces[3 * f]], &pv1[3 * sfaces[3 * f + 1]], &pv1[3 * sfaces[3 * f + 2]], hs);
+      Plane P; P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f] = P;
+      sd3::build_halfspace(&pv2[3 * sfaces[3 * f]], &pv2[3 * sfaces[3 * f + 1]], &pv2[3 * sfaces[3 * f + 2]], hs);
+      P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f + 1] = P;
+    }
+    __syncthreads();
+    int infeasible = 0;
+    for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) infeasible = 1;
+    infeasible = __syncthreads_or(infeasible);
+    float vol_kernel = 0.f;
     // ---- S3 short cut: a rigorous LOWER bound of vol(kernel_h ∩ kernel_c) that is ~80x cheaper than the volume itself.
     // Both kernels are convex and contain the midpoint p (feasibility above), so for every ray direction v_k the point
     // p + t_k v_k, t_k = distance from p to the nearest of the 2F planes along v_k, lies in the intersection, and so does
@@ -491,8 +530,25 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       }
       vol_kernel = (float)block_sum(part, red);     // NOTE: summation order differs from the serial host version (ulp-level in double)
     }
-    float iou = (float)((double)vol_kernel / den);
+    iou = (float)((double)vol_kernel / den);
     if (iou > A.threshold) { if (threadIdx.x == 0) A.state[c] = ST_SUPPRESSED; continue; }
+    if (stage == 1) {
+      // open after S3: hand the pair to the S4/S5 launch and register both polyhedra for the hull kernel (once per round)
+      if (threadIdx.x == 0) {
+        const unsigned int q = atomicAdd(&counters[11], 1u);
+        if (q < pair_cap) X.list4[q] = pairs[pi];
+        const int two[2] = {h, c};
+        for (int e = 0; e < 2; ++e) {
+          const int i = two[e];
+          if (atomicCAS(&X.slot[i], -1, -2) == -1) {
+            const unsigned int u = atomicAdd(&counters[12], 1u);
+            if (u < (unsigned int)X.hull_cap) { X.uniq[u] = i; X.slot[i] = (int)u; } else X.slot[i] = -3;      // -3: no room, hull inside the CTA
+          }
+        }
+      }
+      continue;
+    }
+    }   // stage != 2
 
     // ---- S4: hull ∩ hull (:1282-1295) -----------------------------------------------------
     atomicAdd(&counters[6], threadIdx.x == 0 ? 1u : 0u);
@@ -500,6 +556,16 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
     {
       int n1 = -1, n2 = -1;
       __syncthreads();
+      const int s1 = stage == 2 ? X.slot[h] : -1, s2 = stage == 2 ? X.slot[c] : -1;
+      if (s1 >= 0 && s2 >= 0) {
+        // facets from k_hulls (same routine, same numbers as the in-CTA gift wrapping below)
+        n1 = X.hull_n[s1]; n2 = X.hull_n[s2];
+        if (n1 >= 4 && n2 >= 4) {
+          for (int k = threadIdx.x; k < n1; k += blockDim.x) planes[k] = X.hull_planes[(size_t)s1 * A.F + k];
+          for (int k = threadIdx.x; k < n2; k += blockDim.x) planes[n1 + k] = X.hull_planes[(size_t)s2 * A.F + k];
+        }
+        __syncthreads();
+      } else {
       for (int k = threadIdx.x; k < 3 * A.R; k += blockDim.x) pts[k] = (double)pv1[k];
       __syncthreads();
       if (threadIdx.x < 32) { n1 = hull_planes_warp(pts, A.R, planes, A.F, edge_done, stack, 4 * A.R); if (threadIdx.x == 0) sh_i[0] = n1; }
@@ -511,6 +577,7 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         if (threadIdx.x < 32) { n2 = hull_planes_warp(pts, A.R, planes + n1, A.F, edge_done, stack, 4 * A.R); if (threadIdx.x == 0) sh_i[1] = n2; }
         __syncthreads();
         n2 = sh_i[1];
+      }
       }
       if (n1 >= 4 && n2 >= 4) {
         np = n1 + n2;
@@ -584,8 +651,15 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
   }
 }
 
-__global__ void k_reset(unsigned int* counters) {
-  if (threadIdx.x == 0) { counters[0] = 0; counters[1] = 0; counters[10] = counters[9]; counters[9] = 0; counters[8] = 0; }
+// full: start of a round; !full: retry of the pair stages after the pair list was enlarged
+__global__ void k_reset(unsigned int* counters, int* slot, const int* uniq, int hull_cap, int full) {
+  const unsigned int nu = min(counters[12], (unsigned int)hull_cap);
+  for (unsigned int u = threadIdx.x; u < nu; u += blockDim.x) slot[uniq[u]] = -1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    counters[1] = 0; counters[11] = 0; counters[12] = 0;
+    if (full) { counters[0] = 0; counters[10] = counters[9]; counters[9] = 0; counters[8] = 0; }
+  }
 }
 __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __restrict__ keep) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -598,6 +672,8 @@ __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __
 // The two are bit-identical functions (host build, 7 500 fuzzed pairs: tests/test_cpu_oracle.py); the switch exists because
 // variant 1 has not been run on a GPU yet (tests/test_gpu_3d.py runs it under STARDIST_B200_EXPERIMENTAL=1).
 static int g_nms3d_norm_planes = 0;
+static int g_nms3d_split = 1;         // S3 | hull kernel | S4+S5 as separate launches (sdb_nms3d_set_split; decisions identical)
+extern "C" int sdb_nms3d_set_split(int on) { g_nms3d_split = on ? 1 : 0; return 0; }
 static int g_nms3d_s3_bound = 1;      // S3 lower-bound short cut (sdb_nms3d_set_s3_bound; decisions identical)
 extern "C" int sdb_nms3d_set_s3_bound(int on) { g_nms3d_s3_bound = on ? 1 : 0; return 0; }
 extern "C" int sdb_nms3d_set_variant(int norm_planes) { g_nms3d_norm_planes = norm_planes ? 1 : 0; return 0; }
@@ -659,6 +735,17 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   // pair list: grown on overflow (the round is re-run, decisions are idempotent)
   size_t pair_cap = std::max<size_t>(1 << 16, (size_t)n * 4);
   SDB_CUDA(b_pairs.alloc(pair_cap * sizeof(int2), st));
+  // S3 | hulls | S4+S5 split: open pairs of S3, per-round hull cache (slot: polyhedron -> cache row, -1 unregistered)
+  sdb::DevBuf b_list4, b_slot, b_uniq, b_hull, b_hulln;
+  const int hull_cap = 16384;
+  SDB_CUDA(b_list4.alloc(pair_cap * sizeof(int2), st));
+  SDB_CUDA(b_slot.alloc((size_t)n * 4, st)); SDB_CUDA(cudaMemsetAsync(b_slot.p, 0xff, (size_t)n * 4, st));
+  SDB_CUDA(b_uniq.alloc((size_t)hull_cap * 4, st));
+  SDB_CUDA(b_hull.alloc((size_t)hull_cap * n_faces * sizeof(Plane), st));
+  SDB_CUDA(b_hulln.alloc((size_t)hull_cap * 4, st));
+  const size_t hull_per_warp = (((size_t)3 * n_rays * sizeof(double) + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 16) + 15) / 16 * 16;
+  const size_t hull_smem = 4 * hull_per_warp;
+  SDB_CUDA(cudaFuncSetAttribute(k_hulls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(hull_smem, 48 * 1024)));
   const size_t smem = ((size_t)(6 * n_rays + 3 * n_faces) * 4 + 15) / 16 * 16 + (size_t)2 * n_faces * sizeof(Plane) +
                       (size_t)3 * n_rays * 8 + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 64;
   SDB_CUDA(cudaFuncSetAttribute(k_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
@@ -671,7 +758,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   if (!h_pin) { sdb::set_error("nms3d: pinned host allocation failed"); return 1; }
   int rc = 0;
   for (int round = 0;; ++round) {
-    SDB_LAUNCH(k_reset, 1, 32, 0, st, b_counters.as<unsigned int>());
+    SDB_LAUNCH(k_reset, 1, 256, 0, st, b_counters.as<unsigned int>(), b_slot.as<int>(), b_uniq.as<int>(), hull_cap, 1);
     sdb::ProfSpan sp;
     sdb::profile_begin("nms3d_frontier", st, &sp);
     {
@@ -685,7 +772,16 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       SDB_LAUNCH(k_pretest, 148 * 8, 128, 0, st, A, round, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)pair_cap, b_counters.as<unsigned int>());
       sdb::profile_end("nms3d_pretest", st, &sp);
       sdb::profile_begin("nms3d_heavy", st, &sp);
-      SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap);
+      if (g_nms3d_split) {
+        HeavyCtx X{1, b_list4.as<int2>(), b_slot.as<int>(), b_uniq.as<int>(), b_hull.as<Plane>(), b_hulln.as<int>(), hull_cap};
+        SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
+        SDB_LAUNCH(k_hulls, 148 * 4, 128, hull_smem, st, A, X, b_counters.as<unsigned int>());
+        X.stage = 2;
+        SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
+      } else {
+        HeavyCtx X{0, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+        SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
+      }
       sdb::profile_end("nms3d_heavy", st, &sp);
       if (cudaMemcpyAsync(h_pin, b_counters.p, 64, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) {
         sdb::set_error(std::string("nms3d: round failed: ") + cudaGetErrorString(cudaGetLastError())); rc = 1; break;
@@ -695,8 +791,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       // candidates are skipped, nothing is lost)
       pair_cap = (size_t)h_pin[1] + (size_t)h_pin[1] / 2;
       SDB_CUDA(b_pairs.alloc(pair_cap * sizeof(int2), st));
-      unsigned int zero = 0;
-      SDB_CUDA(cudaMemcpyAsync(b_counters.as<unsigned int>() + 1, &zero, 4, cudaMemcpyHostToDevice, st));
+      SDB_CUDA(b_list4.alloc(pair_cap * sizeof(int2), st));
+      SDB_LAUNCH(k_reset, 1, 256, 0, st, b_counters.as<unsigned int>(), b_slot.as<int>(), b_uniq.as<int>(), hull_cap, 0);
     }
     if (rc) break;
     if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u [decided by the lower bound: %u], convex %u, render %u so far)\n",

@@ -117,6 +117,9 @@ def test_device_nms3d_fuzz_vs_reference(sd, case):
     try:
         lib.sdb_nms3d_set_s3_bound(0)
         got0 = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
-    finally:
         lib.sdb_nms3d_set_s3_bound(1)
-    assert np.array_equal(got0, want)
+        lib.sdb_nms3d_set_split(0)          # all heavy stages in one launch per round (hulls inside the CTA)
+        got1 = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
+    finally:
+        lib.sdb_nms3d_set_s3_bound(1); lib.sdb_nms3d_set_split(1)
+    assert np.array_equal(got0, want) and np.array_equal(got1, want)
