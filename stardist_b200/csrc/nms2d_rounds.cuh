@@ -281,8 +281,9 @@ __device__ __forceinline__ void d_fast(const NmsArrays& A, const int2* pairs, in
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* pairs, int2* xpairs, signed char* verdict, int verify, unsigned int* counters) {
-  d_fast<T>(A, pairs, xpairs, verdict, verify, counters);
+__global__ void __launch_bounds__(256) k_fast(NmsArrays A, const int2* pairs, int2* xpairs, signed char* verdict, int verify, unsigned int* counters,
+                                              int* pend) {
+  d_fast<T>(A, pairs, xpairs, verdict, verify, counters, pend);
 }
 
 // Exact sweep: ONE PAIR PER WARP, executed by lane 0 with the sweep state (~8 KB of pools for 32-gons) in
@@ -500,7 +501,8 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     SDB_LAUNCH((k_clip_slow<NV>), 8, 64, 0, st, A, b_slow.as<int2>(), d_counters);
     return 0;
   };
-  auto launch_pair_stage = [&](int r) -> int {
+  int* d_pend = nullptr;          // set on the k_tail path: round 0 leaves its open pairs to the tail kernel's first flush
+  auto launch_pair_stage = [&](int r, bool defer_exact = false) -> int {
     sdb::ProfSpan sp;
     sdb::profile_begin("nms2d_pairs", st, &sp);
     SDB_LAUNCH(k_pairs, 148 * 8, 256, 0, st, A, r, b_kept.as<int>(), b_pairs.as<int2>(), (unsigned int)cap, d_counters);
@@ -508,9 +510,11 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
     SDB_LAUNCH(k_check_overflow, 1, 1, 0, st, (unsigned int)cap, d_counters);
     if (filter) {
       sdb::profile_begin("nms2d_fast", st, &sp);
-      if (A.max_abs_coord <= 8191.0) SDB_LAUNCH(k_fast<int32_t>, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
-      else SDB_LAUNCH(k_fast<long long>, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters);
+      int* pend = defer_exact ? d_pend : nullptr;
+      if (A.max_abs_coord <= 8191.0) SDB_LAUNCH(k_fast<int32_t>, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters, pend);
+      else SDB_LAUNCH(k_fast<long long>, 148 * 8, 256, 0, st, A, b_pairs.as<int2>(), b_xpairs.as<int2>(), b_verdict.as<signed char>(), filter == 2 ? 1 : 0, d_counters, pend);
       sdb::profile_end("nms2d_fast", st, &sp);
+      if (defer_exact && filter == 1) return 0;       // the open pairs (counters[9], pend[]) are swept by k_tail
     }
     sdb::profile_begin("nms2d_clip", st, &sp);
     {
@@ -559,14 +563,16 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       if (coop && cudaFuncSetAttribute(k_tail<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm) == cudaSuccess &&
           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<NV>, 256, tsm) == cudaSuccess && per_sm > 0)
-        tail_blocks = sms * std::min(per_sm, 2);
+        tail_blocks = sms * std::min(per_sm, 3);
       else { tail_blocks = 0; cudaGetLastError(); }
     }
     if (tail_blocks > 0) {
-      if (launch_frontier(0) || launch_pair_stage(0)) return 1;
       sdb::DevBuf b_pend;
       SDB_CUDA(b_pend.alloc((size_t)n * sizeof(int), st));
       SDB_CUDA(cudaMemsetAsync(b_pend.p, 0, (size_t)n * sizeof(int), st));
+      d_pend = b_pend.as<int>();
+      if (launch_frontier(0) || launch_pair_stage(0, filter == 1)) return 1;
+      d_pend = nullptr;
       sdb::DevBuf b_bar;
       SDB_CUDA(b_bar.alloc(4 * sizeof(unsigned int), st));
       SDB_CUDA(cudaMemsetAsync(b_bar.p, 0, 4 * sizeof(unsigned int), st));
