@@ -373,7 +373,7 @@ def main():
             dev_ms3, n_inst3, n_cand3, stage3 = time_device(model3, x3, SHAPE_3D, PROB_THRESH_3D, NMS_THRESH_3D, steps3)
             launches3 = _lib.launch_count() - l0
             prof_conv3 = _lib.profile_get("conv_tc")
-            prof_n3 = {k: _lib.profile_get("nms3d_" + k) for k in ("pretest", "heavy", "frontier", "paint")}
+            prof_n3 = {k: _lib.profile_get("nms3d_" + k) for k in ("pretest", "heavy", "heavy_bound", "hulls", "heavy_s4s3s5", "frontier", "paint")}
             _lib.profile_enable(False)
             barrier()
             (dev3_max, _, _), (_, n3_total, _) = reduce_max_sum([dev_ms3, float(n_inst3), 0.0])

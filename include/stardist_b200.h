@@ -274,7 +274,8 @@ int sdb_select_ranks(const float* d_x, int ndim, const int* shape, const int* va
 /* in place x = (x - mi) / den in float32 (den = ma - mi + eps computed by the caller in float32), optional clip to [0,1] */
 int sdb_normalize_mi_ma(float* d_x, long long n, float mi, float den, int clip, sdb_stream_t stream);
 /* scipy.ndimage.zoom(x, zoom, order=1) (stardist/models/base.py:735) for ndim 2 / 3; out_shape = round(in_shape * zoom) */
-int sdb_zoom_linear(const float* d_in, int ndim, const int* in_shape, const int* out_shape, float* d_out, sdb_stream_t stream);
+int sdb_zoom_linear(const float* d_in, int ndim, const int* in_shape, const int* out_shape, float* d_out, int round_int,
+                    double int_lo, double int_hi, sdb_stream_t stream);   /* round_int: integer source image -> scipy's rounding */
 /* numpy.pad(mode='reflect') at the end of each spatial axis of a channels-last array (StarDistPadAndCropResizer.before) */
 int sdb_pad_reflect_end(const float* d_in, int ndim, const int* in_shape, const int* out_shape, int channels, float* d_out,
                         sdb_stream_t stream);

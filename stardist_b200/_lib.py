@@ -101,7 +101,7 @@ def _declare(lib):
     lib.sdb_select_ranks.restype = c_int
     lib.sdb_normalize_mi_ma.argtypes = [P, c_longlong, c_float, c_float, c_int, P]
     lib.sdb_normalize_mi_ma.restype = c_int
-    lib.sdb_zoom_linear.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), P, P]
+    lib.sdb_zoom_linear.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), P, c_int, c_double, c_double, P]
     lib.sdb_zoom_linear.restype = c_int
     lib.sdb_pad_reflect_end.argtypes = [P, c_int, POINTER(c_int), POINTER(c_int), c_int, P, P]
     lib.sdb_pad_reflect_end.restype = c_int

@@ -419,7 +419,15 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
   __shared__ float c1[3], c2[3];
   for (int j = threadIdx.x; j < 3 * A.F; j += blockDim.x) sfaces[j] = A.faces[j];
 
-  for (unsigned int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+  // pairs are handed out one at a time (atomic ticket): the expensive ones -- a few per cent -- would otherwise pile up in
+  // whichever CTAs a static stride gives them to, and the slowest CTA sets the length of the round
+  __shared__ unsigned int sh_pi;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh_pi = atomicAdd(&counters[stage == 2 ? 15 : 14], 1u);
+    __syncthreads();
+    const unsigned int pi = sh_pi;
+    if (pi >= n_pairs) break;
     const int h = pairs[pi].x, c = pairs[pi].y;
     __syncthreads();
     if (threadIdx.x == 0) sh_i[2] = A.state[c];
@@ -517,7 +525,7 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         continue;
       }
     }
-    if (!infeasible) {
+    if (!infeasible && stage == 0) {
       PlaneAt PA{planes};
       double part = 0; int ovf = 0;
       if (A.norm_planes) {
@@ -533,7 +541,8 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
     iou = (float)((double)vol_kernel / den);
     if (iou > A.threshold) { if (threadIdx.x == 0) A.state[c] = ST_SUPPRESSED; continue; }
     if (stage == 1) {
-      // open after S3: hand the pair to the S4/S5 launch and register both polyhedra for the hull kernel (once per round)
+      // not decided by the lower bound: hand the pair to the second launch (S4, then the S3 volume only if S4 leaves the pair
+      // open) and register both polyhedra for the hull kernel (once per round)
       if (threadIdx.x == 0) {
         const unsigned int q = atomicAdd(&counters[11], 1u);
         if (q < pair_cap) X.list4[q] = pairs[pi];
@@ -599,6 +608,43 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         }
       }
     }
+    if (stage == 2) {
+      // The reference evaluates S3 (suppress if iou_kernel > t) before S4 (keep if iou_hull <= t).  kernel_h ∩ kernel_c is a
+      // subset of hull_h ∩ hull_c, so iou_hull <= t implies iou_kernel <= t: neither stage suppresses and the S3 volume --
+      // as expensive as S4 -- is not needed.  (1e-4 relative margin against the independent roundings of the two stages;
+      // the sentinel 1e10 of an infeasible hull midpoint never takes this exit.)  ~3/4 of the open pairs end here.
+      if ((double)vol_convex * (1.0 + 1e-4) <= (double)A.threshold * den) continue;
+      atomicAdd(&counters[13], threadIdx.x == 0 ? 1u : 0u);
+      __syncthreads();
+      for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
+        double hs[4];
+        sd3::build_halfspace(&pv1[3 * sfaces[3 * f]], &pv1[3 * sfaces[3 * f + 1]], &pv1[3 * sfaces[3 * f + 2]], hs);
+        Plane P; P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f] = P;
+        sd3::build_halfspace(&pv2[3 * sfaces[3 * f]], &pv2[3 * sfaces[3 * f + 1]], &pv2[3 * sfaces[3 * f + 2]], hs);
+        P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f + 1] = P;
+      }
+      __syncthreads();
+      for (int k = 0; k < 3; ++k) p[k] = .5 * (double)(c1[k] + c2[k]);
+      np = 2 * A.F;
+      int infeasible = 0;
+      for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) infeasible = 1;
+      infeasible = __syncthreads_or(infeasible);
+      float vol_kernel = 0.f;
+      if (!infeasible) {
+        PlaneAt PA{planes};
+        double part = 0; int ovf = 0;
+        if (A.norm_planes) {
+          for (int k = threadIdx.x; k < np; k += blockDim.x) planes[k] = sd3::normalized_plane(planes[k]);
+          __syncthreads();
+          for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume_n(PA, np, k, p, L, &ovf);
+        } else {
+          for (int k = threadIdx.x; k < np; k += blockDim.x) part += sd3::face_cone_volume(PA, np, k, p, L, &ovf);
+        }
+        vol_kernel = (float)block_sum(part, red);
+      }
+      const float iou3 = (float)((double)vol_kernel / den);
+      if (iou3 > A.threshold) { if (threadIdx.x == 0) A.state[c] = ST_SUPPRESSED; continue; }
+    }
     iou = (float)((double)vol_convex / den);
     if (iou <= A.threshold) continue;
 
@@ -657,7 +703,7 @@ __global__ void k_reset(unsigned int* counters, int* slot, const int* uniq, int 
   for (unsigned int u = threadIdx.x; u < nu; u += blockDim.x) slot[uniq[u]] = -1;
   __syncthreads();
   if (threadIdx.x == 0) {
-    counters[1] = 0; counters[11] = 0; counters[12] = 0;
+    counters[1] = 0; counters[11] = 0; counters[12] = 0; counters[14] = 0; counters[15] = 0;
     if (full) { counters[0] = 0; counters[10] = counters[9]; counters[9] = 0; counters[8] = 0; }
   }
 }
@@ -671,7 +717,7 @@ __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __
 // 0 (default): face_cone_volume as validated on the GPU in round 1; 1: face_cone_volume_n on pre-normalised planes.
 // The two are bit-identical functions (host build, 7 500 fuzzed pairs: tests/test_cpu_oracle.py); the switch exists because
 // variant 1 has not been run on a GPU yet (tests/test_gpu_3d.py runs it under STARDIST_B200_EXPERIMENTAL=1).
-static int g_nms3d_norm_planes = 0;
+static int g_nms3d_norm_planes = 1;      // face_cone_volume_n (bit-identical on the host build; goldens green on B200, round 2)
 static int g_nms3d_split = 1;         // S3 | hull kernel | S4+S5 as separate launches (sdb_nms3d_set_split; decisions identical)
 extern "C" int sdb_nms3d_set_split(int on) { g_nms3d_split = on ? 1 : 0; return 0; }
 static int g_nms3d_s3_bound = 1;      // S3 lower-bound short cut (sdb_nms3d_set_s3_bound; decisions identical)
@@ -774,10 +820,17 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       sdb::profile_begin("nms3d_heavy", st, &sp);
       if (g_nms3d_split) {
         HeavyCtx X{1, b_list4.as<int2>(), b_slot.as<int>(), b_uniq.as<int>(), b_hull.as<Plane>(), b_hulln.as<int>(), hull_cap};
+        sdb::ProfSpan s2;
+        sdb::profile_begin("nms3d_heavy_bound", st, &s2);
         SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
+        sdb::profile_end("nms3d_heavy_bound", st, &s2);
+        sdb::profile_begin("nms3d_hulls", st, &s2);
         SDB_LAUNCH(k_hulls, 148 * 4, 128, hull_smem, st, A, X, b_counters.as<unsigned int>());
+        sdb::profile_end("nms3d_hulls", st, &s2);
         X.stage = 2;
+        sdb::profile_begin("nms3d_heavy_s4s3s5", st, &s2);
         SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
+        sdb::profile_end("nms3d_heavy_s4s3s5", st, &s2);
       } else {
         HeavyCtx X{0, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
         SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
@@ -795,8 +848,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       SDB_LAUNCH(k_reset, 1, 256, 0, st, b_counters.as<unsigned int>(), b_slot.as<int>(), b_uniq.as<int>(), hull_cap, 0);
     }
     if (rc) break;
-    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u [decided by the lower bound: %u], convex %u, render %u so far)\n",
-                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[3], h_pin[6], h_pin[7]);
+    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u [decided by the lower bound: %u, volumes after S4: %u], convex %u, render %u so far)\n",
+                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[3], h_pin[13], h_pin[6], h_pin[7]);
     if (h_pin[0] == 0) break;
     if (round > 4 * n + 8) { sdb::set_error("nms3d: no progress"); rc = 1; break; }
   }

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_normalize(float* __restrict__ x, long l
   }
 }
 
-struct ZoomArgs { int nd; int in[3]; int out[3]; double z[3]; };
+struct ZoomArgs { int nd; int in[3]; int out[3]; double z[3]; int round_int; double lo, hi; };
 
 __global__ void __launch_bounds__(256) k_zoom_linear(const float* __restrict__ src, float* __restrict__ dst, ZoomArgs Z, long long n_out) {
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_out; p += (long long)gridDim.x * blockDim.x) {
@@ -119,6 +119,13 @@ __global__ void __launch_bounds__(256) k_zoom_linear(const float* __restrict__ s
             c = c * (c2 ? w1[2] : w0[2]);
             t = t + c;
           }
+    }
+    if (Z.round_int) {
+      // scipy writes an integer output array (the dtype of the input image): unsigned: t > 0 ? t + 0.5 : 0, signed: t +- 0.5,
+      // clipped to the type's range, truncated (ni_interpolation.c CASE_INTERP_OUT_UINT / _INT)
+      if (Z.lo >= 0) t = t > 0 ? t + 0.5 : 0.0; else t = t > 0 ? t + 0.5 : t - 0.5;
+      t = t > Z.hi ? Z.hi : (t < Z.lo ? Z.lo : t);
+      t = trunc(t);
     }
     dst[p] = (float)t;
   }
@@ -167,10 +174,12 @@ extern "C" int sdb_normalize_mi_ma(float* d_x, long long n, float mi, float den,
 
 // scipy.ndimage.zoom(x, zoom, order=1) for a C-contiguous float32 array (ndim 2 or 3): out_shape given by the caller
 // (round(in * zoom)); per axis the sample position is j * (in-1)/(out-1).
-extern "C" int sdb_zoom_linear(const float* d_in, int ndim, const int* in_shape, const int* out_shape, float* d_out, sdb_stream_t stream) {
+// round_int != 0: the result is rounded and clipped to [int_lo, int_hi] like scipy does for an integer input array.
+extern "C" int sdb_zoom_linear(const float* d_in, int ndim, const int* in_shape, const int* out_shape, float* d_out, int round_int,
+                               double int_lo, double int_hi, sdb_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (ndim < 2 || ndim > 3) { sdb::set_error("zoom_linear: ndim 2 or 3"); return 1; }
-  ZoomArgs Z; Z.nd = ndim;
+  ZoomArgs Z; Z.nd = ndim; Z.round_int = round_int; Z.lo = int_lo; Z.hi = int_hi;
   long long n_out = 1;
   for (int a = 0; a < 3; ++a) { Z.in[a] = 1; Z.out[a] = 1; Z.z[a] = 1.0; }
   for (int a = 0; a < ndim; ++a) {

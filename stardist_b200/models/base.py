@@ -253,6 +253,10 @@ class StarDistBase:
             norm = (normalizer.pmin, normalizer.pmax, bool(kw.get('clip', False)), kw.get('eps', 1e-20))
         elif not isinstance(normalizer, NoNormalizer):
             return None
+        if zoom is not None and x.dtype.kind not in 'iuf':
+            return None
+        if zoom is not None and x.dtype == np.float16:
+            return None
         return dict(norm=norm, zoom=None if zoom is None else tuple(zoom), src_dtype=x.dtype)
 
     def _predict_setup(self, img, axes, normalizer, n_tiles, _zoom=None):
@@ -344,7 +348,7 @@ class StarDistBase:
         from .. import prep
         t = x_dev[0, ..., 0]                                  # single channel: the spatial array, contiguous
         if plan['zoom'] is not None:
-            t = prep.zoom_device(t, plan['zoom'][:-1])
+            t = prep.zoom_device(t, plan['zoom'][:-1], plan['src_dtype'])
         if plan['norm'] is not None:
             pmin, pmax, clip, eps = plan['norm']
             mi, ma = prep.normalize_device(t, tuple(t.shape), pmin, pmax, plan['src_dtype'], clip=clip, eps=eps)

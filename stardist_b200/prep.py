@@ -67,13 +67,21 @@ def normalize_device(x_dev, valid_shape, pmin, pmax, src_dtype, clip=False, eps=
     return mi, ma
 
 
-def zoom_device(x_dev, zoom):
-    """scipy.ndimage.zoom(x, zoom, order=1) for a float32 device tensor of 2 or 3 dimensions"""
+def zoom_device(x_dev, zoom, src_dtype=np.float32):
+    """scipy.ndimage.zoom(x, zoom, order=1) for a float32 device tensor of 2 or 3 dimensions that was uploaded from an
+    array of dtype src_dtype: scipy returns the INPUT's dtype, i.e. integer images are rounded (and clipped) again"""
     lib = L.require_cuda()
+    dt = np.dtype(src_dtype)
+    if dt.kind in 'iu':
+        rnd, lo, hi = 1, float(np.iinfo(dt).min), float(np.iinfo(dt).max)
+    elif dt.kind == 'f':
+        rnd, lo, hi = 0, 0.0, 0.0
+    else:
+        raise ValueError("zoom_device: unsupported source dtype %s" % dt)
     in_shape = [int(s) for s in x_dev.shape]
     out_shape = [int(round(s * z)) for s, z in zip(in_shape, zoom)]
     out = torch.empty(out_shape, dtype=torch.float32, device=x_dev.device)
-    L.check(lib.sdb_zoom_linear(L.ptr(x_dev), len(in_shape), L.iarr(in_shape), L.iarr(out_shape), L.ptr(out), L.stream_ptr()))
+    L.check(lib.sdb_zoom_linear(L.ptr(x_dev), len(in_shape), L.iarr(in_shape), L.iarr(out_shape), L.ptr(out), rnd, lo, hi, L.stream_ptr()))
     return out
 
 

@@ -388,6 +388,13 @@ def test_device_zoom_and_reflect_pad_vs_scipy_numpy(sd):
         gotp = prep.pad_reflect_end_device(torch.from_numpy(xc).cuda(), out_sp).cpu().numpy()
         assert np.array_equal(gotp, wantp)
     assert worst <= 1e-6, worst       # float tolerance (bit-equal in 299 of 300 cases of the numpy emulation of this rule)
+    # integer images: scipy returns the input's dtype, i.e. rounds (half up) and clips -- restated on the device
+    for dt in (np.uint16, np.uint8, np.int16):
+        xi = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, (57, 83)).astype(dt)
+        for sc in ((1.5, 1.5), (0.75, 2.0)):
+            want = ndi.zoom(xi, sc, order=1)
+            got = prep.zoom_device(torch.from_numpy(xi.astype(np.float32)).cuda(), sc, dt).cpu().numpy()
+            assert got.shape == want.shape and np.array_equal(got, want.astype(np.float32)), (dt, sc, int((got != want).sum()))
 
 
 @pytest.mark.parametrize("dtype", [np.uint16, np.float32])
@@ -406,7 +413,7 @@ def test_predict_instances_with_device_normaliser_and_scale_equals_host_path(sd,
         ld, rd = model.predict_instances(raw, normalizer=PercentileNormalizer(1, 99.8), **kw)
         assert len(rh['prob']) > 20
         if 'scale' in kw:       # zoom: float tolerance 1e-6 on the input -> allow a handful of borderline candidates
-            assert abs(len(rd['prob']) - len(rh['prob'])) <= 2 and np.mean(ld != lh) < 2e-3
+            assert abs(len(rd['prob']) - len(rh['prob'])) <= 2 and np.mean((ld > 0) != (lh > 0)) < 2e-3
         else:
             assert np.array_equal(ld, lh) and np.array_equal(rd['points'], rh['points']) and np.array_equal(rd['coord'], rh['coord'])
 
@@ -422,9 +429,17 @@ def test_polygon_order_property_through_product(sd):
     img, _ = bench_data.synthetic_image((384, 416), seed=9)
     labels, polys = model.predict_instances(img, nms_thresh=0)
     assert len(polys['coord']) > 30
+    stolen = 0
     for i, coord in enumerate(polys['coord'], start=1):
-        alone = polygons_to_label_coord(coord[None], shape=labels.shape)
-        assert np.array_equal(alone > 0, labels == i), i
+        alone = polygons_to_label_coord(coord[None], shape=labels.shape) > 0
+        mine = labels == i
+        assert not (mine & ~alone).any(), i                 # label i never leaves polygon i
+        # nms_thresh = 0 suppresses polygons whose integer-snapped outlines overlap (Clipper area > 0); two survivors may still
+        # touch in single boundary pixels of the float rendering -- those go to the polygon painted last
+        lost = alone & ~mine
+        assert (labels[lost] > 0).all(), i
+        stolen += int(lost.sum())
+    assert stolen <= 1e-3 * (labels > 0).sum()
 
 
 @pytest.mark.parametrize("n,R,radius,noise,thr,seed", [(20000, 32, 8, .2, .4, 0), (3000, 32, 1.5, .9, .3, 2), (40000, 32, 10, .1, .4, 5),

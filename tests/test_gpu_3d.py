@@ -383,22 +383,23 @@ def test_reference_nms_accuracy_property(sd, noise, n_rays):
             assert nd <= 2
 
 
-@pytest.mark.skipif(os.environ.get("STARDIST_B200_EXPERIMENTAL", "0") != "1",
-                    reason="sdb_nms3d_set_variant(1): bit-identical on the host build (test_face_cone_volume_n_...), not yet run on a GPU")
 @pytest.mark.parametrize("name", list(cases.NMS3D_CASES))
-def test_nms3d_golden_normalised_planes_variant(sd, g3, name):
+def test_nms3d_golden_other_kernel_paths(sd, g3, name):
+    """the goldens through the non-default code paths: volumes on un-normalised planes (variant 0, the round-1 formulation),
+    all heavy stages in one launch (split 0: reference stage order S3 -> S4 -> S5, hulls inside the CTA)"""
     from stardist_b200 import _lib
     from stardist_b200.lib.stardist3d import c_non_max_suppression_inds
     d, p, s, rays, thr, shape = cases.nms3d_inputs(name)
     v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
     lib = _lib.load()
-    lib.sdb_nms3d_set_variant(1)
-    try:
-        keep = c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, thr)
-    finally:
-        lib.sdb_nms3d_set_variant(0)
     want = np.unpackbits(g3[name + "/keep"])[:len(d)].astype(bool)
-    assert np.array_equal(keep, want), "%d decisions differ" % int((keep != want).sum())
+    try:
+        for variant, split, bound in ((0, 1, 1), (1, 0, 1), (0, 0, 0)):
+            lib.sdb_nms3d_set_variant(variant); lib.sdb_nms3d_set_split(split); lib.sdb_nms3d_set_s3_bound(bound)
+            keep = c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, thr)
+            assert np.array_equal(keep, want), "(variant %d, split %d, bound %d): %d decisions differ" % (variant, split, bound, int((keep != want).sum()))
+    finally:
+        lib.sdb_nms3d_set_variant(1); lib.sdb_nms3d_set_split(1); lib.sdb_nms3d_set_s3_bound(1)
 
 
 def _random_polyhedra(rng, n, n_rays, shape, aniso=None):

@@ -29,6 +29,15 @@ def _same_partition(a, b):
     return len(pairs) == len(np.unique(a[a > 0])) == len(np.unique(b[b > 0]))
 
 
+def _relabel_by(a, b):
+    """b with its ids renamed to a's by majority vote"""
+    pairs, counts = np.unique(np.stack([b[b > 0], a[b > 0]], 1), axis=0, return_counts=True)
+    order = np.argsort(counts)
+    lut = np.zeros(int(b.max()) + 1, a.dtype)
+    lut[pairs[order, 0]] = pairs[order, 1]
+    return lut[b]
+
+
 def test_bench_image_1024_equals_oracle(sd):
     """configs[1]: the bench image (1024x1024, ~140 k candidates, ~190 k pair tests, ~1.1 k instances)"""
     if not ref_ext.available(): pytest.skip("oracle/_ref not present")
@@ -59,9 +68,16 @@ def test_big_4096_equals_whole_image_and_oracle(sd):
     ref_labels, ref = pipeline2d.predict_instances(cfg, model.weights, img, 0.5, 0.4, cand_from=model)
     assert np.array_equal(labels, ref_labels) and np.array_equal(res['points'], ref['points'])
     assert len(pb['prob']) == len(res['prob']) > 15000
-    assert _same_partition(labels, lb)
     i, j = np.lexsort(tuple(res['points'].T)), np.lexsort(tuple(pb['points'].T))
-    assert np.array_equal(res['points'][i], pb['points'][j])
+    assert np.array_equal(res['points'][i], pb['points'][j]) and np.array_equal(res['prob'][i], pb['prob'][j])
+    assert np.array_equal(res['coord'][i], pb['coord'][j])
+    # same objects; pixels shared by two overlapping polygons of different blocks go to the block written last
+    # (big.py:319-326) instead of the higher score -- the reference's criterion (tests/test_big.py:104-105) is matching at 0.99
+    assert np.array_equal(labels > 0, lb > 0)
+    from stardist_b200.matching import matching
+    m = matching(labels, lb, thresh=0.99)
+    assert m.accuracy == 1.0 and m.mean_true_score > 0.9999
+    assert np.mean(_relabel_by(labels, lb) != labels) < 1e-4
 
 
 def test_volume_3d_equals_oracle(sd):
