@@ -476,7 +476,7 @@ extern "C" int sdb_nms2d_set_filter(int mode) {
   g_filter_mode = mode;
   return 0;
 }
-extern "C" int sdb_nms2d_set_tail(int on) { g_tail_mode = on ? 1 : 0; return 0; }
+extern "C" int sdb_nms2d_set_tail(int on) { g_tail_mode = on < 0 ? 0 : (on > 2 ? 2 : on); return 0; }
 extern "C" void sdb_nms2d_filter_stats(unsigned long long* out4, int reset) {
   for (int k = 0; k < 4; ++k) { out4[k] = g_filter_stats[k]; if (reset) g_filter_stats[k] = 0; }
 }

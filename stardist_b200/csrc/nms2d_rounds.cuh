@@ -295,12 +295,15 @@ template <int NV> struct ClipCfg { static constexpr int WARPS = (NV <= 32) ? 4 :
 
 template <int NV>
 __device__ __forceinline__ void d_clip(const NmsArrays& A, const int2* pairs, const unsigned int* n_list, const signed char* verdict,
-                                       int2* slow_pairs, unsigned int* counters, unsigned char* clip_smem, int* pend = nullptr) {
+                                       int2* slow_pairs, unsigned int* counters, unsigned char* clip_smem, int* pend = nullptr, int wpb = 0) {
   if (counters[5]) return;
   const unsigned int n_pairs = *n_list;
-  const unsigned int G = (gridDim.x * blockDim.x) >> 5;                       // warps in the grid
-  const unsigned int warp_g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp_g >= n_pairs || lane != 0) return;
+  // wpb: warps of a block that sweep (0 = all); their sweep states occupy the first wpb slots of clip_smem
+  const unsigned int W = wpb ? (unsigned int)wpb : (blockDim.x >> 5);
+  const unsigned int G = gridDim.x * W;                                       // sweeping warps in the grid
+  const unsigned int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int warp_g = blockIdx.x * W + wib;
+  if (wib >= W || warp_g >= n_pairs || lane != 0) return;
   sdclip::ClipSweep<NV, 1>& S = *reinterpret_cast<sdclip::ClipSweep<NV, 1>*>(clip_smem + (size_t)(threadIdx.x >> 5) * sizeof(sdclip::ClipSweep<NV, 1>));
   for (unsigned int t = warp_g; t < n_pairs; t += G) {
     const int2 pr = pairs[t];
@@ -391,10 +394,11 @@ struct GridBarrier {
     dead = dead || s_dead != 0;
   }
 };
+constexpr int TAIL_CLIP_WARPS = 4;                // sweeping warps per block (8 KB of shared sweep state each for 32-gons)
 constexpr unsigned int TAIL_FLUSH_MIN = 1024;     // open pairs that make an exact-sweep phase worth its ~0.2 ms latency
 
-template <int NV>
-__global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
+template <int NV, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_tail(NmsArrays A, TailCtx C) {
   GridBarrier grid(C.bar);
   extern __shared__ __align__(16) unsigned char tail_smem[];
   unsigned int* cnt = C.counters;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
     const bool overflow = vc[1] > C.cap;
     if (C.filter == 1) {
       if (!overflow && n_open_start + vc[1] > C.cap) {    // the open list could overflow: sweep what is there first (both values are stable here)
-        d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
+        d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend, TAIL_CLIP_WARPS);
         grid.sync(); if (grid.dead) return;
         if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
         grid.sync(); if (grid.dead) return;
@@ -443,7 +447,7 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
       const bool must_leave = overflow || vc[4] != 0;
       const unsigned int n_open = vc[9];
       if (n_open > 0 && (must_leave || n_open >= TAIL_FLUSH_MIN || vc[6] == 0)) {
-        d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend);
+        d_clip<NV>(A, C.xpairs, cnt + 9, nullptr, C.slow, cnt, tail_smem, pend, TAIL_CLIP_WARPS);
         grid.sync(); if (grid.dead) return;
         if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
         grid.sync(); if (grid.dead) return;
@@ -451,7 +455,7 @@ __global__ void __launch_bounds__(256) k_tail(NmsArrays A, TailCtx C) {
       leave = must_leave || vc[4] != 0;                   // (a flush that produced slow pairs has swept everything: nothing is pending)
     } else {
       if (!overflow) {
-        d_clip<NV>(A, C.pairs, cnt + 1, nullptr, C.slow, cnt, tail_smem);
+        d_clip<NV>(A, C.pairs, cnt + 1, nullptr, C.slow, cnt, tail_smem, nullptr, TAIL_CLIP_WARPS);
         grid.sync(); if (grid.dead) return;
       }
       leave = overflow || vc[4] != 0;                     // pool overflow in the fast sweep: slow exact path on the host loop
@@ -554,16 +558,23 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
 
   // ---- round 0 as full-occupancy kernels, the remaining rounds in one cooperative launch (k_tail)
   if (g_tail_mode && NV <= 32 && filter != 2 && A.max_abs_coord <= 8191.0) {
-    static int tail_blocks = -1;
-    const size_t tsm = (size_t)8 * sizeof(sdclip::ClipSweep<NV, 1>);
+    // g_tail_mode 1: 3 blocks per SM (no register spills), 2: 4 blocks per SM (64 registers; more warps for the latency-bound
+    // frontier phase, some spills in the sweep)
+    const bool four = g_tail_mode == 2;
+    const void* tail_fn = four ? (const void*)k_tail<NV, 4> : (const void*)k_tail<NV, 3>;
+    static int tail_blocks_v[2] = {-1, -1};
+    int& tail_blocks = tail_blocks_v[four ? 1 : 0];
+    const size_t tsm = (size_t)TAIL_CLIP_WARPS * sizeof(sdclip::ClipSweep<NV, 1>);
     if (tail_blocks < 0) {
       int dev = 0, coop = 0, sms = 0, per_sm = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (coop && cudaFuncSetAttribute(k_tail<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm) == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<NV>, 256, tsm) == cudaSuccess && per_sm > 0)
-        tail_blocks = sms * std::min(per_sm, 3);
+      cudaError_t e1 = four ? cudaFuncSetAttribute(k_tail<NV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm)
+                            : cudaFuncSetAttribute(k_tail<NV, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+      cudaError_t e2 = four ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<NV, 4>, 256, tsm)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tail<NV, 3>, 256, tsm);
+      if (coop && e1 == cudaSuccess && e2 == cudaSuccess && per_sm > 0) tail_blocks = sms * std::min(per_sm, four ? 4 : 3);
       else { tail_blocks = 0; cudaGetLastError(); }
     }
     if (tail_blocks > 0) {
@@ -581,7 +592,7 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       void* args[] = {(void*)&A, (void*)&C};
       sdb::ProfSpan spt;
       sdb::profile_begin("nms2d_tail", st, &spt);
-      SDB_CUDA(cudaLaunchCooperativeKernel((const void*)k_tail<NV>, dim3(tail_blocks), dim3(256), args, tsm, st));
+      SDB_CUDA(cudaLaunchCooperativeKernel(tail_fn, dim3(tail_blocks), dim3(256), args, tsm, st));
       sdb::g_launch_count++;
       sdb::profile_end("nms2d_tail", st, &spt);
       SDB_CUDA(cudaMemcpyAsync(h_pin, d_counters, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
