@@ -459,8 +459,12 @@ def test_nms2d_tail_kernel_equals_host_rounds_and_reference(sd, n, R, radius, no
         host = c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr))
         lib.sdb_nms2d_set_tail(1)
         tail = c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr))
+        lib.sdb_nms2d_set_tail(2)               # 4 blocks per SM variant
+        tail4 = c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr))
+        lib.sdb_nms2d_set_filter(0); lib.sdb_nms2d_set_tail(1)      # no pre-filter: every pair through the exact sweep, nothing deferred
+        tail_nf = c_non_max_suppression_inds(dist, pts, 1, 1, 0, np.float32(thr)) if n <= 20000 else tail
     finally:
-        lib.sdb_nms2d_set_tail(1)
-    assert np.array_equal(tail, host)
+        lib.sdb_nms2d_set_tail(1); lib.sdb_nms2d_set_filter(1)
+    assert np.array_equal(tail, host) and np.array_equal(tail4, host) and np.array_equal(tail_nf, host)
     if want is not None:
         assert np.array_equal(tail, want)
