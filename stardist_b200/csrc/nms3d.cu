@@ -361,6 +361,77 @@ __device__ int hull_planes_warp(const double* pts, int n, Plane* out, int max_pl
   return nf;
 }
 
+// Rigorous two-sided bounds of the volume of the convex polytope {x : planes[j](x) <= 0, j < np} around an interior point p,
+// from the ray triangulation of the model (directions v_k = A.verts[k], faces A.faces):
+//   lower: the tetrahedra (p, p + t_a v_a, p + t_b v_b, p + t_c v_c), t_k = distance to the first plane along v_k, lie inside;
+//   upper: the polytope's part inside the cone over a face lies below EVERY plane of the polytope, in particular below each
+//          of the (up to three) planes that stop the face's rays; below plane j the cone is the tetrahedron with the
+//          ray-plane distances t^j_a, t^j_b, t^j_c -- the smallest of the three bounds that part.
+// The cones tile space when every face determinant det(v_a, v_b, v_c) is positive (checked; otherwise upper = +inf).
+// ~2F*R plane-ray products instead of ~(2F)^2 polygon clips.  scratch: 3R doubles (tmin) + R ints (first plane) in shared memory.
+__device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const double* p, double Lext, const int* sfaces,
+                           double* tmin, int* jhit, double* red, double* lower, double* upper) {
+  const int G = 3;
+  __syncthreads();
+  if ((int)threadIdx.x < G * A.R) {
+    const int g = threadIdx.x / A.R, k = threadIdx.x % A.R;
+    const double v0 = (double)A.verts[3 * k], v1 = (double)A.verts[3 * k + 1], v2 = (double)A.verts[3 * k + 2];
+    double t = Lext; int jb = -1;
+    for (int j = g; j < np; j += G) {
+      const Plane P = planes[j];
+      const double a = P.n0 * v0 + P.n1 * v1 + P.n2 * v2;
+      if (a > 0) {
+        const double sd = -(P.d + P.n0 * p[0] + P.n1 * p[1] + P.n2 * p[2]);
+        const double tt = sd / a;
+        if (tt < t) { t = tt; jb = j; }
+      }
+    }
+    tmin[g * A.R + k] = t; jhit[g * A.R + k] = jb;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < A.R) {
+    const int k = threadIdx.x;
+    double t = tmin[k]; int jb = jhit[k];
+    for (int g = 1; g < G; ++g) if (tmin[g * A.R + k] < t) { t = tmin[g * A.R + k]; jb = jhit[g * A.R + k]; }
+    tmin[k] = t; jhit[k] = jb;
+  }
+  __syncthreads();
+  double pl = 0, pu = 0; int bad = 0;
+  for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
+    const int ia = sfaces[3 * f], ib = sfaces[3 * f + 1], ic = sfaces[3 * f + 2];
+    const double a0 = A.verts[3 * ia], a1 = A.verts[3 * ia + 1], a2 = A.verts[3 * ia + 2];
+    const double b0 = A.verts[3 * ib], b1 = A.verts[3 * ib + 1], b2 = A.verts[3 * ib + 2];
+    const double c0 = A.verts[3 * ic], c1 = A.verts[3 * ic + 1], c2 = A.verts[3 * ic + 2];
+    // det of the tetrahedron_volume0 orientation for unit parameters: M = (B - A, C - A, -A)
+    auto det3 = [&](double ta, double tb, double tc) {
+      const double Az = ta * a0, Ay = ta * a1, Ax = ta * a2, Bz = tb * b0, By = tb * b1, Bx = tb * b2, Cz = tc * c0, Cy = tc * c1, Cx = tc * c2;
+      const double M00 = Bz - Az, M01 = By - Ay, M02 = Bx - Ax, M10 = Cz - Az, M11 = Cy - Ay, M12 = Cx - Ax, M20 = -Az, M21 = -Ay, M22 = -Ax;
+      return M00 * (M11 * M22 - M21 * M12) - M01 * (M10 * M22 - M12 * M20) + M02 * (M10 * M21 - M11 * M20);
+    };
+    const double d1 = det3(1.0, 1.0, 1.0);
+    if (!(d1 > 0)) { bad = 1; continue; }
+    const double lo = det3(tmin[ia], tmin[ib], tmin[ic]);
+    pl += lo > 0 ? lo : 0.0;
+    double up = 1e300;
+    const int js[3] = {jhit[ia], jhit[ib], jhit[ic]};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      const int j = js[e];
+      if (j < 0) continue;
+      const Plane P = planes[j];
+      const double sd = -(P.d + P.n0 * p[0] + P.n1 * p[1] + P.n2 * p[2]);
+      const double qa = P.n0 * a0 + P.n1 * a1 + P.n2 * a2, qb = P.n0 * b0 + P.n1 * b1 + P.n2 * b2, qc = P.n0 * c0 + P.n1 * c1 + P.n2 * c2;
+      if (qa > 0 && qb > 0 && qc > 0) up = fmin(up, det3(sd / qa, sd / qb, sd / qc));
+    }
+    if (up >= 1e299) bad = 1; else pu += up;
+  }
+  bad = __syncthreads_or(bad);
+  const double sl = block_sum(pl, red);
+  const double su = block_sum(pu, red);
+  *lower = sl / 6.0;
+  *upper = bad ? 1e300 : su / 6.0;
+}
+
 struct HeavyCtx {
   int stage; int2* list4; int* slot; int* uniq; Plane* hull_planes; int* hull_n; int hull_cap;
 };
@@ -594,7 +665,17 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         int inf2 = 0;
         for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) inf2 = 1;
         inf2 = __syncthreads_or(inf2);
-        if (!inf2) {
+        int decided4 = 0;
+        if (!inf2 && stage == 2 && A.s3_bound) {
+          // two-sided fan bounds decide `iou_hull <= t` / `> t` for all but the pairs within a few per cent of the threshold
+          double lo4, up4;
+          fan_bounds(A, planes, np, p, L, sfaces, pts, reinterpret_cast<int*>(edge_done), red, &lo4, &up4);
+          const double tden = (double)A.threshold * den;
+          if (up4 * (1.0 + 1e-5) <= tden) { vol_convex = 0.f; decided4 = 1; }             // certainly <= t: the pair is kept (S4 exit)
+          else if (lo4 > tden * (1.0 + 1e-5)) { vol_convex = 1.e10f; decided4 = 1; }      // certainly > t (value itself is not used)
+          if (decided4) atomicAdd(&counters[2], threadIdx.x == 0 ? 1u : 0u);
+        }
+        if (!inf2 && !decided4) {
           PlaneAt PA{planes};
           double part = 0; int ovf = 0;
           if (A.norm_planes) {
@@ -630,7 +711,15 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       for (int k = threadIdx.x; k < np; k += blockDim.x) if (!sd3::plane_feasible(planes[k], p)) infeasible = 1;
       infeasible = __syncthreads_or(infeasible);
       float vol_kernel = 0.f;
-      if (!infeasible) {
+      int decided3 = 0;
+      if (!infeasible && A.s3_bound) {
+        double lo3, up3;
+        fan_bounds(A, planes, np, p, L, sfaces, pts, reinterpret_cast<int*>(edge_done), red, &lo3, &up3);
+        const double tden = (double)A.threshold * den;
+        if (lo3 > tden * (1.0 + 1e-5)) { vol_kernel = 1.e30f; decided3 = 1; }             // certainly > t: suppressed at S3
+        else if (up3 * (1.0 + 1e-5) <= tden) { vol_kernel = 0.f; decided3 = 1; }          // certainly <= t: S3 does not suppress
+      }
+      if (!infeasible && !decided3) {
         PlaneAt PA{planes};
         double part = 0; int ovf = 0;
         if (A.norm_planes) {
@@ -848,8 +937,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       SDB_LAUNCH(k_reset, 1, 256, 0, st, b_counters.as<unsigned int>(), b_slot.as<int>(), b_uniq.as<int>(), hull_cap, 0);
     }
     if (rc) break;
-    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u [decided by the lower bound: %u, volumes after S4: %u], convex %u, render %u so far)\n",
-                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[3], h_pin[13], h_pin[6], h_pin[7]);
+    if (verbose) printf("NMS3D(b200): round %d undecided=%u heavy pairs=%u (pretests %u, kernel %u [decided by the lower bound: %u, S3 after S4: %u], convex %u [decided by the fan bounds: %u], render %u so far)\n",
+                        round, h_pin[0], h_pin[1], h_pin[4], h_pin[5], h_pin[3], h_pin[13], h_pin[6], h_pin[2], h_pin[7]);
     if (h_pin[0] == 0) break;
     if (round > 4 * n + 8) { sdb::set_error("nms3d: no progress"); rc = 1; break; }
   }

@@ -70,7 +70,7 @@ def test_big_4096_equals_whole_image_and_oracle(sd):
     assert len(pb['prob']) == len(res['prob']) > 15000
     i, j = np.lexsort(tuple(res['points'].T)), np.lexsort(tuple(pb['points'].T))
     assert np.array_equal(res['points'][i], pb['points'][j]) and np.array_equal(res['prob'][i], pb['prob'][j])
-    assert np.array_equal(res['coord'][i], pb['coord'][j])
+    assert np.allclose(res['coord'][i], pb['coord'][j], atol=1e-2)      # block-local coordinates + origin vs global: float rounding (reference: atol 1e-2)
     # same objects; pixels shared by two overlapping polygons of different blocks go to the block written last
     # (big.py:319-326) instead of the higher score -- the reference's criterion (tests/test_big.py:104-105) is matching at 0.99
     assert np.array_equal(labels > 0, lb > 0)
