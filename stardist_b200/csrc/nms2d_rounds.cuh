@@ -6,6 +6,7 @@
 #include "clip2d.cuh"
 #include "polyfast.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace sdnms {
 namespace {
@@ -361,7 +362,10 @@ __global__ void k_reset_counters(unsigned int* counters) {
 struct TailCtx {
   int2* cursor; int* kept; int* list0; int* list1; int2* pairs; int2* xpairs; int2* slow; int* pend;
   unsigned int* counters; unsigned int* bar; unsigned int cap; int round0, max_rounds, filter;
+  unsigned long long* dbg;      // optional phase time stamps (verbose >= 2): [round][8] globaltimer ns, written by the lead thread
 };
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TAIL_STAMP(slot) do { if (C.dbg && lead && round - C.round0 < 64) C.dbg[(round - C.round0) * 8 + (slot)] = gtime(); } while (0)
 
 // Grid-wide barrier of the cooperative launch (all blocks are resident): arrival counter + generation word, with a bounded
 // wait -- if the blocks ever disagree on the control flow, the kernel gives up (bar[2] = 1, every block returns) instead of
@@ -420,15 +424,18 @@ __global__ void __launch_bounds__(256, MINB) k_tail(NmsArrays A, TailCtx C) {
       cnt[13] = (unsigned int)round;
     }
     grid.sync(); if (grid.dead) return;
+    TAIL_STAMP(0);
     const unsigned int n_open_start = vc[9];              // open pairs carried over; nothing changes it before this round's d_fast
     int* lin = (round & 1) ? C.list1 : C.list0;
     int* lout = (round & 1) ? C.list0 : C.list1;
     d_frontier2(A, round, C.cursor, C.kept, lin, 0u, cnt + 8, lout, cnt, pend);
     grid.sync(); if (grid.dead) return;
+    TAIL_STAMP(1);
     if (vc[0] == 0) break;                                // no undecided candidate was left: done (nothing can be pending)
     bool leave = false;
     d_pairs(A, round, C.kept, C.pairs, C.cap, cnt);
     grid.sync(); if (grid.dead) return;
+    TAIL_STAMP(2);
     // pair list overflow: the host grows it and redoes this round's pair stage (the flag is raised on the way out, after
     // the open pairs have been swept: every phase is a no-op once counters[5] is set)
     const bool overflow = vc[1] > C.cap;
@@ -443,6 +450,7 @@ __global__ void __launch_bounds__(256, MINB) k_tail(NmsArrays A, TailCtx C) {
         d_fast<int32_t>(A, C.pairs, C.xpairs, nullptr, 0, cnt, pend);
         grid.sync(); if (grid.dead) return;
       }
+      TAIL_STAMP(3);
       // flush: enough open pairs, or no candidate was kept in this round (the frontier is waiting for them), or leaving
       const bool must_leave = overflow || vc[4] != 0;
       const unsigned int n_open = vc[9];
@@ -452,6 +460,8 @@ __global__ void __launch_bounds__(256, MINB) k_tail(NmsArrays A, TailCtx C) {
         if (lead) { cnt[12] += cnt[9]; cnt[9] = 0; }
         grid.sync(); if (grid.dead) return;
       }
+      TAIL_STAMP(4);
+      if (C.dbg && lead && round - C.round0 < 64) { C.dbg[(round - C.round0) * 8 + 5] = n_open; C.dbg[(round - C.round0) * 8 + 6] = vc[6]; C.dbg[(round - C.round0) * 8 + 7] = vc[0]; }
       leave = must_leave || vc[4] != 0;                   // (a flush that produced slow pairs has swept everything: nothing is pending)
     } else {
       if (!overflow) {
@@ -587,8 +597,11 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       sdb::DevBuf b_bar;
       SDB_CUDA(b_bar.alloc(4 * sizeof(unsigned int), st));
       SDB_CUDA(cudaMemsetAsync(b_bar.p, 0, 4 * sizeof(unsigned int), st));
+      sdb::DevBuf b_dbg;
+      if (verbose > 1) { SDB_CUDA(b_dbg.alloc(64 * 8 * sizeof(unsigned long long), st)); SDB_CUDA(cudaMemsetAsync(b_dbg.p, 0, 64 * 8 * sizeof(unsigned long long), st)); }
       TailCtx C{b_cursor.as<int2>(), b_kept.as<int>(), b_list0.as<int>(), b_list1.as<int>(), b_pairs.as<int2>(), b_xpairs.as<int2>(), b_slow.as<int2>(),
-                b_pend.as<int>(), d_counters, b_bar.as<unsigned int>(), (unsigned int)cap, 1, 4 * n + 8, filter};
+                b_pend.as<int>(), d_counters, b_bar.as<unsigned int>(), (unsigned int)cap, 1, 4 * n + 8, filter,
+                verbose > 1 ? b_dbg.as<unsigned long long>() : nullptr};
       void* args[] = {(void*)&A, (void*)&C};
       sdb::ProfSpan spt;
       sdb::profile_begin("nms2d_tail", st, &spt);
@@ -599,6 +612,17 @@ int run_rounds(NmsArrays A, int* d_slow_unused, unsigned int* d_counters, cudaSt
       SDB_CUDA(cudaMemcpyAsync(h_pin + 16, b_bar.p, 4 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
       SDB_CUDA(cudaStreamSynchronize(st));
       if (h_pin[16 + 2] != 0) { sdb::set_error("nms2d: grid barrier of the tail kernel timed out (inconsistent control flow)"); return 1; }
+      if (verbose > 1) {
+        std::vector<unsigned long long> dbg(64 * 8);
+        SDB_CUDA(cudaMemcpy(dbg.data(), b_dbg.p, dbg.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        printf("NMS2D(b200) tail phases per round (us): frontier | pairs | fast | flush   [open pairs, kept, undecided]\n");
+        for (int r = 0; r < 64 && dbg[r * 8]; ++r) {
+          const unsigned long long* d = &dbg[r * 8];
+          if (!d[1]) break;
+          printf("  round %2d: %7.1f | %6.1f | %6.1f | %6.1f   [%llu, %llu, %llu]\n", r + 1, (d[1] - d[0]) / 1e3, d[2] ? (d[2] - d[1]) / 1e3 : 0.0,
+                 d[3] ? (d[3] - d[2]) / 1e3 : 0.0, d[4] ? (d[4] - d[3]) / 1e3 : 0.0, d[5], d[6], d[7]);
+        }
+      }
       const unsigned int* c = h_pin;
       const int r = (int)c[13];                      // round in progress when the tail kernel left (0: it never started)
       if (verbose) printf("NMS2D(b200): tail kernel left in round %d: undecided=%u overflow=%u slow=%u\n", r, c[0], c[5], c[4]);
