@@ -373,8 +373,8 @@ __device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const doub
                            double* tmin, int* jhit, double* red, double* lower, double* upper) {
   const int G = 3;
   __syncthreads();
-  if ((int)threadIdx.x < G * A.R) {
-    const int g = threadIdx.x / A.R, k = threadIdx.x % A.R;
+  for (int idx = threadIdx.x; idx < G * A.R; idx += blockDim.x) {       // (G*R exceeds the block for R > 170)
+    const int g = idx / A.R, k = idx % A.R;
     const double v0 = (double)A.verts[3 * k], v1 = (double)A.verts[3 * k + 1], v2 = (double)A.verts[3 * k + 2];
     double t = Lext; int jb = -1;
     for (int j = g; j < np; j += G) {
@@ -389,8 +389,7 @@ __device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const doub
     tmin[g * A.R + k] = t; jhit[g * A.R + k] = jb;
   }
   __syncthreads();
-  if ((int)threadIdx.x < A.R) {
-    const int k = threadIdx.x;
+  for (int k = threadIdx.x; k < A.R; k += blockDim.x) {
     double t = tmin[k]; int jb = jhit[k];
     for (int g = 1; g < G; ++g) if (tmin[g * A.R + k] < t) { t = tmin[g * A.R + k]; jb = jhit[g * A.R + k]; }
     tmin[k] = t; jhit[k] = jb;
@@ -561,8 +560,8 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       const int G = 3;                                   // pts holds 3R doubles: G partial minima per ray
       double* tmin = pts;
       __syncthreads();
-      if ((int)threadIdx.x < G * A.R) {
-        const int g = threadIdx.x / A.R, k = threadIdx.x % A.R;
+      for (int idx = threadIdx.x; idx < G * A.R; idx += blockDim.x) {     // (G*R exceeds the block for R > 170)
+        const int g = idx / A.R, k = idx % A.R;
         const double v0 = (double)A.verts[3 * k], v1 = (double)A.verts[3 * k + 1], v2 = (double)A.verts[3 * k + 2];
         double t = L;                                    // extent bound of the polytope around p (never binding for closed kernels)
         for (int j = g; j < np; j += G) {
@@ -576,7 +575,7 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         tmin[g * A.R + k] = t;
       }
       __syncthreads();
-      if ((int)threadIdx.x < A.R) tmin[threadIdx.x] = fmin(tmin[threadIdx.x], fmin(tmin[A.R + threadIdx.x], tmin[2 * A.R + threadIdx.x]));
+      for (int k = threadIdx.x; k < A.R; k += blockDim.x) tmin[k] = fmin(tmin[k], fmin(tmin[A.R + k], tmin[2 * A.R + k]));
       __syncthreads();
       double partl = 0;
       for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
