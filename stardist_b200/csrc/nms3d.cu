@@ -184,23 +184,54 @@ __device__ __forceinline__ void for_neighbors(const Arr& A, int c, F&& f) {
 // k_frontier is pull based over the COMPACTED list of undecided candidates (double buffered; round 0 reads the identity):
 // a candidate without an undecided / just-kept neighbour of higher score that reaches it is kept and appended to kept_list.
 __global__ void __launch_bounds__(256) k_frontier(Arr A, int round, const int* __restrict__ list_in, int n_all, int* __restrict__ list_out,
-                                                  int* __restrict__ kept_list, unsigned int* __restrict__ counters) {
+                                                  int* __restrict__ kept_list, int2* __restrict__ cursor, unsigned int* __restrict__ counters) {
+  // one WARP per undecided candidate: the lanes test 32 items of a cell per step (a chain of dependent loads otherwise), and
+  // the scan of the 27 cells RESUMES where it stopped in the previous round (cursor = cell 0..26, offset): an item that did
+  // not block once -- index above c, decided, or out of reach -- never blocks later, so every neighbourhood is walked once
+  // over all rounds.
   const unsigned int n_in = list_in ? counters[10] : (unsigned int)n_all;
+  const unsigned int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
   const int kept_now = ST_KEPT_BASE + round;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+  unsigned int n_und = 0;
+  for (unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_in; i += warps) {
     const int c = list_in ? list_in[i] : (int)i;
     if (A.state[c] != ST_UNDECIDED) continue;
-    atomicAdd(&counters[0], 1u);
+    ++n_und;
+    const float* pc = A.points + 3 * c;
+    int cz = 0, cy = 0, cx = 0;
+    if (!A.G.all_pairs) {
+      cz = cell_of(pc[0], A.G.mn[0], A.G.cell, A.G.g[0]); cy = cell_of(pc[1], A.G.mn[1], A.G.cell, A.G.g[1]);
+      cx = cell_of(pc[2], A.G.mn[2], A.G.cell, A.G.g[2]);
+    }
+    int2 cur = cursor[c];
     bool blocked = false;
-    for_neighbors(A, c, [&](int h, const float* pc) {
-      const int sh = A.state[h];
-      if (sh != ST_UNDECIDED && sh != kept_now) return true;
-      if (reaches(A, h, pc)) { blocked = true; return false; }
-      return true;
-    });
-    if (!blocked) { A.state[c] = kept_now; kept_list[atomicAdd(&counters[8], 1u)] = c; }
-    else list_out[atomicAdd(&counters[9], 1u)] = c;
+    for (int k = cur.x; k < 27 && !blocked; ++k) {
+      const int zz = cz + k / 9 - 1, yy = cy + (k / 3) % 3 - 1, xx = cx + k % 3 - 1;
+      if (zz < 0 || zz >= A.G.g[0] || yy < 0 || yy >= A.G.g[1] || xx < 0 || xx >= A.G.g[2]) { cur.x = k + 1; cur.y = 0; continue; }
+      const int cell = (zz * A.G.g[1] + yy) * A.G.g[2] + xx;
+      const unsigned int b = A.cell_start[cell], e = A.cell_start[cell + 1];
+      for (unsigned int t0 = b + (unsigned int)cur.y; t0 < e && !blocked; t0 += 32) {
+        const unsigned int t = t0 + lane;
+        bool hit = false;
+        if (t < e) {
+          const int h = A.items[t];
+          if (h < c) {
+            const int sh = A.state[h];
+            if (sh == ST_UNDECIDED || sh == kept_now) hit = reaches(A, h, pc);
+          }
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, hit);
+        if (m) { blocked = true; cur.x = k; cur.y = (int)(t0 + (unsigned int)(__ffs(m) - 1) - b); }
+      }
+      if (!blocked) { cur.x = k + 1; cur.y = 0; }
+    }
+    if (lane == 0) {
+      cursor[c] = cur;
+      if (!blocked) { A.state[c] = kept_now; kept_list[atomicAdd(&counters[8], 1u)] = c; }
+      else list_out[atomicAdd(&counters[9], 1u)] = c;
+    }
   }
+  if (lane == 0 && n_und) atomicAdd(&counters[0], n_und);
 }
 
 // S1 + S2 for every (h kept in this round, undecided c > h that h reaches); emits the pairs that need the heavy stages.
@@ -821,6 +852,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   if (n_rays < 4 || n_rays > MAXR || n_faces > MAXF || n_faces < 1) { sdb::set_error("nms3d: unsupported n_rays / n_faces"); return 1; }
   sdb::DevBuf b_vol, b_bbox, b_ro, b_roi, b_rii, b_terms, b_aniso, b_stats, b_cellpt, b_counts, b_start, b_items, b_state, b_pairs, b_counters, b_list0, b_list1, b_kept;
   SDB_CUDA(b_list0.alloc((size_t)n * 4, st)); SDB_CUDA(b_list1.alloc((size_t)n * 4, st)); SDB_CUDA(b_kept.alloc((size_t)n * 4, st));
+  sdb::DevBuf b_cursor; SDB_CUDA(b_cursor.alloc((size_t)n * 8, st)); SDB_CUDA(cudaMemsetAsync(b_cursor.p, 0, (size_t)n * 8, st));
   SDB_CUDA(b_vol.alloc((size_t)n * 4, st)); SDB_CUDA(b_bbox.alloc((size_t)n * 24, st)); SDB_CUDA(b_ro.alloc((size_t)n * 4, st));
   SDB_CUDA(b_roi.alloc((size_t)n * 4, st)); SDB_CUDA(b_rii.alloc((size_t)n * 4, st)); SDB_CUDA(b_terms.alloc((size_t)n * 12, st));
   SDB_CUDA(b_aniso.alloc(16, st)); SDB_CUDA(b_stats.alloc(32, st)); SDB_CUDA(b_state.alloc((size_t)n * 4, st));
@@ -898,7 +930,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
     {
       const int* lin = round == 0 ? (const int*)nullptr : ((round & 1) ? b_list1.as<int>() : b_list0.as<int>());
       int* lout = (round & 1) ? b_list0.as<int>() : b_list1.as<int>();
-      SDB_LAUNCH(k_frontier, std::min(cdiv(n, 256), 148 * 8), 256, 0, st, A, round, lin, n, lout, b_kept.as<int>(), b_counters.as<unsigned int>());
+      SDB_LAUNCH(k_frontier, std::min(cdiv((long long)n * 32, 256), 148 * 8), 256, 0, st, A, round, lin, n, lout, b_kept.as<int>(), b_cursor.as<int2>(), b_counters.as<unsigned int>());
     }
     sdb::profile_end("nms3d_frontier", st, &sp);
     for (;;) {
