@@ -398,7 +398,8 @@ struct GridBarrier {
     dead = dead || s_dead != 0;
   }
 };
-constexpr int TAIL_CLIP_WARPS = 4;                // sweeping warps per block (8 KB of shared sweep state each for 32-gons)
+constexpr int TAIL_CLIP_WARPS = 8;                // sweeping warps per block (8 KB of shared sweep state each for 32-gons): all of them --
+                                                  // a flush of <= 3.5 k pairs is then one sweep latency (~0.2 ms) long (r02h: 4 warps -> 0.4 ms)
 constexpr unsigned int TAIL_FLUSH_MIN = 1024;     // open pairs that make an exact-sweep phase worth its ~0.2 ms latency
 
 template <int NV, int MINB>
