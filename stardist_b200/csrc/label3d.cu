@@ -29,7 +29,7 @@ namespace {
 using sdb::cdiv;
 constexpr int MAXR = sd3::SD3_MAX_RAYS, MAXF = sd3::SD3_MAX_FACES;
 constexpr int RANK_NONE = 0x7fffffff;
-__device__ int g_cull3d = 1;      // sphere culling in k_paint3d (sdb_label3d_set_cull; results identical)
+__device__ int g_cull3d = 3;      // bit 0: sphere culling, bit 1: direction bins in k_paint3d (sdb_label3d_set_cull; results identical)
 
 struct PaintArgs {
   const float* dist; const float* points; const float* verts; const int* faces;
@@ -51,10 +51,73 @@ __global__ void k_hull3d(PaintArgs A, double* __restrict__ hull_planes, int* __r
                                           A.n_faces, ed, st, 4 * MAXR);
 }
 
+// ---- direction bins of the ray triangulation ---------------------------------------------------------------------------
+// inside_polyhedron is an OR over the F tetrahedra (centre, A, B, C); a voxel can only lie in a tetrahedron whose cone
+// (over the spherical triangle of the ray directions, the same for every polyhedron of a call) contains its direction from
+// the centre.  The directions are binned on a cube map (6 faces x 4 x 4 cells); every bin lists the faces whose cone's
+// bounding cap meets the bin's bounding cap widened by 0.05 rad -- a superset of the faces that can answer true, so testing
+// only those gives the same boolean as testing all F (the float determinants of a tetrahedron whose cone is > 0.05 rad away
+// are negative by a margin ~1e4 x their rounding).  The same lists put the kernel plane most likely to be violated first.
+constexpr int BIN_B = 4, BIN_N = 6 * BIN_B * BIN_B, BIN_CAP = 64;
+struct FaceBins { int* count; int* faces; };     // count[BIN_N] (-1: list overflow -> all faces), faces[BIN_N][BIN_CAP]
+
+__device__ __forceinline__ int bin_of(float u0, float u1, float u2) {
+  const float a0 = fabsf(u0), a1 = fabsf(u1), a2 = fabsf(u2);
+  int m = 0; float am = a0, um = u0, p = u1, q = u2;
+  if (a1 > am) { m = 1; am = a1; um = u1; p = u0; q = u2; }
+  if (a2 > am) { m = 2; am = a2; um = u2; p = u0; q = u1; }
+  if (!(am > 0.f)) return -1;
+  const float inv = 1.f / am;
+  int ia = (int)((p * inv + 1.f) * (0.5f * BIN_B)), ib = (int)((q * inv + 1.f) * (0.5f * BIN_B));
+  ia = min(max(ia, 0), BIN_B - 1); ib = min(max(ib, 0), BIN_B - 1);
+  return ((m * 2 + (um < 0.f ? 1 : 0)) * BIN_B + ia) * BIN_B + ib;
+}
+
+// one thread per bin
+__global__ void k_build_bins(const float* __restrict__ verts, const int* __restrict__ faces, int n_faces, FaceBins B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= BIN_N) return;
+  const int ib = b % BIN_B, ia = (b / BIN_B) % BIN_B, ms = b / (BIN_B * BIN_B), m = ms >> 1;
+  const double sgn = (ms & 1) ? -1.0 : 1.0;
+  auto dir = [&](double a, double bb, double* o) {
+    double v[3];
+    v[m] = sgn; v[m == 0 ? 1 : 0] = a; v[m == 2 ? 1 : 2] = bb;
+    const double l = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    o[0] = v[0] / l; o[1] = v[1] / l; o[2] = v[2] / l;
+  };
+  const double a0 = -1.0 + 2.0 * ia / BIN_B, a1 = -1.0 + 2.0 * (ia + 1) / BIN_B, b0 = -1.0 + 2.0 * ib / BIN_B, b1 = -1.0 + 2.0 * (ib + 1) / BIN_B;
+  double c[3], k[3];
+  dir(0.5 * (a0 + a1), 0.5 * (b0 + b1), c);
+  double hb = 0;
+  const double ca[4] = {a0, a0, a1, a1}, cb[4] = {b0, b1, b0, b1};
+  for (int q = 0; q < 4; ++q) { dir(ca[q], cb[q], k); hb = fmax(hb, acos(fmin(1.0, c[0] * k[0] + c[1] * k[1] + c[2] * k[2]))); }
+  int cnt = 0;
+  for (int f = 0; f < n_faces; ++f) {
+    double n[3][3], ax[3] = {0, 0, 0};
+    bool ok = true;
+    for (int e = 0; e < 3; ++e) {
+      const float* v = verts + 3 * faces[3 * f + e];
+      const double l = sqrt((double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2]);
+      if (!(l > 0)) ok = false;
+      for (int d = 0; d < 3; ++d) { n[e][d] = v[d] / (l > 0 ? l : 1.0); ax[d] += n[e][d]; }
+    }
+    const double la = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+    bool take = true;
+    if (ok && la > 1e-6) {
+      double hf = 0;
+      for (int e = 0; e < 3; ++e) hf = fmax(hf, acos(fmax(-1.0, fmin(1.0, (ax[0] * n[e][0] + ax[1] * n[e][1] + ax[2] * n[e][2]) / la))));
+      const double ang = acos(fmax(-1.0, fmin(1.0, (ax[0] * c[0] + ax[1] * c[1] + ax[2] * c[2]) / la)));
+      take = ang <= hf + hb + 0.05;
+    }
+    if (take) { if (cnt < BIN_CAP) B.faces[b * BIN_CAP + cnt] = f; ++cnt; }
+  }
+  B.count[b] = cnt <= BIN_CAP ? cnt : -1;
+}
+
 // one block per polyhedron
 __global__ void __launch_bounds__(256)
 k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img, int* __restrict__ debug_img,
-          const double* __restrict__ hull_planes, const int* __restrict__ hull_count) {
+          const double* __restrict__ hull_planes, const int* __restrict__ hull_count, FaceBins B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* pv = reinterpret_cast<float*>(smem_raw);                         // [R][3]
   int* sfaces = reinterpret_cast<int*>(pv + 3 * A.n_rays);                // [F][3]
@@ -117,7 +180,7 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
       }
     }
     const double r = sqrt(r2);
-    const bool ok = g_cull3d && A.mode <= 1 && nmin >= 1e-6 * r2 && r2 > 0;
+    const bool ok = (g_cull3d & 1) && A.mode <= 1 && nmin >= 1e-6 * r2 && r2 > 0;
     const double ro = r * 1.001 + 0.05, ri = rho * 0.999 - 0.05;
     cull_out2 = ok ? ro * ro : 1e300;
     cull_in2 = (ok && ri > 0) ? ri * ri : -1.0;
@@ -142,6 +205,33 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
       return true;
     };
     if (inside) { /* inside the kernel's inscribed ball: labelled in modes "full" and "kernel" */ }
+    else if (A.mode == 0 && B.count && (g_cull3d & 2)) {
+      // kernel || polyhedron with the direction bins: the tetrahedra whose cone can contain this voxel first (the OR over
+      // all F reduces to them); if none contains it, the kernel planes -- the binned faces' planes first, they are the
+      // ones an outside voxel violates -- decide
+      const int b = bin_of(fz - center[0], fy - center[1], fx - center[2]);
+      const int cnt = b >= 0 ? __ldg(B.count + b) : -1;
+      if (cnt < 0) inside = in_planes(A.n_faces) || sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces);
+      else {
+        const int* lst = B.faces + b * BIN_CAP;
+        bool poly = false;
+        for (int i = 0; i < cnt && !poly; ++i) {
+          const int f = __ldg(lst + i);
+          const int iA = sfaces[3 * f], iB = sfaces[3 * f + 1], iC = sfaces[3 * f + 2];
+          poly = sd3::inside_tetrahedron(fz, fy, fx, center[0], center[1], center[2], pv[3 * iA], pv[3 * iA + 1], pv[3 * iA + 2],
+                                         pv[3 * iB], pv[3 * iB + 1], pv[3 * iB + 2], pv[3 * iC], pv[3 * iC + 1], pv[3 * iC + 2]);
+        }
+        if (poly) inside = true;
+        else {
+          bool ker = true;
+          for (int i = 0; i < cnt && ker; ++i) {
+            const int f = __ldg(lst + i);
+            ker = !(hs[4 * f] * fz + hs[4 * f + 1] * fy + hs[4 * f + 2] * fx + hs[4 * f + 3] > 0);
+          }
+          inside = ker && in_planes(A.n_faces);
+        }
+      }
+    }
     else if (A.mode == 0) inside = in_planes(A.n_faces) || sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces);
     else if (A.mode == 1) inside = in_planes(A.n_faces);
     else if (A.mode == 2) inside = (n_hull >= 4) && in_planes(n_hull);
@@ -236,7 +326,7 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
     }
     for (int i = 0; i < n_polys; ++i) {
       A.poly0 = i;
-      SDB_LAUNCH(k_paint3d, 1, 256, smem, st, A, nullptr, nullptr, nullptr, b_hull.as<double>(), b_hcnt.as<int>());
+      SDB_LAUNCH(k_paint3d, 1, 256, smem, st, A, nullptr, nullptr, nullptr, b_hull.as<double>(), b_hcnt.as<int>(), FaceBins{nullptr, nullptr});
     }
     return 0;
   }
@@ -262,8 +352,15 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
     }
     sdb::ProfSpan sp;
     sdb::profile_begin("nms3d_paint", st, &sp);
+    sdb::DevBuf b_bcnt, b_bfaces;
+    FaceBins FB{nullptr, nullptr};
+    if (render_mode == 0) {
+      SDB_CUDA(b_bcnt.alloc(BIN_N * sizeof(int), st)); SDB_CUDA(b_bfaces.alloc((size_t)BIN_N * BIN_CAP * sizeof(int), st));
+      FB.count = b_bcnt.as<int>(); FB.faces = b_bfaces.as<int>();
+      SDB_LAUNCH(k_build_bins, cdiv(BIN_N, 96), 96, 0, st, d_verts, d_faces, n_faces, FB);
+    }
     SDB_LAUNCH(k_paint3d, n_polys, 256, smem, st, A, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
-               render_mode == 4 ? b_debug.as<int>() : nullptr, b_hull.as<double>(), b_hcnt.as<int>());
+               render_mode == 4 ? b_debug.as<int>() : nullptr, b_hull.as<double>(), b_hcnt.as<int>(), FB);
     sdb::profile_end("nms3d_paint", st, &sp);
   }
   SDB_LAUNCH(k_finalize3d, fb, 256, 0, st, d_result, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
@@ -273,7 +370,7 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
 
 // sphere culling of the bounding-box voxels in k_paint3d: 1 (default) on, 0 off -- identical label maps (tests)
 extern "C" int sdb_label3d_set_cull(int on) {
-  const int v = on ? 1 : 0;
+  const int v = on & 3;          // 0: off, 1: sphere culling, 2: direction bins, 3: both (default)
   SDB_CUDA(cudaMemcpyToSymbol(g_cull3d, &v, sizeof(int)));
   return 0;
 }

@@ -508,11 +508,12 @@ def test_paint3d_sphere_culling_is_result_neutral(sd):
             try:
                 lib.sdb_label3d_set_cull(0)
                 a = c_polyhedron_to_label(d, p, v, f, lab, mode, 0, ov, -1, shape)
-                lib.sdb_label3d_set_cull(1)
-                b = c_polyhedron_to_label(d, p, v, f, lab, mode, 0, ov, -1, shape)
+                for cull in (1, 2, 3):          # sphere culling, direction bins, both (default)
+                    lib.sdb_label3d_set_cull(cull)
+                    b = c_polyhedron_to_label(d, p, v, f, lab, mode, 0, ov, -1, shape)
+                    assert np.array_equal(a, b), (mode, ov, cull, int((a != b).sum()))
             finally:
-                lib.sdb_label3d_set_cull(1)
-            assert np.array_equal(a, b), (mode, ov, int((a != b).sum()))
+                lib.sdb_label3d_set_cull(3)
 
 
 def test_sparse_slab_forward_equals_dense_forward(sd, monkeypatch):
