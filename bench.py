@@ -9,7 +9,7 @@ One JSON line.  What it holds (BASELINE.json: "instances/sec (predict_instances 
   value / e2e / roofline        configs[1]: StarDist2D.predict_instances on one synthetic 1024x1024 image (default Config2D,
                                 n_rays 32, grid (1,1)), K timed steps.  `value` = instances/s with the padded input resident
                                 in HBM; `e2e` = host image in -> host labels + polygons out through the public API.
-                                N > 1: every rank processes its own image (weak scaling, no data-path collective).
+                                N > 1: every rank processes its own copy of the image (weak scaling, no data-path collective).
   value_3d / e2e_3d / roofline_3d   configs[2]: StarDist3D.predict_instances on a 128x512x512 volume, Rays_GoldenSpiral(96),
                                 default Config3D; same two timings (fewer steps, stated in config.steps_3d).
   big_2d / big_3d               configs[3] / [4]: predict_instances_big on a tiled 8192x8192 image / a 512^3 anisotropic volume,
@@ -299,7 +299,7 @@ def main():
     # ------------------------------------------------------------------ configs[1]: 2-D 1024^2
     cfg = Config2D(n_rays=N_RAYS)
     model = StarDist2D(cfg, name=None, basedir=None, weights=bench_data.bench_weights_2d(cfg))
-    img, _ = bench_data.synthetic_image(SHAPE, seed=rank)
+    img, _ = bench_data.synthetic_image(SHAPE, seed=0)        # every rank works on an identical copy (weak scaling: fixed work per GPU)
     x_dev = torch.from_numpy(img[None, ..., None]).cuda()
     for _ in range(warm):
         model.predict_instances_device(x_dev, SHAPE, prob_thresh=PROB_THRESH, nms_thresh=NMS_THRESH)
@@ -362,7 +362,7 @@ def main():
             steps3 = max(2, min(args.steps, 4)); warm3 = 2
             cfg3 = bench_data.bench_config_3d(N_RAYS_3D)
             model3 = StarDist3D(cfg3, name=None, basedir=None, weights=bench_data.bench_weights_3d(cfg3))
-            vol, _ = bench_data.synthetic_volume(SHAPE_3D, seed=rank)
+            vol, _ = bench_data.synthetic_volume(SHAPE_3D, seed=0)
             x3 = torch.from_numpy(vol[None, ..., None]).cuda()
             for _ in range(warm3):
                 model3.predict_instances_device(x3, SHAPE_3D, prob_thresh=PROB_THRESH_3D, nms_thresh=NMS_THRESH_3D)

@@ -371,8 +371,16 @@ class StarDistBase:
         torch.cuda.current_stream().synchronize()
         def host_copy(p):
             if copy_threads and p.numel() >= (1 << 22):
-                out = torch.empty(p.shape, dtype=p.dtype)
-                out.copy_(p)
+                # torchrun starts every rank with OMP_NUM_THREADS=1: give this one large copy its threads back
+                import os
+                nt = torch.get_num_threads()
+                want = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+                try:
+                    if want > nt: torch.set_num_threads(want)
+                    out = torch.empty(p.shape, dtype=p.dtype)
+                    out.copy_(p)
+                finally:
+                    if want > nt: torch.set_num_threads(nt)
                 return out.numpy()
             return p.numpy().copy()
         return [None if p is None else host_copy(p) for p in pinned], sum(0 if p is None else p.numel() * p.element_size() for p in pinned)
@@ -662,7 +670,11 @@ class StarDistBase:
                 return None, None
             if not want_labels:
                 return None, polys_all
+            import os, time
+            t0 = time.perf_counter()
             (lab_np,), nbytes = self._to_host([labels_d], copy_threads=True)
+            if os.environ.get("STARDIST_B200_BIG_TIMING") == "1":
+                print("[big rank 0] %-22s %.1f ms" % ("label map D2H + copy", 1e3 * (time.perf_counter() - t0)), flush=True)
             self._stats['d2h_bytes'] = self._stats.get('d2h_bytes', 0) + nbytes
             if labels_out is None:
                 labels_out = lab_np if lab_np.dtype == np.dtype(labels_out_dtype) else lab_np.astype(labels_out_dtype)

@@ -134,11 +134,17 @@ def run_sharded_device(blocks, process_device, shape_out, axes_out, want_labels=
       * the polygon dicts (a few hundred bytes per object) are gathered with gather_object and concatenated in id order.
     Returns (labels int32 CUDA tensor | None, polys_all) on rank 0, (None, None) elsewhere.  world == 1: same code
     path without the collectives."""
-    import ctypes
+    import ctypes, os, time
     from . import _lib as L
     lib = L.require_cuda()
     rank, world = rank_world(group)
     dev = torch.device("cuda", torch.cuda.current_device())
+    timing = os.environ.get("STARDIST_B200_BIG_TIMING") == "1"
+    T = [time.perf_counter()]
+    def lap(name):
+        if timing:
+            torch.cuda.synchronize(); T.append(time.perf_counter())
+            print("[big rank %d] %-22s %.1f ms" % (rank, name, 1e3 * (T[-1] - T[-2])), flush=True)
     nb = len(blocks)
     nd = len(shape_out)
     mine = {}
@@ -163,10 +169,12 @@ def run_sharded_device(blocks, process_device, shape_out, axes_out, want_labels=
             mine[b.id] = (None, polys)
         else:
             mine[b.id] = (tile if want_labels else None, polys)
+    lap("blocks (%d)" % len(mine))
     if world > 1:
         counts_d = counts.to(dev)
         dist.all_reduce(counts_d, op=dist.ReduceOp.SUM, group=group)
         counts = counts_d.cpu()
+        lap("all-reduce counts")
     offsets = block_offsets(counts.numpy())
     if world > 1 and want_labels:
         ops, remote = [], {}
@@ -189,18 +197,67 @@ def run_sharded_device(blocks, process_device, shape_out, axes_out, want_labels=
                 origin = [s.start for s in b.slice_write(axes_out)]
                 L.check(lib.sdb_label_write(L.ptr(tile), nd, L.iarr(tile.shape), int(offsets[b.id]) - 1, L.ptr(glob), L.iarr(shape_out),
                                            L.iarr(origin), L.stream_ptr()))
+    lap("tiles -> rank 0 + scatter")
     polys_by_block = {bid: p for bid, (_, p) in mine.items()}
     if world > 1:
-        gathered = [None] * world if rank == 0 else None
-        dist.gather_object(polys_by_block, gathered, dst=0, group=group)
+        polys_by_block = _gather_polys(polys_by_block, rank, world, dev, group)
+        lap("polygons -> rank 0")
         if rank != 0:
             return None, None
-        polys_by_block = {}
-        for d in gathered:
-            polys_by_block.update(d)
     polys_all = {}
     for b in blocks:
         for k, v in polys_by_block[b.id].items():
             polys_all.setdefault(k, []).append(v)
     polys_all = {k: (np.concatenate(v) if k in OBJECT_KEYS else v[0]) for k, v in polys_all.items()}
     return glob, polys_all
+
+
+def _gather_polys(polys_by_block, rank, world, dev, group):
+    """per-block polygon dicts of all ranks -> rank 0 ({block id: dict}; None elsewhere).  The object arrays (coord / dist,
+    points, prob, ...: ~300 B per object, tens of MB for a large image) travel as raw bytes through NCCL point-to-point --
+    one buffer per rank and key, straight from / into device memory; only the small description (dtypes, shapes, per-block
+    counts, non-array entries) goes through gather_object (pickle)."""
+    bids = sorted(polys_by_block)
+    keys = sorted(k for k in OBJECT_KEYS if bids and k in polys_by_block[bids[0]] and isinstance(polys_by_block[bids[0]][k], np.ndarray))
+    packed, meta = {}, dict(bids=bids, keys={}, other={})
+    for k in keys:
+        arrs = [np.ascontiguousarray(polys_by_block[b][k]) for b in bids]
+        cat = np.concatenate(arrs) if arrs else np.zeros(0)
+        meta['keys'][k] = (cat.dtype.str, tuple(cat.shape[1:]), [len(a) for a in arrs])
+        packed[k] = torch.from_numpy(cat.view(np.uint8).reshape(-1)).to(dev) if cat.size else None
+    if bids:
+        meta['other'] = {k: v for k, v in polys_by_block[bids[0]].items() if k not in keys}
+    metas = [None] * world if rank == 0 else None
+    dist.gather_object(meta, metas, dst=0, group=group)
+    ops, recv = [], {}
+    if rank == 0:
+        for r in range(1, world):
+            for k, (dt, tail, counts) in metas[r]['keys'].items():
+                nbytes = int(sum(counts)) * int(np.prod(tail, dtype=np.int64)) * np.dtype(dt).itemsize
+                if nbytes:
+                    recv[(r, k)] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    ops.append(dist.P2POp(dist.irecv, recv[(r, k)], r, group=group))
+    else:
+        for k in keys:
+            if packed[k] is not None:
+                ops.append(dist.P2POp(dist.isend, packed[k], 0, group=group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if rank != 0:
+        return None
+    out = dict(polys_by_block)
+    for r in range(1, world):
+        m = metas[r]
+        parts = {}
+        for k, (dt, tail, counts) in m['keys'].items():
+            buf = recv.get((r, k))
+            flat = buf.cpu().numpy().view(np.dtype(dt)) if buf is not None else np.zeros(0, np.dtype(dt))
+            arr = flat.reshape((-1,) + tuple(tail))
+            offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+            parts[k] = [arr[offs[i]:offs[i + 1]] for i in range(len(counts))]
+        for i, b in enumerate(m['bids']):
+            d = {k: parts[k][i] for k in m['keys']}
+            d.update(m['other'])
+            out[b] = d
+    return out

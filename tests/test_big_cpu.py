@@ -215,3 +215,43 @@ def test_vectorised_responsibility_equals_scalar_rule():
                 assert e == inv[i] and (e or r == mine[i])
                 n_checked += 1
     assert n_checked > 10000
+
+
+def _worker_gather(rank, world, port, q):
+    import torch, torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from stardist_b200 import parallel_big
+    rng = np.random.default_rng(100 + rank)
+    mine = {}
+    for bid in range(rank, 7, world):                    # rank 2 of 3 owns blocks 2, 5; block counts incl. an empty block
+        n = 0 if bid == 4 else int(rng.integers(1, 30))
+        mine[bid] = dict(prob=rng.random(n).astype(np.float32), points=rng.integers(0, 1000, (n, 2)), coord=rng.random((n, 2, 32)).astype(np.float32),
+                         extra="not-an-array-%d" % rank)
+    got = parallel_big._gather_polys(mine, rank, world, torch.device("cpu"), None)
+    mine_all = [None] * world if rank == 0 else None
+    dist.gather_object(mine, mine_all, dst=0)
+    if rank == 0:
+        q.put((got, mine_all))
+    dist.barrier(); dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_polygon_gather_as_raw_bytes_equals_object_gather(world):
+    """parallel_big._gather_polys (object arrays as raw bytes point to point, only the description pickled) returns on rank 0
+    exactly the per-block dicts a plain gather_object returns -- incl. empty blocks and ranks without blocks (world 8, 7 blocks)"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + world
+    procs = [ctx.Process(target=_worker_gather, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    got, mine_all = q.get(timeout=120)
+    for p in procs: p.join(timeout=60)
+    want = {}
+    for d in mine_all: want.update(d)
+    assert sorted(got) == sorted(want) == list(range(7))
+    for b in want:
+        assert set(got[b]) == set(want[b])
+        for k in ('prob', 'points', 'coord'):
+            assert got[b][k].dtype == want[b][k].dtype and np.array_equal(got[b][k], want[b][k]), (b, k)
