@@ -494,6 +494,108 @@ __global__ void __launch_bounds__(128) k_hulls(Arr A, HeavyCtx X, const unsigned
   }
 }
 
+// Stage S3 lower bound, ONE WARP per pair (the first of the three launches of a round).  The work of a pair is small (2F
+// planes, R rays x 2F plane-ray products, F tetrahedra) and a CTA per pair spent it mostly in block-wide barriers: 46 us per
+// pair, 41 ms per bench volume; a warp needs no barrier.  Any valid lower bound decides correctly (the summation order of the
+// fan volume differs from the block-wide version by ulps; the 1e-5 margin covers it): decided pairs are suppressed, the rest
+// go to X.list4 and their polyhedra are registered for k_hulls -- exactly what k_heavy's stage 1 does.
+__global__ void __launch_bounds__(256) k_s3_bound_warp(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counters, unsigned int pair_cap,
+                                                       HeavyCtx X, int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char wsm[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (wid >= warps_per_block) return;
+  const size_t per_warp = (((size_t)2 * A.F * sizeof(Plane) + (size_t)A.R * sizeof(double) + (size_t)6 * A.R * sizeof(float)) + 15) / 16 * 16;
+  unsigned char* base = wsm + (size_t)wid * per_warp;
+  Plane* planes = reinterpret_cast<Plane*>(base);                               // [2F]
+  double* tmin = reinterpret_cast<double*>(base + (size_t)2 * A.F * sizeof(Plane));      // [R]
+  float* pv1 = reinterpret_cast<float*>(base + (size_t)2 * A.F * sizeof(Plane) + (size_t)A.R * sizeof(double));   // [R][3]
+  float* pv2 = pv1 + 3 * A.R;
+  const unsigned int n_pairs = min(counters[1], pair_cap);
+  const int np = 2 * A.F;
+  for (;;) {
+    unsigned int pi = 0;
+    if (lane == 0) pi = atomicAdd(&counters[14], 1u);
+    pi = __shfl_sync(0xffffffffu, pi, 0);
+    if (pi >= n_pairs) break;
+    const int h = pairs[pi].x, c = pairs[pi].y;
+    if (A.state[c] == ST_SUPPRESSED) continue;                        // (warp-uniform)
+    const float c1[3] = {A.points[3 * h], A.points[3 * h + 1], A.points[3 * h + 2]};
+    const float c2[3] = {A.points[3 * c], A.points[3 * c + 1], A.points[3 * c + 2]};
+    const float* d1 = A.dist + (size_t)h * A.R; const float* d2 = A.dist + (size_t)c * A.R;
+    __syncwarp();
+    for (int j = lane; j < A.R; j += 32)
+      for (int k = 0; k < 3; ++k) {
+        pv1[3 * j + k] = c1[k] + d1[j] * A.verts[3 * j + k];
+        pv2[3 * j + k] = c2[k] + d2[j] * A.verts[3 * j + k];
+      }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&counters[5], 1u);
+    for (int f = lane; f < A.F; f += 32) {
+      const int ia = A.faces[3 * f], ib = A.faces[3 * f + 1], ic = A.faces[3 * f + 2];
+      double hs[4];
+      sd3::build_halfspace(&pv1[3 * ia], &pv1[3 * ib], &pv1[3 * ic], hs);
+      Plane P; P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f] = P;
+      sd3::build_halfspace(&pv2[3 * ia], &pv2[3 * ib], &pv2[3 * ic], hs);
+      P.n0 = hs[0]; P.n1 = hs[1]; P.n2 = hs[2]; P.d = hs[3]; planes[2 * f + 1] = P;
+    }
+    __syncwarp();
+    double p[3];
+    for (int k = 0; k < 3; ++k) p[k] = .5 * (double)(c1[k] + c2[k]);
+    bool decided = false;
+    if (A.s3_bound) {
+      int infeasible = 0;
+      for (int k = lane; k < np; k += 32) if (!sd3::plane_feasible(planes[k], p)) infeasible = 1;
+      infeasible = __any_sync(0xffffffffu, infeasible);
+      if (!infeasible) {
+        double m = 0;
+        for (int k = lane; k < 3 * A.R; k += 32) { m = fmax(m, fabs((double)pv1[k] - p[k % 3])); m = fmax(m, fabs((double)pv2[k] - p[k % 3])); }
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const double L = 4.0 * m + 1.0;
+        for (int k = lane; k < A.R; k += 32) {
+          const double v0 = (double)A.verts[3 * k], v1 = (double)A.verts[3 * k + 1], v2 = (double)A.verts[3 * k + 2];
+          double t = L;
+          for (int j = 0; j < np; ++j) {
+            const Plane P = planes[j];
+            const double a = P.n0 * v0 + P.n1 * v1 + P.n2 * v2;
+            if (a > 0) t = fmin(t, -(P.d + P.n0 * p[0] + P.n1 * p[1] + P.n2 * p[2]) / a);
+          }
+          tmin[k] = t;
+        }
+        __syncwarp();
+        double part = 0;
+        for (int f = lane; f < A.F; f += 32) {
+          const int ia = A.faces[3 * f], ib = A.faces[3 * f + 1], ic = A.faces[3 * f + 2];
+          const double ta = tmin[ia], tb = tmin[ib], tc = tmin[ic];
+          const double Az = ta * A.verts[3 * ia], Ay = ta * A.verts[3 * ia + 1], Ax = ta * A.verts[3 * ia + 2];
+          const double Bz = tb * A.verts[3 * ib], By = tb * A.verts[3 * ib + 1], Bx = tb * A.verts[3 * ib + 2];
+          const double Cz = tc * A.verts[3 * ic], Cy = tc * A.verts[3 * ic + 1], Cx = tc * A.verts[3 * ic + 2];
+          const double M00 = Bz - Az, M01 = By - Ay, M02 = Bx - Ax, M10 = Cz - Az, M11 = Cy - Ay, M12 = Cx - Ax, M20 = -Az, M21 = -Ay, M22 = -Ax;
+          const double det = M00 * (M11 * M22 - M21 * M12) - M01 * (M10 * M22 - M12 * M20) + M02 * (M10 * M21 - M11 * M20);
+          if (det > 0) part += det;
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const double den = (double)fminf(A.volume[h], A.volume[c]) + 1e-10;
+        if (part / 6.0 > (double)A.threshold * den * (1.0 + 1e-5)) {
+          decided = true;
+          if (lane == 0) { A.state[c] = ST_SUPPRESSED; atomicAdd(&counters[3], 1u); }
+        }
+      }
+    }
+    if (!decided && lane == 0) {
+      const unsigned int q = atomicAdd(&counters[11], 1u);
+      if (q < pair_cap) X.list4[q] = pairs[pi];
+      const int two[2] = {h, c};
+      for (int e = 0; e < 2; ++e) {
+        const int i = two[e];
+        if (atomicCAS(&X.slot[i], -1, -2) == -1) {
+          const unsigned int u = atomicAdd(&counters[12], 1u);
+          if (u < (unsigned int)X.hull_cap) { X.uniq[u] = i; X.slot[i] = (int)u; } else X.slot[i] = -3;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(512)
 k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counters, unsigned int pair_cap, HeavyCtx X) {
   // X.stage 0: all stages for the pairs of k_pretest (single launch);  1: S3 only, the pairs it leaves open go to X.list4 and
@@ -837,8 +939,9 @@ __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __
 // The two are bit-identical functions (host build, 7 500 fuzzed pairs: tests/test_cpu_oracle.py); the switch exists because
 // variant 1 has not been run on a GPU yet (tests/test_gpu_3d.py runs it under STARDIST_B200_EXPERIMENTAL=1).
 static int g_nms3d_norm_planes = 1;      // face_cone_volume_n (bit-identical on the host build; goldens green on B200, round 2)
+static int g_nms3d_warp_bound = 1;    // S3 lower bound by one warp per pair (0: k_heavy stage 1, a CTA per pair)
 static int g_nms3d_split = 1;         // S3 | hull kernel | S4+S5 as separate launches (sdb_nms3d_set_split; decisions identical)
-extern "C" int sdb_nms3d_set_split(int on) { g_nms3d_split = on ? 1 : 0; return 0; }
+extern "C" int sdb_nms3d_set_split(int on) { g_nms3d_split = on ? 1 : 0; g_nms3d_warp_bound = (on & 2) ? 0 : 1; return 0; }   // on = 3: split with the CTA-per-pair bound
 static int g_nms3d_s3_bound = 1;      // S3 lower-bound short cut (sdb_nms3d_set_s3_bound; decisions identical)
 extern "C" int sdb_nms3d_set_s3_bound(int on) { g_nms3d_s3_bound = on ? 1 : 0; return 0; }
 extern "C" int sdb_nms3d_set_variant(int norm_planes) { g_nms3d_norm_planes = norm_planes ? 1 : 0; return 0; }
@@ -911,6 +1014,12 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   SDB_CUDA(b_hulln.alloc((size_t)hull_cap * 4, st));
   const size_t hull_per_warp = (((size_t)3 * n_rays * sizeof(double) + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 16) + 15) / 16 * 16;
   const size_t hull_smem = 4 * hull_per_warp;
+  // warp-per-pair S3 bound: per-warp scratch (2F planes, R distances, two vertex sets); as many warps per block as fit
+  const size_t bound_per_warp = (((size_t)2 * n_faces * sizeof(Plane) + (size_t)n_rays * sizeof(double) + (size_t)6 * n_rays * sizeof(float)) + 15) / 16 * 16;
+  const int bound_wpb = g_nms3d_warp_bound ? (int)std::min<size_t>(8, (size_t)(200 * 1024) / bound_per_warp) : 0;
+  const int bound_bps = bound_wpb > 0 ? std::max(1, std::min(4, (int)((size_t)(200 * 1024) / (bound_per_warp * bound_wpb)))) : 0;
+  const size_t bound_smem = bound_per_warp * (size_t)std::max(bound_wpb, 0);
+  if (bound_wpb > 0) SDB_CUDA(cudaFuncSetAttribute(k_s3_bound_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bound_smem, 48 * 1024)));
   SDB_CUDA(cudaFuncSetAttribute(k_hulls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(hull_smem, 48 * 1024)));
   const size_t smem = ((size_t)(6 * n_rays + 3 * n_faces) * 4 + 15) / 16 * 16 + (size_t)2 * n_faces * sizeof(Plane) +
                       (size_t)3 * n_rays * 8 + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 64;
@@ -942,7 +1051,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
         HeavyCtx X{1, b_list4.as<int2>(), b_slot.as<int>(), b_uniq.as<int>(), b_hull.as<Plane>(), b_hulln.as<int>(), hull_cap};
         sdb::ProfSpan s2;
         sdb::profile_begin("nms3d_heavy_bound", st, &s2);
-        SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
+        if (bound_wpb > 0) SDB_LAUNCH(k_s3_bound_warp, 148 * bound_bps, 256, bound_smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X, bound_wpb);
+        else SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
         sdb::profile_end("nms3d_heavy_bound", st, &s2);
         sdb::profile_begin("nms3d_hulls", st, &s2);
         SDB_LAUNCH(k_hulls, 148 * 4, 128, hull_smem, st, A, X, b_counters.as<unsigned int>());
