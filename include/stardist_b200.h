@@ -280,6 +280,26 @@ int sdb_zoom_linear(const float* d_in, int ndim, const int* in_shape, const int*
 int sdb_pad_reflect_end(const float* d_in, int ndim, const int* in_shape, const int* out_shape, int channels, float* d_out,
                         sdb_stream_t stream);
 
+/* ---- the network boundary as C entry points (keras_model.predict, stardist/models/base.py:408-410) ----
+ * A network object is built from the configuration fields that define the graph (model2d.py:310-349 / model3d.py:360-399) and
+ * the Keras kernels / biases (HOST pointers, layout (k..., Cin, Cout) / (Cout,)) in the order sdb_unet_layer_name(cfg, i)
+ * reports for i in [0, sdb_unet_layer_count(cfg)): the convolution layers in topology order, then "prob", "dist".
+ * _LIB_unet_forward_2d/3d take a DEVICE input [h, w, Cin] / [d, h, w, Cin] float32 (normalised, padded to multiples of
+ * 2^depth) and write prob [h, w] / [d, h, w] and dist [..., n_rays] (raw head outputs: sigmoid applied to prob, dist
+ * not yet clamped to 1e-3).  Default architecture family only (U-Net, 3^d kernels, pool 2, ReLU, no batch norm, grid 1);
+ * sdb_unet_create returns NULL (see sdb_last_error) for anything else. */
+typedef struct sdb_unet sdb_unet;
+typedef struct {
+  int ndim, n_channel_in, n_rays, unet_n_depth, unet_n_filter_base, unet_n_conv_per_depth, net_conv_after_unet;
+  int grid[3];
+} sdb_unet_config;
+int sdb_unet_layer_count(const sdb_unet_config* cfg);
+const char* sdb_unet_layer_name(const sdb_unet_config* cfg, int i);
+sdb_unet* sdb_unet_create(const sdb_unet_config* cfg, const float* const* kernels, const float* const* biases);
+void sdb_unet_destroy(sdb_unet* net);
+int _LIB_unet_forward_2d(sdb_unet* net, const float* d_x, int h, int w, float* d_prob, float* d_dist, sdb_stream_t stream);
+int _LIB_unet_forward_3d(sdb_unet* net, const float* d_x, int d, int h, int w, float* d_prob, float* d_dist, sdb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,18 @@ def _declare(lib):
     lib.sdb_relabel_sequential.argtypes = [P, c_longlong, c_int, c_int, P, POINTER(c_int), P]
     lib.sdb_relabel_sequential.restype = c_int
     lib.sdb_nms3d.argtypes = [P, P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, c_int, P, P]
+    lib.sdb_unet_layer_count.argtypes = [P]
+    lib.sdb_unet_layer_count.restype = c_int
+    lib.sdb_unet_layer_name.argtypes = [P, c_int]
+    lib.sdb_unet_layer_name.restype = c_char_p
+    lib.sdb_unet_create.argtypes = [P, P, P]
+    lib.sdb_unet_create.restype = c_void_p
+    lib.sdb_unet_destroy.argtypes = [P]
+    lib.sdb_unet_destroy.restype = None
+    lib._LIB_unet_forward_2d.argtypes = [P, P, c_int, c_int, P, P, P]
+    lib._LIB_unet_forward_2d.restype = c_int
+    lib._LIB_unet_forward_3d.argtypes = [P, P, c_int, c_int, c_int, P, P, P]
+    lib._LIB_unet_forward_3d.restype = c_int
     lib.sdb_count_above.argtypes = [P, c_longlong, c_float, POINTER(c_int), P]
     lib.sdb_count_above.restype = c_int
     lib.sdb_store_rows_above.argtypes = [P, P, c_longlong, c_int, c_float, c_longlong, c_int, c_int, P, P, P]
@@ -191,3 +203,28 @@ def nms2d_filter_stats(reset=False):
     out = (ctypes.c_ulonglong * 4)()
     load().sdb_nms2d_filter_stats(out, 1 if reset else 0)
     return dict(pairs=int(out[0]), exact=int(out[1]), mismatches=int(out[2]), calls=int(out[3]))
+
+
+class UNetConfigC(ctypes.Structure):
+    """sdb_unet_config of include/stardist_b200.h"""
+    _fields_ = [(n, c_int) for n in ("ndim", "n_channel_in", "n_rays", "unet_n_depth", "unet_n_filter_base", "unet_n_conv_per_depth",
+                                     "net_conv_after_unet")] + [("grid", c_int * 3)]
+
+
+def c_unet_create(config, weights):
+    """network object of the C boundary (_LIB_unet_forward_2d/3d) from a Config2D/3D and a weights dict; returns
+    (handle, config struct).  The kernels are handed over in the order the library names the layers."""
+    import numpy as np
+    lib = require_cuda()
+    g = tuple(config.grid) + (1,) * (3 - len(config.grid))
+    cfg = UNetConfigC(config.n_dim, config.n_channel_in, config.n_rays, config.unet_n_depth, config.unet_n_filter_base,
+                      config.unet_n_conv_per_depth, config.net_conv_after_unet, (c_int * 3)(*g))
+    n = lib.sdb_unet_layer_count(ctypes.byref(cfg))
+    names = [lib.sdb_unet_layer_name(ctypes.byref(cfg), i).decode() for i in range(n)]
+    ks = [np.ascontiguousarray(weights[nm][0], np.float32) for nm in names]
+    bs = [np.ascontiguousarray(weights[nm][1], np.float32) for nm in names]
+    kp = (c_void_p * n)(*[k.ctypes.data for k in ks]); bp = (c_void_p * n)(*[b.ctypes.data for b in bs])
+    h = lib.sdb_unet_create(ctypes.byref(cfg), kp, bp)
+    if not h:
+        raise StarDistB200Error(lib.sdb_last_error().decode("utf-8", "replace"))
+    return c_void_p(h), cfg

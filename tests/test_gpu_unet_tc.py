@@ -134,3 +134,42 @@ def test_conv_variants_agree(variant):
     got = (out[0].float() + out[1].float()).double()
     want = _ref_conv(x_eff, k_eff, b, 1)
     assert (got - want).abs().max().item() <= 1e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("nd", [2, 3])
+def test_c_unet_forward_equals_python_executor(nd):
+    """_LIB_unet_forward_2d / _3d (the network boundary as C entry points, csrc/unet_exec.cu) launch the same kernels
+    in the same order as the Python executor: prob / dist maps bit-equal; the library names the layers it expects"""
+    import ctypes, torch
+    import stardist_b200 as sd
+    from stardist_b200 import _lib as L
+    lib = L.require_cuda()
+    rng = np.random.default_rng(11)
+    if nd == 2:
+        cfg = sd.Config2D(n_rays=32)
+        model = sd.StarDist2D(cfg, name=None, basedir=None)
+        x = rng.uniform(0, 1, (1, 96, 160, 1)).astype(np.float32)
+    else:
+        cfg = sd.Config3D(rays=sd.Rays_GoldenSpiral(96))
+        model = sd.StarDist3D(cfg, name=None, basedir=None)
+        x = rng.uniform(0, 1, (1, 16, 32, 64, 1)).astype(np.float32)
+    net, ccfg = L.c_unet_create(cfg, model.weights)
+    try:
+        n = lib.sdb_unet_layer_count(ctypes.byref(ccfg))
+        names = [lib.sdb_unet_layer_name(ctypes.byref(ccfg), i).decode() for i in range(n)]
+        assert names[0] == 'down_level_0_no_0' and names[-3:] == ['features', 'prob', 'dist'] and set(names) <= set(model.weights)
+        xd = torch.from_numpy(x).cuda()
+        want_p, want_d = model.net.forward(xd)
+        sp = tuple(x.shape[1:-1])
+        prob = torch.empty(sp, dtype=torch.float32, device='cuda')
+        dist = torch.empty(sp + (cfg.n_rays,), dtype=torch.float32, device='cuda')
+        if nd == 2:
+            L.check(lib._LIB_unet_forward_2d(net, L.ptr(xd), sp[0], sp[1], L.ptr(prob), L.ptr(dist), L.stream_ptr()))
+        else:
+            L.check(lib._LIB_unet_forward_3d(net, L.ptr(xd), sp[0], sp[1], sp[2], L.ptr(prob), L.ptr(dist), L.stream_ptr()))
+        torch.cuda.synchronize()
+        assert torch.equal(prob, want_p[0]) and torch.equal(dist, want_d[0])
+        # extents that are not multiples of 2^depth are refused (the caller pads, as StarDistPadAndCropResizer does)
+        assert lib._LIB_unet_forward_2d(net, L.ptr(xd), 97, 160, L.ptr(prob), L.ptr(dist), L.stream_ptr()) != 0
+    finally:
+        lib.sdb_unet_destroy(net)
