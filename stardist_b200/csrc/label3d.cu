@@ -73,10 +73,13 @@ __device__ __forceinline__ int bin_of(float u0, float u1, float u2) {
   return ((m * 2 + (um < 0.f ? 1 : 0)) * BIN_B + ia) * BIN_B + ib;
 }
 
-// one thread per bin
-__global__ void k_build_bins(const float* __restrict__ verts, const int* __restrict__ faces, int n_faces, FaceBins B) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// one block per bin, the faces across its threads (the order of a bin's list is irrelevant: the lists feed an OR / an AND)
+__global__ void __launch_bounds__(128) k_build_bins(const float* __restrict__ verts, const int* __restrict__ faces, int n_faces, FaceBins B) {
+  const int b = blockIdx.x;
   if (b >= BIN_N) return;
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
   const int ib = b % BIN_B, ia = (b / BIN_B) % BIN_B, ms = b / (BIN_B * BIN_B), m = ms >> 1;
   const double sgn = (ms & 1) ? -1.0 : 1.0;
   auto dir = [&](double a, double bb, double* o) {
@@ -91,8 +94,7 @@ __global__ void k_build_bins(const float* __restrict__ verts, const int* __restr
   double hb = 0;
   const double ca[4] = {a0, a0, a1, a1}, cb[4] = {b0, b1, b0, b1};
   for (int q = 0; q < 4; ++q) { dir(ca[q], cb[q], k); hb = fmax(hb, acos(fmin(1.0, c[0] * k[0] + c[1] * k[1] + c[2] * k[2]))); }
-  int cnt = 0;
-  for (int f = 0; f < n_faces; ++f) {
+  for (int f = threadIdx.x; f < n_faces; f += blockDim.x) {
     double n[3][3], ax[3] = {0, 0, 0};
     bool ok = true;
     for (int e = 0; e < 3; ++e) {
@@ -109,9 +111,10 @@ __global__ void k_build_bins(const float* __restrict__ verts, const int* __restr
       const double ang = acos(fmax(-1.0, fmin(1.0, (ax[0] * c[0] + ax[1] * c[1] + ax[2] * c[2]) / la)));
       take = ang <= hf + hb + 0.05;
     }
-    if (take) { if (cnt < BIN_CAP) B.faces[b * BIN_CAP + cnt] = f; ++cnt; }
+    if (take) { const int pos = atomicAdd(&s_cnt, 1); if (pos < BIN_CAP) B.faces[b * BIN_CAP + pos] = f; }
   }
-  B.count[b] = cnt <= BIN_CAP ? cnt : -1;
+  __syncthreads();
+  if (threadIdx.x == 0) B.count[b] = s_cnt <= BIN_CAP ? s_cnt : -1;
 }
 
 // one block per polyhedron
@@ -357,7 +360,7 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
     if (render_mode == 0) {
       SDB_CUDA(b_bcnt.alloc(BIN_N * sizeof(int), st)); SDB_CUDA(b_bfaces.alloc((size_t)BIN_N * BIN_CAP * sizeof(int), st));
       FB.count = b_bcnt.as<int>(); FB.faces = b_bfaces.as<int>();
-      SDB_LAUNCH(k_build_bins, cdiv(BIN_N, 96), 96, 0, st, d_verts, d_faces, n_faces, FB);
+      SDB_LAUNCH(k_build_bins, BIN_N, 128, 0, st, d_verts, d_faces, n_faces, FB);
     }
     SDB_LAUNCH(k_paint3d, n_polys, 256, smem, st, A, b_rank.as<int>(), use_overlap_label ? b_second.as<int>() : nullptr,
                render_mode == 4 ? b_debug.as<int>() : nullptr, b_hull.as<double>(), b_hcnt.as<int>(), FB);
