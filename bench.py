@@ -316,7 +316,7 @@ def main():
     (dev_ms_max, _, _), (_, n_total, _) = reduce_max_sum([dev_ms, float(n_inst), 0.0])
     value = n_total / (dev_ms_max / 1000.0)
     e2e = time_e2e(model, img, PROB_THRESH, NMS_THRESH, args.steps)
-    clocks = sampler.stop()
+    clocks = None if not args.skip_3d else sampler.stop()      # otherwise sampled through the 3-D timed regions as well (the 2-D ones last ~0.1 s)
 
     out = None
     if rank == 0:
@@ -380,6 +380,9 @@ def main():
             peak_mem = torch.cuda.max_memory_allocated() / 2 ** 30
             del x3
             e2e3 = time_e2e(model3, vol, PROB_THRESH_3D, NMS_THRESH_3D, steps3, warmup=1)
+            if clocks is None:
+                clocks = sampler.stop()
+                if rank == 0: out["clocks"] = clocks
             if rank == 0:
                 fl3 = conv_flops(cfg3, SHAPE_3D)
                 unet3 = stage3.get("unet", 0.0) / steps3
@@ -411,6 +414,9 @@ def main():
             torch.cuda.empty_cache()
         except Exception as e:
             if rank == 0: out["error_3d"] = repr(e)[:400]
+        if clocks is None:
+            clocks = sampler.stop()
+            if rank == 0: out["clocks"] = clocks
 
     # ------------------------------------------------------------------ configs[3] / [4]: predict_instances_big sharded over the ranks
     if not args.skip_big:
