@@ -22,6 +22,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "geom3d.cuh"
+#include "bins3d.cuh"
 #include "nms3d_pair.cuh"
 #include "../../include/stardist_b200.h"
 
@@ -463,6 +464,7 @@ __device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const doub
 
 struct HeavyCtx {
   int stage; int2* list4; int* slot; int* uniq; Plane* hull_planes; int* hull_n; int hull_cap;
+  sdbins::FaceBins bins;      // direction bins of the ray triangulation for the S5 rendering (count == nullptr: all faces)
 };
 
 // hull facet planes of the polyhedra registered by the S3 launch: ONE WARP per polyhedron (gift wrapping is a serial chain of
@@ -895,7 +897,7 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         if (q >= nv) break;
         const int x = (int)(q % Nx), y = (int)((q / Nx) % Ny), z = (int)(q / ((long long)Nx * Ny));
         const float fz = (float)(z + bb[0]), fy = (float)(y + bb[2]), fx = (float)(x + bb[4]);
-        if (sd3::inside_polyhedron(fz, fy, fx, c1, pv1, sfaces, A.F) && sd3::inside_polyhedron(fz, fy, fx, c2, pv2, sfaces, A.F)) {
+        if (sdbins::inside_polyhedron_binned(fz, fy, fx, c1, pv1, sfaces, A.F, X.bins) && sdbins::inside_polyhedron_binned(fz, fy, fx, c2, pv2, sfaces, A.F, X.bins)) {
           local++; if (q == 0) sh_i[3] = 1;
         }
       }
@@ -943,11 +945,12 @@ __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __
 // The two are bit-identical functions (host build, 7 500 fuzzed pairs: tests/test_cpu_oracle.py); the switch exists because
 // variant 1 has not been run on a GPU yet (tests/test_gpu_3d.py runs it under STARDIST_B200_EXPERIMENTAL=1).
 static int g_nms3d_norm_planes = 1;      // face_cone_volume_n (bit-identical on the host build; goldens green on B200, round 2)
+static int g_nms3d_s5_bins = 1;       // direction-binned tetrahedra in the S5 rendering (off together with the S3 bound switch)
 static int g_nms3d_warp_bound = 1;    // S3 lower bound by one warp per pair (0: k_heavy stage 1, a CTA per pair)
 static int g_nms3d_split = 1;         // S3 | hull kernel | S4+S5 as separate launches (sdb_nms3d_set_split; decisions identical)
 extern "C" int sdb_nms3d_set_split(int on) { g_nms3d_split = on ? 1 : 0; g_nms3d_warp_bound = (on & 2) ? 0 : 1; return 0; }   // on = 3: split with the CTA-per-pair bound
 static int g_nms3d_s3_bound = 1;      // S3 lower-bound short cut (sdb_nms3d_set_s3_bound; decisions identical)
-extern "C" int sdb_nms3d_set_s3_bound(int on) { g_nms3d_s3_bound = on ? 1 : 0; return 0; }
+extern "C" int sdb_nms3d_set_s3_bound(int on) { g_nms3d_s3_bound = on ? 1 : 0; g_nms3d_s5_bins = on ? 1 : 0; return 0; }
 extern "C" int sdb_nms3d_set_variant(int norm_planes) { g_nms3d_norm_planes = norm_planes ? 1 : 0; return 0; }
 
 extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float* d_verts, const int* d_faces,
@@ -1016,6 +1019,14 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   SDB_CUDA(b_uniq.alloc((size_t)hull_cap * 4, st));
   SDB_CUDA(b_hull.alloc((size_t)hull_cap * n_faces * sizeof(Plane), st));
   SDB_CUDA(b_hulln.alloc((size_t)hull_cap * 4, st));
+  // direction bins for the S5 rendering (same lists as k_paint3d; off with the rendering's switch sdb_label3d_set_cull(0/1))
+  sdb::DevBuf b_bcnt, b_bfaces;
+  sdbins::FaceBins FB{nullptr, nullptr};
+  if (g_nms3d_s5_bins) {
+    SDB_CUDA(b_bcnt.alloc(sdbins::BIN_N * sizeof(int), st)); SDB_CUDA(b_bfaces.alloc((size_t)sdbins::BIN_N * sdbins::BIN_CAP * sizeof(int), st));
+    FB.count = b_bcnt.as<int>(); FB.faces = b_bfaces.as<int>();
+    SDB_LAUNCH(sdbins::k_build_bins, sdbins::BIN_N, 128, 0, st, d_verts, d_faces, n_faces, FB);
+  }
   const size_t hull_per_warp = (((size_t)3 * n_rays * sizeof(double) + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 16) + 15) / 16 * 16;
   const size_t hull_smem = 4 * hull_per_warp;
   // warp-per-pair S3 bound: per-warp scratch (2F planes, R distances, two vertex sets); as many warps per block as fit
@@ -1052,7 +1063,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
       sdb::profile_end("nms3d_pretest", st, &sp);
       sdb::profile_begin("nms3d_heavy", st, &sp);
       if (g_nms3d_split) {
-        HeavyCtx X{1, b_list4.as<int2>(), b_slot.as<int>(), b_uniq.as<int>(), b_hull.as<Plane>(), b_hulln.as<int>(), hull_cap};
+        HeavyCtx X{1, b_list4.as<int2>(), b_slot.as<int>(), b_uniq.as<int>(), b_hull.as<Plane>(), b_hulln.as<int>(), hull_cap, FB};
         sdb::ProfSpan s2;
         sdb::profile_begin("nms3d_heavy_bound", st, &s2);
         if (bound_wpb > 0) SDB_LAUNCH(k_s3_bound_warp, 148 * bound_bps, 256, bound_smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X, bound_wpb);
@@ -1066,7 +1077,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
         SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
         sdb::profile_end("nms3d_heavy_s4s3s5", st, &s2);
       } else {
-        HeavyCtx X{0, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+        HeavyCtx X{0, nullptr, nullptr, nullptr, nullptr, nullptr, 0, FB};
         SDB_LAUNCH(k_heavy, 148 * 2, 512, smem, st, A, b_pairs.as<int2>(), b_counters.as<unsigned int>(), (unsigned int)pair_cap, X);
       }
       sdb::profile_end("nms3d_heavy", st, &sp);
