@@ -131,7 +131,8 @@ int sdb_label3d_set_cull(int on);
 int sdb_nms3d_set_variant(int norm_planes);
 /* 1 (default): a rigorous lower bound of the kernel-intersection volume (ray-wise distances to the 2F planes from the centre
  * midpoint, fan of tetrahedra) decides `iou > threshold` of stage S3 before the volume itself is computed; 0: always the
- * volume.  Decisions are identical (margin 1e-5 relative). */
+ * volume.  Decisions are identical (margin 1e-5 relative).  The same switch governs the two-sided fan bounds of S4 / S3 in the
+ * second launch and the direction bins of S5 (2: bounds on the coarse ray fan, without the extra ray per face). */
 int sdb_nms3d_set_s3_bound(int on);
 /* 1 (default): the heavy stages run as three launches per round -- S3 for all pairs, hull facets of the polyhedra that stay open
  * (one warp each), S4 + S5 with those facets; 0: one launch doing everything per pair.  Decisions identical. */

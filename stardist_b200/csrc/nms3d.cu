@@ -44,6 +44,7 @@ struct Arr {
   float* aniso;          // [3]
   const unsigned int* cell_start; const int* items; int* state;
   float max_dist, threshold; int use_bbox;
+  int fan_subdiv;        // fan bounds on the refined fan (one extra ray per face)
   int s3_bound;          // k_heavy: lower-bound short cut in front of the S3 volume (decisions identical)
   int norm_planes;       // k_heavy: S3/S4 volumes on pre-normalised planes (face_cone_volume_n; bit-identical, see geom3d.cuh)
   Grid3 G;
@@ -402,14 +403,27 @@ __device__ int hull_planes_warp(const double* pts, int n, Plane* out, int max_pl
 // The cones tile space when every face determinant det(v_a, v_b, v_c) is positive (checked; otherwise upper = +inf).
 // ~2F*R plane-ray products instead of ~(2F)^2 polygon clips.  scratch: 3R doubles (tmin) + R ints (first plane) in shared memory.
 __device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const double* p, double Lext, const int* sfaces,
-                           double* tmin, int* jhit, double* red, double* lower, double* upper) {
+                           double* tmin, int* jhit, double* red, double* lower, double* upper, double* tm = nullptr, int* jm = nullptr) {
+  // tm / jm (F entries each, optional): one extra ray per face along v_a + v_b + v_c; every face cone is then split into the
+  // three sub-cones (a,b,m), (b,c,m), (c,a,m) -- same construction, finer fan, bounds a few times tighter
   const int G = 3;
   __syncthreads();
-  for (int idx = threadIdx.x; idx < G * A.R; idx += blockDim.x) {       // (G*R exceeds the block for R > 170)
-    const int g = idx / A.R, k = idx % A.R;
-    const double v0 = (double)A.verts[3 * k], v1 = (double)A.verts[3 * k + 1], v2 = (double)A.verts[3 * k + 2];
+  const int n_ray_jobs = G * A.R, n_jobs = n_ray_jobs + (tm ? A.F : 0);
+  for (int idx = threadIdx.x; idx < n_jobs; idx += blockDim.x) {       // (the job count exceeds the block for large R / F)
+    double v0, v1, v2; int j0, jstep;
+    if (idx < n_ray_jobs) {
+      const int k = idx % A.R;
+      v0 = (double)A.verts[3 * k]; v1 = (double)A.verts[3 * k + 1]; v2 = (double)A.verts[3 * k + 2];
+      j0 = idx / A.R; jstep = G;
+    } else {
+      const int f = idx - n_ray_jobs, ia = sfaces[3 * f], ib = sfaces[3 * f + 1], ic = sfaces[3 * f + 2];
+      v0 = (double)A.verts[3 * ia] + (double)A.verts[3 * ib] + (double)A.verts[3 * ic];
+      v1 = (double)A.verts[3 * ia + 1] + (double)A.verts[3 * ib + 1] + (double)A.verts[3 * ic + 1];
+      v2 = (double)A.verts[3 * ia + 2] + (double)A.verts[3 * ib + 2] + (double)A.verts[3 * ic + 2];
+      j0 = 0; jstep = 1;
+    }
     double tn = Lext, td = 1.0; int jb = -1;        // running minimum of sd / a as a fraction (no division per plane)
-    for (int j = g; j < np; j += G) {
+    for (int j = j0; j < np; j += jstep) {
       const Plane P = planes[j];
       const double a = P.n0 * v0 + P.n1 * v1 + P.n2 * v2;
       if (a > 0) {
@@ -417,7 +431,8 @@ __device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const doub
         if (sd * td < tn * a) { tn = sd; td = a; jb = j; }
       }
     }
-    tmin[g * A.R + k] = tn / td; jhit[g * A.R + k] = jb;
+    if (idx < n_ray_jobs) { tmin[idx] = tn / td; jhit[idx] = jb; }
+    else { tm[idx - n_ray_jobs] = tn / td; jm[idx - n_ray_jobs] = jb; }
   }
   __syncthreads();
   for (int k = threadIdx.x; k < A.R; k += blockDim.x) {
@@ -427,33 +442,49 @@ __device__ void fan_bounds(const Arr& A, const Plane* planes, int np, const doub
   }
   __syncthreads();
   double pl = 0, pu = 0; int bad = 0;
-  for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
-    const int ia = sfaces[3 * f], ib = sfaces[3 * f + 1], ic = sfaces[3 * f + 2];
-    const double a0 = A.verts[3 * ia], a1 = A.verts[3 * ia + 1], a2 = A.verts[3 * ia + 2];
-    const double b0 = A.verts[3 * ib], b1 = A.verts[3 * ib + 1], b2 = A.verts[3 * ib + 2];
-    const double c0 = A.verts[3 * ic], c1 = A.verts[3 * ic + 1], c2 = A.verts[3 * ic + 2];
-    // det of the tetrahedron_volume0 orientation for unit parameters: M = (B - A, C - A, -A)
-    auto det3 = [&](double ta, double tb, double tc) {
-      const double Az = ta * a0, Ay = ta * a1, Ax = ta * a2, Bz = tb * b0, By = tb * b1, Bx = tb * b2, Cz = tc * c0, Cy = tc * c1, Cx = tc * c2;
-      const double M00 = Bz - Az, M01 = By - Ay, M02 = Bx - Ax, M10 = Cz - Az, M11 = Cy - Ay, M12 = Cx - Ax, M20 = -Az, M21 = -Ay, M22 = -Ax;
-      return M00 * (M11 * M22 - M21 * M12) - M01 * (M10 * M22 - M12 * M20) + M02 * (M10 * M21 - M11 * M20);
-    };
-    const double d1 = det3(1.0, 1.0, 1.0);
-    if (!(d1 > 0)) { bad = 1; continue; }
-    const double lo = det3(tmin[ia], tmin[ib], tmin[ic]);
-    pl += lo > 0 ? lo : 0.0;
-    double up = 1e300;
-    const int js[3] = {jhit[ia], jhit[ib], jhit[ic]};
+  // det of the tetrahedron_volume0 orientation: M = (B - A, C - A, -A)
+  auto det3v = [](const double* Av, double ta, const double* Bv, double tb, const double* Cv, double tc) {
+    const double Az = ta * Av[0], Ay = ta * Av[1], Ax = ta * Av[2], Bz = tb * Bv[0], By = tb * Bv[1], Bx = tb * Bv[2], Cz = tc * Cv[0], Cy = tc * Cv[1], Cx = tc * Cv[2];
+    const double M00 = Bz - Az, M01 = By - Ay, M02 = Bx - Ax, M10 = Cz - Az, M11 = Cy - Ay, M12 = Cx - Ax, M20 = -Az, M21 = -Ay, M22 = -Ax;
+    return M00 * (M11 * M22 - M21 * M12) - M01 * (M10 * M22 - M12 * M20) + M02 * (M10 * M21 - M11 * M20);
+  };
+  // lower / upper contribution of the cone over (A, B, C) with first-plane distances tA.. and stopping planes jA..
+  auto cone = [&](const double* Av, double tA, int jA, const double* Bv, double tB, int jB, const double* Cv, double tC, int jC, double* lo, double* up) -> bool {
+    if (!(det3v(Av, 1.0, Bv, 1.0, Cv, 1.0) > 0)) return false;
+    const double l = det3v(Av, tA, Bv, tB, Cv, tC);
+    *lo += l > 0 ? l : 0.0;
+    double u = 1e300;
+    const int js[3] = {jA, jB, jC};
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
       const int j = js[e];
       if (j < 0) continue;
       const Plane P = planes[j];
       const double sd = -(P.d + P.n0 * p[0] + P.n1 * p[1] + P.n2 * p[2]);
-      const double qa = P.n0 * a0 + P.n1 * a1 + P.n2 * a2, qb = P.n0 * b0 + P.n1 * b1 + P.n2 * b2, qc = P.n0 * c0 + P.n1 * c1 + P.n2 * c2;
-      if (qa > 0 && qb > 0 && qc > 0) up = fmin(up, det3(sd / qa, sd / qb, sd / qc));
+      const double qa = P.n0 * Av[0] + P.n1 * Av[1] + P.n2 * Av[2], qb = P.n0 * Bv[0] + P.n1 * Bv[1] + P.n2 * Bv[2], qc = P.n0 * Cv[0] + P.n1 * Cv[1] + P.n2 * Cv[2];
+      if (qa > 0 && qb > 0 && qc > 0) u = fmin(u, det3v(Av, sd / qa, Bv, sd / qb, Cv, sd / qc));
     }
-    if (up >= 1e299) bad = 1; else pu += up;
+    if (u >= 1e299) return false;
+    *up += u;
+    return true;
+  };
+  for (int f = threadIdx.x; f < A.F; f += blockDim.x) {
+    const int ia = sfaces[3 * f], ib = sfaces[3 * f + 1], ic = sfaces[3 * f + 2];
+    const double va[3] = {A.verts[3 * ia], A.verts[3 * ia + 1], A.verts[3 * ia + 2]};
+    const double vb[3] = {A.verts[3 * ib], A.verts[3 * ib + 1], A.verts[3 * ib + 2]};
+    const double vc[3] = {A.verts[3 * ic], A.verts[3 * ic + 1], A.verts[3 * ic + 2]};
+    if (!(det3v(va, 1.0, vb, 1.0, vc, 1.0) > 0)) { bad = 1; continue; }
+    bool ok;
+    if (tm) {
+      const double vm[3] = {va[0] + vb[0] + vc[0], va[1] + vb[1] + vc[1], va[2] + vb[2] + vc[2]};
+      const double t_m = tm[f]; const int j_m = jm[f];
+      ok = cone(va, tmin[ia], jhit[ia], vb, tmin[ib], jhit[ib], vm, t_m, j_m, &pl, &pu);
+      ok = cone(vb, tmin[ib], jhit[ib], vc, tmin[ic], jhit[ic], vm, t_m, j_m, &pl, &pu) && ok;
+      ok = cone(vc, tmin[ic], jhit[ic], va, tmin[ia], jhit[ia], vm, t_m, j_m, &pl, &pu) && ok;
+    } else {
+      ok = cone(va, tmin[ia], jhit[ia], vb, tmin[ib], jhit[ib], vc, tmin[ic], jhit[ic], &pl, &pu);
+    }
+    if (!ok) bad = 1;
   }
   bad = __syncthreads_or(bad);
   const double sl = block_sum(pl, red);
@@ -622,6 +653,9 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
   uint32_t* edge_done = reinterpret_cast<uint32_t*>(smem_raw + off);
   off += (size_t)((A.R * A.R + 31) / 32) * 4;
   int16_t* stack = reinterpret_cast<int16_t*>(smem_raw + off);     // [3*4R]
+  off = (off + (size_t)3 * 4 * A.R * 2 + 15) / 16 * 16;
+  double* fan_tm = reinterpret_cast<double*>(smem_raw + off);      // [F] face-centroid rays of the refined fan bounds
+  int* fan_jm = reinterpret_cast<int*>(smem_raw + off + (size_t)A.F * sizeof(double));   // [F]
   __shared__ double red[16];          // one slot per warp (up to 512 threads)
   __shared__ int sh_i[4];
   __shared__ int sh_cnt;              // S5: running count of voxels inside both polyhedra
@@ -807,7 +841,7 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
         if (!inf2 && stage == 2 && A.s3_bound) {
           // two-sided fan bounds decide `iou_hull <= t` / `> t` for all but the pairs within a few per cent of the threshold
           double lo4, up4;
-          fan_bounds(A, planes, np, p, L, sfaces, pts, reinterpret_cast<int*>(edge_done), red, &lo4, &up4);
+          fan_bounds(A, planes, np, p, L, sfaces, pts, reinterpret_cast<int*>(edge_done), red, &lo4, &up4, A.fan_subdiv ? fan_tm : nullptr, fan_jm);
           const double tden = (double)A.threshold * den;
           if (up4 * (1.0 + 1e-5) <= tden) { vol_convex = 0.f; decided4 = 1; }             // certainly <= t: the pair is kept (S4 exit)
           else if (lo4 > tden * (1.0 + 1e-5)) { vol_convex = 1.e10f; decided4 = 1; }      // certainly > t (value itself is not used)
@@ -852,7 +886,7 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       int decided3 = 0;
       if (!infeasible && A.s3_bound) {
         double lo3, up3;
-        fan_bounds(A, planes, np, p, L, sfaces, pts, reinterpret_cast<int*>(edge_done), red, &lo3, &up3);
+        fan_bounds(A, planes, np, p, L, sfaces, pts, reinterpret_cast<int*>(edge_done), red, &lo3, &up3, A.fan_subdiv ? fan_tm : nullptr, fan_jm);
         const double tden = (double)A.threshold * den;
         if (lo3 > tden * (1.0 + 1e-5)) { vol_kernel = 1.e30f; decided3 = 1; }             // certainly > t: suppressed at S3
         else if (up3 * (1.0 + 1e-5) <= tden) { vol_kernel = 0.f; decided3 = 1; }          // certainly <= t: S3 does not suppress
@@ -945,12 +979,13 @@ __global__ void k_finish(const int* __restrict__ state, int n, unsigned char* __
 // The two are bit-identical functions (host build, 7 500 fuzzed pairs: tests/test_cpu_oracle.py); the switch exists because
 // variant 1 has not been run on a GPU yet (tests/test_gpu_3d.py runs it under STARDIST_B200_EXPERIMENTAL=1).
 static int g_nms3d_norm_planes = 1;      // face_cone_volume_n (bit-identical on the host build; goldens green on B200, round 2)
+static int g_nms3d_fan_subdiv = 1;    // refined fan (sdb_nms3d_set_s3_bound(2) = bounds on the coarse fan only)
 static int g_nms3d_s5_bins = 1;       // direction-binned tetrahedra in the S5 rendering (off together with the S3 bound switch)
 static int g_nms3d_warp_bound = 1;    // S3 lower bound by one warp per pair (0: k_heavy stage 1, a CTA per pair)
 static int g_nms3d_split = 1;         // S3 | hull kernel | S4+S5 as separate launches (sdb_nms3d_set_split; decisions identical)
 extern "C" int sdb_nms3d_set_split(int on) { g_nms3d_split = on ? 1 : 0; g_nms3d_warp_bound = (on & 2) ? 0 : 1; return 0; }   // on = 3: split with the CTA-per-pair bound
 static int g_nms3d_s3_bound = 1;      // S3 lower-bound short cut (sdb_nms3d_set_s3_bound; decisions identical)
-extern "C" int sdb_nms3d_set_s3_bound(int on) { g_nms3d_s3_bound = on ? 1 : 0; g_nms3d_s5_bins = on ? 1 : 0; return 0; }
+extern "C" int sdb_nms3d_set_s3_bound(int on) { g_nms3d_s3_bound = on ? 1 : 0; g_nms3d_s5_bins = on ? 1 : 0; g_nms3d_fan_subdiv = on == 2 ? 0 : 1; return 0; }
 extern "C" int sdb_nms3d_set_variant(int norm_planes) { g_nms3d_norm_planes = norm_planes ? 1 : 0; return 0; }
 
 extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float* d_verts, const int* d_faces,
@@ -975,7 +1010,7 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   A.dist = d_dist; A.points = d_points; A.verts = d_verts; A.faces = d_faces; A.n = n; A.R = n_rays; A.F = n_faces;
   A.volume = b_vol.as<float>(); A.bbox = b_bbox.as<int>(); A.r_outer = b_ro.as<float>(); A.r_outer_iso = b_roi.as<float>();
   A.r_inner_iso = b_rii.as<float>(); A.aniso_terms = b_terms.as<float>(); A.aniso = b_aniso.as<float>();
-  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox; A.norm_planes = g_nms3d_norm_planes; A.s3_bound = g_nms3d_s3_bound;
+  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox; A.norm_planes = g_nms3d_norm_planes; A.s3_bound = g_nms3d_s3_bound; A.fan_subdiv = g_nms3d_fan_subdiv;
   A.cell_start = nullptr; A.items = nullptr; A.max_dist = 0; memset(&A.G, 0, sizeof(A.G));
   SDB_LAUNCH(k_pre1, cdiv(n, 128), 128, 0, st, A, b_stats.as<unsigned int>());
   SDB_LAUNCH(k_aniso, 3, 256, 0, st, A);
@@ -1037,7 +1072,8 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   if (bound_wpb > 0) SDB_CUDA(cudaFuncSetAttribute(k_s3_bound_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(bound_smem, 48 * 1024)));
   SDB_CUDA(cudaFuncSetAttribute(k_hulls, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(hull_smem, 48 * 1024)));
   const size_t smem = ((size_t)(6 * n_rays + 3 * n_faces) * 4 + 15) / 16 * 16 + (size_t)2 * n_faces * sizeof(Plane) +
-                      (size_t)3 * n_rays * 8 + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 64;
+                      (size_t)3 * n_rays * 8 + (size_t)((n_rays * n_rays + 31) / 32) * 4 + (size_t)3 * 4 * n_rays * 2 + 64 +
+                      (size_t)n_faces * 12 + 32;      // + face-centroid rays of the refined fan bounds
   SDB_CUDA(cudaFuncSetAttribute(k_heavy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   if (verbose) {
     printf("Non Maximum Suppression (3D, B200) ++++ \nNMS: n_polys  = %d \nNMS: n_rays   = %d  \nNMS: n_faces  = %d \nNMS: thresh   = %.3f \nNMS: use_bbox = %d \nNMS: use_kdtree = %d \n",

@@ -394,7 +394,7 @@ def test_nms3d_golden_other_kernel_paths(sd, g3, name):
     lib = _lib.load()
     want = np.unpackbits(g3[name + "/keep"])[:len(d)].astype(bool)
     try:
-        for variant, split, bound in ((0, 1, 1), (1, 0, 1), (0, 0, 0), (1, 3, 1)):      # split 3: CTA-per-pair S3 bound
+        for variant, split, bound in ((0, 1, 1), (1, 0, 1), (0, 0, 0), (1, 3, 1), (1, 1, 2)):      # split 3: CTA-per-pair S3 bound; bound 2: coarse fan
             lib.sdb_nms3d_set_variant(variant); lib.sdb_nms3d_set_split(split); lib.sdb_nms3d_set_s3_bound(bound)
             keep = c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, thr)
             assert np.array_equal(keep, want), "(variant %d, split %d, bound %d): %d decisions differ" % (variant, split, bound, int((keep != want).sum()))

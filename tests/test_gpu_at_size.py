@@ -135,6 +135,9 @@ def test_device_nms3d_fuzz_vs_reference(sd, case):
     try:
         lib.sdb_nms3d_set_s3_bound(0)
         got0 = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
+        lib.sdb_nms3d_set_s3_bound(2)          # bounds on the coarse fan only
+        got2 = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
+        assert np.array_equal(got2, want)
         lib.sdb_nms3d_set_s3_bound(1)
         lib.sdb_nms3d_set_split(0)          # all heavy stages in one launch per round (hulls inside the CTA)
         got1 = c_non_max_suppression_inds(d, p, v, f, s, int(use_bbox), int(use_kd), 0, np.float32(nthr))
