@@ -369,6 +369,31 @@ class StarDistBase:
             p.copy_(t, non_blocking=True)
             pinned.append(p)
         torch.cuda.current_stream().synchronize()
+        if copy_threads and len(tensors) == 1 and tensors[0] is not None and tensors[0].numel() >= (1 << 24) and tensors[0].is_contiguous():
+            # one large map (predict_instances_big): D2H in chunks, the host copy of chunk i overlaps the transfer of chunk i+1
+            import os
+            t = tensors[0]
+            p = self._pinned('out0', t.shape, t.dtype)
+            out = torch.empty(t.shape, dtype=t.dtype)
+            src, pin, dst = t.reshape(-1), p.reshape(-1), out.reshape(-1)
+            n, k = t.numel(), 8
+            step = -(-n // k)
+            evs = []
+            for i in range(k):
+                a, b = i * step, min(n, (i + 1) * step)
+                pin[a:b].copy_(src[a:b], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(); evs.append((ev, a, b))
+            nt = torch.get_num_threads()
+            want = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+            try:
+                if want > nt: torch.set_num_threads(want)
+                for ev, a, b in evs:
+                    ev.synchronize()
+                    dst[a:b].copy_(pin[a:b])
+            finally:
+                if want > nt: torch.set_num_threads(nt)
+            return [out.numpy()], t.numel() * t.element_size()
+
         def host_copy(p):
             if copy_threads and p.numel() >= (1 << 22):
                 # torchrun starts every rank with OMP_NUM_THREADS=1: give this one large copy its threads back
