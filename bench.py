@@ -229,14 +229,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        # one process per GPU: keep each on the CPUs next to its GPU (NVML's ideal affinity) -- eight ranks that float over
-        # both sockets cost ~10 % of the 2-D step, which has half a dozen host round trips
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-        except Exception:
-            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from stardist_b200 import Config2D, StarDist2D, StarDist3D, _lib
     import bench_data
