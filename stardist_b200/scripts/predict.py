@@ -57,8 +57,11 @@ def main(argv=None):
         if axes is None or len(axes) != img.ndim:
             raise ValueError("dimension of input (%d) not compatible with the axes (%s)" % (img.ndim, axes))
         if args.verbose: print("loaded image of size %s, normalizing..." % (img.shape,))
-        x = normalize(img, *args.pnorm)
-        labels, res = model.predict_instances(x, axes=axes, n_tiles=args.n_tiles, prob_thresh=args.prob_thresh, nms_thresh=args.nms_thresh)
+        # csbdeep.utils.normalize(img, pmin, pmax, axis=<all but C>) of the reference script (predict2d.py:77) as the model's
+        # normalizer: same numbers, computed in HBM for single-channel images (stardist_b200/prep.py), on the host otherwise
+        from ..models.base import PercentileNormalizer
+        labels, res = model.predict_instances(img, axes=axes, normalizer=PercentileNormalizer(*args.pnorm), n_tiles=args.n_tiles,
+                                              prob_thresh=args.prob_thresh, nms_thresh=args.nms_thresh)
         target = out / args.outname.format(img=pathlib.Path(fname).with_suffix("").name)
         imwrite(target, labels)
         written.append(str(target))
