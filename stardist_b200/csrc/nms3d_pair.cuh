@@ -127,3 +127,75 @@ SD3_HD inline float overlap_convex_volume_n(const float* pv1, const float* c1, c
 }
 
 }  // namespace sd3
+
+// ---- ray-fan bounds of a convex polytope's volume (serial definition of the arithmetic of fan_bounds / k_s3_bound_warp in
+// nms3d.cu; used by tests/hostcheck to check  lower <= volume <= upper  on the CPU) --------------------------------------
+// planes[0..np): n.x + d <= 0 inside; p strictly inside; verts[R][3] ray directions, faces[F][3] their triangulation.
+// subdiv: one extra ray per face along v_a + v_b + v_c, every face cone split into three sub-cones.
+namespace sd3 {
+SD3_HD inline double fan_det(const double* A, double ta, const double* B, double tb, const double* C, double tc) {
+  const double Az = ta * A[0], Ay = ta * A[1], Ax = ta * A[2], Bz = tb * B[0], By = tb * B[1], Bx = tb * B[2], Cz = tc * C[0], Cy = tc * C[1], Cx = tc * C[2];
+  const double M00 = Bz - Az, M01 = By - Ay, M02 = Bx - Ax, M10 = Cz - Az, M11 = Cy - Ay, M12 = Cx - Ax, M20 = -Az, M21 = -Ay, M22 = -Ax;
+  return M00 * (M11 * M22 - M21 * M12) - M01 * (M10 * M22 - M12 * M20) + M02 * (M10 * M21 - M11 * M20);
+}
+SD3_HD inline void fan_first_plane(const Plane* planes, int np, const double* p, double Lext, const double* v, double* t, int* jhit) {
+  double tn = Lext, td = 1.0; int jb = -1;
+  for (int j = 0; j < np; ++j) {
+    const Plane& P = planes[j];
+    const double a = P.n0 * v[0] + P.n1 * v[1] + P.n2 * v[2];
+    if (a > 0) {
+      const double sd = -(P.d + P.n0 * p[0] + P.n1 * p[1] + P.n2 * p[2]);
+      if (sd * td < tn * a) { tn = sd; td = a; jb = j; }
+    }
+  }
+  *t = tn / td; *jhit = jb;
+}
+SD3_HD inline bool fan_cone(const Plane* planes, const double* p, const double* A, double tA, int jA, const double* B, double tB, int jB,
+                            const double* C, double tC, int jC, double* lo, double* up) {
+  if (!(fan_det(A, 1.0, B, 1.0, C, 1.0) > 0)) return false;
+  const double l = fan_det(A, tA, B, tB, C, tC);
+  *lo += l > 0 ? l : 0.0;
+  double u = 1e300;
+  const int js[3] = {jA, jB, jC};
+  for (int e = 0; e < 3; ++e) {
+    const int j = js[e];
+    if (j < 0) continue;
+    const Plane& P = planes[j];
+    const double sd = -(P.d + P.n0 * p[0] + P.n1 * p[1] + P.n2 * p[2]);
+    const double qa = P.n0 * A[0] + P.n1 * A[1] + P.n2 * A[2], qb = P.n0 * B[0] + P.n1 * B[1] + P.n2 * B[2], qc = P.n0 * C[0] + P.n1 * C[1] + P.n2 * C[2];
+    if (qa > 0 && qb > 0 && qc > 0) { const double d = fan_det(A, sd / qa, B, sd / qb, C, sd / qc); u = d < u ? d : u; }
+  }
+  if (u >= 1e299) return false;
+  *up += u;
+  return true;
+}
+// t / jh: scratch of n_rays entries
+SD3_HD inline void fan_bounds_serial(const Plane* planes, int np, const double* p, double Lext, const float* verts, const int* faces, int n_rays,
+                                     int n_faces, int subdiv, double* t, int* jh, double* lower, double* upper) {
+  for (int k = 0; k < n_rays; ++k) {
+    const double v[3] = {verts[3 * k], verts[3 * k + 1], verts[3 * k + 2]};
+    fan_first_plane(planes, np, p, Lext, v, &t[k], &jh[k]);
+  }
+  double lo = 0, up = 0; bool bad = false;
+  for (int f = 0; f < n_faces; ++f) {
+    const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
+    const double va[3] = {verts[3 * ia], verts[3 * ia + 1], verts[3 * ia + 2]}, vb[3] = {verts[3 * ib], verts[3 * ib + 1], verts[3 * ib + 2]},
+                 vc[3] = {verts[3 * ic], verts[3 * ic + 1], verts[3 * ic + 2]};
+    if (!(fan_det(va, 1.0, vb, 1.0, vc, 1.0) > 0)) { bad = true; continue; }
+    bool ok;
+    if (subdiv) {
+      const double vm[3] = {va[0] + vb[0] + vc[0], va[1] + vb[1] + vc[1], va[2] + vb[2] + vc[2]};
+      double tm; int jm;
+      fan_first_plane(planes, np, p, Lext, vm, &tm, &jm);
+      ok = fan_cone(planes, p, va, t[ia], jh[ia], vb, t[ib], jh[ib], vm, tm, jm, &lo, &up);
+      ok = fan_cone(planes, p, vb, t[ib], jh[ib], vc, t[ic], jh[ic], vm, tm, jm, &lo, &up) && ok;
+      ok = fan_cone(planes, p, vc, t[ic], jh[ic], va, t[ia], jh[ia], vm, tm, jm, &lo, &up) && ok;
+    } else {
+      ok = fan_cone(planes, p, va, t[ia], jh[ia], vb, t[ib], jh[ib], vc, t[ic], jh[ic], &lo, &up);
+    }
+    if (!ok) bad = true;
+  }
+  *lower = lo / 6.0;
+  *upper = bad ? 1e300 : up / 6.0;
+}
+}  // namespace sd3

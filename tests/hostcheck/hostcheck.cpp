@@ -266,3 +266,55 @@ void hc_paint3d(const float* dist, const float* center, const float* verts, cons
       }
 }
 }
+
+// ray-fan bounds vs the volumes they bound (nms3d.cu fan_bounds): out = {feasible, V_kernel, lo, up, lo_refined, up_refined,
+//                                                                      hull_ok, V_hull, lo, up, lo_refined, up_refined}
+extern "C" void hc_fan_bounds_pair(const float* pv1, const float* c1, const float* pv2, const float* c2, const float* verts, const int* faces,
+                                   int n_rays, int n_faces, double* out12) {
+  using namespace sd3;
+  for (int i = 0; i < 12; ++i) out12[i] = 0;
+  std::vector<Plane> planes(2 * (size_t)SD3_MAX_FACES);
+  std::vector<double> t(n_rays); std::vector<int> jh(n_rays);
+  double p[3];
+  // kernel halfspaces (stage S3)
+  for (int f = 0; f < n_faces; ++f) {
+    double hs[4];
+    build_halfspace(&pv1[3 * faces[3 * f]], &pv1[3 * faces[3 * f + 1]], &pv1[3 * faces[3 * f + 2]], hs);
+    planes[2 * f] = Plane{hs[0], hs[1], hs[2], hs[3]};
+    build_halfspace(&pv2[3 * faces[3 * f]], &pv2[3 * faces[3 * f + 1]], &pv2[3 * faces[3 * f + 2]], hs);
+    planes[2 * f + 1] = Plane{hs[0], hs[1], hs[2], hs[3]};
+  }
+  for (int k = 0; k < 3; ++k) p[k] = .5 * (double)(c1[k] + c2[k]);
+  int np = 2 * n_faces; bool feas = true;
+  for (int i = 0; i < np; ++i) if (!plane_feasible(planes[i], p)) feas = false;
+  if (feas) {
+    const double L = extent_bound(pv1, pv2, n_rays, p);
+    PlaneArray PA{planes.data()};
+    double vol = 0; int ovf = 0;
+    for (int k = 0; k < np; ++k) vol += face_cone_volume(PA, np, k, p, L, &ovf);
+    out12[0] = 1; out12[1] = vol;
+    fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 0, t.data(), jh.data(), &out12[2], &out12[3]);
+    fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 1, t.data(), jh.data(), &out12[4], &out12[5]);
+  }
+  // hull halfspaces (stage S4)
+  std::vector<double> pts(3 * (size_t)n_rays);
+  std::vector<uint32_t> edge_done(((size_t)n_rays * n_rays + 31) / 32);
+  std::vector<int16_t> stack(3 * 4 * (size_t)n_rays);
+  for (int i = 0; i < 3 * n_rays; ++i) pts[i] = (double)pv1[i];
+  const int n1 = convex_hull_planes(pts.data(), n_rays, planes.data(), SD3_MAX_FACES, edge_done.data(), stack.data(), 4 * n_rays);
+  if (n1 < 4) return;
+  for (int i = 0; i < 3 * n_rays; ++i) pts[i] = (double)pv2[i];
+  const int n2 = convex_hull_planes(pts.data(), n_rays, planes.data() + n1, SD3_MAX_FACES, edge_done.data(), stack.data(), 4 * n_rays);
+  if (n2 < 4) return;
+  for (int k = 0; k < 3; ++k) p[k] = .5 * ((double)c1[k] + (double)c2[k]);
+  np = n1 + n2; feas = true;
+  for (int i = 0; i < np; ++i) if (!plane_feasible(planes[i], p)) feas = false;
+  if (!feas) return;
+  const double L = extent_bound(pv1, pv2, n_rays, p);
+  PlaneArray PA{planes.data()};
+  double vol = 0; int ovf = 0;
+  for (int k = 0; k < np; ++k) vol += face_cone_volume(PA, np, k, p, L, &ovf);
+  out12[6] = 1; out12[7] = vol;
+  fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 0, t.data(), jh.data(), &out12[8], &out12[9]);
+  fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 1, t.data(), jh.data(), &out12[10], &out12[11]);
+}

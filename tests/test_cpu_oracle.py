@@ -629,3 +629,40 @@ def test_auto_named_keras_layers_are_bound_positionally():
         w3 = dict(w); w3.pop(names[0])
         with pytest.raises(ValueError):
             canonicalize_auto_names(cfg, w3)
+
+
+def test_fan_bounds_bracket_the_volumes_they_replace():
+    """the ray-fan bounds that decide the S3 / S4 comparisons of the 3-D NMS without the exact volume (nms3d.cu fan_bounds,
+    serial definition in nms3d_pair.cuh): lower <= volume <= upper for kernel and hull intersections of random polyhedron
+    pairs -- 16 ... 187 rays, anisotropic rays, noise up to 0.6 -- on the coarse and on the refined fan"""
+    so = os.path.join(ROOT, "tests", "hostcheck", "_build", "libhostcheck.so")
+    if not os.path.exists(so):
+        pytest.skip("hostcheck library not built")
+    hc = ctypes.CDLL(so)
+    P = ctypes.c_void_p
+    hc.hc_fan_bounds_pair.argtypes = [P, P, P, P, P, P, ctypes.c_int, ctypes.c_int, P]
+    rng = np.random.default_rng(0)
+    n_poly, ratios = 0, []
+    for n_rays, aniso in ((32, None), (96, (2, 1, 1)), (64, (1, 1.5, 3)), (187, None), (16, None)):
+        rays = cases.rays_golden_spiral(n_rays, aniso)
+        v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
+        for _ in range(40):
+            r = rng.uniform(4, 12); noise = rng.choice([0.0, 0.1, 0.3, 0.6])
+            d1 = (r * (1 + noise * rng.uniform(-1, 1, n_rays))).astype(np.float32)
+            d2 = (r * rng.uniform(0.7, 1.3) * (1 + noise * rng.uniform(-1, 1, n_rays))).astype(np.float32)
+            c1 = rng.integers(10, 40, 3).astype(np.float32); c2 = (c1 + rng.integers(-6, 7, 3)).astype(np.float32)
+            pv1 = (c1[None] + d1[:, None] * v).astype(np.float32); pv2 = (c2[None] + d2[:, None] * v).astype(np.float32)
+            out = np.zeros(12)
+            hc.hc_fan_bounds_pair(pv1.ctypes.data, c1.ctypes.data, pv2.ctypes.data, c2.ctypes.data, v.ctypes.data, f.ctypes.data, n_rays, len(f), out.ctypes.data)
+            for base in (0, 6):
+                if out[base] != 1: continue
+                n_poly += 1
+                V, lo, up, lo2, up2 = out[base + 1:base + 6]
+                for L_, U_ in ((lo, up), (lo2, up2)):
+                    assert L_ <= V * (1 + 1e-9) + 1e-12, (n_rays, base, L_, V)
+                    assert U_ >= V * (1 - 1e-9) - 1e-12, (n_rays, base, U_, V)
+                assert lo2 >= lo * (1 - 1e-9)                      # the refined fan contains the coarse one
+                if up2 < 1e299 and V > 0: ratios.append((lo2 / V, up2 / V))
+    assert n_poly > 250
+    r = np.array(ratios)
+    assert np.median(r[:, 0]) > 0.85 and np.median(r[:, 1]) < 1.15      # and they are tight enough to decide most pairs
