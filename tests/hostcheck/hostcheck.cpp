@@ -318,3 +318,9 @@ extern "C" void hc_fan_bounds_pair(const float* pv1, const float* c1, const floa
   fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 0, t.data(), jh.data(), &out12[8], &out12[9]);
   fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 1, t.data(), jh.data(), &out12[10], &out12[11]);
 }
+
+// direction bins of the 3-D rendering / S5 (bins3d.cuh): bin of a direction, and whether a bin lists a face
+#include "../../stardist_b200/csrc/bins3d.cuh"
+extern "C" int hc_bin_of(float u0, float u1, float u2) { return sdbins::bin_of(u0, u1, u2); }
+extern "C" int hc_bin_takes_face(int b, const float* verts, const int* faces, int f) { return sdbins::bin_takes_face(b, verts, faces, f) ? 1 : 0; }
+extern "C" int hc_bin_count() { return sdbins::BIN_N; }

@@ -666,3 +666,50 @@ def test_fan_bounds_bracket_the_volumes_they_replace():
     assert n_poly > 250
     r = np.array(ratios)
     assert np.median(r[:, 0]) > 0.85 and np.median(r[:, 1]) < 1.15      # and they are tight enough to decide most pairs
+
+
+def test_direction_bins_list_every_face_that_can_contain_the_direction():
+    """the direction bins of the 3-D rendering and of the S5 rule (bins3d.cuh; k_build_bins calls the same bin_takes_face,
+    the voxel loop the same bin_of): for any direction u from the centre, every face whose cone contains u -- with a slack of
+    1e-3 in the barycentric coordinates, ~1000 x what float rounding of inside_tetrahedron can move -- is in the list of u's bin,
+    so the binned OR over tetrahedra is the OR over all of them.  Random directions plus the degenerate ones: the axes, the
+    cube-map cell borders and diagonals, the ray directions themselves and their edge midpoints."""
+    so = os.path.join(ROOT, "tests", "hostcheck", "_build", "libhostcheck.so")
+    if not os.path.exists(so):
+        pytest.skip("hostcheck library not built")
+    hc = ctypes.CDLL(so)
+    if not hasattr(hc, "hc_bin_takes_face"):
+        pytest.skip("hostcheck library predates the bins check")
+    P = ctypes.c_void_p
+    hc.hc_bin_of.argtypes = [ctypes.c_float] * 3
+    hc.hc_bin_takes_face.argtypes = [ctypes.c_int, P, P, ctypes.c_int]
+    n_bins = hc.hc_bin_count()
+    rng = np.random.default_rng(1)
+    sizes = []
+    for n_rays, aniso in ((96, (2, 1, 1)), (32, None), (64, (1, 1.5, 3)), (187, None), (16, None), (8, (4, 1, 1))):
+        rays = cases.rays_golden_spiral(n_rays, aniso)
+        v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
+        takes = np.array([[hc.hc_bin_takes_face(b, v.ctypes.data, f.ctypes.data, j) for j in range(len(f))] for b in range(n_bins)], bool)
+        sizes.append(takes.sum(1).max())
+        u = rng.normal(size=(20000, 3))
+        g = np.linspace(-1, 1, 9)                                     # cube-map cell borders (BIN_B = 4) and centres
+        cube = np.array([np.roll([s, a, b], k) for s in (-1, 1) for a in g for b in g for k in range(3)], float)
+        vd = v.astype(np.float64)
+        mids = np.concatenate([vd[f[:, i]] + vd[f[:, (i + 1) % 3]] for i in range(3)])
+        u = np.concatenate([u, cube, vd, -vd, mids, vd[f].sum(1), np.eye(3), -np.eye(3)]).astype(np.float32)
+        u = u[np.abs(u).max(1) > 0]
+        bins = np.array([hc.hc_bin_of(*map(float, w)) for w in u])
+        assert bins.min() >= 0 and bins.max() < n_bins
+        A, B, C = (vd[f[:, i]] for i in range(3))                     # [F,3]
+        det = np.einsum("fi,fi->f", A, np.cross(B, C))
+        ud = u.astype(np.float64)
+        al = np.einsum("ni,fi->nf", ud, np.cross(B, C)) / det
+        be = np.einsum("ni,fi->nf", ud, np.cross(C, A)) / det
+        ga = np.einsum("ni,fi->nf", ud, np.cross(A, B)) / det
+        s = np.abs(al) + np.abs(be) + np.abs(ga)
+        in_cone = (np.minimum(np.minimum(al, be), ga) >= -1e-3 * s) & (np.abs(det) > 0)[None]
+        listed = takes[bins]                                          # [n,F]
+        missing = in_cone & ~listed
+        assert not missing.any(), (n_rays, aniso, np.argwhere(missing)[:5])
+        assert in_cone.any(1).mean() > 0.99                           # the triangulation covers the sphere: the check is not vacuous
+    assert max(sizes) <= 64                                           # BIN_CAP: no list overflows for the ray sets in use
