@@ -222,6 +222,26 @@ SD3_HD inline bool plane_feasible(const Plane& P, const double* p) {
 
 constexpr int SD3_MAXPOLY = 48;
 
+// Order in which face_cone_volume clips face k against the other planes.  Attempt 0 is the index order.  The intermediate
+// polygon is face k of the polytope of the planes seen so far; in index order its vertex count can pass SD3_MAXPOLY although
+// the final face has a handful (hull facets come out of the gift wrapping as a growing patch: a far face is bounded by the
+// whole rim of the patch -- observed from 128 rays on, never for <= 96).  When that happens the face is clipped again in a
+// scattered order, t -> (t * stride) mod n with a stride coprime to n near n / phi (then n / phi^2): the planes seen so far
+// are spread over the sphere and the intermediate faces stay small.  Faces that do not overflow are untouched, bit for bit.
+SD3_HD inline int clip_order_stride(int n, int attempt) {
+  if (attempt == 0 || n < 3) return 1;
+  int s = (int)((double)n * (attempt == 1 ? 0.6180339887498949 : 0.3819660112501051));
+  if (s < 2) s = 2;
+  for (int guard = 0; guard < n; ++guard, ++s) {
+    if (s >= n) s = 2;
+    int a = s, b = n;
+    while (b) { const int r = a % b; a = b; b = r; }
+    if (a == 1) return s;
+  }
+  return 1;
+}
+constexpr int SD3_CLIP_ATTEMPTS = 3;
+
 // (1/3) * h_k * area(face k) of the polytope {x : planes[j].x + d_j <= 0 for all j}, p strictly inside.
 // L = half edge of the initial square (any bound on the polytope's extent around p).
 template <typename PlaneAt>
@@ -242,10 +262,14 @@ SD3_HD inline double face_cone_volume(const PlaneAt& planes, int n, int k, const
   u0 /= ul; u1 /= ul; u2 /= ul;
   const double v0 = ny * u2 - nx * u1, v1 = nx * u0 - nz * u2, v2 = nz * u1 - ny * u0;
   double pa[SD3_MAXPOLY], pb[SD3_MAXPOLY], qa[SD3_MAXPOLY], qb[SD3_MAXPOLY];
-  int m = 4;
-  pa[0] = -L; pb[0] = -L; pa[1] = L; pb[1] = -L; pa[2] = L; pb[2] = L; pa[3] = -L; pb[3] = L;
+  int m = 4, ovf = 0;
   const double eps_dup = 1e-9;
-  for (int j = 0; j < n && m > 0; ++j) {
+  for (int attempt = 0; attempt < SD3_CLIP_ATTEMPTS; ++attempt) {
+  m = 4; ovf = 0;
+  pa[0] = -L; pb[0] = -L; pa[1] = L; pb[1] = -L; pa[2] = L; pb[2] = L; pa[3] = -L; pb[3] = L;
+  const int stride = clip_order_stride(n, attempt);
+  for (int jt = 0; jt < n && m > 0 && !ovf; ++jt) {
+    const int j = attempt == 0 ? jt : (int)(((long long)jt * stride) % n);
     if (j == k) continue;
     Plane Pj = planes(j);
     const double lj = sqrt(Pj.n0 * Pj.n0 + Pj.n1 * Pj.n1 + Pj.n2 * Pj.n2);
@@ -271,18 +295,21 @@ SD3_HD inline double face_cone_volume(const PlaneAt& planes, int n, int k, const
       if (fe <= 0) {
         if (fs > 0) {
           const double w = fs / (fs - fe);
-          if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else *overflow = 1;
+          if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else ovf = 1;
         }
-        if (mo < SD3_MAXPOLY) { qa[mo] = ea; qb[mo] = eb; mo++; } else *overflow = 1;
+        if (mo < SD3_MAXPOLY) { qa[mo] = ea; qb[mo] = eb; mo++; } else ovf = 1;
       } else if (fs <= 0) {
         const double w = fs / (fs - fe);
-        if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else *overflow = 1;
+        if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else ovf = 1;
       }
       sa = ea; sb = eb; fs = fe;
     }
     m = mo;
     for (int t = 0; t < m; ++t) { pa[t] = qa[t]; pb[t] = qb[t]; }
   }
+  if (!ovf) break;
+  }
+  if (ovf) *overflow = 1;      // every order overflowed: the value below is an under-estimate
   if (m < 3) return 0.0;
   double area2 = 0;
   for (int t = 0; t < m; ++t) {
@@ -329,10 +356,14 @@ SD3_HD inline double face_cone_volume_n(const PlaneAt& planes /* normalized_plan
   u0 /= ul; u1 /= ul; u2 /= ul;
   const double v0 = ny * u2 - nx * u1, v1 = nx * u0 - nz * u2, v2 = nz * u1 - ny * u0;
   double pa[SD3_MAXPOLY], pb[SD3_MAXPOLY], qa[SD3_MAXPOLY], qb[SD3_MAXPOLY];
-  int m = 4;
-  pa[0] = -L; pb[0] = -L; pa[1] = L; pb[1] = -L; pa[2] = L; pb[2] = L; pa[3] = -L; pb[3] = L;
+  int m = 4, ovf = 0;
   const double eps_dup = 1e-9;
-  for (int j = 0; j < n && m > 0; ++j) {
+  for (int attempt = 0; attempt < SD3_CLIP_ATTEMPTS; ++attempt) {
+  m = 4; ovf = 0;
+  pa[0] = -L; pb[0] = -L; pa[1] = L; pb[1] = -L; pa[2] = L; pb[2] = L; pa[3] = -L; pb[3] = L;
+  const int stride = clip_order_stride(n, attempt);
+  for (int jt = 0; jt < n && m > 0 && !ovf; ++jt) {
+    const int j = attempt == 0 ? jt : (int)(((long long)jt * stride) % n);
     if (j == k) continue;
     const Plane Pj = planes(j);
     if (Pj.n0 == 0 && Pj.n1 == 0 && Pj.n2 == 0) continue;
@@ -357,18 +388,21 @@ SD3_HD inline double face_cone_volume_n(const PlaneAt& planes /* normalized_plan
       if (fe <= 0) {
         if (fs > 0) {
           const double w = fs / (fs - fe);
-          if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else *overflow = 1;
+          if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else ovf = 1;
         }
-        if (mo < SD3_MAXPOLY) { qa[mo] = ea; qb[mo] = eb; mo++; } else *overflow = 1;
+        if (mo < SD3_MAXPOLY) { qa[mo] = ea; qb[mo] = eb; mo++; } else ovf = 1;
       } else if (fs <= 0) {
         const double w = fs / (fs - fe);
-        if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else *overflow = 1;
+        if (mo < SD3_MAXPOLY) { qa[mo] = sa + w * (ea - sa); qb[mo] = sb + w * (eb - sb); mo++; } else ovf = 1;
       }
       sa = ea; sb = eb; fs = fe;
     }
     m = mo;
     for (int t = 0; t < m; ++t) { pa[t] = qa[t]; pb[t] = qb[t]; }
   }
+  if (!ovf) break;
+  }
+  if (ovf) *overflow = 1;      // every order overflowed: the value below is an under-estimate
   if (m < 3) return 0.0;
   double area2 = 0;
   for (int t = 0; t < m; ++t) {

@@ -269,10 +269,13 @@ void hc_paint3d(const float* dist, const float* center, const float* verts, cons
 
 // ray-fan bounds vs the volumes they bound (nms3d.cu fan_bounds): out = {feasible, V_kernel, lo, up, lo_refined, up_refined,
 //                                                                      hull_ok, V_hull, lo, up, lo_refined, up_refined}
+static int g_fan_ovf[2];
+extern "C" void hc_fan_last_overflow(int* two) { two[0] = g_fan_ovf[0]; two[1] = g_fan_ovf[1]; }
 extern "C" void hc_fan_bounds_pair(const float* pv1, const float* c1, const float* pv2, const float* c2, const float* verts, const int* faces,
                                    int n_rays, int n_faces, double* out12) {
   using namespace sd3;
   for (int i = 0; i < 12; ++i) out12[i] = 0;
+  g_fan_ovf[0] = g_fan_ovf[1] = 0;
   std::vector<Plane> planes(2 * (size_t)SD3_MAX_FACES);
   std::vector<double> t(n_rays); std::vector<int> jh(n_rays);
   double p[3];
@@ -292,7 +295,7 @@ extern "C" void hc_fan_bounds_pair(const float* pv1, const float* c1, const floa
     PlaneArray PA{planes.data()};
     double vol = 0; int ovf = 0;
     for (int k = 0; k < np; ++k) vol += face_cone_volume(PA, np, k, p, L, &ovf);
-    out12[0] = 1; out12[1] = vol;
+    out12[0] = 1; out12[1] = vol; g_fan_ovf[0] = ovf;
     fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 0, t.data(), jh.data(), &out12[2], &out12[3]);
     fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 1, t.data(), jh.data(), &out12[4], &out12[5]);
   }
@@ -314,7 +317,7 @@ extern "C" void hc_fan_bounds_pair(const float* pv1, const float* c1, const floa
   PlaneArray PA{planes.data()};
   double vol = 0; int ovf = 0;
   for (int k = 0; k < np; ++k) vol += face_cone_volume(PA, np, k, p, L, &ovf);
-  out12[6] = 1; out12[7] = vol;
+  out12[6] = 1; out12[7] = vol; g_fan_ovf[1] = ovf;
   fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 0, t.data(), jh.data(), &out12[8], &out12[9]);
   fan_bounds_serial(planes.data(), np, p, L, verts, faces, n_rays, n_faces, 1, t.data(), jh.data(), &out12[10], &out12[11]);
 }
@@ -324,3 +327,23 @@ extern "C" void hc_fan_bounds_pair(const float* pv1, const float* c1, const floa
 extern "C" int hc_bin_of(float u0, float u1, float u2) { return sdbins::bin_of(u0, u1, u2); }
 extern "C" int hc_bin_takes_face(int b, const float* verts, const int* faces, int f) { return sdbins::bin_takes_face(b, verts, faces, f) ? 1 : 0; }
 extern "C" int hc_bin_count() { return sdbins::BIN_N; }
+
+// hull facet planes of one polyhedron (geom3d.cuh convex_hull_planes): planes[4 * n] out, returns the facet count
+extern "C" int hc_convex_hull_planes(const double* pts, int n, double* planes_out, int max_planes) {
+  std::vector<sd3::Plane> pl(max_planes);
+  std::vector<uint32_t> edge_done(((size_t)n * n + 31) / 32);
+  std::vector<int16_t> stack(3 * 4 * (size_t)n);
+  const int nf = sd3::convex_hull_planes(pts, n, pl.data(), max_planes, edge_done.data(), stack.data(), 4 * n);
+  for (int i = 0; i < nf; ++i) { planes_out[4 * i] = pl[i].n0; planes_out[4 * i + 1] = pl[i].n1; planes_out[4 * i + 2] = pl[i].n2; planes_out[4 * i + 3] = pl[i].d; }
+  return nf;
+}
+
+// volume of the intersection of n halfspaces around the interior point p (geom3d.cuh face_cone_volume), per-face parts out
+extern "C" double hc_planes_volume(const double* planes4, int n, const double* p, double L, double* parts, int* overflow) {
+  std::vector<sd3::Plane> pl(n);
+  for (int i = 0; i < n; ++i) pl[i] = sd3::Plane{planes4[4 * i], planes4[4 * i + 1], planes4[4 * i + 2], planes4[4 * i + 3]};
+  sd3::PlaneArray PA{pl.data()};
+  double vol = 0; *overflow = 0;
+  for (int k = 0; k < n; ++k) { const double v = sd3::face_cone_volume(PA, n, k, p, L, overflow); if (parts) parts[k] = v; vol += v; }
+  return vol;
+}
