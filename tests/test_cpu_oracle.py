@@ -794,3 +794,47 @@ def test_volume_stages_equal_the_reference_qhull_functions():
                     assert abs(want - got) <= 1e-6 * abs(want), (n_rays, noise, want, got)
                 total += 1; equal += int(np.float32(want).view(np.int32) == np.float32(got).view(np.int32))
     assert equal >= 0.99 * total, (equal, total)
+
+
+def test_ctypes_signatures_match_the_header():
+    """include/stardist_b200.h is the boundary; stardist_b200/_lib.py is the binding a consumer would write.  extern "C" symbols
+    carry no types, so a float / double or a missing-argument slip between the two would pass silently: compare, for every
+    prototype, the parameter classes (pointer / i32 / i64 / f32 / f64) and the return class with the ctypes declaration.
+    (The .cu files include the header, so the definitions themselves are checked by the compiler.)"""
+    lib_path = os.path.join(ROOT, "stardist_b200", "libstardist_b200.so")
+    if not os.path.exists(lib_path):
+        pytest.skip("libstardist_b200.so not built")
+    from stardist_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "stardist_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S); hdr = re.sub(r"//[^\n]*", "", hdr)
+    protos = re.findall(r"([\w\s\*]+?)\b((?:sdb_|_LIB_)\w+)\s*\(([^)]*)\)\s*;", hdr, flags=re.S)
+
+    def cls_c(p):
+        p = " ".join(p.split())
+        if p in ("void", ""): return None
+        if "*" in p or "sdb_stream_t" in p: return "ptr"
+        if re.search(r"\bdouble\b", p): return "f64"
+        if re.search(r"\bfloat\b", p): return "f32"
+        if re.search(r"long long|int64_t|size_t", p): return "i64"
+        return "i32"
+
+    def cls_py(t):
+        if t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer)): return "ptr"
+        return {ctypes.c_double: "f64", ctypes.c_float: "f32", ctypes.c_longlong: "i64", ctypes.c_ulonglong: "i64", ctypes.c_size_t: "i64",
+                ctypes.c_int: "i32", ctypes.c_uint: "i32", ctypes.c_bool: "i32"}.get(t, str(t))
+
+    checked, bad = 0, []
+    for ret, name, params in protos:
+        fn = getattr(lib, name)
+        if fn.argtypes is None:
+            continue                                   # bound lazily by the module that mirrors the reference extension
+        want = [c for c in (cls_c(p) for p in params.split(",")) if c]
+        got = [cls_py(t) for t in fn.argtypes]
+        r = " ".join(ret.replace("extern", "").split())
+        want_r = None if (r.endswith("void") and "*" not in r) else cls_c(r)
+        got_r = None if fn.restype is None else cls_py(fn.restype)
+        checked += 1
+        if want != got or want_r != got_r:
+            bad.append((name, want, got, want_r, got_r))
+    assert checked >= 60 and not bad, bad
