@@ -838,3 +838,44 @@ def test_ctypes_signatures_match_the_header():
         if want != got or want_r != got_r:
             bad.append((name, want, got, want_r, got_r))
     assert checked >= 60 and not bad, bad
+
+
+def test_frontier_peeling_model_equals_the_greedy_loop():
+    """The device NMS (2-D: nms2d_rounds.cuh d_frontier2 / d_pairs / d_fast / d_clip; 3-D: nms3d.cu k_frontier / k_pretest /
+    k_heavy) replaces the reference's serial greedy loop (stardist2d.cpp:520-600, stardist3d_impl.cpp:1120-1360) by rounds:
+    an undecided candidate c is KEPT in round r unless some h < c (higher score) that reaches c is still undecided or was kept
+    in this very round (whatever a racing read of state[h] returns among the values it can hold during the launch); the
+    candidates kept in round r then test the undecided c > h they reach and suppress those that overlap.  This is a model of
+    exactly that rule on random 'reach' / 'overlap' relations -- with the racy reads modelled by evaluating the candidates of a
+    round in random order against a state array that changes under them -- against the greedy loop: same keep mask, always,
+    and the lowest undecided index is never blocked (progress)."""
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(1, 120))
+        reach = np.triu(rng.random((n, n)) < rng.choice([0.02, 0.1, 0.4, 1.0]), 1)          # reach[h, c], h < c
+        overlap = reach & (rng.random((n, n)) < rng.choice([0.1, 0.5, 0.9]))              # suppresses only what it reaches
+        # reference: greedy in score order
+        sup = np.zeros(n, bool)
+        for i in range(n):
+            if sup[i]: continue
+            sup[i + 1:] |= overlap[i, i + 1:]
+        want = ~sup
+        UNDECIDED, SUPPRESSED = 0, 1
+        state = np.zeros(n, int)
+        rounds = 0
+        while (state == UNDECIDED).any():
+            kept_now = 2 + rounds
+            und = np.flatnonzero(state == UNDECIDED)
+            kept = []
+            for c in rng.permutation(und):                         # racing warps: any order, state changes under them
+                hs = np.flatnonzero(reach[:c, c])
+                blocked = any(state[h] == UNDECIDED or state[h] == kept_now for h in hs)
+                if not blocked:
+                    state[c] = kept_now; kept.append(c)
+            assert und.min() in kept                               # progress: the best undecided candidate is never blocked
+            for h in kept:                                         # pair tests of this round (any order: they only suppress)
+                cs = np.flatnonzero(overlap[h] & (state == UNDECIDED))
+                state[cs] = SUPPRESSED
+            rounds += 1
+            assert rounds <= n
+        assert np.array_equal(state >= 2, want), trial
