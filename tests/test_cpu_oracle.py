@@ -1,7 +1,7 @@
 """CPU tests (run with -m "not gpu"): the oracle is pinned against the golden vectors, the
 host build of the device geometry agrees with the reference's Clipper, the C-ABI library loads
 and exports everything include/stardist_b200.h declares.  No compute call needs a GPU here."""
-import ctypes, os, re, subprocess, sys
+import ctypes, json, os, re, subprocess, sys
 import numpy as np
 import pytest
 
@@ -879,3 +879,49 @@ def test_frontier_peeling_model_equals_the_greedy_loop():
             rounds += 1
             assert rounds <= n
         assert np.array_equal(state >= 2, want), trial
+
+
+def test_serial_nms3d_other_ray_classes_equal_reference():
+    """the 3-D NMS arithmetic (host build of the device headers, hc_nms3d_serial) against the reference extension for the ray
+    classes beyond Rays_GoldenSpiral: Rays_Cartesian (pole rings = groups of coincident directions -> collinear vertices),
+    Rays_Octo, Rays_Tetra -- same keep mask.  Runs in a subprocess with OMP_NUM_THREADS=1 (the reference's anisotropy sum races).
+    Known deviation, pinned here so that it stays visible: when the distances on coincident rays are EQUAL the polyhedron has
+    duplicate vertices, the gift wrapping gives up (hull volume sentinel 1e10, like a Qhull error in the reference) and stage S4
+    never short-cuts -- S5 decides every such pair, which can differ from the reference's S4 'keep' (DESIGN.md §5)."""
+    code = r'''
+import ctypes, json, os, sys, numpy as np
+ROOT = sys.argv[1]
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from oracle import ref_ext
+from stardist_b200 import rays3d as R3
+hc = ctypes.CDLL(os.path.join(ROOT, "tests/hostcheck/_build/libhostcheck.so")); P = ctypes.c_void_p
+hc.hc_nms3d_serial.argtypes = [P, P, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P]
+out = []
+for k, (name, rays) in enumerate([("cartesian", R3.Rays_Cartesian(8, 5)), ("octo", R3.Rays_Octo(2)), ("tetra", R3.Rays_Tetra(2)), ("octo3", R3.Rays_Octo(3))]):
+    v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32); R = len(v)
+    for noise, nthr in ((0.2, 0.2), (0.5, 0.5), (0.0, 0.3)):
+        rng = np.random.default_rng(100 * k + int(10 * noise)); n = 300
+        p = np.ascontiguousarray(np.stack([rng.integers(2, s - 2, n) for s in (14, 18, 20)], 1), np.float32)
+        s = np.ascontiguousarray(np.sort(rng.uniform(0.5, 1, n))[::-1], np.float32)
+        d = np.ascontiguousarray(rng.uniform(2, 5, (n, 1)) * (1 + noise * rng.uniform(-1, 1, (n, R))), np.float32)
+        want = ref_ext.stardist3d().c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, np.float32(nthr))
+        keep = np.zeros(n, np.uint8); sc = np.zeros(5, np.int32)
+        hc.hc_nms3d_serial(d.ctypes.data, p.ctypes.data, v.ctypes.data, f.ctypes.data, n, R, len(f), ctypes.c_float(nthr), 1, 1, 0, keep.ctypes.data, sc.ctypes.data)
+        out.append(dict(rays=name, noise=noise, kept=int(want.sum()), mismatches=int(np.count_nonzero(keep.astype(bool) != want)), s4=int(sc[3]), s5=int(sc[4])))
+print("RESULT " + json.dumps(out))
+'''
+    so = os.path.join(ROOT, "tests", "hostcheck", "_build", "libhostcheck.so")
+    if not (os.path.exists(so) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stardist3d.so"))):
+        pytest.skip("hostcheck / oracle/_ref not built")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run([sys.executable, "-c", code, ROOT], capture_output=True, text=True, env=env, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
+    assert lines, r.stderr[-2000:]
+    res = json.loads(lines[-1][7:])
+    assert len(res) == 12
+    for e in res:
+        degenerate = e["rays"] == "cartesian" and e["noise"] == 0.0
+        if not degenerate:
+            assert e["mismatches"] == 0, e
+        else:
+            assert e["s4"] == e["s5"], e             # the documented deviation: no pair is decided by S4, all reach S5
