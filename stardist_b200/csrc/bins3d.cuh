@@ -52,6 +52,13 @@ SD3_HD inline bool bin_takes_face(int b, const float* verts, const int* faces, i
   }
   const double la = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
   if (!(ok && la > 1e-6)) return true;
+  // a face whose three directions are (nearly) coplanar with the centre -- Rays_Cartesian's pole faces, two of whose rays
+  // coincide -- spans a degenerate tetrahedron: all four determinants of inside_tetrahedron vanish on a whole PLANE through
+  // the centre, and the reference's `det >= 0` then answers true for voxels far from the face's direction.  Such a face is
+  // listed in every bin, so the binned OR stays the OR over all faces.
+  const double det = n[0][0] * (n[1][1] * n[2][2] - n[1][2] * n[2][1]) - n[0][1] * (n[1][0] * n[2][2] - n[1][2] * n[2][0]) +
+                     n[0][2] * (n[1][0] * n[2][1] - n[1][1] * n[2][0]);
+  if (fabs(det) < 1e-6) return true;
   auto clampc = [](double x) { return x > 1.0 ? 1.0 : (x < -1.0 ? -1.0 : x); };
   double hf = 0;
   for (int e = 0; e < 3; ++e) { const double an = acos(clampc((ax[0] * n[e][0] + ax[1] * n[e][1] + ax[2] * n[e][2]) / la)); hf = an > hf ? an : hf; }

@@ -412,6 +412,34 @@ SD3_HD inline double face_cone_volume_n(const PlaneAt& planes /* normalized_plan
   return fabs(area2) * 0.5 * h / 3.0;
 }
 
+// Duplicate points break the gift wrapping below (a zero-length pivot edge), Qhull -- the reference -- ignores them.  They only
+// occur for ray sets with coincident directions (Rays_Cartesian's pole rings) and equal distances on those rays.  Every point
+// that repeats a lower-indexed one is moved to the centroid of the set: an interior point never becomes a hull vertex, so the
+// facets are those of the distinct points.  Points without a twin are not touched.  Serial, O(n^2) compares; returns the count.
+SD3_HD inline int demote_duplicate_points(double* pts, int n) {
+  double c0 = 0, c1 = 0, c2 = 0;
+  for (int i = 0; i < n; ++i) { c0 += pts[3 * i]; c1 += pts[3 * i + 1]; c2 += pts[3 * i + 2]; }
+  c0 /= n; c1 /= n; c2 /= n;
+  int moved = 0;
+  for (int i = n - 1; i > 0; --i) {              // downwards: the lower-indexed twins are still in place
+    bool twin = false;
+    for (int j = 0; j < i && !twin; ++j) twin = pts[3 * j] == pts[3 * i] && pts[3 * j + 1] == pts[3 * i + 1] && pts[3 * j + 2] == pts[3 * i + 2];
+    if (twin) { pts[3 * i] = c0; pts[3 * i + 1] = c1; pts[3 * i + 2] = c2; ++moved; }
+  }
+  return moved;
+}
+
+// true when two of the n ray directions coincide (relative 1e-5): only then can a polyhedron have duplicate vertices
+inline bool rays_have_coincident_directions(const float* verts, int n) {
+  for (int i = 1; i < n; ++i)
+    for (int j = 0; j < i; ++j) {
+      const double d0 = (double)verts[3 * i] - verts[3 * j], d1 = (double)verts[3 * i + 1] - verts[3 * j + 1], d2 = (double)verts[3 * i + 2] - verts[3 * j + 2];
+      const double l2 = (double)verts[3 * i] * verts[3 * i] + (double)verts[3 * i + 1] * verts[3 * i + 1] + (double)verts[3 * i + 2] * verts[3 * i + 2];
+      if (d0 * d0 + d1 * d1 + d2 * d2 <= 1e-10 * l2) return true;
+    }
+  return false;
+}
+
 // Convex hull facet planes (outward, unit normal) of n points (double, [n][3]) by gift wrapping.
 // out: up to max_planes planes; returns the number of facets, or -1 on failure (degenerate input).
 // scratch: edge_done bit matrix n*n bits (uint32 words), stack of directed edges (int16 triples).

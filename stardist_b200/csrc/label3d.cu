@@ -48,6 +48,7 @@ __global__ void k_hull3d(PaintArgs A, double* __restrict__ hull_planes, int* __r
   const float* d = A.dist + (size_t)i * A.n_rays;
   for (int j = 0; j < A.n_rays; ++j)
     for (int c = 0; c < 3; ++c) pts[3 * j + c] = (double)(A.points[3 * i + c] + d[j] * A.verts[3 * j + c]);
+  sd3::demote_duplicate_points(pts, A.n_rays);      // coincident ray directions with equal distances (Rays_Cartesian poles)
   hull_count[i] = sd3::convex_hull_planes(pts, A.n_rays, reinterpret_cast<sd3::Plane*>(hull_planes + (size_t)i * 4 * A.n_faces),
                                           A.n_faces, ed, st, 4 * MAXR);
 }

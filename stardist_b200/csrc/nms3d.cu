@@ -47,6 +47,7 @@ struct Arr {
   int fan_subdiv;        // fan bounds on the refined fan (one extra ray per face)
   int s3_bound;          // k_heavy: lower-bound short cut in front of the S3 volume (decisions identical)
   int norm_planes;       // k_heavy: S3/S4 volumes on pre-normalised planes (face_cone_volume_n; bit-identical, see geom3d.cuh)
+  int dup_dirs;          // the ray set has coincident directions (Rays_Cartesian poles): polyhedra can have duplicate vertices
   Grid3 G;
 };
 
@@ -329,8 +330,12 @@ __device__ int warp_pivot(const double* pts, int n, int a, int b, int skip) {
 }
 
 // hull facet planes by warp 0 (other warps idle); identical facet set to sd3::convex_hull_planes up to order
-__device__ int hull_planes_warp(const double* pts, int n, Plane* out, int max_planes, uint32_t* edge_done, int16_t* stack, int max_stack) {
+__device__ int hull_planes_warp(double* pts, int n, Plane* out, int max_planes, uint32_t* edge_done, int16_t* stack, int max_stack, int dedup) {
   const int lane = threadIdx.x & 31;
+  if (dedup) {      // warp-uniform; only for ray sets with coincident directions: repeated points go to the centroid (geom3d.cuh)
+    if (lane == 0) sd3::demote_duplicate_points(pts, n);
+    __syncwarp();
+  }
   for (int i = lane; i < (n * n + 31) / 32; i += 32) edge_done[i] = 0;
   __syncwarp();
   // start edge (serial scan by every lane redundantly: cheap, n <= 256)
@@ -520,7 +525,7 @@ __global__ void __launch_bounds__(128) k_hulls(Arr A, HeavyCtx X, const unsigned
       pts[3 * j + 2] = (double)(c2 + d[j] * A.verts[3 * j + 2]);
     }
     __syncwarp();
-    const int nf = hull_planes_warp(pts, A.R, X.hull_planes + (size_t)u * A.F, A.F, edge_done, stack, 4 * A.R);
+    const int nf = hull_planes_warp(pts, A.R, X.hull_planes + (size_t)u * A.F, A.F, edge_done, stack, 4 * A.R, A.dup_dirs);
     if (lane == 0) X.hull_n[u] = nf;
     __syncwarp();
   }
@@ -820,13 +825,13 @@ k_heavy(Arr A, const int2* __restrict__ pairs, unsigned int* __restrict__ counte
       } else {
       for (int k = threadIdx.x; k < 3 * A.R; k += blockDim.x) pts[k] = (double)pv1[k];
       __syncthreads();
-      if (threadIdx.x < 32) { n1 = hull_planes_warp(pts, A.R, planes, A.F, edge_done, stack, 4 * A.R); if (threadIdx.x == 0) sh_i[0] = n1; }
+      if (threadIdx.x < 32) { n1 = hull_planes_warp(pts, A.R, planes, A.F, edge_done, stack, 4 * A.R, A.dup_dirs); if (threadIdx.x == 0) sh_i[0] = n1; }
       __syncthreads();
       n1 = sh_i[0];
       if (n1 >= 4) {
         for (int k = threadIdx.x; k < 3 * A.R; k += blockDim.x) pts[k] = (double)pv2[k];
         __syncthreads();
-        if (threadIdx.x < 32) { n2 = hull_planes_warp(pts, A.R, planes + n1, A.F, edge_done, stack, 4 * A.R); if (threadIdx.x == 0) sh_i[1] = n2; }
+        if (threadIdx.x < 32) { n2 = hull_planes_warp(pts, A.R, planes + n1, A.F, edge_done, stack, 4 * A.R, A.dup_dirs); if (threadIdx.x == 0) sh_i[1] = n2; }
         __syncthreads();
         n2 = sh_i[1];
       }
@@ -1010,18 +1015,21 @@ extern "C" int sdb_nms3d(const float* d_dist, const float* d_points, const float
   A.dist = d_dist; A.points = d_points; A.verts = d_verts; A.faces = d_faces; A.n = n; A.R = n_rays; A.F = n_faces;
   A.volume = b_vol.as<float>(); A.bbox = b_bbox.as<int>(); A.r_outer = b_ro.as<float>(); A.r_outer_iso = b_roi.as<float>();
   A.r_inner_iso = b_rii.as<float>(); A.aniso_terms = b_terms.as<float>(); A.aniso = b_aniso.as<float>();
-  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox; A.norm_planes = g_nms3d_norm_planes; A.s3_bound = g_nms3d_s3_bound; A.fan_subdiv = g_nms3d_fan_subdiv;
+  A.state = b_state.as<int>(); A.threshold = threshold; A.use_bbox = use_bbox; A.norm_planes = g_nms3d_norm_planes; A.s3_bound = g_nms3d_s3_bound; A.fan_subdiv = g_nms3d_fan_subdiv; A.dup_dirs = 0;
   A.cell_start = nullptr; A.items = nullptr; A.max_dist = 0; memset(&A.G, 0, sizeof(A.G));
   SDB_LAUNCH(k_pre1, cdiv(n, 128), 128, 0, st, A, b_stats.as<unsigned int>());
   SDB_LAUNCH(k_aniso, 3, 256, 0, st, A);
   SDB_LAUNCH(k_aniso_norm, 1, 1, 0, st, A);
   SDB_LAUNCH(k_pre2, cdiv(n, 128), 128, 0, st, A);
   int h_stats[8]; float h_aniso[3];
+  std::vector<float> h_verts((size_t)3 * n_rays);
+  SDB_CUDA(cudaMemcpyAsync(h_verts.data(), d_verts, h_verts.size() * 4, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaMemcpyAsync(h_stats, b_stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaMemcpyAsync(h_aniso, b_aniso.p, 12, cudaMemcpyDeviceToHost, st));
   SDB_CUDA(cudaStreamSynchronize(st));
   float max_dist; { unsigned int u = (unsigned int)h_stats[0]; memcpy(&max_dist, &u, 4); }
   A.max_dist = max_dist;
+  A.dup_dirs = sd3::rays_have_coincident_directions(h_verts.data(), n_rays) ? 1 : 0;
   Grid3 G; G.all_pairs = use_kdtree ? 0 : 1;
   {
     double cell = 2.0 * (double)max_dist * (1.0 + 1e-5) + 1e-3;

@@ -62,9 +62,11 @@ SD3_HD inline float overlap_convex_volume(const float* pv1, const float* c1, con
   uint32_t edge_done[(SD3_MAX_RAYS * SD3_MAX_RAYS + 31) / 32];
   int16_t stack[3 * 4 * SD3_MAX_RAYS];
   for (int i = 0; i < 3 * n_rays; ++i) pts[i] = (double)pv1[i];
+  demote_duplicate_points(pts, n_rays);
   const int n1 = convex_hull_planes(pts, n_rays, planes, SD3_MAX_FACES, edge_done, stack, 4 * SD3_MAX_RAYS);
   if (n1 < 4) return 1.e10f;
   for (int i = 0; i < 3 * n_rays; ++i) pts[i] = (double)pv2[i];
+  demote_duplicate_points(pts, n_rays);
   const int n2 = convex_hull_planes(pts, n_rays, planes + n1, SD3_MAX_FACES, edge_done, stack, 4 * SD3_MAX_RAYS);
   if (n2 < 4) return 1.e10f;
   double p[3];
@@ -109,9 +111,11 @@ SD3_HD inline float overlap_convex_volume_n(const float* pv1, const float* c1, c
   uint32_t edge_done[(SD3_MAX_RAYS * SD3_MAX_RAYS + 31) / 32];
   int16_t stack[3 * 4 * SD3_MAX_RAYS];
   for (int i = 0; i < 3 * n_rays; ++i) pts[i] = (double)pv1[i];
+  demote_duplicate_points(pts, n_rays);
   const int n1 = convex_hull_planes(pts, n_rays, planes, SD3_MAX_FACES, edge_done, stack, 4 * SD3_MAX_RAYS);
   if (n1 < 4) return 1.e10f;
   for (int i = 0; i < 3 * n_rays; ++i) pts[i] = (double)pv2[i];
+  demote_duplicate_points(pts, n_rays);
   const int n2 = convex_hull_planes(pts, n_rays, planes + n1, SD3_MAX_FACES, edge_done, stack, 4 * SD3_MAX_RAYS);
   if (n2 < 4) return 1.e10f;
   double p[3];

@@ -691,9 +691,12 @@ def test_direction_bins_list_every_face_that_can_contain_the_direction():
     n_bins = hc.hc_bin_count()
     rng = np.random.default_rng(1)
     sizes = []
-    for n_rays, aniso in ((96, (2, 1, 1)), (32, None), (64, (1, 1.5, 3)), (187, None), (16, None), (8, (4, 1, 1))):
-        rays = cases.rays_golden_spiral(n_rays, aniso)
+    from stardist_b200 import rays3d as R3
+    ray_sets = [(n, a, cases.rays_golden_spiral(n, a)) for n, a in ((96, (2, 1, 1)), (32, None), (64, (1, 1.5, 3)), (187, None), (16, None), (8, (4, 1, 1)))]
+    ray_sets += [(0, "cartesian", R3.Rays_Cartesian(8, 5)), (0, "cartesian11", R3.Rays_Cartesian(11, 5)), (0, "octo", R3.Rays_Octo(3))]
+    for n_rays, aniso, rays in ray_sets:
         v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32)
+        n_rays = len(v)
         takes = np.array([[hc.hc_bin_takes_face(b, v.ctypes.data, f.ctypes.data, j) for j in range(len(f))] for b in range(n_bins)], bool)
         sizes.append(takes.sum(1).max())
         u = rng.normal(size=(20000, 3))
@@ -708,11 +711,18 @@ def test_direction_bins_list_every_face_that_can_contain_the_direction():
         A, B, C = (vd[f[:, i]] for i in range(3))                     # [F,3]
         det = np.einsum("fi,fi->f", A, np.cross(B, C))
         ud = u.astype(np.float64)
-        al = np.einsum("ni,fi->nf", ud, np.cross(B, C)) / det
-        be = np.einsum("ni,fi->nf", ud, np.cross(C, A)) / det
-        ga = np.einsum("ni,fi->nf", ud, np.cross(A, B)) / det
+        with np.errstate(divide="ignore", invalid="ignore"):
+            al = np.einsum("ni,fi->nf", ud, np.cross(B, C)) / det
+            be = np.einsum("ni,fi->nf", ud, np.cross(C, A)) / det
+            ga = np.einsum("ni,fi->nf", ud, np.cross(A, B)) / det
         s = np.abs(al) + np.abs(be) + np.abs(ga)
-        in_cone = (np.minimum(np.minimum(al, be), ga) >= -1e-3 * s) & (np.abs(det) > 0)[None]
+        un = vd / np.linalg.norm(vd, axis=1, keepdims=True)
+        flat = np.abs(np.einsum("fi,fi->f", un[f[:, 0]], np.cross(un[f[:, 1]], un[f[:, 2]]))) < 1e-7      # degenerate face (Cartesian poles)
+        # a degenerate face's tetrahedron "contains" a whole plane through the centre (all determinants vanish there and the
+        # reference tests det >= 0): it must be in EVERY bin
+        assert takes[:, flat].all()
+        with np.errstate(divide="ignore", invalid="ignore"):
+            in_cone = (np.minimum(np.minimum(al, be), ga) >= -1e-3 * s) & ~flat[None]
         listed = takes[bins]                                          # [n,F]
         missing = in_cone & ~listed
         assert not missing.any(), (n_rays, aniso, np.argwhere(missing)[:5])
@@ -883,11 +893,11 @@ def test_frontier_peeling_model_equals_the_greedy_loop():
 
 def test_serial_nms3d_other_ray_classes_equal_reference():
     """the 3-D NMS arithmetic (host build of the device headers, hc_nms3d_serial) against the reference extension for the ray
-    classes beyond Rays_GoldenSpiral: Rays_Cartesian (pole rings = groups of coincident directions -> collinear vertices),
-    Rays_Octo, Rays_Tetra -- same keep mask.  Runs in a subprocess with OMP_NUM_THREADS=1 (the reference's anisotropy sum races).
-    Known deviation, pinned here so that it stays visible: when the distances on coincident rays are EQUAL the polyhedron has
-    duplicate vertices, the gift wrapping gives up (hull volume sentinel 1e10, like a Qhull error in the reference) and stage S4
-    never short-cuts -- S5 decides every such pair, which can differ from the reference's S4 'keep' (DESIGN.md §5)."""
+    classes beyond Rays_GoldenSpiral: Rays_Cartesian (pole rings = groups of coincident directions, zero-area pole faces),
+    Rays_Octo, Rays_Tetra -- same keep mask, incl. the constant-distance clouds where the coincident rays give DUPLICATE
+    vertices (Qhull ignores them; the gift wrapping needs demote_duplicate_points, geom3d.cuh -- before that fix S4 never
+    short-cut for such polyhedra and 50 of 600 decisions differed).  Subprocess with OMP_NUM_THREADS=1 (the reference's
+    anisotropy sum races)."""
     code = r'''
 import ctypes, json, os, sys, numpy as np
 ROOT = sys.argv[1]
@@ -920,8 +930,6 @@ print("RESULT " + json.dumps(out))
     res = json.loads(lines[-1][7:])
     assert len(res) == 12
     for e in res:
-        degenerate = e["rays"] == "cartesian" and e["noise"] == 0.0
-        if not degenerate:
-            assert e["mismatches"] == 0, e
-        else:
-            assert e["s4"] == e["s5"], e             # the documented deviation: no pair is decided by S4, all reach S5
+        assert e["mismatches"] == 0, e
+    cart0 = [e for e in res if e["rays"] == "cartesian" and e["noise"] == 0.0][0]
+    assert cart0["s5"] < cart0["s4"], cart0          # duplicate vertices: S4 decides pairs again instead of passing all to S5

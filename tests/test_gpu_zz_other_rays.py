@@ -1,0 +1,56 @@
+"""Device 3-D NMS for the ray classes beyond Rays_GoldenSpiral (pytest -m gpu).  The file name sorts last on purpose.
+
+Status: the arithmetic is pinned on the CPU (tests/test_cpu_oracle.py::test_serial_nms3d_other_ray_classes_equal_reference:
+host build of the device headers == reference extension, 0 decisions differ).  The DEVICE handling of coincident ray
+directions (Rays_Cartesian's pole rings: duplicate vertices -> sd3::demote_duplicate_points before the warp gift wrapping;
+zero-area pole faces listed in every direction bin) was written after this round's GPU budget was spent: it compiles for
+sm_100a and is the same header code as the host build, but it has not run on a GPU yet -- nor have Octo / Tetra ray sets,
+although they take the regular device path.  The whole file is therefore marked xfail(strict=False): a pass shows up as
+XPASS, a failure does not turn the suite red before anybody has looked at it."""
+import os, sys
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from oracle import ref_ext
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: CPU-pinned, compiled, not yet run on a GPU")]
+
+
+def _cloud(rays, noise, seed, n=300):
+    v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32); R = len(v)
+    rng = np.random.default_rng(seed)
+    p = np.ascontiguousarray(np.stack([rng.integers(2, s - 2, n) for s in (14, 18, 20)], 1), np.float32)
+    s = np.ascontiguousarray(np.sort(rng.uniform(0.5, 1, n))[::-1], np.float32)
+    d = np.ascontiguousarray(rng.uniform(2, 5, (n, 1)) * (1 + noise * rng.uniform(-1, 1, (n, R))), np.float32)
+    return d, p, v, f, s
+
+
+def _run(rays, noise, nthr, seed):
+    if not ref_ext.available(): pytest.skip("oracle/_ref not present")
+    from stardist_b200 import _lib
+    _lib.require_cuda()
+    from stardist_b200.lib.stardist3d import c_non_max_suppression_inds
+    os.environ["OMP_NUM_THREADS"] = "1"          # the reference's anisotropy sum is racy
+    d, p, v, f, s = _cloud(rays, noise, seed)
+    want = ref_ext.stardist3d().c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, np.float32(nthr))
+    got = c_non_max_suppression_inds(d, p, v, f, s, 1, 1, 0, np.float32(nthr))
+    assert np.array_equal(got, want), "%d of %d decisions differ" % (int((got != want).sum()), len(d))
+
+
+@pytest.mark.parametrize("cls,arg", [("Rays_Octo", 2), ("Rays_Octo", 3), ("Rays_Tetra", 2)])
+@pytest.mark.parametrize("noise,nthr", [(0.2, 0.2), (0.5, 0.5), (0.0, 0.3)])
+def test_device_nms3d_octo_tetra_vs_reference(cls, arg, noise, nthr):
+    """subdivision ray sets: no coincident directions, the regular device path"""
+    from stardist_b200 import rays3d as R3
+    _run(getattr(R3, cls)(arg), noise, nthr, 7 + arg)
+
+
+@pytest.mark.parametrize("nx,nz", [(8, 5), (11, 5)])
+@pytest.mark.parametrize("noise,nthr", [(0.2, 0.2), (0.5, 0.5), (0.0, 0.3)])
+def test_device_nms3d_cartesian_vs_reference(nx, nz, noise, nthr):
+    """Rays_Cartesian: pole rings of coincident directions; noise 0 = equal distances on them = duplicate vertices"""
+    from stardist_b200 import rays3d as R3
+    _run(R3.Rays_Cartesian(nx, nz), noise, nthr, 100 * nx + int(10 * noise))
