@@ -440,6 +440,22 @@ inline bool rays_have_coincident_directions(const float* verts, int n) {
   return false;
 }
 
+// A face of the ray triangulation whose three directions are coplanar with the centre (|det of the unit directions| < 1e-6;
+// Rays_Cartesian's pole faces, two of whose rays coincide).  Its tetrahedron (centre, A, B, C) is degenerate: all four
+// determinants of inside_tetrahedron vanish on a whole plane through the centre, where `det >= 0` answers true.
+SD3_HD inline bool ray_face_is_degenerate(const float* verts, const int* faces, int f) {
+  double n[3][3];
+  for (int e = 0; e < 3; ++e) {
+    const float* v = verts + 3 * faces[3 * f + e];
+    const double l = sqrt((double)v[0] * v[0] + (double)v[1] * v[1] + (double)v[2] * v[2]);
+    if (!(l > 0)) return true;
+    n[e][0] = v[0] / l; n[e][1] = v[1] / l; n[e][2] = v[2] / l;
+  }
+  const double det = n[0][0] * (n[1][1] * n[2][2] - n[1][2] * n[2][1]) - n[0][1] * (n[1][0] * n[2][2] - n[1][2] * n[2][0]) +
+                     n[0][2] * (n[1][0] * n[2][1] - n[1][1] * n[2][0]);
+  return fabs(det) < 1e-6;
+}
+
 // Convex hull facet planes (outward, unit normal) of n points (double, [n][3]) by gift wrapping.
 // out: up to max_planes planes; returns the number of facets, or -1 on failure (degenerate input).
 // scratch: edge_done bit matrix n*n bits (uint32 words), stack of directed edges (int16 triples).

@@ -242,6 +242,32 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
   const long long nvox = (long long)nz * ny * nx;
   const int fb = (int)std::min<long long>(cdiv(nvox, 256), 148 * 16);
   if (nvox == 0) return 0;
+  // Render mode "full" here is kernel || inside_polyhedron, the reference's is kernel || (hull && inside_polyhedron)
+  // (stardist3d_impl.cpp:1475-1477).  inside_polyhedron lies inside the hull -- except for DEGENERATE faces of the ray
+  // triangulation (Rays_Cartesian's zero-area pole faces): their tetrahedra "contain" whole planes through the centre, which
+  // the reference's hull test cuts back to the hull and which would otherwise be painted across the bounding box.  Such faces
+  // enclose no volume; they are left out of the rendering (the kernel planes they contribute are all-zero and never reject).
+  // What remains different from the reference for such ray sets: voxels exactly on those planes, inside the hull but in no
+  // proper tetrahedron.  Ray sets without degenerate faces (every golden-spiral / subdivision set) take the arrays as given.
+  sdb::DevBuf b_faces_nd;
+  if (render_mode == 0 && n_polys > 0 && n_faces > 0) {
+    std::vector<float> hv((size_t)3 * n_rays); std::vector<int> hf((size_t)3 * n_faces);
+    SDB_CUDA(cudaMemcpyAsync(hv.data(), d_verts, hv.size() * 4, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaMemcpyAsync(hf.data(), d_faces, hf.size() * 4, cudaMemcpyDeviceToHost, st));
+    SDB_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> keep; keep.reserve(hf.size());
+    bool valid = true;
+    for (int f = 0; f < n_faces && valid; ++f)
+      for (int e = 0; e < 3; ++e) if (hf[3 * f + e] < 0 || hf[3 * f + e] >= n_rays) valid = false;
+    for (int f = 0; f < n_faces && valid; ++f)
+      if (!sd3::ray_face_is_degenerate(hv.data(), hf.data(), f)) { keep.push_back(hf[3 * f]); keep.push_back(hf[3 * f + 1]); keep.push_back(hf[3 * f + 2]); }
+    if (valid && (int)keep.size() < 3 * n_faces && !keep.empty()) {
+      SDB_CUDA(b_faces_nd.alloc(keep.size() * 4, st));
+      SDB_CUDA(cudaMemcpyAsync(b_faces_nd.p, keep.data(), keep.size() * 4, cudaMemcpyHostToDevice, st));
+      SDB_CUDA(cudaStreamSynchronize(st));          // `keep` leaves scope below
+      d_faces = b_faces_nd.as<int>(); n_faces = (int)keep.size() / 3;
+    }
+  }
   // labels == 0 ("paints nothing, and is painted over") and overlap_label == 0 make the reference's in-place rule order
   // dependent beyond "first cover wins": detect them (one 4-byte read-back) and run the polyhedra one launch at a time
   bool sequential = use_overlap_label && overlap_label == 0;

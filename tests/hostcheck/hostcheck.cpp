@@ -347,3 +347,60 @@ extern "C" double hc_planes_volume(const double* planes4, int n, const double* p
   for (int k = 0; k < n; ++k) { const double v = sd3::face_cone_volume(PA, n, k, p, L, overflow); if (parts) parts[k] = v; vol += v; }
   return vol;
 }
+
+// ---------------------------------------------------------------- 3-D label rendering rule (label3d.cu k_paint3d, serial)
+// The DEFINING per-voxel rule of the device rendering, without its result-neutral short cuts (sphere culling, direction bins):
+//   mode 0 "full":   kernel planes  ||  inside_polyhedron          (the reference: kernel || (hull && inside_polyhedron))
+//   mode 1 "kernel": kernel planes;   mode 2 "hull": hull facets (gift wrapping);   mode 3 "bbox": every voxel of the box
+// polyhedra in the given order, first cover wins (all labels non-zero, no overlap label).  out: int32 [nz][ny][nx], zeroed here.
+extern "C" void hc_polyhedron_to_label(const float* dist, const float* points, const float* verts, const int* faces, int n_polys, int n_rays,
+                                       int n_faces, const int* labels, int nz, int ny, int nx, int mode, int* out) {
+  using namespace sd3;
+  for (long long v = 0; v < (long long)nz * ny * nx; ++v) out[v] = 0;
+  // mode 0: degenerate faces of the ray triangulation are left out, as sdb_polyhedron_to_label does on the host side
+  std::vector<int> kept_faces;
+  if (mode == 0) {
+    for (int f = 0; f < n_faces; ++f)
+      if (!ray_face_is_degenerate(verts, faces, f)) { kept_faces.push_back(faces[3 * f]); kept_faces.push_back(faces[3 * f + 1]); kept_faces.push_back(faces[3 * f + 2]); }
+    if ((int)kept_faces.size() < 3 * n_faces && !kept_faces.empty()) { faces = kept_faces.data(); n_faces = (int)kept_faces.size() / 3; }
+  }
+  std::vector<float> pv(3 * (size_t)n_rays);
+  std::vector<double> hs(4 * (size_t)std::max(n_faces, 1)), pts(3 * (size_t)n_rays);
+  std::vector<Plane> hull(n_faces > 4 ? n_faces : 4);
+  std::vector<uint32_t> edge_done(((size_t)n_rays * n_rays + 31) / 32);
+  std::vector<int16_t> stack(3 * 4 * (size_t)n_rays);
+  for (int i = 0; i < n_polys; ++i) {
+    const float* d = dist + (size_t)i * n_rays;
+    const float center[3] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+    int z1 = INT32_MAX, z2 = -1, y1 = INT32_MAX, y2 = -1, x1 = INT32_MAX, x2 = -1;
+    for (int j = 0; j < n_rays; ++j) {
+      pv[3 * j] = center[0] + d[j] * verts[3 * j]; pv[3 * j + 1] = center[1] + d[j] * verts[3 * j + 1]; pv[3 * j + 2] = center[2] + d[j] * verts[3 * j + 2];
+      const int iz = round_to_int(center[0] + d[j] * verts[3 * j]), iy = round_to_int(center[1] + d[j] * verts[3 * j + 1]), ix = round_to_int(center[2] + d[j] * verts[3 * j + 2]);
+      z1 = std::min(z1, iz); z2 = std::max(z2, iz); y1 = std::min(y1, iy); y2 = std::max(y2, iy); x1 = std::min(x1, ix); x2 = std::max(x2, ix);
+    }
+    z1 = std::max(0, z1); z2 = std::min(nz - 1, z2); y1 = std::max(0, y1); y2 = std::min(ny - 1, y2); x1 = std::max(0, x1); x2 = std::min(nx - 1, x2);
+    int n_planes = n_faces;
+    if (mode == 2) {
+      for (int k = 0; k < 3 * n_rays; ++k) pts[k] = (double)pv[k];
+      demote_duplicate_points(pts.data(), n_rays);
+      n_planes = convex_hull_planes(pts.data(), n_rays, hull.data(), n_faces, edge_done.data(), stack.data(), 4 * n_rays);
+      for (int f = 0; f < n_planes; ++f) { hs[4 * f] = hull[f].n0; hs[4 * f + 1] = hull[f].n1; hs[4 * f + 2] = hull[f].n2; hs[4 * f + 3] = hull[f].d; }
+    } else {
+      for (int f = 0; f < n_faces; ++f) build_halfspace(&pv[3 * faces[3 * f]], &pv[3 * faces[3 * f + 1]], &pv[3 * faces[3 * f + 2]], &hs[4 * f]);
+    }
+    for (int z = z1; z <= z2; ++z) for (int y = y1; y <= y2; ++y) for (int x = x1; x <= x2; ++x) {
+      const float fz = (float)z, fy = (float)y, fx = (float)x;
+      auto in_planes = [&](int cnt) {
+        for (int f = 0; f < cnt; ++f) if (hs[4 * f] * fz + hs[4 * f + 1] * fy + hs[4 * f + 2] * fx + hs[4 * f + 3] > 0) return false;
+        return true;
+      };
+      bool inside;
+      if (mode == 0) inside = in_planes(n_faces) || inside_polyhedron(fz, fy, fx, center, pv.data(), faces, n_faces);
+      else if (mode == 1) inside = in_planes(n_faces);
+      else if (mode == 2) inside = n_planes >= 4 && in_planes(n_planes);
+      else inside = true;
+      int& o = out[((size_t)z * ny + y) * nx + x];
+      if (inside && o == 0) o = labels[i];
+    }
+  }
+}
