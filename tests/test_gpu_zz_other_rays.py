@@ -54,3 +54,23 @@ def test_device_nms3d_cartesian_vs_reference(nx, nz, noise, nthr):
     """Rays_Cartesian: pole rings of coincident directions; noise 0 = equal distances on them = duplicate vertices"""
     from stardist_b200 import rays3d as R3
     _run(R3.Rays_Cartesian(nx, nz), noise, nthr, 100 * nx + int(10 * noise))
+
+
+@pytest.mark.parametrize("cls,args", [("Rays_Cartesian", (8, 5)), ("Rays_Octo", (3,)), ("Rays_Tetra", (2,))])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_device_rendering_other_ray_classes_vs_reference(cls, args, mode):
+    """centres off the lattice: the device label volume equals the reference's in every render mode (on the CPU the serial
+    host build of the rule does: test_rendering_rule_vs_reference_all_modes_and_ray_classes)"""
+    if not ref_ext.available(): pytest.skip("oracle/_ref not present")
+    from stardist_b200 import _lib, rays3d as R3
+    _lib.require_cuda()
+    from stardist_b200.lib.stardist3d import c_polyhedron_to_label
+    rays = getattr(R3, cls)(*args)
+    v = np.ascontiguousarray(rays.vertices, np.float32); f = np.ascontiguousarray(rays.faces, np.int32); R = len(v)
+    rng = np.random.default_rng(5); n = 16; shape = (32, 40, 44)
+    p = np.ascontiguousarray(np.stack([rng.uniform(6, s - 6, n) for s in shape], 1), np.float32)
+    d = np.ascontiguousarray(rng.uniform(3, 7, (n, 1)) * (1 + 0.3 * rng.uniform(-1, 1, (n, R))), np.float32)
+    labels = np.arange(1, n + 1, dtype=np.int32)
+    want = ref_ext.stardist3d().c_polyhedron_to_label(d, p, v, f, labels, mode, 0, 0, 0, shape)
+    got = c_polyhedron_to_label(d, p, v, f, labels, mode, 0, 0, 0, shape)
+    assert np.array_equal(got, want), "%d voxels differ" % int((got != want).sum())
