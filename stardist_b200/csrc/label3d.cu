@@ -38,6 +38,7 @@ struct PaintArgs {
   // sequential variant (labels == 0 among the inputs, or overlap_label == 0): one launch per polyhedron, the reference's
   // update rule applied in place (stardist3d_impl.cpp:1508-1517)
   int poly0; int* direct; const int* labels; int use_overlap, overlap_label;
+  int hull_conj;      // mode 0 only: apply the reference's hull conjunct (ray sets with degenerate faces, see sdb_polyhedron_to_label)
 };
 
 // render_mode 2 only: hull facet planes per polyhedron (one thread each; gift wrapping is serial)
@@ -96,6 +97,10 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
   } else {
     for (int f = threadIdx.x; f < A.n_faces; f += blockDim.x)
       sd3::build_halfspace(&pv[3 * sfaces[3 * f]], &pv[3 * sfaces[3 * f + 1]], &pv[3 * sfaces[3 * f + 2]], &hs[4 * f]);
+    if (A.mode == 0 && A.hull_conj) {      // hull facets behind the kernel planes (the launch reserved the room)
+      if (threadIdx.x == 0) n_hull = hull_count[i];
+      for (int f = threadIdx.x; f < 4 * A.n_faces; f += blockDim.x) hs[4 * A.n_faces + f] = hull_planes[(size_t)i * 4 * A.n_faces + f];
+    }
   }
   __syncthreads();
   // Sphere culling of the bounding box (render modes "full" / "kernel"), exactness preserving by margin:
@@ -173,6 +178,16 @@ k_paint3d(PaintArgs A, int* __restrict__ rank_img, int* __restrict__ second_img,
         }
       }
     }
+    else if (A.mode == 0 && A.hull_conj) {
+      // kernel || (hull && polyhedron), the reference's rule in full (stardist3d_impl.cpp:1475-1477)
+      inside = in_planes(A.n_faces);
+      if (!inside && n_hull >= 4 && sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces)) {
+        const double* hh = hs + 4 * A.n_faces;
+        bool in_hull = true;
+        for (int f = 0; f < n_hull && in_hull; ++f) in_hull = !(hh[4 * f] * fz + hh[4 * f + 1] * fy + hh[4 * f + 2] * fx + hh[4 * f + 3] > 0);
+        inside = in_hull;
+      }
+    }
     else if (A.mode == 0) inside = in_planes(A.n_faces) || sd3::inside_polyhedron(fz, fy, fx, center, pv, sfaces, A.n_faces);
     else if (A.mode == 1) inside = in_planes(A.n_faces);
     else if (A.mode == 2) inside = (n_hull >= 4) && in_planes(n_hull);
@@ -245,28 +260,18 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
   // Render mode "full" here is kernel || inside_polyhedron, the reference's is kernel || (hull && inside_polyhedron)
   // (stardist3d_impl.cpp:1475-1477).  inside_polyhedron lies inside the hull -- except for DEGENERATE faces of the ray
   // triangulation (Rays_Cartesian's zero-area pole faces): their tetrahedra "contain" whole planes through the centre, which
-  // the reference's hull test cuts back to the hull and which would otherwise be painted across the bounding box.  Such faces
-  // enclose no volume; they are left out of the rendering (the kernel planes they contribute are all-zero and never reject).
-  // What remains different from the reference for such ray sets: voxels exactly on those planes, inside the hull but in no
-  // proper tetrahedron.  Ray sets without degenerate faces (every golden-spiral / subdivision set) take the arrays as given.
-  sdb::DevBuf b_faces_nd;
+  // the reference's hull test cuts back to the hull and which would otherwise be painted across the bounding box.  For a ray
+  // set with such faces the hull conjunct is applied with the gift-wrapping facets (k_hull3d); the direction bins are not
+  // used.  Ray sets without degenerate faces (every golden-spiral / subdivision set) are rendered as before.
+  bool hull_conj = false;
   if (render_mode == 0 && n_polys > 0 && n_faces > 0) {
     std::vector<float> hv((size_t)3 * n_rays); std::vector<int> hf((size_t)3 * n_faces);
     SDB_CUDA(cudaMemcpyAsync(hv.data(), d_verts, hv.size() * 4, cudaMemcpyDeviceToHost, st));
     SDB_CUDA(cudaMemcpyAsync(hf.data(), d_faces, hf.size() * 4, cudaMemcpyDeviceToHost, st));
     SDB_CUDA(cudaStreamSynchronize(st));
-    std::vector<int> keep; keep.reserve(hf.size());
     bool valid = true;
-    for (int f = 0; f < n_faces && valid; ++f)
-      for (int e = 0; e < 3; ++e) if (hf[3 * f + e] < 0 || hf[3 * f + e] >= n_rays) valid = false;
-    for (int f = 0; f < n_faces && valid; ++f)
-      if (!sd3::ray_face_is_degenerate(hv.data(), hf.data(), f)) { keep.push_back(hf[3 * f]); keep.push_back(hf[3 * f + 1]); keep.push_back(hf[3 * f + 2]); }
-    if (valid && (int)keep.size() < 3 * n_faces && !keep.empty()) {
-      SDB_CUDA(b_faces_nd.alloc(keep.size() * 4, st));
-      SDB_CUDA(cudaMemcpyAsync(b_faces_nd.p, keep.data(), keep.size() * 4, cudaMemcpyHostToDevice, st));
-      SDB_CUDA(cudaStreamSynchronize(st));          // `keep` leaves scope below
-      d_faces = b_faces_nd.as<int>(); n_faces = (int)keep.size() / 3;
-    }
+    for (size_t k = 0; k < hf.size() && valid; ++k) valid = hf[k] >= 0 && hf[k] < n_rays;
+    for (int f = 0; f < n_faces && valid && !hull_conj; ++f) hull_conj = sd3::ray_face_is_degenerate(hv.data(), hf.data(), f);
   }
   // labels == 0 ("paints nothing, and is painted over") and overlap_label == 0 make the reference's in-place rule order
   // dependent beyond "first cover wins": detect them (one 4-byte read-back) and run the polyhedra one launch at a time
@@ -283,10 +288,10 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
   }
   if (sequential && render_mode != 4) {
     SDB_CUDA(cudaMemsetAsync(d_result, 0, (size_t)nvox * sizeof(int), st));
-    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode, 0, d_result, d_labels, use_overlap_label, overlap_label};
-    const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double);
+    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode, 0, d_result, d_labels, use_overlap_label, overlap_label, hull_conj ? 1 : 0};
+    const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double) * (hull_conj ? 2 : 1);
     sdb::DevBuf b_hull, b_hcnt;
-    if (render_mode == 2) {
+    if (render_mode == 2 || hull_conj) {
       SDB_CUDA(b_hull.alloc((size_t)n_polys * n_faces * 4 * sizeof(double), st));
       SDB_CUDA(b_hcnt.alloc((size_t)n_polys * sizeof(int), st));
       SDB_LAUNCH(k_hull3d, cdiv(n_polys, 32), 32, 0, st, A, b_hull.as<double>(), b_hcnt.as<int>());
@@ -309,10 +314,10 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
     SDB_CUDA(cudaMemsetAsync(b_debug.p, 0, (size_t)nvox * sizeof(int), st));
   }
   if (n_polys > 0) {
-    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode, 0, nullptr, d_labels, use_overlap_label, overlap_label};
-    const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double);
+    PaintArgs A{d_dist, d_points, d_verts, d_faces, n_polys, n_rays, n_faces, nz, ny, nx, render_mode, 0, nullptr, d_labels, use_overlap_label, overlap_label, hull_conj ? 1 : 0};
+    const size_t smem = ((3 * n_rays * 4 + 3 * n_faces * 4 + 15) / 16) * 16 + (size_t)n_faces * 4 * sizeof(double) * (hull_conj ? 2 : 1);
     sdb::DevBuf b_hull, b_hcnt;
-    if (render_mode == 2) {
+    if (render_mode == 2 || hull_conj) {
       SDB_CUDA(b_hull.alloc((size_t)n_polys * n_faces * 4 * sizeof(double), st));
       SDB_CUDA(b_hcnt.alloc((size_t)n_polys * sizeof(int), st));
       SDB_LAUNCH(k_hull3d, cdiv(n_polys, 32), 32, 0, st, A, b_hull.as<double>(), b_hcnt.as<int>());
@@ -321,7 +326,7 @@ extern "C" int sdb_polyhedron_to_label(const float* d_dist, const float* d_point
     sdb::profile_begin("nms3d_paint", st, &sp);
     sdb::DevBuf b_bcnt, b_bfaces;
     FaceBins FB{nullptr, nullptr};
-    if (render_mode == 0) {
+    if (render_mode == 0 && !hull_conj) {
       SDB_CUDA(b_bcnt.alloc(BIN_N * sizeof(int), st)); SDB_CUDA(b_bfaces.alloc((size_t)BIN_N * BIN_CAP * sizeof(int), st));
       FB.count = b_bcnt.as<int>(); FB.faces = b_bfaces.as<int>();
       SDB_LAUNCH(k_build_bins, BIN_N, 128, 0, st, d_verts, d_faces, n_faces, FB);

@@ -357,13 +357,10 @@ extern "C" void hc_polyhedron_to_label(const float* dist, const float* points, c
                                        int n_faces, const int* labels, int nz, int ny, int nx, int mode, int* out) {
   using namespace sd3;
   for (long long v = 0; v < (long long)nz * ny * nx; ++v) out[v] = 0;
-  // mode 0: degenerate faces of the ray triangulation are left out, as sdb_polyhedron_to_label does on the host side
-  std::vector<int> kept_faces;
-  if (mode == 0) {
-    for (int f = 0; f < n_faces; ++f)
-      if (!ray_face_is_degenerate(verts, faces, f)) { kept_faces.push_back(faces[3 * f]); kept_faces.push_back(faces[3 * f + 1]); kept_faces.push_back(faces[3 * f + 2]); }
-    if ((int)kept_faces.size() < 3 * n_faces && !kept_faces.empty()) { faces = kept_faces.data(); n_faces = (int)kept_faces.size() / 3; }
-  }
+  // mode 0 for a ray set with degenerate faces: the reference's hull conjunct is applied (sdb_polyhedron_to_label does the same)
+  bool hull_conj = false;
+  if (mode == 0) for (int f = 0; f < n_faces; ++f) hull_conj = hull_conj || ray_face_is_degenerate(verts, faces, f);
+  std::vector<double> hh(4 * (size_t)std::max(n_faces, 4));
   std::vector<float> pv(3 * (size_t)n_rays);
   std::vector<double> hs(4 * (size_t)std::max(n_faces, 1)), pts(3 * (size_t)n_rays);
   std::vector<Plane> hull(n_faces > 4 ? n_faces : 4);
@@ -379,7 +376,13 @@ extern "C" void hc_polyhedron_to_label(const float* dist, const float* points, c
       z1 = std::min(z1, iz); z2 = std::max(z2, iz); y1 = std::min(y1, iy); y2 = std::max(y2, iy); x1 = std::min(x1, ix); x2 = std::max(x2, ix);
     }
     z1 = std::max(0, z1); z2 = std::min(nz - 1, z2); y1 = std::max(0, y1); y2 = std::min(ny - 1, y2); x1 = std::max(0, x1); x2 = std::min(nx - 1, x2);
-    int n_planes = n_faces;
+    int n_planes = n_faces, n_hull = 0;
+    if (mode == 0 && hull_conj) {
+      for (int k = 0; k < 3 * n_rays; ++k) pts[k] = (double)pv[k];
+      demote_duplicate_points(pts.data(), n_rays);
+      n_hull = convex_hull_planes(pts.data(), n_rays, hull.data(), n_faces, edge_done.data(), stack.data(), 4 * n_rays);
+      for (int f = 0; f < n_hull; ++f) { hh[4 * f] = hull[f].n0; hh[4 * f + 1] = hull[f].n1; hh[4 * f + 2] = hull[f].n2; hh[4 * f + 3] = hull[f].d; }
+    }
     if (mode == 2) {
       for (int k = 0; k < 3 * n_rays; ++k) pts[k] = (double)pv[k];
       demote_duplicate_points(pts.data(), n_rays);
@@ -395,7 +398,13 @@ extern "C" void hc_polyhedron_to_label(const float* dist, const float* points, c
         return true;
       };
       bool inside;
-      if (mode == 0) inside = in_planes(n_faces) || inside_polyhedron(fz, fy, fx, center, pv.data(), faces, n_faces);
+      auto in_hull = [&]() {
+        if (n_hull < 4) return false;
+        for (int f = 0; f < n_hull; ++f) if (hh[4 * f] * fz + hh[4 * f + 1] * fy + hh[4 * f + 2] * fx + hh[4 * f + 3] > 0) return false;
+        return true;
+      };
+      if (mode == 0 && hull_conj) inside = in_planes(n_faces) || (in_hull() && inside_polyhedron(fz, fy, fx, center, pv.data(), faces, n_faces));
+      else if (mode == 0) inside = in_planes(n_faces) || inside_polyhedron(fz, fy, fx, center, pv.data(), faces, n_faces);
       else if (mode == 1) inside = in_planes(n_faces);
       else if (mode == 2) inside = n_planes >= 4 && in_planes(n_planes);
       else inside = true;
