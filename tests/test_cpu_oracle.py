@@ -987,3 +987,88 @@ def test_rendering_rule_vs_reference_all_modes_and_ray_classes():
             assert d_ker == 0 and d_box == 0, (name, noise, r)
             assert d_hull <= 0.002 * n_hull + 2, (name, noise, r)
             assert d_full <= 0.002 * n_full + 2, (name, noise, r)
+
+
+def test_warp_gift_wrapping_model_with_demoted_duplicates():
+    """lane-by-lane model of the device hull routine (nms3d.cu hull_planes_warp / warp_pivot: lane-strided scan, xor-shuffle
+    tournament with a deterministic comparison, edge bookkeeping, guard) on point sets as the device sees them for
+    Rays_Cartesian -- duplicate vertices moved to the centroid by demote_duplicate_points, several copies of that interior
+    point included, or collinear pole points -- against scipy's hull of the distinct points: same volume, no give-up.
+    (The serial routine of geom3d.cuh is compared with the reference directly; this covers the warp formulation, which exists
+    only as device code.)"""
+    from scipy.spatial import ConvexHull
+    from stardist_b200 import rays3d as R3
+
+    def orient(P,a,b,c,d):
+        B=P[b]-P[a]; C=P[c]-P[a]; D=P[d]-P[a]
+        return D[0]*(B[1]*C[2]-B[2]*C[1]) + D[1]*(B[2]*C[0]-B[0]*C[2]) + D[2]*(B[0]*C[1]-B[1]*C[0])
+    def warp_pivot(P,n,a,b,skip):
+        q=[-1]*32
+        for lane in range(32):
+            for r in range(lane,n,32):
+                if r==a or r==b or r==skip: continue
+                if q[lane]<0: q[lane]=r; continue
+                if orient(P,a,b,q[lane],r)>0: q[lane]=r
+        o=16
+        while o>0:
+            nq=list(q)
+            for lane in range(32):
+                other=q[lane^o]; best=q[lane]
+                if q[lane]<0: best=other
+                elif other>=0 and other!=q[lane]:
+                    lo,hi=min(q[lane],other),max(q[lane],other)
+                    best = hi if orient(P,a,b,lo,hi)>0 else lo
+                nq[lane]=best
+            q=nq; o>>=1
+        assert len(set(q))==1
+        return q[0]
+    def demote(P):
+        P=P.copy(); c=P.mean(0); n=len(P)   # (device sums sequentially; value differences irrelevant here)
+        for i in range(n-1,0,-1):
+            if any((P[j]==P[i]).all() for j in range(i)): P[i]=c
+        return P
+    def hull_warp(P):
+        n=len(P)
+        p0=0
+        for i in range(1,n):
+            if tuple(P[i])<tuple(P[p0]): p0=i
+        p1=-1
+        for i in range(n):
+            if i==p0: continue
+            if p1<0: p1=i; continue
+            ax,ay=P[p1][0]-P[p0][0],P[p1][1]-P[p0][1]; bx,by=P[i][0]-P[p0][0],P[i][1]-P[p0][1]
+            cr=ax*by-ay*bx
+            if cr<0 or (cr==0 and bx*bx+by*by>ax*ax+ay*ay): p1=i
+        p2=warp_pivot(P,n,p0,p1,-1)
+        done=set(); facets=[]; stack=[]
+        def emit(a,b,c):
+            facets.append((a,b,c)); done.update([(a,b),(b,c),(c,a)])
+        emit(p0,p1,p2); stack+= [(p1,p0,p2),(p2,p1,p0),(p0,p2,p1)]
+        guard=0
+        while stack:
+            guard+=1
+            if guard>16*n+64: return None
+            a,b,opp=stack.pop()
+            if (a,b) in done: continue
+            q=warp_pivot(P,n,a,b,opp)
+            if q<0: return None
+            emit(a,b,q)
+            if (q,b) not in done: stack.append((q,b,a))
+            if (a,q) not in done: stack.append((a,q,b))
+        return facets
+
+    rng = np.random.default_rng(0)
+    for rays in (R3.Rays_Cartesian(8, 5), R3.Rays_Cartesian(11, 5)):
+        v = rays.vertices.astype(np.float32)
+        for it in range(6):
+            c = rng.integers(5, 40, 3).astype(np.float32)
+            d = (rng.uniform(2, 6) * (1 + 0.3 * rng.uniform(-1, 1, len(v)))).astype(np.float32)
+            if it % 3 == 0: d[:] = d[0]                      # equal everywhere: duplicates at both poles
+            elif it % 3 == 2: d[:4] = d[0]                   # some duplicates, some collinear points
+            P = (c[None] + d[:, None] * v).astype(np.float32).astype(np.float64)
+            Pd = demote(P)
+            F = hull_warp(Pd)
+            assert F is not None, (len(v), it)
+            want = ConvexHull(np.unique(P, axis=0)).volume
+            vol = abs(sum(np.dot(Pd[a], np.cross(Pd[b], Pd[c_])) for a, b, c_ in F)) / 6
+            assert abs(vol - want) <= 1e-9 * want, (len(v), it, vol, want)
